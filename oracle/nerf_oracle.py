@@ -1,0 +1,434 @@
+"""CPU oracle for the NeRF volume-rendering hot path of JulianKnodt/nerf_atlas.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``nerf_atlas_b200/`` may import this
+module; only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py`` use it, and only as the checker or as
+the CPU arm being timed -- never as the thing that is shipped.
+
+It is a restatement, in plain ``torch`` CPU tensor ops (the reference's own
+arithmetic library; no ``nn.Module`` from the reference is used), of
+
+  * stratified sample generation      reference src/nerf.py:29-55
+  * the hash-grid encoder             reference src/neural_blocks.py:92-193
+  * the Fourier encoder               reference src/neural_blocks.py:36-55, src/utils.py:10-17
+  * SkipConnMLP                       reference src/neural_blocks.py:204-296
+  * the View reflectance head         reference src/refl.py:190-207, src/utils.py:247-254
+  * the sigmoid family                reference src/utils.py:484-518
+  * alpha-from-density + composite    reference src/nerf.py:22-27,60-80
+  * PlainNeRF.forward / from_pts      reference src/nerf.py:326-361
+  * TinyNeRF.forward (intended)       reference src/nerf.py:292-305
+  * VolSDF volume branch              reference src/nerf.py:981-1013, src/utils.py:50-58
+  * DynamicNeRF direct / spline       reference src/nerf.py:1173-1206,1261-1303
+  * sample_pdf (restated, dead code)  reference src/nerf.py:1745-1779
+
+Parity pin: the reference has no tests or golden vectors of its own (SURVEY.md
+section 8c), so this oracle is pinned against the *reference modules themselves*,
+imported in the build container by ``tests/golden/make_golden.py`` (with the
+shim list of ``oracle/ref_shim.py``).  The outputs of that run are committed as
+``tests/golden/*.npz`` and ``tests/test_oracle_golden.py`` checks this file
+against them bit-for-bit on CPU.
+
+Parameters are carried as a flat ``dict[str, Tensor]`` with the reference's own
+``state_dict`` names (``first.init.weight`` ...), so a reference checkpoint's
+``model.state_dict()`` can be fed to the oracle directly.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+Params = Dict[str, Tensor]
+
+# ----------------------------------------------------------------------------
+# hash-grid constants (reference src/neural_blocks.py:92-130)
+# ----------------------------------------------------------------------------
+HASH_PRIMES = (1, 2654435761, 805459861)
+HASH_LEVELS = 8
+HASH_TABLE = 1 << 16
+HASH_FEAT = 4
+HASH_LOW = 1 << 4
+HASH_HIGH = 1 << 14
+# NB operator precedence in the reference: exp((ln hi - ln lo)/levels - 1)
+HASH_SCALE = math.exp((math.log(HASH_HIGH) - math.log(HASH_LOW)) / HASH_LEVELS - 1)
+
+
+def hash_resolutions(levels: int = HASH_LEVELS) -> np.ndarray:
+  """fp32 per-level N_l exactly as ``x * N_l`` sees it (python double -> fp32).
+  reference src/neural_blocks.py:146-147."""
+  return np.array([HASH_LOW * (HASH_SCALE ** i) for i in range(levels)], dtype=np.float64).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------
+# activations
+# ----------------------------------------------------------------------------
+def leaky_relu(x: Tensor) -> Tensor: return F.leaky_relu(x, 0.01)
+
+ACTS: Dict[str, Callable[[Tensor], Tensor]] = {
+  "leaky_relu": leaky_relu,   # nn.LeakyReLU() default slope, neural_blocks.py:214
+  "sin": torch.sin,           # refl.py:203
+  "relu": F.relu,
+  "none": lambda x: x,
+}
+
+# reference src/utils.py:484-518
+def fat_sigmoid(v, eps: float = 1e-2): return v.sigmoid() * (1 + 2 * eps) - eps
+def thin_sigmoid(v, eps: float = 1e-2): return fat_sigmoid(v, -eps) + eps
+def cyclic_sigmoid(v, eps: float = -1e-2, period: int = 5):
+  return ((v / period).sin() + 1) / 2 * (1 + 2 * eps) - eps
+def upshifted_sigmoid(v, eps=1e-2): return v.sigmoid() + eps
+def upshifted_softplus(v, eps=1e-2): return F.softplus(v) + eps
+def upshifted_relu(v, eps=1e-2): return F.relu(v) + eps
+
+SIGMOIDS: Dict[str, Callable[[Tensor], Tensor]] = {
+  "normal": torch.sigmoid,
+  "thin": thin_sigmoid,
+  "tanh": torch.tanh,
+  "cyclic": cyclic_sigmoid,
+  "upshifted": upshifted_sigmoid,
+  "fat": fat_sigmoid,
+  "softmax": lambda v: torch.softmax(v, dim=-1),
+  "leaky_relu": F.leaky_relu,
+  "relu": F.relu,
+  "sin": torch.sin,
+  "upshifted_softplus": upshifted_softplus,
+  "upshifted_relu": upshifted_relu,
+}
+
+
+# ----------------------------------------------------------------------------
+# a-1  sample generation   (reference src/nerf.py:29-55)
+# ----------------------------------------------------------------------------
+def compute_ts(near: float, far: float, steps: int, rand: Optional[Tensor] = None,
+               perturb: float = 1.0, lindisp: bool = False) -> Tensor:
+  """``ts[T]`` shared by every ray.  ``rand`` is the explicit ``rand_like(lower)``
+  draw of nerf.py:45 (None = eval mode, no jitter)."""
+  if lindisp:
+    t_vals = torch.linspace(0, 1, steps, dtype=torch.float32)
+    ts = 1 / (1 / max(near, 1e-10) * (1 - t_vals) + 1 / far * t_vals)
+  else:
+    ts = torch.linspace(near, far, steps=steps, dtype=torch.float32)
+  if rand is not None:
+    mids = 0.5 * (ts[:-1] + ts[1:])
+    lower = torch.cat([mids, ts[-1:]])
+    upper = torch.cat([ts[:1], mids])
+    ts = lower + (upper - lower) * (rand * perturb)
+  return ts
+
+
+def compute_pts(rays: Tensor, ts: Tensor):
+  """``pts[T,...,3] = r_o + ts (x) r_d`` -- a rounded product then a rounded add
+  (nerf.py:54), never an FMA."""
+  r_o, r_d = rays.split([3, 3], dim=-1)
+  pts = r_o.unsqueeze(0) + torch.tensordot(ts, r_d, dims=0)
+  return pts, r_o, r_d
+
+
+# ----------------------------------------------------------------------------
+# a-2  hash-grid encoder   (reference src/neural_blocks.py:139-193)
+# ----------------------------------------------------------------------------
+# corner order of neural_blocks.py:155-165: (bx,by,bz) with z the fastest bit
+HASH_CORNERS = ((0, 0, 0), (0, 0, 1), (0, 1, 0), (0, 1, 1), (1, 0, 0), (1, 0, 1), (1, 1, 0), (1, 1, 1))
+
+
+def hash_indices(x: Tensor, level: int) -> Tensor:
+  """Table row per corner, ``[8, N]`` int64 in [0, 65536).  Same arithmetic as the
+  reference: int64 multiply, xor, python-style ``% emb_size``."""
+  N_l = float(HASH_LOW * (HASH_SCALE ** level))
+  v_l = x * N_l
+  l = v_l.floor().long()
+  primes = torch.tensor(HASH_PRIMES, dtype=torch.int64)
+  out = []
+  for (bx, by, bz) in HASH_CORNERS:
+    c = l + torch.tensor([bx, by, bz], dtype=torch.int64)
+    v = c * primes
+    h = v[..., 0].bitwise_xor(v[..., 1]).bitwise_xor(v[..., 2])
+    out.append(h % HASH_TABLE)
+  return torch.stack(out, dim=0)
+
+
+def hash_indices_u32(x: np.ndarray, level: int) -> np.ndarray:
+  """The uint32 low-16-bit identity the CUDA kernel uses:
+  ``((ix)*1 ^ (iy)*(P1 & 0xFFFF) ^ (iz)*(P2 & 0xFFFF)) & 0xFFFF`` on two's
+  complement int32 cell coordinates.  numpy; used to prove the identity against
+  :func:`hash_indices`."""
+  N_l = hash_resolutions()[level]
+  v = (x.astype(np.float32) * N_l).astype(np.float32)
+  l = np.floor(v).astype(np.int32)
+  out = []
+  for (bx, by, bz) in HASH_CORNERS:
+    ix = (l[..., 0] + bx).astype(np.uint32)
+    iy = (l[..., 1] + by).astype(np.uint32)
+    iz = (l[..., 2] + bz).astype(np.uint32)
+    h = (ix * np.uint32(1)) ^ (iy * np.uint32(HASH_PRIMES[1] & 0xFFFF)) ^ (iz * np.uint32(HASH_PRIMES[2] & 0xFFFF))
+    out.append((h & np.uint32(0xFFFF)).astype(np.int64))
+  return np.stack(out, axis=0)
+
+
+def hash_encode(x: Tensor, tables: Tensor) -> Tensor:
+  """``[N,3] -> [N, 3 + 8*4]``; ``tables`` is ``[8, 65536, 4]``."""
+  out = []
+  for i in range(HASH_LEVELS):
+    N_l = float(HASH_LOW * (HASH_SCALE ** i))
+    v_l = x * N_l
+    l = v_l.floor().long()
+    idx = hash_indices(x, i)                                  # [8, N]
+    embs = tables[i][idx]                                     # [8, N, 4]
+    ws = v_l - l
+    wx, wy, wz = ws.split([1, 1, 1], dim=-1)
+    iws = 1 - ws
+    iwx, iwy, iwz = iws.split([1, 1, 1], dim=-1)
+    weights = torch.stack([
+      iwx * iwy * iwz, iwx * iwy * wz, iwx * wy * iwz, iwx * wy * wz,
+      wx * iwy * iwz, wx * iwy * wz, wx * wy * iwz, wx * wy * wz,
+    ], dim=0)                                                 # [8, N, 1]
+    out.append((embs * weights).sum(dim=0))
+  out = torch.cat(out, dim=-1)
+  return torch.cat([x, out], dim=-1)
+
+
+def hash_tables(params: Params, prefix: str) -> Tensor:
+  return torch.stack([params[f"{prefix}.embs.{i}.weight"] for i in range(HASH_LEVELS)], dim=0)
+
+
+# ----------------------------------------------------------------------------
+# a-3  Fourier encoder  (reference src/neural_blocks.py:36-55, src/utils.py:14-17)
+# ----------------------------------------------------------------------------
+def fourier_encode(x: Tensor, basis: Tensor) -> Tensor:
+  mapped = x @ basis
+  return torch.cat([mapped.sin(), mapped.cos()], dim=-1)
+
+
+# ----------------------------------------------------------------------------
+# a-5  SkipConnMLP  (reference src/neural_blocks.py:279-296)
+# ----------------------------------------------------------------------------
+def _q(x: Tensor, quant: Optional[torch.dtype]) -> Tensor:
+  """Emulate tensor-core operand rounding (round GEMM inputs to ``quant``, fp32
+  accumulate).  ``None`` = the reference's plain fp32."""
+  return x if quant is None else x.to(quant).to(torch.float32)
+
+
+def skip_mlp(x0: Tensor, params: Params, prefix: str, act: str = "leaky_relu",
+             skip: int = 3, quant: Optional[torch.dtype] = None) -> Tensor:
+  """``x0`` is the already-assembled ``[N, dim_p]`` input ``[p, enc(p), latent]``.
+  The activation PRECEDES every hidden Linear and is also applied to the
+  re-concatenated raw inputs (neural_blocks.py:290-293)."""
+  a = ACTS[act]
+  lin = lambda x, n: F.linear(_q(x, quant), _q(params[f"{prefix}.{n}.weight"], quant), params[f"{prefix}.{n}.bias"])
+  n_layers = 0
+  while f"{prefix}.layers.{n_layers}.weight" in params: n_layers += 1
+  x = lin(x0, "init")
+  for i in range(n_layers):
+    if i != n_layers - 1 and (i % skip) == 0:
+      x = torch.cat([x, x0], dim=-1)
+    x = lin(a(x), f"layers.{i}")
+  return lin(a(x), "out")
+
+
+# ----------------------------------------------------------------------------
+# a-10  view direction -> (elevation, azimuth)   (reference src/utils.py:247-254)
+# ----------------------------------------------------------------------------
+def dir_to_elev_azim(direc: Tensor) -> Tensor:
+  lim = 1 - 1e-6
+  x, y, z = F.normalize(direc, dim=-1).clamp(min=-lim, max=lim).split([1, 1, 1], dim=-1)
+  return torch.cat([z.acos(), torch.atan2(y, x)], dim=-1)
+
+
+# ----------------------------------------------------------------------------
+# a-8 / a-9  density -> alpha -> weights -> integrate  (reference src/nerf.py:22-27,60-80)
+# ----------------------------------------------------------------------------
+def cumuprod_exclusive(t: Tensor) -> Tensor:
+  cp = torch.cumprod(t, dim=0)
+  cp = torch.roll(cp, 1, dims=0)
+  cp[0, ...] = 1.0
+  return cp
+
+
+def alpha_from_density(density: Tensor, ts: Tensor, r_d: Tensor, softplus: bool = True):
+  """``density[T,...]``, shared ``ts[T]``, ``r_d[...,3]`` (NOT normalised)."""
+  sigma_a = F.softplus(density - 1) if softplus else F.relu(density)
+  end_val = torch.full_like(ts[..., :1], 1e10)
+  dists = torch.cat([ts[..., 1:] - ts[..., :-1], end_val], dim=-1).clamp(min=1e-5)
+  while len(dists.shape) < density.dim(): dists = dists[..., None]
+  dists = dists * torch.linalg.norm(r_d, dim=-1)
+  alpha = 1 - torch.exp(-sigma_a * dists)
+  weights = alpha * cumuprod_exclusive(1.0 - alpha + 1e-10)
+  return alpha, weights
+
+
+def alpha_from_density_per_ray(density: Tensor, ts: Tensor, r_d: Tensor, softplus: bool = True):
+  """Restated compositor for PER-RAY sample positions ``ts[T,...]`` (coarse+fine,
+  SURVEY.md a-7): same formula, delta taken along dim 0."""
+  sigma_a = F.softplus(density - 1) if softplus else F.relu(density)
+  end_val = torch.full_like(ts[:1], 1e10)
+  dists = torch.cat([ts[1:] - ts[:-1], end_val], dim=0).clamp(min=1e-5)
+  dists = dists * torch.linalg.norm(r_d, dim=-1)
+  alpha = 1 - torch.exp(-sigma_a * dists)
+  weights = alpha * cumuprod_exclusive(1.0 - alpha + 1e-10)
+  return alpha, weights
+
+
+def volumetric_integrate(weights: Tensor, other: Tensor) -> Tensor:
+  return torch.sum(weights[..., None] * other, dim=0)
+
+
+def sky(bg: str, weights: Tensor):
+  """reference src/nerf.py:96-109."""
+  if bg == "black": return 0
+  if bg == "white": return 1 - weights[:-1].sum(dim=0).unsqueeze(-1)
+  raise NotImplementedError(bg)
+
+
+# ----------------------------------------------------------------------------
+# a-6  PlainNeRF  (reference src/nerf.py:326-361) with the View head of refl.py:190-207
+# ----------------------------------------------------------------------------
+def plain_from_pts(params: Params, pts: Tensor, ts: Tensor, r_o: Tensor, r_d: Tensor, *,
+                   sigmoid: str = "upshifted", bg: str = "black",
+                   density_noise: Optional[Tensor] = None,
+                   quant: Optional[torch.dtype] = None, per_ray_ts: bool = False,
+                   pts_encode: Optional[Tensor] = None) -> Dict[str, Tensor]:
+  """Returns every stage so tests can localise a mismatch."""
+  T = pts.shape[0]
+  batches = pts.shape[:-1]
+  p = pts.reshape(-1, 3)
+  tables = hash_tables(params, "first.enc")
+  enc = hash_encode(p, tables)                               # [N,35] = [p, feats]
+  x0 = torch.cat([p, enc], dim=-1)                           # [N,38] = [p, p, feats]
+  first_out = skip_mlp(x0, params, "first", "leaky_relu", quant=quant).reshape(batches + (-1,))
+  density = first_out[..., 0]
+  if density_noise is not None: density = density + density_noise
+  intermediate = first_out[..., 1:]
+  view = r_d.unsqueeze(0).expand_as(pts)
+  elaz = dir_to_elev_azim(view)
+  x0r = torch.cat([pts, elaz, intermediate], dim=-1).reshape(-1, 5 + intermediate.shape[-1])
+  rgb_raw = skip_mlp(x0r, params, "refl.mlp", "sin", quant=quant).reshape(batches + (-1,))
+  rgb = SIGMOIDS[sigmoid](rgb_raw)
+  if per_ray_ts: alpha, weights = alpha_from_density_per_ray(density, ts, r_d)
+  else: alpha, weights = alpha_from_density(density, ts, r_d)
+  out = volumetric_integrate(weights, rgb) + sky(bg, weights)
+  return dict(out=out, alpha=alpha, weights=weights, rgb=rgb, density=density,
+              first_out=first_out, hash_feats=enc[:, 3:], elaz=elaz[0])
+
+
+def plain_forward(params: Params, rays: Tensor, ts: Tensor, **kw) -> Dict[str, Tensor]:
+  pts, r_o, r_d = compute_pts(rays, ts)
+  res = plain_from_pts(params, pts, ts, r_o, r_d, **kw)
+  res["pts"] = pts
+  return res
+
+
+# ----------------------------------------------------------------------------
+# a-13  TinyNeRF, intended semantics  (reference src/nerf.py:292-305; the
+# reference's own forward mis-broadcasts a [...,1] density -- SURVEY.md a-13)
+# ----------------------------------------------------------------------------
+def tiny_forward(params: Params, rays: Tensor, ts: Tensor, *, sigmoid: str = "upshifted",
+                 bg: str = "black", quant: Optional[torch.dtype] = None) -> Dict[str, Tensor]:
+  pts, r_o, r_d = compute_pts(rays, ts)
+  batches = pts.shape[:-1]
+  o = skip_mlp(pts.reshape(-1, 3), params, "estim", "leaky_relu", quant=quant).reshape(batches + (-1,))
+  density, feats = o[..., 0], o[..., 1:]
+  alpha, weights = alpha_from_density(density, ts, r_d)
+  rgb = SIGMOIDS[sigmoid](feats)
+  out = volumetric_integrate(weights, rgb) + sky(bg, weights)
+  return dict(out=out, alpha=alpha, weights=weights, rgb=rgb, density=density, pts=pts)
+
+
+# ----------------------------------------------------------------------------
+# a-11  VolSDF volume branch  (reference src/nerf.py:981-1013, src/utils.py:50-58)
+# ----------------------------------------------------------------------------
+def laplace_cdf(sdf_vals: Tensor, beta: Tensor) -> Tensor:
+  scaled = sdf_vals / beta
+  return torch.where(scaled <= 0, scaled.exp() / 2, 1 - scaled.neg().exp() / 2)
+
+
+# ----------------------------------------------------------------------------
+# a-7  inverse-CDF resampling, restated from the dead code at nerf.py:1745-1779
+# ----------------------------------------------------------------------------
+def sample_pdf(bins: Tensor, weights: Tensor, u: Tensor) -> Tensor:
+  """``bins[T-1]`` mid-points shared by all rays, ``weights[T-2, R]``, ``u[Nf, R]``
+  in [0,1) -> new sample positions ``[Nf, R]``.  Follows lines 1754-1777 with the
+  undefined ``bins_g`` read as the gather of ``bins``."""
+  w = weights + 1e-5
+  pdf = w / w.sum(dim=0, keepdim=True)
+  cdf = torch.cumsum(pdf, dim=0)
+  cdf = torch.cat([torch.zeros_like(cdf[:1]), cdf], dim=0)   # [T-1, R]
+  cdf_t = cdf.transpose(0, 1).contiguous()                   # [R, T-1]
+  u_t = u.transpose(0, 1).contiguous()                       # [R, Nf]
+  inds = torch.searchsorted(cdf_t, u_t, right=True)
+  below = (inds - 1).clamp(min=0)
+  above = inds.clamp(max=cdf_t.shape[-1] - 1)
+  cdf_b, cdf_a = cdf_t.gather(1, below), cdf_t.gather(1, above)
+  bins_b, bins_a = bins[below], bins[above]
+  denom = cdf_a - cdf_b
+  denom = torch.where(denom < 1e-5, torch.ones_like(denom), denom)
+  t = (u_t - cdf_b) / denom
+  return (bins_b + t * (bins_a - bins_b)).transpose(0, 1).contiguous()
+
+
+# ----------------------------------------------------------------------------
+# deterministic synthetic inputs (shared by tests, golden generator, bench)
+# ----------------------------------------------------------------------------
+def make_plain_params(seed: int = 1337, intermediate: int = 64, sigma_gain: float = 1.0) -> Params:
+  """Parameters with the reference's init *distributions* (first MLP: torch
+  default U(+-1/sqrt(fan_in)), neural_blocks.py:258-259; View MLP: siren
+  U(+-sqrt(6/fan_in)) with zero bias, 266-271; hash tables N(0,1),
+  neural_blocks.py:123-125) drawn from numpy's PCG64 so the values are
+  platform independent.  ``sigma_gain`` scales the density row of ``first.out``
+  (weight set "S" of SURVEY.md section 8d: sharp density, early termination)."""
+  g = np.random.default_rng(seed)
+  P: Params = {}
+  def uni(shape, a): return torch.from_numpy(g.uniform(-a, a, size=shape).astype(np.float32))
+  def default_linear(name, out_f, in_f):
+    a = 1.0 / math.sqrt(in_f)
+    P[f"{name}.weight"] = uni((out_f, in_f), a); P[f"{name}.bias"] = uni((out_f,), a)
+  def siren_linear(name, out_f, in_f):
+    P[f"{name}.weight"] = uni((out_f, in_f), math.sqrt(6.0 / in_f)); P[f"{name}.bias"] = torch.zeros(out_f)
+  I = intermediate
+  P["empty_latent"] = torch.zeros(1, 1, 1, 1, 0)
+  P["first.enc.primes"] = torch.tensor([1, 2654435761, 805459861, 3674653429, 2097192037, 1434869437, 2165219737])
+  for i in range(HASH_LEVELS):
+    P[f"first.enc.embs.{i}.weight"] = torch.from_numpy(g.standard_normal((HASH_TABLE, HASH_FEAT)).astype(np.float32))
+  default_linear("first.init", 256, 38)
+  default_linear("first.layers.0", 256, 256 + 38)
+  for i in (1, 2, 3): default_linear(f"first.layers.{i}", 256, 256)
+  default_linear("first.out", 1 + I, 256)
+  if sigma_gain != 1.0:
+    P["first.out.weight"][0] *= sigma_gain; P["first.out.bias"][0] *= sigma_gain
+  siren_linear("refl.mlp.init", 256, 5 + I)
+  siren_linear("refl.mlp.layers.0", 256, 256 + 5 + I)
+  for i in (1, 2, 3): siren_linear(f"refl.mlp.layers.{i}", 256, 256)
+  siren_linear("refl.mlp.out", 3, 256)
+  return P
+
+
+def make_rays(n_views: int, h: int, w: int, size: int = 800, seed: int = 0,
+              crop_top: int = 0, crop_left: int = 0, radius: float = 4.0) -> Tensor:
+  """``rays[B,H,W,6]`` exactly as runner.render + NeRFCamera.sample_positions build
+  them (reference runner.py:495-505, src/cameras.py:45-66; ``with_noise=False``):
+  lego-like geometry, focal from camera_angle_x=0.6911112 (loaders.py:83), camera
+  on a radius-4 sphere looking at the origin.  r_d is NOT normalised."""
+  g = np.random.default_rng(seed)
+  focal = 0.5 * size / math.tan(0.5 * 0.6911112)
+  c2w = []
+  for _ in range(n_views):
+    th, ph = g.uniform(0, 2 * math.pi), g.uniform(0.15, 1.2)
+    eye = np.array([radius * math.cos(th) * math.cos(ph), radius * math.sin(th) * math.cos(ph), radius * math.sin(ph)])
+    fwd = -eye / np.linalg.norm(eye)
+    right = np.cross(fwd, np.array([0.0, 0.0, 1.0])); right /= np.linalg.norm(right)
+    up = np.cross(right, fwd)
+    m = np.eye(4); m[:3, 0], m[:3, 1], m[:3, 2], m[:3, 3] = right, up, -fwd, eye
+    c2w.append(m[:3, :4])
+  c2w = torch.from_numpy(np.stack(c2w).astype(np.float32))
+  ii, jj = torch.meshgrid(torch.arange(size, dtype=torch.float), torch.arange(size, dtype=torch.float), indexing="ij")
+  positions = torch.stack([ii.transpose(-1, -2), jj.transpose(-1, -2)], dim=-1)
+  positions = positions[crop_top:crop_top + h, crop_left:crop_left + w, :]
+  u, v = positions.split([1, 1], dim=-1)
+  d = torch.stack([(u - size * 0.5) / focal, -(v - size * 0.5) / focal, -torch.ones_like(u)], dim=-1)
+  r_d = torch.sum(d[..., None, :] * c2w[..., :3, :3], dim=-1)
+  r_d = r_d.permute(2, 0, 1, 3)
+  r_o = c2w[..., :3, -1][:, None, None, :].expand_as(r_d)
+  return torch.cat([r_o, r_d], dim=-1).contiguous()

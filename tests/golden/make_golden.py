@@ -1,0 +1,107 @@
+"""Generate the golden vectors in this directory by EXECUTING THE REFERENCE
+(/root/reference, imported read-only with oracle/ref_shim.py) on seeded inputs.
+
+Run in the build container:   python tests/golden/make_golden.py
+The reference tree cannot travel to the GPU box, so the outputs are committed.
+Parameters and rays are regenerated from seeds (numpy PCG64, platform
+independent) by oracle.nerf_oracle.make_plain_params / make_rays, so a fixture
+only stores the small outputs of the reference run.
+"""
+import os, sys
+import numpy as np
+import torch
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+from oracle import nerf_oracle as O, ref_shim
+
+def ref_plain(params, steps, train=False):
+  runner, nerf, refl, utils, cameras = ref_shim.load()
+  model, args = ref_shim.build_model("plain", steps)
+  sd = {k: v.clone() for k, v in params.items()}
+  model.load_state_dict(sd, strict=True)
+  model.train(train)
+  return model, args
+
+def case_plain(name, seed, B, H, W, T, sigma_gain=1.0, train=False, top=0, left=0, stages=True):
+  params = O.make_plain_params(seed, 64, sigma_gain)
+  rays = O.make_rays(B, H, W, size=800, seed=seed, crop_top=top, crop_left=left)
+  model, args = ref_plain(params, T, train)
+  runner, nerf, refl, utils, cameras = ref_shim.load()
+  draws = {}
+  if train:
+    # capture the two RNG draws of the training path (nerf.py:45 rand_like, nerf.py:348 randn_like)
+    torch.manual_seed(seed)
+    o_rand, o_randn = torch.rand_like, torch.randn_like
+    def rl(x, *a, **k): r = o_rand(x, *a, **k); draws["rand"] = r.clone(); return r
+    def rnl(x, *a, **k): r = o_randn(x, *a, **k); draws["randn"] = r.clone(); return r
+    torch.rand_like, torch.randn_like = rl, rnl
+  try:
+    with torch.no_grad(): out = model(rays)
+  finally:
+    if train: torch.rand_like, torch.randn_like = o_rand, o_randn
+  fx = dict(
+    kind="plain", seed=seed, B=B, H=H, W=W, T=T, sigma_gain=sigma_gain, train=int(train), top=top, left=left,
+    near=float(args.near), far=float(args.far), sigmoid=args.sigmoid_kind, bg=args.bg,
+    ts=model.ts.numpy(), out=out.numpy(), alpha=model.alpha.numpy(), weights=model.weights.numpy(),
+  )
+  if train: fx["rand"] = draws["rand"].numpy(); fx["randn"] = draws["randn"].numpy()
+  if stages:
+    # per-stage tensors straight from the reference sub-modules
+    with torch.no_grad():
+      pts, ts, r_o, r_d, _ = nerf.compute_pts_ts(rays, args.near, args.far, T, perturb=0) if not train else \
+        (r_o_pts(rays, model.ts))
+      p = pts.reshape(-1, 3)
+      fx["pts"] = pts.numpy()
+      fx["hash_enc"] = model.first.enc(p).numpy()
+      fo = model.first(pts, model.empty_latent.expand(pts.shape[:-1] + (0,)))
+      fx["first_out"] = fo.numpy()
+      fx["elaz"] = utils.dir_to_elev_azim(r_d).numpy()
+      idx = []
+      for lvl in range(8):
+        N_l = model.first.enc.low_reso * (model.first.enc.scale ** lvl)
+        l = (p * N_l).floor().long()
+        h = l + 1
+        lx, ly, lz = l.split([1, 1, 1], dim=-1); hx, hy, hz = h.split([1, 1, 1], dim=-1)
+        cat = lambda x, y, z: torch.cat([x, y, z], dim=-1)
+        vs = [l, cat(lx, ly, hz), cat(lx, hy, lz), cat(lx, hy, hz), cat(hx, ly, lz), cat(hx, ly, hz), cat(hx, hy, lz), h]
+        idx.append(torch.stack([(model.first.enc.hash_fn(v) % model.first.enc.emb_size).squeeze(-1) for v in vs], 0))
+      fx["hash_idx"] = torch.stack(idx, 0).numpy().astype(np.uint16)   # [level, corner, N]
+  # the synthetic ray generator must equal the reference camera (cameras.py:45-66, runner.py:495-505)
+  np.savez_compressed(os.path.join(HERE, name + ".npz"), **fx)
+  print(name, "out", out.shape, "mean", float(out.mean()), "acc-before-last", float(model.weights[:-1].sum(0).mean()))
+
+def r_o_pts(rays, ts):
+  r_o, r_d = rays.split([3, 3], dim=-1)
+  pts = r_o.unsqueeze(0) + torch.tensordot(ts, r_d, dims=0)
+  return pts, ts, r_o, r_d, None
+
+def check_rays():
+  runner, nerf, refl, utils, cameras = ref_shim.load()
+  import math
+  size = 800
+  rays = O.make_rays(2, 5, 7, size=size, seed=3, crop_top=11, crop_left=400)
+  # rebuild the same poses and go through the reference camera + runner.render's pixel grid
+  g = np.random.default_rng(3)
+  focal = 0.5 * size / math.tan(0.5 * 0.6911112)
+  c2w = []
+  for _ in range(2):
+    th, ph = g.uniform(0, 2 * math.pi), g.uniform(0.15, 1.2)
+    eye = np.array([4 * math.cos(th) * math.cos(ph), 4 * math.sin(th) * math.cos(ph), 4 * math.sin(ph)])
+    fwd = -eye / np.linalg.norm(eye)
+    right = np.cross(fwd, np.array([0.0, 0.0, 1.0])); right /= np.linalg.norm(right)
+    up = np.cross(right, fwd)
+    m = np.eye(4); m[:3, 0], m[:3, 1], m[:3, 2], m[:3, 3] = right, up, -fwd, eye
+    c2w.append(m[:3, :4])
+  cam = cameras.NeRFCamera(cam_to_world=torch.from_numpy(np.stack(c2w).astype(np.float32)), focal=focal)
+  ii, jj = torch.meshgrid(torch.arange(size, dtype=torch.float), torch.arange(size, dtype=torch.float), indexing="ij")
+  positions = torch.stack([ii.transpose(-1, -2), jj.transpose(-1, -2)], dim=-1)[11:16, 400:407, :]
+  ref = cam.sample_positions(positions, size=size, with_noise=False)
+  assert torch.equal(ref, rays), "make_rays != reference camera"
+  print("make_rays == NeRFCamera.sample_positions: ok")
+
+if __name__ == "__main__":
+  check_rays()
+  case_plain("plain_t16", seed=11, B=1, H=4, W=6, T=16)
+  case_plain("plain_t16_sharp", seed=12, B=2, H=3, W=5, T=16, sigma_gain=20.0, top=390, left=380)
+  case_plain("plain_t128", seed=1337, B=1, H=8, W=8, T=128, sigma_gain=20.0, top=396, left=396, stages=False)
+  case_plain("plain_t64_train", seed=21, B=1, H=4, W=4, T=64, sigma_gain=20.0, train=True, top=300, left=420, stages=False)

@@ -1,0 +1,85 @@
+"""Pin the CPU oracle (oracle/nerf_oracle.py) against golden vectors produced by
+EXECUTING THE REFERENCE modules (tests/golden/make_golden.py).  CPU, bit-exact."""
+import os
+import numpy as np
+import pytest
+import torch
+from oracle import nerf_oracle as O
+
+CASES = ["plain_t16", "plain_t16_sharp", "plain_t128", "plain_t64_train"]
+
+def load(golden_dir, name):
+  fx = np.load(os.path.join(golden_dir, name + ".npz"))
+  return {k: fx[k] for k in fx.files}
+
+def run_oracle(fx, quant=None):
+  params = O.make_plain_params(int(fx["seed"]), 64, float(fx["sigma_gain"]))
+  rays = O.make_rays(int(fx["B"]), int(fx["H"]), int(fx["W"]), 800, int(fx["seed"]), int(fx["top"]), int(fx["left"]))
+  train = bool(fx["train"])
+  ts = O.compute_ts(float(fx["near"]), float(fx["far"]), int(fx["T"]), rand=torch.from_numpy(fx["rand"]) if train else None)
+  noise = torch.from_numpy(fx["randn"]) * 0.2 if train else None
+  return O.plain_forward(params, rays, ts, sigmoid=str(fx["sigmoid"]), bg=str(fx["bg"]), density_noise=noise, quant=quant), ts
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_bit_exact(golden_dir, name):
+  fx = load(golden_dir, name)
+  with torch.no_grad(): res, ts = run_oracle(fx)
+  assert np.array_equal(ts.numpy(), fx["ts"])
+  for k in ("out", "alpha", "weights"):
+    assert np.array_equal(res[k].numpy(), fx[k]), f"{name}: {k} differs from the reference run"
+  if "pts" in fx:
+    assert np.array_equal(res["pts"].numpy(), fx["pts"])
+    assert np.array_equal(res["first_out"].numpy(), fx["first_out"])
+    assert np.array_equal(res["hash_feats"].numpy(), fx["hash_enc"][:, 3:])
+    assert np.array_equal(res["elaz"].numpy(), fx["elaz"])
+
+@pytest.mark.parametrize("name", ["plain_t16", "plain_t16_sharp"])
+def test_hash_indices_bit_exact_and_u32_identity(golden_dir, name):
+  fx = load(golden_dir, name)
+  p = torch.from_numpy(fx["pts"]).reshape(-1, 3)
+  for lvl in range(8):
+    idx = O.hash_indices(p, lvl).numpy()
+    assert np.array_equal(idx, fx["hash_idx"][lvl].astype(np.int64))
+    # the low-16-bit uint32 form the CUDA kernel uses is the same function
+    assert np.array_equal(O.hash_indices_u32(p.numpy(), lvl), idx)
+
+def test_u32_identity_negative_and_large_coordinates():
+  g = np.random.default_rng(5)
+  p = (g.uniform(-300, 300, size=(20000, 3))).astype(np.float32)
+  for lvl in range(8):
+    assert np.array_equal(O.hash_indices_u32(p, lvl), O.hash_indices(torch.from_numpy(p), lvl).numpy())
+
+def test_hash_resolutions_decrease():
+  # operator-precedence quirk of neural_blocks.py:126-128: scale < 1, resolutions 16 -> 6.28
+  r = O.hash_resolutions()
+  assert abs(O.HASH_SCALE - 0.8749696978086082) < 1e-15
+  assert r[0] == 16.0 and abs(r[7] - 6.2817) < 1e-3 and np.all(np.diff(r) < 0)
+
+def test_composite_identities():
+  # analytic KATs of SURVEY.md section 8c
+  g = torch.Generator().manual_seed(0)
+  T, R = 32, 50
+  dens = torch.randn(T, R, generator=g) * 3
+  ts = torch.linspace(2, 6, T)
+  r_d = torch.randn(R, 3, generator=g)
+  alpha, w = O.alpha_from_density(dens, ts, r_d)
+  assert torch.allclose(w.sum(0), 1 - torch.prod(1 - alpha + 1e-10, dim=0), atol=1e-5)
+  assert torch.all(alpha[-1] > 0.999999)          # the 1e10 end cap
+  # vanishing (but non-zero) density -> the 1e10 end cap sends everything to the last sample's colour
+  alpha0, w0 = O.alpha_from_density(torch.full((T, R), -14.0), ts, r_d)
+  rgb = torch.rand(T, R, 3, generator=g)
+  assert torch.allclose(O.volumetric_integrate(w0, rgb), rgb[-1], atol=1e-4)
+  # exactly zero density (softplus underflow) -> nothing is accumulated at all
+  _, wz = O.alpha_from_density(torch.full((T, R), -1e4), ts, r_d)
+  assert float(wz.abs().max()) == 0.0
+
+def test_fp16_operand_emulation_within_stated_tolerance(golden_dir):
+  """The tensor-core path rounds GEMM operands to fp16 (fp32 accumulate).  Its
+  stated tolerance against the fp32 reference is max|d rgb| <= 1e-3 and
+  PSNR >= 70 dB; the emulation must sit inside it with margin."""
+  for name in ("plain_t128", "plain_t16_sharp"):
+    fx = load(golden_dir, name)
+    with torch.no_grad(): res, _ = run_oracle(fx, quant=torch.float16)
+    d = np.abs(res["out"].numpy() - fx["out"])
+    psnr = -10 * np.log10(np.mean(d.astype(np.float64) ** 2))
+    assert d.max() < 1e-3 and psnr > 70, (name, d.max(), psnr)
