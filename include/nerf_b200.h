@@ -1,0 +1,143 @@
+/*
+ * nerf_b200.h -- C ABI of the B200-native NeRF volume-rendering path.
+ *
+ * The reference (JulianKnodt/nerf_atlas) has no FFI: its surface for this path is
+ * the Python duck-type  model(rays[B,H,W,6]) -> rgb[B,H,W,3]  (reference
+ * src/nerf.py:326-361, called from runner.py:490-509).  This header is the
+ * boundary a maintainer binds that surface to (see INTEGRATION.md for the ctypes
+ * stub).  Conventions:
+ *   - every export returns int: 0 = ok, >0 = cudaError_t, <0 = NF_E_* below;
+ *     nf_last_error() gives the message (thread local).  Nothing throws or exits.
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless the
+ *     name ends in _host; tensors are contiguous fp32 row-major.
+ *   - the library owns no parameters: nf_pack_weights() snapshots the caller's
+ *     live parameter tensors into a caller-allocated `packed` blob.
+ *   - every launch goes to the caller's stream; no global mutable state.
+ */
+#ifndef NERF_B200_H
+#define NERF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NF_ABI_VERSION 1
+
+/* error codes (negative; positive values are cudaError_t) */
+#define NF_E_BADARG    (-1)
+#define NF_E_UNSUPPORTED (-2)
+#define NF_E_SMALLBUF  (-3)
+
+/* activation that PRECEDES each hidden Linear (reference src/neural_blocks.py:290-296) */
+enum nf_act { NF_ACT_NONE = 0, NF_ACT_LEAKY = 1 /* LeakyReLU(0.01) */, NF_ACT_SIN = 2, NF_ACT_RELU = 3 };
+/* input encoder of the density MLP (reference src/neural_blocks.py:36-55,92-193) */
+enum nf_enc { NF_ENC_NONE = 0, NF_ENC_HASH = 1, NF_ENC_FOURIER = 2 };
+/* raw density -> sigma (reference src/nerf.py:60-65) */
+enum nf_density_act { NF_DENS_SOFTPLUS_M1 = 0 /* softplus(x-1) */, NF_DENS_RELU = 1 };
+/* feature activation = the sigmoid family of reference src/utils.py:484-518 */
+enum nf_feat_act { NF_FEAT_NORMAL = 0, NF_FEAT_THIN = 1, NF_FEAT_TANH = 2, NF_FEAT_CYCLIC = 3, NF_FEAT_UPSHIFTED = 4,
+                   NF_FEAT_FAT = 5, NF_FEAT_LEAKY_RELU = 6, NF_FEAT_RELU = 7, NF_FEAT_SIN = 8,
+                   NF_FEAT_UPSHIFTED_SOFTPLUS = 9, NF_FEAT_UPSHIFTED_RELU = 10 };
+/* background (reference src/nerf.py:96-109) */
+enum nf_bg { NF_BG_BLACK = 0, NF_BG_WHITE = 1 };
+/* model family */
+enum nf_kind {
+  NF_KIND_PLAIN = 0, /* PlainNeRF + View head: reference src/nerf.py:310-361, src/refl.py:190-207 */
+  NF_KIND_TINY  = 1  /* TinyNeRF (intended semantics): reference src/nerf.py:278-305 */
+};
+/* arithmetic of the MLP contractions */
+enum nf_precision {
+  NF_PREC_FP32 = 0, /* CUDA-core fp32 FMA; the exact mode (matches the reference's SGEMM to ~1e-6) */
+  NF_PREC_FP16_TC = 1 /* tcgen05 tensor cores, fp16 operands, fp32 accumulate in TMEM */
+};
+
+/* One SkipConnMLP (reference src/neural_blocks.py:204-296). */
+typedef struct nf_mlp_desc {
+  int32_t in_dims;   /* dim_p = width of x0 = [p, enc(p), latent] */
+  int32_t hidden;    /* hidden_size (256 in every reference instance on this path) */
+  int32_t n_layers;  /* len(self.layers) */
+  int32_t out_dims;  /* out.out_features */
+  int32_t skip;      /* x0 is re-concatenated before hidden layer i iff i%skip==0 && i!=n_layers-1 */
+  int32_t act;       /* enum nf_act */
+} nf_mlp_desc;
+
+typedef struct nf_model_desc {
+  int32_t struct_bytes;      /* = sizeof(nf_model_desc); ABI guard */
+  int32_t kind;              /* enum nf_kind */
+  nf_mlp_desc density;       /* PlainNeRF.first / TinyNeRF.estim */
+  nf_mlp_desc refl;          /* View.mlp (ignored for NF_KIND_TINY) */
+  int32_t intermediate;      /* I = intermediate_size */
+  int32_t enc;               /* enum nf_enc, encoder of `density` */
+  int32_t hash_levels;       /* 8 */
+  int32_t hash_table_size;   /* 65536 (power of two) */
+  int32_t hash_feat;         /* 4 */
+  uint32_t hash_primes[3];   /* 1, 2654435761, 805459861 */
+  float hash_res[16];        /* fp32(N_l) per level, exactly as `x * N_l` rounds it */
+  int32_t density_act;       /* enum nf_density_act */
+  int32_t feat_act;          /* enum nf_feat_act */
+  int32_t bg;                /* enum nf_bg */
+} nf_model_desc;
+
+/* ---- library ----------------------------------------------------------- */
+int nf_version(void);
+const char* nf_last_error(void);
+
+/* ---- parameters -------------------------------------------------------- */
+/* Number of parameter pointers nf_pack_weights expects for `desc`, in this order:
+ *   density MLP: init.weight, init.bias, layers[0].weight, layers[0].bias, ..., out.weight, out.bias
+ *   refl MLP   : same order                                   (NF_KIND_PLAIN only)
+ *   hash tables: embs[0].weight ... embs[levels-1].weight      (NF_ENC_HASH only)
+ * Each is the live fp32 nn.Parameter storage ([out,in] row-major for weights). */
+int nf_param_count(const nf_model_desc* desc);
+/* Bytes of the packed blob for `desc` (all precisions). */
+int64_t nf_packed_bytes(const nf_model_desc* desc);
+/* Snapshot the parameters into `packed` (device, >= nf_packed_bytes, 1024-byte aligned):
+ * fp32 k-major copies for NF_PREC_FP32, fp16 UMMA-canonical weight chunks for
+ * NF_PREC_FP16_TC, biases, and the hash tables. Replaces: the implicit read of
+ * nn.Parameter by F.linear / nn.Embedding (reference src/neural_blocks.py:166,289-296). */
+int nf_pack_weights(const nf_model_desc* desc, const float* const* params_host, int32_t n_params,
+                    void* packed, int64_t packed_bytes, void* stream);
+
+/* ---- the hot path ------------------------------------------------------ */
+/* rays[R,6] -> rgb[R,out].  Replaces PlainNeRF.forward / TinyNeRF.forward
+ * (reference src/nerf.py:326-361, 292-305):  sample positions (nerf.py:50-55),
+ * encode, both MLPs, alpha_from_density (nerf.py:60-73), volumetric_integrate
+ * (nerf.py:79-80) and the sky term.
+ *   ts             sample distances; ts_ray_stride == 0: one ts[T] shared by all rays
+ *                  (the reference's layout); == T: per-ray ts[R,T] (coarse+fine pass)
+ *   density_noise  nullable [R,T]; added to the raw density (nerf.py:347-348, already scaled)
+ *   alpha_out, weights_out  nullable [R,T] (ray-major; the reference's self.alpha/self.weights
+ *                  are the [T,R] transposes)
+ */
+int nf_render_forward(const nf_model_desc* desc, const void* packed,
+                      const float* rays, int64_t n_rays,
+                      const float* ts, int32_t T, int64_t ts_ray_stride,
+                      const float* density_noise,
+                      float* rgb_out, float* alpha_out, float* weights_out,
+                      int32_t precision, void* stream);
+
+/* ---- stages of the path, exported for parity tests and micro-benchmarks -- */
+/* pts[R,T,3] = r_o + ts*r_d, rounded product then rounded add (reference src/nerf.py:54). */
+int nf_sample_points(const float* rays, int64_t n_rays, const float* ts, int32_t T, int64_t ts_ray_stride,
+                     float* pts_out, void* stream);
+/* HashEncoder.forward (reference src/neural_blocks.py:139-193) on pts[N,3]:
+ * feats_out[N, levels*feat]; idx_out nullable uint16 [levels, 8, N] table rows per corner. */
+int nf_hash_encode(const nf_model_desc* desc, const void* packed, const float* pts, int64_t n,
+                   float* feats_out, uint16_t* idx_out, void* stream);
+/* alpha_from_density + volumetric_integrate (+sky) (reference src/nerf.py:60-80) on
+ * sigma_raw[R,T], feats[R,T,3] (already activated). HBM-bound stand-alone form of the fused tail. */
+int nf_composite(const nf_model_desc* desc, const float* sigma_raw, const float* feats,
+                 const float* rays, int64_t n_rays, const float* ts, int32_t T, int64_t ts_ray_stride,
+                 float* rgb_out, float* alpha_out, float* weights_out, void* stream);
+/* One SkipConnMLP.forward (reference src/neural_blocks.py:279-296) on assembled inputs
+ * x0[N,in_dims] -> out[N,out_dims]; which = 0 density MLP, 1 refl MLP. */
+int nf_mlp_forward(const nf_model_desc* desc, const void* packed, int32_t which,
+                   const float* x0, int64_t n, float* out, int32_t precision, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NERF_B200_H */

@@ -1,0 +1,65 @@
+"""ctypes binding of the C ABI in include/nerf_b200.h (libnerf_b200.so, built in-tree by
+nerf_atlas_b200/build.py).  There is NO fallback: if the library is missing or a call fails, the
+caller gets an exception -- the product path never routes through PyTorch ops or the CPU oracle."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libnerf_b200.so")
+
+# enums of include/nerf_b200.h
+ACT = {"none": 0, "leaky_relu": 1, "sin": 2, "relu": 3}
+ENC = {"none": 0, "hash": 1, "fourier": 2}
+DENSITY = {"softplus": 0, "relu": 1}
+FEAT = {"normal": 0, "thin": 1, "tanh": 2, "cyclic": 3, "upshifted": 4, "fat": 5, "leaky_relu": 6, "relu": 7,
+        "sin": 8, "upshifted_softplus": 9, "upshifted_relu": 10}
+BG = {"black": 0, "white": 1}
+KIND = {"plain": 0, "tiny": 1}
+PRECISION = {"fp32": 0, "fp16": 1}
+
+class MlpDesc(C.Structure):
+  _fields_ = [("in_dims", C.c_int32), ("hidden", C.c_int32), ("n_layers", C.c_int32),
+              ("out_dims", C.c_int32), ("skip", C.c_int32), ("act", C.c_int32)]
+
+class ModelDesc(C.Structure):
+  _fields_ = [("struct_bytes", C.c_int32), ("kind", C.c_int32), ("density", MlpDesc), ("refl", MlpDesc),
+              ("intermediate", C.c_int32), ("enc", C.c_int32), ("hash_levels", C.c_int32),
+              ("hash_table_size", C.c_int32), ("hash_feat", C.c_int32), ("hash_primes", C.c_uint32 * 3),
+              ("hash_res", C.c_float * 16), ("density_act", C.c_int32), ("feat_act", C.c_int32), ("bg", C.c_int32)]
+
+EXPORTS = {
+  "nf_version": (C.c_int, []),
+  "nf_last_error": (C.c_char_p, []),
+  "nf_param_count": (C.c_int, [C.POINTER(ModelDesc)]),
+  "nf_packed_bytes": (C.c_int64, [C.POINTER(ModelDesc)]),
+  "nf_pack_weights": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
+  "nf_render_forward": (C.c_int, [C.POINTER(ModelDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int64,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+  "nf_sample_points": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
+  "nf_hash_encode": (C.c_int, [C.POINTER(ModelDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+  "nf_composite": (C.c_int, [C.POINTER(ModelDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int64,
+                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+  "nf_mlp_forward": (C.c_int, [C.POINTER(ModelDesc), C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),
+}
+
+_lib = None
+
+def lib():
+  """The loaded library; raises if it has not been built."""
+  global _lib
+  if _lib is None:
+    if not os.path.exists(LIB_PATH):
+      raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m nerf_atlas_b200.build` "
+                         "(there is no PyTorch/CPU fallback for the render path)")
+    l = C.CDLL(LIB_PATH)
+    for name, (res, args) in EXPORTS.items():
+      fn = getattr(l, name)          # AttributeError if the export is missing
+      fn.restype, fn.argtypes = res, args
+    if l.nf_version() != 1: raise RuntimeError("libnerf_b200.so: ABI version mismatch")
+    _lib = l
+  return _lib
+
+def check(rc: int, what: str):
+  if rc != 0:
+    msg = lib().nf_last_error().decode("utf-8", "replace")
+    raise RuntimeError(f"{what} failed (code {rc}): {msg}")

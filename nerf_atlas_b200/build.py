@@ -1,0 +1,39 @@
+"""Build the C-ABI library (include/nerf_b200.h) in-tree for sm_100a with nvcc.
+
+    python -m nerf_atlas_b200.build [--force] [--verbose]
+
+The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
+"""
+import os, subprocess, sys, hashlib
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+SOURCES = ["nf_api.cu", "nf_fp32.cu", "nf_tc.cu"]
+HEADERS = ["nf_common.cuh", "nf_kernels.h", os.path.join("..", "..", "include", "nerf_b200.h")]
+LIB = os.path.join(HERE, "libnerf_b200.so")
+STAMP = LIB + ".stamp"
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+         "-Xcompiler", "-fPIC", "--shared", "-Xptxas", "-v"]
+
+def _digest() -> str:
+  h = hashlib.sha256()
+  for f in SOURCES + HEADERS:
+    with open(os.path.join(CSRC, f), "rb") as fh: h.update(fh.read())
+  h.update(" ".join(FLAGS).encode())
+  return h.hexdigest()
+
+def build(force: bool = False, verbose: bool = False) -> str:
+  d = _digest()
+  if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == d:
+    return LIB
+  cmd = [NVCC, *FLAGS, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES]]
+  r = subprocess.run(cmd, capture_output=True, text=True)
+  if verbose or r.returncode != 0: sys.stderr.write(r.stdout + r.stderr)
+  if r.returncode != 0: raise RuntimeError("nvcc failed building libnerf_b200.so")
+  with open(os.path.join(HERE, "ptxas_info.txt"), "w") as f: f.write(r.stderr)
+  with open(STAMP, "w") as f: f.write(d)
+  return LIB
+
+if __name__ == "__main__":
+  print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,141 @@
+// nf_api.cu -- the C ABI declared in include/nerf_b200.h.  Argument checking, plan building and
+// kernel launches only; no torch types, no global mutable state (errors are thread local).
+#include <string>
+#include <cstdio>
+#include "nf_common.cuh"
+#include "nf_kernels.h"
+
+namespace {
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int cuda_fail(cudaError_t e, const char* where) {
+  g_err = std::string(where) + ": " + cudaGetErrorString(e);
+  return (int)e;
+}
+int plan_of(const nf_model_desc* d, NfPlan* p) {
+  const char* why = "";
+  const int rc = nf_build_plan(d, p, &why);
+  if (rc) g_err = std::string("nf_model_desc: ") + why;
+  return rc;
+}
+int check_ts(int32_t T, int64_t ts_stride) {
+  if (T < 1) return fail(NF_E_BADARG, "T must be >= 1");
+  if (ts_stride != 0 && ts_stride != T) return fail(NF_E_BADARG, "ts_ray_stride must be 0 (shared ts[T]) or T (per-ray ts[R,T])");
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int nf_version(void) { return NF_ABI_VERSION; }
+const char* nf_last_error(void) { return g_err.c_str(); }
+
+int nf_param_count(const nf_model_desc* desc) {
+  NfPlan p; if (int rc = plan_of(desc, &p)) return rc;
+  int n = 0;
+  for (int m = 0; m < p.n_mlps; ++m) n += 2 * p.mlp[m].n_lin;
+  if (p.enc == NF_ENC_HASH) n += p.hash_levels;
+  return n;
+}
+
+int64_t nf_packed_bytes(const nf_model_desc* desc) {
+  NfPlan p; if (int rc = plan_of(desc, &p)) return rc;
+  return p.total_bytes;
+}
+
+int nf_pack_weights(const nf_model_desc* desc, const float* const* params, int32_t n_params,
+                    void* packed, int64_t packed_bytes, void* stream) {
+  NfPlan p; if (int rc = plan_of(desc, &p)) return rc;
+  if (!params || !packed) return fail(NF_E_BADARG, "nf_pack_weights: null pointer");
+  if (n_params != nf_param_count(desc)) return fail(NF_E_BADARG, "nf_pack_weights: wrong number of parameter pointers");
+  if (packed_bytes < p.total_bytes) return fail(NF_E_SMALLBUF, "nf_pack_weights: packed buffer too small");
+  if (((uintptr_t)packed & 1023) != 0) return fail(NF_E_BADARG, "nf_pack_weights: packed must be 1024-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* base = (uint8_t*)packed;
+  int pi = 0;
+  for (int m = 0; m < p.n_mlps; ++m) {
+    for (int j = 0; j < p.mlp[m].n_lin; ++j) {
+      const NfLinPlan& L = p.mlp[m].lin[j];
+      const float* W = params[pi++]; const float* b = params[pi++];
+      if (!W || !b) return fail(NF_E_BADARG, "nf_pack_weights: null parameter");
+      cudaError_t e = nf_launch_pack_fp32(W, b, (float*)(base + L.wt_off), (float*)(base + L.b_off), L.n, L.k_hidden + L.k_x0, L.n_pad, st);
+      if (e != cudaSuccess) return cuda_fail(e, "pack fp32");
+      e = nf_launch_pack_fp16(p, m, j, W, b, packed, st);
+      if (e != cudaSuccess) return cuda_fail(e, "pack fp16");
+    }
+  }
+  if (p.enc == NF_ENC_HASH) {
+    const size_t per = (size_t)(p.hash_mask + 1) * 4 * sizeof(float);
+    for (int l = 0; l < p.hash_levels; ++l) {
+      const float* t = params[pi++];
+      if (!t) return fail(NF_E_BADARG, "nf_pack_weights: null hash table");
+      cudaError_t e = cudaMemcpyAsync(base + p.hash_off + l * per, t, per, cudaMemcpyDeviceToDevice, st);
+      if (e != cudaSuccess) return cuda_fail(e, "pack hash tables");
+    }
+  }
+  return 0;
+}
+
+int nf_render_forward(const nf_model_desc* desc, const void* packed, const float* rays, int64_t n_rays,
+                      const float* ts, int32_t T, int64_t ts_ray_stride, const float* density_noise,
+                      float* rgb_out, float* alpha_out, float* weights_out, int32_t precision, void* stream) {
+  NfPlan p; if (int rc = plan_of(desc, &p)) return rc;
+  if (n_rays < 0) return fail(NF_E_BADARG, "n_rays < 0");
+  if (n_rays == 0) return 0;
+  if (!packed || !rays || !ts || !rgb_out) return fail(NF_E_BADARG, "nf_render_forward: null pointer");
+  if (int rc = check_ts(T, ts_ray_stride)) return rc;
+  cudaError_t e;
+  if (precision == NF_PREC_FP32)
+    e = nf_launch_render_fp32(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, rgb_out, alpha_out, weights_out, (cudaStream_t)stream);
+  else if (precision == NF_PREC_FP16_TC)
+    e = nf_launch_render_tc(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, rgb_out, alpha_out, weights_out, (cudaStream_t)stream);
+  else return fail(NF_E_BADARG, "unknown precision");
+  if (e != cudaSuccess) return cuda_fail(e, "nf_render_forward");
+  return 0;
+}
+
+int nf_sample_points(const float* rays, int64_t n_rays, const float* ts, int32_t T, int64_t ts_ray_stride, float* pts_out, void* stream) {
+  if (n_rays < 0) return fail(NF_E_BADARG, "n_rays < 0");
+  if (n_rays == 0) return 0;
+  if (!rays || !ts || !pts_out) return fail(NF_E_BADARG, "nf_sample_points: null pointer");
+  if (int rc = check_ts(T, ts_ray_stride)) return rc;
+  cudaError_t e = nf_launch_sample_points(rays, n_rays, ts, T, ts_ray_stride, pts_out, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nf_sample_points");
+}
+
+int nf_hash_encode(const nf_model_desc* desc, const void* packed, const float* pts, int64_t n, float* feats_out, uint16_t* idx_out, void* stream) {
+  NfPlan p; if (int rc = plan_of(desc, &p)) return rc;
+  if (p.enc != NF_ENC_HASH) return fail(NF_E_BADARG, "nf_hash_encode: model has no hash encoder");
+  if (n < 0) return fail(NF_E_BADARG, "n < 0");
+  if (n == 0) return 0;
+  if (!packed || !pts || !feats_out) return fail(NF_E_BADARG, "nf_hash_encode: null pointer");
+  cudaError_t e = nf_launch_hash_encode(p, packed, pts, n, feats_out, idx_out, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nf_hash_encode");
+}
+
+int nf_composite(const nf_model_desc* desc, const float* sigma_raw, const float* feats, const float* rays, int64_t n_rays,
+                 const float* ts, int32_t T, int64_t ts_ray_stride, float* rgb_out, float* alpha_out, float* weights_out, void* stream) {
+  NfPlan p; if (int rc = plan_of(desc, &p)) return rc;
+  if (n_rays < 0) return fail(NF_E_BADARG, "n_rays < 0");
+  if (n_rays == 0) return 0;
+  if (!sigma_raw || !feats || !rays || !ts || !rgb_out) return fail(NF_E_BADARG, "nf_composite: null pointer");
+  if (int rc = check_ts(T, ts_ray_stride)) return rc;
+  cudaError_t e = nf_launch_composite(p, sigma_raw, feats, rays, n_rays, ts, T, ts_ray_stride, rgb_out, alpha_out, weights_out, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nf_composite");
+}
+
+int nf_mlp_forward(const nf_model_desc* desc, const void* packed, int32_t which, const float* x0, int64_t n, float* out,
+                   int32_t precision, void* stream) {
+  NfPlan p; if (int rc = plan_of(desc, &p)) return rc;
+  if (which < 0 || which >= p.n_mlps) return fail(NF_E_BADARG, "nf_mlp_forward: no such MLP");
+  if (n < 0) return fail(NF_E_BADARG, "n < 0");
+  if (n == 0) return 0;
+  if (!packed || !x0 || !out) return fail(NF_E_BADARG, "nf_mlp_forward: null pointer");
+  cudaError_t e;
+  if (precision == NF_PREC_FP32) e = nf_launch_mlp_fp32(p, which, packed, x0, n, out, (cudaStream_t)stream);
+  else if (precision == NF_PREC_FP16_TC) e = nf_launch_mlp_tc(p, which, packed, x0, n, out, (cudaStream_t)stream);
+  else return fail(NF_E_BADARG, "unknown precision");
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nf_mlp_forward");
+}
+
+}  // extern "C"

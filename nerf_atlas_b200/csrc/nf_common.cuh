@@ -1,0 +1,234 @@
+// nf_common.cuh -- layout plan of the packed parameter blob + device helpers shared by
+// the fp32 and tcgen05 pipelines.  Reference file:line citations are to JulianKnodt/nerf_atlas.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include "../../include/nerf_b200.h"
+
+#define NF_MAX_LIN 10          // init + up to 8 hidden + out
+#define NF_HIDDEN 256
+#define NF_TC_ROWS 128         // samples per tensor-core tile (= UMMA M)
+#define NF_TC_CHUNK_K 32       // K columns per streamed weight chunk (2 UMMA K-steps)
+
+// ---- plan ---------------------------------------------------------------------
+struct NfLinPlan {
+  int32_t k_hidden;   // inputs fed from the previous layer's (activated) output
+  int32_t k_x0;       // inputs fed from x0 (raw for `init`, activated for skip layers)
+  int32_t k0_pad;     // k_x0 rounded up to 16 (tensor path)
+  int32_t n;          // out features
+  int32_t n_pad;      // rounded up to 16
+  int32_t x0_raw;     // 1: x0 is consumed without activation (the `init` Linear)
+  int32_t is_out;     // 1: the `out` Linear (result is NOT activated)
+  int32_t n_chunks;   // tensor path: number of streamed weight chunks
+  int64_t wt_off;     // byte offset: fp32 Wt[k_hidden+k_x0][n_pad], k order = reference column order
+  int64_t b_off;      // byte offset: fp32 bias[n_pad]
+  int64_t w16_off;    // byte offset: fp16 UMMA-canonical image [K_tc/8][n_pad][8], K order = [x0 (k0_pad) | hidden]
+  int64_t b16_off;    // byte offset: fp32 bias[n_pad] in tensor-path column order
+};
+struct NfMlpPlan {
+  int32_t n_lin, in_dims, k0_pad, act, out_dims, pad_;
+  NfLinPlan lin[NF_MAX_LIN];
+};
+struct NfPlan {
+  int32_t kind, n_mlps, intermediate, enc;
+  int32_t hash_levels, hash_mask, density_act, feat_act;
+  int32_t bg, pad_;
+  uint32_t hash_primes[3]; uint32_t pad2_;
+  float hash_res[16];
+  int64_t hash_off;     // byte offset: fp32 [levels][table][4]
+  int64_t total_bytes;
+  NfMlpPlan mlp[2];
+};
+
+__host__ __device__ inline int nf_round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// Builds the plan; returns 0 or an NF_E_* code with *why set.
+static inline int nf_build_plan(const nf_model_desc* d, NfPlan* p, const char** why) {
+  *why = "";
+  if (!d || d->struct_bytes != (int32_t)sizeof(nf_model_desc)) { *why = "bad nf_model_desc (struct_bytes)"; return NF_E_BADARG; }
+  if (d->kind != NF_KIND_PLAIN && d->kind != NF_KIND_TINY) { *why = "unsupported model kind"; return NF_E_UNSUPPORTED; }
+  *p = NfPlan{};
+  p->kind = d->kind; p->n_mlps = (d->kind == NF_KIND_PLAIN) ? 2 : 1;
+  p->intermediate = d->intermediate; p->enc = d->enc;
+  p->density_act = d->density_act; p->feat_act = d->feat_act; p->bg = d->bg;
+  if (d->enc == NF_ENC_HASH) {
+    if (d->hash_feat != 4 || d->hash_levels < 1 || d->hash_levels > 16 ||
+        (d->hash_table_size & (d->hash_table_size - 1)) != 0 || d->hash_table_size < 2) {
+      *why = "hash encoder: need feat==4, 1..16 levels, power-of-two table"; return NF_E_UNSUPPORTED; }
+    p->hash_levels = d->hash_levels; p->hash_mask = d->hash_table_size - 1;
+    for (int i = 0; i < 3; ++i) p->hash_primes[i] = d->hash_primes[i];
+    for (int i = 0; i < 16; ++i) p->hash_res[i] = d->hash_res[i];
+  } else if (d->enc != NF_ENC_NONE) { *why = "unsupported encoder"; return NF_E_UNSUPPORTED; }
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) { int64_t o = off; off += (bytes + 1023) / 1024 * 1024; return o; };
+  if (d->enc == NF_ENC_HASH) p->hash_off = take((int64_t)d->hash_levels * d->hash_table_size * 4 * sizeof(float));
+  for (int m = 0; m < p->n_mlps; ++m) {
+    const nf_mlp_desc& md = m == 0 ? d->density : d->refl;
+    NfMlpPlan& mp = p->mlp[m];
+    if (md.hidden != NF_HIDDEN) { *why = "hidden_size must be 256"; return NF_E_UNSUPPORTED; }
+    if (md.n_layers < 1 || md.n_layers + 2 > NF_MAX_LIN) { *why = "unsupported number of layers"; return NF_E_UNSUPPORTED; }
+    if (md.in_dims < 1 || md.in_dims > 272 || md.out_dims < 1 || md.out_dims > 256 || md.skip < 1) { *why = "unsupported MLP dims"; return NF_E_UNSUPPORTED; }
+    mp.n_lin = md.n_layers + 2; mp.in_dims = md.in_dims; mp.k0_pad = nf_round_up(md.in_dims, 16);
+    mp.act = md.act; mp.out_dims = md.out_dims;
+    for (int j = 0; j < mp.n_lin; ++j) {
+      NfLinPlan& L = mp.lin[j];
+      const bool is_init = j == 0, is_out = j == mp.n_lin - 1;
+      const int i = j - 1;  // index into SkipConnMLP.layers
+      const bool skip = !is_init && !is_out && i != md.n_layers - 1 && (i % md.skip) == 0;
+      L.k_hidden = is_init ? 0 : NF_HIDDEN;
+      L.k_x0 = (is_init || skip) ? md.in_dims : 0;
+      L.k0_pad = L.k_x0 ? mp.k0_pad : 0;
+      L.n = is_out ? md.out_dims : NF_HIDDEN; L.n_pad = nf_round_up(L.n, 16);
+      L.x0_raw = is_init; L.is_out = is_out;
+      const int k_tc = L.k0_pad + L.k_hidden;
+      L.n_chunks = (k_tc + NF_TC_CHUNK_K - 1) / NF_TC_CHUNK_K;
+      L.wt_off = take((int64_t)(L.k_hidden + L.k_x0) * L.n_pad * sizeof(float));
+      L.b_off = take((int64_t)L.n_pad * sizeof(float));
+      L.w16_off = take((int64_t)k_tc * L.n_pad * sizeof(__half));
+      L.b16_off = take((int64_t)L.n_pad * sizeof(float));
+    }
+  }
+  if (d->kind == NF_KIND_PLAIN) {
+    if (d->density.out_dims != 1 + d->intermediate) { *why = "density MLP out must be 1+intermediate"; return NF_E_BADARG; }
+    if (d->refl.in_dims != 5 + d->intermediate || d->refl.out_dims != 3) { *why = "refl MLP must map 5+intermediate -> 3"; return NF_E_BADARG; }
+    const int want = d->enc == NF_ENC_HASH ? 6 + d->hash_levels * 4 : 3;
+    if (d->density.in_dims != want) { *why = "density MLP in_dims does not match the encoder"; return NF_E_BADARG; }
+  } else {
+    if (d->density.in_dims != 3 || d->density.out_dims != 4 || d->enc != NF_ENC_NONE) { *why = "tiny: density MLP must map 3 -> 4 without encoder"; return NF_E_BADARG; }
+  }
+  p->total_bytes = off;
+  return 0;
+}
+
+// ---- tensor-path column orders ---------------------------------------------------------------
+// The tensor path permutes x0 columns (and the density MLP's output columns) so that every
+// producer writes whole 16-byte groups of 8 halves:
+//   density x0 (hash): reference [p(3), p(3), feats(4L)]      -> [feats(4L), p, p]
+//   refl x0          : reference [p(3), elaz(2), inter(I)]    -> [inter(I), p, elaz]
+//   density out      : reference [sigma, inter(I)]            -> [inter(I), sigma]
+__host__ __device__ inline int nf_x0_perm(const NfPlan& p, int m, int k_ref) {
+  if (p.kind == NF_KIND_PLAIN) {
+    if (m == 0 && p.enc == NF_ENC_HASH) { const int nfe = p.hash_levels * 4; return k_ref < 6 ? nfe + k_ref : k_ref - 6; }
+    if (m == 1) return k_ref < 5 ? p.intermediate + k_ref : k_ref - 5;
+  }
+  return k_ref;
+}
+__host__ __device__ inline int nf_out_perm(const NfPlan& p, int m, int n_ref) {
+  if (p.kind == NF_KIND_PLAIN && m == 0) return n_ref == 0 ? p.intermediate : n_ref - 1;
+  return n_ref;
+}
+
+#ifdef __CUDACC__
+// ---- activations --------------------------------------------------------------
+__device__ __forceinline__ float nf_apply_act(float x, int act) {
+  switch (act) {
+    case NF_ACT_LEAKY: return x > 0.f ? x : 0.01f * x;
+    case NF_ACT_SIN:   return sinf(x);
+    case NF_ACT_RELU:  return fmaxf(x, 0.f);
+    default:           return x;
+  }
+}
+__device__ __forceinline__ float nf_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float nf_softplus(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+// sigmoid family, reference src/utils.py:484-518
+__device__ __forceinline__ float nf_feat_act_fn(float v, int kind) {
+  switch (kind) {
+    case NF_FEAT_NORMAL:    return nf_sigmoid(v);
+    case NF_FEAT_THIN:      return nf_sigmoid(v) * (1.f - 2e-2f) + 1e-2f + 1e-2f;  // fat(v,-eps)+eps
+    case NF_FEAT_TANH:      return tanhf(v);
+    case NF_FEAT_CYCLIC:    return (sinf(v / 5.f) + 1.f) / 2.f * (1.f - 2e-2f) + 1e-2f;
+    case NF_FEAT_UPSHIFTED: return nf_sigmoid(v) + 1e-2f;
+    case NF_FEAT_FAT:       return nf_sigmoid(v) * (1.f + 2e-2f) - 1e-2f;
+    case NF_FEAT_LEAKY_RELU:return v > 0.f ? v : 0.01f * v;
+    case NF_FEAT_RELU:      return fmaxf(v, 0.f);
+    case NF_FEAT_SIN:       return sinf(v);
+    case NF_FEAT_UPSHIFTED_SOFTPLUS: return nf_softplus(v) + 1e-2f;
+    case NF_FEAT_UPSHIFTED_RELU:     return fmaxf(v, 0.f) + 1e-2f;
+    default: return v;
+  }
+}
+// raw density -> sigma, reference src/nerf.py:64-65
+__device__ __forceinline__ float nf_density_act_fn(float d, int kind) {
+  return kind == NF_DENS_RELU ? fmaxf(d, 0.f) : nf_softplus(d - 1.f);
+}
+
+// ---- sample position, reference src/nerf.py:54: rounded product, then rounded add (no FMA) ----
+__device__ __forceinline__ float nf_pt(float o, float t, float d) { return __fadd_rn(o, __fmul_rn(t, d)); }
+
+// ---- view direction -> (elev, azim), reference src/utils.py:247-254 ------------------------
+__device__ __forceinline__ void nf_elaz(float dx, float dy, float dz, float& elev, float& azim) {
+  const float nrm = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);  // F.normalize eps
+  const float lim = 1.f - 1e-6f;
+  const float x = fminf(fmaxf(dx / nrm, -lim), lim), y = fminf(fmaxf(dy / nrm, -lim), lim),
+              z = fminf(fmaxf(dz / nrm, -lim), lim);
+  elev = acosf(z); azim = atan2f(y, x);
+}
+
+// ---- hash grid, reference src/neural_blocks.py:139-193 -------------------------------------
+// One level for one point. Corner order = (bx,by,bz) with z the fastest bit (lines 155-165).
+// idx8 (nullable) receives the 8 table rows. Products are rounded separately (no FMA) and the
+// 8 corner terms are summed in corner order, like the reference's stack(...).sum(dim=0).
+__device__ __forceinline__ float4 nf_hash_level(const float4* __restrict__ table, float px, float py, float pz,
+                                                float res, uint32_t p0, uint32_t p1, uint32_t p2, uint32_t mask,
+                                                uint32_t* idx8) {
+  const float vx = __fmul_rn(px, res), vy = __fmul_rn(py, res), vz = __fmul_rn(pz, res);
+  const float fx = floorf(vx), fy = floorf(vy), fz = floorf(vz);
+  const uint32_t ix = (uint32_t)(int32_t)fx, iy = (uint32_t)(int32_t)fy, iz = (uint32_t)(int32_t)fz;
+  const float wx = __fsub_rn(vx, fx), wy = __fsub_rn(vy, fy), wz = __fsub_rn(vz, fz);
+  const float ux = __fsub_rn(1.f, wx), uy = __fsub_rn(1.f, wy), uz = __fsub_rn(1.f, wz);
+  const uint32_t hx0 = ix * p0, hx1 = (ix + 1u) * p0, hy0 = iy * p1, hy1 = (iy + 1u) * p1,
+                 hz0 = iz * p2, hz1 = (iz + 1u) * p2;
+  uint32_t id[8];
+  float w[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int bx = (c >> 2) & 1, by = (c >> 1) & 1, bz = c & 1;
+    id[c] = ((bx ? hx1 : hx0) ^ (by ? hy1 : hy0) ^ (bz ? hz1 : hz0)) & mask;
+    w[c] = __fmul_rn(__fmul_rn(bx ? wx : ux, by ? wy : uy), bz ? wz : uz);
+  }
+  float4 e[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) e[c] = __ldg(table + id[c]);
+  float4 s;
+  s.x = __fmul_rn(e[0].x, w[0]); s.y = __fmul_rn(e[0].y, w[0]); s.z = __fmul_rn(e[0].z, w[0]); s.w = __fmul_rn(e[0].w, w[0]);
+#pragma unroll
+  for (int c = 1; c < 8; ++c) {
+    s.x = __fadd_rn(s.x, __fmul_rn(e[c].x, w[c])); s.y = __fadd_rn(s.y, __fmul_rn(e[c].y, w[c]));
+    s.z = __fadd_rn(s.z, __fmul_rn(e[c].z, w[c])); s.w = __fadd_rn(s.w, __fmul_rn(e[c].w, w[c]));
+  }
+  if (idx8) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) idx8[c] = id[c];
+  }
+  return s;
+}
+
+// ---- compositing step, reference src/nerf.py:60-73 -----------------------------------------
+// delta for sample t of a ray: clamp(ts[t+1]-ts[t], 1e-5) (1e10 for the last) times |r_d|.
+__device__ __forceinline__ float nf_delta(const float* __restrict__ ts_ray, int t, int T, float rd_norm) {
+  const float d = (t == T - 1) ? 1e10f : fmaxf(__fsub_rn(ts_ray[t + 1], ts_ray[t]), 1e-5f);
+  return __fmul_rn(d, rd_norm);
+}
+__device__ __forceinline__ float nf_alpha(float sigma_raw, float delta, int density_act) {
+  const float s = nf_density_act_fn(sigma_raw, density_act);
+  return 1.f - expf(-s * delta);
+}
+
+// ---- tile <-> (ray, t) map -------------------------------------------------------------------
+// A tile is `rows` consecutive samples. T <= rows: rpt = rows/T whole rays per tile.
+// T > rows: a ray spans tpr = ceil(T/rows) consecutive tiles of the same CTA (carry in smem).
+struct NfTileMap {
+  int T, rows, rpt, tpr;
+  __host__ __device__ NfTileMap(int T_, int rows_) : T(T_), rows(rows_) {
+    if (T <= rows) { rpt = rows / T; tpr = 1; } else { rpt = 1; tpr = (T + rows - 1) / rows; }
+  }
+  // number of work units (a unit = one tile of rpt rays, or one whole ray of tpr tiles)
+  __host__ __device__ long long units(long long n_rays) const { return T <= rows ? (n_rays + rpt - 1) / rpt : n_rays; }
+  // row r of sub-tile s of unit u -> ray, t; returns validity
+  __device__ __forceinline__ bool locate(long long u, int s, int r, long long n_rays, long long& ray, int& t) const {
+    if (T <= rows) { const int rl = r / T; ray = u * rpt + rl; t = r - rl * T; return rl < rpt && ray < n_rays; }
+    ray = u; t = s * rows + r; return t < T;
+  }
+};
+#endif  // __CUDACC__

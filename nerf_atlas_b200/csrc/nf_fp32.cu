@@ -1,0 +1,376 @@
+// nf_fp32.cu -- the exact (fp32 CUDA-core) form of the fused render pipeline, plus the
+// stand-alone stage kernels (sample points, hash encode, composite) used by parity tests
+// and HBM-bound micro-benchmarks.  One CTA owns a tile of 64 consecutive samples and keeps
+// every activation in shared memory: rays in, RGB (+ optional alpha/weights) out.
+#include "nf_common.cuh"
+#include "nf_kernels.h"
+
+namespace {
+
+constexpr int ROWS = 64;          // samples per tile
+constexpr int THREADS = 256;      // 16 row-groups (4 rows) x 16 col-groups (16 cols)
+constexpr int X0_MAX = 272;
+
+struct Fp32Smem {
+  float H[2][NF_HIDDEN * ROWS];   // [k][row], ping-pong between layers
+  float X0[X0_MAX * ROWS];        // [k][row], raw inputs of the current MLP
+  float P[3 * ROWS];              // sample positions
+  float sig[ROWS];                // raw density
+  float carry[8];                 // T > ROWS: transmittance, rgb, sum w (before last) carried across sub-tiles
+  long long ray[ROWS];
+  int t[ROWS];
+  int valid[ROWS];
+};
+
+// One Linear of SkipConnMLP (reference src/neural_blocks.py:289-296): Hout = [act?](W [act(Hin), act?(X0)] + b)
+__device__ __forceinline__ void linear_fp32(const NfLinPlan& L, int act, const uint8_t* __restrict__ packed,
+                                            const float* __restrict__ Hin, const float* __restrict__ X0,
+                                            float* __restrict__ Hout) {
+  const int tid = threadIdx.x, cg = tid & 15, rg = tid >> 4;
+  const int n0 = cg * 16, r0 = rg * 4;
+  if (n0 < L.n_pad) {
+    float acc[4][16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[i][j] = 0.f;
+    const float* __restrict__ Wt = reinterpret_cast<const float*>(packed + L.wt_off) + n0;
+    const int np = L.n_pad;
+    auto fma_row = [&](const float4 a, const float* __restrict__ wrow) {
+      float w[16];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(wrow) + q);
+        w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+      }
+      const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[i][j] = fmaf(av[i], w[j], acc[i][j]);
+    };
+#pragma unroll 4
+    for (int k = 0; k < L.k_hidden; ++k)
+      fma_row(*reinterpret_cast<const float4*>(Hin + k * ROWS + r0), Wt + (size_t)k * np);
+    const float* __restrict__ Wx = Wt + (size_t)L.k_hidden * np;
+    for (int k = 0; k < L.k_x0; ++k) {
+      float4 a = *reinterpret_cast<const float4*>(X0 + k * ROWS + r0);
+      if (!L.x0_raw) { a.x = nf_apply_act(a.x, act); a.y = nf_apply_act(a.y, act); a.z = nf_apply_act(a.z, act); a.w = nf_apply_act(a.w, act); }
+      fma_row(a, Wx + (size_t)k * np);
+    }
+    const float* __restrict__ b = reinterpret_cast<const float*>(packed + L.b_off) + n0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float bj = __ldg(b + j);
+      float4 o;
+      o.x = acc[0][j] + bj; o.y = acc[1][j] + bj; o.z = acc[2][j] + bj; o.w = acc[3][j] + bj;
+      if (!L.is_out) { o.x = nf_apply_act(o.x, act); o.y = nf_apply_act(o.y, act); o.z = nf_apply_act(o.z, act); o.w = nf_apply_act(o.w, act); }
+      *reinterpret_cast<float4*>(Hout + (n0 + j) * ROWS + r0) = o;
+    }
+  }
+  __syncthreads();
+}
+
+// Runs every Linear of one MLP; returns the H buffer index holding out[n][row].
+__device__ __forceinline__ int mlp_fp32(const NfMlpPlan& M, const uint8_t* __restrict__ packed, Fp32Smem& s) {
+  int cur = 0;
+  for (int j = 0; j < M.n_lin; ++j) {
+    linear_fp32(M.lin[j], M.act, packed, s.H[cur], s.X0, s.H[cur ^ 1]);
+    cur ^= 1;
+  }
+  return cur;
+}
+
+struct RenderArgs {
+  const uint8_t* packed;
+  const float* rays; long long n_rays;
+  const float* ts; int T; long long ts_stride;
+  const float* noise;
+  float* rgb_out; float* alpha_out; float* weights_out;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+k_render_fp32(const __grid_constant__ NfPlan plan, const RenderArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  Fp32Smem& s = *reinterpret_cast<Fp32Smem*>(smem_raw);
+  const NfTileMap map(a.T, ROWS);
+  const long long units = map.units(a.n_rays);
+  const int tid = threadIdx.x;
+  const int out_ch = 3;
+  for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+    for (int sub = 0; sub < map.tpr; ++sub) {
+      // ---- stage 0: sample positions + encode -> X0 (reference nerf.py:50-55, neural_blocks.py:139-193)
+      {
+        const int row = tid % ROWS, part = tid / ROWS;  // 4 threads per sample, levels interleaved
+        long long ray; int t;
+        const bool ok = map.locate(u, sub, row, a.n_rays, ray, t);
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (ok) {
+          const float* r = a.rays + ray * 6;
+          const float tt = __ldg(a.ts + ray * a.ts_stride + t);
+          px = nf_pt(__ldg(r + 0), tt, __ldg(r + 3)); py = nf_pt(__ldg(r + 1), tt, __ldg(r + 4)); pz = nf_pt(__ldg(r + 2), tt, __ldg(r + 5));
+        }
+        if (part == 0) {
+          s.ray[row] = ray; s.t[row] = t; s.valid[row] = ok;
+          s.P[row] = px; s.P[ROWS + row] = py; s.P[2 * ROWS + row] = pz;
+          s.X0[0 * ROWS + row] = px; s.X0[1 * ROWS + row] = py; s.X0[2 * ROWS + row] = pz;
+          if (plan.enc == NF_ENC_HASH) { s.X0[3 * ROWS + row] = px; s.X0[4 * ROWS + row] = py; s.X0[5 * ROWS + row] = pz; }
+        }
+        if (plan.enc == NF_ENC_HASH) {
+          const float4* tables = reinterpret_cast<const float4*>(a.packed + plan.hash_off);
+          for (int lvl = part; lvl < plan.hash_levels; lvl += THREADS / ROWS) {
+            const float4 f = nf_hash_level(tables + (size_t)lvl * (plan.hash_mask + 1), px, py, pz, plan.hash_res[lvl],
+                                           plan.hash_primes[0], plan.hash_primes[1], plan.hash_primes[2], plan.hash_mask, nullptr);
+            float* x = s.X0 + (6 + lvl * 4) * ROWS + row;
+            x[0] = f.x; x[ROWS] = f.y; x[2 * ROWS] = f.z; x[3 * ROWS] = f.w;
+          }
+        }
+      }
+      __syncthreads();
+      // ---- stage 1: density MLP
+      int ob = mlp_fp32(plan.mlp[0], a.packed, s);
+      const float* rgb_raw;
+      if (plan.kind == NF_KIND_PLAIN) {
+        // ---- glue: sigma_raw, x0 of the View head = [pts, elaz(view), intermediate] (nerf.py:344-358, refl.py:205-207)
+        const float* O = s.H[ob];
+        if (tid < ROWS) {
+          const int row = tid;
+          s.sig[row] = O[row];
+          float el = 0.f, az = 0.f;
+          if (s.valid[row]) { const float* r = a.rays + s.ray[row] * 6; nf_elaz(__ldg(r + 3), __ldg(r + 4), __ldg(r + 5), el, az); }
+          s.X0[0 * ROWS + row] = s.P[row]; s.X0[1 * ROWS + row] = s.P[ROWS + row]; s.X0[2 * ROWS + row] = s.P[2 * ROWS + row];
+          s.X0[3 * ROWS + row] = el; s.X0[4 * ROWS + row] = az;
+        }
+        for (int i = tid; i < plan.intermediate * ROWS; i += THREADS) s.X0[5 * ROWS + i] = O[ROWS + i];
+        __syncthreads();
+        // ---- stage 2: View MLP
+        ob = mlp_fp32(plan.mlp[1], a.packed, s);
+        rgb_raw = s.H[ob];
+      } else {
+        const float* O = s.H[ob];
+        if (tid < ROWS) s.sig[tid] = O[tid];
+        rgb_raw = O + ROWS;
+        __syncthreads();
+      }
+      // ---- stage 3: alpha_from_density + volumetric_integrate (nerf.py:60-80), sequential per ray
+      const int nseg = a.T <= ROWS ? map.rpt : 1;
+      if (tid < nseg) {
+        const int row0 = a.T <= ROWS ? tid * a.T : 0;
+        if (s.valid[row0]) {
+          const long long ray = s.ray[row0];
+          const float* r = a.rays + ray * 6;
+          const float dx = __ldg(r + 3), dy = __ldg(r + 4), dz = __ldg(r + 5);
+          const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
+          const float* tsr = a.ts + ray * a.ts_stride;
+          float trans = 1.f, cr = 0.f, cg = 0.f, cb = 0.f, wsum = 0.f;
+          if (sub > 0) { trans = s.carry[0]; cr = s.carry[1]; cg = s.carry[2]; cb = s.carry[3]; wsum = s.carry[4]; }
+          const int nrow = a.T <= ROWS ? a.T : min(ROWS, a.T - sub * ROWS);
+          for (int i = 0; i < nrow; ++i) {
+            const int row = row0 + i, t = s.t[row];
+            float sr = s.sig[row];
+            if (a.noise) sr += __ldg(a.noise + ray * a.T + t);
+            const float al = nf_alpha(sr, nf_delta(tsr, t, a.T, nrm), plan.density_act);
+            const float w = al * trans;
+            trans *= (1.f - al) + 1e-10f;
+            cr += w * nf_feat_act_fn(rgb_raw[0 * ROWS + row], plan.feat_act);
+            cg += w * nf_feat_act_fn(rgb_raw[1 * ROWS + row], plan.feat_act);
+            cb += w * nf_feat_act_fn(rgb_raw[2 * ROWS + row], plan.feat_act);
+            if (t < a.T - 1) wsum += w;
+            if (a.alpha_out) a.alpha_out[ray * a.T + t] = al;
+            if (a.weights_out) a.weights_out[ray * a.T + t] = w;
+          }
+          if (sub == map.tpr - 1) {
+            const float skyv = plan.bg == NF_BG_WHITE ? 1.f - wsum : 0.f;
+            a.rgb_out[ray * out_ch + 0] = cr + skyv; a.rgb_out[ray * out_ch + 1] = cg + skyv; a.rgb_out[ray * out_ch + 2] = cb + skyv;
+          } else { s.carry[0] = trans; s.carry[1] = cr; s.carry[2] = cg; s.carry[3] = cb; s.carry[4] = wsum; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// Stand-alone SkipConnMLP on assembled inputs x0[N,in] -> out[N,out].
+__global__ void __launch_bounds__(THREADS, 1)
+k_mlp_fp32(const __grid_constant__ NfPlan plan, int which, const uint8_t* __restrict__ packed,
+           const float* __restrict__ x0, long long n, float* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  Fp32Smem& s = *reinterpret_cast<Fp32Smem*>(smem_raw);
+  const NfMlpPlan& M = plan.mlp[which];
+  const long long tiles = (n + ROWS - 1) / ROWS;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    for (int i = threadIdx.x; i < M.in_dims * ROWS; i += THREADS) {
+      const int row = i / M.in_dims, k = i - row * M.in_dims;
+      const long long g = tile * ROWS + row;
+      s.X0[k * ROWS + row] = g < n ? __ldg(x0 + g * M.in_dims + k) : 0.f;
+    }
+    __syncthreads();
+    const int ob = mlp_fp32(M, packed, s);
+    for (int i = threadIdx.x; i < M.out_dims * ROWS; i += THREADS) {
+      const int row = i / M.out_dims, c = i - row * M.out_dims;
+      const long long g = tile * ROWS + row;
+      if (g < n) out[g * M.out_dims + c] = s.H[ob][c * ROWS + row];
+    }
+    __syncthreads();
+  }
+}
+
+// ---- stage kernels ---------------------------------------------------------------------------
+__global__ void k_sample_points(const float* __restrict__ rays, long long n_rays, const float* __restrict__ ts,
+                                int T, long long ts_stride, float* __restrict__ pts) {
+  const long long total = n_rays * T;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long ray = i / T; const int t = (int)(i - ray * T);
+    const float* r = rays + ray * 6;
+    const float tt = __ldg(ts + ray * ts_stride + t);
+    pts[i * 3 + 0] = nf_pt(__ldg(r + 0), tt, __ldg(r + 3));
+    pts[i * 3 + 1] = nf_pt(__ldg(r + 1), tt, __ldg(r + 4));
+    pts[i * 3 + 2] = nf_pt(__ldg(r + 2), tt, __ldg(r + 5));
+  }
+}
+
+__global__ void k_hash_encode(const __grid_constant__ NfPlan plan, const uint8_t* __restrict__ packed,
+                              const float* __restrict__ pts, long long n, float* __restrict__ feats,
+                              uint16_t* __restrict__ idx_out) {
+  const float4* tables = reinterpret_cast<const float4*>(packed + plan.hash_off);
+  const int L = plan.hash_levels;
+  const long long total = n * L;  // one thread per (point, level); level fastest -> coalesced 16 B stores
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / L; const int lvl = (int)(i - p * L);
+    uint32_t id[8];
+    const float4 f = nf_hash_level(tables + (size_t)lvl * (plan.hash_mask + 1), __ldg(pts + p * 3), __ldg(pts + p * 3 + 1),
+                                   __ldg(pts + p * 3 + 2), plan.hash_res[lvl], plan.hash_primes[0], plan.hash_primes[1],
+                                   plan.hash_primes[2], plan.hash_mask, id);
+    reinterpret_cast<float4*>(feats)[i] = f;
+    if (idx_out) for (int c = 0; c < 8; ++c) idx_out[((size_t)lvl * 8 + c) * n + p] = (uint16_t)id[c];
+  }
+}
+
+// Warp per ray; lanes own consecutive samples in chunks of 32; running transmittance is a
+// warp-shuffle multiplicative scan (the stand-alone form of the fused tail). HBM-bound:
+// reads 16 B/sample (sigma + rgb), writes 8 B/sample when alpha/weights are requested.
+__global__ void k_composite(int density_act, int feat_unused, int bg, const float* __restrict__ sigma_raw,
+                            const float* __restrict__ feats, const float* __restrict__ rays, long long n_rays,
+                            const float* __restrict__ ts, int T, long long ts_stride,
+                            float* __restrict__ rgb_out, float* __restrict__ alpha_out, float* __restrict__ weights_out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long ray = warp; ray < n_rays; ray += nwarps) {
+    const float* r = rays + ray * 6;
+    const float dx = __ldg(r + 3), dy = __ldg(r + 4), dz = __ldg(r + 5);
+    const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
+    const float* tsr = ts + ray * ts_stride;
+    float carry = 1.f, cr = 0.f, cg = 0.f, cb = 0.f, wsum = 0.f;
+    for (int base = 0; base < T; base += 32) {
+      const int t = base + lane;
+      float al = 0.f, fr = 0.f, fg = 0.f, fb = 0.f;
+      if (t < T) {
+        al = nf_alpha(__ldg(sigma_raw + ray * T + t), nf_delta(tsr, t, T, nrm), density_act);
+        const float* f = feats + (ray * T + t) * 3;
+        fr = __ldg(f); fg = __ldg(f + 1); fb = __ldg(f + 2);
+      }
+      float p = t < T ? (1.f - al) + 1e-10f : 1.f;   // inclusive product scan of (1 - alpha + 1e-10)
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const float q = __shfl_up_sync(0xffffffffu, p, d); if (lane >= d) p *= q; }
+      float excl = __shfl_up_sync(0xffffffffu, p, 1); if (lane == 0) excl = 1.f;
+      const float w = al * (carry * excl);
+      carry *= __shfl_sync(0xffffffffu, p, 31);
+      if (t < T) {
+        if (alpha_out) alpha_out[ray * T + t] = al;
+        if (weights_out) weights_out[ray * T + t] = w;
+        cr += w * fr; cg += w * fg; cb += w * fb;
+        if (t < T - 1) wsum += w;
+      }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      cr += __shfl_xor_sync(0xffffffffu, cr, d); cg += __shfl_xor_sync(0xffffffffu, cg, d);
+      cb += __shfl_xor_sync(0xffffffffu, cb, d); wsum += __shfl_xor_sync(0xffffffffu, wsum, d);
+    }
+    if (lane == 0) {
+      const float skyv = bg == NF_BG_WHITE ? 1.f - wsum : 0.f;
+      rgb_out[ray * 3 + 0] = cr + skyv; rgb_out[ray * 3 + 1] = cg + skyv; rgb_out[ray * 3 + 2] = cb + skyv;
+    }
+  }
+}
+
+// ---- packing -----------------------------------------------------------------------------------
+// W[n][k] (nn.Linear, row-major) -> Wt[k][n_pad] fp32, zero padded.
+__global__ void k_pack_fp32(const float* __restrict__ W, const float* __restrict__ b, float* __restrict__ Wt,
+                            float* __restrict__ bp, int n, int k, int n_pad) {
+  const int total = k * n_pad;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int kk = i / n_pad, nn = i - kk * n_pad;
+    Wt[i] = nn < n ? W[(size_t)nn * k + kk] : 0.f;
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) bp[i] = i < n ? b[i] : 0.f;
+}
+
+int num_sms() {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
+}  // namespace
+
+// ---- launchers (called from nf_api.cu) -------------------------------------------------------
+cudaError_t nf_launch_pack_fp32(const float* W, const float* b, float* Wt, float* bp, int n, int k, int n_pad, cudaStream_t st) {
+  const int total = k * n_pad;
+  k_pack_fp32<<<(total + 255) / 256, 256, 0, st>>>(W, b, Wt, bp, n, k, n_pad);
+  return cudaGetLastError();
+}
+
+cudaError_t nf_launch_render_fp32(const NfPlan& plan, const void* packed, const float* rays, int64_t n_rays, const float* ts,
+                                  int T, int64_t ts_stride, const float* noise, float* rgb, float* alpha, float* weights,
+                                  cudaStream_t st) {
+  static_assert(sizeof(Fp32Smem) <= 227 * 1024, "fp32 pipeline smem");
+  cudaError_t e = cudaFuncSetAttribute(k_render_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Fp32Smem));
+  if (e != cudaSuccess) return e;
+  const NfTileMap map(T, ROWS);
+  const long long units = map.units(n_rays);
+  if (units == 0) return cudaSuccess;
+  const int grid = (int)(units < num_sms() ? units : num_sms());
+  RenderArgs a{(const uint8_t*)packed, rays, n_rays, ts, T, ts_stride, noise, rgb, alpha, weights};
+  k_render_fp32<<<grid, THREADS, sizeof(Fp32Smem), st>>>(plan, a);
+  return cudaGetLastError();
+}
+
+cudaError_t nf_launch_mlp_fp32(const NfPlan& plan, int which, const void* packed, const float* x0, int64_t n, float* out, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(k_mlp_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Fp32Smem));
+  if (e != cudaSuccess) return e;
+  const long long tiles = (n + ROWS - 1) / ROWS;
+  if (tiles == 0) return cudaSuccess;
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  k_mlp_fp32<<<grid, THREADS, sizeof(Fp32Smem), st>>>(plan, which, (const uint8_t*)packed, x0, n, out);
+  return cudaGetLastError();
+}
+
+cudaError_t nf_launch_sample_points(const float* rays, int64_t n_rays, const float* ts, int T, int64_t ts_stride, float* pts, cudaStream_t st) {
+  const long long total = n_rays * T;
+  if (total == 0) return cudaSuccess;
+  const long long want = (total + 255) / 256;
+  const int grid = (int)(want < (long long)num_sms() * 8 ? want : (long long)num_sms() * 8);
+  k_sample_points<<<grid, 256, 0, st>>>(rays, n_rays, ts, T, ts_stride, pts);
+  return cudaGetLastError();
+}
+
+cudaError_t nf_launch_hash_encode(const NfPlan& plan, const void* packed, const float* pts, int64_t n, float* feats, uint16_t* idx, cudaStream_t st) {
+  const long long total = n * plan.hash_levels;
+  if (total == 0) return cudaSuccess;
+  const long long want = (total + 255) / 256;
+  const int grid = (int)(want < (long long)num_sms() * 8 ? want : (long long)num_sms() * 8);
+  k_hash_encode<<<grid, 256, 0, st>>>(plan, (const uint8_t*)packed, pts, n, feats, idx);
+  return cudaGetLastError();
+}
+
+cudaError_t nf_launch_composite(const NfPlan& plan, const float* sigma_raw, const float* feats, const float* rays, int64_t n_rays,
+                                const float* ts, int T, int64_t ts_stride, float* rgb, float* alpha, float* weights, cudaStream_t st) {
+  if (n_rays == 0) return cudaSuccess;
+  const long long want = (n_rays * 32 + 255) / 256;
+  const int grid = (int)(want < (long long)num_sms() * 8 ? want : (long long)num_sms() * 8);
+  k_composite<<<grid, 256, 0, st>>>(plan.density_act, 0, plan.bg, sigma_raw, feats, rays, n_rays, ts, T, ts_stride, rgb, alpha, weights);
+  return cudaGetLastError();
+}

@@ -1,0 +1,18 @@
+// nf_kernels.h -- launchers implemented in nf_fp32.cu / nf_tc.cu, called from nf_api.cu.
+#pragma once
+#include "nf_common.cuh"
+
+cudaError_t nf_launch_pack_fp32(const float* W, const float* b, float* Wt, float* bp, int n, int k, int n_pad, cudaStream_t st);
+cudaError_t nf_launch_pack_fp16(const NfPlan& plan, int m, int j, const float* W, const float* b, void* packed, cudaStream_t st);
+cudaError_t nf_launch_render_fp32(const NfPlan& plan, const void* packed, const float* rays, int64_t n_rays, const float* ts,
+                                  int T, int64_t ts_stride, const float* noise, float* rgb, float* alpha, float* weights,
+                                  cudaStream_t st);
+cudaError_t nf_launch_render_tc(const NfPlan& plan, const void* packed, const float* rays, int64_t n_rays, const float* ts,
+                                int T, int64_t ts_stride, const float* noise, float* rgb, float* alpha, float* weights,
+                                cudaStream_t st);
+cudaError_t nf_launch_mlp_fp32(const NfPlan& plan, int which, const void* packed, const float* x0, int64_t n, float* out, cudaStream_t st);
+cudaError_t nf_launch_mlp_tc(const NfPlan& plan, int which, const void* packed, const float* x0, int64_t n, float* out, cudaStream_t st);
+cudaError_t nf_launch_sample_points(const float* rays, int64_t n_rays, const float* ts, int T, int64_t ts_stride, float* pts, cudaStream_t st);
+cudaError_t nf_launch_hash_encode(const NfPlan& plan, const void* packed, const float* pts, int64_t n, float* feats, uint16_t* idx, cudaStream_t st);
+cudaError_t nf_launch_composite(const NfPlan& plan, const float* sigma_raw, const float* feats, const float* rays, int64_t n_rays,
+                                const float* ts, int T, int64_t ts_stride, float* rgb, float* alpha, float* weights, cudaStream_t st);

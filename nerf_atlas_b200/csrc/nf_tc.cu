@@ -1,0 +1,595 @@
+// nf_tc.cu -- the Blackwell (sm_100a) tensor-core form of the fused render pipeline.
+//
+// One persistent CTA per SM owns tiles of 128 consecutive samples (UMMA M = 128).  Per tile:
+//   sample positions -> hash-grid encode -> SkipConnMLP (density) -> SkipConnMLP (View) ->
+//   alpha composite, with nothing but rays in and RGB (+ optional alpha/weights) out.
+// Every Linear is a tcgen05.mma (kind::f16, fp16 operands, fp32 accumulators in TMEM):
+//   A = activations [128 x K] in shared memory, UMMA-canonical K-major no-swizzle layout
+//       [K/8][128 rows][8 halves] (16-byte cores; written conflict-free by the epilogue warps),
+//   B = weights [N x K], pre-packed on the device by nf_pack_weights into the same canonical
+//       layout and streamed from L2 by the bulk-copy engine (cp.async.bulk = TMA 1-D) through
+//       a 6-stage mbarrier ring,
+//   D = [128 x N] fp32 in TMEM, two 256-column accumulators used alternately by consecutive
+//       layers so that layer j+1's MMAs start on the K-chunks of layer j's output as soon as the
+//       epilogue has written them (chunk-granular h_ready barriers).
+// Warp roles: 0 = weight producer, 1 = MMA issuer (one thread), 2 = TMEM allocator,
+// 4..11 = encode/epilogue warps (TMEM lane quarter = warp % 4, column half = (warp-4)/4).
+#include <cstdio>
+#include "nf_common.cuh"
+#include "nf_kernels.h"
+
+namespace {
+
+constexpr int ROWS = NF_TC_ROWS;          // 128
+constexpr int X0K = 80;                   // max padded x0 width on this path
+constexpr int STAGES = 6;
+constexpr int STAGE_BYTES = NF_TC_CHUNK_K * 256 * 2;   // 16 KB: 32 K-columns x 256 N x fp16
+constexpr int MAX_LIN_TOTAL = 12;
+constexpr int THREADS = 384;
+constexpr int EPI_THREADS = 256;
+constexpr int KG_BYTES = ROWS * 16;       // one 8-column K-group of an A operand: 128 rows x 16 B
+
+struct TcSmem {
+  uint8_t H[ROWS * 256 * 2];
+  uint8_t X0raw[ROWS * X0K * 2];
+  uint8_t X0act[ROWS * X0K * 2];
+  uint8_t W[STAGES][STAGE_BYTES];
+  float bias[MAX_LIN_TOTAL * 256];
+  float P[3 * ROWS];
+  float sig[ROWS], delta[ROWS], el[ROWS], az[ROWS];
+  float wrgb[ROWS * 4];
+  long long ray[ROWS];
+  int t[ROWS];
+  int valid[ROWS];
+  float warp_agg[4]; int warp_cont[4]; float warp_sum[4][4]; float carry[8];
+  unsigned long long w_full[STAGES], w_empty[STAGES], acc_full[2], h_ready[4], x0_ready;
+  uint32_t tmem_base;
+};
+static_assert(sizeof(TcSmem) <= 227 * 1024, "tensor pipeline smem");
+
+struct TcArgs {
+  const uint8_t* packed;
+  const float* rays; long long n_rays;
+  const float* ts; int T; long long ts_stride;
+  const float* noise;
+  float* rgb_out; float* alpha_out; float* weights_out;
+  // MLP-only mode
+  int mlp_only; int which; const float* x0; long long n; float* out;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) { printf("nf_tc: mbarrier timeout (block %d thread %d bar %u)\n", blockIdx.x, threadIdx.x, bar); __trap(); }
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// K-major, no-swizzle UMMA shared-memory descriptor: 8x16-byte core matrices; LBO = byte distance
+// between the two K-adjacent cores of one K=16 step, SBO = byte distance between 8-row groups.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=n.
+__device__ __forceinline__ uint32_t umma_idesc(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+               ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+               : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float tc_act(float x, int act) {
+  switch (act) {
+    case NF_ACT_LEAKY: return fmaxf(x, 0.01f * x);
+    case NF_ACT_SIN:   return __sinf(x);
+    case NF_ACT_RELU:  return fmaxf(x, 0.f);
+    default:           return x;
+  }
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ void st_v4(uint8_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d);
+}
+
+// ---- the sequence of tiles a CTA walks (identical in every warp role) ---------------------------
+struct TileIter {
+  long long units; int tpr;
+  __device__ TileIter(const TcArgs& a, const NfTileMap& map) {
+    if (a.mlp_only) { units = (a.n + ROWS - 1) / ROWS; tpr = 1; } else { units = map.units(a.n_rays); tpr = map.tpr; }
+  }
+};
+
+// ---- composite of one tile by the 4 column-half-0 epilogue warps (thread = row) ----------------
+// reference src/nerf.py:60-80. Running transmittance = segmented warp-shuffle product scan,
+// stitched across the 4 warps (and across sub-tiles of a ray longer than 128 samples) in smem.
+__device__ __forceinline__ void composite_tile(TcSmem& s, const NfPlan& plan, const TcArgs& a, const NfTileMap& map,
+                                               int sub, int row, int lane, int q, float cr, float cg, float cb) {
+  const bool valid = s.valid[row] != 0;
+  const int t = valid ? s.t[row] : 0;
+  const long long ray = s.ray[row];
+  float al = 0.f;
+  if (valid) {
+    float sr = s.sig[row];
+    if (a.noise) sr += __ldg(a.noise + ray * a.T + t);
+    al = nf_alpha(sr, s.delta[row], plan.density_act);
+  }
+  float incl = valid ? (1.f - al) + 1e-10f : 1.f;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const float o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d && t >= d) incl *= o;
+  }
+  float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+  if (lane == 0 || t == 0) excl = 1.f;
+  if (lane == 31) { s.warp_agg[q] = incl; s.warp_cont[q] = t > 31; }
+  named_bar(2, 128);
+  float c = 1.f; bool open = true;
+  for (int v = q - 1; v >= 0 && open; --v) { c *= s.warp_agg[v]; open = s.warp_cont[v] != 0; }
+  if (open && sub > 0) c *= s.carry[0];
+  const float trans = excl * (t > lane ? c : 1.f);
+  const float w = al * trans;
+  if (valid) {
+    if (a.alpha_out) a.alpha_out[ray * a.T + t] = al;
+    if (a.weights_out) a.weights_out[ray * a.T + t] = w;
+  }
+  const float wr = w * cr, wg = w * cg, wb = w * cb, wl = (valid && t < a.T - 1) ? w : 0.f;
+  const int row_thread = q * 32 + lane;   // 0..127
+  if ((a.T & 31) == 0) {
+    float x0 = wr, x1 = wg, x2 = wb, x3 = wl;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      x0 += __shfl_xor_sync(0xffffffffu, x0, d); x1 += __shfl_xor_sync(0xffffffffu, x1, d);
+      x2 += __shfl_xor_sync(0xffffffffu, x2, d); x3 += __shfl_xor_sync(0xffffffffu, x3, d);
+    }
+    if (lane == 0) { s.warp_sum[q][0] = x0; s.warp_sum[q][1] = x1; s.warp_sum[q][2] = x2; s.warp_sum[q][3] = x3; }
+    named_bar(2, 128);
+    const int wpr = a.T <= ROWS ? a.T / 32 : 4;          // warps per ray (segment) inside this tile
+    const int nseg = a.T <= ROWS ? map.rpt : 1;
+    if (row_thread < nseg && s.valid[row_thread * (a.T <= ROWS ? a.T : 0)]) {
+      float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+      if (sub > 0) { o0 = s.carry[1]; o1 = s.carry[2]; o2 = s.carry[3]; o3 = s.carry[4]; }
+      for (int v = 0; v < wpr; ++v) {
+        const float* ws = s.warp_sum[row_thread * wpr + v];
+        o0 += ws[0]; o1 += ws[1]; o2 += ws[2]; o3 += ws[3];
+      }
+      const long long r = s.ray[row_thread * (a.T <= ROWS ? a.T : 0)];
+      if (sub == map.tpr - 1) {
+        const float skyv = plan.bg == NF_BG_WHITE ? 1.f - o3 : 0.f;
+        a.rgb_out[r * 3 + 0] = o0 + skyv; a.rgb_out[r * 3 + 1] = o1 + skyv; a.rgb_out[r * 3 + 2] = o2 + skyv;
+      } else {
+        s.carry[1] = o0; s.carry[2] = o1; s.carry[3] = o2; s.carry[4] = o3;
+        s.carry[0] = (sub > 0 ? s.carry[0] : 1.f) * s.warp_agg[0] * s.warp_agg[1] * s.warp_agg[2] * s.warp_agg[3];
+      }
+    }
+  } else {
+    float* wq = s.wrgb + row_thread * 4;
+    wq[0] = wr; wq[1] = wg; wq[2] = wb; wq[3] = wl;
+    named_bar(2, 128);
+    const int nseg = a.T <= ROWS ? map.rpt : 1;
+    const int row0 = a.T <= ROWS ? row_thread * a.T : 0;
+    if (row_thread < nseg && s.valid[row0]) {
+      float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+      if (sub > 0) { o0 = s.carry[1]; o1 = s.carry[2]; o2 = s.carry[3]; o3 = s.carry[4]; }
+      const int nrow = a.T <= ROWS ? a.T : min(ROWS, a.T - sub * ROWS);
+      for (int i = 0; i < nrow; ++i) { const float* x = s.wrgb + (row0 + i) * 4; o0 += x[0]; o1 += x[1]; o2 += x[2]; o3 += x[3]; }
+      const long long r = s.ray[row0];
+      if (sub == map.tpr - 1) {
+        const float skyv = plan.bg == NF_BG_WHITE ? 1.f - o3 : 0.f;
+        a.rgb_out[r * 3 + 0] = o0 + skyv; a.rgb_out[r * 3 + 1] = o1 + skyv; a.rgb_out[r * 3 + 2] = o2 + skyv;
+      } else {
+        s.carry[1] = o0; s.carry[2] = o1; s.carry[3] = o2; s.carry[4] = o3;
+        s.carry[0] = (sub > 0 ? s.carry[0] : 1.f) * s.warp_agg[0] * s.warp_agg[1] * s.warp_agg[2] * s.warp_agg[3];
+      }
+    }
+  }
+}
+
+// =================================================================================================
+__global__ void __launch_bounds__(THREADS, 1)
+k_render_tc(const __grid_constant__ NfPlan plan, const TcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  TcSmem& s = *reinterpret_cast<TcSmem*>(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const NfTileMap map(a.mlp_only ? ROWS : a.T, ROWS);
+  const TileIter it(a, map);
+  const int m_begin = a.mlp_only ? a.which : 0, m_end = a.mlp_only ? a.which + 1 : plan.n_mlps;
+  const int lin_base1 = plan.mlp[0].n_lin;   // global linear index of refl MLP's first Linear
+
+  // ---- one-time setup ----
+  for (int i = threadIdx.x; i < MAX_LIN_TOTAL * 256; i += THREADS) {
+    const int g = i >> 8, n = i & 255;
+    const int m = g >= lin_base1 ? 1 : 0, j = g - (m ? lin_base1 : 0);
+    float v = 0.f;
+    if (m < plan.n_mlps && j < plan.mlp[m].n_lin && n < plan.mlp[m].lin[j].n_pad)
+      v = __ldg(reinterpret_cast<const float*>(a.packed + plan.mlp[m].lin[j].b16_off) + n);
+    s.bias[i] = v;
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(smem_u32(&s.w_full[i]), 1); mbar_init(smem_u32(&s.w_empty[i]), 1); }
+    mbar_init(smem_u32(&s.acc_full[0]), 1); mbar_init(smem_u32(&s.acc_full[1]), 1);
+    for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&s.h_ready[i]), 8);
+    mbar_init(smem_u32(&s.x0_ready), 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s.tmem_base;
+
+  if (warp == 0) {
+    // ================= weight producer: stream every Linear's chunks through the ring =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (long long u = blockIdx.x; u < it.units; u += gridDim.x)
+        for (int sub = 0; sub < it.tpr; ++sub)
+          for (int m = m_begin; m < m_end; ++m)
+            for (int j = 0; j < plan.mlp[m].n_lin; ++j) {
+              const NfLinPlan& L = plan.mlp[m].lin[j];
+              const int steps = (L.k0_pad + L.k_hidden) >> 4;
+              const uint8_t* src = a.packed + L.w16_off;
+              for (int c = 0; c < L.n_chunks; ++c) {
+                const int nst = min(2, steps - 2 * c);
+                const uint32_t bytes = (uint32_t)nst * 2u * (uint32_t)L.n_pad * 16u;
+                mbar_wait(smem_u32(&s.w_empty[stage]), phase ^ 1);
+                mbar_expect_tx(smem_u32(&s.w_full[stage]), bytes);
+                bulk_g2s(smem_u32(s.W[stage]), src + (size_t)c * 4 * L.n_pad * 16, bytes, smem_u32(&s.w_full[stage]));
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+              }
+            }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer: one thread issues every tcgen05.mma of the CTA =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      uint32_t h_par = 0, x0_par = 0;     // expected parities of h_ready[0..3], x0_ready
+      uint32_t lin_count = 0;
+      const uint32_t Hs = smem_u32(s.H), Xr = smem_u32(s.X0raw), Xa = smem_u32(s.X0act);
+      for (long long u = blockIdx.x; u < it.units; u += gridDim.x)
+        for (int sub = 0; sub < it.tpr; ++sub)
+          for (int m = m_begin; m < m_end; ++m) {
+            bool x0_waited = false;
+            for (int j = 0; j < plan.mlp[m].n_lin; ++j, ++lin_count) {
+              const NfLinPlan& L = plan.mlp[m].lin[j];
+              const int steps = (L.k0_pad + L.k_hidden) >> 4;
+              const uint32_t d_tmem = tmem_base + (lin_count & 1) * 256;
+              const uint32_t idesc = umma_idesc(L.n_pad);
+              const uint32_t b_lbo = (uint32_t)L.n_pad * 16u;
+              uint32_t h_waited = 0;
+              int step = 0;
+              for (int c = 0; c < L.n_chunks; ++c) {
+                mbar_wait(smem_u32(&s.w_full[stage]), phase);
+                const int nst = min(2, steps - 2 * c);
+                for (int s2 = 0; s2 < nst; ++s2, ++step) {
+                  const int k = step << 4;
+                  uint32_t a_addr;
+                  if (k < L.k0_pad) {
+                    if (!x0_waited) { mbar_wait(smem_u32(&s.x0_ready), x0_par); x0_par ^= 1; x0_waited = true; }
+                    a_addr = (L.x0_raw ? Xr : Xa) + (uint32_t)(k >> 3) * KG_BYTES;
+                  } else {
+                    const int kh = k - L.k0_pad, hc = kh >> 6;
+                    if (!(h_waited & (1u << hc))) {
+                      mbar_wait(smem_u32(&s.h_ready[hc]), (h_par >> hc) & 1u);
+                      h_par ^= 1u << hc; h_waited |= 1u << hc;
+                    }
+                    a_addr = Hs + (uint32_t)(kh >> 3) * KG_BYTES;
+                  }
+                  tc_fence_after();
+                  const uint32_t b_addr = smem_u32(s.W[stage]) + (uint32_t)s2 * 2u * b_lbo;
+                  umma_f16(d_tmem, umma_desc(a_addr, KG_BYTES, 128), umma_desc(b_addr, b_lbo, 128), idesc, step > 0);
+                }
+                umma_commit(smem_u32(&s.w_empty[stage]));
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+              }
+              umma_commit(smem_u32(&s.acc_full[lin_count & 1]));
+            }
+          }
+    }
+  } else if (warp >= 4) {
+    // ================= encode + epilogue warps =================
+    const int ew = warp - 4, q = warp & 3, half = ew >> 2;
+    const int e_tid = ew * 32 + lane;
+    const int row = q * 32 + lane;                       // TMEM lane == tile row owned in epilogues
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t acc_par = 0, lin_count = 0;
+    for (long long u = blockIdx.x; u < it.units; u += gridDim.x)
+      for (int sub = 0; sub < it.tpr; ++sub) {
+        // ---------- stage inputs of the first MLP ----------
+        if (a.mlp_only) {
+          const NfMlpPlan& M = plan.mlp[a.which];
+          for (int i = e_tid; i < (M.k0_pad >> 3) * ROWS; i += EPI_THREADS) {
+            st_v4(s.X0raw + i * 16, 0, 0, 0, 0); st_v4(s.X0act + i * 16, 0, 0, 0, 0);
+          }
+          named_bar(1, EPI_THREADS);
+          for (int i = e_tid; i < M.in_dims * ROWS; i += EPI_THREADS) {
+            const int r = i / M.in_dims, k = i - r * M.in_dims;
+            const long long g = u * ROWS + r;
+            const float v = g < a.n ? __ldg(a.x0 + g * M.in_dims + k) : 0.f;
+            const int kt = nf_x0_perm(plan, a.which, k);
+            const int off = (kt >> 3) * KG_BYTES + r * 16 + (kt & 7) * 2;
+            *reinterpret_cast<__half*>(s.X0raw + off) = __float2half_rn(v);
+            *reinterpret_cast<__half*>(s.X0act + off) = __float2half_rn(tc_act(v, M.act));
+          }
+        } else {
+          const int r = e_tid & (ROWS - 1), part = e_tid >> 7;
+          long long ray; int t;
+          const bool ok = map.locate(u, sub, r, a.n_rays, ray, t);
+          float px = 0.f, py = 0.f, pz = 0.f, dx = 0.f, dy = 0.f, dz = 1.f;
+          if (ok) {
+            const float* rr = a.rays + ray * 6;
+            const float tt = __ldg(a.ts + ray * a.ts_stride + t);
+            dx = __ldg(rr + 3); dy = __ldg(rr + 4); dz = __ldg(rr + 5);
+            px = nf_pt(__ldg(rr + 0), tt, dx); py = nf_pt(__ldg(rr + 1), tt, dy); pz = nf_pt(__ldg(rr + 2), tt, dz);
+          }
+          const int act0 = plan.mlp[0].act;
+          int kg = 0;   // first K-group after the encoder features
+          if (plan.enc == NF_ENC_HASH) {
+            const float4* tables = reinterpret_cast<const float4*>(a.packed + plan.hash_off);
+            for (int lvl = part; lvl < plan.hash_levels; lvl += 2) {
+              const float4 f = nf_hash_level(tables + (size_t)lvl * (plan.hash_mask + 1), px, py, pz, plan.hash_res[lvl],
+                                             plan.hash_primes[0], plan.hash_primes[1], plan.hash_primes[2], plan.hash_mask, nullptr);
+              const int off = (lvl >> 1) * KG_BYTES + r * 16 + (lvl & 1) * 8;
+              *reinterpret_cast<uint2*>(s.X0raw + off) = make_uint2(pack_h2(f.x, f.y), pack_h2(f.z, f.w));
+              *reinterpret_cast<uint2*>(s.X0act + off) = make_uint2(pack_h2(tc_act(f.x, act0), tc_act(f.y, act0)),
+                                                                    pack_h2(tc_act(f.z, act0), tc_act(f.w, act0)));
+            }
+            kg = plan.hash_levels >> 1;
+          }
+          if (part == 0) {
+            const float ax = tc_act(px, act0), ay = tc_act(py, act0), az_ = tc_act(pz, act0);
+            if (plan.enc == NF_ENC_HASH) {   // [p, p, 0, 0]
+              st_v4(s.X0raw + kg * KG_BYTES + r * 16, pack_h2(px, py), pack_h2(pz, px), pack_h2(py, pz), 0);
+              st_v4(s.X0act + kg * KG_BYTES + r * 16, pack_h2(ax, ay), pack_h2(az_, ax), pack_h2(ay, az_), 0);
+            } else {                          // [p, 0...]
+              st_v4(s.X0raw + kg * KG_BYTES + r * 16, pack_h2(px, py), pack_h2(pz, 0.f), 0, 0);
+              st_v4(s.X0act + kg * KG_BYTES + r * 16, pack_h2(ax, ay), pack_h2(az_, 0.f), 0, 0);
+            }
+            for (int g = kg + 1; g < (plan.mlp[0].k0_pad >> 3); ++g) {
+              st_v4(s.X0raw + g * KG_BYTES + r * 16, 0, 0, 0, 0); st_v4(s.X0act + g * KG_BYTES + r * 16, 0, 0, 0, 0);
+            }
+            s.P[r] = px; s.P[ROWS + r] = py; s.P[2 * ROWS + r] = pz;
+            s.ray[r] = ray; s.t[r] = t; s.valid[r] = ok ? 1 : 0;
+          } else {
+            float el = 0.f, az = 0.f, dl = 0.f;
+            if (ok) {
+              nf_elaz(dx, dy, dz, el, az);
+              dl = nf_delta(a.ts + ray * a.ts_stride, t, a.T, sqrtf(dx * dx + dy * dy + dz * dz));
+            }
+            s.el[r] = el; s.az[r] = az; s.delta[r] = dl;
+          }
+        }
+        fence_proxy_async();
+        named_bar(1, EPI_THREADS);
+        if (lane == 0) mbar_arrive(smem_u32(&s.x0_ready));
+
+        // ---------- the MLPs ----------
+        for (int m = m_begin; m < m_end; ++m) {
+          const NfMlpPlan& M = plan.mlp[m];
+          const int act = M.act;
+          for (int j = 0; j < M.n_lin; ++j, ++lin_count) {
+            const NfLinPlan& L = M.lin[j];
+            const uint32_t buf = lin_count & 1;
+            const float* bias = s.bias + ((m ? lin_base1 : 0) + j) * 256;
+            mbar_wait(smem_u32(&s.acc_full[buf]), (acc_par >> buf) & 1u);
+            acc_par ^= 1u << buf;
+            tc_fence_after();
+            const uint32_t t_acc = t_lane + buf * 256;
+            if (!L.is_out) {
+              // hidden Linear: H <- act(acc + bias) as fp16, chunk by chunk (64 columns = one h_ready)
+              for (int c = 0; c < 4; ++c) {
+                const int col = c * 64 + half * 32;
+                uint32_t v[32];
+                tmem_ld16(t_acc + col, v); tmem_ld16(t_acc + col + 16, v + 16);
+                tmem_ld_wait();
+                uint32_t o[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const float x0 = __uint_as_float(v[2 * i]) + bias[col + 2 * i];
+                  const float x1 = __uint_as_float(v[2 * i + 1]) + bias[col + 2 * i + 1];
+                  o[i] = pack_h2(tc_act(x0, act), tc_act(x1, act));
+                }
+                uint8_t* dst = s.H + (col >> 3) * KG_BYTES + row * 16;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) st_v4(dst + g * KG_BYTES, o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+                tc_fence_before();
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&s.h_ready[c]));
+              }
+            } else if (a.mlp_only) {
+              // dump raw outputs in reference column order
+              const long long g = u * ROWS + row;
+              for (int un = half; un < (L.n_pad >> 4); un += 2) {
+                uint32_t v[16];
+                tmem_ld16(t_acc + un * 16, v); tmem_ld_wait();
+                if (g < a.n) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) {
+                    const int nt = un * 16 + i;
+                    int nr = nt;
+                    if (plan.kind == NF_KIND_PLAIN && m == 0) nr = nt == plan.intermediate ? 0 : nt + 1;
+                    if (nr < L.n) a.out[g * L.n + nr] = __uint_as_float(v[i]) + bias[nt];
+                  }
+                }
+              }
+              tc_fence_before();
+            } else if (plan.kind == NF_KIND_PLAIN && m == 0) {
+              // density MLP out (tensor order [inter(I), sigma]): x0 of the View head + raw density
+              const int act1 = plan.mlp[1].act;
+              const int iu = plan.intermediate >> 4;       // 16-column units of intermediate
+              for (int un = half; un <= iu; un += 2) {
+                uint32_t v[16];
+                tmem_ld16(t_acc + un * 16, v); tmem_ld_wait();
+                if (un < iu) {
+                  uint32_t o[8], oa[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const float x0 = __uint_as_float(v[2 * i]) + bias[un * 16 + 2 * i];
+                    const float x1 = __uint_as_float(v[2 * i + 1]) + bias[un * 16 + 2 * i + 1];
+                    o[i] = pack_h2(x0, x1); oa[i] = pack_h2(tc_act(x0, act1), tc_act(x1, act1));
+                  }
+                  uint8_t* d0 = s.X0raw + (un * 2) * KG_BYTES + row * 16; uint8_t* d1 = s.X0act + (un * 2) * KG_BYTES + row * 16;
+                  st_v4(d0, o[0], o[1], o[2], o[3]); st_v4(d0 + KG_BYTES, o[4], o[5], o[6], o[7]);
+                  st_v4(d1, oa[0], oa[1], oa[2], oa[3]); st_v4(d1 + KG_BYTES, oa[4], oa[5], oa[6], oa[7]);
+                } else {
+                  s.sig[row] = __uint_as_float(v[0]) + bias[plan.intermediate];
+                  const float px = s.P[row], py = s.P[ROWS + row], pz = s.P[2 * ROWS + row], el = s.el[row], az = s.az[row];
+                  uint8_t* d0 = s.X0raw + (iu * 2) * KG_BYTES + row * 16; uint8_t* d1 = s.X0act + (iu * 2) * KG_BYTES + row * 16;
+                  st_v4(d0, pack_h2(px, py), pack_h2(pz, el), pack_h2(az, 0.f), 0);
+                  st_v4(d1, pack_h2(tc_act(px, act1), tc_act(py, act1)), pack_h2(tc_act(pz, act1), tc_act(el, act1)),
+                        pack_h2(tc_act(az, act1), 0.f), 0);
+                  st_v4(d0 + KG_BYTES, 0, 0, 0, 0); st_v4(d1 + KG_BYTES, 0, 0, 0, 0);
+                }
+              }
+              tc_fence_before();
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(smem_u32(&s.x0_ready));
+            } else {
+              // final Linear of the path -> colours (and raw density for TinyNeRF) -> composite
+              if (half == 0) {
+                uint32_t v[16];
+                tmem_ld16(t_acc, v); tmem_ld_wait();
+                tc_fence_before();
+                float cr, cg, cb;
+                if (plan.kind == NF_KIND_TINY) {
+                  s.sig[row] = __uint_as_float(v[0]) + bias[0];
+                  cr = __uint_as_float(v[1]) + bias[1]; cg = __uint_as_float(v[2]) + bias[2]; cb = __uint_as_float(v[3]) + bias[3];
+                } else {
+                  cr = __uint_as_float(v[0]) + bias[0]; cg = __uint_as_float(v[1]) + bias[1]; cb = __uint_as_float(v[2]) + bias[2];
+                }
+                cr = nf_feat_act_fn(cr, plan.feat_act); cg = nf_feat_act_fn(cg, plan.feat_act); cb = nf_feat_act_fn(cb, plan.feat_act);
+                composite_tile(s, plan, a, map, sub, row, lane, q, cr, cg, cb);
+              }
+            }
+          }
+        }
+        named_bar(1, EPI_THREADS);   // tile-private smem (sig/delta/ray/...) is free for the next tile
+      }
+  }
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ---- packing: nn.Linear W[n][k] -> fp16 UMMA-canonical image [K_tc/8][n_pad][8] + bias in tensor order ----
+__global__ void k_pack_fp16(const __grid_constant__ NfPlan plan, int m, int j, const float* __restrict__ W,
+                            const float* __restrict__ b, uint8_t* __restrict__ packed) {
+  const NfLinPlan& L = plan.mlp[m].lin[j];
+  const int k_ref_total = L.k_hidden + L.k_x0;
+  __half* img = reinterpret_cast<__half*>(packed + L.w16_off);
+  float* b16 = reinterpret_cast<float*>(packed + L.b16_off);
+  const int total = L.n * k_ref_total;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int n_ref = i / k_ref_total, k_ref = i - n_ref * k_ref_total;
+    const int k_tc = k_ref < L.k_hidden ? L.k0_pad + k_ref : nf_x0_perm(plan, m, k_ref - L.k_hidden);
+    const int n_tc = L.is_out ? nf_out_perm(plan, m, n_ref) : n_ref;
+    img[(size_t)(k_tc >> 3) * (L.n_pad * 8) + n_tc * 8 + (k_tc & 7)] = __float2half_rn(W[i]);
+  }
+  for (int n_ref = blockIdx.x * blockDim.x + threadIdx.x; n_ref < L.n; n_ref += gridDim.x * blockDim.x)
+    b16[L.is_out ? nf_out_perm(plan, m, n_ref) : n_ref] = b[n_ref];
+}
+
+int tc_num_sms() {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
+// nullptr if the tensor path can run this model, else the reason.
+const char* tc_unsupported(const NfPlan& p) {
+  int total = 0;
+  for (int m = 0; m < p.n_mlps; ++m) { total += p.mlp[m].n_lin; if (p.mlp[m].k0_pad > X0K) return "x0 wider than 80 columns"; }
+  if (total > MAX_LIN_TOTAL) return "more than 12 Linear layers";
+  if (p.enc == NF_ENC_HASH && (p.hash_levels & 1)) return "odd number of hash levels";
+  if (p.kind == NF_KIND_PLAIN && (p.intermediate & 15)) return "intermediate_size not a multiple of 16";
+  return nullptr;
+}
+
+cudaError_t launch_tc(const NfPlan& plan, const TcArgs& a, long long units, cudaStream_t st) {
+  if (tc_unsupported(plan)) return cudaErrorNotSupported;
+  cudaError_t e = cudaFuncSetAttribute(k_render_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcSmem));
+  if (e != cudaSuccess) return e;
+  if (units == 0) return cudaSuccess;
+  const int grid = (int)(units < tc_num_sms() ? units : tc_num_sms());
+  k_render_tc<<<grid, THREADS, sizeof(TcSmem), st>>>(plan, a);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t nf_launch_pack_fp16(const NfPlan& plan, int m, int j, const float* W, const float* b, void* packed, cudaStream_t st) {
+  const NfLinPlan& L = plan.mlp[m].lin[j];
+  cudaError_t e = cudaMemsetAsync((uint8_t*)packed + L.w16_off, 0, (size_t)(L.k0_pad + L.k_hidden) * L.n_pad * sizeof(__half), st);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync((uint8_t*)packed + L.b16_off, 0, (size_t)L.n_pad * sizeof(float), st);
+  if (e != cudaSuccess) return e;
+  const int total = L.n * (L.k_hidden + L.k_x0);
+  k_pack_fp16<<<(total + 255) / 256, 256, 0, st>>>(plan, m, j, W, b, (uint8_t*)packed);
+  return cudaGetLastError();
+}
+
+cudaError_t nf_launch_render_tc(const NfPlan& plan, const void* packed, const float* rays, int64_t n_rays, const float* ts,
+                                int T, int64_t ts_stride, const float* noise, float* rgb, float* alpha, float* weights,
+                                cudaStream_t st) {
+  TcArgs a{};
+  a.packed = (const uint8_t*)packed; a.rays = rays; a.n_rays = n_rays; a.ts = ts; a.T = T; a.ts_stride = ts_stride;
+  a.noise = noise; a.rgb_out = rgb; a.alpha_out = alpha; a.weights_out = weights; a.mlp_only = 0;
+  const NfTileMap map(T, ROWS);
+  return launch_tc(plan, a, map.units(n_rays), st);
+}
+
+cudaError_t nf_launch_mlp_tc(const NfPlan& plan, int which, const void* packed, const float* x0, int64_t n, float* out, cudaStream_t st) {
+  TcArgs a{};
+  a.packed = (const uint8_t*)packed; a.mlp_only = 1; a.which = which; a.x0 = x0; a.n = n; a.out = out; a.T = ROWS;
+  return launch_tc(plan, a, (n + ROWS - 1) / ROWS, st);
+}

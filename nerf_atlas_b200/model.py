@@ -1,0 +1,399 @@
+"""Host-side mirror of the reference's NeRF forward surface over the C ABI.
+
+``FusedPlainNeRF`` / ``FusedTinyNeRF`` are ``nn.Module``s that ``runner.py`` can use in place of
+``src.nerf.PlainNeRF`` / ``TinyNeRF`` (reference src/nerf.py:278-361): same constructor keywords,
+``forward(rays[B,H,W,6]) -> rgb[B,H,W,3]``, ``from_pts`` is intentionally absent (the fused
+pipeline never materialises ``pts``), and the attributes the runner reads or writes afterwards
+(SURVEY.md section 8b): ``steps/t_near/t_far``, ``ts``, ``alpha``, ``weights``, ``nerf``, ``refl``,
+``intermediate_size``, ``set_bg``, ``set_sigmoid``, ``set_refl``, ``total_latent_size``.
+Parameters keep the reference's ``state_dict`` names, so checkpoints interchange.
+
+The module owns ordinary ``nn.Parameter``s; the CUDA side only ever sees a packed snapshot that
+is refreshed when a parameter's ``data_ptr``/``_version`` changes (``RenderEngine.pack``).
+There is no PyTorch or CPU fallback: without the built library or a CUDA device, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import ModelDesc, MlpDesc
+
+HASH_PRIMES = [1, 2654435761, 805459861, 3674653429, 2097192037, 1434869437, 2165219737]
+
+
+# ------------------------------------------------------------------------------------------------
+# descriptors
+# ------------------------------------------------------------------------------------------------
+def _hash_res(levels: int, low: int = 16, high: int = 1 << 14) -> List[float]:
+  # operator precedence of reference src/neural_blocks.py:126-128: exp((ln hi - ln lo)/levels - 1)
+  scale = math.exp((math.log(high) - math.log(low)) / levels - 1)
+  return [float(np.float32(low * (scale ** i))) for i in range(levels)]
+
+
+def _mlp(in_dims, n_layers, out_dims, act, skip=3, hidden=256) -> MlpDesc:
+  return MlpDesc(in_dims, hidden, n_layers, out_dims, skip, _lib.ACT[act])
+
+
+def describe_plain(intermediate: int = 64, sigmoid: str = "upshifted", bg: str = "black",
+                   hash_levels: int = 8, hash_table: int = 1 << 16) -> ModelDesc:
+  """PlainNeRF + View head as built by runner.load_model (reference src/nerf.py:310-324,
+  src/refl.py:190-204, runner.py:1182-1183)."""
+  d = ModelDesc()
+  d.struct_bytes = C.sizeof(ModelDesc)
+  d.kind = _lib.KIND["plain"]
+  d.density = _mlp(6 + 4 * hash_levels, 4, 1 + intermediate, "leaky_relu")
+  d.refl = _mlp(5 + intermediate, 4, 3, "sin")
+  d.intermediate = intermediate
+  d.enc = _lib.ENC["hash"]
+  d.hash_levels, d.hash_table_size, d.hash_feat = hash_levels, hash_table, 4
+  for i in range(3): d.hash_primes[i] = HASH_PRIMES[i] & 0xFFFFFFFF
+  for i, r in enumerate(_hash_res(hash_levels)): d.hash_res[i] = r
+  d.density_act = _lib.DENSITY["softplus"]
+  d.feat_act = _lib.FEAT[sigmoid]
+  d.bg = _lib.BG[bg]
+  return d
+
+
+def describe_tiny(sigmoid: str = "upshifted", bg: str = "black") -> ModelDesc:
+  """TinyNeRF (reference src/nerf.py:278-305), intended semantics."""
+  d = ModelDesc()
+  d.struct_bytes = C.sizeof(ModelDesc)
+  d.kind = _lib.KIND["tiny"]
+  d.density = _mlp(3, 6, 4, "leaky_relu")
+  d.refl = _mlp(0, 0, 0, "none")
+  d.enc = _lib.ENC["none"]
+  d.density_act = _lib.DENSITY["softplus"]
+  d.feat_act = _lib.FEAT[sigmoid]
+  d.bg = _lib.BG[bg]
+  return d
+
+
+# ------------------------------------------------------------------------------------------------
+# low-level engine: descriptor + packed blob + calls
+# ------------------------------------------------------------------------------------------------
+def _ptr(t: Optional[torch.Tensor]):
+  return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _chk(t: torch.Tensor, name: str, dtype=torch.float32):
+  if not t.is_cuda: raise RuntimeError(f"{name} must be a CUDA tensor (no CPU fallback)")
+  if t.dtype != dtype: raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+  if not t.is_contiguous(): raise ValueError(f"{name} must be contiguous")
+  return t
+
+
+class RenderEngine:
+  """Thin object over the C ABI for one model description on one device."""
+
+  def __init__(self, desc: ModelDesc, precision: str = "fp16"):
+    self.desc = desc
+    self.precision = precision
+    self.lib = _lib.lib()
+    n = self.lib.nf_param_count(C.byref(desc))
+    if n < 0: _lib.check(n, "nf_param_count")
+    self.n_params = n
+    self.packed_bytes = int(self.lib.nf_packed_bytes(C.byref(desc)))
+    if self.packed_bytes < 0: _lib.check(self.packed_bytes, "nf_packed_bytes")
+    self.packed: Optional[torch.Tensor] = None
+    self._key = None
+
+  @staticmethod
+  def _stream(): return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+  def pack(self, params: Sequence[torch.Tensor], force: bool = False):
+    """Snapshot live parameters (order documented at nf_param_count) if anything changed."""
+    if len(params) != self.n_params: raise ValueError(f"expected {self.n_params} parameter tensors, got {len(params)}")
+    key = tuple((p.data_ptr(), p._version, p.device) for p in params)
+    if not force and key == self._key and self.packed is not None: return False
+    dev = params[0].device
+    for i, p in enumerate(params): _chk(p, f"param[{i}]")
+    if self.packed is None or self.packed.device != dev:
+      raw = torch.empty(self.packed_bytes + 1024, dtype=torch.uint8, device=dev)
+      off = (-raw.data_ptr()) % 1024
+      self.packed = raw[off:off + self.packed_bytes]
+      self._raw = raw
+    arr = (C.c_void_p * len(params))(*[p.data_ptr() for p in params])
+    with torch.cuda.device(dev):
+      rc = self.lib.nf_pack_weights(C.byref(self.desc), arr, len(params), _ptr(self.packed), self.packed_bytes, self._stream())
+    _lib.check(rc, "nf_pack_weights")
+    self._key = key
+    return True
+
+  def _need_packed(self):
+    if self.packed is None: raise RuntimeError("RenderEngine.pack(params) has not been called")
+
+  def render(self, rays: torch.Tensor, ts: torch.Tensor, density_noise: Optional[torch.Tensor] = None,
+             want_weights: bool = True, precision: Optional[str] = None):
+    """rays[R,6], ts[T] (shared) or ts[R,T] (per ray) -> rgb[R,3], alpha[R,T]|None, weights[R,T]|None."""
+    self._need_packed()
+    _chk(rays, "rays"); _chk(ts, "ts")
+    if rays.dim() != 2 or rays.shape[1] != 6: raise ValueError("rays must be [R,6]")
+    R = rays.shape[0]
+    if ts.dim() == 1: T, stride = ts.shape[0], 0
+    elif ts.dim() == 2 and ts.shape[0] == R: T, stride = ts.shape[1], ts.shape[1]
+    else: raise ValueError("ts must be [T] or [R,T]")
+    if density_noise is not None:
+      _chk(density_noise, "density_noise")
+      if tuple(density_noise.shape) != (R, T): raise ValueError("density_noise must be [R,T]")
+    rgb = torch.empty(R, 3, dtype=torch.float32, device=rays.device)
+    alpha = torch.empty(R, T, dtype=torch.float32, device=rays.device) if want_weights else None
+    weights = torch.empty(R, T, dtype=torch.float32, device=rays.device) if want_weights else None
+    with torch.cuda.device(rays.device):
+      rc = self.lib.nf_render_forward(C.byref(self.desc), _ptr(self.packed), _ptr(rays), R, _ptr(ts), T, stride,
+                                      _ptr(density_noise), _ptr(rgb), _ptr(alpha), _ptr(weights),
+                                      _lib.PRECISION[precision or self.precision], self._stream())
+    _lib.check(rc, "nf_render_forward")
+    return rgb, alpha, weights
+
+  # ---- stage entry points (parity tests, micro-benchmarks) ----
+  def sample_points(self, rays: torch.Tensor, ts: torch.Tensor) -> torch.Tensor:
+    _chk(rays, "rays"); _chk(ts, "ts")
+    R = rays.shape[0]
+    T, stride = (ts.shape[0], 0) if ts.dim() == 1 else (ts.shape[1], ts.shape[1])
+    pts = torch.empty(R, T, 3, dtype=torch.float32, device=rays.device)
+    with torch.cuda.device(rays.device):
+      rc = self.lib.nf_sample_points(_ptr(rays), R, _ptr(ts), T, stride, _ptr(pts), self._stream())
+    _lib.check(rc, "nf_sample_points")
+    return pts
+
+  def hash_encode(self, pts: torch.Tensor, want_indices: bool = False):
+    self._need_packed(); _chk(pts, "pts")
+    n, L = pts.shape[0], self.desc.hash_levels
+    feats = torch.empty(n, L * 4, dtype=torch.float32, device=pts.device)
+    idx = torch.empty(L, 8, n, dtype=torch.uint16, device=pts.device) if want_indices else None
+    with torch.cuda.device(pts.device):
+      rc = self.lib.nf_hash_encode(C.byref(self.desc), _ptr(self.packed), _ptr(pts), n, _ptr(feats), _ptr(idx), self._stream())
+    _lib.check(rc, "nf_hash_encode")
+    return feats, idx
+
+  def composite(self, sigma_raw: torch.Tensor, feats: torch.Tensor, rays: torch.Tensor, ts: torch.Tensor, want_weights: bool = True):
+    _chk(sigma_raw, "sigma_raw"); _chk(feats, "feats"); _chk(rays, "rays"); _chk(ts, "ts")
+    R, T = sigma_raw.shape
+    stride = 0 if ts.dim() == 1 else T
+    rgb = torch.empty(R, 3, dtype=torch.float32, device=rays.device)
+    alpha = torch.empty(R, T, dtype=torch.float32, device=rays.device) if want_weights else None
+    weights = torch.empty(R, T, dtype=torch.float32, device=rays.device) if want_weights else None
+    with torch.cuda.device(rays.device):
+      rc = self.lib.nf_composite(C.byref(self.desc), _ptr(sigma_raw), _ptr(feats), _ptr(rays), R, _ptr(ts), T, stride,
+                                 _ptr(rgb), _ptr(alpha), _ptr(weights), self._stream())
+    _lib.check(rc, "nf_composite")
+    return rgb, alpha, weights
+
+  def mlp_forward(self, which: int, x0: torch.Tensor, precision: Optional[str] = None) -> torch.Tensor:
+    self._need_packed(); _chk(x0, "x0")
+    md = self.desc.density if which == 0 else self.desc.refl
+    if x0.dim() != 2 or x0.shape[1] != md.in_dims: raise ValueError(f"x0 must be [N,{md.in_dims}]")
+    out = torch.empty(x0.shape[0], md.out_dims, dtype=torch.float32, device=x0.device)
+    with torch.cuda.device(x0.device):
+      rc = self.lib.nf_mlp_forward(C.byref(self.desc), _ptr(self.packed), which, _ptr(x0), x0.shape[0], _ptr(out),
+                                   _lib.PRECISION[precision or self.precision], self._stream())
+    _lib.check(rc, "nf_mlp_forward")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter containers with the reference's state_dict names
+# ------------------------------------------------------------------------------------------------
+class HashParams(nn.Module):
+  """Parameters of HashEncoder (reference src/neural_blocks.py:92-131)."""
+  def __init__(self, levels: int = 8, emb_size: int = 1 << 16, feat_size: int = 4):
+    super().__init__()
+    self.register_buffer("primes", torch.tensor(HASH_PRIMES), persistent=True)
+    self.embs = nn.ModuleList([nn.Embedding(emb_size, feat_size) for _ in range(levels)])
+    self.levels, self.emb_size, self.feat_size = levels, emb_size, feat_size
+
+
+class SkipConnParams(nn.Module):
+  """Parameters (and init kinds) of SkipConnMLP (reference src/neural_blocks.py:204-277)."""
+  def __init__(self, in_dims: int, out: int, num_layers: int, hidden_size: int = 256, skip: int = 3,
+               init: Optional[str] = None, enc: Optional[nn.Module] = None):
+    super().__init__()
+    self.enc = enc
+    self.dim_p, self.skip = in_dims, skip
+    self.init = nn.Linear(in_dims, hidden_size)
+    self.layers = nn.ModuleList([
+      nn.Linear(hidden_size + in_dims if (i % skip) == 0 and i != num_layers - 1 else hidden_size, hidden_size)
+      for i in range(num_layers)])
+    self.out = nn.Linear(hidden_size, out)
+    ws = [self.init.weight, self.out.weight, *[l.weight for l in self.layers]]
+    bs = [self.init.bias, self.out.bias, *[l.bias for l in self.layers]]
+    if init == "xavier":
+      for t in ws: nn.init.xavier_uniform_(t)
+      for t in bs: nn.init.zeros_(t)
+    elif init == "siren":
+      for t in ws:
+        fan_in, _ = nn.init._calculate_fan_in_and_fan_out(t)
+        a = math.sqrt(6 / fan_in)
+        nn.init._no_grad_uniform_(t, -a, a)
+      for t in bs: nn.init.zeros_(t)
+    elif init is not None: raise NotImplementedError(init)
+
+  def linears(self) -> List[nn.Linear]: return [self.init, *self.layers, self.out]
+
+
+def _linears_of(mlp) -> List[nn.Module]:
+  """Works for SkipConnParams and for the reference's own SkipConnMLP (duck-typed)."""
+  return [mlp.init, *list(mlp.layers), mlp.out]
+
+
+class ViewHead(nn.Module):
+  """Parameters of refl.View (reference src/refl.py:190-207); ``act`` is a sigmoid-kind name."""
+  def __init__(self, latent_size: int, out_features: int = 3, act: str = "thin"):
+    super().__init__()
+    self.latent_size, self.out_features = latent_size, out_features
+    self.act = act
+    self.mlp = SkipConnParams(5 + latent_size, out_features, 4, init="siren")
+
+
+_ACT_NAMES = {"sigmoid": "normal", "thin_sigmoid": "thin", "tanh": "tanh", "cyclic_sigmoid": "cyclic",
+              "upshifted_sigmoid": "upshifted", "fat_sigmoid": "fat", "leaky_relu": "leaky_relu", "relu": "relu",
+              "sin": "sin", "upshifted_softplus": "upshifted_softplus", "upshifted_relu": "upshifted_relu"}
+
+
+def _sigmoid_name(act) -> str:
+  if isinstance(act, str): return act
+  name = getattr(act, "__name__", None)
+  if name in _ACT_NAMES: return _ACT_NAMES[name]
+  raise NotImplementedError(f"feature activation {act!r} is not supported by the fused path")
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference-facing modules
+# ------------------------------------------------------------------------------------------------
+class FusedNeRF(nn.Module):
+  """Common part (mirrors CommonNeRF, reference src/nerf.py:147-276)."""
+  kind = "plain"
+
+  def __init__(self, steps: int = 64, t_near: float = 0, t_far: float = 1, intermediate_size: int = 32,
+               sigmoid_kind: str = "thin", bg: str = "black", precision: str = "fp16", keep_weights: bool = True,
+               **unused):
+    super().__init__()
+    for k in ("mip", "per_pixel_latent_size", "per_point_latent_size", "instance_latent_size"):
+      if unused.get(k): raise NotImplementedError(f"{k} is not supported by the fused path yet")
+    self.empty_latent = nn.Parameter(torch.zeros(1, 1, 1, 1, 0, dtype=torch.float), requires_grad=False)
+    self.t_near, self.t_far, self.steps = t_near, t_far, steps
+    self.intermediate_size = intermediate_size
+    self.noise_std = 0.2                                    # reference src/nerf.py:197
+    self.precision, self.keep_weights = precision, keep_weights
+    self.sigmoid_kind, self.bg = sigmoid_kind, bg
+    self.alpha = self.weights = self.ts = None
+    self._engine: Optional[RenderEngine] = None
+    self._engine_key = None
+
+  # ---- surface the runner touches ----
+  @property
+  def nerf(self): return self
+  def total_latent_size(self) -> int: return 0
+  def set_bg(self, bg="black"):
+    if bg not in _lib.BG: raise NotImplementedError(bg)
+    self.bg = bg
+  def set_sigmoid(self, kind="thin"):
+    if kind not in _lib.FEAT: raise NotImplementedError(f"Unknown sigmoid kind({kind})")
+    self.sigmoid_kind = kind
+    if hasattr(self, "refl"): self.refl.act = kind
+  def set_refl(self, refl):
+    if hasattr(self, "refl"): self.refl = refl
+
+  # ---- pickling: never carry the ctypes handle / packed blob (checkpoint = torch.save(model)) ----
+  def __getstate__(self):
+    st = self.__dict__.copy(); st["_engine"] = None; st["_engine_key"] = None
+    st["alpha"] = st["weights"] = st["ts"] = None
+    return st
+
+  # ---- implemented by subclasses ----
+  def _describe(self) -> ModelDesc: raise NotImplementedError
+  def _param_list(self) -> List[torch.Tensor]: raise NotImplementedError
+
+  def engine(self) -> RenderEngine:
+    key = (self.kind, self.sigmoid_kind if not hasattr(self, "refl") else _sigmoid_name(self.refl.act), self.bg, self.precision)
+    if self._engine is None or self._engine_key != key:
+      self._engine, self._engine_key = RenderEngine(self._describe(), self.precision), key
+    return self._engine
+
+  def forward(self, rays: torch.Tensor) -> torch.Tensor:
+    if not rays.is_cuda: raise RuntimeError("FusedNeRF.forward needs CUDA rays: the fused path has no CPU fallback")
+    if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
+      raise NotImplementedError("backward of the fused pipeline is not built yet (SURVEY.md f-1); "
+                                "call under torch.no_grad() / model.eval()")
+    B = rays.shape[:-1]
+    flat = rays.reshape(-1, 6).to(torch.float32).contiguous()
+    # reference src/nerf.py:29-47 -- linspace on the rays' device; jitter with ONE rand[T] for all rays
+    ts = torch.linspace(self.t_near, self.t_far, steps=self.steps, device=rays.device, dtype=torch.float32)
+    noise = None
+    if self.training:
+      mids = 0.5 * (ts[:-1] + ts[1:])
+      lower, upper = torch.cat([mids, ts[-1:]]), torch.cat([ts[:1], mids])
+      ts = lower + (upper - lower) * torch.rand_like(lower)
+      if self.noise_std > 0 and self.kind == "plain":       # reference src/nerf.py:347-348
+        noise = torch.randn(flat.shape[0], self.steps, device=rays.device) * self.noise_std
+    eng = self.engine()
+    eng.pack(self._param_list())
+    rgb, alpha, weights = eng.render(flat, ts, noise, want_weights=self.keep_weights)
+    self.ts = ts
+    if self.keep_weights:   # the reference keeps [T,B,H,W]; these are transposed views of the [R,T] buffers
+      self.alpha = alpha.reshape(*B, self.steps).movedim(-1, 0)
+      self.weights = weights.reshape(*B, self.steps).movedim(-1, 0)
+    return rgb.reshape(*B, 3)
+
+
+class FusedPlainNeRF(FusedNeRF):
+  """Drop-in for PlainNeRF + View (reference src/nerf.py:310-361)."""
+  kind = "plain"
+
+  def __init__(self, out_features: int = 3, **kwargs):
+    kwargs.setdefault("sigmoid_kind", "thin")
+    super().__init__(**kwargs)
+    if out_features != 3: raise NotImplementedError("out_features != 3")
+    self.refl = ViewHead(latent_size=self.intermediate_size, out_features=out_features, act=self.sigmoid_kind)
+    self.first = SkipConnParams(38, 1 + self.intermediate_size, 4, enc=HashParams())
+
+  @classmethod
+  def from_reference(cls, ref, precision: str = "fp16", keep_weights: bool = True) -> "FusedPlainNeRF":
+    """Adopt a live reference PlainNeRF: its ``first`` and ``refl`` sub-modules become ours, so
+    parameters (and optimiser references to them) are shared, not copied."""
+    self = cls.__new__(cls)
+    FusedNeRF.__init__(self, steps=ref.steps, t_near=ref.t_near, t_far=ref.t_far, intermediate_size=ref.intermediate_size,
+                       sigmoid_kind=_sigmoid_name(ref.refl.act), precision=precision, keep_weights=keep_weights)
+    bg = [k for k, v in {"black": "black", "white": "white"}.items() if getattr(ref.sky_color, "__name__", "") == v]
+    if not bg: raise NotImplementedError("background kind of the reference model")
+    self.bg = bg[0]
+    if type(ref.refl).__name__ not in ("View", "ViewHead"): raise NotImplementedError(f"refl head {type(ref.refl).__name__}")
+    if getattr(ref, "mip", None) is not None: raise NotImplementedError("mip")
+    self.refl, self.first = ref.refl, ref.first
+    return self
+
+  def _describe(self) -> ModelDesc:
+    enc = self.first.enc
+    levels = len(enc.embs)
+    return describe_plain(self.intermediate_size, _sigmoid_name(self.refl.act), self.bg, levels, enc.embs[0].weight.shape[0])
+
+  def _param_list(self) -> List[torch.Tensor]:
+    ps: List[torch.Tensor] = []
+    for mlp in (self.first, self.refl.mlp):
+      for lin in _linears_of(mlp): ps += [lin.weight, lin.bias]
+    ps += [e.weight for e in self.first.enc.embs]
+    return ps
+
+
+class FusedTinyNeRF(FusedNeRF):
+  """Drop-in for TinyNeRF with the intended density semantics (reference src/nerf.py:278-305)."""
+  kind = "tiny"
+
+  def __init__(self, out_features: int = 3, **kwargs):
+    kwargs.setdefault("sigmoid_kind", "thin")
+    super().__init__(**kwargs)
+    if out_features != 3: raise NotImplementedError("out_features != 3")
+    self.estim = SkipConnParams(3, 1 + out_features, 6, init="xavier")
+
+  def _describe(self) -> ModelDesc: return describe_tiny(self.sigmoid_kind, self.bg)
+  def _param_list(self) -> List[torch.Tensor]:
+    ps: List[torch.Tensor] = []
+    for lin in _linears_of(self.estim): ps += [lin.weight, lin.bias]
+    return ps

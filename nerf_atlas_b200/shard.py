@@ -1,0 +1,56 @@
+"""Ray sharding across the GPUs of one box.
+
+Rays are independent, so the render path shards with NO data-path collective: rank g renders the
+contiguous block ``[g*R/G, (g+1)*R/G)`` of the flattened ``[B,H,W]`` ray grid with replicated
+parameters.  The only (optional) communication is an all-gather of the 12 B/ray RGB result when
+one rank needs the whole frame.  The reference's counterpart is ``nn.DataParallel`` scatter/gather
+along dim 0 (reference runner.py:1207-1209), which is single-process and broken at HEAD.
+One process per GPU; ``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests) is plumbing only.
+"""
+from __future__ import annotations
+from typing import Callable, Optional, Tuple
+import torch
+import torch.distributed as dist
+
+
+def shard_rays(n_rays: int, rank: int, world: int, align: int = 1) -> Tuple[int, int]:
+  """Contiguous block of rank ``rank``; boundaries are multiples of ``align`` (e.g. the image width,
+  so that shards are whole pixel rows).  Blocks differ by at most ``align`` rays and cover [0, n_rays)."""
+  if not (0 <= rank < world): raise ValueError("rank out of range")
+  if align < 1: raise ValueError("align must be >= 1")
+  units = (n_rays + align - 1) // align
+  base, rem = divmod(units, world)
+  u0 = rank * base + min(rank, rem)
+  u1 = u0 + base + (1 if rank < rem else 0)
+  return min(u0 * align, n_rays), min(u1 * align, n_rays)
+
+
+class ShardedRenderer:
+  """Wraps ``render_fn(rays[r,6]) -> rgb[r,C]`` so that every rank renders only its block.
+
+  ``gather=True`` returns the full ``[R,C]`` result on every rank (all-gather of padded blocks);
+  ``gather=False`` returns the local block and its ``(start, end)``.
+  """
+  def __init__(self, render_fn: Callable[[torch.Tensor], torch.Tensor], group: Optional[dist.ProcessGroup] = None,
+               gather: bool = True, align: int = 1):
+    self.render_fn, self.group, self.gather, self.align = render_fn, group, gather, align
+
+  def _world(self):
+    if dist.is_available() and dist.is_initialized():
+      return dist.get_rank(self.group), dist.get_world_size(self.group)
+    return 0, 1
+
+  def __call__(self, rays: torch.Tensor):
+    rank, world = self._world()
+    R = rays.shape[0]
+    s, e = shard_rays(R, rank, world, self.align)
+    local = self.render_fn(rays[s:e].contiguous())
+    if not self.gather: return local, (s, e)
+    if world == 1: return local
+    bounds = [shard_rays(R, r, world, self.align) for r in range(world)]
+    longest = max(b[1] - b[0] for b in bounds)
+    pad = torch.zeros(longest, local.shape[1], dtype=local.dtype, device=local.device)
+    pad[: e - s] = local
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=self.group)
+    return torch.cat([p[: b[1] - b[0]] for p, b in zip(parts, bounds)], dim=0)

@@ -1,0 +1,54 @@
+"""Shared helpers for the parity tests (CUDA path through the C ABI vs the CPU oracle)."""
+import os
+import numpy as np
+import torch
+from oracle import nerf_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+def load_golden(name):
+  fx = np.load(os.path.join(GOLDEN, name + ".npz"))
+  return {k: fx[k] for k in fx.files}
+
+def plain_param_list(P, device):
+  """Order documented at nf_param_count (include/nerf_b200.h)."""
+  names = []
+  for pre in ("first", "refl.mlp"):
+    names += [f"{pre}.init.weight", f"{pre}.init.bias"]
+    i = 0
+    while f"{pre}.layers.{i}.weight" in P:
+      names += [f"{pre}.layers.{i}.weight", f"{pre}.layers.{i}.bias"]; i += 1
+    names += [f"{pre}.out.weight", f"{pre}.out.bias"]
+  names += [f"first.enc.embs.{i}.weight" for i in range(8)]
+  return [P[n].to(device).contiguous() for n in names]
+
+def plain_engine(P, device, sigmoid="upshifted", bg="black", precision="fp16"):
+  import nerf_atlas_b200 as N
+  eng = N.RenderEngine(N.describe_plain(64, sigmoid, bg), precision)
+  eng._params = plain_param_list(P, device)   # keep alive
+  eng.pack(eng._params)
+  return eng
+
+def make_tiny_params(seed=7):
+  """TinyNeRF.estim (reference src/nerf.py:286-290): xavier-uniform weights, zero biases."""
+  import math
+  g = np.random.default_rng(seed)
+  P = {}
+  def xav(name, o, i):
+    a = math.sqrt(6.0 / (i + o))
+    P[f"{name}.weight"] = torch.from_numpy(g.uniform(-a, a, size=(o, i)).astype(np.float32))
+    P[f"{name}.bias"] = torch.from_numpy(g.uniform(-0.1, 0.1, size=(o,)).astype(np.float32))
+  xav("estim.init", 256, 3)
+  for i in range(6): xav(f"estim.layers.{i}", 256, 259 if i in (0, 3) else 256)
+  xav("estim.out", 4, 256)
+  return P
+
+def tiny_param_list(P, device):
+  names = ["estim.init.weight", "estim.init.bias"]
+  for i in range(6): names += [f"estim.layers.{i}.weight", f"estim.layers.{i}.bias"]
+  names += ["estim.out.weight", "estim.out.bias"]
+  return [P[n].to(device).contiguous() for n in names]
+
+def psnr(a, b):
+  mse = float(np.mean((np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)) ** 2))
+  return 200.0 if mse == 0 else -10 * np.log10(mse)

@@ -1,0 +1,210 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and the committed golden
+vectors (which were produced by executing the reference).  Run with -m gpu on a B200.
+
+Stated tolerances (DESIGN.md section "Parity"):
+  * sample positions, ray ids, hash-table row indices: bit-exact
+  * fp32 pipeline  (NF_PREC_FP32):    max|d rgb| <= 2e-5
+  * fp16 tensor pipeline (NF_PREC_FP16_TC): max|d rgb| <= 1e-3 and PSNR >= 70 dB vs the fp32
+    reference; <= 3e-4 vs the oracle's fp16-operand emulation
+"""
+import numpy as np
+import pytest
+import torch
+from oracle import nerf_oracle as O
+from helpers import load_golden, plain_engine, plain_param_list, make_tiny_params, tiny_param_list, psnr
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+@pytest.fixture(scope="module")
+def P(): return O.make_plain_params(1337, 64, 20.0)
+
+@pytest.fixture(scope="module")
+def eng(P): return plain_engine(P, DEV)
+
+def _case(name):
+  fx = load_golden(name)
+  params = O.make_plain_params(int(fx["seed"]), 64, float(fx["sigma_gain"]))
+  rays = O.make_rays(int(fx["B"]), int(fx["H"]), int(fx["W"]), 800, int(fx["seed"]), int(fx["top"]), int(fx["left"]))
+  return fx, params, rays
+
+# ---------------------------------------------------------------- stages
+def test_sample_points_bit_exact(eng):
+  rays = O.make_rays(2, 9, 13, seed=4, crop_top=100, crop_left=37).reshape(-1, 6)
+  for T in (1, 16, 128, 192):
+    ts = torch.linspace(2, 6, T)
+    pts = eng.sample_points(rays.to(DEV), ts.to(DEV)).cpu()
+    ref, _, _ = O.compute_pts(rays, ts)           # [T,R,3]
+    assert torch.equal(pts, ref.permute(1, 0, 2).contiguous())
+  tsr = torch.sort(torch.rand(rays.shape[0], 24) * 4 + 2, dim=1).values   # per-ray ts
+  pts = eng.sample_points(rays.to(DEV), tsr.to(DEV)).cpu()
+  ref = rays[:, None, :3] + tsr[:, :, None] * rays[:, None, 3:]
+  assert torch.equal(pts, ref)
+
+@pytest.mark.parametrize("name", ["plain_t16", "plain_t16_sharp"])
+def test_hash_encode_indices_bit_exact_vs_reference(name):
+  fx, params, rays = _case(name)
+  e = plain_engine(params, DEV)
+  pts = torch.from_numpy(fx["pts"]).reshape(-1, 3)
+  feats, idx = e.hash_encode(pts.to(DEV), want_indices=True)
+  assert np.array_equal(idx.cpu().numpy().astype(np.uint16), fx["hash_idx"]), "hash table rows differ from the reference"
+  np.testing.assert_allclose(feats.cpu().numpy(), fx["hash_enc"][:, 3:], rtol=0, atol=2e-6)
+
+def test_hash_encode_random_points_incl_negative(eng, P):
+  g = torch.Generator().manual_seed(3)
+  pts = (torch.rand(50000, 3, generator=g) - 0.5) * 14
+  feats, idx = eng.hash_encode(pts.to(DEV), want_indices=True)
+  for lvl in range(8):
+    assert torch.equal(idx[lvl].cpu().to(torch.int64), O.hash_indices(pts, lvl))
+  ref = O.hash_encode(pts, O.hash_tables(P, "first.enc"))[:, 3:]
+  np.testing.assert_allclose(feats.cpu().numpy(), ref.numpy(), rtol=0, atol=2e-6)
+
+@pytest.mark.parametrize("T", [1, 7, 16, 32, 100, 128, 192, 256])
+def test_composite_matches_oracle(eng, T):
+  g = torch.Generator().manual_seed(T)
+  R = 333
+  rays = torch.randn(R, 6, generator=g)
+  sig = torch.randn(R, T, generator=g) * 4
+  feats = torch.rand(R, T, 3, generator=g)
+  ts = torch.linspace(2, 6, T)
+  rgb, alpha, w = eng.composite(sig.to(DEV), feats.to(DEV), rays.to(DEV), ts.to(DEV))
+  a_ref, w_ref = O.alpha_from_density(sig.t().contiguous(), ts, rays[:, 3:])
+  out_ref = O.volumetric_integrate(w_ref, feats.permute(1, 0, 2))
+  np.testing.assert_allclose(alpha.cpu().numpy(), a_ref.t().numpy(), atol=2e-6, rtol=1e-5)
+  np.testing.assert_allclose(w.cpu().numpy(), w_ref.t().numpy(), atol=2e-6, rtol=1e-5)
+  np.testing.assert_allclose(rgb.cpu().numpy(), out_ref.numpy(), atol=1e-5, rtol=1e-5)
+
+# ---------------------------------------------------------------- MLPs
+@pytest.mark.parametrize("which,pre,act,width", [(0, "first", "leaky_relu", 38), (1, "refl.mlp", "sin", 69)])
+def test_mlp_forward_fp32(eng, P, which, pre, act, width):
+  g = torch.Generator().manual_seed(which)
+  x0 = torch.randn(1000, width, generator=g)
+  out = eng.mlp_forward(which, x0.to(DEV), precision="fp32").cpu()
+  ref = O.skip_mlp(x0, P, pre, act)
+  np.testing.assert_allclose(out.numpy(), ref.numpy(), atol=2e-4, rtol=1e-4)
+
+@pytest.mark.parametrize("which,pre,act,width", [(0, "first", "leaky_relu", 38), (1, "refl.mlp", "sin", 69)])
+def test_mlp_forward_tensor_core(eng, P, which, pre, act, width):
+  g = torch.Generator().manual_seed(10 + which)
+  x0 = torch.randn(1000, width, generator=g)      # ragged: 1000 = 7 tiles + 104 rows
+  out = eng.mlp_forward(which, x0.to(DEV), precision="fp16").cpu()
+  refq = O.skip_mlp(x0, P, pre, act, quant=torch.float16)
+  ref = O.skip_mlp(x0, P, pre, act)
+  scale = float(ref.abs().max())
+  assert float((out - refq).abs().max()) <= 4e-3 * max(scale, 1.0), "tensor path vs fp16-operand emulation"
+  assert float((out - ref).abs().max()) <= 2e-2 * max(scale, 1.0), "tensor path vs fp32"
+
+# ---------------------------------------------------------------- full path vs golden (reference run)
+@pytest.mark.parametrize("name", ["plain_t16", "plain_t16_sharp", "plain_t128", "plain_t64_train"])
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("fp16", 1e-3)])
+def test_render_matches_reference_golden(name, precision, tol):
+  fx, params, rays = _case(name)
+  e = plain_engine(params, DEV, str(fx["sigmoid"]), str(fx["bg"]), precision)
+  T = int(fx["T"])
+  ts = torch.from_numpy(fx["ts"])
+  R = rays.reshape(-1, 6).shape[0]
+  noise = None
+  if int(fx["train"]): noise = (torch.from_numpy(fx["randn"]) * 0.2).reshape(T, R).t().contiguous().to(DEV)
+  rgb, alpha, w = e.render(rays.reshape(-1, 6).to(DEV), ts.to(DEV), noise)
+  out = rgb.cpu().numpy().reshape(fx["out"].shape)
+  a = alpha.cpu().numpy().T.reshape(fx["alpha"].shape); ww = w.cpu().numpy().T.reshape(fx["weights"].shape)
+  assert np.isfinite(out).all()
+  assert np.abs(out - fx["out"]).max() <= tol, (np.abs(out - fx["out"]).max(), psnr(out, fx["out"]))
+  assert np.abs(a - fx["alpha"]).max() <= max(tol, 1e-4) * 5 and np.abs(ww - fx["weights"]).max() <= max(tol, 1e-4) * 5
+  if precision == "fp16": assert psnr(out, fx["out"]) >= 70.0
+
+@pytest.mark.parametrize("T", [16, 32, 64, 100, 128, 192, 256])
+def test_render_all_T_vs_oracle(P, T):
+  rays = O.make_rays(1, 5, 7, seed=T, crop_top=380, crop_left=390).reshape(-1, 6)   # ragged: 35 rays
+  ts = torch.linspace(2, 6, T)
+  with torch.no_grad():
+    ref = O.plain_forward(P, rays, ts)
+    refq = O.plain_forward(P, rays, ts, quant=torch.float16)
+  for precision, r, tol in (("fp32", ref, 2e-5), ("fp16", refq, 3e-4), ("fp16", ref, 1e-3)):
+    e = plain_engine(P, DEV, precision=precision)
+    rgb, alpha, w = e.render(rays.to(DEV), ts.to(DEV))
+    assert np.abs(rgb.cpu().numpy() - r["out"].numpy()).max() <= tol, (precision, T)
+    assert np.abs(w.cpu().numpy() - r["weights"].t().numpy()).max() <= 5e-3 if precision == "fp16" else 1e-4
+
+def test_render_per_ray_ts_noise_white_bg(P):
+  g = torch.Generator().manual_seed(5)
+  rays = O.make_rays(1, 4, 9, seed=2, crop_top=300, crop_left=500).reshape(-1, 6)
+  R, T = rays.shape[0], 48
+  tsr = torch.sort(torch.rand(R, T, generator=g) * 4 + 2, dim=1).values
+  noise = torch.randn(R, T, generator=g) * 0.2
+  pts = (rays[:, None, :3] + tsr[:, :, None] * rays[:, None, 3:]).permute(1, 0, 2).contiguous()   # [T,R,3]
+  with torch.no_grad():
+    ref = O.plain_from_pts(P, pts, tsr.t().contiguous(), rays[:, :3], rays[:, 3:], bg="white",
+                           density_noise=noise.t().contiguous(), per_ray_ts=True)
+  for precision, tol in (("fp32", 3e-5), ("fp16", 1e-3)):
+    e = plain_engine(P, DEV, bg="white", precision=precision)
+    rgb, _, w = e.render(rays.to(DEV), tsr.to(DEV), noise.to(DEV))
+    assert np.abs(rgb.cpu().numpy() - ref["out"].numpy()).max() <= tol, precision
+
+def test_tiny_nerf_vs_oracle():
+  import nerf_atlas_b200 as N
+  Pt = make_tiny_params()
+  rays = O.make_rays(1, 64, 64, size=64, seed=1).reshape(-1, 6)[:777]
+  ts = torch.linspace(2, 6, 32)
+  with torch.no_grad():
+    ref = O.tiny_forward(Pt, rays, ts)
+    refq = O.tiny_forward(Pt, rays, ts, quant=torch.float16)
+  for precision, r, tol in (("fp32", ref, 2e-5), ("fp16", refq, 3e-4), ("fp16", ref, 1e-3)):
+    e = N.RenderEngine(N.describe_tiny("upshifted", "black"), precision)
+    e._p = tiny_param_list(Pt, DEV); e.pack(e._p)
+    rgb, _, _ = e.render(rays.to(DEV), ts.to(DEV))
+    assert np.abs(rgb.cpu().numpy() - r["out"].numpy()).max() <= tol, precision
+
+# ---------------------------------------------------------------- properties at size
+def test_properties_full_frame_tile(P):
+  """800x800x128 is the bench workload; here a 200-row band of it (160k rays, 20.5M samples) checks the
+  size-independent properties: determinism, sum-of-weights identity, shard == whole, empty input."""
+  e = plain_engine(P, DEV, precision="fp16")
+  rays = O.make_rays(1, 200, 800, seed=0, crop_top=300).reshape(-1, 6).to(DEV)
+  ts = torch.linspace(2, 6, 128, device=DEV)
+  rgb, alpha, w = e.render(rays, ts)
+  rgb2, _, w2 = e.render(rays, ts)
+  assert torch.equal(rgb, rgb2) and torch.equal(w, w2), "not deterministic"
+  assert torch.isfinite(rgb).all() and float(rgb.min()) >= 0.0 and float(rgb.max()) <= 1.011
+  ident = 1 - torch.prod(1 - alpha.double() + 1e-10, dim=1)
+  assert float((w.double().sum(1) - ident).abs().max()) < 1e-4
+  assert float((alpha[:, -1] - 1).abs().max()) < 1e-6          # the 1e10 end cap
+  half = rays.shape[0] // 2 + 13
+  a, _, _ = e.render(rays[:half].contiguous(), ts, want_weights=False)
+  b, _, _ = e.render(rays[half:].contiguous(), ts, want_weights=False)
+  assert torch.equal(torch.cat([a, b]), rgb), "sharded render differs from the whole"
+  z, _, _ = e.render(rays[:0].contiguous(), ts)
+  assert z.shape == (0, 3)
+
+def test_module_surface_matches_runner_expectations(P):
+  import nerf_atlas_b200 as N
+  m = N.FusedPlainNeRF(steps=64, t_near=2, t_far=6, intermediate_size=64, sigmoid_kind="upshifted", precision="fp32")
+  m.load_state_dict({k: v for k, v in P.items()}, strict=True)      # reference state_dict names
+  m = m.to(DEV).eval()
+  rays = O.make_rays(2, 6, 5, seed=9).to(DEV)
+  with torch.no_grad(): out = m(rays)
+  assert out.shape == (2, 6, 5, 3) and m.weights.shape == (64, 2, 6, 5) and m.alpha.shape == (64, 2, 6, 5) and m.ts.shape == (64,)
+  with torch.no_grad(): ref = O.plain_forward(P, rays.cpu(), m.ts.cpu())
+  assert np.abs(out.cpu().numpy() - ref["out"].numpy()).max() <= 2e-5
+  assert np.abs(m.weights.cpu().numpy() - ref["weights"].numpy()).max() <= 1e-5
+  m.nerf.steps = 32                                                   # runner.py:1048-1050 mutates these per run
+  with torch.no_grad(): assert m(rays).shape == (2, 6, 5, 3) and m.weights.shape[0] == 32
+  with torch.no_grad(): m.first.out.bias.add_(0.5)                    # in-place update must trigger a re-pack
+  with torch.no_grad(): out2 = m(rays)
+  assert not torch.equal(out2, out), "stale packed weights after an in-place parameter update"
+  import pickle; m2 = pickle.loads(pickle.dumps(m))                  # checkpoint = whole-module pickle
+  with torch.no_grad(): assert torch.equal(m2(rays), out2)
+
+def test_c_abi_error_codes(eng):
+  import ctypes as C
+  from nerf_atlas_b200 import _lib
+  l = _lib.lib()
+  rays = torch.zeros(4, 6, device=DEV); ts = torch.linspace(2, 6, 8, device=DEV); rgb = torch.zeros(4, 3, device=DEV)
+  v = lambda t: C.c_void_p(t.data_ptr())
+  rc = l.nf_render_forward(C.byref(eng.desc), v(eng.packed), v(rays), 4, v(ts), 8, 5, None, v(rgb), None, None, 1, None)
+  assert rc == -1 and b"ts_ray_stride" in l.nf_last_error()
+  rc = l.nf_render_forward(C.byref(eng.desc), v(eng.packed), None, 4, v(ts), 8, 0, None, v(rgb), None, None, 1, None)
+  assert rc == -1
+  rc = l.nf_render_forward(C.byref(eng.desc), v(eng.packed), v(rays), 4, v(ts), 8, 0, None, v(rgb), None, None, 7, None)
+  assert rc == -1 and b"precision" in l.nf_last_error()
+  with pytest.raises(RuntimeError): eng.render(rays.cpu(), ts)
