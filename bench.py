@@ -1,0 +1,205 @@
+#!/usr/bin/env python
+"""bench.py -- rays/s of the fused NeRF render path on synthetic 800x800x128 frames.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (1 process per GPU under torchrun for N>1)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU PyTorch path (oracle port), rank 0 only
+
+One step = one full forward render of one synthetic 800x800 view at 128 samples/ray (PlainNeRF + View
+head, hash encoder, I=64: the configuration BASELINE.json's metric is quoted on) per GPU.  Prints ONE
+JSON line (contract in the task statement): `value` = whole-job rays/s with rays resident in HBM,
+`e2e` = the same through the public FusedPlainNeRF.forward call with pinned HOST rays in and HOST rgb
+out, `roofline` for the dominant kernel (k_render_tc, tensor-bound), `cpu_baseline` = the CPU oracle
+port timed on this box's host cores on a bounded sample.
+"""
+import argparse, json, os, statistics, subprocess, sys, threading, time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SIZE, T = 800, 128
+RAYS_PER_FRAME = SIZE * SIZE
+FLOP_PER_SAMPLE = 1_192_960          # 2 x unpadded GEMM MACs, Plain+View, I=64
+N_VIEWS = 16                         # rotated inputs: 16 x 15.4 MB of rays = 246 MB > 126 MB L2
+CPU_TILE = 64                        # cpu_baseline sample: CPU_TILE x CPU_TILE rays x 128 samples per step
+
+
+def peaks():
+  p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  if os.path.exists(p):
+    d = json.load(open(p))
+    return float(d["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)"
+  return 1400.0, "fallback (B200_PROFILING.md sustained figure)"
+
+
+class ClockSampler:
+  """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+  Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+  def __init__(self, index):
+    self.index, self.rows, self.stop, self.th = index, [], threading.Event(), None
+  def _run(self):
+    while not self.stop.is_set():
+      try:
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if out: self.rows.append([x.strip() for x in out.split(",")])
+      except Exception: pass
+      self.stop.wait(0.1)
+  def __enter__(self): self.th = threading.Thread(target=self._run, daemon=True); self.th.start(); return self
+  def __exit__(self, *a): self.stop.set(); self.th.join(timeout=6)
+  def summary(self):
+    sm = [int(r[0]) for r in self.rows if r[0].isdigit()]
+    mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+    return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+            "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_port_rays_per_s(steps, warmup, tile=CPU_TILE):
+  """The reference's CPU PyTorch path, restated (oracle/nerf_oracle.py), all host cores."""
+  import torch
+  from oracle import nerf_oracle as O
+  cores = os.cpu_count() or 1
+  torch.set_num_threads(cores)
+  P = O.make_plain_params(1337, 64, 1.0)
+  ts = torch.linspace(2, 6, T)
+  times = []
+  with torch.no_grad():
+    for i in range(warmup + steps):
+      rays = O.make_rays(1, tile, tile, size=SIZE, seed=i, crop_top=368, crop_left=368)
+      t0 = time.perf_counter()
+      O.plain_forward(P, rays, ts)
+      if i >= warmup: times.append(time.perf_counter() - t0)
+  dt = sum(times) / len(times)
+  return tile * tile / dt, cores, dt, f"{steps} steps x ({tile}x{tile} crop of the 800x800 view) x {T} samples/ray, fp32, torch CPU, {cores} threads"
+
+
+def run_reference(args):
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0: return
+  steps = max(1, min(args.steps, 6)); warm = 1
+  v, cores, dt, sample = cpu_port_rays_per_s(steps, warm)
+  line = {
+    "impl": "reference", "metric": "rays_per_sec_800x800x128", "value": v, "unit": "rays/s", "n_gpus": args.gpus,
+    "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    "dtype": "f32", "data": "synthetic",
+    "config": {"workload": "PlainNeRF+View (hash enc, I=64) forward render, 800x800 view, 128 samples/ray, near 2 far 6; "
+                           "reference arm = CPU port of the reference's PyTorch path on a bounded crop per step"},
+    "msamples_per_sec": v * T / 1e6,
+    "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+    "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+  }
+  print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+  import torch
+  import torch.distributed as dist
+  import nerf_atlas_b200 as N
+  from oracle import nerf_oracle as O   # synthetic inputs + the cpu_baseline leg only
+  world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+  if not torch.cuda.is_available(): raise SystemExit("bench.py needs a CUDA device: the render path has no CPU fallback")
+  torch.cuda.set_device(local)
+  dev = torch.device("cuda", local)
+  if world > 1: dist.init_process_group("nccl", device_id=dev)
+
+  # model: PlainNeRF + View with the reference's init distributions, seeded (random-init weights; no dataset)
+  model = N.FusedPlainNeRF(steps=T, t_near=2, t_far=6, intermediate_size=64, sigmoid_kind="upshifted", precision="fp16")
+  model.load_state_dict(O.make_plain_params(1337, 64, 1.0), strict=True)
+  model = model.to(dev).eval()
+  eng = model.engine(); eng.pack(model._param_list())
+
+  # inputs: N_VIEWS distinct 800x800 views per rank (rank-specific seeds), rays resident in HBM + pinned host copies
+  views_host = [O.make_rays(1, SIZE, SIZE, size=SIZE, seed=1000 * rank + v).reshape(-1, 6).contiguous().pin_memory() for v in range(N_VIEWS)]
+  views_dev = [v.to(dev) for v in views_host]
+  ts = torch.linspace(2, 6, T, device=dev)
+  rgb_host = torch.empty(RAYS_PER_FRAME, 3).pin_memory()
+
+  def step_resident(i):
+    return eng.render(views_dev[i % N_VIEWS], ts, None, want_weights=False)[0]
+  def step_e2e(i):
+    rays = views_host[i % N_VIEWS].to(dev, non_blocking=True).reshape(1, SIZE, SIZE, 6)
+    with torch.no_grad(): out = model(rays)
+    rgb_host.copy_(out.reshape(-1, 3), non_blocking=True)
+    return out
+
+  def barrier():
+    if world > 1: dist.barrier()
+    torch.cuda.synchronize()
+
+  def timed(fn, steps, warmup):
+    for i in range(warmup): fn(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps): fn(warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+      t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    barrier()
+    return ms
+
+  model.keep_weights = False
+  with ClockSampler(local) as cs:
+    ms = timed(step_resident, args.steps, args.warmup)
+  clocks = cs.summary()
+  ms_e2e = timed(step_e2e, args.steps, max(3, args.warmup))
+
+  total_rays = world * RAYS_PER_FRAME * args.steps
+  value = total_rays / (ms * 1e-3)
+  e2e = total_rays / (ms_e2e * 1e-3)
+  peak, peak_src = peaks()
+  # dominant kernel = k_render_tc: exactly one launch per step; its average duration IS the step (events on the launch stream)
+  kern_ms = ms / args.steps
+  achieved = RAYS_PER_FRAME * T * FLOP_PER_SAMPLE / (kern_ms * 1e-3) / 1e12
+  traffic = None
+  tp = os.path.join(ROOT, "profiles", "traffic.json")
+  if os.path.exists(tp):
+    try: traffic = json.load(open(tp)).get("k_render_tc_dram_bytes_per_launch")
+    except Exception: traffic = None
+
+  if rank == 0:
+    cpu_v, cores, cpu_dt, sample = (None, None, None, None)
+    if world == 1 and not args.no_cpu_baseline:
+      cpu_v, cores, cpu_dt, sample = cpu_port_rays_per_s(steps=3, warmup=1)
+    line = {
+      "metric": "rays_per_sec_800x800x128", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+      "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+      "dtype": "f16 operands / f32 accumulate (tcgen05 kind::f16)", "data": "synthetic",
+      "config": {"workload": "PlainNeRF+View (hash enc, I=64) forward render, one 800x800 view x 128 samples/ray per GPU per step, near 2 far 6",
+                 "rays_per_step_per_gpu": RAYS_PER_FRAME, "samples_per_ray": T, "weights": "seeded random init (reference distributions)",
+                 "l2": f"inputs rotate over {N_VIEWS} distinct views = {N_VIEWS * RAYS_PER_FRAME * 24 / 1e6:.0f} MB of rays > 126 MB L2",
+                 "parallelism": f"ray-sharded x{world} (one view per GPU per step), no data-path collective"},
+      "msamples_per_sec": value * T / 1e6,
+      "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": RAYS_PER_FRAME * 24, "d2h_bytes_per_step": RAYS_PER_FRAME * 12,
+              "ms_per_step": ms_e2e / args.steps, "api": "FusedPlainNeRF.forward(rays) with pinned host rays in, host rgb out"},
+      "gpu_launches": args.steps,
+      "clocks": clocks,
+      "roofline": {"bound": "tensor", "kernel": "k_render_tc", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                   "traffic": traffic, "peak_source": peak_src,
+                   "algorithmic": f"{FLOP_PER_SAMPLE} FLOP/sample x {RAYS_PER_FRAME * T} samples per launch"},
+    }
+    if cpu_v is not None:
+      line["cpu_baseline"] = {"value": cpu_v, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample}
+    print(json.dumps(line), flush=True)
+  if world > 1: dist.destroy_process_group()
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=10)
+  ap.add_argument("--warmup", type=int, default=3)
+  ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+  ap.add_argument("--no-cpu-baseline", action="store_true")
+  args = ap.parse_args()
+  args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+  if args.impl == "reference": run_reference(args)
+  else: run_ours(args)
+
+
+if __name__ == "__main__":
+  main()
