@@ -9,7 +9,7 @@
 #define NF_MAX_LIN 10          // init + up to 8 hidden + out
 #define NF_HIDDEN 256
 #define NF_TC_ROWS 128         // samples per tensor-core tile (= UMMA M)
-#define NF_TC_CHUNK_K 32       // K columns per streamed weight chunk (2 UMMA K-steps)
+#define NF_TC_CHUNK_K 64       // K columns per streamed weight chunk (4 UMMA K-steps; 32 KB at N=256 -- see profiles/microbench)
 
 // ---- plan ---------------------------------------------------------------------
 struct NfLinPlan {
@@ -228,7 +228,7 @@ struct NfTileMap {
   // row r of sub-tile s of unit u -> ray, t; returns validity
   __device__ __forceinline__ bool locate(long long u, int s, int r, long long n_rays, long long& ray, int& t) const {
     if (T <= rows) { const int rl = r / T; ray = u * rpt + rl; t = r - rl * T; return rl < rpt && ray < n_rays; }
-    ray = u; t = s * rows + r; return t < T;
+    ray = u; t = s * rows + r; return t < T && ray < n_rays;
   }
 };
 #endif  // __CUDACC__

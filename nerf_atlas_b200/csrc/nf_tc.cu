@@ -8,13 +8,15 @@
 //       [K/8][128 rows][8 halves] (16-byte cores; written conflict-free by the epilogue warps),
 //   B = weights [N x K], pre-packed on the device by nf_pack_weights into the same canonical
 //       layout and streamed from L2 by the bulk-copy engine (cp.async.bulk = TMA 1-D) through
-//       a 6-stage mbarrier ring,
+//       a 3-stage mbarrier ring of 32 KB chunks (the bulk-copy engine has a ~430-cycle fixed cost per copy and
+//       ~2 copies in flight per SM, so bandwidth scales with copy size: profiles/microbench/copy_bw.cu),
 //   D = [128 x N] fp32 in TMEM, two 256-column accumulators used alternately by consecutive
 //       layers so that layer j+1's MMAs start on the K-chunks of layer j's output as soon as the
 //       epilogue has written them (chunk-granular h_ready barriers).
 // Warp roles: 0 = weight producer, 1 = MMA issuer (one thread), 2 = TMEM allocator,
 // 4..11 = encode/epilogue warps (TMEM lane quarter = warp % 4, column half = (warp-4)/4).
 #include <cstdio>
+#include <cstdlib>
 #include "nf_common.cuh"
 #include "nf_kernels.h"
 
@@ -22,12 +24,16 @@ namespace {
 
 constexpr int ROWS = NF_TC_ROWS;          // 128
 constexpr int X0K = 80;                   // max padded x0 width on this path
-constexpr int STAGES = 6;
-constexpr int STAGE_BYTES = NF_TC_CHUNK_K * 256 * 2;   // 16 KB: 32 K-columns x 256 N x fp16
+constexpr int STAGES = 3;
+constexpr int SPC = NF_TC_CHUNK_K / 16;                 // UMMA K-steps per weight chunk
+constexpr int STAGE_BYTES = NF_TC_CHUNK_K * 256 * 2;   // 32 KB: 64 K-columns x 256 N x fp16
 constexpr int MAX_LIN_TOTAL = 12;
 constexpr int THREADS = 384;
 constexpr int EPI_THREADS = 256;
 constexpr int KG_BYTES = ROWS * 16;       // one 8-column K-group of an A operand: 128 rows x 16 B
+constexpr int MAX_CHUNKS = 64;
+// flags of one weight chunk of the per-tile MMA program: bits 0-2 = UMMA steps in the chunk (1..4)
+constexpr uint32_t F_NSTEP = 7, F_FIRST = 8, F_LAST = 16, F_BUF = 32, F_WAIT_X0 = 64, F_WAIT_H = 0xF00;
 
 struct TcSmem {
   uint8_t H[ROWS * 256 * 2];
@@ -44,6 +50,9 @@ struct TcSmem {
   float warp_agg[4]; int warp_cont[4]; float warp_sum[4][4]; float carry[8];
   unsigned long long w_full[STAGES], w_empty[STAGES], acc_full[2], h_ready[4], x0_ready;
   uint32_t tmem_base;
+  int n_chunks, odd_lin;
+  uint4 prog[2 * MAX_CHUNKS];   // per-tile MMA program, one entry per weight chunk: {a_desc_lo[4]}, {b_step, idesc, flags, -}
+  uint2 chunks[MAX_CHUNKS];     // per-tile weight chunk list: {byte offset into packed, bytes}
 };
 static_assert(sizeof(TcSmem) <= 227 * 1024, "tensor pipeline smem");
 
@@ -55,6 +64,8 @@ struct TcArgs {
   float* rgb_out; float* alpha_out; float* weights_out;
   // MLP-only mode
   int mlp_only; int which; const float* x0; long long n; float* out;
+  long long* trace;   // debug & 4: clock64 timeline of one tile of block 0: [role][512] x {tag, clock}
+  int debug;   // timing experiments only (NF_TC_DEBUG): 1 = epilogue does no work, 2 = no MMA issued
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -75,28 +86,42 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
+__device__ __noinline__ void mbar_timeout(uint32_t bar) {
+  if ((threadIdx.x & 31) == 0) printf("nf_tc: mbarrier timeout (block %d thread %d bar %u)\n", blockIdx.x, threadIdx.x, bar);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) { printf("nf_tc: mbarrier timeout (block %d thread %d bar %u)\n", blockIdx.x, threadIdx.x, bar); __trap(); }
-  }
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) { if (++spins > (1u << 22)) mbar_timeout(bar); }
+}
+// for waits that are off the critical path (the weight producer): yield issue slots while waiting
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) { __nanosleep(128); if (++spins > (1u << 22)) mbar_timeout(bar); }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-// K-major, no-swizzle UMMA shared-memory descriptor: 8x16-byte core matrices; LBO = byte distance
-// between the two K-adjacent cores of one K=16 step, SBO = byte distance between 8-row groups.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
-         ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
-}
+// K-major, no-swizzle UMMA shared-memory descriptors: 8x16-byte core matrices; LBO (bits 16-29) = byte distance
+// between the two K-adjacent cores of one K=16 step, SBO (bits 32-45) = byte distance between 8-row groups.
+// high word shared by every operand here: SBO = 128 B, descriptor version 1 (bit 46)
+__device__ __forceinline__ uint64_t umma_desc_lo(uint32_t lo) { return ((uint64_t)0x4008u << 32) | lo; }
 // kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=n.
 __device__ __forceinline__ uint32_t umma_idesc(int n) {
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
@@ -108,6 +133,9 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
@@ -115,6 +143,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
                : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// ties 16 registers to the preceding tcgen05.wait::ld so no consumer is scheduled above it
+__device__ __forceinline__ void reg_fence16(uint32_t* v) {
+  asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                    "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]) :: "memory");
+}
+template <int ACT> __device__ __forceinline__ float tc_act_t(float x) {
+  if (ACT == NF_ACT_LEAKY) return fmaxf(x, 0.01f * x);
+  if (ACT == NF_ACT_SIN) return __sinf(x);
+  if (ACT == NF_ACT_RELU) return fmaxf(x, 0.f);
+  return x;
+}
 
 __device__ __forceinline__ float tc_act(float x, int act) {
   switch (act) {
@@ -132,13 +171,46 @@ __device__ __forceinline__ void st_v4(uint8_t* p, uint32_t a, uint32_t b, uint32
   *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d);
 }
 
+#define NF_TRACE(role, tag) do { if (tr_on && tr_n[role] < 512) { tr[(role * 512 + tr_n[role]) * 2] = (tag); tr[(role * 512 + tr_n[role]) * 2 + 1] = clock64(); ++tr_n[role]; } } while (0)
+
 // ---- the sequence of tiles a CTA walks (identical in every warp role) ---------------------------
 struct TileIter {
-  long long units; int tpr;
+  long long units, trips; int tpr;   // every CTA makes `trips` passes; passes with u >= units are all-masked tiles
   __device__ TileIter(const TcArgs& a, const NfTileMap& map) {
     if (a.mlp_only) { units = (a.n + ROWS - 1) / ROWS; tpr = 1; } else { units = map.units(a.n_rays); tpr = map.tpr; }
+    trips = (units + gridDim.x - 1) / gridDim.x;
   }
 };
+
+// ---- epilogue of a hidden Linear: H <- fp16(act(acc + bias)), in place, 64-column chunks ----------
+// TMEM loads of chunk c+1 are in flight while chunk c is converted and stored.
+template <int ACT>
+__device__ __forceinline__ void epi_hidden(TcSmem& s, uint32_t t_acc, const float* __restrict__ bias, int half, int row, int lane) {
+  uint32_t v[2][32];
+  tmem_ld16(t_acc + half * 32, v[0]); tmem_ld16(t_acc + half * 32 + 16, v[0] + 16);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    tmem_ld_wait();
+    reg_fence16(v[c & 1]); reg_fence16(v[c & 1] + 16);
+    if (c < 3) { tmem_ld16(t_acc + (c + 1) * 64 + half * 32, v[(c + 1) & 1]); tmem_ld16(t_acc + (c + 1) * 64 + half * 32 + 16, v[(c + 1) & 1] + 16); }
+    const int col = c * 64 + half * 32;
+    const float4* b4 = reinterpret_cast<const float4*>(bias + col);
+    uint32_t o[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 b = b4[i];
+      o[2 * i]     = pack_h2(tc_act_t<ACT>(__uint_as_float(v[c & 1][4 * i]) + b.x), tc_act_t<ACT>(__uint_as_float(v[c & 1][4 * i + 1]) + b.y));
+      o[2 * i + 1] = pack_h2(tc_act_t<ACT>(__uint_as_float(v[c & 1][4 * i + 2]) + b.z), tc_act_t<ACT>(__uint_as_float(v[c & 1][4 * i + 3]) + b.w));
+    }
+    uint8_t* dst = s.H + (col >> 3) * KG_BYTES + row * 16;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) st_v4(dst + g * KG_BYTES, o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+    tc_fence_before();
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&s.h_ready[c]));
+  }
+}
 
 // ---- composite of one tile by the 4 column-half-0 epilogue warps (thread = row) ----------------
 // reference src/nerf.py:60-80. Running transmittance = segmented warp-shuffle product scan,
@@ -236,6 +308,11 @@ k_render_tc(const __grid_constant__ NfPlan plan, const TcArgs a) {
   const int m_begin = a.mlp_only ? a.which : 0, m_end = a.mlp_only ? a.which + 1 : plan.n_mlps;
   const int lin_base1 = plan.mlp[0].n_lin;   // global linear index of refl MLP's first Linear
 
+  long long* tr = a.trace; int tr_n[3] = {0, 0, 0}; bool tr_on = false;
+  // A cluster of `csize` CTAs shares every weight chunk: CTA (chunk % csize) issues one multicast bulk copy
+  // that lands in the same ring stage of every CTA, so L2 is read once per cluster instead of once per SM.
+  const uint32_t csize = cluster_nctarank(), crank = cluster_ctarank();
+  const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
   // ---- one-time setup ----
   for (int i = threadIdx.x; i < MAX_LIN_TOTAL * 256; i += THREADS) {
     const int g = i >> 8, n = i & 255;
@@ -246,7 +323,7 @@ k_render_tc(const __grid_constant__ NfPlan plan, const TcArgs a) {
     s.bias[i] = v;
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(smem_u32(&s.w_full[i]), 1); mbar_init(smem_u32(&s.w_empty[i]), 1); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(smem_u32(&s.w_full[i]), 1); mbar_init(smem_u32(&s.w_empty[i]), csize); }
     mbar_init(smem_u32(&s.acc_full[0]), 1); mbar_init(smem_u32(&s.acc_full[1]), 1);
     for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&s.h_ready[i]), 8);
     mbar_init(smem_u32(&s.x0_ready), 8);
@@ -256,78 +333,108 @@ k_render_tc(const __grid_constant__ NfPlan plan, const TcArgs a) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (warp == 3 && lane == 0) {
+    // The per-tile MMA program and weight chunk list (identical for every tile): one entry per weight chunk.
+    const uint32_t Hs = smem_u32(s.H), Xr = smem_u32(s.X0raw), Xa = smem_u32(s.X0act);
+    int nc = 0, lin = 0;
+    for (int m = m_begin; m < m_end; ++m) {
+      bool x0_first = true;
+      for (int j = 0; j < plan.mlp[m].n_lin; ++j, ++lin) {
+        const NfLinPlan& L = plan.mlp[m].lin[j];
+        const int steps = (L.k0_pad + L.k_hidden) >> 4;
+        const uint32_t b_lbo = (uint32_t)L.n_pad * 16u, idesc = umma_idesc(L.n_pad);
+        uint32_t hmask = 0;
+        for (int c = 0; c < L.n_chunks; ++c) {
+          const int nst = min(SPC, steps - SPC * c);
+          uint32_t f = (uint32_t)nst | (c == 0 ? F_FIRST : 0u) | (c == L.n_chunks - 1 ? F_LAST : 0u) | ((lin & 1) ? F_BUF : 0u);
+          uint32_t alo[4] = {0, 0, 0, 0};
+          for (int q4 = 0; q4 < nst; ++q4) {
+            const int k = (c * SPC + q4) << 4;
+            uint32_t a_addr;
+            if (k < L.k0_pad) {
+              if (x0_first) { f |= F_WAIT_X0; x0_first = false; }
+              a_addr = (L.x0_raw ? Xr : Xa) + (uint32_t)(k >> 3) * KG_BYTES;
+            } else {
+              const int kh = k - L.k0_pad, hc = kh >> 6;
+              if (!(hmask & (1u << hc))) { f |= 0x100u << hc; hmask |= 1u << hc; }
+              a_addr = Hs + (uint32_t)(kh >> 3) * KG_BYTES;
+            }
+            alo[q4] = ((a_addr >> 4) & 0x3FFFu) | ((uint32_t)(KG_BYTES >> 4) << 16);
+          }
+          s.prog[2 * nc] = make_uint4(alo[0], alo[1], alo[2], alo[3]);
+          s.prog[2 * nc + 1] = make_uint4((2u * b_lbo) >> 4, idesc, f, (b_lbo >> 4) << 16);
+          s.chunks[nc] = make_uint2((uint32_t)(L.w16_off + (int64_t)c * (2 * SPC) * L.n_pad * 16), (uint32_t)nst * 2u * b_lbo);
+          ++nc;
+        }
+      }
+    }
+    s.n_chunks = nc; s.odd_lin = lin & 1;
+  }
   tc_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();     // peers' barriers are initialised before anyone multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = s.tmem_base;
 
   if (warp == 0) {
-    // ================= weight producer: stream every Linear's chunks through the ring =================
+    // ================= weight producer: ONE thread streams every Linear's chunks through the ring =================
     if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (long long u = blockIdx.x; u < it.units; u += gridDim.x)
-        for (int sub = 0; sub < it.tpr; ++sub)
-          for (int m = m_begin; m < m_end; ++m)
-            for (int j = 0; j < plan.mlp[m].n_lin; ++j) {
-              const NfLinPlan& L = plan.mlp[m].lin[j];
-              const int steps = (L.k0_pad + L.k_hidden) >> 4;
-              const uint8_t* src = a.packed + L.w16_off;
-              for (int c = 0; c < L.n_chunks; ++c) {
-                const int nst = min(2, steps - 2 * c);
-                const uint32_t bytes = (uint32_t)nst * 2u * (uint32_t)L.n_pad * 16u;
-                mbar_wait(smem_u32(&s.w_empty[stage]), phase ^ 1);
-                mbar_expect_tx(smem_u32(&s.w_full[stage]), bytes);
-                bulk_g2s(smem_u32(s.W[stage]), src + (size_t)c * 4 * L.n_pad * 16, bytes, smem_u32(&s.w_full[stage]));
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
-              }
-            }
+      int stage = 0, cidx = 0; uint32_t phase = 0;
+      const int nc = s.n_chunks;
+      for (long long trip = 0; trip < it.trips * it.tpr; ++trip) {   // one pass per tile (tpr tiles per unit)
+        tr_on = (a.debug & 4) && blockIdx.x == 0 && trip == 2;
+        for (int c = 0; c < nc; ++c, ++cidx) {
+          const uint2 ch = s.chunks[c];
+          mbar_wait_backoff(smem_u32(&s.w_empty[stage]), phase ^ 1);
+          NF_TRACE(0, c);
+          mbar_expect_tx(smem_u32(&s.w_full[stage]), ch.y);
+          if (csize == 1) bulk_g2s(smem_u32(s.W[stage]), a.packed + ch.x, ch.y, smem_u32(&s.w_full[stage]));
+          else if ((uint32_t)(cidx % (int)csize) == crank)
+            bulk_g2s_mc(smem_u32(s.W[stage]), a.packed + ch.x, ch.y, smem_u32(&s.w_full[stage]), cmask);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer: one thread issues every tcgen05.mma of the CTA =================
+    // ================= MMA issuer: ONE thread walks the chunk program and issues every tcgen05.mma =================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      uint32_t h_par = 0, x0_par = 0;     // expected parities of h_ready[0..3], x0_ready
-      uint32_t lin_count = 0;
-      const uint32_t Hs = smem_u32(s.H), Xr = smem_u32(s.X0raw), Xa = smem_u32(s.X0act);
-      for (long long u = blockIdx.x; u < it.units; u += gridDim.x)
-        for (int sub = 0; sub < it.tpr; ++sub)
-          for (int m = m_begin; m < m_end; ++m) {
-            bool x0_waited = false;
-            for (int j = 0; j < plan.mlp[m].n_lin; ++j, ++lin_count) {
-              const NfLinPlan& L = plan.mlp[m].lin[j];
-              const int steps = (L.k0_pad + L.k_hidden) >> 4;
-              const uint32_t d_tmem = tmem_base + (lin_count & 1) * 256;
-              const uint32_t idesc = umma_idesc(L.n_pad);
-              const uint32_t b_lbo = (uint32_t)L.n_pad * 16u;
-              uint32_t h_waited = 0;
-              int step = 0;
-              for (int c = 0; c < L.n_chunks; ++c) {
-                mbar_wait(smem_u32(&s.w_full[stage]), phase);
-                const int nst = min(2, steps - 2 * c);
-                for (int s2 = 0; s2 < nst; ++s2, ++step) {
-                  const int k = step << 4;
-                  uint32_t a_addr;
-                  if (k < L.k0_pad) {
-                    if (!x0_waited) { mbar_wait(smem_u32(&s.x0_ready), x0_par); x0_par ^= 1; x0_waited = true; }
-                    a_addr = (L.x0_raw ? Xr : Xa) + (uint32_t)(k >> 3) * KG_BYTES;
-                  } else {
-                    const int kh = k - L.k0_pad, hc = kh >> 6;
-                    if (!(h_waited & (1u << hc))) {
-                      mbar_wait(smem_u32(&s.h_ready[hc]), (h_par >> hc) & 1u);
-                      h_par ^= 1u << hc; h_waited |= 1u << hc;
-                    }
-                    a_addr = Hs + (uint32_t)(kh >> 3) * KG_BYTES;
-                  }
-                  tc_fence_after();
-                  const uint32_t b_addr = smem_u32(s.W[stage]) + (uint32_t)s2 * 2u * b_lbo;
-                  umma_f16(d_tmem, umma_desc(a_addr, KG_BYTES, 128), umma_desc(b_addr, b_lbo, 128), idesc, step > 0);
-                }
-                umma_commit(smem_u32(&s.w_empty[stage]));
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
-              }
-              umma_commit(smem_u32(&s.acc_full[lin_count & 1]));
-            }
+      uint32_t h_par = 0, x0_par = 0, tile_par = 0;   // expected parities of h_ready[0..3], x0_ready; accumulator flip
+      const int nc = s.n_chunks; const uint32_t odd = (uint32_t)s.odd_lin;
+      const uint32_t w_base4 = smem_u32(s.W) >> 4;
+      for (long long trip = 0; trip < it.trips * it.tpr; ++trip) {   // one pass per tile (tpr tiles per unit)
+        tr_on = (a.debug & 4) && blockIdx.x == 0 && trip == 2;
+        uint4 na = s.prog[0], nb = s.prog[1];
+        for (int c = 0; c < nc; ++c) {
+          const uint4 pa = na, pb = nb;
+          if (c + 1 < nc) { na = s.prog[2 * c + 2]; nb = s.prog[2 * c + 3]; }
+          const uint32_t f = pb.z;
+          NF_TRACE(1, c * 4 + 0);
+          mbar_wait(smem_u32(&s.w_full[stage]), phase);
+          if (f & (F_WAIT_X0 | F_WAIT_H)) {
+            if (f & F_WAIT_X0) { mbar_wait(smem_u32(&s.x0_ready), x0_par); x0_par ^= 1u; }
+#pragma unroll
+            for (int hc = 0; hc < 4; ++hc)
+              if (f & (0x100u << hc)) { mbar_wait(smem_u32(&s.h_ready[hc]), (h_par >> hc) & 1u); h_par ^= 1u << hc; }
           }
+          tc_fence_after();
+          NF_TRACE(1, c * 4 + 1);
+          const uint32_t buf = ((f >> 5) & 1u) ^ tile_par;
+          const uint32_t d_tmem = tmem_base + buf * 256u;
+          const uint32_t b0 = (w_base4 + (uint32_t)stage * (STAGE_BYTES >> 4)) | pb.w;
+          const uint32_t nst = f & F_NSTEP;
+          if (!(a.debug & 2)) {
+            umma_f16(d_tmem, umma_desc_lo(pa.x), umma_desc_lo(b0), pb.y, (f & F_FIRST) ? 0u : 1u);
+            if (nst > 1) umma_f16(d_tmem, umma_desc_lo(pa.y), umma_desc_lo(b0 + pb.x), pb.y, 1u);
+            if (nst > 2) umma_f16(d_tmem, umma_desc_lo(pa.z), umma_desc_lo(b0 + 2u * pb.x), pb.y, 1u);
+            if (nst > 3) umma_f16(d_tmem, umma_desc_lo(pa.w), umma_desc_lo(b0 + 3u * pb.x), pb.y, 1u);
+          }
+          if (csize == 1) umma_commit(smem_u32(&s.w_empty[stage])); else umma_commit_mc(smem_u32(&s.w_empty[stage]), cmask);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (f & F_LAST) umma_commit(smem_u32(&s.acc_full[buf]));
+        }
+        tile_par ^= odd;
+      }
     }
   } else if (warp >= 4) {
     // ================= encode + epilogue warps =================
@@ -336,10 +443,11 @@ k_render_tc(const __grid_constant__ NfPlan plan, const TcArgs a) {
     const int row = q * 32 + lane;                       // TMEM lane == tile row owned in epilogues
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t acc_par = 0, lin_count = 0;
-    for (long long u = blockIdx.x; u < it.units; u += gridDim.x)
+    for (long long trip = 0, u = blockIdx.x; trip < it.trips; ++trip, u += gridDim.x)
       for (int sub = 0; sub < it.tpr; ++sub) {
         // ---------- stage inputs of the first MLP ----------
-        if (a.mlp_only) {
+        if (a.debug & 1) {
+        } else if (a.mlp_only) {
           const NfMlpPlan& M = plan.mlp[a.which];
           for (int i = e_tid; i < (M.k0_pad >> 3) * ROWS; i += EPI_THREADS) {
             st_v4(s.X0raw + i * 16, 0, 0, 0, 0); st_v4(s.X0act + i * 16, 0, 0, 0, 0);
@@ -414,38 +522,28 @@ k_render_tc(const __grid_constant__ NfPlan plan, const TcArgs a) {
             const NfLinPlan& L = M.lin[j];
             const uint32_t buf = lin_count & 1;
             const float* bias = s.bias + ((m ? lin_base1 : 0) + j) * 256;
+            tr_on = (a.debug & 4) && blockIdx.x == 0 && trip == 2 && warp == 4 && lane == 0;
+            NF_TRACE(2, (m * 16 + j) * 4 + 0);
             mbar_wait(smem_u32(&s.acc_full[buf]), (acc_par >> buf) & 1u);
+            NF_TRACE(2, (m * 16 + j) * 4 + 1);
             acc_par ^= 1u << buf;
             tc_fence_after();
             const uint32_t t_acc = t_lane + buf * 256;
-            if (!L.is_out) {
+            if (a.debug & 1) {
+              if (!L.is_out) { for (int c = 0; c < 4; ++c) { __syncwarp(); if (lane == 0) mbar_arrive(smem_u32(&s.h_ready[c])); } }
+              else if (!a.mlp_only && plan.kind == NF_KIND_PLAIN && m == 0) { __syncwarp(); if (lane == 0) mbar_arrive(smem_u32(&s.x0_ready)); }
+            } else if (!L.is_out) {
               // hidden Linear: H <- act(acc + bias) as fp16, chunk by chunk (64 columns = one h_ready)
-              for (int c = 0; c < 4; ++c) {
-                const int col = c * 64 + half * 32;
-                uint32_t v[32];
-                tmem_ld16(t_acc + col, v); tmem_ld16(t_acc + col + 16, v + 16);
-                tmem_ld_wait();
-                uint32_t o[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  const float x0 = __uint_as_float(v[2 * i]) + bias[col + 2 * i];
-                  const float x1 = __uint_as_float(v[2 * i + 1]) + bias[col + 2 * i + 1];
-                  o[i] = pack_h2(tc_act(x0, act), tc_act(x1, act));
-                }
-                uint8_t* dst = s.H + (col >> 3) * KG_BYTES + row * 16;
-#pragma unroll
-                for (int g = 0; g < 4; ++g) st_v4(dst + g * KG_BYTES, o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
-                tc_fence_before();
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&s.h_ready[c]));
-              }
+              if (act == NF_ACT_SIN) epi_hidden<NF_ACT_SIN>(s, t_acc, bias, half, row, lane);
+              else if (act == NF_ACT_LEAKY) epi_hidden<NF_ACT_LEAKY>(s, t_acc, bias, half, row, lane);
+              else if (act == NF_ACT_RELU) epi_hidden<NF_ACT_RELU>(s, t_acc, bias, half, row, lane);
+              else epi_hidden<NF_ACT_NONE>(s, t_acc, bias, half, row, lane);
             } else if (a.mlp_only) {
               // dump raw outputs in reference column order
               const long long g = u * ROWS + row;
               for (int un = half; un < (L.n_pad >> 4); un += 2) {
                 uint32_t v[16];
-                tmem_ld16(t_acc + un * 16, v); tmem_ld_wait();
+                tmem_ld16(t_acc + un * 16, v); tmem_ld_wait(); reg_fence16(v);
                 if (g < a.n) {
 #pragma unroll
                   for (int i = 0; i < 16; ++i) {
@@ -463,7 +561,7 @@ k_render_tc(const __grid_constant__ NfPlan plan, const TcArgs a) {
               const int iu = plan.intermediate >> 4;       // 16-column units of intermediate
               for (int un = half; un <= iu; un += 2) {
                 uint32_t v[16];
-                tmem_ld16(t_acc + un * 16, v); tmem_ld_wait();
+                tmem_ld16(t_acc + un * 16, v); tmem_ld_wait(); reg_fence16(v);
                 if (un < iu) {
                   uint32_t o[8], oa[8];
 #pragma unroll
@@ -493,7 +591,7 @@ k_render_tc(const __grid_constant__ NfPlan plan, const TcArgs a) {
               // final Linear of the path -> colours (and raw density for TinyNeRF) -> composite
               if (half == 0) {
                 uint32_t v[16];
-                tmem_ld16(t_acc, v); tmem_ld_wait();
+                tmem_ld16(t_acc, v); tmem_ld_wait(); reg_fence16(v);
                 tc_fence_before();
                 float cr, cg, cb;
                 if (plan.kind == NF_KIND_TINY) {
@@ -514,6 +612,7 @@ k_render_tc(const __grid_constant__ NfPlan plan, const TcArgs a) {
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();     // no CTA exits while a peer may still signal its barriers
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
@@ -555,14 +654,44 @@ const char* tc_unsupported(const NfPlan& p) {
   return nullptr;
 }
 
-cudaError_t launch_tc(const NfPlan& plan, const TcArgs& a, long long units, cudaStream_t st) {
+cudaError_t launch_tc(const NfPlan& plan, TcArgs a, long long units, cudaStream_t st) {
+  if (const char* dbg = getenv("NF_TC_DEBUG")) a.debug = atoi(dbg);
   if (tc_unsupported(plan)) return cudaErrorNotSupported;
   cudaError_t e = cudaFuncSetAttribute(k_render_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcSmem));
   if (e != cudaSuccess) return e;
   if (units == 0) return cudaSuccess;
-  const int grid = (int)(units < tc_num_sms() ? units : tc_num_sms());
-  k_render_tc<<<grid, THREADS, sizeof(TcSmem), st>>>(plan, a);
-  return cudaGetLastError();
+  int csize = 1;   // clusters: experimental (multicast brings no L2 saving below 8 CTAs on this part)
+  if (const char* c = getenv("NF_TC_CLUSTER")) csize = atoi(c);
+  if (csize != 1 && csize != 2 && csize != 4) csize = 1;
+  const int sms = tc_num_sms();
+  // a cluster of 4 must sit inside one GPC: on B200 only 132 of 148 SMs can host such clusters at 1 CTA/SM
+  const int max_ctas = csize == 4 ? 132 : sms / csize * csize;
+  long long want = (units + csize - 1) / csize * csize;
+  const int grid = (int)(want < max_ctas ? want : max_ctas);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = sizeof(TcSmem); cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (a.debug & 4) {
+    static long long* d_trace = nullptr;
+    if (!d_trace) cudaMalloc(&d_trace, 3 * 512 * 2 * sizeof(long long));
+    cudaMemset(d_trace, 0, 3 * 512 * 2 * sizeof(long long));
+    a.trace = d_trace;
+    cudaError_t e2 = cudaLaunchKernelEx(&cfg, k_render_tc, plan, a);
+    cudaStreamSynchronize(st);
+    static long long h[3 * 512 * 2];
+    cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost);
+    long long t0 = -1;
+    for (int i = 0; i < 3 * 512; ++i) if (h[2 * i + 1] && (t0 < 0 || h[2 * i + 1] < t0)) t0 = h[2 * i + 1];
+    static int printed = 0;
+    if (t0 >= 0 && printed++ < 1)
+      for (int r = 0; r < 3; ++r) for (int i = 0; i < 512; ++i) if (h[2 * (r * 512 + i) + 1])
+        printf("TRACE role=%d tag=%lld t=%lld\n", r, h[2 * (r * 512 + i)], h[2 * (r * 512 + i) + 1] - t0);
+    return e2;
+  }
+  return cudaLaunchKernelEx(&cfg, k_render_tc, plan, a);
 }
 
 }  // namespace
