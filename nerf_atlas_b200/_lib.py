@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libnerf_b200.so")
+LIB_PATH = os.path.join(HERE, os.environ.get("NF_LIB", "libnerf_b200.so"))
 
 # enums of include/nerf_b200.h
 ACT = {"none": 0, "leaky_relu": 1, "sin": 2, "relu": 3}

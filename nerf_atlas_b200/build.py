@@ -10,11 +10,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SOURCES = ["nf_api.cu", "nf_fp32.cu", "nf_tc.cu"]
 HEADERS = ["nf_common.cuh", "nf_kernels.h", os.path.join("..", "..", "include", "nerf_b200.h")]
-LIB = os.path.join(HERE, "libnerf_b200.so")
+TRACE = bool(os.environ.get("NF_TC_TRACE"))     # debug build: clock64 timeline of one tile (profiles/)
+LIB = os.path.join(HERE, "libnerf_b200_trace.so" if TRACE else "libnerf_b200.so")
 STAMP = LIB + ".stamp"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC", "--shared", "-Xptxas", "-v"]
+         "-Xcompiler", "-fPIC", "--shared", "-Xptxas", "-v"] + (["-DNF_TC_TRACE"] if TRACE else [])
 
 def _digest() -> str:
   h = hashlib.sha256()

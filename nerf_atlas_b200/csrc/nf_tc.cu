@@ -13,10 +13,11 @@
 //   D = [128 x N] fp32 in TMEM, two 256-column accumulators used alternately by consecutive
 //       layers so that layer j+1's MMAs start on the K-chunks of layer j's output as soon as the
 //       epilogue has written them (chunk-granular h_ready barriers).
-// Warp roles: 0 = weight producer, 1 = MMA issuer (one thread), 2 = TMEM allocator,
+// Warp roles: 0, 2, 3 = weight producers (one ring stage each; 2 also allocates TMEM), 1 = MMA issuer (one thread),
 // 4..11 = encode/epilogue warps (TMEM lane quarter = warp % 4, column half = (warp-4)/4).
 #include <cstdio>
 #include <cstdlib>
+#include <cstddef>
 #include "nf_common.cuh"
 #include "nf_kernels.h"
 
@@ -31,7 +32,7 @@ constexpr int MAX_LIN_TOTAL = 12;
 constexpr int THREADS = 384;
 constexpr int EPI_THREADS = 256;
 constexpr int KG_BYTES = ROWS * 16;       // one 8-column K-group of an A operand: 128 rows x 16 B
-constexpr int MAX_CHUNKS = 64;
+constexpr int MAX_CHUNKS = 56;
 // flags of one weight chunk of the per-tile MMA program: bits 0-2 = UMMA steps in the chunk (1..4)
 constexpr uint32_t F_NSTEP = 7, F_FIRST = 8, F_LAST = 16, F_BUF = 32, F_WAIT_X0 = 64, F_WAIT_H = 0xF00;
 
@@ -50,11 +51,15 @@ struct TcSmem {
   float warp_agg[4]; int warp_cont[4]; float warp_sum[4][4]; float carry[8];
   unsigned long long w_full[STAGES], w_empty[STAGES], acc_full[2], h_ready[4], x0_ready;
   uint32_t tmem_base;
-  int n_chunks, odd_lin;
-  uint4 prog[2 * MAX_CHUNKS];   // per-tile MMA program, one entry per weight chunk: {a_desc_lo[4]}, {b_step, idesc, flags, -}
+  int n_chunks, pad_;
   uint2 chunks[MAX_CHUNKS];     // per-tile weight chunk list: {byte offset into packed, bytes}
 };
 static_assert(sizeof(TcSmem) <= 227 * 1024, "tensor pipeline smem");
+
+// Per-tile MMA program, built on the host and passed as a kernel parameter so that the issuing thread reads it
+// through uniform constant loads (LDCU) and every descriptor lives in uniform registers.
+struct TcProgEnt { uint32_t a4[4]; uint32_t bstep4, idesc, flags, bhi; };   // a4 = (A smem offset >> 4) | LBO field
+struct TcProg { int32_t n_chunks, odd_lin; TcProgEnt e[MAX_CHUNKS]; };
 
 struct TcArgs {
   const uint8_t* packed;
@@ -86,18 +91,40 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
-__device__ __noinline__ void mbar_timeout(uint32_t bar) {
-  if ((threadIdx.x & 31) == 0) printf("nf_tc: mbarrier timeout (block %d thread %d bar %u)\n", blockIdx.x, threadIdx.x, bar);
-  __trap();
+// A protocol bug must surface as a trapped launch (cudaErrorLaunchFailure), never as a hung GPU.  No function call
+// here: a call in the wait loop makes ptxas drop the MMA issuer's descriptors out of uniform registers.
+__device__ __forceinline__ void mbar_timeout(uint32_t) { __trap(); }
+// Non-blocking probe. Measured on B200 (profiles/trace_*.txt): a failed mbarrier.try_wait suspends the thread for a
+// ~440-cycle quantum and is NOT woken early by async-proxy completions (TMA complete_tx, tcgen05.commit), so every
+// wait on the critical path polls with test_wait instead.
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) { if (++spins > (1u << 22)) mbar_timeout(bar); }
+  while (!mbar_test_wait(bar, parity)) { if (++spins > (1u << 26)) mbar_timeout(bar); }
 }
-// for waits that are off the critical path (the weight producer): yield issue slots while waiting
+// two barriers polled together: the two test_wait latencies (~150 cycles each) overlap
+__device__ __forceinline__ void mbar_wait2(uint32_t bar_a, uint32_t par_a, uint32_t bar_b, uint32_t par_b) {
+  uint32_t spins = 0;
+  while (true) {
+    const bool oa = mbar_test_wait(bar_a, par_a), ob = mbar_test_wait(bar_b, par_b);
+    if (oa && ob) break;
+    if (++spins > (1u << 26)) mbar_timeout(oa ? bar_b : bar_a);
+  }
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n .reg .pred P1;\n elect.sync _|P1, 0xffffffff;\n selp.u32 %0, 1, 0, P1;\n}" : "=r"(pred));
+  return pred != 0;
+}
+// for the 8 epilogue warps (they share schedulers with the MMA issuer): poll, but yield between polls
 __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) { __nanosleep(128); if (++spins > (1u << 22)) mbar_timeout(bar); }
+  while (!mbar_test_wait(bar, parity)) { __nanosleep(32); if (++spins > (1u << 24)) mbar_timeout(bar); }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -171,7 +198,11 @@ __device__ __forceinline__ void st_v4(uint8_t* p, uint32_t a, uint32_t b, uint32
   *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d);
 }
 
+#ifdef NF_TC_TRACE   // compile-time only: the trace stores push the MMA issuer's descriptors out of uniform registers
 #define NF_TRACE(role, tag) do { if (tr_on && tr_n[role] < 512) { tr[(role * 512 + tr_n[role]) * 2] = (tag); tr[(role * 512 + tr_n[role]) * 2 + 1] = clock64(); ++tr_n[role]; } } while (0)
+#else
+#define NF_TRACE(role, tag) do { (void)tr_on; } while (0)
+#endif
 
 // ---- the sequence of tiles a CTA walks (identical in every warp role) ---------------------------
 struct TileIter {
@@ -185,7 +216,8 @@ struct TileIter {
 // ---- epilogue of a hidden Linear: H <- fp16(act(acc + bias)), in place, 64-column chunks ----------
 // TMEM loads of chunk c+1 are in flight while chunk c is converted and stored.
 template <int ACT>
-__device__ __forceinline__ void epi_hidden(TcSmem& s, uint32_t t_acc, const float* __restrict__ bias, int half, int row, int lane) {
+__device__ __forceinline__ void epi_hidden(TcSmem& s, uint32_t t_acc, const float* __restrict__ bias, int half, int row, int lane,
+                                           int trace_tag = -1, bool tr_on_ = false, long long* tr_ = nullptr, int* tr_n_ = nullptr) {
   uint32_t v[2][32];
   tmem_ld16(t_acc + half * 32, v[0]); tmem_ld16(t_acc + half * 32 + 16, v[0] + 16);
 #pragma unroll
@@ -209,6 +241,7 @@ __device__ __forceinline__ void epi_hidden(TcSmem& s, uint32_t t_acc, const floa
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&s.h_ready[c]));
+    if (trace_tag >= 0 && tr_on_ && lane == 0 && *tr_n_ < 512) { tr_[(2 * 512 + *tr_n_) * 2] = 1000 + trace_tag * 4 + c; tr_[(2 * 512 + *tr_n_) * 2 + 1] = clock64(); ++*tr_n_; }
   }
 }
 
@@ -299,7 +332,7 @@ __device__ __forceinline__ void composite_tile(TcSmem& s, const NfPlan& plan, co
 
 // =================================================================================================
 __global__ void __launch_bounds__(THREADS, 1)
-k_render_tc(const __grid_constant__ NfPlan plan, const TcArgs a) {
+k_render_tc(const __grid_constant__ NfPlan plan, const __grid_constant__ TcProg prog, const TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   TcSmem& s = *reinterpret_cast<TcSmem*>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -308,11 +341,7 @@ k_render_tc(const __grid_constant__ NfPlan plan, const TcArgs a) {
   const int m_begin = a.mlp_only ? a.which : 0, m_end = a.mlp_only ? a.which + 1 : plan.n_mlps;
   const int lin_base1 = plan.mlp[0].n_lin;   // global linear index of refl MLP's first Linear
 
-  long long* tr = a.trace; int tr_n[3] = {0, 0, 0}; bool tr_on = false;
-  // A cluster of `csize` CTAs shares every weight chunk: CTA (chunk % csize) issues one multicast bulk copy
-  // that lands in the same ring stage of every CTA, so L2 is read once per cluster instead of once per SM.
-  const uint32_t csize = cluster_nctarank(), crank = cluster_ctarank();
-  const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
+  long long* tr = a.trace; int tr_n[3] = {0, 0, 0}; bool tr_on = false; (void)tr; (void)tr_n;
   // ---- one-time setup ----
   for (int i = threadIdx.x; i < MAX_LIN_TOTAL * 256; i += THREADS) {
     const int g = i >> 8, n = i & 255;
@@ -323,7 +352,7 @@ k_render_tc(const __grid_constant__ NfPlan plan, const TcArgs a) {
     s.bias[i] = v;
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(smem_u32(&s.w_full[i]), 1); mbar_init(smem_u32(&s.w_empty[i]), csize); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(smem_u32(&s.w_full[i]), 1); mbar_init(smem_u32(&s.w_empty[i]), 1); }
     mbar_init(smem_u32(&s.acc_full[0]), 1); mbar_init(smem_u32(&s.acc_full[1]), 1);
     for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&s.h_ready[i]), 8);
     mbar_init(smem_u32(&s.x0_ready), 8);
@@ -334,106 +363,98 @@ k_render_tc(const __grid_constant__ NfPlan plan, const TcArgs a) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (warp == 3 && lane == 0) {
-    // The per-tile MMA program and weight chunk list (identical for every tile): one entry per weight chunk.
-    const uint32_t Hs = smem_u32(s.H), Xr = smem_u32(s.X0raw), Xa = smem_u32(s.X0act);
-    int nc = 0, lin = 0;
-    for (int m = m_begin; m < m_end; ++m) {
-      bool x0_first = true;
-      for (int j = 0; j < plan.mlp[m].n_lin; ++j, ++lin) {
+    // weight chunk list for the producers (identical for every tile): {byte offset into packed, bytes}
+    int nc = 0;
+    for (int m = m_begin; m < m_end; ++m)
+      for (int j = 0; j < plan.mlp[m].n_lin; ++j) {
         const NfLinPlan& L = plan.mlp[m].lin[j];
         const int steps = (L.k0_pad + L.k_hidden) >> 4;
-        const uint32_t b_lbo = (uint32_t)L.n_pad * 16u, idesc = umma_idesc(L.n_pad);
-        uint32_t hmask = 0;
-        for (int c = 0; c < L.n_chunks; ++c) {
-          const int nst = min(SPC, steps - SPC * c);
-          uint32_t f = (uint32_t)nst | (c == 0 ? F_FIRST : 0u) | (c == L.n_chunks - 1 ? F_LAST : 0u) | ((lin & 1) ? F_BUF : 0u);
-          uint32_t alo[4] = {0, 0, 0, 0};
-          for (int q4 = 0; q4 < nst; ++q4) {
-            const int k = (c * SPC + q4) << 4;
-            uint32_t a_addr;
-            if (k < L.k0_pad) {
-              if (x0_first) { f |= F_WAIT_X0; x0_first = false; }
-              a_addr = (L.x0_raw ? Xr : Xa) + (uint32_t)(k >> 3) * KG_BYTES;
-            } else {
-              const int kh = k - L.k0_pad, hc = kh >> 6;
-              if (!(hmask & (1u << hc))) { f |= 0x100u << hc; hmask |= 1u << hc; }
-              a_addr = Hs + (uint32_t)(kh >> 3) * KG_BYTES;
-            }
-            alo[q4] = ((a_addr >> 4) & 0x3FFFu) | ((uint32_t)(KG_BYTES >> 4) << 16);
-          }
-          s.prog[2 * nc] = make_uint4(alo[0], alo[1], alo[2], alo[3]);
-          s.prog[2 * nc + 1] = make_uint4((2u * b_lbo) >> 4, idesc, f, (b_lbo >> 4) << 16);
-          s.chunks[nc] = make_uint2((uint32_t)(L.w16_off + (int64_t)c * (2 * SPC) * L.n_pad * 16), (uint32_t)nst * 2u * b_lbo);
-          ++nc;
-        }
+        for (int c = 0; c < L.n_chunks; ++c, ++nc)
+          s.chunks[nc] = make_uint2((uint32_t)(L.w16_off + (int64_t)c * (2 * SPC) * L.n_pad * 16),
+                                    (uint32_t)min(SPC, steps - SPC * c) * 2u * (uint32_t)L.n_pad * 16u);
       }
-    }
-    s.n_chunks = nc; s.odd_lin = lin & 1;
+    s.n_chunks = nc;
   }
   tc_fence_before();
   __syncthreads();
-  if (csize > 1) cluster_sync_all();     // peers' barriers are initialised before anyone multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = s.tmem_base;
+  if (tmem_base != 0) { if (threadIdx.x == 0) printf("nf_tc: unexpected TMEM base %u\n", tmem_base); __trap(); }
 
-  if (warp == 0) {
-    // ================= weight producer: ONE thread streams every Linear's chunks through the ring =================
+  if (warp == 0 || warp == 2 || warp == 3) {
+    // ================= weight producers: three single-thread issuers, one per ring stage =================
+    // cp.async.bulk costs the ISSUING warp ~450 cycles per copy (about 2 copies in flight per warp, any size;
+    // profiles/microbench/copy_bw.cu), so one issuer tops out at ~75 B/cycle with 32 KB chunks; issuers scale.
     if (lane == 0) {
-      int stage = 0, cidx = 0; uint32_t phase = 0;
+      const int p = warp == 0 ? 0 : warp - 1;           // producer index == ring stage it owns
       const int nc = s.n_chunks;
-      for (long long trip = 0; trip < it.trips * it.tpr; ++trip) {   // one pass per tile (tpr tiles per unit)
-        tr_on = (a.debug & 4) && blockIdx.x == 0 && trip == 2;
-        for (int c = 0; c < nc; ++c, ++cidx) {
-          const uint2 ch = s.chunks[c];
-          mbar_wait_backoff(smem_u32(&s.w_empty[stage]), phase ^ 1);
-          NF_TRACE(0, c);
-          mbar_expect_tx(smem_u32(&s.w_full[stage]), ch.y);
-          if (csize == 1) bulk_g2s(smem_u32(s.W[stage]), a.packed + ch.x, ch.y, smem_u32(&s.w_full[stage]));
-          else if ((uint32_t)(cidx % (int)csize) == crank)
-            bulk_g2s_mc(smem_u32(s.W[stage]), a.packed + ch.x, ch.y, smem_u32(&s.w_full[stage]), cmask);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
+      const long long total = it.trips * it.tpr * nc;
+      int c = p % nc;
+      for (long long g = p; g < total; g += STAGES) {
+        const uint2 ch = s.chunks[c];
+        tr_on = (a.debug & 4) && blockIdx.x == 0 && p == 0 && g / nc == 2;
+        mbar_wait(smem_u32(&s.w_empty[p]), (uint32_t)(((g / STAGES) & 1) ^ 1));
+        NF_TRACE(0, c);
+        mbar_expect_tx(smem_u32(&s.w_full[p]), ch.y);
+        bulk_g2s(smem_u32(s.W[p]), a.packed + ch.x, ch.y, smem_u32(&s.w_full[p]));
+        c += STAGES; while (c >= nc) c -= nc;
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer: ONE thread walks the chunk program and issues every tcgen05.mma =================
     if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
+      uint32_t stage = 0, phase = 0;
       uint32_t h_par = 0, x0_par = 0, tile_par = 0;   // expected parities of h_ready[0..3], x0_ready; accumulator flip
-      const int nc = s.n_chunks; const uint32_t odd = (uint32_t)s.odd_lin;
-      const uint32_t w_base4 = smem_u32(s.W) >> 4;
-      for (long long trip = 0; trip < it.trips * it.tpr; ++trip) {   // one pass per tile (tpr tiles per unit)
+      const uint32_t base4 = smem_u32(smem_raw) >> 4;
+      const uint32_t w4 = base4 + (uint32_t)(offsetof(TcSmem, W) >> 4);
+      const uint32_t bar_wfull = smem_u32(&s.w_full[0]), bar_wempty = smem_u32(&s.w_empty[0]);
+      const uint32_t bar_h = smem_u32(&s.h_ready[0]), bar_x0 = smem_u32(&s.x0_ready), bar_acc = smem_u32(&s.acc_full[0]);
+      for (long long trip = 0; trip < it.trips * it.tpr; ++trip) {
         tr_on = (a.debug & 4) && blockIdx.x == 0 && trip == 2;
-        uint4 na = s.prog[0], nb = s.prog[1];
-        for (int c = 0; c < nc; ++c) {
-          const uint4 pa = na, pb = nb;
-          if (c + 1 < nc) { na = s.prog[2 * c + 2]; nb = s.prog[2 * c + 3]; }
-          const uint32_t f = pb.z;
+        for (int c = 0; c < prog.n_chunks; ++c) {
+          const TcProgEnt& e = prog.e[c];
+          const uint32_t f = e.flags;
           NF_TRACE(1, c * 4 + 0);
-          mbar_wait(smem_u32(&s.w_full[stage]), phase);
-          if (f & (F_WAIT_X0 | F_WAIT_H)) {
-            if (f & F_WAIT_X0) { mbar_wait(smem_u32(&s.x0_ready), x0_par); x0_par ^= 1u; }
-#pragma unroll
-            for (int hc = 0; hc < 4; ++hc)
-              if (f & (0x100u << hc)) { mbar_wait(smem_u32(&s.h_ready[hc]), (h_par >> hc) & 1u); h_par ^= 1u << hc; }
+          // One polling loop for everything this chunk needs (weights landed, x0 staged, H chunk(s) written): the
+          // test_wait latencies (~150 cycles each) overlap instead of adding up.
+          {
+            const uint32_t hm = (f >> 8) & 15u;
+            const uint32_t hc0 = hm ? (uint32_t)__ffs((int)hm) - 1u : 0u;          // first needed H chunk
+            const uint32_t hm2 = hm & (hm - 1u);                                    // a second one (misaligned skip layers)
+            const uint32_t hc1 = hm2 ? (uint32_t)__ffs((int)hm2) - 1u : hc0;
+            uint32_t spins = 0;
+            while (true) {
+              bool ok = mbar_test_wait(bar_wfull + stage * 8u, phase);
+              if (hm) ok &= mbar_test_wait(bar_h + hc0 * 8u, (h_par >> hc0) & 1u);
+              if (hm2) ok &= mbar_test_wait(bar_h + hc1 * 8u, (h_par >> hc1) & 1u);
+              if (f & F_WAIT_X0) ok &= mbar_test_wait(bar_x0, x0_par);
+              if (ok) break;
+              if (++spins > (1u << 26)) __trap();
+            }
+            h_par ^= hm;
+            if (f & F_WAIT_X0) x0_par ^= 1u;
           }
-          tc_fence_after();
+          if (!(a.debug & 8)) tc_fence_after();
           NF_TRACE(1, c * 4 + 1);
           const uint32_t buf = ((f >> 5) & 1u) ^ tile_par;
-          const uint32_t d_tmem = tmem_base + buf * 256u;
-          const uint32_t b0 = (w_base4 + (uint32_t)stage * (STAGE_BYTES >> 4)) | pb.w;
+          const uint32_t d_tmem = buf * 256u;                       // TMEM base is 0 (checked at setup)
+          const uint32_t b0 = (w4 + stage * (STAGE_BYTES >> 4)) | e.bhi;
           const uint32_t nst = f & F_NSTEP;
+          // debug & 32 (timing experiment): issue half-width MMAs (N/2) -- results are wrong, execution time halves
+          const uint32_t idesc = (a.debug & 32) ? ((e.idesc & ~(0x3Fu << 17)) | ((((e.idesc >> 17) & 0x3Fu) >> 1) << 17)) : e.idesc;
           if (!(a.debug & 2)) {
-            umma_f16(d_tmem, umma_desc_lo(pa.x), umma_desc_lo(b0), pb.y, (f & F_FIRST) ? 0u : 1u);
-            if (nst > 1) umma_f16(d_tmem, umma_desc_lo(pa.y), umma_desc_lo(b0 + pb.x), pb.y, 1u);
-            if (nst > 2) umma_f16(d_tmem, umma_desc_lo(pa.z), umma_desc_lo(b0 + 2u * pb.x), pb.y, 1u);
-            if (nst > 3) umma_f16(d_tmem, umma_desc_lo(pa.w), umma_desc_lo(b0 + 3u * pb.x), pb.y, 1u);
+            umma_f16(d_tmem, umma_desc_lo(base4 + e.a4[0]), umma_desc_lo(b0), idesc, (f & F_FIRST) ? 0u : 1u);
+            if (nst > 1) umma_f16(d_tmem, umma_desc_lo(base4 + e.a4[1]), umma_desc_lo(b0 + e.bstep4), idesc, 1u);
+            if (nst > 2) umma_f16(d_tmem, umma_desc_lo(base4 + e.a4[2]), umma_desc_lo(b0 + 2u * e.bstep4), idesc, 1u);
+            if (nst > 3) umma_f16(d_tmem, umma_desc_lo(base4 + e.a4[3]), umma_desc_lo(b0 + 3u * e.bstep4), idesc, 1u);
           }
-          if (csize == 1) umma_commit(smem_u32(&s.w_empty[stage])); else umma_commit_mc(smem_u32(&s.w_empty[stage]), cmask);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          if (f & F_LAST) umma_commit(smem_u32(&s.acc_full[buf]));
+          NF_TRACE(1, c * 4 + 2);
+          umma_commit(bar_wempty + stage * 8u);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          if (f & F_LAST) umma_commit(bar_acc + buf * 8u);
+          NF_TRACE(1, c * 4 + 3);
         }
-        tile_par ^= odd;
+        tile_par ^= (uint32_t)prog.odd_lin;
       }
     }
   } else if (warp >= 4) {
@@ -524,7 +545,7 @@ k_render_tc(const __grid_constant__ NfPlan plan, const TcArgs a) {
             const float* bias = s.bias + ((m ? lin_base1 : 0) + j) * 256;
             tr_on = (a.debug & 4) && blockIdx.x == 0 && trip == 2 && warp == 4 && lane == 0;
             NF_TRACE(2, (m * 16 + j) * 4 + 0);
-            mbar_wait(smem_u32(&s.acc_full[buf]), (acc_par >> buf) & 1u);
+            mbar_wait_backoff(smem_u32(&s.acc_full[buf]), (acc_par >> buf) & 1u);
             NF_TRACE(2, (m * 16 + j) * 4 + 1);
             acc_par ^= 1u << buf;
             tc_fence_after();
@@ -534,8 +555,13 @@ k_render_tc(const __grid_constant__ NfPlan plan, const TcArgs a) {
               else if (!a.mlp_only && plan.kind == NF_KIND_PLAIN && m == 0) { __syncwarp(); if (lane == 0) mbar_arrive(smem_u32(&s.x0_ready)); }
             } else if (!L.is_out) {
               // hidden Linear: H <- act(acc + bias) as fp16, chunk by chunk (64 columns = one h_ready)
+#ifdef NF_TC_TRACE
+              if (act == NF_ACT_SIN) epi_hidden<NF_ACT_SIN>(s, t_acc, bias, half, row, lane, m * 16 + j, tr_on, tr, &tr_n[2]);
+              else if (act == NF_ACT_LEAKY) epi_hidden<NF_ACT_LEAKY>(s, t_acc, bias, half, row, lane, m * 16 + j, tr_on, tr, &tr_n[2]);
+#else
               if (act == NF_ACT_SIN) epi_hidden<NF_ACT_SIN>(s, t_acc, bias, half, row, lane);
               else if (act == NF_ACT_LEAKY) epi_hidden<NF_ACT_LEAKY>(s, t_acc, bias, half, row, lane);
+#endif
               else if (act == NF_ACT_RELU) epi_hidden<NF_ACT_RELU>(s, t_acc, bias, half, row, lane);
               else epi_hidden<NF_ACT_NONE>(s, t_acc, bias, half, row, lane);
             } else if (a.mlp_only) {
@@ -612,7 +638,6 @@ k_render_tc(const __grid_constant__ NfPlan plan, const TcArgs a) {
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
-  if (csize > 1) cluster_sync_all();     // no CTA exits while a peer may still signal its barriers
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
@@ -654,32 +679,62 @@ const char* tc_unsupported(const NfPlan& p) {
   return nullptr;
 }
 
+// Builds the per-tile MMA program (one entry per weight chunk) for MLPs [m_begin, m_end).
+void build_prog(const NfPlan& plan, int m_begin, int m_end, TcProg* P) {
+  *P = TcProg{};
+  const uint32_t Hs = (uint32_t)offsetof(TcSmem, H), Xr = (uint32_t)offsetof(TcSmem, X0raw), Xa = (uint32_t)offsetof(TcSmem, X0act);
+  int nc = 0, lin = 0;
+  for (int m = m_begin; m < m_end; ++m) {
+    bool x0_first = true;
+    for (int j = 0; j < plan.mlp[m].n_lin; ++j, ++lin) {
+      const NfLinPlan& L = plan.mlp[m].lin[j];
+      const int steps = (L.k0_pad + L.k_hidden) >> 4;
+      const uint32_t b_lbo = (uint32_t)L.n_pad * 16u;
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(L.n_pad >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
+      uint32_t hmask = 0;
+      for (int c = 0; c < L.n_chunks; ++c, ++nc) {
+        const int nst = steps - SPC * c < SPC ? steps - SPC * c : SPC;
+        TcProgEnt& e = P->e[nc];
+        uint32_t f = (uint32_t)nst | (c == 0 ? F_FIRST : 0u) | (c == L.n_chunks - 1 ? F_LAST : 0u) | ((lin & 1) ? F_BUF : 0u);
+        for (int q4 = 0; q4 < nst; ++q4) {
+          const int k = (c * SPC + q4) << 4;
+          uint32_t off;
+          if (k < L.k0_pad) {
+            if (x0_first) { f |= F_WAIT_X0; x0_first = false; }
+            off = (L.x0_raw ? Xr : Xa) + (uint32_t)(k >> 3) * KG_BYTES;
+          } else {
+            const int kh = k - L.k0_pad, hc = kh >> 6;
+            if (!(hmask & (1u << hc))) { f |= 0x100u << hc; hmask |= 1u << hc; }
+            off = Hs + (uint32_t)(kh >> 3) * KG_BYTES;
+          }
+          e.a4[q4] = (off >> 4) | ((uint32_t)(KG_BYTES >> 4) << 16);
+        }
+        e.bstep4 = (2u * b_lbo) >> 4; e.idesc = idesc; e.flags = f; e.bhi = (b_lbo >> 4) << 16;
+      }
+    }
+  }
+  P->n_chunks = nc; P->odd_lin = lin & 1;
+}
+
 cudaError_t launch_tc(const NfPlan& plan, TcArgs a, long long units, cudaStream_t st) {
   if (const char* dbg = getenv("NF_TC_DEBUG")) a.debug = atoi(dbg);
   if (tc_unsupported(plan)) return cudaErrorNotSupported;
   cudaError_t e = cudaFuncSetAttribute(k_render_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcSmem));
   if (e != cudaSuccess) return e;
   if (units == 0) return cudaSuccess;
-  int csize = 1;   // clusters: experimental (multicast brings no L2 saving below 8 CTAs on this part)
-  if (const char* c = getenv("NF_TC_CLUSTER")) csize = atoi(c);
-  if (csize != 1 && csize != 2 && csize != 4) csize = 1;
   const int sms = tc_num_sms();
-  // a cluster of 4 must sit inside one GPC: on B200 only 132 of 148 SMs can host such clusters at 1 CTA/SM
-  const int max_ctas = csize == 4 ? 132 : sms / csize * csize;
-  long long want = (units + csize - 1) / csize * csize;
-  const int grid = (int)(want < max_ctas ? want : max_ctas);
+  const int grid = (int)(units < sms ? units : sms);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = sizeof(TcSmem); cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  cfg.attrs = nullptr; cfg.numAttrs = 0;
+  TcProg prog;
+  build_prog(plan, a.mlp_only ? a.which : 0, a.mlp_only ? a.which + 1 : plan.n_mlps, &prog);
   if (a.debug & 4) {
     static long long* d_trace = nullptr;
     if (!d_trace) cudaMalloc(&d_trace, 3 * 512 * 2 * sizeof(long long));
     cudaMemset(d_trace, 0, 3 * 512 * 2 * sizeof(long long));
     a.trace = d_trace;
-    cudaError_t e2 = cudaLaunchKernelEx(&cfg, k_render_tc, plan, a);
+    cudaError_t e2 = cudaLaunchKernelEx(&cfg, k_render_tc, plan, prog, a);
     cudaStreamSynchronize(st);
     static long long h[3 * 512 * 2];
     cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost);
@@ -691,7 +746,7 @@ cudaError_t launch_tc(const NfPlan& plan, TcArgs a, long long units, cudaStream_
         printf("TRACE role=%d tag=%lld t=%lld\n", r, h[2 * (r * 512 + i)], h[2 * (r * 512 + i) + 1] - t0);
     return e2;
   }
-  return cudaLaunchKernelEx(&cfg, k_render_tc, plan, a);
+  return cudaLaunchKernelEx(&cfg, k_render_tc, plan, prog, a);
 }
 
 }  // namespace
