@@ -132,6 +132,13 @@ int nf_hash_encode(const nf_model_desc* desc, const void* packed, const float* p
 int nf_composite(const nf_model_desc* desc, const float* sigma_raw, const float* feats,
                  const float* rays, int64_t n_rays, const float* ts, int32_t T, int64_t ts_ray_stride,
                  float* rgb_out, float* alpha_out, float* weights_out, void* stream);
+/* Hierarchical resampling for the coarse+fine configuration: restatement of the reference's dead
+ * sample_pdf (reference src/nerf.py:1745-1779, called from CoarseFineNeRF.from_pts nerf.py:573-577):
+ * bins = mid-points of ts_coarse[T]; pdf from weights[r, 1:T-1] + 1e-5; inverse-CDF at u[R,Nf] in [0,1)
+ * (searchsorted right, linear interpolation); the Nf new positions are merged with ts_coarse and
+ * written sorted: ts_out[R, T+Nf] (the per-ray ts of the fine pass, ts_ray_stride = T+Nf). */
+int nf_sample_pdf(const float* ts_coarse, int32_t T, const float* weights, int64_t n_rays,
+                  const float* u, int32_t n_fine, float* ts_out, void* stream);
 /* One SkipConnMLP.forward (reference src/neural_blocks.py:279-296) on assembled inputs
  * x0[N,in_dims] -> out[N,out_dims]; which = 0 density MLP, 1 refl MLP. */
 int nf_mlp_forward(const nf_model_desc* desc, const void* packed, int32_t which,

@@ -15,7 +15,7 @@ LIB = os.path.join(HERE, "libnerf_b200_trace.so" if TRACE else "libnerf_b200.so"
 STAMP = LIB + ".stamp"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC", "--shared", "-Xptxas", "-v"] + (["-DNF_TC_TRACE"] if TRACE else [])
+         "-Xcompiler", "-fPIC", "--shared", "-Xptxas", "-v"] + ([f"-DNF_TC_TRACE={os.environ.get('NF_TC_TRACE')}"] if TRACE else [])
 
 def _digest() -> str:
   h = hashlib.sha256()

@@ -124,6 +124,16 @@ int nf_composite(const nf_model_desc* desc, const float* sigma_raw, const float*
   return e == cudaSuccess ? 0 : cuda_fail(e, "nf_composite");
 }
 
+int nf_sample_pdf(const float* ts_coarse, int32_t T, const float* weights, int64_t n_rays, const float* u, int32_t n_fine,
+                  float* ts_out, void* stream) {
+  if (n_rays < 0) return fail(NF_E_BADARG, "n_rays < 0");
+  if (n_rays == 0) return 0;
+  if (!ts_coarse || !weights || !u || !ts_out) return fail(NF_E_BADARG, "nf_sample_pdf: null pointer");
+  if (T < 3 || T > 256 || n_fine < 1 || n_fine > 256) return fail(NF_E_UNSUPPORTED, "nf_sample_pdf: need 3 <= T <= 256 and 1 <= n_fine <= 256");
+  cudaError_t e = nf_launch_sample_pdf(ts_coarse, T, weights, n_rays, u, n_fine, ts_out, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nf_sample_pdf");
+}
+
 int nf_mlp_forward(const nf_model_desc* desc, const void* packed, int32_t which, const float* x0, int64_t n, float* out,
                    int32_t precision, void* stream) {
   NfPlan p; if (int rc = plan_of(desc, &p)) return rc;

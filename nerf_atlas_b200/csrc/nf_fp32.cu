@@ -295,6 +295,62 @@ __global__ void k_composite(int density_act, int feat_unused, int bg, const floa
   }
 }
 
+// Inverse-CDF resampling + sorted merge, one warp per ray (T, Nf <= 256).  reference src/nerf.py:1745-1779 (restated).
+constexpr int PDF_MAX = 256;
+__global__ void k_sample_pdf(const float* __restrict__ ts, int T, const float* __restrict__ weights, long long n_rays,
+                             const float* __restrict__ u, int nf, float* __restrict__ out) {
+  __shared__ float s_cdf[8][PDF_MAX];
+  __shared__ float s_new[8][PDF_MAX];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  float* cdf = s_cdf[wib]; float* nw = s_new[wib];
+  const int nb = T - 1;                                   // bins (mid-points) == cdf entries
+  for (long long ray = warp; ray < n_rays; ray += nwarps) {
+    const float* w = weights + ray * T + 1;               // weights[1:-1]: T-2 values
+    // sum of (w + 1e-5), then pdf and its running sum; sequential adds like torch.cumsum
+    float part = 0.f;
+    for (int i = lane; i < T - 2; i += 32) part += __ldg(w + i) + 1e-5f;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+    if (lane == 0) {
+      float c = 0.f; cdf[0] = 0.f;
+      for (int i = 0; i < T - 2; ++i) { c += (__ldg(w + i) + 1e-5f) / part; cdf[i + 1] = c; }
+    }
+    __syncwarp();
+    for (int j = lane; j < nf; j += 32) {
+      const float uu = __ldg(u + ray * nf + j);
+      int lo = 0, hi = nb;                                // searchsorted(cdf, u, right=True): first index with cdf > u
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (cdf[mid] > uu) hi = mid; else lo = mid + 1; }
+      const int below = max(lo - 1, 0), above = min(lo, nb - 1);
+      const float cb = cdf[below], ca = cdf[above];
+      float denom = ca - cb; if (denom < 1e-5f) denom = 1.f;
+      const float t = (uu - cb) / denom;
+      const float bb = 0.5f * (__ldg(ts + below) + __ldg(ts + below + 1)), ba = 0.5f * (__ldg(ts + above) + __ldg(ts + above + 1));
+      nw[j] = __fadd_rn(bb, __fmul_rn(t, ba - bb));
+    }
+    __syncwarp();
+    // rank-based merge of {coarse ts (sorted), new samples (unsorted)} into the sorted output; ties: coarse first,
+    // then new samples by index
+    float* o = out + ray * (T + nf);
+    for (int j = lane; j < nf; j += 32) {
+      const float v = nw[j];
+      int lo = 0, hi = T;                                 // coarse ts <= v
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(ts + mid) <= v) lo = mid + 1; else hi = mid; }
+      int r = lo;
+      for (int k = 0; k < nf; ++k) { const float x = nw[k]; r += (x < v) || (x == v && k < j); }
+      o[r] = v;
+    }
+    for (int i = lane; i < T; i += 32) {
+      const float v = __ldg(ts + i);
+      int r = i;
+      for (int k = 0; k < nf; ++k) r += nw[k] < v;
+      o[r] = v;
+    }
+    __syncwarp();
+  }
+}
+
 // ---- packing -----------------------------------------------------------------------------------
 // W[n][k] (nn.Linear, row-major) -> Wt[k][n_pad] fp32, zero padded.
 __global__ void k_pack_fp32(const float* __restrict__ W, const float* __restrict__ b, float* __restrict__ Wt,
@@ -363,6 +419,15 @@ cudaError_t nf_launch_hash_encode(const NfPlan& plan, const void* packed, const 
   const long long want = (total + 255) / 256;
   const int grid = (int)(want < (long long)num_sms() * 8 ? want : (long long)num_sms() * 8);
   k_hash_encode<<<grid, 256, 0, st>>>(plan, (const uint8_t*)packed, pts, n, feats, idx);
+  return cudaGetLastError();
+}
+
+cudaError_t nf_launch_sample_pdf(const float* ts, int T, const float* weights, int64_t n_rays, const float* u, int nf, float* out, cudaStream_t st) {
+  if (n_rays == 0) return cudaSuccess;
+  if (T < 3 || T > PDF_MAX || nf < 1 || nf > PDF_MAX) return cudaErrorInvalidValue;
+  const long long want = (n_rays + 7) / 8;
+  const int grid = (int)(want < (long long)num_sms() * 8 ? want : (long long)num_sms() * 8);
+  k_sample_pdf<<<grid, 256, 0, st>>>(ts, T, weights, n_rays, u, nf, out);
   return cudaGetLastError();
 }
 

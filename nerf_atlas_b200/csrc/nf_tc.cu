@@ -58,8 +58,8 @@ static_assert(sizeof(TcSmem) <= 227 * 1024, "tensor pipeline smem");
 
 // Per-tile MMA program, built on the host and passed as a kernel parameter so that the issuing thread reads it
 // through uniform constant loads (LDCU) and every descriptor lives in uniform registers.
-struct TcProgEnt { uint32_t a4[4]; uint32_t bstep4, idesc, flags, bhi; };   // a4 = (A smem offset >> 4) | LBO field
-struct TcProg { int32_t n_chunks, odd_lin; TcProgEnt e[MAX_CHUNKS]; };
+struct __align__(16) TcProgEnt { uint32_t a4[4]; uint32_t bstep4, idesc, flags, bhi; };   // a4 = (A smem offset >> 4) | LBO field
+struct __align__(16) TcProg { int32_t n_chunks, odd_lin, pad0_, pad1_; TcProgEnt e[MAX_CHUNKS]; };
 
 struct TcArgs {
   const uint8_t* packed;
@@ -199,7 +199,7 @@ __device__ __forceinline__ void st_v4(uint8_t* p, uint32_t a, uint32_t b, uint32
 }
 
 #ifdef NF_TC_TRACE   // compile-time only: the trace stores push the MMA issuer's descriptors out of uniform registers
-#define NF_TRACE(role, tag) do { if (tr_on && tr_n[role] < 512) { tr[(role * 512 + tr_n[role]) * 2] = (tag); tr[(role * 512 + tr_n[role]) * 2 + 1] = clock64(); ++tr_n[role]; } } while (0)
+#define NF_TRACE(role, tag) do { if ((NF_TC_TRACE != 2 || (role) == 2) && tr_on && tr_n[role] < 512) { tr[(role * 512 + tr_n[role]) * 2] = (tag); tr[(role * 512 + tr_n[role]) * 2 + 1] = clock64(); ++tr_n[role]; } } while (0)
 #else
 #define NF_TRACE(role, tag) do { (void)tr_on; } while (0)
 #endif
@@ -412,8 +412,10 @@ k_render_tc(const __grid_constant__ NfPlan plan, const __grid_constant__ TcProg 
       for (long long trip = 0; trip < it.trips * it.tpr; ++trip) {
         tr_on = (a.debug & 4) && blockIdx.x == 0 && trip == 2;
         for (int c = 0; c < prog.n_chunks; ++c) {
-          const TcProgEnt& e = prog.e[c];
-          const uint32_t f = e.flags;
+          // the whole entry with two 128-bit uniform loads, before anything depends on it
+          const uint4 ea = *reinterpret_cast<const uint4*>(prog.e[c].a4);
+          const uint4 eb = *reinterpret_cast<const uint4*>(&prog.e[c].bstep4);
+          const uint32_t f = eb.z;
           NF_TRACE(1, c * 4 + 0);
           // One polling loop for everything this chunk needs (weights landed, x0 staged, H chunk(s) written): the
           // test_wait latencies (~150 cycles each) overlap instead of adding up.
@@ -438,15 +440,17 @@ k_render_tc(const __grid_constant__ NfPlan plan, const __grid_constant__ TcProg 
           NF_TRACE(1, c * 4 + 1);
           const uint32_t buf = ((f >> 5) & 1u) ^ tile_par;
           const uint32_t d_tmem = buf * 256u;                       // TMEM base is 0 (checked at setup)
-          const uint32_t b0 = (w4 + stage * (STAGE_BYTES >> 4)) | e.bhi;
+          const uint32_t b0 = (w4 + stage * (STAGE_BYTES >> 4)) | eb.w;
           const uint32_t nst = f & F_NSTEP;
           // debug & 32 (timing experiment): issue half-width MMAs (N/2) -- results are wrong, execution time halves
-          const uint32_t idesc = (a.debug & 32) ? ((e.idesc & ~(0x3Fu << 17)) | ((((e.idesc >> 17) & 0x3Fu) >> 1) << 17)) : e.idesc;
+          const uint32_t idesc = (a.debug & 32) ? ((eb.y & ~(0x3Fu << 17)) | ((((eb.y >> 17) & 0x3Fu) >> 1) << 17)) : eb.y;
           if (!(a.debug & 2)) {
-            umma_f16(d_tmem, umma_desc_lo(base4 + e.a4[0]), umma_desc_lo(b0), idesc, (f & F_FIRST) ? 0u : 1u);
-            if (nst > 1) umma_f16(d_tmem, umma_desc_lo(base4 + e.a4[1]), umma_desc_lo(b0 + e.bstep4), idesc, 1u);
-            if (nst > 2) umma_f16(d_tmem, umma_desc_lo(base4 + e.a4[2]), umma_desc_lo(b0 + 2u * e.bstep4), idesc, 1u);
-            if (nst > 3) umma_f16(d_tmem, umma_desc_lo(base4 + e.a4[3]), umma_desc_lo(b0 + 3u * e.bstep4), idesc, 1u);
+            const uint32_t a0 = base4 + ea.x, a1 = base4 + ea.y, a2 = base4 + ea.z, a3 = base4 + ea.w;
+            const uint32_t b1 = b0 + eb.x, b2 = b1 + eb.x, b3 = b2 + eb.x;
+            umma_f16(d_tmem, umma_desc_lo(a0), umma_desc_lo(b0), idesc, (f & F_FIRST) ? 0u : 1u);
+            if (nst > 1) umma_f16(d_tmem, umma_desc_lo(a1), umma_desc_lo(b1), idesc, 1u);
+            if (nst > 2) umma_f16(d_tmem, umma_desc_lo(a2), umma_desc_lo(b2), idesc, 1u);
+            if (nst > 3) umma_f16(d_tmem, umma_desc_lo(a3), umma_desc_lo(b3), idesc, 1u);
           }
           NF_TRACE(1, c * 4 + 2);
           umma_commit(bar_wempty + stage * 8u);

@@ -186,6 +186,25 @@ class RenderEngine:
     _lib.check(rc, "nf_composite")
     return rgb, alpha, weights
 
+  def sample_pdf(self, ts_coarse: torch.Tensor, weights: torch.Tensor, u: torch.Tensor) -> torch.Tensor:
+    """ts_coarse[T], weights[R,T] (coarse pass), u[R,Nf] in [0,1) -> sorted per-ray ts[R, T+Nf] for the fine pass."""
+    _chk(ts_coarse, "ts_coarse"); _chk(weights, "weights"); _chk(u, "u")
+    R, T = weights.shape
+    if ts_coarse.shape != (T,) or u.shape[0] != R: raise ValueError("shapes: ts_coarse[T], weights[R,T], u[R,Nf]")
+    out = torch.empty(R, T + u.shape[1], dtype=torch.float32, device=weights.device)
+    with torch.cuda.device(weights.device):
+      rc = self.lib.nf_sample_pdf(_ptr(ts_coarse), T, _ptr(weights), R, _ptr(u), u.shape[1], _ptr(out), self._stream())
+    _lib.check(rc, "nf_sample_pdf")
+    return out
+
+  def render_coarse_fine(self, rays: torch.Tensor, ts_coarse: torch.Tensor, u: torch.Tensor, want_weights: bool = True):
+    """Config 2 of BASELINE.json (coarse + fine): coarse pass on shared ts_coarse[T], inverse-CDF resampling
+    at u[R,Nf], fine pass on the T+Nf merged per-ray positions.  Returns (rgb_fine, rgb_coarse, ts_fine, alpha, weights)."""
+    rgb_c, _, w_c = self.render(rays, ts_coarse, want_weights=True)
+    ts_f = self.sample_pdf(ts_coarse, w_c, u)
+    rgb_f, alpha, w_f = self.render(rays, ts_f, want_weights=want_weights)
+    return rgb_f, rgb_c, ts_f, alpha, w_f
+
   def mlp_forward(self, which: int, x0: torch.Tensor, precision: Optional[str] = None) -> torch.Tensor:
     self._need_packed(); _chk(x0, "x0")
     md = self.desc.density if which == 0 else self.desc.refl

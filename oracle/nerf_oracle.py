@@ -369,6 +369,20 @@ def sample_pdf(bins: Tensor, weights: Tensor, u: Tensor) -> Tensor:
   return (bins_b + t * (bins_a - bins_b)).transpose(0, 1).contiguous()
 
 
+def plain_coarse_fine(params: Params, rays: Tensor, ts_coarse: Tensor, u: Tensor, **kw) -> Dict[str, Tensor]:
+  """Config 2 (coarse+fine) as SURVEY.md a-7 contracts it: two passes of the Plain pipeline; the fine pass runs on
+  the coarse positions merged (sorted) with the inverse-CDF samples.  rays[R,6] flat, u[Nf,R]."""
+  coarse = plain_forward(params, rays, ts_coarse, **kw)
+  mids = 0.5 * (ts_coarse[:-1] + ts_coarse[1:])
+  new = sample_pdf(mids, coarse["weights"][1:-1], u)                       # [Nf,R]
+  ts_f = torch.sort(torch.cat([ts_coarse[:, None].expand(-1, rays.shape[0]), new], dim=0), dim=0).values   # [T+Nf,R]
+  r_o, r_d = rays.split([3, 3], dim=-1)
+  pts = r_o.unsqueeze(0) + ts_f[..., None] * r_d.unsqueeze(0)
+  fine = plain_from_pts(params, pts, ts_f, r_o, r_d, per_ray_ts=True, **kw)
+  fine["ts"] = ts_f; fine["coarse"] = coarse["out"]
+  return fine
+
+
 # ----------------------------------------------------------------------------
 # deterministic synthetic inputs (shared by tests, golden generator, bench)
 # ----------------------------------------------------------------------------

@@ -208,3 +208,42 @@ def test_c_abi_error_codes(eng):
   rc = l.nf_render_forward(C.byref(eng.desc), v(eng.packed), v(rays), 4, v(ts), 8, 0, None, v(rgb), None, None, 7, None)
   assert rc == -1 and b"precision" in l.nf_last_error()
   with pytest.raises(RuntimeError): eng.render(rays.cpu(), ts)
+
+# ---------------------------------------------------------------- coarse + fine (config 2)
+def test_sample_pdf_matches_oracle(eng):
+  """Inverse-CDF resampling.  Where the pdf is tiny the inverse CDF is steep (d sample / d cdf ~ bin/pdf), so a 1-ulp
+  difference in the running sum legitimately moves a sample; the bar is: output sorted, coarse positions present
+  bit-exactly, >= 99 % of positions within 2e-5 of the oracle and all within one coarse bin."""
+  g = torch.Generator().manual_seed(11)
+  for T, Nf, R in ((64, 128, 257), (16, 8, 33), (128, 64, 19)):
+    ts = torch.linspace(2, 6, T)
+    w = torch.rand(R, T, generator=g) ** 2 * 0.05
+    w[:, T // 3] += 0.6                                # a peaked pdf, like a surface
+    u = torch.rand(R, Nf, generator=g)
+    out = eng.sample_pdf(ts.to(DEV), w.to(DEV), u.to(DEV)).cpu()
+    mids = 0.5 * (ts[:-1] + ts[1:])
+    new = O.sample_pdf(mids, w.t()[1:-1].contiguous(), u.t().contiguous())          # [Nf,R]
+    ref = torch.sort(torch.cat([ts[:, None].expand(-1, R), new], 0), dim=0).values.t()
+    assert out.shape == (R, T + Nf)
+    assert torch.all(out[:, 1:] >= out[:, :-1]), "fine-pass positions not sorted"
+    for r in range(0, R, 7):                           # every coarse position survives the merge, bit-exactly
+      assert np.isin(ts.numpy(), out[r].numpy()).all()
+    d = (out - ref).abs()
+    assert float((d <= 2e-5).float().mean()) >= 0.99, float((d <= 2e-5).float().mean())
+    assert float(d.max()) <= float(ts[1] - ts[0])
+
+def test_render_coarse_fine_64_128(P):
+  """BASELINE config 2: PlainNeRF coarse+fine, 64 + 128 samples/ray (fine pass on 192 sorted positions)."""
+  g = torch.Generator().manual_seed(3)
+  rays = O.make_rays(1, 6, 7, seed=5, crop_top=397, crop_left=396).reshape(-1, 6)
+  R = rays.shape[0]
+  ts = torch.linspace(2, 6, 64)
+  u = torch.rand(R, 128, generator=g)
+  with torch.no_grad(): ref = O.plain_coarse_fine(P, rays, ts, u.t().contiguous())
+  for precision, tol in (("fp32", 5e-5), ("fp16", 1e-3)):
+    e = plain_engine(P, DEV, precision=precision)
+    rgb_f, rgb_c, ts_f, alpha, w = e.render_coarse_fine(rays.to(DEV), ts.to(DEV), u.to(DEV))
+    assert ts_f.shape == (R, 192)
+    np.testing.assert_allclose(ts_f.cpu().numpy(), ref["ts"].t().numpy(), rtol=0, atol=2e-4 if precision == "fp16" else 2e-5)
+    assert np.abs(rgb_c.cpu().numpy() - ref["coarse"].numpy()).max() <= tol
+    assert np.abs(rgb_f.cpu().numpy() - ref["out"].numpy()).max() <= (2e-3 if precision == "fp16" else tol), precision
