@@ -2,6 +2,7 @@
 // kernel launches only; no torch types, no global mutable state (errors are thread local).
 #include <string>
 #include <cstdio>
+#include <cstdlib>
 #include "nf_common.cuh"
 #include "nf_kernels.h"
 
@@ -87,8 +88,13 @@ int nf_render_forward(const nf_model_desc* desc, const void* packed, const float
   cudaError_t e;
   if (precision == NF_PREC_FP32)
     e = nf_launch_render_fp32(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, rgb_out, alpha_out, weights_out, (cudaStream_t)stream);
-  else if (precision == NF_PREC_FP16_TC)
-    e = nf_launch_render_tc(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, rgb_out, alpha_out, weights_out, (cudaStream_t)stream);
+  else if (precision == NF_PREC_FP16_TC) {
+    // default: the paired (cta_group::2) pipeline; NF_TC_PAIRED=0 selects the single-CTA pipeline (kept for A/B timing)
+    const char* env = getenv("NF_TC_PAIRED");
+    const bool paired = !(env && env[0] == '0') && nf_tc2_unsupported(p) == nullptr;
+    e = paired ? nf_launch_render_tc2(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, rgb_out, alpha_out, weights_out, (cudaStream_t)stream)
+               : nf_launch_render_tc(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, rgb_out, alpha_out, weights_out, (cudaStream_t)stream);
+  }
   else return fail(NF_E_BADARG, "unknown precision");
   if (e != cudaSuccess) return cuda_fail(e, "nf_render_forward");
   return 0;

@@ -25,6 +25,7 @@ struct NfLinPlan {
   int64_t b_off;      // byte offset: fp32 bias[n_pad]
   int64_t w16_off;    // byte offset: fp16 UMMA-canonical image [K_tc/8][n_pad][8], K order = [x0 (k0_pad) | hidden]
   int64_t b16_off;    // byte offset: fp32 bias[n_pad] in tensor-path column order
+  int64_t w16h_off;   // byte offset: the same image split for a CTA pair: [rank 0..1][K_tc/8][n_pad/2][8]
 };
 struct NfMlpPlan {
   int32_t n_lin, in_dims, k0_pad, act, out_dims, pad_;
@@ -87,6 +88,7 @@ static inline int nf_build_plan(const nf_model_desc* d, NfPlan* p, const char** 
       L.b_off = take((int64_t)L.n_pad * sizeof(float));
       L.w16_off = take((int64_t)k_tc * L.n_pad * sizeof(__half));
       L.b16_off = take((int64_t)L.n_pad * sizeof(float));
+      L.w16h_off = take((int64_t)k_tc * L.n_pad * sizeof(__half));
     }
   }
   if (d->kind == NF_KIND_PLAIN) {

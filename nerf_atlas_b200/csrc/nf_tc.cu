@@ -13,17 +13,19 @@
 //   D = [128 x N] fp32 in TMEM, two 256-column accumulators used alternately by consecutive
 //       layers so that layer j+1's MMAs start on the K-chunks of layer j's output as soon as the
 //       epilogue has written them (chunk-granular h_ready barriers).
-// Warp roles: 0, 2, 3 = weight producers (one ring stage each; 2 also allocates TMEM), 1 = MMA issuer (one thread),
-// 4..11 = encode/epilogue warps (TMEM lane quarter = warp % 4, column half = (warp-4)/4).
+// Warp roles: 0..7 = encode/epilogue warps (TMEM lane quarter = warp % 4, column half = warp / 4); 8, 10, 11 = weight
+// producers (one ring stage each; 10 also allocates TMEM), 9 = MMA issuer (one thread).  The role warps carry the highest
+// warp ids because the SM schedulers favour higher ids: the lone issuing thread must not queue behind the epilogue warps.
 #include <cstdio>
 #include <cstdlib>
 #include <cstddef>
 #include "nf_common.cuh"
 #include "nf_kernels.h"
+#include "nf_tc_ptx.cuh"
 
 namespace {
+using namespace nf_ptx;
 
-constexpr int ROWS = NF_TC_ROWS;          // 128
 constexpr int X0K = 80;                   // max padded x0 width on this path
 constexpr int STAGES = 3;
 constexpr int SPC = NF_TC_CHUNK_K / 16;                 // UMMA K-steps per weight chunk
@@ -31,7 +33,6 @@ constexpr int STAGE_BYTES = NF_TC_CHUNK_K * 256 * 2;   // 32 KB: 64 K-columns x 
 constexpr int MAX_LIN_TOTAL = 12;
 constexpr int THREADS = 384;
 constexpr int EPI_THREADS = 256;
-constexpr int KG_BYTES = ROWS * 16;       // one 8-column K-group of an A operand: 128 rows x 16 B
 constexpr int MAX_CHUNKS = 56;
 // flags of one weight chunk of the per-tile MMA program: bits 0-2 = UMMA steps in the chunk (1..4)
 constexpr uint32_t F_NSTEP = 7, F_FIRST = 8, F_LAST = 16, F_BUF = 32, F_WAIT_X0 = 64, F_WAIT_H = 0xF00;
@@ -72,131 +73,6 @@ struct TcArgs {
   long long* trace;   // debug & 4: clock64 timeline of one tile of block 0: [role][512] x {tag, clock}
   int debug;   // timing experiments only (NF_TC_DEBUG): 1 = epilogue does no work, 2 = no MMA issued
 };
-
-// ---- PTX wrappers ------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU.
-// A protocol bug must surface as a trapped launch (cudaErrorLaunchFailure), never as a hung GPU.  No function call
-// here: a call in the wait loop makes ptxas drop the MMA issuer's descriptors out of uniform registers.
-__device__ __forceinline__ void mbar_timeout(uint32_t) { __trap(); }
-// Non-blocking probe. Measured on B200 (profiles/trace_*.txt): a failed mbarrier.try_wait suspends the thread for a
-// ~440-cycle quantum and is NOT woken early by async-proxy completions (TMA complete_tx, tcgen05.commit), so every
-// wait on the critical path polls with test_wait instead.
-__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_test_wait(bar, parity)) { if (++spins > (1u << 26)) mbar_timeout(bar); }
-}
-// two barriers polled together: the two test_wait latencies (~150 cycles each) overlap
-__device__ __forceinline__ void mbar_wait2(uint32_t bar_a, uint32_t par_a, uint32_t bar_b, uint32_t par_b) {
-  uint32_t spins = 0;
-  while (true) {
-    const bool oa = mbar_test_wait(bar_a, par_a), ob = mbar_test_wait(bar_b, par_b);
-    if (oa && ob) break;
-    if (++spins > (1u << 26)) mbar_timeout(oa ? bar_b : bar_a);
-  }
-}
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n .reg .pred P1;\n elect.sync _|P1, 0xffffffff;\n selp.u32 %0, 1, 0, P1;\n}" : "=r"(pred));
-  return pred != 0;
-}
-// for the 8 epilogue warps (they share schedulers with the MMA issuer): poll, but yield between polls
-__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_test_wait(bar, parity)) { __nanosleep(32); if (++spins > (1u << 24)) mbar_timeout(bar); }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-
-// K-major, no-swizzle UMMA shared-memory descriptors: 8x16-byte core matrices; LBO (bits 16-29) = byte distance
-// between the two K-adjacent cores of one K=16 step, SBO (bits 32-45) = byte distance between 8-row groups.
-// high word shared by every operand here: SBO = 128 B, descriptor version 1 (bit 46)
-__device__ __forceinline__ uint64_t umma_desc_lo(uint32_t lo) { return ((uint64_t)0x4008u << 32) | lo; }
-// kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=n.
-__device__ __forceinline__ uint32_t umma_idesc(int n) {
-  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
-}
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
-               ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-               : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// ties 16 registers to the preceding tcgen05.wait::ld so no consumer is scheduled above it
-__device__ __forceinline__ void reg_fence16(uint32_t* v) {
-  asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
-                    "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]) :: "memory");
-}
-template <int ACT> __device__ __forceinline__ float tc_act_t(float x) {
-  if (ACT == NF_ACT_LEAKY) return fmaxf(x, 0.01f * x);
-  if (ACT == NF_ACT_SIN) return __sinf(x);
-  if (ACT == NF_ACT_RELU) return fmaxf(x, 0.f);
-  return x;
-}
-
-__device__ __forceinline__ float tc_act(float x, int act) {
-  switch (act) {
-    case NF_ACT_LEAKY: return fmaxf(x, 0.01f * x);
-    case NF_ACT_SIN:   return __sinf(x);
-    case NF_ACT_RELU:  return fmaxf(x, 0.f);
-    default:           return x;
-  }
-}
-__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
-  const __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<const uint32_t*>(&h);
-}
-__device__ __forceinline__ void st_v4(uint8_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d);
-}
 
 #ifdef NF_TC_TRACE   // compile-time only: the trace stores push the MMA issuer's descriptors out of uniform registers
 #define NF_TRACE(role, tag) do { if ((NF_TC_TRACE != 2 || (role) == 2) && tr_on && tr_n[role] < 512) { tr[(role * 512 + tr_n[role]) * 2] = (tag); tr[(role * 512 + tr_n[role]) * 2 + 1] = clock64(); ++tr_n[role]; } } while (0)
@@ -358,11 +234,11 @@ k_render_tc(const __grid_constant__ NfPlan plan, const __grid_constant__ TcProg 
     mbar_init(smem_u32(&s.x0_ready), 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {
+  if (warp == 10) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (warp == 3 && lane == 0) {
+  if (warp == 11 && lane == 0) {
     // weight chunk list for the producers (identical for every tile): {byte offset into packed, bytes}
     int nc = 0;
     for (int m = m_begin; m < m_end; ++m)
@@ -381,12 +257,12 @@ k_render_tc(const __grid_constant__ NfPlan plan, const __grid_constant__ TcProg 
   const uint32_t tmem_base = s.tmem_base;
   if (tmem_base != 0) { if (threadIdx.x == 0) printf("nf_tc: unexpected TMEM base %u\n", tmem_base); __trap(); }
 
-  if (warp == 0 || warp == 2 || warp == 3) {
+  if (warp == 8 || warp == 10 || warp == 11) {
     // ================= weight producers: three single-thread issuers, one per ring stage =================
     // cp.async.bulk costs the ISSUING warp ~450 cycles per copy (about 2 copies in flight per warp, any size;
     // profiles/microbench/copy_bw.cu), so one issuer tops out at ~75 B/cycle with 32 KB chunks; issuers scale.
     if (lane == 0) {
-      const int p = warp == 0 ? 0 : warp - 1;           // producer index == ring stage it owns
+      const int p = warp == 8 ? 0 : warp - 9;           // producer index == ring stage it owns
       const int nc = s.n_chunks;
       const long long total = it.trips * it.tpr * nc;
       int c = p % nc;
@@ -400,7 +276,7 @@ k_render_tc(const __grid_constant__ NfPlan plan, const __grid_constant__ TcProg 
         c += STAGES; while (c >= nc) c -= nc;
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     // ================= MMA issuer: ONE thread walks the chunk program and issues every tcgen05.mma =================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
@@ -461,9 +337,9 @@ k_render_tc(const __grid_constant__ NfPlan plan, const __grid_constant__ TcProg 
         tile_par ^= (uint32_t)prog.odd_lin;
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 8) {
     // ================= encode + epilogue warps =================
-    const int ew = warp - 4, q = warp & 3, half = ew >> 2;
+    const int ew = warp, q = warp & 3, half = ew >> 2;
     const int e_tid = ew * 32 + lane;
     const int row = q * 32 + lane;                       // TMEM lane == tile row owned in epilogues
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -547,7 +423,7 @@ k_render_tc(const __grid_constant__ NfPlan plan, const __grid_constant__ TcProg 
             const NfLinPlan& L = M.lin[j];
             const uint32_t buf = lin_count & 1;
             const float* bias = s.bias + ((m ? lin_base1 : 0) + j) * 256;
-            tr_on = (a.debug & 4) && blockIdx.x == 0 && trip == 2 && warp == 4 && lane == 0;
+            tr_on = (a.debug & 4) && blockIdx.x == 0 && trip == 2 && warp == 0 && lane == 0;
             NF_TRACE(2, (m * 16 + j) * 4 + 0);
             mbar_wait_backoff(smem_u32(&s.acc_full[buf]), (acc_par >> buf) & 1u);
             NF_TRACE(2, (m * 16 + j) * 4 + 1);
@@ -642,7 +518,7 @@ k_render_tc(const __grid_constant__ NfPlan plan, const __grid_constant__ TcProg 
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 10) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
@@ -654,13 +530,18 @@ __global__ void k_pack_fp16(const __grid_constant__ NfPlan plan, int m, int j, c
   const NfLinPlan& L = plan.mlp[m].lin[j];
   const int k_ref_total = L.k_hidden + L.k_x0;
   __half* img = reinterpret_cast<__half*>(packed + L.w16_off);
+  __half* imgh = reinterpret_cast<__half*>(packed + L.w16h_off);
+  const int k_total = L.k0_pad + L.k_hidden;
   float* b16 = reinterpret_cast<float*>(packed + L.b16_off);
   const int total = L.n * k_ref_total;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int n_ref = i / k_ref_total, k_ref = i - n_ref * k_ref_total;
     const int k_tc = k_ref < L.k_hidden ? L.k0_pad + k_ref : nf_x0_perm(plan, m, k_ref - L.k_hidden);
     const int n_tc = L.is_out ? nf_out_perm(plan, m, n_ref) : n_ref;
-    img[(size_t)(k_tc >> 3) * (L.n_pad * 8) + n_tc * 8 + (k_tc & 7)] = __float2half_rn(W[i]);
+    const __half h = __float2half_rn(W[i]);
+    img[(size_t)(k_tc >> 3) * (L.n_pad * 8) + n_tc * 8 + (k_tc & 7)] = h;
+    const int nh = L.n_pad >> 1, rank = n_tc / nh, nl = n_tc - rank * nh;        // CTA-pair split along N
+    imgh[(size_t)rank * (k_total >> 3) * (nh * 8) + (size_t)(k_tc >> 3) * (nh * 8) + nl * 8 + (k_tc & 7)] = h;
   }
   for (int n_ref = blockIdx.x * blockDim.x + threadIdx.x; n_ref < L.n; n_ref += gridDim.x * blockDim.x)
     b16[L.is_out ? nf_out_perm(plan, m, n_ref) : n_ref] = b[n_ref];
@@ -758,6 +639,8 @@ cudaError_t launch_tc(const NfPlan& plan, TcArgs a, long long units, cudaStream_
 cudaError_t nf_launch_pack_fp16(const NfPlan& plan, int m, int j, const float* W, const float* b, void* packed, cudaStream_t st) {
   const NfLinPlan& L = plan.mlp[m].lin[j];
   cudaError_t e = cudaMemsetAsync((uint8_t*)packed + L.w16_off, 0, (size_t)(L.k0_pad + L.k_hidden) * L.n_pad * sizeof(__half), st);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync((uint8_t*)packed + L.w16h_off, 0, (size_t)(L.k0_pad + L.k_hidden) * L.n_pad * sizeof(__half), st);
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync((uint8_t*)packed + L.b16_off, 0, (size_t)L.n_pad * sizeof(float), st);
   if (e != cudaSuccess) return e;
