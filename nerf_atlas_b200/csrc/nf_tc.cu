@@ -261,7 +261,7 @@ k_render_tc(const __grid_constant__ NfPlan plan, const __grid_constant__ TcProg 
     // ================= weight producers: three single-thread issuers, one per ring stage =================
     // cp.async.bulk costs the ISSUING warp ~450 cycles per copy (about 2 copies in flight per warp, any size;
     // profiles/microbench/copy_bw.cu), so one issuer tops out at ~75 B/cycle with 32 KB chunks; issuers scale.
-    if (lane == 0) {
+    if (lane == 0 && !(a.debug & 64)) {
       const int p = warp == 8 ? 0 : warp - 9;           // producer index == ring stage it owns
       const int nc = s.n_chunks;
       const long long total = it.trips * it.tpr * nc;
@@ -302,7 +302,7 @@ k_render_tc(const __grid_constant__ NfPlan plan, const __grid_constant__ TcProg 
             const uint32_t hc1 = hm2 ? (uint32_t)__ffs((int)hm2) - 1u : hc0;
             uint32_t spins = 0;
             while (true) {
-              bool ok = mbar_test_wait(bar_wfull + stage * 8u, phase);
+              bool ok = (a.debug & 64) ? true : mbar_test_wait(bar_wfull + stage * 8u, phase);
               if (hm) ok &= mbar_test_wait(bar_h + hc0 * 8u, (h_par >> hc0) & 1u);
               if (hm2) ok &= mbar_test_wait(bar_h + hc1 * 8u, (h_par >> hc1) & 1u);
               if (f & F_WAIT_X0) ok &= mbar_test_wait(bar_x0, x0_par);
@@ -329,7 +329,7 @@ k_render_tc(const __grid_constant__ NfPlan plan, const __grid_constant__ TcProg 
             if (nst > 3) umma_f16(d_tmem, umma_desc_lo(a3), umma_desc_lo(b3), idesc, 1u);
           }
           NF_TRACE(1, c * 4 + 2);
-          umma_commit(bar_wempty + stage * 8u);
+          if (!(a.debug & 64)) umma_commit(bar_wempty + stage * 8u);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           if (f & F_LAST) umma_commit(bar_acc + buf * 8u);
           NF_TRACE(1, c * 4 + 3);

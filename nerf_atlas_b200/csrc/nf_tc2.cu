@@ -52,8 +52,13 @@ struct Tc2Smem {
 };
 static_assert(sizeof(Tc2Smem) <= 227 * 1024, "paired tensor pipeline smem");
 
-struct __align__(16) Tc2Ent { uint32_t a4[4]; uint32_t bstep4, idesc, flags, bhi; };
-struct __align__(16) Tc2Prog { int32_t n_ent, n_chunks, pad0_, pad1_; Tc2Ent e[MAX_ENT]; };
+// Host-built program (kernel parameter => uniform constant loads in the issuing thread).
+struct __align__(16) Tc2Lin { uint32_t k0_steps, h_steps, idesc, bstep4, bhi, pad0_, pad1_, pad2_; };   // one Linear
+struct __align__(16) Tc2Prog {
+  int32_t n_lin, n_ent, pad0_, pad1_;
+  Tc2Lin lin[12];
+  uint8_t ent_chunk[MAX_ENT];     // producers: distinct weight-chunk index of every ring entry of a round
+};
 
 struct Tc2Args {
   const uint8_t* packed;
@@ -90,24 +95,26 @@ __device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {
 // ---- epilogue of a hidden Linear: H <- fp16(act(acc + bias)) ----------------------------------------------
 template <int ACT>
 __device__ __forceinline__ void epi_hidden2(uint8_t* __restrict__ H, uint32_t t_acc, const float* __restrict__ bias, int half, int row) {
-#pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
-    const int col = c * 64 + half * 32;
-    uint32_t v[32];
-    tmem_ld16(t_acc + col, v); tmem_ld16(t_acc + col + 16, v + 16);
-    tmem_ld_wait();
-    reg_fence16(v); reg_fence16(v + 16);
-    const float4* b4 = reinterpret_cast<const float4*>(bias + col);
-    uint32_t o[16];
+  // 8 units of 16 columns per warp (this warp's 32-column half of each 64-column chunk); unit u+1's TMEM load is in
+  // flight while unit u is converted and stored.
+  uint32_t v[2][16];
+  tmem_ld16(t_acc + half * 32, v[0]);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+  for (int u = 0; u < 8; ++u) {
+    const int col = (u >> 1) * 64 + half * 32 + (u & 1) * 16;
+    tmem_ld_wait();
+    reg_fence16(v[u & 1]);
+    if (u < 7) tmem_ld16(t_acc + ((u + 1) >> 1) * 64 + half * 32 + ((u + 1) & 1) * 16, v[(u + 1) & 1]);
+    const float4* b4 = reinterpret_cast<const float4*>(bias + col);
+    uint32_t o[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
       const float4 b = __ldg(b4 + i);
-      o[2 * i]     = pack_h2(tc_act_t<ACT>(__uint_as_float(v[4 * i]) + b.x), tc_act_t<ACT>(__uint_as_float(v[4 * i + 1]) + b.y));
-      o[2 * i + 1] = pack_h2(tc_act_t<ACT>(__uint_as_float(v[4 * i + 2]) + b.z), tc_act_t<ACT>(__uint_as_float(v[4 * i + 3]) + b.w));
+      o[2 * i]     = act_pack_t<ACT>(__uint_as_float(v[u & 1][4 * i]) + b.x, __uint_as_float(v[u & 1][4 * i + 1]) + b.y);
+      o[2 * i + 1] = act_pack_t<ACT>(__uint_as_float(v[u & 1][4 * i + 2]) + b.z, __uint_as_float(v[u & 1][4 * i + 3]) + b.w);
     }
     uint8_t* dst = H + (col >> 3) * KG_BYTES + row * 16;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) st_v4(dst + g * KG_BYTES, o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+    st_v4(dst, o[0], o[1], o[2], o[3]); st_v4(dst + KG_BYTES, o[4], o[5], o[6], o[7]);
   }
 }
 
@@ -245,7 +252,7 @@ k_render_tc2(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc2Pro
 
   if (warp == 16 || warp == 18 || warp == 19) {
     // ================= weight producers (both CTAs): one ring stage each =================
-    if (lane == 0) {
+    if (lane == 0 && !(a.debug & 64)) {
       const int p = warp == 16 ? 0 : warp - 17;
       const int nc = s.n_chunks;
       // the round's chunk sequence is: for each Linear { its chunks for slot 0, the same chunks again for slot 1 }
@@ -254,7 +261,7 @@ k_render_tc2(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc2Pro
       (void)nc;
       for (long long g = p; g < total; g += STAGES) {
         const int e = (int)(g % prog.n_ent);
-        const uint2 ch = s.chunks[prog.e[e].bstep4 >> 16];          // high half of bstep4 = distinct chunk index
+        const uint2 ch = s.chunks[prog.ent_chunk[e]];
         const uint32_t par = (uint32_t)((g / STAGES) & 1);
         tr_on = (a.debug & 4) && blockIdx.x == 0 && p == 0 && g / prog.n_ent == 2;
         NF_TRACE2(0, e * 4 + 0);
@@ -268,49 +275,58 @@ k_render_tc2(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc2Pro
       }
     }
   } else if (warp == 17) {
-    // ================= MMA issuer (leader CTA only) =================
+    // ================= MMA issuer (leader CTA only): one thread, tight nested loops =================
+    // Per Linear and slot: wait a_ready, then k0 steps on X0[slot] and 16 steps on H[slot]; every 4th step starts a new ring
+    // stage (wait w_ready) and every chunk end releases it (multicast commit).  All operands are uniform arithmetic on
+    // kernel parameters and loop counters, so ptxas keeps them in uniform registers (~15 instructions per MMA).
     if (crank == 0 && lane == 0) {
       uint32_t stage = 0, phase = 0, a_par = 0;
       const uint32_t base4 = smem_u32(smem_raw) >> 4;
       const uint32_t w4 = base4 + (uint32_t)(offsetof(Tc2Smem, W) >> 4);
       const uint32_t bar_wready = smem_u32(&s.w_ready[0]), bar_wempty = smem_u32(&s.w_empty[0]);
       const uint32_t bar_a = smem_u32(&s.a_ready[0]), bar_acc = smem_u32(&s.acc_full[0]);
+      const uint32_t a_lbo = (uint32_t)(KG_BYTES >> 4) << 16, kstep4 = (uint32_t)(2 * KG_BYTES) >> 4;
+      const bool no_w = (a.debug & 64) != 0, no_mma = (a.debug & 2) != 0, alone = (a.debug & 128) != 0;
       for (long long pass = 0; pass < passes; ++pass)
-        for (int c = 0; c < prog.n_ent; ++c) {
-          const uint4 ea = *reinterpret_cast<const uint4*>(prog.e[c].a4);
-          const uint4 eb = *reinterpret_cast<const uint4*>(&prog.e[c].bstep4);
-          const uint32_t f = eb.z, slot = (f >> 5) & 1u;
-          tr_on = (a.debug & 4) && blockIdx.x == 0 && pass == 2;
-          NF_TRACE2(1, c * 4 + 0);
-          {
-            uint32_t spins = 0;
-            while (true) {
-              bool ok = mbar_test_wait(bar_wready + stage * 8u, phase);
-              if (f & F_WAIT_A) ok &= mbar_test_wait(bar_a + slot * 8u, (a_par >> slot) & 1u);
-              if (ok) break;
-              if (++spins > (1u << 26)) __trap();
+        for (int li = 0; li < prog.n_lin; ++li) {
+          const uint4 r0 = *reinterpret_cast<const uint4*>(&prog.lin[li].k0_steps);
+          const uint32_t bhi = prog.lin[li].bhi;
+          const uint32_t k0s = r0.x, total = r0.x + r0.y, idesc = r0.z, bstep4 = r0.w;
+#pragma unroll 1
+          for (uint32_t slot = 0; slot < 2; ++slot) {
+            if (!alone) { mbar_wait(bar_a + slot * 8u, (a_par >> slot) & 1u); a_par ^= 1u << slot; }
+            tc_fence_after();
+            const uint32_t d_tmem = slot * 256u;
+            const uint32_t x4 = (base4 + (uint32_t)(offsetof(Tc2Smem, X0) >> 4) + slot * (uint32_t)(sizeof(s.X0[0]) >> 4)) | a_lbo;
+            const uint32_t h4 = (base4 + (uint32_t)(offsetof(Tc2Smem, H) >> 4) + slot * (uint32_t)(sizeof(s.H[0]) >> 4)) | a_lbo;
+            const uint32_t n_chunks = (total + 3u) >> 2;
+#pragma unroll 1
+            for (uint32_t c = 0; c < n_chunks; ++c) {
+              const uint32_t gs0 = c << 2;
+              if (!no_w) { mbar_wait(bar_wready + stage * 8u, phase); tc_fence_after(); }
+              const uint32_t b4 = (w4 + stage * (uint32_t)(STAGE_BYTES >> 4)) | bhi;
+              if (gs0 + 4u <= total && (gs0 + 4u <= k0s || gs0 >= k0s)) {
+                // fast path: a full chunk fed from one buffer -> four back-to-back MMAs, operands differ by constants
+                const uint32_t a4 = gs0 < k0s ? x4 + gs0 * kstep4 : h4 + (gs0 - k0s) * kstep4;
+                if (!no_mma) {
+                  umma2_f16(d_tmem, umma_desc_lo(a4), umma_desc_lo(b4), idesc, gs0 > 0 ? 1u : 0u);
+                  umma2_f16(d_tmem, umma_desc_lo(a4 + kstep4), umma_desc_lo(b4 + bstep4), idesc, 1u);
+                  umma2_f16(d_tmem, umma_desc_lo(a4 + 2u * kstep4), umma_desc_lo(b4 + 2u * bstep4), idesc, 1u);
+                  umma2_f16(d_tmem, umma_desc_lo(a4 + 3u * kstep4), umma_desc_lo(b4 + 3u * bstep4), idesc, 1u);
+                }
+              } else {
+                const uint32_t nst = total - gs0 < 4u ? total - gs0 : 4u;
+                for (uint32_t i = 0; i < nst; ++i) {
+                  const uint32_t gs = gs0 + i;
+                  const uint32_t a4 = gs < k0s ? x4 + gs * kstep4 : h4 + (gs - k0s) * kstep4;
+                  if (!no_mma) umma2_f16(d_tmem, umma_desc_lo(a4), umma_desc_lo(b4 + i * bstep4), idesc, gs > 0 ? 1u : 0u);
+                }
+              }
+              if (!no_w) umma2_commit_mc(bar_wempty + stage * 8u);
+              if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             }
-            if (f & F_WAIT_A) a_par ^= 1u << slot;
+            if (!alone) umma2_commit_mc(bar_acc + slot * 8u);
           }
-          NF_TRACE2(1, c * 4 + 1);
-          // no cluster-scope fence here: it costs ~0.6 us per chunk; the release.cluster arrives + the barrier wait order
-          // the peer's (already proxy-fenced) smem writes before the MMA, as in CUTLASS's 2-SM mainloops
-          tc_fence_after();
-          const uint32_t d_tmem = slot * 256u;
-          const uint32_t b0 = (w4 + stage * (STAGE_BYTES >> 4)) | eb.w;
-          const uint32_t bs = eb.x & 0xFFFFu, nst = f & F_NSTEP;
-          if (!(a.debug & 2)) {
-            const uint32_t a0 = base4 + ea.x, a1 = base4 + ea.y, a2 = base4 + ea.z, a3 = base4 + ea.w;
-            const uint32_t b1 = b0 + bs, b2 = b1 + bs, b3 = b2 + bs;
-            umma2_f16(d_tmem, umma_desc_lo(a0), umma_desc_lo(b0), eb.y, (f & F_FIRST) ? 0u : 1u);
-            if (nst > 1) umma2_f16(d_tmem, umma_desc_lo(a1), umma_desc_lo(b1), eb.y, 1u);
-            if (nst > 2) umma2_f16(d_tmem, umma_desc_lo(a2), umma_desc_lo(b2), eb.y, 1u);
-            if (nst > 3) umma2_f16(d_tmem, umma_desc_lo(a3), umma_desc_lo(b3), eb.y, 1u);
-          }
-          umma2_commit_mc(bar_wempty + stage * 8u);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-          if (f & F_LAST) umma2_commit_mc(bar_acc + slot * 8u);
-          NF_TRACE2(1, c * 4 + 2);
         }
     }
   } else {
@@ -323,7 +339,7 @@ k_render_tc2(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc2Pro
     const uint32_t a_ready_leader = leader_addr(smem_u32(&s.a_ready[slot]));
     const uint32_t bar_acc = smem_u32(&s.acc_full[slot]);
     uint32_t acc_par = 0;
-    for (long long pass = 0; pass < passes; ++pass) {
+    for (long long pass = 0; pass < ((a.debug & 128) ? 0 : passes); ++pass) {
       const long long trip = pass / map.tpr; const int sub = (int)(pass - trip * map.tpr);
       const long long u = (trip * gridDim.x + blockIdx.x) * 2 + slot;
       // ---------- stage inputs of the density MLP (raw x0) ----------
@@ -449,47 +465,38 @@ k_render_tc2(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc2Pro
   }
 }
 
-// Per-round MMA program: for every Linear, its chunks for slot 0 and then the same chunks for slot 1.
+// Per-round program: one record per Linear (issuer) and the ring-entry -> weight-chunk map (producers): for every Linear
+// its chunks for slot 0 and then the same chunks again for slot 1.
 void build_prog2(const NfPlan& plan, Tc2Prog* P) {
   *P = Tc2Prog{};
-  int ne = 0, nc_base = 0;
+  int nl = 0, ne = 0, nc_base = 0;
   for (int m = 0; m < plan.n_mlps; ++m)
-    for (int j = 0; j < plan.mlp[m].n_lin; ++j) {
+    for (int j = 0; j < plan.mlp[m].n_lin; ++j, ++nl) {
       const NfLinPlan& L = plan.mlp[m].lin[j];
-      const int steps = (L.k0_pad + L.k_hidden) >> 4;
       const uint32_t nh = (uint32_t)L.n_pad >> 1, b_lbo = nh * 16u;
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(L.n_pad >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);   // M = 256 across the pair
-      for (int slot = 0; slot < 2; ++slot) {
-        const uint32_t Hs = (uint32_t)offsetof(Tc2Smem, H) + slot * (uint32_t)sizeof(((Tc2Smem*)0)->H[0]);
-        const uint32_t Xs = (uint32_t)offsetof(Tc2Smem, X0) + slot * (uint32_t)sizeof(((Tc2Smem*)0)->X0[0]);
-        for (int c = 0; c < L.n_chunks; ++c, ++ne) {
-          const int nst = steps - SPC * c < SPC ? steps - SPC * c : SPC;
-          Tc2Ent& e = P->e[ne];
-          uint32_t f = (uint32_t)nst | (c == 0 ? (F_FIRST | F_WAIT_A) : 0u) | (c == L.n_chunks - 1 ? F_LAST : 0u) | (slot ? F_SLOT : 0u);
-          for (int q4 = 0; q4 < nst; ++q4) {
-            const int k = (c * SPC + q4) << 4;
-            const uint32_t off = k < L.k0_pad ? Xs + (uint32_t)(k >> 3) * KG_BYTES : Hs + (uint32_t)((k - L.k0_pad) >> 3) * KG_BYTES;
-            e.a4[q4] = (off >> 4) | ((uint32_t)(KG_BYTES >> 4) << 16);
-          }
-          e.bstep4 = ((2u * b_lbo) >> 4) | ((uint32_t)(nc_base + c) << 16);   // low: B step per K=16; high: distinct chunk index
-          e.idesc = idesc; e.flags = f; e.bhi = (b_lbo >> 4) << 16;
-        }
-      }
+      Tc2Lin& R = P->lin[nl];
+      R.k0_steps = (uint32_t)L.k0_pad >> 4; R.h_steps = (uint32_t)L.k_hidden >> 4;
+      R.idesc = (1u << 4) | ((uint32_t)(L.n_pad >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);   // M = 256 across the pair
+      R.bstep4 = (2u * b_lbo) >> 4; R.bhi = (b_lbo >> 4) << 16;
+      for (int slot = 0; slot < 2; ++slot)
+        for (int c = 0; c < L.n_chunks; ++c) P->ent_chunk[ne++] = (uint8_t)(nc_base + c);
       nc_base += L.n_chunks;
     }
-  P->n_ent = ne; P->n_chunks = nc_base;
+  P->n_lin = nl; P->n_ent = ne;
 }
 
 }  // namespace
 
 // nullptr if the paired pipeline can run this model, else the reason.
 const char* nf_tc2_unsupported(const NfPlan& p) {
-  int chunks = 0;
+  int chunks = 0, nlin = 0;
   for (int m = 0; m < p.n_mlps; ++m) {
+    nlin += p.mlp[m].n_lin;
     if (p.mlp[m].k0_pad > X0K) return "x0 wider than 80 columns";
     for (int j = 0; j < p.mlp[m].n_lin; ++j) chunks += p.mlp[m].lin[j].n_chunks;
   }
   if (2 * chunks > MAX_ENT) return "too many weight chunks";
+  if (nlin > 12) return "more than 12 Linear layers";
   if (p.enc == NF_ENC_HASH && (p.hash_levels & 1)) return "odd number of hash levels";
   if (p.kind == NF_KIND_PLAIN && (p.intermediate & 15)) return "intermediate_size not a multiple of 16";
   return nullptr;

@@ -126,6 +126,22 @@ __device__ __forceinline__ float tc_act(float x, int act) {
     default:           return x;
   }
 }
+// act(x0), act(x1) -> packed fp16x2.  LeakyReLU/ReLU run as ONE packed half2 op pair after the conversion (the result is
+// rounded to fp16 anyway); sin stays in fp32 (MUFU) and is rounded afterwards.
+template <int ACT> __device__ __forceinline__ uint32_t act_pack_t(float x0, float x1) {
+  if (ACT == NF_ACT_LEAKY) {
+    __half2 h = __floats2half2_rn(x0, x1);
+    h = __hmax2(h, __hmul2(h, __float2half2_rn(0.01f)));
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+  if (ACT == NF_ACT_RELU) {
+    __half2 h = __floats2half2_rn(x0, x1);
+    h = __hmax2(h, __float2half2_rn(0.f));
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+  const __half2 h = __floats2half2_rn(tc_act_t<ACT>(x0), tc_act_t<ACT>(x1));
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
