@@ -82,6 +82,11 @@ __device__ __forceinline__ uint32_t leader_addr(uint32_t a) { return a & 0xFEFFF
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// After fence.proxy.async the payload (this CTA's smem, read by this SM's tensor core through the async proxy) is already
+// ordered; the cross-CTA arrive then only has to be delivered, not to release memory at cluster scope.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
 __device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
   asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
@@ -271,7 +276,7 @@ k_render_tc2(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc2Pro
         bulk_g2s(smem_u32(s.W[p]), a.packed + ch.x, ch.y, smem_u32(&s.w_land[p]));
         mbar_wait(smem_u32(&s.w_land[p]), par);                      // landed in THIS CTA ...
         NF_TRACE2(0, e * 4 + 2);
-        mbar_arrive_cluster(ready_leader);                           // ... tell the leader's MMA thread
+        mbar_arrive_cluster_relaxed(ready_leader);                   // ... tell the leader's MMA thread
       }
     }
   } else if (warp == 17) {
@@ -372,7 +377,7 @@ k_render_tc2(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc2Pro
       }
       fence_proxy_async();
       named_bar(1 + slot, GROUP_THREADS);
-      if (lane == 0) mbar_arrive_cluster(a_ready_leader);
+      if (lane == 0) mbar_arrive_cluster_relaxed(a_ready_leader);
 
       // ---------- the MLPs ----------
       for (int m = 0; m < plan.n_mlps; ++m) {
@@ -383,11 +388,12 @@ k_render_tc2(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc2Pro
           const float* bias = reinterpret_cast<const float*>(a.packed + L.b16_off);
           tr_on = (a.debug & 4) && blockIdx.x == 0 && pass == 2 && ew == 0 && lane == 0;
           NF_TRACE2(2 + slot, (m * 16 + j) * 4 + 0);
-          mbar_wait_backoff(bar_acc, acc_par); acc_par ^= 1u;
+          if (a.debug & 256) mbar_wait_backoff(bar_acc, acc_par); else mbar_wait_suspend(bar_acc, acc_par);
+          acc_par ^= 1u;
           NF_TRACE2(2 + slot, (m * 16 + j) * 4 + 1);
           tc_fence_after();
           if (a.debug & 1) {
-            if (!(m == plan.n_mlps - 1 && L.is_out)) { __syncwarp(); if (lane == 0) mbar_arrive_cluster(a_ready_leader); }
+            if (!(m == plan.n_mlps - 1 && L.is_out)) { __syncwarp(); if (lane == 0) mbar_arrive_cluster_relaxed(a_ready_leader); }
           } else if (!L.is_out) {
             if (j == 0) x0_activate(X0, M.k0_pad, act, g_tid);     // init consumed raw x0; the skip Linear wants act(x0)
             if (act == NF_ACT_SIN) epi_hidden2<NF_ACT_SIN>(H, t_acc, bias, half, row);
@@ -397,7 +403,7 @@ k_render_tc2(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc2Pro
             tc_fence_before();
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(a_ready_leader);
+            if (lane == 0) mbar_arrive_cluster_relaxed(a_ready_leader);
             NF_TRACE2(2 + slot, (m * 16 + j) * 4 + 2);
           } else if (plan.kind == NF_KIND_PLAIN && m == 0) {
             // density MLP out (tensor order [inter(I), sigma]) -> raw x0 of the View head + raw density
@@ -431,7 +437,7 @@ k_render_tc2(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc2Pro
             tc_fence_before();
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(a_ready_leader);
+            if (lane == 0) mbar_arrive_cluster_relaxed(a_ready_leader);
           } else {
             // final Linear of the path -> colours (and raw density for TinyNeRF) -> composite
             if (half == 0) {
