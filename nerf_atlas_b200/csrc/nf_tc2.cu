@@ -7,7 +7,8 @@
 // each CTA stages only HALF of every weight chunk (N/2 rows, 16 KB per 64 K-columns).
 //
 // Cluster of 2 CTAs, 640 threads each:
-//   warps 0-7    encode + epilogue group of tile slot 0;  warps 8-15: the same for slot 1
+//   warps 0-15   encode + epilogue: all sixteen work on whichever slot is in its epilogue (lane quarter = warp % 4,
+//                column quarter = warp / 4), so an epilogue takes half as long as with one 8-warp group per slot
 //   warps 16,18,19  weight producers (one ring stage each): bulk-copy this CTA's half chunk, wait for it to land, then
 //                arrive on the LEADER's w_ready[stage] (count 2) through the shared::cluster window
 //   warp 17      MMA issuer -- only in the leader CTA (rank 0), one thread, M = 256 instructions for both SMs
@@ -32,7 +33,7 @@ constexpr int STAGES = 3;
 constexpr int SPC = NF_TC_CHUNK_K / 16;                     // UMMA K-steps per weight chunk (4)
 constexpr int STAGE_BYTES = NF_TC_CHUNK_K * 128 * 2;       // 16 KB: 64 K-columns x 128 N (this CTA's half) x fp16
 constexpr int THREADS = 640;
-constexpr int GROUP_THREADS = 256;
+constexpr int EPI_THREADS = 512;                             // 16 encode/epilogue warps
 constexpr int MAX_ENT = 96;                                 // program entries per round (every Linear's chunks, twice)
 constexpr uint32_t F_NSTEP = 7, F_FIRST = 8, F_LAST = 16, F_SLOT = 32, F_WAIT_A = 64;
 
@@ -71,7 +72,7 @@ struct Tc2Args {
 };
 
 #ifdef NF_TC_TRACE
-#define NF_TRACE2(role, tag) do { if (tr_on && tr_n < 512) { a.trace[((role) * 512 + tr_n) * 2] = (tag); a.trace[((role) * 512 + tr_n) * 2 + 1] = clock64(); ++tr_n; } } while (0)
+#define NF_TRACE2(role, tag) do { if ((NF_TC_TRACE != 2 || (role) >= 2) && tr_on && tr_n < 512) { a.trace[((role) * 512 + tr_n) * 2] = (tag); a.trace[((role) * 512 + tr_n) * 2 + 1] = clock64(); ++tr_n; } } while (0)
 #else
 #define NF_TRACE2(role, tag) do { } while (0)
 #endif
@@ -98,35 +99,46 @@ __device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {
 }
 
 // ---- epilogue of a hidden Linear: H <- fp16(act(acc + bias)) ----------------------------------------------
-template <int ACT>
-__device__ __forceinline__ void epi_hidden2(uint8_t* __restrict__ H, uint32_t t_acc, const float* __restrict__ bias, int half, int row) {
-  // 8 units of 16 columns per warp (this warp's 32-column half of each 64-column chunk); unit u+1's TMEM load is in
-  // flight while unit u is converted and stored.
-  uint32_t v[2][16];
-  tmem_ld16(t_acc + half * 32, v[0]);
+// Bias of this warp's first 16 columns, fetched BEFORE the acc_full wait (it does not depend on the accumulator): with a
+// 227 KB shared-memory carve-out the L1 is nearly gone, so every bias load is a ~300-cycle L2 hit that must be hidden.
+struct Bias16 { float4 b[4]; };
+__device__ __forceinline__ Bias16 bias_prefetch(const float* __restrict__ bias, int col) {
+  Bias16 r; const float4* b4 = reinterpret_cast<const float4*>(bias + col);
 #pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    const int col = (u >> 1) * 64 + half * 32 + (u & 1) * 16;
+  for (int i = 0; i < 4; ++i) r.b[i] = __ldg(b4 + i);
+  return r;
+}
+template <int ACT>
+__device__ __forceinline__ void epi_hidden2(uint8_t* __restrict__ H, uint32_t t_acc, const float* __restrict__ bias, int cq, int row, Bias16 bcur) {
+  // this warp's 64-column quarter = 4 units of 16 columns; unit u+1's TMEM load and bias loads are in flight while unit u
+  // is converted and stored
+  uint32_t v[2][16];
+  tmem_ld16(t_acc + cq * 64, v[0]);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int col = cq * 64 + u * 16;
+    Bias16 bnext = bcur;
+    if (u < 3) bnext = bias_prefetch(bias, col + 16);
     tmem_ld_wait();
     reg_fence16(v[u & 1]);
-    if (u < 7) tmem_ld16(t_acc + ((u + 1) >> 1) * 64 + half * 32 + ((u + 1) & 1) * 16, v[(u + 1) & 1]);
-    const float4* b4 = reinterpret_cast<const float4*>(bias + col);
+    if (u < 3) tmem_ld16(t_acc + col + 16, v[(u + 1) & 1]);
     uint32_t o[8];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float4 b = __ldg(b4 + i);
+      const float4 b = bcur.b[i];
       o[2 * i]     = act_pack_t<ACT>(__uint_as_float(v[u & 1][4 * i]) + b.x, __uint_as_float(v[u & 1][4 * i + 1]) + b.y);
       o[2 * i + 1] = act_pack_t<ACT>(__uint_as_float(v[u & 1][4 * i + 2]) + b.z, __uint_as_float(v[u & 1][4 * i + 3]) + b.w);
     }
     uint8_t* dst = H + (col >> 3) * KG_BYTES + row * 16;
     st_v4(dst, o[0], o[1], o[2], o[3]); st_v4(dst + KG_BYTES, o[4], o[5], o[6], o[7]);
+    bcur = bnext;
   }
 }
 
 // x0 raw -> act(x0), in place (the `init` Linear consumed the raw form; the skip Linear wants the activated one)
 __device__ __forceinline__ void x0_activate(uint8_t* X0, int k0_pad, int act, int g_tid) {
   const int n16 = (k0_pad >> 3) * ROWS;             // 16-byte groups
-  for (int i = g_tid; i < n16; i += GROUP_THREADS) {
+  for (int i = g_tid; i < n16; i += EPI_THREADS) {
     uint4 q = *reinterpret_cast<uint4*>(X0 + i * 16);
     uint32_t* w = reinterpret_cast<uint32_t*>(&q);
 #pragma unroll
@@ -228,7 +240,7 @@ k_render_tc2(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc2Pro
   // ---- one-time setup ----
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(smem_u32(&s.w_land[i]), 1); mbar_init(smem_u32(&s.w_empty[i]), 1); mbar_init(smem_u32(&s.w_ready[i]), 2); }
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s.acc_full[i]), 1); mbar_init(smem_u32(&s.a_ready[i]), 16); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s.acc_full[i]), 1); mbar_init(smem_u32(&s.a_ready[i]), 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 18) {
@@ -335,129 +347,140 @@ k_render_tc2(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc2Pro
         }
     }
   } else {
-    // ================= encode + epilogue groups: warps 4-11 -> slot 0, warps 12-19 -> slot 1 =================
-    const int slot = warp >> 3, ew = warp & 7, q = warp & 3, half = ew >> 2;
-    const int g_tid = ew * 32 + lane;
+    // ================= encode + epilogue: ALL 16 warps work on whichever slot is in its epilogue =================
+    // TMEM lane quarter q = warp % 4 (rows 32q..32q+31), column quarter cq = warp / 4 (64 accumulator columns).
+    const int q = warp & 3, cq = warp >> 2;
+    const int e_tid = warp * 32 + lane;
     const int row = q * 32 + lane;
-    const uint32_t t_acc = ((uint32_t)(q * 32) << 16) + (uint32_t)slot * 256u;
-    uint8_t* H = s.H[slot]; uint8_t* X0 = s.X0[slot];
-    const uint32_t a_ready_leader = leader_addr(smem_u32(&s.a_ready[slot]));
-    const uint32_t bar_acc = smem_u32(&s.acc_full[slot]);
+    const uint32_t t_lane = (uint32_t)(q * 32) << 16;
     uint32_t acc_par = 0;
     for (long long pass = 0; pass < ((a.debug & 128) ? 0 : passes); ++pass) {
       const long long trip = pass / map.tpr; const int sub = (int)(pass - trip * map.tpr);
-      const long long u = (trip * gridDim.x + blockIdx.x) * 2 + slot;
-      // ---------- stage inputs of the density MLP (raw x0) ----------
+      // ---------- stage the density MLP's raw x0 for both slots ----------
       if (!(a.debug & 1)) {
-        const int r = g_tid & (ROWS - 1), part = g_tid >> 7;
-        long long ray; int t;
-        const bool ok = map.locate(u, sub, r, a.n_rays, ray, t);
-        float px = 0.f, py = 0.f, pz = 0.f;
-        if (ok) {
-          const float* rr = a.rays + ray * 6;
-          const float tt = __ldg(a.ts + ray * a.ts_stride + t);
-          px = nf_pt(__ldg(rr + 0), tt, __ldg(rr + 3)); py = nf_pt(__ldg(rr + 1), tt, __ldg(rr + 4)); pz = nf_pt(__ldg(rr + 2), tt, __ldg(rr + 5));
-        }
-        int kg = 0;
-        if (plan.enc == NF_ENC_HASH) {
-          const float4* tables = reinterpret_cast<const float4*>(a.packed + plan.hash_off);
-          for (int lvl = part; lvl < plan.hash_levels; lvl += 2) {
-            const float4 f = nf_hash_level(tables + (size_t)lvl * (plan.hash_mask + 1), px, py, pz, plan.hash_res[lvl],
-                                           plan.hash_primes[0], plan.hash_primes[1], plan.hash_primes[2], plan.hash_mask, nullptr);
-            *reinterpret_cast<uint2*>(X0 + (lvl >> 1) * KG_BYTES + r * 16 + (lvl & 1) * 8) = make_uint2(pack_h2(f.x, f.y), pack_h2(f.z, f.w));
+        const int r = e_tid & (ROWS - 1), part = e_tid >> 7;            // 4 threads per row, hash levels interleaved
+#pragma unroll 1
+        for (int slot = 0; slot < 2; ++slot) {
+          uint8_t* X0 = s.X0[slot];
+          const long long u = (trip * gridDim.x + blockIdx.x) * 2 + slot;
+          long long ray; int t;
+          const bool ok = map.locate(u, sub, r, a.n_rays, ray, t);
+          float px = 0.f, py = 0.f, pz = 0.f;
+          if (ok) {
+            const float* rr = a.rays + ray * 6;
+            const float tt = __ldg(a.ts + ray * a.ts_stride + t);
+            px = nf_pt(__ldg(rr + 0), tt, __ldg(rr + 3)); py = nf_pt(__ldg(rr + 1), tt, __ldg(rr + 4)); pz = nf_pt(__ldg(rr + 2), tt, __ldg(rr + 5));
           }
-          kg = plan.hash_levels >> 1;
-        }
-        if (part == 0) {
-          if (plan.enc == NF_ENC_HASH) st_v4(X0 + kg * KG_BYTES + r * 16, pack_h2(px, py), pack_h2(pz, px), pack_h2(py, pz), 0);
-          else st_v4(X0 + kg * KG_BYTES + r * 16, pack_h2(px, py), pack_h2(pz, 0.f), 0, 0);
-          for (int g = kg + 1; g < (plan.mlp[0].k0_pad >> 3); ++g) st_v4(X0 + g * KG_BYTES + r * 16, 0, 0, 0, 0);
-          s.ray[slot][r] = ray; s.t[slot][r] = t; s.valid[slot][r] = ok ? 1 : 0;
+          int kg = 0;
+          if (plan.enc == NF_ENC_HASH) {
+            const float4* tables = reinterpret_cast<const float4*>(a.packed + plan.hash_off);
+            for (int lvl = part; lvl < plan.hash_levels; lvl += 4) {
+              const float4 f = nf_hash_level(tables + (size_t)lvl * (plan.hash_mask + 1), px, py, pz, plan.hash_res[lvl],
+                                             plan.hash_primes[0], plan.hash_primes[1], plan.hash_primes[2], plan.hash_mask, nullptr);
+              *reinterpret_cast<uint2*>(X0 + (lvl >> 1) * KG_BYTES + r * 16 + (lvl & 1) * 8) = make_uint2(pack_h2(f.x, f.y), pack_h2(f.z, f.w));
+            }
+            kg = plan.hash_levels >> 1;
+          }
+          if (part == 0) {
+            if (plan.enc == NF_ENC_HASH) st_v4(X0 + kg * KG_BYTES + r * 16, pack_h2(px, py), pack_h2(pz, px), pack_h2(py, pz), 0);
+            else st_v4(X0 + kg * KG_BYTES + r * 16, pack_h2(px, py), pack_h2(pz, 0.f), 0, 0);
+            for (int g = kg + 1; g < (plan.mlp[0].k0_pad >> 3); ++g) st_v4(X0 + g * KG_BYTES + r * 16, 0, 0, 0, 0);
+            s.ray[slot][r] = ray; s.t[slot][r] = t; s.valid[slot][r] = ok ? 1 : 0;
+          }
         }
       }
       fence_proxy_async();
-      named_bar(1 + slot, GROUP_THREADS);
-      if (lane == 0) mbar_arrive_cluster_relaxed(a_ready_leader);
+      named_bar(1, EPI_THREADS);
+      if (lane == 0) { mbar_arrive_cluster_relaxed(leader_addr(smem_u32(&s.a_ready[0]))); mbar_arrive_cluster_relaxed(leader_addr(smem_u32(&s.a_ready[1]))); }
 
-      // ---------- the MLPs ----------
+      // ---------- the MLPs: slot 0's epilogue while the tensor pipe runs slot 1's Linear, and vice versa ----------
       for (int m = 0; m < plan.n_mlps; ++m) {
         const NfMlpPlan& M = plan.mlp[m];
         const int act = M.act;
         for (int j = 0; j < M.n_lin; ++j) {
           const NfLinPlan& L = M.lin[j];
           const float* bias = reinterpret_cast<const float*>(a.packed + L.b16_off);
-          tr_on = (a.debug & 4) && blockIdx.x == 0 && pass == 2 && ew == 0 && lane == 0;
-          NF_TRACE2(2 + slot, (m * 16 + j) * 4 + 0);
-          if (a.debug & 256) mbar_wait_backoff(bar_acc, acc_par); else mbar_wait_suspend(bar_acc, acc_par);
-          acc_par ^= 1u;
-          NF_TRACE2(2 + slot, (m * 16 + j) * 4 + 1);
-          tc_fence_after();
-          if (a.debug & 1) {
-            if (!(m == plan.n_mlps - 1 && L.is_out)) { __syncwarp(); if (lane == 0) mbar_arrive_cluster_relaxed(a_ready_leader); }
-          } else if (!L.is_out) {
-            if (j == 0) x0_activate(X0, M.k0_pad, act, g_tid);     // init consumed raw x0; the skip Linear wants act(x0)
-            if (act == NF_ACT_SIN) epi_hidden2<NF_ACT_SIN>(H, t_acc, bias, half, row);
-            else if (act == NF_ACT_LEAKY) epi_hidden2<NF_ACT_LEAKY>(H, t_acc, bias, half, row);
-            else if (act == NF_ACT_RELU) epi_hidden2<NF_ACT_RELU>(H, t_acc, bias, half, row);
-            else epi_hidden2<NF_ACT_NONE>(H, t_acc, bias, half, row);
-            tc_fence_before();
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster_relaxed(a_ready_leader);
-            NF_TRACE2(2 + slot, (m * 16 + j) * 4 + 2);
-          } else if (plan.kind == NF_KIND_PLAIN && m == 0) {
-            // density MLP out (tensor order [inter(I), sigma]) -> raw x0 of the View head + raw density
-            const int iu = plan.intermediate >> 4;
-            for (int un = half; un <= iu; un += 2) {
-              uint32_t v[16];
-              tmem_ld16(t_acc + un * 16, v); tmem_ld_wait(); reg_fence16(v);
-              if (un < iu) {
-                uint32_t o[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  o[i] = pack_h2(__uint_as_float(v[2 * i]) + __ldg(bias + un * 16 + 2 * i), __uint_as_float(v[2 * i + 1]) + __ldg(bias + un * 16 + 2 * i + 1));
-                uint8_t* d0 = X0 + (un * 2) * KG_BYTES + row * 16;
-                st_v4(d0, o[0], o[1], o[2], o[3]); st_v4(d0 + KG_BYTES, o[4], o[5], o[6], o[7]);
-              } else {
-                s.sig[slot][row] = __uint_as_float(v[0]) + __ldg(bias + plan.intermediate);
-                float px = 0.f, py = 0.f, pz = 0.f, el = 0.f, az = 0.f;
-                if (s.valid[slot][row]) {
-                  const long long ray = s.ray[slot][row];
-                  const float* rr = a.rays + ray * 6;
-                  const float tt = __ldg(a.ts + ray * a.ts_stride + s.t[slot][row]);
-                  const float dx = __ldg(rr + 3), dy = __ldg(rr + 4), dz = __ldg(rr + 5);
-                  px = nf_pt(__ldg(rr + 0), tt, dx); py = nf_pt(__ldg(rr + 1), tt, dy); pz = nf_pt(__ldg(rr + 2), tt, dz);
-                  nf_elaz(dx, dy, dz, el, az);
-                }
-                uint8_t* d0 = X0 + (iu * 2) * KG_BYTES + row * 16;
-                st_v4(d0, pack_h2(px, py), pack_h2(pz, el), pack_h2(az, 0.f), 0);
-                st_v4(d0 + KG_BYTES, 0, 0, 0, 0);
-              }
-            }
-            tc_fence_before();
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster_relaxed(a_ready_leader);
-          } else {
-            // final Linear of the path -> colours (and raw density for TinyNeRF) -> composite
-            if (half == 0) {
-              uint32_t v[16];
-              tmem_ld16(t_acc, v); tmem_ld_wait(); reg_fence16(v);
+#pragma unroll 1
+          for (int slot = 0; slot < 2; ++slot) {
+            uint8_t* H = s.H[slot]; uint8_t* X0 = s.X0[slot];
+            const uint32_t t_acc = t_lane + (uint32_t)slot * 256u;
+            const uint32_t a_ready_leader = leader_addr(smem_u32(&s.a_ready[slot]));
+            const Bias16 b0 = bias_prefetch(bias, L.is_out ? 0 : cq * 64);    // in flight across the acc_full wait
+            tr_on = (a.debug & 4) && blockIdx.x == 0 && pass == 2 && warp == 0 && lane == 0;
+            NF_TRACE2(2 + slot, (m * 16 + j) * 4 + 0);
+            if (a.debug & 256) mbar_wait_backoff(smem_u32(&s.acc_full[slot]), (acc_par >> slot) & 1u);
+            else mbar_wait_suspend(smem_u32(&s.acc_full[slot]), (acc_par >> slot) & 1u);
+            acc_par ^= 1u << slot;
+            NF_TRACE2(2 + slot, (m * 16 + j) * 4 + 1);
+            tc_fence_after();
+            if (a.debug & 1) {
+              if (!(m == plan.n_mlps - 1 && L.is_out)) { __syncwarp(); if (lane == 0) mbar_arrive_cluster_relaxed(a_ready_leader); }
+            } else if (!L.is_out) {
+              if (j == 0) x0_activate(X0, M.k0_pad, act, e_tid);       // init consumed raw x0; the skip Linear wants act(x0)
+              if (act == NF_ACT_SIN) epi_hidden2<NF_ACT_SIN>(H, t_acc, bias, cq, row, b0);
+              else if (act == NF_ACT_LEAKY) epi_hidden2<NF_ACT_LEAKY>(H, t_acc, bias, cq, row, b0);
+              else if (act == NF_ACT_RELU) epi_hidden2<NF_ACT_RELU>(H, t_acc, bias, cq, row, b0);
+              else epi_hidden2<NF_ACT_NONE>(H, t_acc, bias, cq, row, b0);
+              NF_TRACE2(2 + slot, (m * 16 + j) * 4 + 2);
               tc_fence_before();
-              float cr, cg, cb;
-              if (plan.kind == NF_KIND_TINY) {
-                s.sig[slot][row] = __uint_as_float(v[0]) + __ldg(bias);
-                cr = __uint_as_float(v[1]) + __ldg(bias + 1); cg = __uint_as_float(v[2]) + __ldg(bias + 2); cb = __uint_as_float(v[3]) + __ldg(bias + 3);
-              } else {
-                cr = __uint_as_float(v[0]) + __ldg(bias); cg = __uint_as_float(v[1]) + __ldg(bias + 1); cb = __uint_as_float(v[2]) + __ldg(bias + 2);
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster_relaxed(a_ready_leader);
+              NF_TRACE2(2 + slot, (m * 16 + j) * 4 + 3);
+            } else if (plan.kind == NF_KIND_PLAIN && m == 0) {
+              // density MLP out (tensor order [inter(I), sigma]) -> raw x0 of the View head + raw density
+              const int iu = plan.intermediate >> 4;
+              for (int un = cq; un <= iu; un += 4) {
+                uint32_t v[16];
+                tmem_ld16(t_acc + un * 16, v); tmem_ld_wait(); reg_fence16(v);
+                if (un < iu) {
+                  uint32_t o[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i)
+                    o[i] = pack_h2(__uint_as_float(v[2 * i]) + __ldg(bias + un * 16 + 2 * i), __uint_as_float(v[2 * i + 1]) + __ldg(bias + un * 16 + 2 * i + 1));
+                  uint8_t* d0 = X0 + (un * 2) * KG_BYTES + row * 16;
+                  st_v4(d0, o[0], o[1], o[2], o[3]); st_v4(d0 + KG_BYTES, o[4], o[5], o[6], o[7]);
+                } else {
+                  s.sig[slot][row] = __uint_as_float(v[0]) + __ldg(bias + plan.intermediate);
+                  float px = 0.f, py = 0.f, pz = 0.f, el = 0.f, az = 0.f;
+                  if (s.valid[slot][row]) {
+                    const long long ray = s.ray[slot][row];
+                    const float* rr = a.rays + ray * 6;
+                    const float tt = __ldg(a.ts + ray * a.ts_stride + s.t[slot][row]);
+                    const float dx = __ldg(rr + 3), dy = __ldg(rr + 4), dz = __ldg(rr + 5);
+                    px = nf_pt(__ldg(rr + 0), tt, dx); py = nf_pt(__ldg(rr + 1), tt, dy); pz = nf_pt(__ldg(rr + 2), tt, dz);
+                    nf_elaz(dx, dy, dz, el, az);
+                  }
+                  uint8_t* d0 = X0 + (iu * 2) * KG_BYTES + row * 16;
+                  st_v4(d0, pack_h2(px, py), pack_h2(pz, el), pack_h2(az, 0.f), 0);
+                  st_v4(d0 + KG_BYTES, 0, 0, 0, 0);
+                }
               }
-              cr = nf_feat_act_fn(cr, plan.feat_act); cg = nf_feat_act_fn(cg, plan.feat_act); cb = nf_feat_act_fn(cb, plan.feat_act);
-              composite_tile2(s, slot, plan, a, map, sub, row, lane, q, cr, cg, cb);
+              tc_fence_before();
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster_relaxed(a_ready_leader);
+            } else {
+              // final Linear of the path -> colours (and raw density for TinyNeRF) -> composite by the cq == 0 warps
+              if (cq == 0) {
+                uint32_t v[16];
+                tmem_ld16(t_acc, v); tmem_ld_wait(); reg_fence16(v);
+                tc_fence_before();
+                float cr, cg, cb;
+                if (plan.kind == NF_KIND_TINY) {
+                  s.sig[slot][row] = __uint_as_float(v[0]) + __ldg(bias);
+                  cr = __uint_as_float(v[1]) + __ldg(bias + 1); cg = __uint_as_float(v[2]) + __ldg(bias + 2); cb = __uint_as_float(v[3]) + __ldg(bias + 3);
+                } else {
+                  cr = __uint_as_float(v[0]) + __ldg(bias); cg = __uint_as_float(v[1]) + __ldg(bias + 1); cb = __uint_as_float(v[2]) + __ldg(bias + 2);
+                }
+                cr = nf_feat_act_fn(cr, plan.feat_act); cg = nf_feat_act_fn(cg, plan.feat_act); cb = nf_feat_act_fn(cb, plan.feat_act);
+                composite_tile2(s, slot, plan, a, map, sub, row, lane, q, cr, cg, cb);
+              }
             }
           }
         }
       }
-      named_bar(1 + slot, GROUP_THREADS);   // this slot's tile-private smem is free for its next tile
+      named_bar(1, EPI_THREADS);   // both slots' tile-private smem is free for the next tiles
     }
     (void)lin_base1;
   }
