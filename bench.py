@@ -152,7 +152,7 @@ def run_ours(args):
   value = total_rays / (ms * 1e-3)
   e2e = total_rays / (ms_e2e * 1e-3)
   peak, peak_src = peaks()
-  # dominant kernel = k_render_tc: exactly one launch per step; its average duration IS the step (events on the launch stream)
+  # dominant kernel = k_render_tc2 (paired pipeline): exactly one launch per step; its average duration IS the step (events on the launch stream)
   kern_ms = ms / args.steps
   achieved = RAYS_PER_FRAME * T * FLOP_PER_SAMPLE / (kern_ms * 1e-3) / 1e12
   traffic = None
@@ -178,7 +178,7 @@ def run_ours(args):
               "ms_per_step": ms_e2e / args.steps, "api": "FusedPlainNeRF.forward(rays) with pinned host rays in, host rgb out"},
       "gpu_launches": args.steps,
       "clocks": clocks,
-      "roofline": {"bound": "tensor", "kernel": "k_render_tc", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+      "roofline": {"bound": "tensor", "kernel": "k_render_tc2 (paired cta_group::2 pipeline)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                    "traffic": traffic, "peak_source": peak_src,
                    "algorithmic": f"{FLOP_PER_SAMPLE} FLOP/sample x {RAYS_PER_FRAME * T} samples per launch"},
     }
