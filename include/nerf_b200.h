@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NF_ABI_VERSION 1
+#define NF_ABI_VERSION 2
 
 /* error codes (negative; positive values are cudaError_t) */
 #define NF_E_BADARG    (-1)
@@ -36,7 +36,12 @@ enum nf_act { NF_ACT_NONE = 0, NF_ACT_LEAKY = 1 /* LeakyReLU(0.01) */, NF_ACT_SI
 /* input encoder of the density MLP (reference src/neural_blocks.py:36-55,92-193) */
 enum nf_enc { NF_ENC_NONE = 0, NF_ENC_HASH = 1, NF_ENC_FOURIER = 2 };
 /* raw density -> sigma (reference src/nerf.py:60-65) */
-enum nf_density_act { NF_DENS_SOFTPLUS_M1 = 0 /* softplus(x-1) */, NF_DENS_RELU = 1 };
+enum nf_density_act {
+  NF_DENS_SOFTPLUS_M1 = 0, /* softplus(x-1) */
+  NF_DENS_RELU = 1,
+  NF_DENS_LAPLACE = 2      /* VolSDF: relu(laplace_cdf(-sdf, beta) / beta), beta = the learned `scale` (reference
+                              src/nerf.py:1000-1003, src/utils.py:50-58) */
+};
 /* feature activation = the sigmoid family of reference src/utils.py:484-518 */
 enum nf_feat_act { NF_FEAT_NORMAL = 0, NF_FEAT_THIN = 1, NF_FEAT_TANH = 2, NF_FEAT_CYCLIC = 3, NF_FEAT_UPSHIFTED = 4,
                    NF_FEAT_FAT = 5, NF_FEAT_LEAKY_RELU = 6, NF_FEAT_RELU = 7, NF_FEAT_SIN = 8,
@@ -45,7 +50,9 @@ enum nf_feat_act { NF_FEAT_NORMAL = 0, NF_FEAT_THIN = 1, NF_FEAT_TANH = 2, NF_FE
 enum nf_bg { NF_BG_BLACK = 0, NF_BG_WHITE = 1 };
 /* model family */
 enum nf_kind {
-  NF_KIND_PLAIN = 0, /* PlainNeRF + View head: reference src/nerf.py:310-361, src/refl.py:190-207 */
+  NF_KIND_PLAIN = 0, /* density MLP -> [raw density | sdf, intermediate(I)] -> View head -> composite:
+                        PlainNeRF + View (reference src/nerf.py:310-361, src/refl.py:190-207) and the volume branch of
+                        VolSDF (reference src/nerf.py:981-1013, src/sdf.py:109-112,250-287) */
   NF_KIND_TINY  = 1  /* TinyNeRF (intended semantics): reference src/nerf.py:278-305 */
 };
 /* arithmetic of the MLP contractions */
@@ -79,6 +86,7 @@ typedef struct nf_model_desc {
   int32_t density_act;       /* enum nf_density_act */
   int32_t feat_act;          /* enum nf_feat_act */
   int32_t bg;                /* enum nf_bg */
+  int32_t fourier_freqs;     /* NF_ENC_FOURIER: columns of the basis [3, freqs] (x0 = [p, sin(pB), cos(pB)]) */
 } nf_model_desc;
 
 /* ---- library ----------------------------------------------------------- */
@@ -90,6 +98,8 @@ const char* nf_last_error(void);
  *   density MLP: init.weight, init.bias, layers[0].weight, layers[0].bias, ..., out.weight, out.bias
  *   refl MLP   : same order                                   (NF_KIND_PLAIN only)
  *   hash tables: embs[0].weight ... embs[levels-1].weight      (NF_ENC_HASH only)
+ *   fourier    : enc.basis [3, freqs]                          (NF_ENC_FOURIER only)
+ *   beta       : VolSDF.scale (scalar)                         (NF_DENS_LAPLACE only)
  * Each is the live fp32 nn.Parameter storage ([out,in] row-major for weights). */
 int nf_param_count(const nf_model_desc* desc);
 /* Bytes of the packed blob for `desc` (all precisions). */
@@ -128,8 +138,9 @@ int nf_sample_points(const float* rays, int64_t n_rays, const float* ts, int32_t
 int nf_hash_encode(const nf_model_desc* desc, const void* packed, const float* pts, int64_t n,
                    float* feats_out, uint16_t* idx_out, void* stream);
 /* alpha_from_density + volumetric_integrate (+sky) (reference src/nerf.py:60-80) on
- * sigma_raw[R,T], feats[R,T,3] (already activated). HBM-bound stand-alone form of the fused tail. */
-int nf_composite(const nf_model_desc* desc, const float* sigma_raw, const float* feats,
+ * sigma_raw[R,T], feats[R,T,3] (already activated). HBM-bound stand-alone form of the fused tail.
+ * `packed` is only read for NF_DENS_LAPLACE (beta); it may be NULL otherwise. */
+int nf_composite(const nf_model_desc* desc, const void* packed, const float* sigma_raw, const float* feats,
                  const float* rays, int64_t n_rays, const float* ts, int32_t T, int64_t ts_ray_stride,
                  float* rgb_out, float* alpha_out, float* weights_out, void* stream);
 /* Hierarchical resampling for the coarse+fine configuration: restatement of the reference's dead

@@ -36,6 +36,8 @@ int nf_param_count(const nf_model_desc* desc) {
   int n = 0;
   for (int m = 0; m < p.n_mlps; ++m) n += 2 * p.mlp[m].n_lin;
   if (p.enc == NF_ENC_HASH) n += p.hash_levels;
+  if (p.enc == NF_ENC_FOURIER) n += 1;
+  if (p.density_act == NF_DENS_LAPLACE) n += 1;
   return n;
 }
 
@@ -73,6 +75,18 @@ int nf_pack_weights(const nf_model_desc* desc, const float* const* params, int32
       cudaError_t e = cudaMemcpyAsync(base + p.hash_off + l * per, t, per, cudaMemcpyDeviceToDevice, st);
       if (e != cudaSuccess) return cuda_fail(e, "pack hash tables");
     }
+  }
+  if (p.enc == NF_ENC_FOURIER) {
+    const float* b = params[pi++];
+    if (!b) return fail(NF_E_BADARG, "nf_pack_weights: null fourier basis");
+    cudaError_t e = cudaMemcpyAsync(base + p.fourier_off, b, (size_t)3 * p.fourier_freqs * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return cuda_fail(e, "pack fourier basis");
+  }
+  if (p.density_act == NF_DENS_LAPLACE) {
+    const float* b = params[pi++];
+    if (!b) return fail(NF_E_BADARG, "nf_pack_weights: null beta");
+    cudaError_t e = cudaMemcpyAsync(base + p.scale_off, b, sizeof(float), cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return cuda_fail(e, "pack beta");
   }
   return 0;
 }
@@ -119,14 +133,15 @@ int nf_hash_encode(const nf_model_desc* desc, const void* packed, const float* p
   return e == cudaSuccess ? 0 : cuda_fail(e, "nf_hash_encode");
 }
 
-int nf_composite(const nf_model_desc* desc, const float* sigma_raw, const float* feats, const float* rays, int64_t n_rays,
+int nf_composite(const nf_model_desc* desc, const void* packed, const float* sigma_raw, const float* feats, const float* rays, int64_t n_rays,
                  const float* ts, int32_t T, int64_t ts_ray_stride, float* rgb_out, float* alpha_out, float* weights_out, void* stream) {
   NfPlan p; if (int rc = plan_of(desc, &p)) return rc;
   if (n_rays < 0) return fail(NF_E_BADARG, "n_rays < 0");
   if (n_rays == 0) return 0;
   if (!sigma_raw || !feats || !rays || !ts || !rgb_out) return fail(NF_E_BADARG, "nf_composite: null pointer");
+  if (p.density_act == NF_DENS_LAPLACE && !packed) return fail(NF_E_BADARG, "nf_composite: packed (beta) required for the Laplace density");
   if (int rc = check_ts(T, ts_ray_stride)) return rc;
-  cudaError_t e = nf_launch_composite(p, sigma_raw, feats, rays, n_rays, ts, T, ts_ray_stride, rgb_out, alpha_out, weights_out, (cudaStream_t)stream);
+  cudaError_t e = nf_launch_composite(p, packed, sigma_raw, feats, rays, n_rays, ts, T, ts_ray_stride, rgb_out, alpha_out, weights_out, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(e, "nf_composite");
 }
 

@@ -38,6 +38,9 @@ struct NfPlan {
   uint32_t hash_primes[3]; uint32_t pad2_;
   float hash_res[16];
   int64_t hash_off;     // byte offset: fp32 [levels][table][4]
+  int64_t fourier_off;  // byte offset: fp32 basis [3][freqs]
+  int64_t scale_off;    // byte offset: fp32 beta (VolSDF.scale)
+  int32_t fourier_freqs, pad3_;
   int64_t total_bytes;
   NfMlpPlan mlp[2];
 };
@@ -60,10 +63,16 @@ static inline int nf_build_plan(const nf_model_desc* d, NfPlan* p, const char** 
     p->hash_levels = d->hash_levels; p->hash_mask = d->hash_table_size - 1;
     for (int i = 0; i < 3; ++i) p->hash_primes[i] = d->hash_primes[i];
     for (int i = 0; i < 16; ++i) p->hash_res[i] = d->hash_res[i];
+  } else if (d->enc == NF_ENC_FOURIER) {
+    if (d->fourier_freqs < 1 || d->fourier_freqs > 128 || (d->fourier_freqs & 3)) { *why = "fourier encoder: need freqs in 4..128, multiple of 4"; return NF_E_UNSUPPORTED; }
+    p->fourier_freqs = d->fourier_freqs;
   } else if (d->enc != NF_ENC_NONE) { *why = "unsupported encoder"; return NF_E_UNSUPPORTED; }
+  if (d->density_act < 0 || d->density_act > NF_DENS_LAPLACE) { *why = "unknown density activation"; return NF_E_BADARG; }
   int64_t off = 0;
   auto take = [&](int64_t bytes) { int64_t o = off; off += (bytes + 1023) / 1024 * 1024; return o; };
   if (d->enc == NF_ENC_HASH) p->hash_off = take((int64_t)d->hash_levels * d->hash_table_size * 4 * sizeof(float));
+  if (d->enc == NF_ENC_FOURIER) p->fourier_off = take((int64_t)3 * d->fourier_freqs * sizeof(float));
+  p->scale_off = take(sizeof(float));
   for (int m = 0; m < p->n_mlps; ++m) {
     const nf_mlp_desc& md = m == 0 ? d->density : d->refl;
     NfMlpPlan& mp = p->mlp[m];
@@ -94,7 +103,7 @@ static inline int nf_build_plan(const nf_model_desc* d, NfPlan* p, const char** 
   if (d->kind == NF_KIND_PLAIN) {
     if (d->density.out_dims != 1 + d->intermediate) { *why = "density MLP out must be 1+intermediate"; return NF_E_BADARG; }
     if (d->refl.in_dims != 5 + d->intermediate || d->refl.out_dims != 3) { *why = "refl MLP must map 5+intermediate -> 3"; return NF_E_BADARG; }
-    const int want = d->enc == NF_ENC_HASH ? 6 + d->hash_levels * 4 : 3;
+    const int want = d->enc == NF_ENC_HASH ? 6 + d->hash_levels * 4 : d->enc == NF_ENC_FOURIER ? 3 + 2 * d->fourier_freqs : 3;
     if (d->density.in_dims != want) { *why = "density MLP in_dims does not match the encoder"; return NF_E_BADARG; }
   } else {
     if (d->density.in_dims != 3 || d->density.out_dims != 4 || d->enc != NF_ENC_NONE) { *why = "tiny: density MLP must map 3 -> 4 without encoder"; return NF_E_BADARG; }
@@ -151,8 +160,16 @@ __device__ __forceinline__ float nf_feat_act_fn(float v, int kind) {
   }
 }
 // raw density -> sigma, reference src/nerf.py:64-65
-__device__ __forceinline__ float nf_density_act_fn(float d, int kind) {
-  return kind == NF_DENS_RELU ? fmaxf(d, 0.f) : nf_softplus(d - 1.f);
+// `beta` is only used by NF_DENS_LAPLACE (VolSDF): sigma = relu(Psi_beta(-sdf) / beta), reference src/nerf.py:1000-1003,
+// src/utils.py:50-58 (the raw MLP output is the signed distance).
+__device__ __forceinline__ float nf_density_act_fn(float d, int kind, float beta = 1.f) {
+  if (kind == NF_DENS_RELU) return fmaxf(d, 0.f);
+  if (kind == NF_DENS_LAPLACE) {
+    const float sc = (-d) / beta;
+    const float cdf = sc <= 0.f ? expf(fminf(sc, 0.f)) / 2.f : 1.f - expf(-fmaxf(sc, 0.f)) / 2.f;
+    return fmaxf(1.f / beta * cdf, 0.f);
+  }
+  return nf_softplus(d - 1.f);
 }
 
 // ---- sample position, reference src/nerf.py:54: rounded product, then rounded add (no FMA) ----
@@ -212,8 +229,8 @@ __device__ __forceinline__ float nf_delta(const float* __restrict__ ts_ray, int 
   const float d = (t == T - 1) ? 1e10f : fmaxf(__fsub_rn(ts_ray[t + 1], ts_ray[t]), 1e-5f);
   return __fmul_rn(d, rd_norm);
 }
-__device__ __forceinline__ float nf_alpha(float sigma_raw, float delta, int density_act) {
-  const float s = nf_density_act_fn(sigma_raw, density_act);
+__device__ __forceinline__ float nf_alpha(float sigma_raw, float delta, int density_act, float beta = 1.f) {
+  const float s = nf_density_act_fn(sigma_raw, density_act, beta);
   return 1.f - expf(-s * delta);
 }
 

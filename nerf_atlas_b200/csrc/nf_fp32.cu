@@ -116,6 +116,15 @@ k_render_fp32(const __grid_constant__ NfPlan plan, const RenderArgs a) {
           s.X0[0 * ROWS + row] = px; s.X0[1 * ROWS + row] = py; s.X0[2 * ROWS + row] = pz;
           if (plan.enc == NF_ENC_HASH) { s.X0[3 * ROWS + row] = px; s.X0[4 * ROWS + row] = py; s.X0[5 * ROWS + row] = pz; }
         }
+        if (plan.enc == NF_ENC_FOURIER) {
+          // x0 = [p, sin(p B), cos(p B)], B = basis[3][F] (reference src/neural_blocks.py:36-55, src/utils.py:14-17)
+          const float* B = reinterpret_cast<const float*>(a.packed + plan.fourier_off);
+          const int F = plan.fourier_freqs;
+          for (int f = part; f < F; f += THREADS / ROWS) {
+            const float m = fmaf(pz, __ldg(B + 2 * F + f), fmaf(py, __ldg(B + F + f), __fmul_rn(px, __ldg(B + f))));
+            s.X0[(3 + f) * ROWS + row] = sinf(m); s.X0[(3 + F + f) * ROWS + row] = cosf(m);
+          }
+        }
         if (plan.enc == NF_ENC_HASH) {
           const float4* tables = reinterpret_cast<const float4*>(a.packed + plan.hash_off);
           for (int lvl = part; lvl < plan.hash_levels; lvl += THREADS / ROWS) {
@@ -162,6 +171,7 @@ k_render_fp32(const __grid_constant__ NfPlan plan, const RenderArgs a) {
           const float dx = __ldg(r + 3), dy = __ldg(r + 4), dz = __ldg(r + 5);
           const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
           const float* tsr = a.ts + ray * a.ts_stride;
+          const float beta = plan.density_act == NF_DENS_LAPLACE ? __ldg(reinterpret_cast<const float*>(a.packed + plan.scale_off)) : 1.f;
           float trans = 1.f, cr = 0.f, cg = 0.f, cb = 0.f, wsum = 0.f;
           if (sub > 0) { trans = s.carry[0]; cr = s.carry[1]; cg = s.carry[2]; cb = s.carry[3]; wsum = s.carry[4]; }
           const int nrow = a.T <= ROWS ? a.T : min(ROWS, a.T - sub * ROWS);
@@ -169,7 +179,7 @@ k_render_fp32(const __grid_constant__ NfPlan plan, const RenderArgs a) {
             const int row = row0 + i, t = s.t[row];
             float sr = s.sig[row];
             if (a.noise) sr += __ldg(a.noise + ray * a.T + t);
-            const float al = nf_alpha(sr, nf_delta(tsr, t, a.T, nrm), plan.density_act);
+            const float al = nf_alpha(sr, nf_delta(tsr, t, a.T, nrm), plan.density_act, beta);
             const float w = al * trans;
             trans *= (1.f - al) + 1e-10f;
             cr += w * nf_feat_act_fn(rgb_raw[0 * ROWS + row], plan.feat_act);
@@ -249,13 +259,14 @@ __global__ void k_hash_encode(const __grid_constant__ NfPlan plan, const uint8_t
 // Warp per ray; lanes own consecutive samples in chunks of 32; running transmittance is a
 // warp-shuffle multiplicative scan (the stand-alone form of the fused tail). HBM-bound:
 // reads 16 B/sample (sigma + rgb), writes 8 B/sample when alpha/weights are requested.
-__global__ void k_composite(int density_act, int feat_unused, int bg, const float* __restrict__ sigma_raw,
+__global__ void k_composite(int density_act, const float* __restrict__ beta_ptr, int bg, const float* __restrict__ sigma_raw,
                             const float* __restrict__ feats, const float* __restrict__ rays, long long n_rays,
                             const float* __restrict__ ts, int T, long long ts_stride,
                             float* __restrict__ rgb_out, float* __restrict__ alpha_out, float* __restrict__ weights_out) {
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const float beta = beta_ptr ? __ldg(beta_ptr) : 1.f;
   for (long long ray = warp; ray < n_rays; ray += nwarps) {
     const float* r = rays + ray * 6;
     const float dx = __ldg(r + 3), dy = __ldg(r + 4), dz = __ldg(r + 5);
@@ -266,7 +277,7 @@ __global__ void k_composite(int density_act, int feat_unused, int bg, const floa
       const int t = base + lane;
       float al = 0.f, fr = 0.f, fg = 0.f, fb = 0.f;
       if (t < T) {
-        al = nf_alpha(__ldg(sigma_raw + ray * T + t), nf_delta(tsr, t, T, nrm), density_act);
+        al = nf_alpha(__ldg(sigma_raw + ray * T + t), nf_delta(tsr, t, T, nrm), density_act, beta);
         const float* f = feats + (ray * T + t) * 3;
         fr = __ldg(f); fg = __ldg(f + 1); fb = __ldg(f + 2);
       }
@@ -431,11 +442,12 @@ cudaError_t nf_launch_sample_pdf(const float* ts, int T, const float* weights, i
   return cudaGetLastError();
 }
 
-cudaError_t nf_launch_composite(const NfPlan& plan, const float* sigma_raw, const float* feats, const float* rays, int64_t n_rays,
+cudaError_t nf_launch_composite(const NfPlan& plan, const void* packed, const float* sigma_raw, const float* feats, const float* rays, int64_t n_rays,
                                 const float* ts, int T, int64_t ts_stride, float* rgb, float* alpha, float* weights, cudaStream_t st) {
   if (n_rays == 0) return cudaSuccess;
   const long long want = (n_rays * 32 + 255) / 256;
   const int grid = (int)(want < (long long)num_sms() * 8 ? want : (long long)num_sms() * 8);
-  k_composite<<<grid, 256, 0, st>>>(plan.density_act, 0, plan.bg, sigma_raw, feats, rays, n_rays, ts, T, ts_stride, rgb, alpha, weights);
+  const float* beta = (plan.density_act == NF_DENS_LAPLACE && packed) ? reinterpret_cast<const float*>((const uint8_t*)packed + plan.scale_off) : nullptr;
+  k_composite<<<grid, 256, 0, st>>>(plan.density_act, beta, plan.bg, sigma_raw, feats, rays, n_rays, ts, T, ts_stride, rgb, alpha, weights);
   return cudaGetLastError();
 }

@@ -14,7 +14,7 @@ cudaError_t nf_launch_mlp_fp32(const NfPlan& plan, int which, const void* packed
 cudaError_t nf_launch_mlp_tc(const NfPlan& plan, int which, const void* packed, const float* x0, int64_t n, float* out, cudaStream_t st);
 cudaError_t nf_launch_sample_points(const float* rays, int64_t n_rays, const float* ts, int T, int64_t ts_stride, float* pts, cudaStream_t st);
 cudaError_t nf_launch_hash_encode(const NfPlan& plan, const void* packed, const float* pts, int64_t n, float* feats, uint16_t* idx, cudaStream_t st);
-cudaError_t nf_launch_composite(const NfPlan& plan, const float* sigma_raw, const float* feats, const float* rays, int64_t n_rays,
+cudaError_t nf_launch_composite(const NfPlan& plan, const void* packed, const float* sigma_raw, const float* feats, const float* rays, int64_t n_rays,
                                 const float* ts, int T, int64_t ts_stride, float* rgb, float* alpha, float* weights, cudaStream_t st);
 cudaError_t nf_launch_sample_pdf(const float* ts, int T, const float* weights, int64_t n_rays, const float* u, int nf, float* out, cudaStream_t st);
 // paired (cta_group::2, two tiles in flight) tensor pipeline, nf_tc2.cu

@@ -133,7 +133,8 @@ __device__ __forceinline__ void composite_tile(TcSmem& s, const NfPlan& plan, co
   if (valid) {
     float sr = s.sig[row];
     if (a.noise) sr += __ldg(a.noise + ray * a.T + t);
-    al = nf_alpha(sr, s.delta[row], plan.density_act);
+    const float beta = plan.density_act == NF_DENS_LAPLACE ? __ldg(reinterpret_cast<const float*>(a.packed + plan.scale_off)) : 1.f;
+    al = nf_alpha(sr, s.delta[row], plan.density_act, beta);
   }
   float incl = valid ? (1.f - al) + 1e-10f : 1.f;
 #pragma unroll
@@ -215,13 +216,13 @@ k_render_tc(const __grid_constant__ NfPlan plan, const __grid_constant__ TcProg 
   const NfTileMap map(a.mlp_only ? ROWS : a.T, ROWS);
   const TileIter it(a, map);
   const int m_begin = a.mlp_only ? a.which : 0, m_end = a.mlp_only ? a.which + 1 : plan.n_mlps;
-  const int lin_base1 = plan.mlp[0].n_lin;   // global linear index of refl MLP's first Linear
+  const int lin_base1 = a.mlp_only ? 0 : plan.mlp[0].n_lin;   // bias slot of the refl MLP's first Linear (mlp-only runs: the one MLP at 0)
 
   long long* tr = a.trace; int tr_n[3] = {0, 0, 0}; bool tr_on = false; (void)tr; (void)tr_n;
   // ---- one-time setup ----
   for (int i = threadIdx.x; i < MAX_LIN_TOTAL * 256; i += THREADS) {
     const int g = i >> 8, n = i & 255;
-    const int m = g >= lin_base1 ? 1 : 0, j = g - (m ? lin_base1 : 0);
+    const int m = a.mlp_only ? a.which : (g >= lin_base1 ? 1 : 0), j = g - ((!a.mlp_only && m) ? lin_base1 : 0);
     float v = 0.f;
     if (m < plan.n_mlps && j < plan.mlp[m].n_lin && n < plan.mlp[m].lin[j].n_pad)
       v = __ldg(reinterpret_cast<const float*>(a.packed + plan.mlp[m].lin[j].b16_off) + n);
@@ -422,7 +423,7 @@ k_render_tc(const __grid_constant__ NfPlan plan, const __grid_constant__ TcProg 
           for (int j = 0; j < M.n_lin; ++j, ++lin_count) {
             const NfLinPlan& L = M.lin[j];
             const uint32_t buf = lin_count & 1;
-            const float* bias = s.bias + ((m ? lin_base1 : 0) + j) * 256;
+            const float* bias = s.bias + (((!a.mlp_only && m) ? lin_base1 : 0) + j) * 256;
             tr_on = (a.debug & 4) && blockIdx.x == 0 && trip == 2 && warp == 0 && lane == 0;
             NF_TRACE(2, (m * 16 + j) * 4 + 0);
             mbar_wait_backoff(smem_u32(&s.acc_full[buf]), (acc_par >> buf) & 1u);
@@ -555,10 +556,14 @@ int tc_num_sms() {
 }
 
 // nullptr if the tensor path can run this model, else the reason.
-const char* tc_unsupported(const NfPlan& p) {
+const char* tc_unsupported(const NfPlan& p, int only_mlp = -1) {
   int total = 0;
-  for (int m = 0; m < p.n_mlps; ++m) { total += p.mlp[m].n_lin; if (p.mlp[m].k0_pad > X0K) return "x0 wider than 80 columns"; }
+  for (int m = 0; m < p.n_mlps; ++m) {
+    if (only_mlp >= 0 && m != only_mlp) continue;
+    total += p.mlp[m].n_lin; if (p.mlp[m].k0_pad > X0K) return "x0 wider than 80 columns";
+  }
   if (total > MAX_LIN_TOTAL) return "more than 12 Linear layers";
+  if (p.enc == NF_ENC_FOURIER && only_mlp != 1) return "Fourier-encoded density MLP runs on the fp32 pipeline only";
   if (p.enc == NF_ENC_HASH && (p.hash_levels & 1)) return "odd number of hash levels";
   if (p.kind == NF_KIND_PLAIN && (p.intermediate & 15)) return "intermediate_size not a multiple of 16";
   return nullptr;
@@ -603,7 +608,7 @@ void build_prog(const NfPlan& plan, int m_begin, int m_end, TcProg* P) {
 
 cudaError_t launch_tc(const NfPlan& plan, TcArgs a, long long units, cudaStream_t st) {
   if (const char* dbg = getenv("NF_TC_DEBUG")) a.debug = atoi(dbg);
-  if (tc_unsupported(plan)) return cudaErrorNotSupported;
+  if (tc_unsupported(plan, a.mlp_only ? a.which : -1)) return cudaErrorNotSupported;
   cudaError_t e = cudaFuncSetAttribute(k_render_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcSmem));
   if (e != cudaSuccess) return e;
   if (units == 0) return cudaSuccess;

@@ -34,7 +34,8 @@ constexpr int SPC = NF_TC_CHUNK_K / 16;                     // UMMA K-steps per 
 constexpr int STAGE_BYTES = NF_TC_CHUNK_K * 128 * 2;       // 16 KB: 64 K-columns x 128 N (this CTA's half) x fp16
 constexpr int THREADS = 640;
 constexpr int EPI_THREADS = 512;                             // 16 encode/epilogue warps
-constexpr int MAX_ENT = 96;                                 // program entries per round (every Linear's chunks, twice)
+constexpr int MAX_ENT = 128;                                // ring entries per round (every Linear's chunks, twice)
+constexpr int MAX_LIN2 = 16;
 constexpr uint32_t F_NSTEP = 7, F_FIRST = 8, F_LAST = 16, F_SLOT = 32, F_WAIT_A = 64;
 
 struct Tc2Smem {
@@ -57,7 +58,7 @@ static_assert(sizeof(Tc2Smem) <= 227 * 1024, "paired tensor pipeline smem");
 struct __align__(16) Tc2Lin { uint32_t k0_steps, h_steps, idesc, bstep4, bhi, pad0_, pad1_, pad2_; };   // one Linear
 struct __align__(16) Tc2Prog {
   int32_t n_lin, n_ent, pad0_, pad1_;
-  Tc2Lin lin[12];
+  Tc2Lin lin[MAX_LIN2];
   uint8_t ent_chunk[MAX_ENT];     // producers: distinct weight-chunk index of every ring entry of a round
 };
 
@@ -162,7 +163,8 @@ __device__ __forceinline__ void composite_tile2(Tc2Smem& s, int slot, const NfPl
     if (a.noise) sr += __ldg(a.noise + ray * a.T + t);
     const float* rr = a.rays + ray * 6;
     const float dx = __ldg(rr + 3), dy = __ldg(rr + 4), dz = __ldg(rr + 5);
-    al = nf_alpha(sr, nf_delta(a.ts + ray * a.ts_stride, t, a.T, sqrtf(dx * dx + dy * dy + dz * dz)), plan.density_act);
+    const float beta = plan.density_act == NF_DENS_LAPLACE ? __ldg(reinterpret_cast<const float*>(a.packed + plan.scale_off)) : 1.f;
+    al = nf_alpha(sr, nf_delta(a.ts + ray * a.ts_stride, t, a.T, sqrtf(dx * dx + dy * dy + dz * dz)), plan.density_act, beta);
   }
   float incl = valid ? (1.f - al) + 1e-10f : 1.f;
 #pragma unroll
@@ -525,7 +527,8 @@ const char* nf_tc2_unsupported(const NfPlan& p) {
     for (int j = 0; j < p.mlp[m].n_lin; ++j) chunks += p.mlp[m].lin[j].n_chunks;
   }
   if (2 * chunks > MAX_ENT) return "too many weight chunks";
-  if (nlin > 12) return "more than 12 Linear layers";
+  if (nlin > MAX_LIN2) return "more than 16 Linear layers";
+  if (p.enc == NF_ENC_FOURIER) return "Fourier-encoded density MLP (x0 is 259 wide) runs on the fp32 pipeline only";
   if (p.enc == NF_ENC_HASH && (p.hash_levels & 1)) return "odd number of hash levels";
   if (p.kind == NF_KIND_PLAIN && (p.intermediate & 15)) return "intermediate_size not a multiple of 16";
   return nullptr;

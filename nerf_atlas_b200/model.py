@@ -61,6 +61,26 @@ def describe_plain(intermediate: int = 64, sigmoid: str = "upshifted", bg: str =
   return d
 
 
+def describe_volsdf(sdf_kind: str = "siren", intermediate: int = 64, sigmoid: str = "upshifted", fourier_freqs: int = 128) -> ModelDesc:
+  """Volume branch of VolSDF (reference src/nerf.py:981-1013): SDF network (`siren`: src/sdf.py:278-287, `mlp`:
+  src/sdf.py:250-258) -> Laplace-CDF density with the learned `scale` -> View head (sdf.refl) -> composite, no sky."""
+  d = ModelDesc()
+  d.struct_bytes = C.sizeof(ModelDesc)
+  d.kind = _lib.KIND["plain"]
+  if sdf_kind == "siren":
+    d.density = _mlp(3, 5, 1 + intermediate, "sin"); d.enc = _lib.ENC["none"]
+  elif sdf_kind == "mlp":
+    d.density = _mlp(3 + 2 * fourier_freqs, 6, 1 + intermediate, "leaky_relu"); d.enc = _lib.ENC["fourier"]
+    d.fourier_freqs = fourier_freqs
+  else: raise NotImplementedError(f"sdf kind {sdf_kind}")
+  d.refl = _mlp(5 + intermediate, 4, 3, "sin")
+  d.intermediate = intermediate
+  d.density_act = _lib.DENSITY["laplace"]
+  d.feat_act = _lib.FEAT[sigmoid]
+  d.bg = _lib.BG["black"]          # volumetric_integrate only: no sky term (nerf.py:1013)
+  return d
+
+
 def describe_tiny(sigmoid: str = "upshifted", bg: str = "black") -> ModelDesc:
   """TinyNeRF (reference src/nerf.py:278-305), intended semantics."""
   d = ModelDesc()
@@ -181,7 +201,7 @@ class RenderEngine:
     alpha = torch.empty(R, T, dtype=torch.float32, device=rays.device) if want_weights else None
     weights = torch.empty(R, T, dtype=torch.float32, device=rays.device) if want_weights else None
     with torch.cuda.device(rays.device):
-      rc = self.lib.nf_composite(C.byref(self.desc), _ptr(sigma_raw), _ptr(feats), _ptr(rays), R, _ptr(ts), T, stride,
+      rc = self.lib.nf_composite(C.byref(self.desc), _ptr(self.packed), _ptr(sigma_raw), _ptr(feats), _ptr(rays), R, _ptr(ts), T, stride,
                                  _ptr(rgb), _ptr(alpha), _ptr(weights), self._stream())
     _lib.check(rc, "nf_composite")
     return rgb, alpha, weights
@@ -398,6 +418,81 @@ class FusedPlainNeRF(FusedNeRF):
     for mlp in (self.first, self.refl.mlp):
       for lin in _linears_of(mlp): ps += [lin.weight, lin.bias]
     ps += [e.weight for e in self.first.enc.embs]
+    return ps
+
+
+class _SdfBox(nn.Module):
+  """Container mirroring the reference's `SDF` (src/sdf.py:83-112): `.underlying.{siren|mlp}` and `.refl`."""
+  def __init__(self, underlying: nn.Module, refl: nn.Module):
+    super().__init__(); self.underlying = underlying; self.refl = refl
+
+
+class _SdfNet(nn.Module):
+  def __init__(self, kind: str, intermediate: int, freqs: int = 128):
+    super().__init__()
+    self.kind, self.intermediate_size = kind, intermediate
+    if kind == "siren": self.siren = SkipConnParams(3, 1 + intermediate, 5, init="siren")
+    else:
+      enc = nn.Module(); enc.basis = nn.Parameter(16 * torch.randn(freqs, 3).T.contiguous(), requires_grad=False)
+      self.mlp = SkipConnParams(3 + 2 * freqs, 1 + intermediate, 6, init="xavier", enc=enc)
+  def net(self): return self.siren if self.kind == "siren" else self.mlp
+
+
+class FusedVolSDF(FusedNeRF):
+  """Drop-in for the volume-rendering branch of VolSDF (reference src/nerf.py:861-1018) with a View head.  Parameter
+  names follow the reference (`scale`, `sdf.underlying.{siren|mlp}.*`, `sdf.refl.mlp.*`).  Secondary lighting,
+  normals and occlusion (nerf.py:923-980,1006-1011) are out of scope."""
+  kind = "volsdf"
+
+  def __init__(self, sdf_kind: str = "siren", out_features: int = 3, **kwargs):
+    kwargs.setdefault("sigmoid_kind", "thin")
+    super().__init__(**kwargs)
+    if out_features != 3: raise NotImplementedError("out_features != 3")
+    self.scale = nn.Parameter(torch.tensor(0.1))
+    self.sdf = _SdfBox(_SdfNet(sdf_kind, self.intermediate_size),
+                       ViewHead(latent_size=self.intermediate_size, out_features=3, act=self.sigmoid_kind))
+
+  @property
+  def refl(self): return self.sdf.refl
+  def set_refl(self, refl): self.sdf.refl = refl
+  def set_sigmoid(self, kind="thin"):
+    if kind not in _lib.FEAT: raise NotImplementedError(f"Unknown sigmoid kind({kind})")
+    self.sigmoid_kind = kind; self.sdf.refl.act = kind
+
+  @classmethod
+  def from_reference(cls, ref, precision: str = "fp16", keep_weights: bool = True) -> "FusedVolSDF":
+    self = cls.__new__(cls)
+    FusedNeRF.__init__(self, steps=ref.steps, t_near=ref.t_near, t_far=ref.t_far, intermediate_size=ref.intermediate_size,
+                       sigmoid_kind=_sigmoid_name(ref.sdf.refl.act), precision=precision, keep_weights=keep_weights)
+    if type(ref.sdf.refl).__name__ not in ("View", "ViewHead"): raise NotImplementedError(f"refl head {type(ref.sdf.refl).__name__}")
+    if getattr(ref, "secondary", None) is not None: raise NotImplementedError("VolSDF secondary lighting")
+    self.scale, self.sdf = ref.scale, ref.sdf
+    return self
+
+  def _sdf_net(self):
+    u = self.sdf.underlying
+    if hasattr(u, "siren"): return "siren", u.siren
+    if hasattr(u, "mlp"): return "mlp", u.mlp
+    raise NotImplementedError(f"sdf network {type(u).__name__}")
+
+  def engine(self) -> RenderEngine:
+    key = (self.kind, self._sdf_net()[0], _sigmoid_name(self.sdf.refl.act), self.precision)
+    if self._engine is None or self._engine_key != key:
+      self._engine, self._engine_key = RenderEngine(self._describe(), self.precision), key
+    return self._engine
+
+  def _describe(self) -> ModelDesc:
+    kind, net = self._sdf_net()
+    freqs = net.enc.basis.shape[1] if kind == "mlp" else 128
+    return describe_volsdf(kind, self.intermediate_size, _sigmoid_name(self.sdf.refl.act), freqs)
+
+  def _param_list(self) -> List[torch.Tensor]:
+    kind, net = self._sdf_net()
+    ps: List[torch.Tensor] = []
+    for mlp in (net, self.sdf.refl.mlp):
+      for lin in _linears_of(mlp): ps += [lin.weight, lin.bias]
+    if kind == "mlp": ps.append(net.enc.basis)
+    ps.append(self.scale.reshape(1) if self.scale.dim() == 0 else self.scale)
     return ps
 
 

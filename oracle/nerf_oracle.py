@@ -17,7 +17,7 @@ arithmetic library; no ``nn.Module`` from the reference is used), of
   * alpha-from-density + composite    reference src/nerf.py:22-27,60-80
   * PlainNeRF.forward / from_pts      reference src/nerf.py:326-361
   * TinyNeRF.forward (intended)       reference src/nerf.py:292-305
-  * VolSDF volume branch              reference src/nerf.py:981-1013, src/utils.py:50-58
+  * VolSDF volume branch              reference src/nerf.py:981-1013, src/utils.py:50-58, src/sdf.py:109-112,250-287
   * DynamicNeRF direct / spline       reference src/nerf.py:1173-1206,1261-1303
   * sample_pdf (restated, dead code)  reference src/nerf.py:1745-1779
 
@@ -342,7 +342,33 @@ def tiny_forward(params: Params, rays: Tensor, ts: Tensor, *, sigmoid: str = "up
 # ----------------------------------------------------------------------------
 def laplace_cdf(sdf_vals: Tensor, beta: Tensor) -> Tensor:
   scaled = sdf_vals / beta
-  return torch.where(scaled <= 0, scaled.exp() / 2, 1 - scaled.neg().exp() / 2)
+  return torch.where(scaled <= 0, scaled.clamp(max=0).exp() / 2, 1 - scaled.clamp(min=0).neg().exp() / 2)
+
+
+def volsdf_forward(params: Params, rays: Tensor, ts: Tensor, *, sdf_kind: str = "siren", sigmoid: str = "upshifted",
+                   quant: Optional[torch.dtype] = None) -> Dict[str, Tensor]:
+  """VolSDF.forward / from_pts, volume-rendering branch with a View head (reference src/nerf.py:981-1013; SDF
+  networks src/sdf.py:250-258 `mlp`, 278-287 `siren`; SDF.from_pts src/sdf.py:109-112)."""
+  pts, r_o, r_d = compute_pts(rays, ts)
+  batches = pts.shape[:-1]
+  p = pts.reshape(-1, 3)
+  if sdf_kind == "siren":
+    raw = skip_mlp(p, params, "sdf.underlying.siren", "sin", quant=quant)
+  elif sdf_kind == "mlp":
+    x0 = torch.cat([p, fourier_encode(p, params["sdf.underlying.mlp.enc.basis"])], dim=-1)
+    raw = skip_mlp(x0, params, "sdf.underlying.mlp", "leaky_relu", quant=quant)
+  else: raise NotImplementedError(sdf_kind)
+  raw = raw.reshape(batches + (-1,))
+  sdf_vals, latent = raw[..., 0], raw[..., 1:]
+  scale = params["scale"]
+  density = 1 / scale * laplace_cdf(-sdf_vals, scale)
+  alpha, weights = alpha_from_density(density, ts, r_d, softplus=False)
+  view = r_d.unsqueeze(0).expand_as(pts)
+  elaz = dir_to_elev_azim(view)
+  x0r = torch.cat([pts, elaz, latent], dim=-1).reshape(-1, 5 + latent.shape[-1])
+  rgb = SIGMOIDS[sigmoid](skip_mlp(x0r, params, "sdf.refl.mlp", "sin", quant=quant).reshape(batches + (-1,)))
+  out = volumetric_integrate(weights, rgb)
+  return dict(out=out, alpha=alpha, weights=weights, rgb=rgb, sdf=sdf_vals, pts=pts)
 
 
 # ----------------------------------------------------------------------------
@@ -416,6 +442,30 @@ def make_plain_params(seed: int = 1337, intermediate: int = 64, sigma_gain: floa
   siren_linear("refl.mlp.layers.0", 256, 256 + 5 + I)
   for i in (1, 2, 3): siren_linear(f"refl.mlp.layers.{i}", 256, 256)
   siren_linear("refl.mlp.out", 3, 256)
+  return P
+
+
+def make_volsdf_params(seed: int = 7, sdf_kind: str = "siren", intermediate: int = 64, beta: float = 0.1) -> Params:
+  """VolSDF + View parameters with the reference's init distributions and state_dict names (SIREN: siren init, MLP:
+  xavier-uniform with zero bias and a 16*N(0,1) Fourier basis, src/sdf.py:250-287; View: siren init)."""
+  g = np.random.default_rng(seed)
+  P: Params = {"empty_latent": torch.zeros(1, 1, 1, 1, 0), "scale": torch.tensor(beta)}
+  def uni(shape, a): return torch.from_numpy(g.uniform(-a, a, size=shape).astype(np.float32))
+  def siren(name, o, i): P[f"{name}.weight"] = uni((o, i), math.sqrt(6.0 / i)); P[f"{name}.bias"] = torch.zeros(o)
+  def xavier(name, o, i): P[f"{name}.weight"] = uni((o, i), math.sqrt(6.0 / (i + o))); P[f"{name}.bias"] = torch.zeros(o)
+  I = intermediate
+  if sdf_kind == "siren":
+    pre, lin, n_layers, d0 = "sdf.underlying.siren", siren, 5, 3
+  else:
+    pre, lin, n_layers, d0 = "sdf.underlying.mlp", xavier, 6, 3 + 256
+    P[f"{pre}.enc.basis"] = torch.from_numpy((16 * g.standard_normal((128, 3))).astype(np.float32)).T.contiguous()
+  lin(f"{pre}.init", 256, d0)
+  for i in range(n_layers): lin(f"{pre}.layers.{i}", 256, 256 + d0 if (i % 3 == 0 and i != n_layers - 1) else 256)
+  lin(f"{pre}.out", 1 + I, 256)
+  siren("sdf.refl.mlp.init", 256, 5 + I)
+  siren("sdf.refl.mlp.layers.0", 256, 256 + 5 + I)
+  for i in (1, 2, 3): siren(f"sdf.refl.mlp.layers.{i}", 256, 256)
+  siren("sdf.refl.mlp.out", 3, 256)
   return P
 
 

@@ -70,6 +70,19 @@ def case_plain(name, seed, B, H, W, T, sigma_gain=1.0, train=False, top=0, left=
   np.savez_compressed(os.path.join(HERE, name + ".npz"), **fx)
   print(name, "out", out.shape, "mean", float(out.mean()), "acc-before-last", float(model.weights[:-1].sum(0).mean()))
 
+def case_volsdf(name, seed, sdf_kind, B, H, W, T, top=0, left=0):
+  params = O.make_volsdf_params(seed, sdf_kind, 64, 0.1)
+  rays = O.make_rays(B, H, W, size=800, seed=seed, crop_top=top, crop_left=left)
+  model, args = ref_shim.build_model("volsdf", T, extra=("--sdf-kind", sdf_kind))
+  model.load_state_dict({k: v.clone() for k, v in params.items()}, strict=True)
+  model.eval()
+  with torch.no_grad(): out = model(rays)
+  fx = dict(kind="volsdf", sdf_kind=sdf_kind, seed=seed, B=B, H=H, W=W, T=T, top=top, left=left,
+            near=float(args.near), far=float(args.far), sigmoid=args.sigmoid_kind,
+            ts=model.ts.numpy(), out=out.numpy(), alpha=model.alpha.numpy(), weights=model.weights.numpy())
+  np.savez_compressed(os.path.join(HERE, name + ".npz"), **fx)
+  print(name, "out", out.shape, "mean", float(out.mean()), "acc-before-last", float(model.weights[:-1].sum(0).mean()))
+
 def r_o_pts(rays, ts):
   r_o, r_d = rays.split([3, 3], dim=-1)
   pts = r_o.unsqueeze(0) + torch.tensordot(ts, r_d, dims=0)
@@ -104,4 +117,6 @@ if __name__ == "__main__":
   case_plain("plain_t16", seed=11, B=1, H=4, W=6, T=16)
   case_plain("plain_t16_sharp", seed=12, B=2, H=3, W=5, T=16, sigma_gain=20.0, top=390, left=380)
   case_plain("plain_t128", seed=1337, B=1, H=8, W=8, T=128, sigma_gain=20.0, top=396, left=396, stages=False)
+  case_volsdf("volsdf_siren_t32", seed=31, sdf_kind="siren", B=1, H=4, W=5, T=32, top=398, left=397)
+  case_volsdf("volsdf_mlp_t32", seed=32, sdf_kind="mlp", B=1, H=3, W=4, T=32, top=398, left=397)
   case_plain("plain_t64_train", seed=21, B=1, H=4, W=4, T=64, sigma_gain=20.0, train=True, top=300, left=420, stages=False)

@@ -52,3 +52,24 @@ def tiny_param_list(P, device):
 def psnr(a, b):
   mse = float(np.mean((np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64)) ** 2))
   return 200.0 if mse == 0 else -10 * np.log10(mse)
+
+def volsdf_param_list(P, sdf_kind, device):
+  pre = "sdf.underlying.siren" if sdf_kind == "siren" else "sdf.underlying.mlp"
+  names = []
+  for q in (pre, "sdf.refl.mlp"):
+    names += [f"{q}.init.weight", f"{q}.init.bias"]
+    i = 0
+    while f"{q}.layers.{i}.weight" in P:
+      names += [f"{q}.layers.{i}.weight", f"{q}.layers.{i}.bias"]; i += 1
+    names += [f"{q}.out.weight", f"{q}.out.bias"]
+  ps = [P[n].to(device).contiguous() for n in names]
+  if sdf_kind == "mlp": ps.append(P[f"{pre}.enc.basis"].to(device).contiguous())
+  ps.append(P["scale"].reshape(1).to(device))
+  return ps
+
+def volsdf_engine(P, sdf_kind, device, sigmoid="upshifted", precision="fp16"):
+  import nerf_atlas_b200 as N
+  eng = N.RenderEngine(N.describe_volsdf(sdf_kind, 64, sigmoid), precision)
+  eng._params = volsdf_param_list(P, sdf_kind, device)
+  eng.pack(eng._params)
+  return eng

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 import torch
 from oracle import nerf_oracle as O
-from helpers import load_golden, plain_engine, plain_param_list, make_tiny_params, tiny_param_list, psnr
+from helpers import load_golden, plain_engine, plain_param_list, make_tiny_params, tiny_param_list, psnr, volsdf_engine
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -247,3 +247,46 @@ def test_render_coarse_fine_64_128(P):
     np.testing.assert_allclose(ts_f.cpu().numpy(), ref["ts"].t().numpy(), rtol=0, atol=2e-4 if precision == "fp16" else 2e-5)
     assert np.abs(rgb_c.cpu().numpy() - ref["coarse"].numpy()).max() <= tol
     assert np.abs(rgb_f.cpu().numpy() - ref["out"].numpy()).max() <= (2e-3 if precision == "fp16" else tol), precision
+
+# ---------------------------------------------------------------- VolSDF volume branch (config 4)
+@pytest.mark.parametrize("name,precision,tol", [("volsdf_siren_t32", "fp32", 5e-5), ("volsdf_siren_t32", "fp16", 1e-3),
+                                                ("volsdf_mlp_t32", "fp32", 2e-4)])
+def test_volsdf_matches_reference_golden(name, precision, tol):
+  fx = load_golden(name)
+  kind = str(fx["sdf_kind"])
+  P = O.make_volsdf_params(int(fx["seed"]), kind, 64, 0.1)
+  rays = O.make_rays(int(fx["B"]), int(fx["H"]), int(fx["W"]), 800, int(fx["seed"]), int(fx["top"]), int(fx["left"])).reshape(-1, 6)
+  e = volsdf_engine(P, kind, DEV, str(fx["sigmoid"]), precision)
+  rgb, alpha, w = e.render(rays.to(DEV), torch.from_numpy(fx["ts"]).to(DEV))
+  out = rgb.cpu().numpy().reshape(fx["out"].shape)
+  assert np.isfinite(out).all()
+  assert np.abs(out - fx["out"]).max() <= tol, np.abs(out - fx["out"]).max()
+  ww = w.cpu().numpy().T.reshape(fx["weights"].shape)
+  assert np.abs(ww - fx["weights"]).max() <= (2e-2 if precision == "fp16" else 2e-3)
+
+def test_volsdf_256_samples_and_tensor_path_refuses_fourier():
+  """BASELINE config 4 shape: 256 SDF samples/ray (two 128-sample tiles per ray, transmittance carried across)."""
+  P = O.make_volsdf_params(41, "siren", 64, 0.25)
+  rays = O.make_rays(1, 5, 6, seed=41, crop_top=397, crop_left=396).reshape(-1, 6)
+  rays[:, 3:] = torch.nn.functional.normalize(rays[:, 3:], dim=-1)            # DTU cameras give unit directions
+  ts = torch.linspace(0.3, 1.8, 256)
+  with torch.no_grad(): ref = O.volsdf_forward(P, rays, ts, sdf_kind="siren")
+  for precision, tol in (("fp32", 5e-5), ("fp16", 1e-3)):
+    e = volsdf_engine(P, "siren", DEV, precision=precision)
+    rgb, _, w = e.render(rays.to(DEV), ts.to(DEV))
+    assert np.abs(rgb.cpu().numpy() - ref["out"].numpy()).max() <= tol, precision
+  Pm = O.make_volsdf_params(42, "mlp", 64, 0.1)
+  em = volsdf_engine(Pm, "mlp", DEV, precision="fp16")
+  with pytest.raises(RuntimeError): em.render(rays.to(DEV), ts.to(DEV))       # no silent fallback: fp32 only for the Fourier MLP
+
+def test_fused_volsdf_module_surface():
+  import nerf_atlas_b200 as N
+  P = O.make_volsdf_params(43, "siren", 64, 0.1)
+  m = N.FusedVolSDF(sdf_kind="siren", steps=32, t_near=2, t_far=6, intermediate_size=64, sigmoid_kind="upshifted", precision="fp32")
+  m.load_state_dict(P, strict=True)                                             # the reference's state_dict names
+  m = m.to(DEV).eval()
+  rays = O.make_rays(1, 4, 5, seed=43, crop_top=397, crop_left=396).to(DEV)
+  with torch.no_grad(): out = m(rays)
+  with torch.no_grad(): ref = O.volsdf_forward(P, rays.cpu(), m.ts.cpu(), sdf_kind="siren")
+  assert out.shape == (1, 4, 5, 3) and m.weights.shape == (32, 1, 4, 5)
+  assert np.abs(out.cpu().numpy() - ref["out"].numpy()).max() <= 5e-5

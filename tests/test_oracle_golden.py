@@ -49,6 +49,16 @@ def test_u32_identity_negative_and_large_coordinates():
   for lvl in range(8):
     assert np.array_equal(O.hash_indices_u32(p, lvl), O.hash_indices(torch.from_numpy(p), lvl).numpy())
 
+@pytest.mark.parametrize("name", ["volsdf_siren_t32", "volsdf_mlp_t32"])
+def test_volsdf_oracle_matches_reference_bit_exact(golden_dir, name):
+  fx = load(golden_dir, name)
+  params = O.make_volsdf_params(int(fx["seed"]), str(fx["sdf_kind"]), 64, 0.1)
+  rays = O.make_rays(int(fx["B"]), int(fx["H"]), int(fx["W"]), 800, int(fx["seed"]), int(fx["top"]), int(fx["left"]))
+  ts = O.compute_ts(float(fx["near"]), float(fx["far"]), int(fx["T"]))
+  with torch.no_grad(): res = O.volsdf_forward(params, rays, ts, sdf_kind=str(fx["sdf_kind"]), sigmoid=str(fx["sigmoid"]))
+  for k in ("out", "alpha", "weights"):
+    assert np.array_equal(res[k].numpy(), fx[k]), f"{name}: {k} differs from the reference run"
+
 def test_hash_resolutions_decrease():
   # operator-precedence quirk of neural_blocks.py:126-128: scale < 1, resolutions 16 -> 6.28
   r = O.hash_resolutions()
