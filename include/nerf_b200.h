@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NF_ABI_VERSION 2
+#define NF_ABI_VERSION 3
 
 /* error codes (negative; positive values are cudaError_t) */
 #define NF_E_BADARG    (-1)
@@ -53,7 +53,9 @@ enum nf_kind {
   NF_KIND_PLAIN = 0, /* density MLP -> [raw density | sdf, intermediate(I)] -> View head -> composite:
                         PlainNeRF + View (reference src/nerf.py:310-361, src/refl.py:190-207) and the volume branch of
                         VolSDF (reference src/nerf.py:981-1013, src/sdf.py:109-112,250-287) */
-  NF_KIND_TINY  = 1  /* TinyNeRF (intended semantics): reference src/nerf.py:278-305 */
+  NF_KIND_TINY  = 1, /* TinyNeRF (intended semantics): reference src/nerf.py:278-305 */
+  NF_KIND_DYN   = 2  /* DynamicNeRF, direct deformation MLP over a canonical PlainNeRF (reference src/nerf.py:1209-1303):
+                        delta_estim([p, t]) -> (dp[1], rigidity[3]); p' = p + dp * sigmoid(rigidity / 2); then NF_KIND_PLAIN on p' */
 };
 /* arithmetic of the MLP contractions */
 enum nf_precision {
@@ -87,6 +89,7 @@ typedef struct nf_model_desc {
   int32_t feat_act;          /* enum nf_feat_act */
   int32_t bg;                /* enum nf_bg */
   int32_t fourier_freqs;     /* NF_ENC_FOURIER: columns of the basis [3, freqs] (x0 = [p, sin(pB), cos(pB)]) */
+  nf_mlp_desc deform;        /* NF_KIND_DYN: DynamicNeRF.delta_estim (in 4 = xyz,t; out 4) */
 } nf_model_desc;
 
 /* ---- library ----------------------------------------------------------- */
@@ -96,7 +99,8 @@ const char* nf_last_error(void);
 /* ---- parameters -------------------------------------------------------- */
 /* Number of parameter pointers nf_pack_weights expects for `desc`, in this order:
  *   density MLP: init.weight, init.bias, layers[0].weight, layers[0].bias, ..., out.weight, out.bias
- *   refl MLP   : same order                                   (NF_KIND_PLAIN only)
+ *   refl MLP   : same order                                   (NF_KIND_PLAIN, NF_KIND_DYN)
+ *   deform MLP : same order                                   (NF_KIND_DYN only)
  *   hash tables: embs[0].weight ... embs[levels-1].weight      (NF_ENC_HASH only)
  *   fourier    : enc.basis [3, freqs]                          (NF_ENC_FOURIER only)
  *   beta       : VolSDF.scale (scalar)                         (NF_DENS_LAPLACE only)
@@ -119,13 +123,15 @@ int nf_pack_weights(const nf_model_desc* desc, const float* const* params_host, 
  *   ts             sample distances; ts_ray_stride == 0: one ts[T] shared by all rays
  *                  (the reference's layout); == T: per-ray ts[R,T] (coarse+fine pass)
  *   density_noise  nullable [R,T]; added to the raw density (nerf.py:347-348, already scaled)
+ *   ray_time       NF_KIND_DYN: time of every ray, [R] (the reference broadcasts times[B] over the view's pixels,
+ *                  nerf.py:1301); NULL otherwise
  *   alpha_out, weights_out  nullable [R,T] (ray-major; the reference's self.alpha/self.weights
  *                  are the [T,R] transposes)
  */
 int nf_render_forward(const nf_model_desc* desc, const void* packed,
                       const float* rays, int64_t n_rays,
                       const float* ts, int32_t T, int64_t ts_ray_stride,
-                      const float* density_noise,
+                      const float* density_noise, const float* ray_time,
                       float* rgb_out, float* alpha_out, float* weights_out,
                       int32_t precision, void* stream);
 

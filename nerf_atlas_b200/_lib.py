@@ -7,7 +7,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, os.environ.get("NF_LIB", "libnerf_b200.so"))
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 # enums of include/nerf_b200.h
 ACT = {"none": 0, "leaky_relu": 1, "sin": 2, "relu": 3}
 ENC = {"none": 0, "hash": 1, "fourier": 2}
@@ -15,7 +15,7 @@ DENSITY = {"softplus": 0, "relu": 1, "laplace": 2}
 FEAT = {"normal": 0, "thin": 1, "tanh": 2, "cyclic": 3, "upshifted": 4, "fat": 5, "leaky_relu": 6, "relu": 7,
         "sin": 8, "upshifted_softplus": 9, "upshifted_relu": 10}
 BG = {"black": 0, "white": 1}
-KIND = {"plain": 0, "tiny": 1}
+KIND = {"plain": 0, "tiny": 1, "dyn": 2}
 PRECISION = {"fp32": 0, "fp16": 1}
 
 class MlpDesc(C.Structure):
@@ -27,7 +27,7 @@ class ModelDesc(C.Structure):
               ("intermediate", C.c_int32), ("enc", C.c_int32), ("hash_levels", C.c_int32),
               ("hash_table_size", C.c_int32), ("hash_feat", C.c_int32), ("hash_primes", C.c_uint32 * 3),
               ("hash_res", C.c_float * 16), ("density_act", C.c_int32), ("feat_act", C.c_int32), ("bg", C.c_int32),
-              ("fourier_freqs", C.c_int32)]
+              ("fourier_freqs", C.c_int32), ("deform", MlpDesc)]
 
 EXPORTS = {
   "nf_version": (C.c_int, []),
@@ -36,7 +36,7 @@ EXPORTS = {
   "nf_packed_bytes": (C.c_int64, [C.POINTER(ModelDesc)]),
   "nf_pack_weights": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
   "nf_render_forward": (C.c_int, [C.POINTER(ModelDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int64,
-                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
   "nf_sample_points": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
   "nf_hash_encode": (C.c_int, [C.POINTER(ModelDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
   "nf_composite": (C.c_int, [C.POINTER(ModelDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int64,

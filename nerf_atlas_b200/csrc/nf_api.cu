@@ -92,20 +92,22 @@ int nf_pack_weights(const nf_model_desc* desc, const float* const* params, int32
 }
 
 int nf_render_forward(const nf_model_desc* desc, const void* packed, const float* rays, int64_t n_rays,
-                      const float* ts, int32_t T, int64_t ts_ray_stride, const float* density_noise,
+                      const float* ts, int32_t T, int64_t ts_ray_stride, const float* density_noise, const float* ray_time,
                       float* rgb_out, float* alpha_out, float* weights_out, int32_t precision, void* stream) {
   NfPlan p; if (int rc = plan_of(desc, &p)) return rc;
   if (n_rays < 0) return fail(NF_E_BADARG, "n_rays < 0");
   if (n_rays == 0) return 0;
   if (!packed || !rays || !ts || !rgb_out) return fail(NF_E_BADARG, "nf_render_forward: null pointer");
   if (int rc = check_ts(T, ts_ray_stride)) return rc;
+  if (p.kind == NF_KIND_DYN && !ray_time) return fail(NF_E_BADARG, "nf_render_forward: ray_time is required for NF_KIND_DYN");
   cudaError_t e;
   if (precision == NF_PREC_FP32)
-    e = nf_launch_render_fp32(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, rgb_out, alpha_out, weights_out, (cudaStream_t)stream);
+    e = nf_launch_render_fp32(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, ray_time, rgb_out, alpha_out, weights_out, (cudaStream_t)stream);
   else if (precision == NF_PREC_FP16_TC) {
     // default: the paired (cta_group::2) pipeline; NF_TC_PAIRED=0 selects the single-CTA pipeline (kept for A/B timing)
     const char* env = getenv("NF_TC_PAIRED");
     const bool paired = !(env && env[0] == '0') && nf_tc2_unsupported(p) == nullptr;
+    if (p.kind == NF_KIND_DYN) return fail(NF_E_UNSUPPORTED, "NF_KIND_DYN runs on the fp32 pipeline only in this build");
     e = paired ? nf_launch_render_tc2(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, rgb_out, alpha_out, weights_out, (cudaStream_t)stream)
                : nf_launch_render_tc(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, rgb_out, alpha_out, weights_out, (cudaStream_t)stream);
   }

@@ -42,7 +42,7 @@ struct NfPlan {
   int64_t scale_off;    // byte offset: fp32 beta (VolSDF.scale)
   int32_t fourier_freqs, pad3_;
   int64_t total_bytes;
-  NfMlpPlan mlp[2];
+  NfMlpPlan mlp[3];     // [0] density, [1] refl, [2] deformation (NF_KIND_DYN; executed first)
 };
 
 __host__ __device__ inline int nf_round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -51,9 +51,9 @@ __host__ __device__ inline int nf_round_up(int x, int m) { return (x + m - 1) / 
 static inline int nf_build_plan(const nf_model_desc* d, NfPlan* p, const char** why) {
   *why = "";
   if (!d || d->struct_bytes != (int32_t)sizeof(nf_model_desc)) { *why = "bad nf_model_desc (struct_bytes)"; return NF_E_BADARG; }
-  if (d->kind != NF_KIND_PLAIN && d->kind != NF_KIND_TINY) { *why = "unsupported model kind"; return NF_E_UNSUPPORTED; }
+  if (d->kind != NF_KIND_PLAIN && d->kind != NF_KIND_TINY && d->kind != NF_KIND_DYN) { *why = "unsupported model kind"; return NF_E_UNSUPPORTED; }
   *p = NfPlan{};
-  p->kind = d->kind; p->n_mlps = (d->kind == NF_KIND_PLAIN) ? 2 : 1;
+  p->kind = d->kind; p->n_mlps = d->kind == NF_KIND_DYN ? 3 : d->kind == NF_KIND_PLAIN ? 2 : 1;
   p->intermediate = d->intermediate; p->enc = d->enc;
   p->density_act = d->density_act; p->feat_act = d->feat_act; p->bg = d->bg;
   if (d->enc == NF_ENC_HASH) {
@@ -74,7 +74,7 @@ static inline int nf_build_plan(const nf_model_desc* d, NfPlan* p, const char** 
   if (d->enc == NF_ENC_FOURIER) p->fourier_off = take((int64_t)3 * d->fourier_freqs * sizeof(float));
   p->scale_off = take(sizeof(float));
   for (int m = 0; m < p->n_mlps; ++m) {
-    const nf_mlp_desc& md = m == 0 ? d->density : d->refl;
+    const nf_mlp_desc& md = m == 0 ? d->density : m == 1 ? d->refl : d->deform;
     NfMlpPlan& mp = p->mlp[m];
     if (md.hidden != NF_HIDDEN) { *why = "hidden_size must be 256"; return NF_E_UNSUPPORTED; }
     if (md.n_layers < 1 || md.n_layers + 2 > NF_MAX_LIN) { *why = "unsupported number of layers"; return NF_E_UNSUPPORTED; }
@@ -100,7 +100,8 @@ static inline int nf_build_plan(const nf_model_desc* d, NfPlan* p, const char** 
       L.w16h_off = take((int64_t)k_tc * L.n_pad * sizeof(__half));
     }
   }
-  if (d->kind == NF_KIND_PLAIN) {
+  if (d->kind == NF_KIND_DYN && (d->deform.in_dims != 4 || d->deform.out_dims != 4)) { *why = "dyn: deformation MLP must map 4 -> 4"; return NF_E_BADARG; }
+  if (d->kind == NF_KIND_PLAIN || d->kind == NF_KIND_DYN) {
     if (d->density.out_dims != 1 + d->intermediate) { *why = "density MLP out must be 1+intermediate"; return NF_E_BADARG; }
     if (d->refl.in_dims != 5 + d->intermediate || d->refl.out_dims != 3) { *why = "refl MLP must map 5+intermediate -> 3"; return NF_E_BADARG; }
     const int want = d->enc == NF_ENC_HASH ? 6 + d->hash_levels * 4 : d->enc == NF_ENC_FOURIER ? 3 + 2 * d->fourier_freqs : 3;
@@ -119,14 +120,14 @@ static inline int nf_build_plan(const nf_model_desc* d, NfPlan* p, const char** 
 //   refl x0          : reference [p(3), elaz(2), inter(I)]    -> [inter(I), p, elaz]
 //   density out      : reference [sigma, inter(I)]            -> [inter(I), sigma]
 __host__ __device__ inline int nf_x0_perm(const NfPlan& p, int m, int k_ref) {
-  if (p.kind == NF_KIND_PLAIN) {
+  if (p.kind == NF_KIND_PLAIN || p.kind == NF_KIND_DYN) {
     if (m == 0 && p.enc == NF_ENC_HASH) { const int nfe = p.hash_levels * 4; return k_ref < 6 ? nfe + k_ref : k_ref - 6; }
     if (m == 1) return k_ref < 5 ? p.intermediate + k_ref : k_ref - 5;
   }
   return k_ref;
 }
 __host__ __device__ inline int nf_out_perm(const NfPlan& p, int m, int n_ref) {
-  if (p.kind == NF_KIND_PLAIN && m == 0) return n_ref == 0 ? p.intermediate : n_ref - 1;
+  if ((p.kind == NF_KIND_PLAIN || p.kind == NF_KIND_DYN) && m == 0) return n_ref == 0 ? p.intermediate : n_ref - 1;
   return n_ref;
 }
 

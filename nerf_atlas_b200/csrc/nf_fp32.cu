@@ -85,7 +85,7 @@ struct RenderArgs {
   const uint8_t* packed;
   const float* rays; long long n_rays;
   const float* ts; int T; long long ts_stride;
-  const float* noise;
+  const float* noise; const float* ray_time;
   float* rgb_out; float* alpha_out; float* weights_out;
 };
 
@@ -99,20 +99,47 @@ k_render_fp32(const __grid_constant__ NfPlan plan, const RenderArgs a) {
   const int out_ch = 3;
   for (long long u = blockIdx.x; u < units; u += gridDim.x) {
     for (int sub = 0; sub < map.tpr; ++sub) {
-      // ---- stage 0: sample positions + encode -> X0 (reference nerf.py:50-55, neural_blocks.py:139-193)
+      // ---- stage 0: sample positions (reference nerf.py:50-55)
       {
-        const int row = tid % ROWS, part = tid / ROWS;  // 4 threads per sample, levels interleaved
-        long long ray; int t;
-        const bool ok = map.locate(u, sub, row, a.n_rays, ray, t);
-        float px = 0.f, py = 0.f, pz = 0.f;
-        if (ok) {
-          const float* r = a.rays + ray * 6;
-          const float tt = __ldg(a.ts + ray * a.ts_stride + t);
-          px = nf_pt(__ldg(r + 0), tt, __ldg(r + 3)); py = nf_pt(__ldg(r + 1), tt, __ldg(r + 4)); pz = nf_pt(__ldg(r + 2), tt, __ldg(r + 5));
-        }
+        const int row = tid % ROWS, part = tid / ROWS;
         if (part == 0) {
+          long long ray; int t;
+          const bool ok = map.locate(u, sub, row, a.n_rays, ray, t);
+          float px = 0.f, py = 0.f, pz = 0.f;
+          if (ok) {
+            const float* r = a.rays + ray * 6;
+            const float tt = __ldg(a.ts + ray * a.ts_stride + t);
+            px = nf_pt(__ldg(r + 0), tt, __ldg(r + 3)); py = nf_pt(__ldg(r + 1), tt, __ldg(r + 4)); pz = nf_pt(__ldg(r + 2), tt, __ldg(r + 5));
+          }
           s.ray[row] = ray; s.t[row] = t; s.valid[row] = ok;
           s.P[row] = px; s.P[ROWS + row] = py; s.P[2 * ROWS + row] = pz;
+        }
+      }
+      __syncthreads();
+      if (plan.kind == NF_KIND_DYN) {
+        // ---- stage 0b: deformation (reference nerf.py:1261-1266,1292-1303): delta_estim([p, t]) -> (dp[1], rigidity[3]);
+        //      p' = p + dp * sigmoid(rigidity / 2)
+        if (tid < ROWS) {
+          const int row = tid;
+          s.X0[0 * ROWS + row] = s.P[row]; s.X0[1 * ROWS + row] = s.P[ROWS + row]; s.X0[2 * ROWS + row] = s.P[2 * ROWS + row];
+          s.X0[3 * ROWS + row] = s.valid[row] ? __ldg(a.ray_time + s.ray[row]) : 0.f;
+        }
+        __syncthreads();
+        const int ob = mlp_fp32(plan.mlp[2], a.packed, s);
+        if (tid < ROWS) {
+          const float* O = s.H[ob]; const int row = tid;
+          const float dp = O[row];
+          s.P[row] += dp * nf_sigmoid(O[1 * ROWS + row] / 2.f);
+          s.P[ROWS + row] += dp * nf_sigmoid(O[2 * ROWS + row] / 2.f);
+          s.P[2 * ROWS + row] += dp * nf_sigmoid(O[3 * ROWS + row] / 2.f);
+        }
+        __syncthreads();
+      }
+      // ---- stage 0c: encode -> X0 (reference neural_blocks.py:139-193 / 36-55)
+      {
+        const int row = tid % ROWS, part = tid / ROWS;  // 4 threads per sample, levels / frequencies interleaved
+        const float px = s.P[row], py = s.P[ROWS + row], pz = s.P[2 * ROWS + row];
+        if (part == 0) {
           s.X0[0 * ROWS + row] = px; s.X0[1 * ROWS + row] = py; s.X0[2 * ROWS + row] = pz;
           if (plan.enc == NF_ENC_HASH) { s.X0[3 * ROWS + row] = px; s.X0[4 * ROWS + row] = py; s.X0[5 * ROWS + row] = pz; }
         }
@@ -139,7 +166,7 @@ k_render_fp32(const __grid_constant__ NfPlan plan, const RenderArgs a) {
       // ---- stage 1: density MLP
       int ob = mlp_fp32(plan.mlp[0], a.packed, s);
       const float* rgb_raw;
-      if (plan.kind == NF_KIND_PLAIN) {
+      if (plan.kind == NF_KIND_PLAIN || plan.kind == NF_KIND_DYN) {
         // ---- glue: sigma_raw, x0 of the View head = [pts, elaz(view), intermediate] (nerf.py:344-358, refl.py:205-207)
         const float* O = s.H[ob];
         if (tid < ROWS) {
@@ -391,7 +418,7 @@ cudaError_t nf_launch_pack_fp32(const float* W, const float* b, float* Wt, float
 }
 
 cudaError_t nf_launch_render_fp32(const NfPlan& plan, const void* packed, const float* rays, int64_t n_rays, const float* ts,
-                                  int T, int64_t ts_stride, const float* noise, float* rgb, float* alpha, float* weights,
+                                  int T, int64_t ts_stride, const float* noise, const float* ray_time, float* rgb, float* alpha, float* weights,
                                   cudaStream_t st) {
   static_assert(sizeof(Fp32Smem) <= 227 * 1024, "fp32 pipeline smem");
   cudaError_t e = cudaFuncSetAttribute(k_render_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Fp32Smem));
@@ -400,7 +427,7 @@ cudaError_t nf_launch_render_fp32(const NfPlan& plan, const void* packed, const 
   const long long units = map.units(n_rays);
   if (units == 0) return cudaSuccess;
   const int grid = (int)(units < num_sms() ? units : num_sms());
-  RenderArgs a{(const uint8_t*)packed, rays, n_rays, ts, T, ts_stride, noise, rgb, alpha, weights};
+  RenderArgs a{(const uint8_t*)packed, rays, n_rays, ts, T, ts_stride, noise, ray_time, rgb, alpha, weights};
   k_render_fp32<<<grid, THREADS, sizeof(Fp32Smem), st>>>(plan, a);
   return cudaGetLastError();
 }

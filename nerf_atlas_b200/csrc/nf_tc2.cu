@@ -520,6 +520,7 @@ void build_prog2(const NfPlan& plan, Tc2Prog* P) {
 
 // nullptr if the paired pipeline can run this model, else the reason.
 const char* nf_tc2_unsupported(const NfPlan& p) {
+  if (p.kind == NF_KIND_DYN) return "NF_KIND_DYN runs on the fp32 pipeline only in this build";
   int chunks = 0, nlin = 0;
   for (int m = 0; m < p.n_mlps; ++m) {
     nlin += p.mlp[m].n_lin;

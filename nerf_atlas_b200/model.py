@@ -81,6 +81,14 @@ def describe_volsdf(sdf_kind: str = "siren", intermediate: int = 64, sigmoid: st
   return d
 
 
+def describe_dyn(intermediate: int = 64, sigmoid: str = "upshifted", bg: str = "black") -> ModelDesc:
+  """DynamicNeRF with the direct deformation MLP over a canonical PlainNeRF (reference src/nerf.py:1209-1303)."""
+  d = describe_plain(intermediate, sigmoid, bg)
+  d.kind = _lib.KIND["dyn"]
+  d.deform = _mlp(4, 5, 4, "leaky_relu")
+  return d
+
+
 def describe_tiny(sigmoid: str = "upshifted", bg: str = "black") -> ModelDesc:
   """TinyNeRF (reference src/nerf.py:278-305), intended semantics."""
   d = ModelDesc()
@@ -150,7 +158,7 @@ class RenderEngine:
     if self.packed is None: raise RuntimeError("RenderEngine.pack(params) has not been called")
 
   def render(self, rays: torch.Tensor, ts: torch.Tensor, density_noise: Optional[torch.Tensor] = None,
-             want_weights: bool = True, precision: Optional[str] = None):
+             want_weights: bool = True, precision: Optional[str] = None, ray_time: Optional[torch.Tensor] = None):
     """rays[R,6], ts[T] (shared) or ts[R,T] (per ray) -> rgb[R,3], alpha[R,T]|None, weights[R,T]|None."""
     self._need_packed()
     _chk(rays, "rays"); _chk(ts, "ts")
@@ -162,12 +170,15 @@ class RenderEngine:
     if density_noise is not None:
       _chk(density_noise, "density_noise")
       if tuple(density_noise.shape) != (R, T): raise ValueError("density_noise must be [R,T]")
+    if ray_time is not None:
+      _chk(ray_time, "ray_time")
+      if tuple(ray_time.shape) != (R,): raise ValueError("ray_time must be [R]")
     rgb = torch.empty(R, 3, dtype=torch.float32, device=rays.device)
     alpha = torch.empty(R, T, dtype=torch.float32, device=rays.device) if want_weights else None
     weights = torch.empty(R, T, dtype=torch.float32, device=rays.device) if want_weights else None
     with torch.cuda.device(rays.device):
       rc = self.lib.nf_render_forward(C.byref(self.desc), _ptr(self.packed), _ptr(rays), R, _ptr(ts), T, stride,
-                                      _ptr(density_noise), _ptr(rgb), _ptr(alpha), _ptr(weights),
+                                      _ptr(density_noise), _ptr(ray_time), _ptr(rgb), _ptr(alpha), _ptr(weights),
                                       _lib.PRECISION[precision or self.precision], self._stream())
     _lib.check(rc, "nf_render_forward")
     return rgb, alpha, weights
@@ -227,7 +238,7 @@ class RenderEngine:
 
   def mlp_forward(self, which: int, x0: torch.Tensor, precision: Optional[str] = None) -> torch.Tensor:
     self._need_packed(); _chk(x0, "x0")
-    md = self.desc.density if which == 0 else self.desc.refl
+    md = (self.desc.density, self.desc.refl, self.desc.deform)[which]
     if x0.dim() != 2 or x0.shape[1] != md.in_dims: raise ValueError(f"x0 must be [N,{md.in_dims}]")
     out = torch.empty(x0.shape[0], md.out_dims, dtype=torch.float32, device=x0.device)
     with torch.cuda.device(x0.device):
@@ -494,6 +505,75 @@ class FusedVolSDF(FusedNeRF):
     if kind == "mlp": ps.append(net.enc.basis)
     ps.append(self.scale.reshape(1) if self.scale.dim() == 0 else self.scale)
     return ps
+
+
+class FusedDynamicNeRF(nn.Module):
+  """Drop-in for DynamicNeRF with the direct deformation MLP (reference src/nerf.py:1209-1303) over a canonical
+  FusedPlainNeRF: `model((rays[B,H,W,6], times[B])) -> rgb[B,H,W,3]`.  State-dict names follow the reference
+  (`delta_estim.*`, `canonical.*`).  The spline variant and `refl_latent > 0` are not built."""
+
+  def __init__(self, canonical: FusedPlainNeRF, spline: int = 0, refl_latent: int = 0):
+    super().__init__()
+    if spline or refl_latent: raise NotImplementedError("spline / refl_latent variants of DynamicNeRF")
+    self.canonical = canonical
+    self.delta_estim = SkipConnParams(4, 4, 5, init="xavier")
+    nn.init.zeros_(self.delta_estim.out.weight); nn.init.zeros_(self.delta_estim.out.bias)   # zero_last_layer(), nerf.py:1239
+    self._engine: Optional[RenderEngine] = None
+    self._engine_key = None
+
+  @classmethod
+  def from_reference(cls, ref, precision: str = "fp32") -> "FusedDynamicNeRF":
+    if getattr(ref, "spline", 0): raise NotImplementedError("spline DynamicNeRF")
+    self = cls.__new__(cls); nn.Module.__init__(self)
+    self.canonical = FusedPlainNeRF.from_reference(ref.canonical, precision=precision)
+    self.delta_estim = ref.delta_estim
+    self._engine = None; self._engine_key = None
+    return self
+
+  @property
+  def nerf(self): return self.canonical
+  @property
+  def refl(self): return self.canonical.refl
+  @property
+  def intermediate_size(self): return self.canonical.intermediate_size
+  def total_latent_size(self): return self.canonical.total_latent_size()
+  def set_refl(self, refl): self.canonical.set_refl(refl)
+  def set_bg(self, bg): self.canonical.set_bg(bg)
+  def __getstate__(self):
+    st = self.__dict__.copy(); st["_engine"] = None; st["_engine_key"] = None
+    return st
+
+  def engine(self) -> RenderEngine:
+    c = self.canonical
+    key = (_sigmoid_name(c.refl.act), c.bg, c.precision)
+    if self._engine is None or self._engine_key != key:
+      self._engine = RenderEngine(describe_dyn(c.intermediate_size, key[0], c.bg), c.precision); self._engine_key = key
+    return self._engine
+
+  def _param_list(self) -> List[torch.Tensor]:
+    c = self.canonical
+    ps: List[torch.Tensor] = []
+    for mlp in (c.first, c.refl.mlp, self.delta_estim):
+      for lin in _linears_of(mlp): ps += [lin.weight, lin.bias]
+    ps += [e.weight for e in c.first.enc.embs]
+    return ps
+
+  def forward(self, rays_t):
+    rays, t = rays_t
+    c = self.canonical
+    if not rays.is_cuda: raise RuntimeError("FusedDynamicNeRF.forward needs CUDA rays: the fused path has no CPU fallback")
+    if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
+      raise NotImplementedError("backward of the fused pipeline is not built yet (SURVEY.md f-1)")
+    B = rays.shape[:-1]
+    flat = rays.reshape(-1, 6).to(torch.float32).contiguous()
+    ts = torch.linspace(c.t_near, c.t_far, steps=c.steps, device=rays.device, dtype=torch.float32)
+    ray_time = t.to(torch.float32).reshape(-1, 1, 1).expand(B).reshape(-1).contiguous()        # nerf.py:1301
+    eng = self.engine(); eng.pack(self._param_list())
+    rgb, alpha, weights = eng.render(flat, ts, None, want_weights=c.keep_weights, ray_time=ray_time)
+    c.ts = self.ts = ts
+    if c.keep_weights:
+      c.alpha = alpha.reshape(*B, c.steps).movedim(-1, 0); c.weights = weights.reshape(*B, c.steps).movedim(-1, 0)
+    return rgb.reshape(*B, 3)
 
 
 class FusedTinyNeRF(FusedNeRF):

@@ -18,7 +18,7 @@ arithmetic library; no ``nn.Module`` from the reference is used), of
   * PlainNeRF.forward / from_pts      reference src/nerf.py:326-361
   * TinyNeRF.forward (intended)       reference src/nerf.py:292-305
   * VolSDF volume branch              reference src/nerf.py:981-1013, src/utils.py:50-58, src/sdf.py:109-112,250-287
-  * DynamicNeRF direct / spline       reference src/nerf.py:1173-1206,1261-1303
+  * DynamicNeRF, direct deformation   reference src/nerf.py:1209-1303 (spline variant not restated)
   * sample_pdf (restated, dead code)  reference src/nerf.py:1745-1779
 
 Parity pin: the reference has no tests or golden vectors of its own (SURVEY.md
@@ -372,6 +372,27 @@ def volsdf_forward(params: Params, rays: Tensor, ts: Tensor, *, sdf_kind: str = 
 
 
 # ----------------------------------------------------------------------------
+# a-12  DynamicNeRF, direct deformation MLP  (reference src/nerf.py:1209-1303)
+# ----------------------------------------------------------------------------
+def dnerf_direct_forward(params: Params, rays: Tensor, times: Tensor, ts: Tensor, *, sigmoid: str = "upshifted",
+                         bg: str = "black", quant: Optional[torch.dtype] = None) -> Dict[str, Tensor]:
+  """rays[B,H,W,6], times[B].  direct_predict (nerf.py:1261-1266) splits the MLP output [1,3] as (dp, rigidity) --
+  the NAMES are swapped w.r.t. the comment at nerf.py:1231, so `dp` is one channel broadcast over xyz and the rigidity
+  mask has three -- and reads `self.dp`, which the reference never sets (the golden run patches that in).
+  Parameter names: `delta_estim.*`, `canonical.first.*`, `canonical.refl.mlp.*`."""
+  pts, r_o, r_d = compute_pts(rays, ts)
+  t = times[None, :, None, None, None].expand(*pts.shape[:-1], 1)
+  xt = torch.cat([pts, t], dim=-1)
+  o = skip_mlp(xt.reshape(-1, 4), params, "delta_estim", "leaky_relu", quant=quant).reshape(pts.shape[:-1] + (4,))
+  dp, rigidity = o[..., :1], o[..., 1:4]
+  rigid_dp = dp * (rigidity / 2).sigmoid()
+  canon = {k[len("canonical."):]: v for k, v in params.items() if k.startswith("canonical.")}
+  res = plain_from_pts(canon, pts + rigid_dp, ts, r_o, r_d, sigmoid=sigmoid, bg=bg, quant=quant)
+  res["rigid_dp"] = rigid_dp; res["pts"] = pts
+  return res
+
+
+# ----------------------------------------------------------------------------
 # a-7  inverse-CDF resampling, restated from the dead code at nerf.py:1745-1779
 # ----------------------------------------------------------------------------
 def sample_pdf(bins: Tensor, weights: Tensor, u: Tensor) -> Tensor:
@@ -466,6 +487,22 @@ def make_volsdf_params(seed: int = 7, sdf_kind: str = "siren", intermediate: int
   siren("sdf.refl.mlp.layers.0", 256, 256 + 5 + I)
   for i in (1, 2, 3): siren(f"sdf.refl.mlp.layers.{i}", 256, 256)
   siren("sdf.refl.mlp.out", 3, 256)
+  return P
+
+
+def make_dnerf_params(seed: int = 9, intermediate: int = 64, sigma_gain: float = 20.0, out_scale: float = 0.3) -> Params:
+  """DynamicNeRF(direct) over PlainNeRF+View.  delta_estim: xavier-uniform, zero biases (nerf.py:1234-1237); its last
+  layer is zero-initialised in the reference (nerf.py:1239) -- here it gets small random values so that the deformation
+  is exercised."""
+  g = np.random.default_rng(seed)
+  P: Params = {"canonical." + k: v for k, v in make_plain_params(seed + 1, intermediate, sigma_gain).items()}
+  def xav(name, o, i, scale=1.0):
+    a = math.sqrt(6.0 / (i + o)) * scale
+    P[f"{name}.weight"] = torch.from_numpy(g.uniform(-a, a, size=(o, i)).astype(np.float32)); P[f"{name}.bias"] = torch.zeros(o)
+  xav("delta_estim.init", 256, 4)
+  for i in range(5): xav(f"delta_estim.layers.{i}", 256, 260 if (i % 3 == 0 and i != 4) else 256)
+  xav("delta_estim.out", 4, 256, out_scale)
+  P["delta_estim.out.bias"] = torch.from_numpy(g.uniform(-0.2, 0.2, size=(4,)).astype(np.float32))
   return P
 
 

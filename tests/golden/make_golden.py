@@ -83,6 +83,31 @@ def case_volsdf(name, seed, sdf_kind, B, H, W, T, top=0, left=0):
   np.savez_compressed(os.path.join(HERE, name + ".npz"), **fx)
   print(name, "out", out.shape, "mean", float(out.mean()), "acc-before-last", float(model.weights[:-1].sum(0).mean()))
 
+def case_dnerf(name, seed, B, H, W, T, top=0, left=0):
+  runner, nerf, refl, utils, cameras = ref_shim.load()
+  params = O.make_dnerf_params(seed, 64)
+  rays = O.make_rays(B, H, W, size=800, seed=seed, crop_top=top, crop_left=left)
+  times = torch.linspace(0.1, 0.9, B)
+  canonical, args = ref_shim.build_model("plain", T)
+  model = nerf.DynamicNeRF(canonical=canonical, spline=0)
+  # shim (5) of SURVEY.md 8c: direct_predict reads self.dp, which the reference never sets (nerf.py:1265)
+  def direct_predict(self, x, t):
+    xt = torch.cat([x, t], dim=-1)
+    dp, rigidity, enc_rigidity, enc = self.delta_estim(xt).split(self.mlp_out_layout, dim=-1)
+    self.dp = dp
+    self.rigidity = (rigidity / 2).sigmoid()
+    self.rigid_dp = self.dp * self.rigidity
+    return self.rigid_dp, enc * enc_rigidity.sigmoid()
+  model.time_estim = direct_predict.__get__(model)
+  model.load_state_dict({k: v.clone() for k, v in params.items()}, strict=True)
+  model.eval()
+  with torch.no_grad(): out = model((rays, times))
+  fx = dict(kind="dnerf", seed=seed, B=B, H=H, W=W, T=T, top=top, left=left, near=float(args.near), far=float(args.far),
+            sigmoid=args.sigmoid_kind, bg=args.bg, times=times.numpy(), ts=model.ts.numpy(), out=out.numpy(),
+            alpha=canonical.alpha.numpy(), weights=canonical.weights.numpy(), rigid_dp=model.rigid_dp.numpy())
+  np.savez_compressed(os.path.join(HERE, name + ".npz"), **fx)
+  print(name, "out", out.shape, "mean", float(out.mean()), "max|rigid_dp|", float(model.rigid_dp.abs().max()))
+
 def r_o_pts(rays, ts):
   r_o, r_d = rays.split([3, 3], dim=-1)
   pts = r_o.unsqueeze(0) + torch.tensordot(ts, r_d, dims=0)
@@ -119,4 +144,5 @@ if __name__ == "__main__":
   case_plain("plain_t128", seed=1337, B=1, H=8, W=8, T=128, sigma_gain=20.0, top=396, left=396, stages=False)
   case_volsdf("volsdf_siren_t32", seed=31, sdf_kind="siren", B=1, H=4, W=5, T=32, top=398, left=397)
   case_volsdf("volsdf_mlp_t32", seed=32, sdf_kind="mlp", B=1, H=3, W=4, T=32, top=398, left=397)
+  case_dnerf("dnerf_direct_t64", seed=51, B=2, H=3, W=4, T=64, top=398, left=397)
   case_plain("plain_t64_train", seed=21, B=1, H=4, W=4, T=64, sigma_gain=20.0, train=True, top=300, left=420, stages=False)

@@ -201,11 +201,11 @@ def test_c_abi_error_codes(eng):
   l = _lib.lib()
   rays = torch.zeros(4, 6, device=DEV); ts = torch.linspace(2, 6, 8, device=DEV); rgb = torch.zeros(4, 3, device=DEV)
   v = lambda t: C.c_void_p(t.data_ptr())
-  rc = l.nf_render_forward(C.byref(eng.desc), v(eng.packed), v(rays), 4, v(ts), 8, 5, None, v(rgb), None, None, 1, None)
+  rc = l.nf_render_forward(C.byref(eng.desc), v(eng.packed), v(rays), 4, v(ts), 8, 5, None, None, v(rgb), None, None, 1, None)
   assert rc == -1 and b"ts_ray_stride" in l.nf_last_error()
-  rc = l.nf_render_forward(C.byref(eng.desc), v(eng.packed), None, 4, v(ts), 8, 0, None, v(rgb), None, None, 1, None)
+  rc = l.nf_render_forward(C.byref(eng.desc), v(eng.packed), None, 4, v(ts), 8, 0, None, None, v(rgb), None, None, 1, None)
   assert rc == -1
-  rc = l.nf_render_forward(C.byref(eng.desc), v(eng.packed), v(rays), 4, v(ts), 8, 0, None, v(rgb), None, None, 7, None)
+  rc = l.nf_render_forward(C.byref(eng.desc), v(eng.packed), v(rays), 4, v(ts), 8, 0, None, None, v(rgb), None, None, 7, None)
   assert rc == -1 and b"precision" in l.nf_last_error()
   with pytest.raises(RuntimeError): eng.render(rays.cpu(), ts)
 
@@ -290,3 +290,31 @@ def test_fused_volsdf_module_surface():
   with torch.no_grad(): ref = O.volsdf_forward(P, rays.cpu(), m.ts.cpu(), sdf_kind="siren")
   assert out.shape == (1, 4, 5, 3) and m.weights.shape == (32, 1, 4, 5)
   assert np.abs(out.cpu().numpy() - ref["out"].numpy()).max() <= 5e-5
+
+# ---------------------------------------------------------------- D-NeRF, direct deformation MLP (config 5)
+def test_dnerf_direct_matches_reference_golden():
+  import nerf_atlas_b200 as N
+  fx = load_golden("dnerf_direct_t64")
+  P = O.make_dnerf_params(int(fx["seed"]), 64)
+  rays = O.make_rays(int(fx["B"]), int(fx["H"]), int(fx["W"]), 800, int(fx["seed"]), int(fx["top"]), int(fx["left"]))
+  canon = N.FusedPlainNeRF(steps=int(fx["T"]), t_near=float(fx["near"]), t_far=float(fx["far"]), intermediate_size=64,
+                           sigmoid_kind=str(fx["sigmoid"]), bg=str(fx["bg"]), precision="fp32")
+  m = N.FusedDynamicNeRF(canon)
+  m.load_state_dict(P, strict=True)                      # reference names: delta_estim.*, canonical.*
+  m = m.to(DEV).eval()
+  with torch.no_grad(): out = m((rays.to(DEV), torch.from_numpy(fx["times"]).to(DEV)))
+  assert out.shape == fx["out"].shape
+  assert np.abs(out.cpu().numpy() - fx["out"]).max() <= 5e-5, np.abs(out.cpu().numpy() - fx["out"]).max()
+  assert np.abs(m.nerf.weights.cpu().numpy() - fx["weights"]).max() <= 2e-4
+  assert m.nerf.ts.shape == (int(fx["T"]),)
+  # the deformation MLP alone, both precisions, through nf_mlp_forward (which = 2)
+  g = torch.Generator().manual_seed(1)
+  xt = torch.cat([torch.randn(500, 3, generator=g) * 2, torch.rand(500, 1, generator=g)], dim=1)
+  ref = O.skip_mlp(xt, P, "delta_estim", "leaky_relu")
+  eng = m.engine()
+  o32 = eng.mlp_forward(2, xt.to(DEV), precision="fp32").cpu()
+  o16 = eng.mlp_forward(2, xt.to(DEV), precision="fp16").cpu()
+  assert float((o32 - ref).abs().max()) <= 1e-4 and float((o16 - ref).abs().max()) <= 2e-2
+  # the tensor pipeline does not take this kind yet: loud refusal, no fallback
+  canon.precision = "fp16"
+  with pytest.raises(RuntimeError): m((rays.to(DEV), torch.from_numpy(fx["times"]).to(DEV)))

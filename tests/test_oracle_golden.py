@@ -59,6 +59,16 @@ def test_volsdf_oracle_matches_reference_bit_exact(golden_dir, name):
   for k in ("out", "alpha", "weights"):
     assert np.array_equal(res[k].numpy(), fx[k]), f"{name}: {k} differs from the reference run"
 
+def test_dnerf_direct_oracle_matches_reference_bit_exact(golden_dir):
+  fx = load(golden_dir, "dnerf_direct_t64")
+  params = O.make_dnerf_params(int(fx["seed"]), 64)
+  rays = O.make_rays(int(fx["B"]), int(fx["H"]), int(fx["W"]), 800, int(fx["seed"]), int(fx["top"]), int(fx["left"]))
+  ts = O.compute_ts(float(fx["near"]), float(fx["far"]), int(fx["T"]))
+  with torch.no_grad():
+    res = O.dnerf_direct_forward(params, rays, torch.from_numpy(fx["times"]), ts, sigmoid=str(fx["sigmoid"]), bg=str(fx["bg"]))
+  for k in ("out", "alpha", "weights", "rigid_dp"):
+    assert np.array_equal(res[k].numpy(), fx[k]), f"dnerf: {k} differs from the reference run"
+
 def test_hash_resolutions_decrease():
   # operator-precedence quirk of neural_blocks.py:126-128: scale < 1, resolutions 16 -> 6.28
   r = O.hash_resolutions()
