@@ -74,6 +74,25 @@ def cpu_port_rays_per_s(steps, warmup, tile=CPU_TILE):
   return tile * tile / dt, cores, dt, f"{steps} steps x ({tile}x{tile} crop of the 800x800 view) x {T} samples/ray, fp32, torch CPU, {cores} threads"
 
 
+def torch_eager_gpu_rays_per_s(dev, tile=200, reps=3):
+  """Informational: the reference's algorithm as eager PyTorch fp32 ops ON THE GPU (the oracle port moved to the
+  device; TF32 off = PyTorch default), tiled like runner.render_test_set (reference runner.py:881-890).  This is the
+  denominator of the north-star's >=10x target; the unmodified reference cannot travel to the GPU box."""
+  import torch
+  from oracle import nerf_oracle as O
+  P = {k: v.to(dev) for k, v in O.make_plain_params(1337, 64, 1.0).items()}
+  ts = torch.linspace(2, 6, T, device=dev)
+  rays = O.make_rays(1, tile, tile, size=SIZE, seed=0, crop_top=300, crop_left=300).to(dev)
+  with torch.no_grad():
+    O.plain_forward(P, rays, ts); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): O.plain_forward(P, rays, ts)
+    e1.record(); torch.cuda.synchronize()
+  ms = e0.elapsed_time(e1) / reps
+  return tile * tile / (ms * 1e-3), f"{tile}x{tile}-ray tiles x {T} samples, eager fp32 torch ops on the GPU (oracle port), TF32 off, peak mem {torch.cuda.max_memory_allocated(dev) / 2**30:.1f} GiB"
+
+
 def run_reference(args):
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0: return
@@ -182,6 +201,12 @@ def run_ours(args):
                    "traffic": traffic, "peak_source": peak_src,
                    "algorithmic": f"{FLOP_PER_SAMPLE} FLOP/sample x {RAYS_PER_FRAME * T} samples per launch"},
     }
+    if world == 1 and args.torch_eager_gpu:
+      try:
+        v, how = torch_eager_gpu_rays_per_s(dev)
+        line["torch_eager_gpu"] = {"value": v, "unit": "rays/s", "sample": how, "note": "informational: reference algorithm as eager PyTorch on this GPU"}
+      except Exception as ex:  # e.g. out of memory at this tile size
+        line["torch_eager_gpu"] = {"error": str(ex)[:200]}
     if cpu_v is not None:
       line["cpu_baseline"] = {"value": cpu_v, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample}
     print(json.dumps(line), flush=True)
@@ -195,6 +220,7 @@ def main():
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--torch-eager-gpu", action="store_true", help="also time the reference algorithm as eager PyTorch on the GPU (informational)")
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
   if args.impl == "reference": run_reference(args)

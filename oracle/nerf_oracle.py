@@ -141,10 +141,10 @@ def hash_indices(x: Tensor, level: int) -> Tensor:
   N_l = float(HASH_LOW * (HASH_SCALE ** level))
   v_l = x * N_l
   l = v_l.floor().long()
-  primes = torch.tensor(HASH_PRIMES, dtype=torch.int64)
+  primes = torch.tensor(HASH_PRIMES, dtype=torch.int64, device=x.device)
   out = []
   for (bx, by, bz) in HASH_CORNERS:
-    c = l + torch.tensor([bx, by, bz], dtype=torch.int64)
+    c = l + torch.tensor([bx, by, bz], dtype=torch.int64, device=x.device)
     v = c * primes
     h = v[..., 0].bitwise_xor(v[..., 1]).bitwise_xor(v[..., 2])
     out.append(h % HASH_TABLE)
