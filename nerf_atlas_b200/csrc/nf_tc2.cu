@@ -78,27 +78,6 @@ struct Tc2Args {
 #define NF_TRACE2(role, tag) do { } while (0)
 #endif
 
-// ---- cluster helpers --------------------------------------------------------------------------------
-// shared::cluster address of the same smem object in the pair's leader (rank 0): bit 24 of the window address is the rank
-__device__ __forceinline__ uint32_t leader_addr(uint32_t a) { return a & 0xFEFFFFFFu; }
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// After fence.proxy.async the payload (this CTA's smem, read by this SM's tensor core through the async proxy) is already
-// ordered; the cross-CTA arrive then only has to be delivered, not to release memory at cluster scope.
-__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
-__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
-               ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
-}
-__device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"((uint16_t)3) : "memory");
-}
-
 // ---- epilogue of a hidden Linear: H <- fp16(act(acc + bias)) ----------------------------------------------
 // Bias of this warp's first 16 columns, fetched BEFORE the acc_full wait (it does not depend on the accumulator): with a
 // 227 KB shared-memory carve-out the L1 is nearly gone, so every bias load is a ~300-cycle L2 hit that must be hidden.

@@ -1,0 +1,554 @@
+// nf_tc3.cu -- the STAGGERED form of the paired (cta_group::2) tensor-core render pipeline.
+//
+// Same data path as nf_tc2.cu (CTA pair, two 128-sample tiles -- "slots" -- in flight per CTA, M = 256 MMAs issued by one
+// thread of the leader, fp16 operands in the UMMA canonical no-swizzle K-major layout, 3-stage bulk-copy weight ring, the
+// epilogue warps write the next layer's A operand in place).  What changes is the schedule (profiles/r01_trace_paired_*):
+//
+//  * In nf_tc2 both slots walk the Linears in lockstep, so at every tile boundary BOTH slots sit in "composite the old tile,
+//    hash-encode the new one" while the tensor pipe has nothing to do: 22 % of a round.  Here slot 1 runs half a round
+//    (n_lin / 2 Linears) behind slot 0: while one slot is at its tile boundary the other is in the middle of its MLPs and
+//    keeps the tensor pipe fed, and the LeakyReLU (density MLP) and sin (View head) epilogues alternate instead of bunching.
+//  * The tile boundary itself is one phase: the four cq == 0 warps composite the finished tile while the other twelve
+//    already gather the next tile's hash features.
+//  * Biases come from shared memory (per slot, double-buffered, fetched one phase ahead) instead of L2: with a 227 KB
+//    carve-out there is no L1 left, and the ~300-700 cycle bias loads were the epilogue's largest stall (stall_long_sb).
+//  * No per-row bookkeeping in shared memory: (ray, t) of a row is recomputed from the tile index.
+//
+// A slot's life is a cycle of n = n_lin phases; phase j >= 1 = epilogue of Linear j-1, phase 0 = composite of the previous
+// tile (result of Linear n-1) + encode of the next one.  After phase j the issuer runs Linear j for that slot.
+//
+// Warp roles as in nf_tc2.cu: 0-15 encode/epilogue (TMEM lane quarter q = warp % 4, column quarter cq = warp / 4), 16/18/19
+// weight producers (one ring stage each), 17 the MMA issuer (leader CTA only).
+#include <cstdio>
+#include <cstdlib>
+#include <cstddef>
+#include "nf_common.cuh"
+#include "nf_kernels.h"
+#include "nf_tc_ptx.cuh"
+
+namespace {
+using namespace nf_ptx;
+
+constexpr int X0K = 80;
+constexpr int RING_BYTES = 48 * 1024;                       // weight ring per CTA: NST stages of SPCT K-steps (4 KB each at N = 256)
+constexpr int EPI_THREADS = 512;
+constexpr int MAX_LIN3 = 16;
+constexpr int MAX_STAGES3 = 6;
+
+struct Tc3Smem {
+  uint8_t H[2][ROWS * 256 * 2];
+  uint8_t X0[2][ROWS * X0K * 2];
+  uint8_t W[RING_BYTES];
+  float bias[2][2][256];                                     // [slot][step parity][column]
+  float sig[2][ROWS];
+  float warp_agg[2][4]; int warp_cont[2][4]; float warp_sum[2][4][4]; float carry[2][8];
+  unsigned long long w_land[MAX_STAGES3], w_empty[MAX_STAGES3], w_ready[MAX_STAGES3], acc_full[2], a_ready[2];
+  uint32_t tmem_base; int pad_;
+};
+static_assert(sizeof(Tc3Smem) <= 227 * 1024, "staggered tensor pipeline smem");
+
+// Host-built program (kernel parameter => uniform constant loads in the issuing thread).  One record per Linear:
+// MMA shape/steps (issuer), this Linear's weight image (producers), (mlp, layer) (epilogue).
+struct __align__(16) Tc3Lin {
+  uint32_t k0_steps, h_steps, idesc, bstep4;
+  uint32_t bhi, mj, w_off, half_bytes;       // mj = m * 16 + j; w_off = byte offset of rank 0's half image, half_bytes = its size
+  uint32_t step_bytes, pad0_, pad1_, pad2_;  // bytes of one K-step (16 K-columns) of a half image
+};
+struct __align__(16) Tc3Prog { int32_t n_lin, lag, pad0_, pad1_; Tc3Lin lin[MAX_LIN3]; };
+
+struct Tc3Args {
+  const uint8_t* packed;
+  const float* rays; long long n_rays;
+  const float* ts; int T; long long ts_stride;
+  const float* noise;
+  float* rgb_out; float* alpha_out; float* weights_out;
+  int debug;          // NF_TC_DEBUG (timing experiments): 256 = poll acc_full with backoff, 512 = try_wait with a short suspend hint
+};
+
+// acc_full wait of the 16 epilogue warps.  Default: hardware-suspended try_wait (no issue slots burnt).
+__device__ __forceinline__ void wait_acc(uint32_t bar, uint32_t parity, int debug) {
+  if (debug & 256) { mbar_wait_backoff(bar, parity); return; }
+  if (debug & 512) {
+    uint32_t spins = 0, ok = 0;
+    while (true) {
+      asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
+                   : "=r"(ok) : "r"(bar), "r"(parity), "r"(64u) : "memory");
+      if (ok) break;
+      if (++spins > (1u << 24)) mbar_timeout(bar);
+    }
+    return;
+  }
+  mbar_wait_suspend(bar, parity);
+}
+
+// ---- epilogue of a hidden Linear: H <- fp16(act(acc + bias)), bias from shared memory ---------------------
+template <int ACT>
+__device__ __forceinline__ void epi_hidden3(uint8_t* __restrict__ H, uint32_t t_acc, const float* __restrict__ bias_s, int cq, int row) {
+  // this warp's 64-column quarter = 4 units of 16 columns; unit u+1's TMEM load is in flight while unit u is converted
+  uint32_t v[2][16];
+  tmem_ld16(t_acc + cq * 64, v[0]);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int col = cq * 64 + u * 16;
+    tmem_ld_wait();
+    reg_fence16(v[u & 1]);
+    if (u < 3) tmem_ld16(t_acc + col + 16, v[(u + 1) & 1]);
+    const float4* b4 = reinterpret_cast<const float4*>(bias_s + col);
+    uint32_t o[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 b = b4[i];                                 // same address in every lane: one broadcast wavefront
+      o[2 * i]     = act_pack_t<ACT>(__uint_as_float(v[u & 1][4 * i]) + b.x, __uint_as_float(v[u & 1][4 * i + 1]) + b.y);
+      o[2 * i + 1] = act_pack_t<ACT>(__uint_as_float(v[u & 1][4 * i + 2]) + b.z, __uint_as_float(v[u & 1][4 * i + 3]) + b.w);
+    }
+    uint8_t* dst = H + (col >> 3) * KG_BYTES + row * 16;
+    st_v4(dst, o[0], o[1], o[2], o[3]); st_v4(dst + KG_BYTES, o[4], o[5], o[6], o[7]);
+  }
+}
+
+// x0 raw -> act(x0), in place (the `init` Linear consumed the raw form; the skip Linear wants the activated one)
+__device__ __forceinline__ void x0_activate3(uint8_t* X0, int k0_pad, int act, int g_tid) {
+  const int n16 = (k0_pad >> 3) * ROWS;             // 16-byte groups
+  for (int i = g_tid; i < n16; i += EPI_THREADS) {
+    uint4 q = *reinterpret_cast<uint4*>(X0 + i * 16);
+    uint32_t* w = reinterpret_cast<uint32_t*>(&q);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+      w[k] = pack_h2(tc_act(f.x, act), tc_act(f.y, act));
+    }
+    *reinterpret_cast<uint4*>(X0 + i * 16) = q;
+  }
+}
+
+// work unit of (pass, slot) for this CTA, and the sub-tile within a ray (T > 128)
+__device__ __forceinline__ void unit_of(int pass, int slot, int tpr, long long& u, int& sub) {
+  const int trip = tpr == 1 ? pass : pass / tpr;
+  sub = pass - trip * tpr;
+  u = ((long long)trip * gridDim.x + blockIdx.x) * 2 + slot;
+}
+
+// ---- composite of one tile by the 4 cq == 0 warps (thread = row); reference nerf.py:60-80 ----
+__device__ __forceinline__ void composite_tile3(Tc3Smem& s, int slot, const NfPlan& plan, const Tc3Args& a, const NfTileMap& map,
+                                                long long u, int sub, int row, int lane, int q, float cr, float cg, float cb) {
+  long long ray; int t;
+  const bool valid = map.locate(u, sub, row, a.n_rays, ray, t);
+  if (!valid) t = 0;
+  float al = 0.f;
+  if (valid) {
+    float sr = s.sig[slot][row];
+    if (a.noise) sr += __ldg(a.noise + ray * a.T + t);
+    const float* rr = a.rays + ray * 6;
+    const float dx = __ldg(rr + 3), dy = __ldg(rr + 4), dz = __ldg(rr + 5);
+    const float beta = plan.density_act == NF_DENS_LAPLACE ? __ldg(reinterpret_cast<const float*>(a.packed + plan.scale_off)) : 1.f;
+    al = nf_alpha(sr, nf_delta(a.ts + ray * a.ts_stride, t, a.T, sqrtf(dx * dx + dy * dy + dz * dz)), plan.density_act, beta);
+  }
+  float incl = valid ? (1.f - al) + 1e-10f : 1.f;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const float o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d && t >= d) incl *= o;
+  }
+  float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+  if (lane == 0 || t == 0) excl = 1.f;
+  if (lane == 31) { s.warp_agg[slot][q] = incl; s.warp_cont[slot][q] = t > 31; }
+  named_bar(3 + slot, 128);
+  float c = 1.f; bool open = true;
+  for (int v = q - 1; v >= 0 && open; --v) { c *= s.warp_agg[slot][v]; open = s.warp_cont[slot][v] != 0; }
+  if (open && sub > 0) c *= s.carry[slot][0];
+  const float trans = excl * (t > lane ? c : 1.f);
+  const float w = al * trans;
+  if (valid) {
+    if (a.alpha_out) a.alpha_out[ray * a.T + t] = al;
+    if (a.weights_out) a.weights_out[ray * a.T + t] = w;
+  }
+  const float wr = w * cr, wg = w * cg, wb = w * cb, wl = (valid && t < a.T - 1) ? w : 0.f;
+  const int row_thread = q * 32 + lane;
+  float* carry = s.carry[slot];
+  float* wrgb = reinterpret_cast<float*>(s.H[slot]);          // H[slot] is dead between the last Linear's MMA and the next tile
+  const bool fast = (a.T & 31) == 0;
+  if (fast) {
+    float x0 = wr, x1 = wg, x2 = wb, x3 = wl;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      x0 += __shfl_xor_sync(0xffffffffu, x0, d); x1 += __shfl_xor_sync(0xffffffffu, x1, d);
+      x2 += __shfl_xor_sync(0xffffffffu, x2, d); x3 += __shfl_xor_sync(0xffffffffu, x3, d);
+    }
+    if (lane == 0) { float* ws = s.warp_sum[slot][q]; ws[0] = x0; ws[1] = x1; ws[2] = x2; ws[3] = x3; }
+  } else {
+    float* wq = wrgb + row_thread * 4;
+    wq[0] = wr; wq[1] = wg; wq[2] = wb; wq[3] = wl;
+  }
+  named_bar(3 + slot, 128);
+  const int nseg = a.T <= ROWS ? map.rpt : 1;
+  const int row0 = a.T <= ROWS ? row_thread * a.T : 0;
+  if (row_thread < nseg) {
+    long long r; int t0;
+    if (map.locate(u, sub, row0, a.n_rays, r, t0)) {
+      float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+      if (sub > 0) { o0 = carry[1]; o1 = carry[2]; o2 = carry[3]; o3 = carry[4]; }
+      if (fast) {
+        const int wpr = a.T <= ROWS ? a.T / 32 : 4;
+        for (int v = 0; v < wpr; ++v) { const float* ws = s.warp_sum[slot][row_thread * wpr + v]; o0 += ws[0]; o1 += ws[1]; o2 += ws[2]; o3 += ws[3]; }
+      } else {
+        const int nrow = a.T <= ROWS ? a.T : min(ROWS, a.T - sub * ROWS);
+        for (int i = 0; i < nrow; ++i) { const float* x = wrgb + (row0 + i) * 4; o0 += x[0]; o1 += x[1]; o2 += x[2]; o3 += x[3]; }
+      }
+      if (sub == map.tpr - 1) {
+        const float skyv = plan.bg == NF_BG_WHITE ? 1.f - o3 : 0.f;
+        a.rgb_out[r * 3 + 0] = o0 + skyv; a.rgb_out[r * 3 + 1] = o1 + skyv; a.rgb_out[r * 3 + 2] = o2 + skyv;
+      } else {
+        carry[1] = o0; carry[2] = o1; carry[3] = o2; carry[4] = o3;
+        carry[0] = (sub > 0 ? carry[0] : 1.f) * s.warp_agg[slot][0] * s.warp_agg[slot][1] * s.warp_agg[slot][2] * s.warp_agg[slot][3];
+      }
+    }
+  }
+}
+
+// =====================================================================================================
+// NST ring stages of SPCT K-steps each (NST * SPCT * 4 KB = 48 KB).  Warps 0-15 encode/epilogue, 16..16+NST-1 weight
+// producers (one stage each; warp 16 also owns the TMEM allocation), warp 16+NST the MMA issuer (highest warp id).
+template <int NST, int SPCT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EPI_THREADS + 32 * (NST + 1), 1)
+k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Prog prog, const Tc3Args a) {
+  static_assert(NST * SPCT * 4096 == RING_BYTES && NST <= MAX_STAGES3, "ring geometry");
+  constexpr int STAGE_BYTES = SPCT * 4096;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  Tc3Smem& s = *reinterpret_cast<Tc3Smem*>(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const NfTileMap map(a.T, ROWS);
+  const long long units = map.units(a.n_rays);
+  const int trips = (int)((units + 2LL * gridDim.x - 1) / (2LL * gridDim.x));     // every CTA, every slot: same trip count
+  const int passes = trips * map.tpr;
+  const int n = prog.n_lin, lag = prog.lag;
+  const int nsteps = passes * n;                   // MMA steps (Linears) per slot
+
+  // ---- one-time setup ----
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NST; ++i) { mbar_init(smem_u32(&s.w_land[i]), 1); mbar_init(smem_u32(&s.w_empty[i]), 1); mbar_init(smem_u32(&s.w_ready[i]), 2); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s.acc_full[i]), 1); mbar_init(smem_u32(&s.a_ready[i]), 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 16) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  if (s.tmem_base != 0) __trap();
+
+  if (warp >= 16 && warp < 16 + NST) {
+    // ================= weight producers (both CTAs): one ring stage each =================
+    // The ring carries, step by step, slot 0's Linear then slot 1's (half a round behind); entry g goes to stage g % NST.
+    if (lane == 0) {
+      const int p = warp - 16;
+      const uint32_t ready_leader = leader_addr(smem_u32(&s.w_ready[p]));
+      const uint32_t bar_empty = smem_u32(&s.w_empty[p]), bar_land = smem_u32(&s.w_land[p]), dst = smem_u32(s.W + p * STAGE_BYTES);
+      int rs = 0, li0 = 0, li1 = 0; uint32_t use = 0;
+      for (int k = 0; k < nsteps + lag; ++k) {
+#pragma unroll 1
+        for (int slot = 0; slot < 2; ++slot) {
+          const int kl = k - (slot ? lag : 0);
+          if (kl < 0 || kl >= nsteps) continue;
+          const int li = slot ? li1 : li0;
+          const uint32_t steps = prog.lin[li].k0_steps + prog.lin[li].h_steps, sb = prog.lin[li].step_bytes;
+          const uint8_t* src = a.packed + prog.lin[li].w_off + (size_t)crank * prog.lin[li].half_bytes;
+          for (uint32_t st0 = 0; st0 < steps; st0 += SPCT) {
+            if (rs == p) {
+              const uint32_t bytes = (steps - st0 < (uint32_t)SPCT ? steps - st0 : (uint32_t)SPCT) * sb;
+              const uint32_t par = use & 1u; ++use;
+              mbar_wait(bar_empty, par ^ 1u);
+              mbar_expect_tx(bar_land, bytes);
+              bulk_g2s(dst, src + (size_t)st0 * sb, bytes, bar_land);
+              mbar_wait(bar_land, par);                                    // landed in THIS CTA ...
+              mbar_arrive_cluster_relaxed(ready_leader);                   // ... tell the leader's MMA thread
+            }
+            if (++rs == NST) rs = 0;
+          }
+          const int ln = li + 1 == n ? 0 : li + 1;
+          if (slot) li1 = ln; else li0 = ln;
+        }
+      }
+    }
+  } else if (warp == 16 + NST) {
+    // ================= MMA issuer (leader CTA only): one thread, tight nested loops =================
+    // The probe of the NEXT ring stage is issued before the current chunk's MMAs, so its ~150-cycle latency is hidden.
+    if (crank == 0 && lane == 0) {
+      uint32_t stage = 0, phase = 0, a_par = 0;
+      const uint32_t base4 = smem_u32(smem_raw) >> 4;
+      const uint32_t w4 = base4 + (uint32_t)(offsetof(Tc3Smem, W) >> 4);
+      const uint32_t bar_wready = smem_u32(&s.w_ready[0]), bar_wempty = smem_u32(&s.w_empty[0]);
+      const uint32_t bar_a = smem_u32(&s.a_ready[0]), bar_acc = smem_u32(&s.acc_full[0]);
+      const uint32_t a_lbo = (uint32_t)(KG_BYTES >> 4) << 16, kstep4 = (uint32_t)(2 * KG_BYTES) >> 4;
+      int li0 = 0, li1 = 0;
+      bool w_ok = false;                               // ring stage `stage` is known to be full
+      for (int k = 0; k < nsteps + lag; ++k) {
+#pragma unroll 1
+        for (uint32_t slot = 0; slot < 2; ++slot) {
+          const int kl = k - (slot ? lag : 0);
+          if (kl < 0 || kl >= nsteps) continue;
+          const int li = slot ? li1 : li0;
+          const uint4 r0 = *reinterpret_cast<const uint4*>(&prog.lin[li].k0_steps);
+          const uint32_t bhi = prog.lin[li].bhi;
+          const uint32_t k0s = r0.x, total = r0.x + r0.y, idesc = r0.z, bstep4 = r0.w;
+          mbar_wait(bar_a + slot * 8u, (a_par >> slot) & 1u); a_par ^= 1u << slot;
+          tc_fence_after();
+          const uint32_t d_tmem = slot * 256u;
+          const uint32_t x4 = (base4 + (uint32_t)(offsetof(Tc3Smem, X0) >> 4) + slot * (uint32_t)(sizeof(s.X0[0]) >> 4)) | a_lbo;
+          const uint32_t h4 = (base4 + (uint32_t)(offsetof(Tc3Smem, H) >> 4) + slot * (uint32_t)(sizeof(s.H[0]) >> 4)) | a_lbo;
+#pragma unroll 1
+          for (uint32_t gs0 = 0; gs0 < total; gs0 += SPCT) {
+            if (!w_ok) { mbar_wait(bar_wready + stage * 8u, phase); }
+            const uint32_t nstage = stage + 1 == NST ? 0u : stage + 1u, nphase = stage + 1 == NST ? phase ^ 1u : phase;
+            w_ok = mbar_test_wait(bar_wready + nstage * 8u, nphase);       // consumed on the next iteration
+            tc_fence_after();
+            const uint32_t b4 = (w4 + stage * (uint32_t)(STAGE_BYTES >> 4)) | bhi;
+            if (gs0 + SPCT <= total && (gs0 + SPCT <= k0s || gs0 >= k0s)) {
+              // fast path: a full chunk fed from one buffer -> back-to-back MMAs, operands differ by constants
+              const uint32_t a4 = gs0 < k0s ? x4 + gs0 * kstep4 : h4 + (gs0 - k0s) * kstep4;
+              umma2_f16(d_tmem, umma_desc_lo(a4), umma_desc_lo(b4), idesc, gs0 > 0 ? 1u : 0u);
+#pragma unroll
+              for (uint32_t i = 1; i < SPCT; ++i)
+                umma2_f16(d_tmem, umma_desc_lo(a4 + i * kstep4), umma_desc_lo(b4 + i * bstep4), idesc, 1u);
+            } else {
+              const uint32_t nst = total - gs0 < (uint32_t)SPCT ? total - gs0 : (uint32_t)SPCT;
+              for (uint32_t i = 0; i < nst; ++i) {
+                const uint32_t gs = gs0 + i;
+                const uint32_t a4 = gs < k0s ? x4 + gs * kstep4 : h4 + (gs - k0s) * kstep4;
+                umma2_f16(d_tmem, umma_desc_lo(a4), umma_desc_lo(b4 + i * bstep4), idesc, gs > 0 ? 1u : 0u);
+              }
+            }
+            umma2_commit_mc(bar_wempty + stage * 8u);
+            stage = nstage; phase = nphase;
+          }
+          umma2_commit_mc(bar_acc + slot * 8u);
+          const int ln = li + 1 == n ? 0 : li + 1;
+          if (slot) li1 = ln; else li0 = ln;
+        }
+      }
+    }
+  } else {
+    // ================= encode + epilogue: all 16 warps serve the two slots alternately =================
+    // TMEM lane quarter q = warp % 4 (rows 32q..32q+31), column quarter cq = warp / 4 (64 accumulator columns).
+    const int q = warp & 3, cq = warp >> 2;
+    const int e_tid = warp * 32 + lane;
+    const int row = q * 32 + lane;
+    const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+    uint32_t acc_par = 0;
+    int j0 = 0, j1 = 0, P0 = 0, P1 = 0;                 // per slot: phase within the cycle, pass (tile) index
+    for (int k = 0; k <= nsteps + lag; ++k) {
+#pragma unroll 1
+      for (int slot = 0; slot < 2; ++slot) {
+        const int kl = k - (slot ? lag : 0);
+        if (kl < 0 || kl > nsteps) continue;
+        const int j = slot ? j1 : j0, P = slot ? P1 : P0;
+        uint8_t* H = s.H[slot]; uint8_t* X0 = s.X0[slot];
+        const uint32_t t_acc = t_lane + (uint32_t)slot * 256u;
+        const uint32_t a_ready_leader = leader_addr(smem_u32(&s.a_ready[slot]));
+        const bool has_next = kl < nsteps;              // Linear j of this slot runs after this phase
+        // bias of Linear j (consumed by this slot's NEXT phase): in flight across the acc_full wait
+        float bnext = 0.f; bool bload = false;
+        if (has_next) {
+          const uint32_t mj = prog.lin[j].mj;
+          const NfLinPlan& Ln = plan.mlp[mj >> 4].lin[mj & 15];
+          bload = e_tid < Ln.n_pad;
+          if (bload) bnext = __ldg(reinterpret_cast<const float*>(a.packed + Ln.b16_off) + e_tid);
+        }
+        const float* bias = s.bias[slot][(kl & 1) ^ 1];   // bias of the Linear whose result this phase consumes
+        if (kl > 0) {
+          wait_acc(smem_u32(&s.acc_full[slot]), (acc_par >> slot) & 1u, a.debug);
+          acc_par ^= 1u << slot;
+          tc_fence_after();
+        }
+        if (bload) { s.bias[slot][kl & 1][e_tid] = bnext; __threadfence_block(); }
+
+        if (j == 0) {
+          // ---------- tile boundary: composite of pass P-1 (cq == 0 warps) while the others start encoding pass P ----------
+          const bool comp = P >= 1;
+          if (comp && cq == 0) {
+            long long u; int sub; unit_of(P - 1, slot, map.tpr, u, sub);
+            uint32_t v[16];
+            tmem_ld16(t_acc, v); tmem_ld_wait(); reg_fence16(v);
+            tc_fence_before();
+            float cr, cg, cb;
+            if (plan.kind == NF_KIND_TINY) {
+              s.sig[slot][row] = __uint_as_float(v[0]) + bias[0];
+              cr = __uint_as_float(v[1]) + bias[1]; cg = __uint_as_float(v[2]) + bias[2]; cb = __uint_as_float(v[3]) + bias[3];
+            } else {
+              cr = __uint_as_float(v[0]) + bias[0]; cg = __uint_as_float(v[1]) + bias[1]; cb = __uint_as_float(v[2]) + bias[2];
+            }
+            cr = nf_feat_act_fn(cr, plan.feat_act); cg = nf_feat_act_fn(cg, plan.feat_act); cb = nf_feat_act_fn(cb, plan.feat_act);
+            composite_tile3(s, slot, plan, a, map, u, sub, row, lane, q, cr, cg, cb);
+          }
+          if (has_next) {
+            long long u; int sub; unit_of(P, slot, map.tpr, u, sub);
+            long long ray; int t;
+            const bool ok = map.locate(u, sub, row, a.n_rays, ray, t);
+            float px = 0.f, py = 0.f, pz = 0.f;
+            if (ok) {
+              const float* rr = a.rays + ray * 6;
+              const float tt = __ldg(a.ts + ray * a.ts_stride + t);
+              px = nf_pt(__ldg(rr + 0), tt, __ldg(rr + 3)); py = nf_pt(__ldg(rr + 1), tt, __ldg(rr + 4)); pz = nf_pt(__ldg(rr + 2), tt, __ldg(rr + 5));
+            }
+            int kg = 0;
+            if (plan.enc == NF_ENC_HASH) {
+              // 4 threads per row share the levels; when the cq == 0 warps are compositing, the other three take them all
+              const float4* tables = reinterpret_cast<const float4*>(a.packed + plan.hash_off);
+              const int first = comp ? cq - 1 : cq, stride = comp ? 3 : 4;
+              if (first >= 0)
+                for (int lvl = first; lvl < plan.hash_levels; lvl += stride) {
+                  const float4 f = nf_hash_level(tables + (size_t)lvl * (plan.hash_mask + 1), px, py, pz, plan.hash_res[lvl],
+                                                 plan.hash_primes[0], plan.hash_primes[1], plan.hash_primes[2], plan.hash_mask, nullptr);
+                  *reinterpret_cast<uint2*>(X0 + (lvl >> 1) * KG_BYTES + row * 16 + (lvl & 1) * 8) = make_uint2(pack_h2(f.x, f.y), pack_h2(f.z, f.w));
+                }
+              kg = plan.hash_levels >> 1;
+            }
+            if (cq == 0) {
+              if (plan.enc == NF_ENC_HASH) st_v4(X0 + kg * KG_BYTES + row * 16, pack_h2(px, py), pack_h2(pz, px), pack_h2(py, pz), 0);
+              else st_v4(X0 + kg * KG_BYTES + row * 16, pack_h2(px, py), pack_h2(pz, 0.f), 0, 0);
+              for (int g = kg + 1; g < (plan.mlp[0].k0_pad >> 3); ++g) st_v4(X0 + g * KG_BYTES + row * 16, 0, 0, 0, 0);
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster_relaxed(a_ready_leader);
+          }
+        } else {
+          // ---------- epilogue of Linear j-1 ----------
+          const uint32_t mj = prog.lin[j - 1].mj;
+          const int m = (int)(mj >> 4), jj = (int)(mj & 15);
+          const NfMlpPlan& M = plan.mlp[m];
+          const NfLinPlan& L = M.lin[jj];
+          const int act = M.act;
+          if (!L.is_out) {
+            if (jj == 0) x0_activate3(X0, M.k0_pad, act, e_tid);       // init consumed raw x0; the skip Linear wants act(x0)
+            if (act == NF_ACT_SIN) epi_hidden3<NF_ACT_SIN>(H, t_acc, bias, cq, row);
+            else if (act == NF_ACT_LEAKY) epi_hidden3<NF_ACT_LEAKY>(H, t_acc, bias, cq, row);
+            else if (act == NF_ACT_RELU) epi_hidden3<NF_ACT_RELU>(H, t_acc, bias, cq, row);
+            else epi_hidden3<NF_ACT_NONE>(H, t_acc, bias, cq, row);
+          } else {
+            // density MLP out (tensor order [inter(I), sigma]) -> raw x0 of the View head + raw density
+            const int iu = plan.intermediate >> 4;
+            for (int un = cq; un <= iu; un += 4) {
+              uint32_t v[16];
+              tmem_ld16(t_acc + un * 16, v); tmem_ld_wait(); reg_fence16(v);
+              if (un < iu) {
+                uint32_t o[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  o[i] = pack_h2(__uint_as_float(v[2 * i]) + bias[un * 16 + 2 * i], __uint_as_float(v[2 * i + 1]) + bias[un * 16 + 2 * i + 1]);
+                uint8_t* d0 = X0 + (un * 2) * KG_BYTES + row * 16;
+                st_v4(d0, o[0], o[1], o[2], o[3]); st_v4(d0 + KG_BYTES, o[4], o[5], o[6], o[7]);
+              } else {
+                s.sig[slot][row] = __uint_as_float(v[0]) + bias[plan.intermediate];
+                long long u; int sub; unit_of(P, slot, map.tpr, u, sub);
+                long long ray; int t;
+                float px = 0.f, py = 0.f, pz = 0.f, el = 0.f, az = 0.f;
+                if (map.locate(u, sub, row, a.n_rays, ray, t)) {
+                  const float* rr = a.rays + ray * 6;
+                  const float tt = __ldg(a.ts + ray * a.ts_stride + t);
+                  const float dx = __ldg(rr + 3), dy = __ldg(rr + 4), dz = __ldg(rr + 5);
+                  px = nf_pt(__ldg(rr + 0), tt, dx); py = nf_pt(__ldg(rr + 1), tt, dy); pz = nf_pt(__ldg(rr + 2), tt, dz);
+                  nf_elaz(dx, dy, dz, el, az);
+                }
+                uint8_t* d0 = X0 + (iu * 2) * KG_BYTES + row * 16;
+                st_v4(d0, pack_h2(px, py), pack_h2(pz, el), pack_h2(az, 0.f), 0);
+                st_v4(d0 + KG_BYTES, 0, 0, 0, 0);
+              }
+            }
+          }
+          tc_fence_before();
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster_relaxed(a_ready_leader);
+        }
+        int jn = j + 1, Pn = P;
+        if (jn == n) { jn = 0; ++Pn; }
+        if (slot) { j1 = jn; P1 = Pn; } else { j0 = jn; P0 = Pn; }
+      }
+    }
+  }
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 16) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(0), "r"(512) : "memory");
+  }
+}
+
+bool build_prog3(const NfPlan& plan, Tc3Prog* P) {
+  *P = Tc3Prog{};
+  int nl = 0;
+  for (int m = 0; m < plan.n_mlps; ++m)
+    for (int j = 0; j < plan.mlp[m].n_lin; ++j, ++nl) {
+      const NfLinPlan& L = plan.mlp[m].lin[j];
+      const uint32_t nh = (uint32_t)L.n_pad >> 1, b_lbo = nh * 16u;
+      Tc3Lin& R = P->lin[nl];
+      R.k0_steps = (uint32_t)L.k0_pad >> 4; R.h_steps = (uint32_t)L.k_hidden >> 4;
+      R.idesc = (1u << 4) | ((uint32_t)(L.n_pad >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);   // M = 256 across the pair
+      R.bstep4 = (2u * b_lbo) >> 4; R.bhi = (b_lbo >> 4) << 16;
+      R.mj = (uint32_t)(m * 16 + j);
+      const int64_t half_bytes = (int64_t)(L.k0_pad + L.k_hidden) * nh * 2;
+      if (L.w16h_off + 2 * half_bytes >= (1LL << 32)) return false;
+      R.w_off = (uint32_t)L.w16h_off; R.half_bytes = (uint32_t)half_bytes; R.step_bytes = 2u * b_lbo;
+    }
+  P->n_lin = nl; P->lag = nl / 2;
+  return true;
+}
+
+}  // namespace
+
+// nullptr if the staggered paired pipeline can run this model, else the reason.
+const char* nf_tc3_unsupported(const NfPlan& p) {
+  if (p.kind == NF_KIND_DYN) return "NF_KIND_DYN runs on the fp32 pipeline only in this build";
+  int nlin = 0;
+  for (int m = 0; m < p.n_mlps; ++m) {
+    nlin += p.mlp[m].n_lin;
+    if (p.mlp[m].k0_pad > X0K) return "x0 wider than 80 columns";
+    for (int j = 0; j < p.mlp[m].n_lin; ++j) {
+      // only the density MLP of a two-MLP model may end in a non-final `out` Linear
+      if (p.mlp[m].lin[j].is_out && m != p.n_mlps - 1 && !(p.kind == NF_KIND_PLAIN && m == 0)) return "unsupported MLP chain";
+    }
+  }
+  if (nlin > MAX_LIN3 || nlin < 2) return "unsupported number of Linear layers";
+  if (p.enc == NF_ENC_FOURIER) return "Fourier-encoded density MLP (x0 is 259 wide) runs on the fp32 pipeline only";
+  if (p.enc == NF_ENC_HASH && (p.hash_levels & 1)) return "odd number of hash levels";
+  if (p.kind == NF_KIND_PLAIN && (p.intermediate & 15)) return "intermediate_size not a multiple of 16";
+  return nullptr;
+}
+
+cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const float* rays, int64_t n_rays, const float* ts,
+                                 int T, int64_t ts_stride, const float* noise, float* rgb, float* alpha, float* weights,
+                                 cudaStream_t st) {
+  if (nf_tc3_unsupported(plan)) return cudaErrorNotSupported;
+  Tc3Args a{};
+  a.packed = (const uint8_t*)packed; a.rays = rays; a.n_rays = n_rays; a.ts = ts; a.T = T; a.ts_stride = ts_stride;
+  a.noise = noise; a.rgb_out = rgb; a.alpha_out = alpha; a.weights_out = weights;
+  if (const char* dbg = getenv("NF_TC_DEBUG")) a.debug = atoi(dbg);
+  // NF_TC_RING selects the weight-ring geometry (same 48 KB): "6" = 6 stages x 8 KB (default), "3" = 3 stages x 16 KB
+  int ring = 6;
+  if (const char* r = getenv("NF_TC_RING")) ring = atoi(r);
+  const void* fn = ring == 3 ? (const void*)k_render_tc3<3, 4> : (const void*)k_render_tc3<6, 2>;
+  const int threads = EPI_THREADS + 32 * ((ring == 3 ? 3 : 6) + 1);
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tc3Smem));
+  if (e != cudaSuccess) return e;
+  const NfTileMap map(T, ROWS);
+  const long long units = map.units(n_rays);
+  if (units == 0) return cudaSuccess;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long want = (units + 3) / 4 * 2;                      // 2 CTAs x 2 slots per cluster
+  const int grid = (int)(want < (sms / 2) * 2 ? want : (sms / 2) * 2);
+  Tc3Prog prog;
+  if (!build_prog3(plan, &prog)) return cudaErrorNotSupported;
+  const long long trips = (units + 2LL * grid - 1) / (2LL * grid);
+  if (trips * map.tpr * prog.n_lin + prog.lag >= (1LL << 30)) return cudaErrorNotSupported;   // 32-bit step counters in the kernel
+  if (ring == 3) k_render_tc3<3, 4><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a);
+  else k_render_tc3<6, 2><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a);
+  return cudaGetLastError();
+}

@@ -155,6 +155,49 @@ def test_tiny_nerf_vs_oracle():
     rgb, _, _ = e.render(rays.to(DEV), ts.to(DEV))
     assert np.abs(rgb.cpu().numpy() - r["out"].numpy()).max() <= tol, precision
 
+# ---------------------------------------------------------------- every tensor pipeline / ring geometry
+@pytest.mark.parametrize("env", [{"NF_TC_PIPE": "3", "NF_TC_RING": "6"}, {"NF_TC_PIPE": "3", "NF_TC_RING": "3"},
+                                 {"NF_TC_PIPE": "2"}, {"NF_TC_PIPE": "1"}],
+                         ids=["pipe3_ring6", "pipe3_ring3", "pipe2", "pipe1"])
+def test_tensor_pipeline_variants_vs_oracle(P, env, monkeypatch):
+  """The C ABI reads NF_TC_PIPE / NF_TC_RING at every call: 3 = staggered paired pipeline (default; ring 6x8 KB or
+  3x16 KB), 2 = lockstep paired pipeline, 1 = single-CTA pipeline.  All must meet the same bars, incl. rays spanning two
+  tiles (T = 256), ragged tiles (T = 100), several rays per tile (T = 32), noise, per-ray ts and the white background."""
+  for k, v in env.items(): monkeypatch.setenv(k, v)
+  e = plain_engine(P, DEV, precision="fp16")
+  for T, nr in ((128, 1500), (256, 333), (100, 77), (32, 1001)):
+    rays = O.make_rays(1, 40, 40, seed=T, crop_top=380, crop_left=380).reshape(-1, 6)[:nr]
+    ts = torch.linspace(2, 6, T)
+    with torch.no_grad():
+      sub = rays[:64]
+      ref = O.plain_forward(P, sub, ts); refq = O.plain_forward(P, sub, ts, quant=torch.float16)
+    rgb, alpha, w = e.render(rays.to(DEV), ts.to(DEV))
+    rgb2, _, _ = e.render(rays.to(DEV), ts.to(DEV), want_weights=False)
+    assert torch.equal(rgb, rgb2), (env, T, "not deterministic")
+    out = rgb.cpu().numpy()
+    assert np.isfinite(out).all()
+    assert np.abs(out[:64] - refq["out"].numpy()).max() <= 3e-4, (env, T)
+    assert np.abs(out[:64] - ref["out"].numpy()).max() <= 1e-3, (env, T)
+    assert np.abs(w.cpu().numpy()[:64] - ref["weights"].t().numpy()).max() <= 5e-3, (env, T)
+    # every ray, not only the checked head: shard == whole (different tile <-> slot assignment)
+    cut = nr // 2 + 3
+    a, _, _ = e.render(rays[:cut].contiguous().to(DEV), ts.to(DEV), want_weights=False)
+    b, _, _ = e.render(rays[cut:].contiguous().to(DEV), ts.to(DEV), want_weights=False)
+    assert torch.equal(torch.cat([a, b]), rgb), (env, T, "sharded render differs from the whole")
+  # white background + per-ray ts + density noise
+  g = torch.Generator().manual_seed(5)
+  rays = O.make_rays(1, 4, 9, seed=2, crop_top=300, crop_left=500).reshape(-1, 6)
+  R, T = rays.shape[0], 48
+  tsr = torch.sort(torch.rand(R, T, generator=g) * 4 + 2, dim=1).values
+  noise = torch.randn(R, T, generator=g) * 0.2
+  pts = (rays[:, None, :3] + tsr[:, :, None] * rays[:, None, 3:]).permute(1, 0, 2).contiguous()
+  with torch.no_grad():
+    ref = O.plain_from_pts(P, pts, tsr.t().contiguous(), rays[:, :3], rays[:, 3:], bg="white",
+                           density_noise=noise.t().contiguous(), per_ray_ts=True)
+  ew = plain_engine(P, DEV, bg="white", precision="fp16")
+  rgb, _, _ = ew.render(rays.to(DEV), tsr.to(DEV), noise.to(DEV))
+  assert np.abs(rgb.cpu().numpy() - ref["out"].numpy()).max() <= 1e-3, env
+
 # ---------------------------------------------------------------- properties at size
 def test_properties_full_frame_tile(P):
   """800x800x128 is the bench workload; here a 200-row band of it (160k rays, 20.5M samples) checks the
