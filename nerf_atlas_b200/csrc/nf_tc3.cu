@@ -44,6 +44,7 @@ struct Tc3Smem {
   float warp_agg[2][4]; int warp_cont[2][4]; float warp_sum[2][4][4]; float carry[2][8];
   unsigned long long w_land[MAX_STAGES3], w_empty[MAX_STAGES3], w_ready[MAX_STAGES3], acc_full[2], a_ready[2];
   uint32_t tmem_base; int pad_;
+  int4 lin[MAX_LIN3][2];        // per Linear, for the epilogue warps: {n_pad, bias byte offset, act, flags(1 = out, 2 = init)}, {k0_pad, -, -, -}
 };
 static_assert(sizeof(Tc3Smem) <= 227 * 1024, "staggered tensor pipeline smem");
 
@@ -63,7 +64,22 @@ struct Tc3Args {
   const float* noise;
   float* rgb_out; float* alpha_out; float* weights_out;
   int debug;          // NF_TC_DEBUG (timing experiments): 256 = poll acc_full with backoff, 512 = try_wait with a short suspend hint
+  long long* stats;   // NF_TC_STATS builds: time-in-state counters of CTA 0 (issuer, producer 0, epilogue warps 0 and 15)
 };
+
+#ifdef NF_TC_STATS
+#define ST_DECL long long st_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long st_t = clock64(); const long long st_begin = st_t; (void)st_begin
+#define ST_MARK() (st_t = clock64())
+#define ST_ADD(i) do { const long long st_now = clock64(); st_acc[i] += st_now - st_t; st_t = st_now; } while (0)
+#define ST_INC(i) (++st_acc[i])
+#define ST_FLUSH(base, cond) do { if ((cond) && a.stats) { a.stats[(base)] = clock64() - st_begin; for (int st_i = 0; st_i < 7; ++st_i) a.stats[(base) + 1 + st_i] = st_acc[st_i]; } } while (0)
+#else
+#define ST_DECL do { } while (0)
+#define ST_MARK() do { } while (0)
+#define ST_ADD(i) do { } while (0)
+#define ST_INC(i) do { } while (0)
+#define ST_FLUSH(base, cond) do { } while (0)
+#endif
 
 // acc_full wait of the 16 epilogue warps.  Default: hardware-suspended try_wait (no issue slots burnt).
 __device__ __forceinline__ void wait_acc(uint32_t bar, uint32_t parity, int debug) {
@@ -234,6 +250,15 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
+  if (threadIdx.x < prog.n_lin) {
+    // the epilogue's per-Linear facts, copied once from the kernel parameters (dependent indexed constant loads cost
+    // ~250 cycles each when they miss the constant cache: ~600 cycles per phase before this table existed)
+    const uint32_t mj = prog.lin[threadIdx.x].mj;
+    const NfMlpPlan& M = plan.mlp[mj >> 4];
+    const NfLinPlan& L = M.lin[mj & 15];
+    s.lin[threadIdx.x][0] = make_int4(L.n_pad, (int)L.b16_off, M.act, (L.is_out ? 1 : 0) | ((mj & 15) == 0 ? 2 : 0));
+    s.lin[threadIdx.x][1] = make_int4(M.k0_pad, 0, 0, 0);
+  }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
@@ -243,11 +268,12 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
   if (warp >= 16 && warp < 16 + NST) {
     // ================= weight producers (both CTAs): one ring stage each =================
     // The ring carries, step by step, slot 0's Linear then slot 1's (half a round behind); entry g goes to stage g % NST.
-    if (lane == 0) {
+    if (elect_one()) {
       const int p = warp - 16;
       const uint32_t ready_leader = leader_addr(smem_u32(&s.w_ready[p]));
       const uint32_t bar_empty = smem_u32(&s.w_empty[p]), bar_land = smem_u32(&s.w_land[p]), dst = smem_u32(s.W + p * STAGE_BYTES);
       int rs = 0, li0 = 0, li1 = 0; uint32_t use = 0;
+      ST_DECL;
       for (int k = 0; k < nsteps + lag; ++k) {
 #pragma unroll 1
         for (int slot = 0; slot < 2; ++slot) {
@@ -260,11 +286,15 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
             if (rs == p) {
               const uint32_t bytes = (steps - st0 < (uint32_t)SPCT ? steps - st0 : (uint32_t)SPCT) * sb;
               const uint32_t par = use & 1u; ++use;
-              mbar_wait(bar_empty, par ^ 1u);
+              ST_ADD(2);
+              if (a.debug & 1024) mbar_wait_backoff(bar_empty, par ^ 1u); else mbar_wait(bar_empty, par ^ 1u);
+              ST_ADD(0);
               mbar_expect_tx(bar_land, bytes);
               bulk_g2s(dst, src + (size_t)st0 * sb, bytes, bar_land);
               mbar_wait(bar_land, par);                                    // landed in THIS CTA ...
+              ST_ADD(1);
               mbar_arrive_cluster_relaxed(ready_leader);                   // ... tell the leader's MMA thread
+              ST_INC(3);
             }
             if (++rs == NST) rs = 0;
           }
@@ -272,11 +302,12 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
           if (slot) li1 = ln; else li0 = ln;
         }
       }
+      ST_FLUSH(8, blockIdx.x == 0 && p == 0);
     }
   } else if (warp == 16 + NST) {
     // ================= MMA issuer (leader CTA only): one thread, tight nested loops =================
     // The probe of the NEXT ring stage is issued before the current chunk's MMAs, so its ~150-cycle latency is hidden.
-    if (crank == 0 && lane == 0) {
+    if (crank == 0 && elect_one()) {
       uint32_t stage = 0, phase = 0, a_par = 0;
       const uint32_t base4 = smem_u32(smem_raw) >> 4;
       const uint32_t w4 = base4 + (uint32_t)(offsetof(Tc3Smem, W) >> 4);
@@ -285,6 +316,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
       const uint32_t a_lbo = (uint32_t)(KG_BYTES >> 4) << 16, kstep4 = (uint32_t)(2 * KG_BYTES) >> 4;
       int li0 = 0, li1 = 0;
       bool w_ok = false;                               // ring stage `stage` is known to be full
+      ST_DECL;
       for (int k = 0; k < nsteps + lag; ++k) {
 #pragma unroll 1
         for (uint32_t slot = 0; slot < 2; ++slot) {
@@ -294,14 +326,16 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
           const uint4 r0 = *reinterpret_cast<const uint4*>(&prog.lin[li].k0_steps);
           const uint32_t bhi = prog.lin[li].bhi;
           const uint32_t k0s = r0.x, total = r0.x + r0.y, idesc = r0.z, bstep4 = r0.w;
+          ST_ADD(2);
           mbar_wait(bar_a + slot * 8u, (a_par >> slot) & 1u); a_par ^= 1u << slot;
+          ST_ADD(0);
           tc_fence_after();
           const uint32_t d_tmem = slot * 256u;
           const uint32_t x4 = (base4 + (uint32_t)(offsetof(Tc3Smem, X0) >> 4) + slot * (uint32_t)(sizeof(s.X0[0]) >> 4)) | a_lbo;
           const uint32_t h4 = (base4 + (uint32_t)(offsetof(Tc3Smem, H) >> 4) + slot * (uint32_t)(sizeof(s.H[0]) >> 4)) | a_lbo;
 #pragma unroll 1
           for (uint32_t gs0 = 0; gs0 < total; gs0 += SPCT) {
-            if (!w_ok) { mbar_wait(bar_wready + stage * 8u, phase); }
+            if (!w_ok) { ST_ADD(2); mbar_wait(bar_wready + stage * 8u, phase); ST_ADD(1); ST_INC(3); }
             const uint32_t nstage = stage + 1 == NST ? 0u : stage + 1u, nphase = stage + 1 == NST ? phase ^ 1u : phase;
             w_ok = mbar_test_wait(bar_wready + nstage * 8u, nphase);       // consumed on the next iteration
             tc_fence_after();
@@ -329,6 +363,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
           if (slot) li1 = ln; else li0 = ln;
         }
       }
+      ST_FLUSH(0, blockIdx.x == 0);
     }
   } else {
     // ================= encode + epilogue: all 16 warps serve the two slots alternately =================
@@ -339,6 +374,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
     const uint32_t t_lane = (uint32_t)(q * 32) << 16;
     uint32_t acc_par = 0;
     int j0 = 0, j1 = 0, P0 = 0, P1 = 0;                 // per slot: phase within the cycle, pass (tile) index
+    ST_DECL;
     for (int k = 0; k <= nsteps + lag; ++k) {
 #pragma unroll 1
       for (int slot = 0; slot < 2; ++slot) {
@@ -352,18 +388,18 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
         // bias of Linear j (consumed by this slot's NEXT phase): in flight across the acc_full wait
         float bnext = 0.f; bool bload = false;
         if (has_next) {
-          const uint32_t mj = prog.lin[j].mj;
-          const NfLinPlan& Ln = plan.mlp[mj >> 4].lin[mj & 15];
-          bload = e_tid < Ln.n_pad;
-          if (bload) bnext = __ldg(reinterpret_cast<const float*>(a.packed + Ln.b16_off) + e_tid);
+          const int4 Ln = s.lin[j][0];
+          bload = e_tid < Ln.x;
+          if (bload) bnext = __ldg(reinterpret_cast<const float*>(a.packed + (uint32_t)Ln.y) + e_tid);
         }
         const float* bias = s.bias[slot][(kl & 1) ^ 1];   // bias of the Linear whose result this phase consumes
         if (kl > 0) {
+          ST_ADD(5);
           wait_acc(smem_u32(&s.acc_full[slot]), (acc_par >> slot) & 1u, a.debug);
+          ST_ADD(0);
           acc_par ^= 1u << slot;
           tc_fence_after();
         }
-        if (bload) { s.bias[slot][kl & 1][e_tid] = bnext; __threadfence_block(); }
 
         if (j == 0) {
           // ---------- tile boundary: composite of pass P-1 (cq == 0 warps) while the others start encoding pass P ----------
@@ -411,20 +447,20 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
               else st_v4(X0 + kg * KG_BYTES + row * 16, pack_h2(px, py), pack_h2(pz, 0.f), 0, 0);
               for (int g = kg + 1; g < (plan.mlp[0].k0_pad >> 3); ++g) st_v4(X0 + g * KG_BYTES + row * 16, 0, 0, 0, 0);
             }
+            if (bload) { s.bias[slot][kl & 1][e_tid] = bnext; __threadfence_block(); }   // for this slot's next phase
             tc_fence_before();
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster_relaxed(a_ready_leader);
           }
+          ST_ADD(1);
         } else {
           // ---------- epilogue of Linear j-1 ----------
-          const uint32_t mj = prog.lin[j - 1].mj;
-          const int m = (int)(mj >> 4), jj = (int)(mj & 15);
-          const NfMlpPlan& M = plan.mlp[m];
-          const NfLinPlan& L = M.lin[jj];
-          const int act = M.act;
-          if (!L.is_out) {
-            if (jj == 0) x0_activate3(X0, M.k0_pad, act, e_tid);       // init consumed raw x0; the skip Linear wants act(x0)
+          const int4 Lc = s.lin[j - 1][0];
+          const int act = Lc.z;
+          const bool is_out = (Lc.w & 1) != 0;
+          if (!is_out) {
+            if (Lc.w & 2) x0_activate3(X0, s.lin[j - 1][1].x, act, e_tid);       // init consumed raw x0; the skip Linear wants act(x0)
             if (act == NF_ACT_SIN) epi_hidden3<NF_ACT_SIN>(H, t_acc, bias, cq, row);
             else if (act == NF_ACT_LEAKY) epi_hidden3<NF_ACT_LEAKY>(H, t_acc, bias, cq, row);
             else if (act == NF_ACT_RELU) epi_hidden3<NF_ACT_RELU>(H, t_acc, bias, cq, row);
@@ -460,18 +496,26 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
               }
             }
           }
+          if (bload) { s.bias[slot][kl & 1][e_tid] = bnext; __threadfence_block(); }     // for this slot's next phase
           tc_fence_before();
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster_relaxed(a_ready_leader);
+          if (is_out) ST_ADD(4); else if (act == NF_ACT_SIN) ST_ADD(3); else ST_ADD(2);
         }
         int jn = j + 1, Pn = P;
         if (jn == n) { jn = 0; ++Pn; }
         if (slot) { j1 = jn; P1 = Pn; } else { j0 = jn; P0 = Pn; }
       }
     }
+    ST_FLUSH(16, blockIdx.x == 0 && warp == 0 && lane == 0);
+    ST_FLUSH(24, blockIdx.x == 0 && warp == 15 && lane == 0);
+    ST_FLUSH(32, blockIdx.x == 1 && warp == 0 && lane == 0);
   }
   // ---- teardown ----
+#ifdef NF_TC_STATS
+  // (the epilogue warps' counters live in their branch scope; they are flushed there)
+#endif
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
@@ -530,8 +574,9 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
   a.packed = (const uint8_t*)packed; a.rays = rays; a.n_rays = n_rays; a.ts = ts; a.T = T; a.ts_stride = ts_stride;
   a.noise = noise; a.rgb_out = rgb; a.alpha_out = alpha; a.weights_out = weights;
   if (const char* dbg = getenv("NF_TC_DEBUG")) a.debug = atoi(dbg);
-  // NF_TC_RING selects the weight-ring geometry (same 48 KB): "6" = 6 stages x 8 KB (default), "3" = 3 stages x 16 KB
-  int ring = 6;
+  // NF_TC_RING selects the weight-ring geometry (same 48 KB): "3" = 3 stages x 16 KB (default; measured faster: the single
+  // issuing thread pays one probe + one commit per stage), "6" = 6 stages x 8 KB
+  int ring = 3;
   if (const char* r = getenv("NF_TC_RING")) ring = atoi(r);
   const void* fn = ring == 3 ? (const void*)k_render_tc3<3, 4> : (const void*)k_render_tc3<6, 2>;
   const int threads = EPI_THREADS + 32 * ((ring == 3 ? 3 : 6) + 1);
@@ -548,7 +593,28 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
   if (!build_prog3(plan, &prog)) return cudaErrorNotSupported;
   const long long trips = (units + 2LL * grid - 1) / (2LL * grid);
   if (trips * map.tpr * prog.n_lin + prog.lag >= (1LL << 30)) return cudaErrorNotSupported;   // 32-bit step counters in the kernel
+#ifdef NF_TC_STATS
+  static long long* d_stats = nullptr;
+  if (!d_stats) cudaMalloc(&d_stats, 64 * sizeof(long long));
+  cudaMemsetAsync(d_stats, 0, 64 * sizeof(long long), st);
+  a.stats = d_stats;
+#endif
   if (ring == 3) k_render_tc3<3, 4><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a);
   else k_render_tc3<6, 2><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a);
+#ifdef NF_TC_STATS
+  if (getenv("NF_TC_STATS_PRINT")) {
+    cudaStreamSynchronize(st);
+    long long h[64];
+    cudaMemcpy(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost);
+    const char* names[5] = {"issuer  [total, wait_a, wait_w, issue+other, n_w_waits]", "producer0 [total, wait_empty, copy, other, n]",
+                            "epi w0  [total, wait_acc, phase0, leaky, sin, dens_out, other]", "epi w15 [same]", "epi w0 of the peer CTA [same]"};
+    for (int r = 0; r < 5; ++r) {
+      printf("STATS %s:", names[r]);
+      for (int i = 0; i < 8; ++i) printf(" %lld", h[r * 8 + i]);
+      printf("\n");
+    }
+    fflush(stdout);
+  }
+#endif
   return cudaGetLastError();
 }

@@ -13,14 +13,13 @@ from oracle import nerf_oracle as O   # synthetic inputs only
 
 VARIANTS = [
   ("pipe2_lockstep", {"NF_TC_PIPE": "2"}),
-  ("pipe3_ring6x8", {"NF_TC_PIPE": "3", "NF_TC_RING": "6"}),
   ("pipe3_ring3x16", {"NF_TC_PIPE": "3", "NF_TC_RING": "3"}),
-  ("pipe3_ring6x8_hint64", {"NF_TC_PIPE": "3", "NF_TC_RING": "6", "NF_TC_DEBUG": "512"}),
-  ("pipe3_ring6x8_backoff", {"NF_TC_PIPE": "3", "NF_TC_RING": "6", "NF_TC_DEBUG": "256"}),
+  ("pipe3_ring3x16_producer_backoff", {"NF_TC_PIPE": "3", "NF_TC_RING": "3", "NF_TC_DEBUG": "1024"}),
   ("pipe3_ring3x16_hint64", {"NF_TC_PIPE": "3", "NF_TC_RING": "3", "NF_TC_DEBUG": "512"}),
+  ("pipe3_ring3x16_hint64_producer_backoff", {"NF_TC_PIPE": "3", "NF_TC_RING": "3", "NF_TC_DEBUG": "1536"}),
+  ("pipe3_ring6x8", {"NF_TC_PIPE": "3", "NF_TC_RING": "6"}),
   ("pipe1_single_cta", {"NF_TC_PIPE": "1"}),
 ]
-
 def main():
   ap = argparse.ArgumentParser(); ap.add_argument("--steps", type=int, default=4); ap.add_argument("--views", type=int, default=4)
   args = ap.parse_args()
