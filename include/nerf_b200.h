@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NF_ABI_VERSION 3
+#define NF_ABI_VERSION 4
 
 /* error codes (negative; positive values are cudaError_t) */
 #define NF_E_BADARG    (-1)
@@ -56,6 +56,18 @@ enum nf_kind {
   NF_KIND_TINY  = 1, /* TinyNeRF (intended semantics): reference src/nerf.py:278-305 */
   NF_KIND_DYN   = 2  /* DynamicNeRF, direct deformation MLP over a canonical PlainNeRF (reference src/nerf.py:1209-1303):
                         delta_estim([p, t]) -> (dp[1], rigidity[3]); p' = p + dp * sigmoid(rigidity / 2); then NF_KIND_PLAIN on p' */
+};
+/* Mip-NeRF integrated positional encoding appended to BOTH MLP inputs (reference src/nerf.py:255-261,340-358;
+ * src/utils.py:39-48,60-140): 96 features per sample, E[sin/cos(2^k x)], k = 0..15, of the Gaussian of the ray segment
+ * [t_i, t_i+1].  x0 becomes [p, enc(p), ipe(96)] and the View head's [p, elaz, ipe(96), intermediate(I)]. */
+enum nf_mip {
+  NF_MIP_NONE = 0,
+  NF_MIP_CYLINDER = 1,     /* CylinderGaussian as intended: per-sample variance, last segment capped to t[T-1]+(t[T-1]-t[T-2]) */
+  NF_MIP_CONE = 2,         /* ConicGaussian as intended (same layout and cap; the reference's own cone run is all-NaN) */
+  NF_MIP_CYLINDER_REF = 3  /* CylinderGaussian exactly as the reference computes it, bug for bug: last segment ends at 1e10
+                              and the variance of feature c of sample (t, ray) is taken from the element with the same flat
+                              index of the [xyz, ray, k, t] covariance array (utils.py:73 moves the wrong axis, 42-44
+                              reinterpret) -- needs every ray of the crop: nf_mip_args.rays_all / radius_all */
 };
 /* arithmetic of the MLP contractions */
 enum nf_precision {
@@ -89,8 +101,21 @@ typedef struct nf_model_desc {
   int32_t feat_act;          /* enum nf_feat_act */
   int32_t bg;                /* enum nf_bg */
   int32_t fourier_freqs;     /* NF_ENC_FOURIER: columns of the basis [3, freqs] (x0 = [p, sin(pB), cos(pB)]) */
-  nf_mlp_desc deform;        /* NF_KIND_DYN: DynamicNeRF.delta_estim (in 4 = xyz,t; out 4) */
+  nf_mlp_desc deform;        /* NF_KIND_DYN: DynamicNeRF.delta_estim (direct: in 4 = xyz,t, out 4; spline: in 38, out 1+3n) */
+  int32_t mip;               /* enum nf_mip (NF_PREC_FP32 only: x0 is 134 / 165 wide) */
+  int32_t deform_enc;        /* NF_KIND_DYN: encoder of `deform`: NF_ENC_NONE (direct) or NF_ENC_HASH (spline; its own tables) */
+  int32_t spline_points;     /* NF_KIND_DYN: 0 = direct_predict (nerf.py:1261-1266); n in 2..8 = spline_interpolate with n
+                                Bezier control points (nerf.py:1267-1278; de_casteljau 1173-1178, cubic_bezier 1201-1206) */
 } nf_model_desc;
+
+/* Per-call inputs of the Mip encoder (nf_model_desc.mip != NF_MIP_NONE); all device pointers. */
+typedef struct nf_mip_args {
+  const float* radius;       /* [R] pixel radius of every ray of this call (nf_ray_radii) */
+  const float* rays_all;     /* NF_MIP_CYLINDER_REF: rays of the WHOLE crop [R_all,6] (== rays when not sharded) */
+  const float* radius_all;   /* NF_MIP_CYLINDER_REF: [R_all] */
+  int64_t n_rays_all;        /* R_all = B*H*W of the crop */
+  int64_t ray_base;          /* index of this call's first ray within the crop */
+} nf_mip_args;
 
 /* ---- library ----------------------------------------------------------- */
 int nf_version(void);
@@ -102,6 +127,7 @@ const char* nf_last_error(void);
  *   refl MLP   : same order                                   (NF_KIND_PLAIN, NF_KIND_DYN)
  *   deform MLP : same order                                   (NF_KIND_DYN only)
  *   hash tables: embs[0].weight ... embs[levels-1].weight      (NF_ENC_HASH only)
+ *   deform hash: delta_estim.enc.embs[0..levels-1].weight      (NF_KIND_DYN with deform_enc == NF_ENC_HASH only)
  *   fourier    : enc.basis [3, freqs]                          (NF_ENC_FOURIER only)
  *   beta       : VolSDF.scale (scalar)                         (NF_DENS_LAPLACE only)
  * Each is the live fp32 nn.Parameter storage ([out,in] row-major for weights). */
@@ -125,17 +151,22 @@ int nf_pack_weights(const nf_model_desc* desc, const float* const* params_host, 
  *   density_noise  nullable [R,T]; added to the raw density (nerf.py:347-348, already scaled)
  *   ray_time       NF_KIND_DYN: time of every ray, [R] (the reference broadcasts times[B] over the view's pixels,
  *                  nerf.py:1301); NULL otherwise
+ *   mip            nf_model_desc.mip != NF_MIP_NONE: radii (and, for NF_MIP_CYLINDER_REF, the whole crop); needs a shared
+ *                  ts[T] (ts_ray_stride == 0, as in the reference); NULL otherwise
  *   alpha_out, weights_out  nullable [R,T] (ray-major; the reference's self.alpha/self.weights
  *                  are the [T,R] transposes)
  */
 int nf_render_forward(const nf_model_desc* desc, const void* packed,
                       const float* rays, int64_t n_rays,
                       const float* ts, int32_t T, int64_t ts_ray_stride,
-                      const float* density_noise, const float* ray_time,
+                      const float* density_noise, const float* ray_time, const nf_mip_args* mip,
                       float* rgb_out, float* alpha_out, float* weights_out,
                       int32_t precision, void* stream);
 
 /* ---- stages of the path, exported for parity tests and micro-benchmarks -- */
+/* radii_x (reference src/utils.py:77-81) on a crop of rays[B,H,W,6] (H >= 3): radius_out[B,H,W] = |r_d[h] - r_d[h+1]| * 2/sqrt(12),
+ * the last row repeating difference H-3 exactly like the reference's `dx[:, -2:-1, :]`. */
+int nf_ray_radii(const float* rays, int64_t B, int32_t H, int32_t W, float* radius_out, void* stream);
 /* pts[R,T,3] = r_o + ts*r_d, rounded product then rounded add (reference src/nerf.py:54). */
 int nf_sample_points(const float* rays, int64_t n_rays, const float* ts, int32_t T, int64_t ts_ray_stride,
                      float* pts_out, void* stream);

@@ -7,7 +7,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, os.environ.get("NF_LIB", "libnerf_b200.so"))
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 # enums of include/nerf_b200.h
 ACT = {"none": 0, "leaky_relu": 1, "sin": 2, "relu": 3}
 ENC = {"none": 0, "hash": 1, "fourier": 2}
@@ -17,6 +17,7 @@ FEAT = {"normal": 0, "thin": 1, "tanh": 2, "cyclic": 3, "upshifted": 4, "fat": 5
 BG = {"black": 0, "white": 1}
 KIND = {"plain": 0, "tiny": 1, "dyn": 2}
 PRECISION = {"fp32": 0, "fp16": 1}
+MIP = {None: 0, "none": 0, "cylinder": 1, "cone": 2, "cylinder_ref": 3}
 
 class MlpDesc(C.Structure):
   _fields_ = [("in_dims", C.c_int32), ("hidden", C.c_int32), ("n_layers", C.c_int32),
@@ -27,7 +28,12 @@ class ModelDesc(C.Structure):
               ("intermediate", C.c_int32), ("enc", C.c_int32), ("hash_levels", C.c_int32),
               ("hash_table_size", C.c_int32), ("hash_feat", C.c_int32), ("hash_primes", C.c_uint32 * 3),
               ("hash_res", C.c_float * 16), ("density_act", C.c_int32), ("feat_act", C.c_int32), ("bg", C.c_int32),
-              ("fourier_freqs", C.c_int32), ("deform", MlpDesc)]
+              ("fourier_freqs", C.c_int32), ("deform", MlpDesc), ("mip", C.c_int32), ("deform_enc", C.c_int32),
+              ("spline_points", C.c_int32)]
+
+class MipArgs(C.Structure):
+  _fields_ = [("radius", C.c_void_p), ("rays_all", C.c_void_p), ("radius_all", C.c_void_p), ("n_rays_all", C.c_int64),
+              ("ray_base", C.c_int64)]
 
 EXPORTS = {
   "nf_version": (C.c_int, []),
@@ -36,7 +42,8 @@ EXPORTS = {
   "nf_packed_bytes": (C.c_int64, [C.POINTER(ModelDesc)]),
   "nf_pack_weights": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
   "nf_render_forward": (C.c_int, [C.POINTER(ModelDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int64,
-                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+                                  C.c_void_p, C.c_void_p, C.POINTER(MipArgs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+  "nf_ray_radii": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
   "nf_sample_points": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
   "nf_hash_encode": (C.c_int, [C.POINTER(ModelDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
   "nf_composite": (C.c_int, [C.POINTER(ModelDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int64,

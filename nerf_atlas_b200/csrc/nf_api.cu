@@ -36,6 +36,7 @@ int nf_param_count(const nf_model_desc* desc) {
   int n = 0;
   for (int m = 0; m < p.n_mlps; ++m) n += 2 * p.mlp[m].n_lin;
   if (p.enc == NF_ENC_HASH) n += p.hash_levels;
+  if (p.kind == NF_KIND_DYN && p.deform_enc == NF_ENC_HASH) n += p.hash_levels;
   if (p.enc == NF_ENC_FOURIER) n += 1;
   if (p.density_act == NF_DENS_LAPLACE) n += 1;
   return n;
@@ -76,6 +77,15 @@ int nf_pack_weights(const nf_model_desc* desc, const float* const* params, int32
       if (e != cudaSuccess) return cuda_fail(e, "pack hash tables");
     }
   }
+  if (p.kind == NF_KIND_DYN && p.deform_enc == NF_ENC_HASH) {
+    const size_t per = (size_t)(p.hash_mask + 1) * 4 * sizeof(float);
+    for (int l = 0; l < p.hash_levels; ++l) {
+      const float* t = params[pi++];
+      if (!t) return fail(NF_E_BADARG, "nf_pack_weights: null deformation hash table");
+      cudaError_t e = cudaMemcpyAsync(base + p.hash2_off + l * per, t, per, cudaMemcpyDeviceToDevice, st);
+      if (e != cudaSuccess) return cuda_fail(e, "pack deformation hash tables");
+    }
+  }
   if (p.enc == NF_ENC_FOURIER) {
     const float* b = params[pi++];
     if (!b) return fail(NF_E_BADARG, "nf_pack_weights: null fourier basis");
@@ -93,16 +103,23 @@ int nf_pack_weights(const nf_model_desc* desc, const float* const* params, int32
 
 int nf_render_forward(const nf_model_desc* desc, const void* packed, const float* rays, int64_t n_rays,
                       const float* ts, int32_t T, int64_t ts_ray_stride, const float* density_noise, const float* ray_time,
-                      float* rgb_out, float* alpha_out, float* weights_out, int32_t precision, void* stream) {
+                      const nf_mip_args* mip, float* rgb_out, float* alpha_out, float* weights_out, int32_t precision, void* stream) {
   NfPlan p; if (int rc = plan_of(desc, &p)) return rc;
   if (n_rays < 0) return fail(NF_E_BADARG, "n_rays < 0");
   if (n_rays == 0) return 0;
   if (!packed || !rays || !ts || !rgb_out) return fail(NF_E_BADARG, "nf_render_forward: null pointer");
   if (int rc = check_ts(T, ts_ray_stride)) return rc;
   if (p.kind == NF_KIND_DYN && !ray_time) return fail(NF_E_BADARG, "nf_render_forward: ray_time is required for NF_KIND_DYN");
+  if (p.mip != NF_MIP_NONE) {
+    if (!mip || !mip->radius) return fail(NF_E_BADARG, "nf_render_forward: nf_mip_args with radii is required when desc.mip is set");
+    if (ts_ray_stride != 0) return fail(NF_E_UNSUPPORTED, "nf_render_forward: the Mip encoder needs a shared ts[T]");
+    if (p.mip == NF_MIP_CYLINDER_REF && (!mip->rays_all || !mip->radius_all || mip->ray_base < 0 || mip->ray_base + n_rays > mip->n_rays_all))
+      return fail(NF_E_BADARG, "nf_render_forward: NF_MIP_CYLINDER_REF needs the whole crop (rays_all, radius_all, n_rays_all, ray_base)");
+    if (precision != NF_PREC_FP32) return fail(NF_E_UNSUPPORTED, "the Mip encoder (x0 134/165 wide) runs on the fp32 pipeline only in this build");
+  }
   cudaError_t e;
   if (precision == NF_PREC_FP32)
-    e = nf_launch_render_fp32(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, ray_time, rgb_out, alpha_out, weights_out, (cudaStream_t)stream);
+    e = nf_launch_render_fp32(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, ray_time, mip, rgb_out, alpha_out, weights_out, (cudaStream_t)stream);
   else if (precision == NF_PREC_FP16_TC) {
     // NF_TC_PIPE selects the tensor pipeline: 3 (default) = staggered paired pipeline (nf_tc3.cu), 2 = lockstep paired
     // pipeline (nf_tc2.cu), 1 = single-CTA pipeline (nf_tc.cu); the older ones are kept for A/B timing.  NF_TC_PAIRED=0 == 1.
@@ -120,6 +137,15 @@ int nf_render_forward(const nf_model_desc* desc, const void* packed, const float
   else return fail(NF_E_BADARG, "unknown precision");
   if (e != cudaSuccess) return cuda_fail(e, "nf_render_forward");
   return 0;
+}
+
+int nf_ray_radii(const float* rays, int64_t B, int32_t H, int32_t W, float* radius_out, void* stream) {
+  if (B < 0 || H < 0 || W < 0) return fail(NF_E_BADARG, "nf_ray_radii: negative size");
+  if (B == 0 || W == 0 || H == 0) return 0;
+  if (H < 3) return fail(NF_E_UNSUPPORTED, "nf_ray_radii: needs H >= 3 (the reference's radii_x indexes row H-3)");
+  if (!rays || !radius_out) return fail(NF_E_BADARG, "nf_ray_radii: null pointer");
+  cudaError_t e = nf_launch_ray_radii(rays, B, H, W, radius_out, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nf_ray_radii");
 }
 
 int nf_sample_points(const float* rays, int64_t n_rays, const float* ts, int32_t T, int64_t ts_ray_stride, float* pts_out, void* stream) {

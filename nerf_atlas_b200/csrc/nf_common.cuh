@@ -10,6 +10,7 @@
 #define NF_HIDDEN 256
 #define NF_TC_ROWS 128         // samples per tensor-core tile (= UMMA M)
 #define NF_TC_CHUNK_K 64       // K columns per streamed weight chunk (4 UMMA K-steps; 32 KB at N=256 -- see profiles/microbench)
+#define NF_MIP_FEATS 96        // Mip IPE: 2 (sin, cos) x 16 degrees x 3 axes (reference src/utils.py:104-111, src/nerf.py:255)
 
 // ---- plan ---------------------------------------------------------------------
 struct NfLinPlan {
@@ -40,7 +41,9 @@ struct NfPlan {
   int64_t hash_off;     // byte offset: fp32 [levels][table][4]
   int64_t fourier_off;  // byte offset: fp32 basis [3][freqs]
   int64_t scale_off;    // byte offset: fp32 beta (VolSDF.scale)
-  int32_t fourier_freqs, pad3_;
+  int32_t fourier_freqs, mip;
+  int32_t deform_enc, spline_points;
+  int64_t hash2_off;    // byte offset: fp32 [levels][table][4], tables of the spline deformation MLP's own HashEncoder
   int64_t total_bytes;
   NfMlpPlan mlp[3];     // [0] density, [1] refl, [2] deformation (NF_KIND_DYN; executed first)
 };
@@ -56,6 +59,15 @@ static inline int nf_build_plan(const nf_model_desc* d, NfPlan* p, const char** 
   p->kind = d->kind; p->n_mlps = d->kind == NF_KIND_DYN ? 3 : d->kind == NF_KIND_PLAIN ? 2 : 1;
   p->intermediate = d->intermediate; p->enc = d->enc;
   p->density_act = d->density_act; p->feat_act = d->feat_act; p->bg = d->bg;
+  if (d->mip < NF_MIP_NONE || d->mip > NF_MIP_CYLINDER_REF) { *why = "unknown mip kind"; return NF_E_BADARG; }
+  if (d->mip != NF_MIP_NONE && d->kind == NF_KIND_TINY) { *why = "mip: not for NF_KIND_TINY"; return NF_E_UNSUPPORTED; }
+  p->mip = d->mip;
+  if (d->kind == NF_KIND_DYN) {
+    p->deform_enc = d->deform_enc; p->spline_points = d->spline_points;
+    if (d->spline_points == 0 ? d->deform_enc != NF_ENC_NONE : (d->deform_enc != NF_ENC_HASH || d->enc != NF_ENC_HASH)) {
+      *why = "dyn: direct deformation takes no encoder, the spline variant takes the hash encoder"; return NF_E_BADARG; }
+    if (d->spline_points != 0 && (d->spline_points < 2 || d->spline_points > 8)) { *why = "dyn: spline_points must be 0 or 2..8"; return NF_E_UNSUPPORTED; }
+  }
   if (d->enc == NF_ENC_HASH) {
     if (d->hash_feat != 4 || d->hash_levels < 1 || d->hash_levels > 16 ||
         (d->hash_table_size & (d->hash_table_size - 1)) != 0 || d->hash_table_size < 2) {
@@ -72,6 +84,7 @@ static inline int nf_build_plan(const nf_model_desc* d, NfPlan* p, const char** 
   auto take = [&](int64_t bytes) { int64_t o = off; off += (bytes + 1023) / 1024 * 1024; return o; };
   if (d->enc == NF_ENC_HASH) p->hash_off = take((int64_t)d->hash_levels * d->hash_table_size * 4 * sizeof(float));
   if (d->enc == NF_ENC_FOURIER) p->fourier_off = take((int64_t)3 * d->fourier_freqs * sizeof(float));
+  if (d->kind == NF_KIND_DYN && d->deform_enc == NF_ENC_HASH) p->hash2_off = take((int64_t)d->hash_levels * d->hash_table_size * 4 * sizeof(float));
   p->scale_off = take(sizeof(float));
   for (int m = 0; m < p->n_mlps; ++m) {
     const nf_mlp_desc& md = m == 0 ? d->density : m == 1 ? d->refl : d->deform;
@@ -100,11 +113,16 @@ static inline int nf_build_plan(const nf_model_desc* d, NfPlan* p, const char** 
       L.w16h_off = take((int64_t)k_tc * L.n_pad * sizeof(__half));
     }
   }
-  if (d->kind == NF_KIND_DYN && (d->deform.in_dims != 4 || d->deform.out_dims != 4)) { *why = "dyn: deformation MLP must map 4 -> 4"; return NF_E_BADARG; }
+  if (d->kind == NF_KIND_DYN) {
+    if (d->spline_points == 0 && (d->deform.in_dims != 4 || d->deform.out_dims != 4)) { *why = "dyn: direct deformation MLP must map 4 -> 4"; return NF_E_BADARG; }
+    if (d->spline_points != 0 && (d->deform.in_dims != 6 + d->hash_levels * 4 || d->deform.out_dims != 1 + 3 * d->spline_points)) {
+      *why = "dyn: spline deformation MLP must map [p, hash(p)] -> 1 + 3n"; return NF_E_BADARG; }
+  }
   if (d->kind == NF_KIND_PLAIN || d->kind == NF_KIND_DYN) {
+    const int ml = d->mip != NF_MIP_NONE ? NF_MIP_FEATS : 0;
     if (d->density.out_dims != 1 + d->intermediate) { *why = "density MLP out must be 1+intermediate"; return NF_E_BADARG; }
-    if (d->refl.in_dims != 5 + d->intermediate || d->refl.out_dims != 3) { *why = "refl MLP must map 5+intermediate -> 3"; return NF_E_BADARG; }
-    const int want = d->enc == NF_ENC_HASH ? 6 + d->hash_levels * 4 : d->enc == NF_ENC_FOURIER ? 3 + 2 * d->fourier_freqs : 3;
+    if (d->refl.in_dims != 5 + ml + d->intermediate || d->refl.out_dims != 3) { *why = "refl MLP must map 5(+96 mip)+intermediate -> 3"; return NF_E_BADARG; }
+    const int want = (d->enc == NF_ENC_HASH ? 6 + d->hash_levels * 4 : d->enc == NF_ENC_FOURIER ? 3 + 2 * d->fourier_freqs : 3) + ml;
     if (d->density.in_dims != want) { *why = "density MLP in_dims does not match the encoder"; return NF_E_BADARG; }
   } else {
     if (d->density.in_dims != 3 || d->density.out_dims != 4 || d->enc != NF_ENC_NONE) { *why = "tiny: density MLP must map 3 -> 4 without encoder"; return NF_E_BADARG; }
@@ -222,6 +240,88 @@ __device__ __forceinline__ float4 nf_hash_level(const float4* __restrict__ table
     for (int c = 0; c < 8; ++c) idx8[c] = id[c];
   }
   return s;
+}
+
+// ---- Mip IPE, reference src/nerf.py:257-261, src/utils.py:22-27,39-48,60-101 ---------------------------------
+struct NfMipIn {
+  int mode;                    // enum nf_mip
+  const float* ts; int T;      // shared ts[T]
+  const float* rays; const float* radius;            // this call's rays [R,6] / radii [R]
+  const float* rays_all; const float* radius_all;    // NF_MIP_CYLINDER_REF: the whole crop
+  long long n_rays_all, ray_base;
+};
+// segment [t0, t1] of sample t: the reference appends 1e10 (nerf.py:258); the intended encoder repeats the last spacing
+__device__ __forceinline__ void nf_mip_segment(const NfMipIn& m, int t, float& t0, float& t1) {
+  t0 = __ldg(m.ts + t);
+  if (t + 1 < m.T) t1 = __ldg(m.ts + t + 1);
+  else if (m.mode == NF_MIP_CYLINDER_REF) t1 = 1e10f;
+  else t1 = m.T > 1 ? __fadd_rn(t0, __fsub_rn(t0, __ldg(m.ts + t - 1))) : t0;
+}
+// (t_mean, t_var, r_var) of a segment: cylinder utils.py:95-101, cone utils.py:83-93 (operation order as written there)
+__device__ __forceinline__ void nf_mip_moments(int mode, float t0, float t1, float rad, float& t_mean, float& t_var, float& r_var) {
+  if (mode == NF_MIP_CONE) {
+    const float mu = __fdiv_rn(__fadd_rn(t1, t0), 2.f), hw = __fdiv_rn(__fsub_rn(t1, t0), 2.f);
+    const float mu2 = __fmul_rn(mu, mu), hw2 = __fmul_rn(hw, hw), hw4 = __fmul_rn(hw2, hw2);
+    const float den = __fadd_rn(__fmul_rn(3.f, mu2), hw2);
+    t_mean = __fadd_rn(mu, __fdiv_rn(__fmul_rn(__fmul_rn(2.f, mu), hw2), den));
+    t_var = __fsub_rn(__fdiv_rn(hw, 3.f), __fmul_rn(4.f / 15.f, __fdiv_rn(__fmul_rn(hw4, __fsub_rn(__fmul_rn(12.f, mu2), hw2)), __fmul_rn(den, den))));
+    r_var = __fmul_rn(__fmul_rn(rad, rad), __fsub_rn(__fadd_rn(__fdiv_rn(mu2, 4.f), __fmul_rn(5.f / 12.f, hw2)), __fdiv_rn(__fmul_rn(4.f / 15.f, hw4), den)));
+  } else {
+    t_mean = __fdiv_rn(__fadd_rn(t1, t0), 2.f);
+    const float d = __fsub_rn(t1, t0);
+    t_var = __fdiv_rn(__fmul_rn(d, d), 12.f);
+    r_var = __fdiv_rn(__fmul_rn(rad, rad), 4.f);
+  }
+}
+// diagonal covariance entry `x` of the lifted Gaussian (lift_gaussian, utils.py:60-73)
+__device__ __forceinline__ float nf_mip_cov(const float* __restrict__ ray6, int x, float t_var, float r_var) {
+  const float dx = __ldg(ray6 + 3), dy = __ldg(ray6 + 4), dz = __ldg(ray6 + 5);
+  const float magn = fmaxf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)), 1e-10f);
+  const float d = x == 0 ? dx : x == 1 ? dy : dz;
+  const float od = __fmul_rn(d, d);
+  return __fadd_rn(__fmul_rn(t_var, od), __fmul_rn(r_var, __fsub_rn(1.f, __fdiv_rn(od, magn))));
+}
+// feature c (0..95) of sample t of local ray `ray`: [ (k, xyz) sin | (k, xyz) sin(. + pi/2) ]
+__device__ __forceinline__ float nf_mip_feature(const NfMipIn& m, long long ray, int t, int c) {
+  const int cc = c >= 48 ? c - 48 : c, k = cc / 3, x = cc - 3 * k;
+  float t0, t1, t_mean, t_var, r_var;
+  nf_mip_segment(m, t, t0, t1);
+  nf_mip_moments(m.mode, t0, t1, __ldg(m.radius + ray), t_mean, t_var, r_var);
+  const float* r6 = m.rays + ray * 6;
+  float y = __fmul_rn(__fadd_rn(__fmul_rn(__ldg(r6 + 3 + x), t_mean), __ldg(r6 + x)), (float)(1 << k));
+  if (c >= 48) y = __fadd_rn(y, 1.5707963267948966f);
+  float cov; int kv = k;
+  if (m.mode == NF_MIP_CYLINDER_REF) {
+    // the reference's layout: same flat index in [xyz, ray, k, t] as (t, ray, c) has in [t, ray, 48]
+    long long flat = ((long long)t * m.n_rays_all + (m.ray_base + ray)) * 48 + cc;
+    const int tv = (int)(flat % m.T); flat /= m.T;
+    kv = (int)(flat & 15); flat >>= 4;
+    const long long rv = flat % m.n_rays_all; const int xv = (int)(flat / m.n_rays_all);
+    float a0, a1, tm, tvv, rvv;
+    nf_mip_segment(m, tv, a0, a1);
+    nf_mip_moments(m.mode, a0, a1, __ldg(m.radius_all + rv), tm, tvv, rvv);
+    cov = nf_mip_cov(m.rays_all + rv * 6, xv, tvv, rvv);
+  } else {
+    cov = nf_mip_cov(r6, x, t_var, r_var);
+  }
+  const float yv = __fmul_rn(cov, (float)(1u << (2 * kv)));
+  return __fmul_rn(expf(__fmul_rn(-0.5f, yv)), sinf(y));
+}
+
+// ---- Bezier spline of the deformation, reference src/nerf.py:1173-1178 (de_casteljau), 1201-1206 (cubic_bezier) ----
+// ps[i] = control point i (one coordinate), n points, parameter t
+__device__ __forceinline__ float nf_bezier(const float* ps, int n, float t) {
+  const float m1t = __fsub_rn(1.f, t);
+  if (n == 4) {
+    const float m2 = __fmul_rn(m1t, m1t), t2 = __fmul_rn(t, t);
+    const float k0 = __fmul_rn(m2, m1t), k1 = __fmul_rn(__fmul_rn(3.f, m2), t), k2 = __fmul_rn(__fmul_rn(3.f, t2), m1t), k3 = __fmul_rn(t2, t);
+    return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(k0, ps[0]), __fmul_rn(k1, ps[1])), __fmul_rn(k2, ps[2])), __fmul_rn(k3, ps[3]));
+  }
+  float b[8];
+  for (int i = 0; i < n; ++i) b[i] = ps[i];
+  for (int i = 1; i < n; ++i)
+    for (int j = 0; j < n - i; ++j) b[j] = __fadd_rn(__fmul_rn(b[j], m1t), __fmul_rn(b[j + 1], t));
+  return b[0];
 }
 
 // ---- compositing step, reference src/nerf.py:60-73 -----------------------------------------

@@ -15,6 +15,7 @@ struct Fp32Smem {
   float H[2][NF_HIDDEN * ROWS];   // [k][row], ping-pong between layers
   float X0[X0_MAX * ROWS];        // [k][row], raw inputs of the current MLP
   float P[3 * ROWS];              // sample positions
+  float M[NF_MIP_FEATS * ROWS];   // Mip IPE latent of the tile (appended to both MLP inputs)
   float sig[ROWS];                // raw density
   float carry[8];                 // T > ROWS: transmittance, rgb, sum w (before last) carried across sub-tiles
   long long ray[ROWS];
@@ -87,6 +88,7 @@ struct RenderArgs {
   const float* ts; int T; long long ts_stride;
   const float* noise; const float* ray_time;
   float* rgb_out; float* alpha_out; float* weights_out;
+  NfMipIn mip;
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -117,21 +119,49 @@ k_render_fp32(const __grid_constant__ NfPlan plan, const RenderArgs a) {
       }
       __syncthreads();
       if (plan.kind == NF_KIND_DYN) {
-        // ---- stage 0b: deformation (reference nerf.py:1261-1266,1292-1303): delta_estim([p, t]) -> (dp[1], rigidity[3]);
-        //      p' = p + dp * sigmoid(rigidity / 2)
-        if (tid < ROWS) {
-          const int row = tid;
-          s.X0[0 * ROWS + row] = s.P[row]; s.X0[1 * ROWS + row] = s.P[ROWS + row]; s.X0[2 * ROWS + row] = s.P[2 * ROWS + row];
-          s.X0[3 * ROWS + row] = s.valid[row] ? __ldg(a.ray_time + s.ray[row]) : 0.f;
+        // ---- stage 0b: deformation (reference nerf.py:1261-1278,1292-1303)
+        //   direct: delta_estim([p, t]) -> (dp[1], rigidity[3]);                       p' = p + dp * sigmoid(rigidity / 2)
+        //   spline: delta_estim([p, hash(p)]) -> (rigidity[1], n control points[3]);    p' = p + Bezier(points, t) * sigmoid(rigidity / 2)
+        if (plan.spline_points == 0) {
+          if (tid < ROWS) {
+            const int row = tid;
+            s.X0[0 * ROWS + row] = s.P[row]; s.X0[1 * ROWS + row] = s.P[ROWS + row]; s.X0[2 * ROWS + row] = s.P[2 * ROWS + row];
+            s.X0[3 * ROWS + row] = s.valid[row] ? __ldg(a.ray_time + s.ray[row]) : 0.f;
+          }
+        } else {
+          const int row = tid % ROWS, part = tid / ROWS;
+          const float px = s.P[row], py = s.P[ROWS + row], pz = s.P[2 * ROWS + row];
+          if (part == 0) {
+            s.X0[0 * ROWS + row] = px; s.X0[1 * ROWS + row] = py; s.X0[2 * ROWS + row] = pz;
+            s.X0[3 * ROWS + row] = px; s.X0[4 * ROWS + row] = py; s.X0[5 * ROWS + row] = pz;
+          }
+          const float4* tables = reinterpret_cast<const float4*>(a.packed + plan.hash2_off);
+          for (int lvl = part; lvl < plan.hash_levels; lvl += THREADS / ROWS) {
+            const float4 f = nf_hash_level(tables + (size_t)lvl * (plan.hash_mask + 1), px, py, pz, plan.hash_res[lvl],
+                                           plan.hash_primes[0], plan.hash_primes[1], plan.hash_primes[2], plan.hash_mask, nullptr);
+            float* x = s.X0 + (6 + lvl * 4) * ROWS + row;
+            x[0] = f.x; x[ROWS] = f.y; x[2 * ROWS] = f.z; x[3 * ROWS] = f.w;
+          }
         }
         __syncthreads();
         const int ob = mlp_fp32(plan.mlp[2], a.packed, s);
         if (tid < ROWS) {
           const float* O = s.H[ob]; const int row = tid;
-          const float dp = O[row];
-          s.P[row] += dp * nf_sigmoid(O[1 * ROWS + row] / 2.f);
-          s.P[ROWS + row] += dp * nf_sigmoid(O[2 * ROWS + row] / 2.f);
-          s.P[2 * ROWS + row] += dp * nf_sigmoid(O[3 * ROWS + row] / 2.f);
+          if (plan.spline_points == 0) {
+            const float dp = O[row];
+            s.P[row] += dp * nf_sigmoid(O[1 * ROWS + row] / 2.f);
+            s.P[ROWS + row] += dp * nf_sigmoid(O[2 * ROWS + row] / 2.f);
+            s.P[2 * ROWS + row] += dp * nf_sigmoid(O[3 * ROWS + row] / 2.f);
+          } else {
+            const int n = plan.spline_points;
+            const float rig = nf_sigmoid(O[row] / 2.f);
+            const float tt = s.valid[row] ? __ldg(a.ray_time + s.ray[row]) : 0.f;
+            for (int x = 0; x < 3; ++x) {
+              float ps[8];
+              for (int i = 0; i < n; ++i) ps[i] = O[(1 + 3 * i + x) * ROWS + row];
+              s.P[x * ROWS + row] += nf_bezier(ps, n, tt) * rig;
+            }
+          }
         }
         __syncthreads();
       }
@@ -161,6 +191,14 @@ k_render_fp32(const __grid_constant__ NfPlan plan, const RenderArgs a) {
             x[0] = f.x; x[ROWS] = f.y; x[2 * ROWS] = f.z; x[3 * ROWS] = f.w;
           }
         }
+        if (plan.mip != NF_MIP_NONE) {
+          // Mip IPE of the UNdeformed ray segment (nerf.py:340: mip_encoding(r_o, r_d, ts)), kept in s.M for the View head
+          const int base = plan.mlp[0].in_dims - NF_MIP_FEATS;
+          for (int c = part; c < NF_MIP_FEATS; c += THREADS / ROWS) {
+            const float f = s.valid[row] ? nf_mip_feature(a.mip, s.ray[row], s.t[row], c) : 0.f;
+            s.M[c * ROWS + row] = f; s.X0[(base + c) * ROWS + row] = f;
+          }
+        }
       }
       __syncthreads();
       // ---- stage 1: density MLP
@@ -177,7 +215,9 @@ k_render_fp32(const __grid_constant__ NfPlan plan, const RenderArgs a) {
           s.X0[0 * ROWS + row] = s.P[row]; s.X0[1 * ROWS + row] = s.P[ROWS + row]; s.X0[2 * ROWS + row] = s.P[2 * ROWS + row];
           s.X0[3 * ROWS + row] = el; s.X0[4 * ROWS + row] = az;
         }
-        for (int i = tid; i < plan.intermediate * ROWS; i += THREADS) s.X0[5 * ROWS + i] = O[ROWS + i];
+        const int ml = plan.mip != NF_MIP_NONE ? NF_MIP_FEATS : 0;
+        for (int i = tid; i < ml * ROWS; i += THREADS) s.X0[5 * ROWS + i] = s.M[i];
+        for (int i = tid; i < plan.intermediate * ROWS; i += THREADS) s.X0[(5 + ml) * ROWS + i] = O[ROWS + i];
         __syncthreads();
         // ---- stage 2: View MLP
         ob = mlp_fp32(plan.mlp[1], a.packed, s);
@@ -389,6 +429,20 @@ __global__ void k_sample_pdf(const float* __restrict__ ts, int T, const float* _
   }
 }
 
+// radii_x, reference src/utils.py:77-81: one thread per ray of the [B,H,W] crop
+__global__ void k_ray_radii(const float* __restrict__ rays, long long B, int H, int W, float* __restrict__ out) {
+  const long long total = B * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W); const int h = (int)((i / W) % H); const long long b = i / ((long long)W * H);
+    const int hd = h < H - 1 ? h : H - 3;              // cat([dx, dx[:, -2:-1, :]]): the last row repeats difference H-3
+    const float* r0 = rays + ((b * H + hd) * W + w) * 6 + 3;
+    const float* r1 = r0 + (long long)W * 6;
+    const float dx = __fsub_rn(__ldg(r0), __ldg(r1)), dy = __fsub_rn(__ldg(r0 + 1), __ldg(r1 + 1)), dz = __fsub_rn(__ldg(r0 + 2), __ldg(r1 + 2));
+    const float d = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    out[i] = __fdiv_rn(__fmul_rn(d, 2.f), 3.4641016151377544f);
+  }
+}
+
 // ---- packing -----------------------------------------------------------------------------------
 // W[n][k] (nn.Linear, row-major) -> Wt[k][n_pad] fp32, zero padded.
 __global__ void k_pack_fp32(const float* __restrict__ W, const float* __restrict__ b, float* __restrict__ Wt,
@@ -417,9 +471,18 @@ cudaError_t nf_launch_pack_fp32(const float* W, const float* b, float* Wt, float
   return cudaGetLastError();
 }
 
+cudaError_t nf_launch_ray_radii(const float* rays, int64_t B, int H, int W, float* out, cudaStream_t st) {
+  const long long total = B * H * W;
+  if (total == 0) return cudaSuccess;
+  const long long want = (total + 255) / 256;
+  const int grid = (int)(want < (long long)num_sms() * 8 ? want : (long long)num_sms() * 8);
+  k_ray_radii<<<grid, 256, 0, st>>>(rays, B, H, W, out);
+  return cudaGetLastError();
+}
+
 cudaError_t nf_launch_render_fp32(const NfPlan& plan, const void* packed, const float* rays, int64_t n_rays, const float* ts,
-                                  int T, int64_t ts_stride, const float* noise, const float* ray_time, float* rgb, float* alpha, float* weights,
-                                  cudaStream_t st) {
+                                  int T, int64_t ts_stride, const float* noise, const float* ray_time, const nf_mip_args* mip,
+                                  float* rgb, float* alpha, float* weights, cudaStream_t st) {
   static_assert(sizeof(Fp32Smem) <= 227 * 1024, "fp32 pipeline smem");
   cudaError_t e = cudaFuncSetAttribute(k_render_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Fp32Smem));
   if (e != cudaSuccess) return e;
@@ -427,7 +490,13 @@ cudaError_t nf_launch_render_fp32(const NfPlan& plan, const void* packed, const 
   const long long units = map.units(n_rays);
   if (units == 0) return cudaSuccess;
   const int grid = (int)(units < num_sms() ? units : num_sms());
-  RenderArgs a{(const uint8_t*)packed, rays, n_rays, ts, T, ts_stride, noise, ray_time, rgb, alpha, weights};
+  RenderArgs a{(const uint8_t*)packed, rays, n_rays, ts, T, ts_stride, noise, ray_time, rgb, alpha, weights, NfMipIn{}};
+  if (plan.mip != NF_MIP_NONE) {
+    if (!mip || !mip->radius || ts_stride != 0) return cudaErrorInvalidValue;
+    a.mip = NfMipIn{plan.mip, ts, T, rays, mip->radius, mip->rays_all, mip->radius_all, (long long)mip->n_rays_all, (long long)mip->ray_base};
+    if (plan.mip == NF_MIP_CYLINDER_REF && (!mip->rays_all || !mip->radius_all || mip->ray_base < 0 || mip->ray_base + n_rays > mip->n_rays_all))
+      return cudaErrorInvalidValue;
+  }
   k_render_fp32<<<grid, THREADS, sizeof(Fp32Smem), st>>>(plan, a);
   return cudaGetLastError();
 }

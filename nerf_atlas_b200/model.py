@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import ModelDesc, MlpDesc
+from ._lib import ModelDesc, MlpDesc, MipArgs
 
 HASH_PRIMES = [1, 2654435761, 805459861, 3674653429, 2097192037, 1434869437, 2165219737]
 
@@ -41,15 +41,21 @@ def _mlp(in_dims, n_layers, out_dims, act, skip=3, hidden=256) -> MlpDesc:
   return MlpDesc(in_dims, hidden, n_layers, out_dims, skip, _lib.ACT[act])
 
 
+MIP_FEATS = 96   # 2 x 16 degrees x 3 axes (reference src/utils.py:104-111, src/nerf.py:255)
+
+
 def describe_plain(intermediate: int = 64, sigmoid: str = "upshifted", bg: str = "black",
-                   hash_levels: int = 8, hash_table: int = 1 << 16) -> ModelDesc:
+                   hash_levels: int = 8, hash_table: int = 1 << 16, mip: Optional[str] = None) -> ModelDesc:
   """PlainNeRF + View head as built by runner.load_model (reference src/nerf.py:310-324,
-  src/refl.py:190-204, runner.py:1182-1183)."""
+  src/refl.py:190-204, runner.py:1182-1183).  ``mip`` in (None, "cylinder", "cone", "cylinder_ref"): the IPE latent
+  widens both MLP inputs by 96 (nerf.py:255,311-324)."""
   d = ModelDesc()
   d.struct_bytes = C.sizeof(ModelDesc)
   d.kind = _lib.KIND["plain"]
-  d.density = _mlp(6 + 4 * hash_levels, 4, 1 + intermediate, "leaky_relu")
-  d.refl = _mlp(5 + intermediate, 4, 3, "sin")
+  d.mip = _lib.MIP[mip]
+  ml = MIP_FEATS if d.mip else 0
+  d.density = _mlp(6 + 4 * hash_levels + ml, 4, 1 + intermediate, "leaky_relu")
+  d.refl = _mlp(5 + ml + intermediate, 4, 3, "sin")
   d.intermediate = intermediate
   d.enc = _lib.ENC["hash"]
   d.hash_levels, d.hash_table_size, d.hash_feat = hash_levels, hash_table, 4
@@ -81,11 +87,17 @@ def describe_volsdf(sdf_kind: str = "siren", intermediate: int = 64, sigmoid: st
   return d
 
 
-def describe_dyn(intermediate: int = 64, sigmoid: str = "upshifted", bg: str = "black") -> ModelDesc:
-  """DynamicNeRF with the direct deformation MLP over a canonical PlainNeRF (reference src/nerf.py:1209-1303)."""
+def describe_dyn(intermediate: int = 64, sigmoid: str = "upshifted", bg: str = "black", spline: int = 0) -> ModelDesc:
+  """DynamicNeRF over a canonical PlainNeRF (reference src/nerf.py:1209-1303): ``spline == 0`` the direct deformation MLP
+  (set_delta_estim, 1226-1241), ``spline == n > 1`` the hash-encoded MLP predicting n Bezier control points
+  (set_spline_estim, 1242-1260)."""
   d = describe_plain(intermediate, sigmoid, bg)
   d.kind = _lib.KIND["dyn"]
-  d.deform = _mlp(4, 5, 4, "leaky_relu")
+  d.spline_points = spline
+  if spline:
+    d.deform = _mlp(6 + 4 * d.hash_levels, 5, 1 + 3 * spline, "leaky_relu"); d.deform_enc = _lib.ENC["hash"]
+  else:
+    d.deform = _mlp(4, 5, 4, "leaky_relu"); d.deform_enc = _lib.ENC["none"]
   return d
 
 
@@ -157,9 +169,23 @@ class RenderEngine:
   def _need_packed(self):
     if self.packed is None: raise RuntimeError("RenderEngine.pack(params) has not been called")
 
+  def ray_radii(self, rays_bhw: torch.Tensor) -> torch.Tensor:
+    """radii_x (reference src/utils.py:77-81) of a crop rays[B,H,W,6] -> [B,H,W]."""
+    _chk(rays_bhw, "rays")
+    if rays_bhw.dim() != 4 or rays_bhw.shape[-1] != 6: raise ValueError("rays must be [B,H,W,6]")
+    B, H, W, _ = rays_bhw.shape
+    out = torch.empty(B, H, W, dtype=torch.float32, device=rays_bhw.device)
+    with torch.cuda.device(rays_bhw.device):
+      rc = self.lib.nf_ray_radii(_ptr(rays_bhw), B, H, W, _ptr(out), self._stream())
+    _lib.check(rc, "nf_ray_radii")
+    return out
+
   def render(self, rays: torch.Tensor, ts: torch.Tensor, density_noise: Optional[torch.Tensor] = None,
-             want_weights: bool = True, precision: Optional[str] = None, ray_time: Optional[torch.Tensor] = None):
-    """rays[R,6], ts[T] (shared) or ts[R,T] (per ray) -> rgb[R,3], alpha[R,T]|None, weights[R,T]|None."""
+             want_weights: bool = True, precision: Optional[str] = None, ray_time: Optional[torch.Tensor] = None,
+             radius: Optional[torch.Tensor] = None, crop: Optional[tuple] = None):
+    """rays[R,6], ts[T] (shared) or ts[R,T] (per ray) -> rgb[R,3], alpha[R,T]|None, weights[R,T]|None.
+    Mip models: ``radius[R]`` (``ray_radii``); "cylinder_ref" also takes ``crop = (rays_all[R_all,6], radius_all[R_all],
+    ray_base)`` when ``rays`` is a shard of a larger crop (default: the call's rays are the whole crop)."""
     self._need_packed()
     _chk(rays, "rays"); _chk(ts, "ts")
     if rays.dim() != 2 or rays.shape[1] != 6: raise ValueError("rays must be [R,6]")
@@ -176,9 +202,18 @@ class RenderEngine:
     rgb = torch.empty(R, 3, dtype=torch.float32, device=rays.device)
     alpha = torch.empty(R, T, dtype=torch.float32, device=rays.device) if want_weights else None
     weights = torch.empty(R, T, dtype=torch.float32, device=rays.device) if want_weights else None
+    mip = None
+    if self.desc.mip:
+      if radius is None: raise ValueError("this model has a Mip encoder: pass radius[R] (RenderEngine.ray_radii)")
+      _chk(radius, "radius")
+      if radius.numel() != R: raise ValueError("radius must be [R]")
+      rays_all, radius_all, base = crop if crop is not None else (rays, radius, 0)
+      _chk(rays_all, "rays_all"); _chk(radius_all, "radius_all")
+      mip = MipArgs(radius.data_ptr(), rays_all.data_ptr(), radius_all.data_ptr(), rays_all.shape[0], base)
     with torch.cuda.device(rays.device):
       rc = self.lib.nf_render_forward(C.byref(self.desc), _ptr(self.packed), _ptr(rays), R, _ptr(ts), T, stride,
-                                      _ptr(density_noise), _ptr(ray_time), _ptr(rgb), _ptr(alpha), _ptr(weights),
+                                      _ptr(density_noise), _ptr(ray_time), C.byref(mip) if mip is not None else None,
+                                      _ptr(rgb), _ptr(alpha), _ptr(weights),
                                       _lib.PRECISION[precision or self.precision], self._stream())
     _lib.check(rc, "nf_render_forward")
     return rgb, alpha, weights
@@ -325,8 +360,18 @@ class FusedNeRF(nn.Module):
                sigmoid_kind: str = "thin", bg: str = "black", precision: str = "fp16", keep_weights: bool = True,
                **unused):
     super().__init__()
-    for k in ("mip", "per_pixel_latent_size", "per_point_latent_size", "instance_latent_size"):
+    for k in ("per_pixel_latent_size", "per_point_latent_size", "instance_latent_size"):
       if unused.get(k): raise NotImplementedError(f"{k} is not supported by the fused path yet")
+    # mip: None | "cylinder" | "cone" (the encoder as intended) | "cylinder_ref" (the reference's CylinderGaussian bug for
+    # bug); an instance of the reference's utils.CylinderGaussian maps to "cylinder_ref" (reference src/utils.py:103-140)
+    mip = unused.get("mip")
+    if mip is not None and not isinstance(mip, str):
+      name = type(mip).__name__
+      if name == "CylinderGaussian": mip = "cylinder_ref"
+      elif name == "ConicGaussian": raise NotImplementedError("the reference's ConicGaussian renders NaN (SURVEY.md a-4); use mip='cone'")
+      else: raise NotImplementedError(f"mip encoder {name}")
+    if mip not in _lib.MIP: raise NotImplementedError(f"mip kind {mip!r}")
+    self.mip = mip
     self.empty_latent = nn.Parameter(torch.zeros(1, 1, 1, 1, 0, dtype=torch.float), requires_grad=False)
     self.t_near, self.t_far, self.steps = t_near, t_far, steps
     self.intermediate_size = intermediate_size
@@ -340,7 +385,8 @@ class FusedNeRF(nn.Module):
   # ---- surface the runner touches ----
   @property
   def nerf(self): return self
-  def total_latent_size(self) -> int: return 0
+  def mip_size(self) -> int: return MIP_FEATS if _lib.MIP[getattr(self, "mip", None)] else 0
+  def total_latent_size(self) -> int: return self.mip_size()
   def set_bg(self, bg="black"):
     if bg not in _lib.BG: raise NotImplementedError(bg)
     self.bg = bg
@@ -362,7 +408,8 @@ class FusedNeRF(nn.Module):
   def _param_list(self) -> List[torch.Tensor]: raise NotImplementedError
 
   def engine(self) -> RenderEngine:
-    key = (self.kind, self.sigmoid_kind if not hasattr(self, "refl") else _sigmoid_name(self.refl.act), self.bg, self.precision)
+    key = (self.kind, self.sigmoid_kind if not hasattr(self, "refl") else _sigmoid_name(self.refl.act), self.bg, self.precision,
+           getattr(self, "mip", None))
     if self._engine is None or self._engine_key != key:
       self._engine, self._engine_key = RenderEngine(self._describe(), self.precision), key
     return self._engine
@@ -385,7 +432,11 @@ class FusedNeRF(nn.Module):
         noise = torch.randn(flat.shape[0], self.steps, device=rays.device) * self.noise_std
     eng = self.engine()
     eng.pack(self._param_list())
-    rgb, alpha, weights = eng.render(flat, ts, noise, want_weights=self.keep_weights)
+    radius = None
+    if self.mip_size():
+      if rays.dim() != 4: raise ValueError("a Mip model needs rays[B,H,W,6]: the pixel radius differences neighbouring rows (utils.py:77-81)")
+      radius = eng.ray_radii(rays.to(torch.float32).contiguous()).reshape(-1)
+    rgb, alpha, weights = eng.render(flat, ts, noise, want_weights=self.keep_weights, radius=radius)
     self.ts = ts
     if self.keep_weights:   # the reference keeps [T,B,H,W]; these are transposed views of the [R,T] buffers
       self.alpha = alpha.reshape(*B, self.steps).movedim(-1, 0)
@@ -401,8 +452,8 @@ class FusedPlainNeRF(FusedNeRF):
     kwargs.setdefault("sigmoid_kind", "thin")
     super().__init__(**kwargs)
     if out_features != 3: raise NotImplementedError("out_features != 3")
-    self.refl = ViewHead(latent_size=self.intermediate_size, out_features=out_features, act=self.sigmoid_kind)
-    self.first = SkipConnParams(38, 1 + self.intermediate_size, 4, enc=HashParams())
+    self.refl = ViewHead(latent_size=self.mip_size() + self.intermediate_size, out_features=out_features, act=self.sigmoid_kind)
+    self.first = SkipConnParams(38 + self.mip_size(), 1 + self.intermediate_size, 4, enc=HashParams())
 
   @classmethod
   def from_reference(cls, ref, precision: str = "fp16", keep_weights: bool = True) -> "FusedPlainNeRF":
@@ -410,19 +461,20 @@ class FusedPlainNeRF(FusedNeRF):
     parameters (and optimiser references to them) are shared, not copied."""
     self = cls.__new__(cls)
     FusedNeRF.__init__(self, steps=ref.steps, t_near=ref.t_near, t_far=ref.t_far, intermediate_size=ref.intermediate_size,
-                       sigmoid_kind=_sigmoid_name(ref.refl.act), precision=precision, keep_weights=keep_weights)
+                       sigmoid_kind=_sigmoid_name(ref.refl.act), precision=precision, keep_weights=keep_weights,
+                       mip=getattr(ref, "mip", None))
     bg = [k for k, v in {"black": "black", "white": "white"}.items() if getattr(ref.sky_color, "__name__", "") == v]
     if not bg: raise NotImplementedError("background kind of the reference model")
     self.bg = bg[0]
     if type(ref.refl).__name__ not in ("View", "ViewHead"): raise NotImplementedError(f"refl head {type(ref.refl).__name__}")
-    if getattr(ref, "mip", None) is not None: raise NotImplementedError("mip")
     self.refl, self.first = ref.refl, ref.first
     return self
 
   def _describe(self) -> ModelDesc:
     enc = self.first.enc
     levels = len(enc.embs)
-    return describe_plain(self.intermediate_size, _sigmoid_name(self.refl.act), self.bg, levels, enc.embs[0].weight.shape[0])
+    return describe_plain(self.intermediate_size, _sigmoid_name(self.refl.act), self.bg, levels, enc.embs[0].weight.shape[0],
+                          mip=getattr(self, "mip", None))
 
   def _param_list(self) -> List[torch.Tensor]:
     ps: List[torch.Tensor] = []
@@ -508,23 +560,28 @@ class FusedVolSDF(FusedNeRF):
 
 
 class FusedDynamicNeRF(nn.Module):
-  """Drop-in for DynamicNeRF with the direct deformation MLP (reference src/nerf.py:1209-1303) over a canonical
-  FusedPlainNeRF: `model((rays[B,H,W,6], times[B])) -> rgb[B,H,W,3]`.  State-dict names follow the reference
-  (`delta_estim.*`, `canonical.*`).  The spline variant and `refl_latent > 0` are not built."""
+  """Drop-in for DynamicNeRF (reference src/nerf.py:1209-1303) over a canonical FusedPlainNeRF:
+  `model((rays[B,H,W,6], times[B])) -> rgb[B,H,W,3]`; `spline == 0`: the direct deformation MLP, `spline == n`: n Bezier
+  control points from a hash-encoded MLP.  State-dict names follow the reference (`delta_estim.*`, `canonical.*`).
+  `refl_latent > 0` is not built."""
 
   def __init__(self, canonical: FusedPlainNeRF, spline: int = 0, refl_latent: int = 0):
     super().__init__()
-    if spline or refl_latent: raise NotImplementedError("spline / refl_latent variants of DynamicNeRF")
+    if refl_latent: raise NotImplementedError("refl_latent variant of DynamicNeRF")
+    if spline and not 2 <= spline <= 8: raise NotImplementedError("spline points must be in 2..8")
     self.canonical = canonical
-    self.delta_estim = SkipConnParams(4, 4, 5, init="xavier")
+    self.spline = spline
+    if spline: self.delta_estim = SkipConnParams(38, 1 + 3 * spline, 5, init="xavier", enc=HashParams())
+    else: self.delta_estim = SkipConnParams(4, 4, 5, init="xavier")
     nn.init.zeros_(self.delta_estim.out.weight); nn.init.zeros_(self.delta_estim.out.bias)   # zero_last_layer(), nerf.py:1239
     self._engine: Optional[RenderEngine] = None
     self._engine_key = None
 
   @classmethod
   def from_reference(cls, ref, precision: str = "fp32") -> "FusedDynamicNeRF":
-    if getattr(ref, "spline", 0): raise NotImplementedError("spline DynamicNeRF")
+    if getattr(ref, "refl_latent", 0): raise NotImplementedError("refl_latent variant of DynamicNeRF")
     self = cls.__new__(cls); nn.Module.__init__(self)
+    self.spline = int(getattr(ref, "spline", 0))
     self.canonical = FusedPlainNeRF.from_reference(ref.canonical, precision=precision)
     self.delta_estim = ref.delta_estim
     self._engine = None; self._engine_key = None
@@ -545,9 +602,9 @@ class FusedDynamicNeRF(nn.Module):
 
   def engine(self) -> RenderEngine:
     c = self.canonical
-    key = (_sigmoid_name(c.refl.act), c.bg, c.precision)
+    key = (_sigmoid_name(c.refl.act), c.bg, c.precision, self.spline)
     if self._engine is None or self._engine_key != key:
-      self._engine = RenderEngine(describe_dyn(c.intermediate_size, key[0], c.bg), c.precision); self._engine_key = key
+      self._engine = RenderEngine(describe_dyn(c.intermediate_size, key[0], c.bg, self.spline), c.precision); self._engine_key = key
     return self._engine
 
   def _param_list(self) -> List[torch.Tensor]:
@@ -556,6 +613,7 @@ class FusedDynamicNeRF(nn.Module):
     for mlp in (c.first, c.refl.mlp, self.delta_estim):
       for lin in _linears_of(mlp): ps += [lin.weight, lin.bias]
     ps += [e.weight for e in c.first.enc.embs]
+    if self.spline: ps += [e.weight for e in self.delta_estim.enc.embs]
     return ps
 
   def forward(self, rays_t):

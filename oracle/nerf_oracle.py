@@ -18,7 +18,8 @@ arithmetic library; no ``nn.Module`` from the reference is used), of
   * PlainNeRF.forward / from_pts      reference src/nerf.py:326-361
   * TinyNeRF.forward (intended)       reference src/nerf.py:292-305
   * VolSDF volume branch              reference src/nerf.py:981-1013, src/utils.py:50-58, src/sdf.py:109-112,250-287
-  * DynamicNeRF, direct deformation   reference src/nerf.py:1209-1303 (spline variant not restated)
+  * Mip-NeRF IPE (cylinder, cone)     reference src/nerf.py:255-261, src/utils.py:22-27,39-48,60-140
+  * DynamicNeRF, direct + spline      reference src/nerf.py:1173-1178,1201-1303
   * sample_pdf (restated, dead code)  reference src/nerf.py:1745-1779
 
 Parity pin: the reference has no tests or golden vectors of its own (SURVEY.md
@@ -284,27 +285,104 @@ def sky(bg: str, weights: Tensor):
 
 
 # ----------------------------------------------------------------------------
+# a-4  Mip-NeRF integrated positional encoding
+#      (reference src/nerf.py:255-261, src/utils.py:22-27,39-48,60-140)
+# ----------------------------------------------------------------------------
+MIP_DEG = 16                     # min_deg 0, max_deg 16 (utils.py:104-111,127-134) -> 6 * 16 = 96 features
+
+def radii_x(r_d: Tensor) -> Tensor:
+  """utils.py:77-81.  ``r_d[B,H,W,3]`` -> ``[B,H,W,1]``: distance to the next ray along H (the last row repeats row
+  H-3 of the differences: ``dx[:, -2:-1, :]`` of an ``[B,H-1,W]`` tensor), times 2/sqrt(12)."""
+  dx = (r_d[..., :-1, :, :] - r_d[..., 1:, :, :]).square().sum(dim=-1).sqrt()
+  dx = torch.cat([dx, dx[:, -2:-1, :]], dim=-2)
+  return dx[..., None] * 2 / math.sqrt(12)
+
+def expected_sin(x: Tensor, x_var: Tensor) -> Tensor:
+  """utils.py:22-27 (only the mean is used by the encoder)."""
+  return (-0.5 * x_var).exp() * x.sin()
+
+def _gaussian_moments(kind: str, t0: Tensor, t1: Tensor, rad: Tensor):
+  """(t_mean[T], t_var[T], r_var[B,H,W,1 or T]) of one ray segment: cylinder utils.py:95-101, cone utils.py:83-93."""
+  if kind == "cylinder":
+    return (t1 + t0) / 2, (t1 - t0).square() / 12, rad * rad / 4
+  mu = (t1 + t0) / 2; hw = (t1 - t0) / 2
+  mu2 = mu * mu; hw2 = hw * hw; hw4 = hw2 * hw2
+  t_mean = mu + (2 * mu * hw2) / (3 * mu2 + hw2)
+  t_var = hw / 3 - (4 / 15) * ((hw4 * (12 * mu2 - hw2)) / (3 * mu2 + hw2).square())
+  r_var = rad * rad * (mu2 / 4 + (5 / 12) * hw2 - 4 / 15 * (hw4) / (3 * mu2 + hw2))
+  return t_mean, t_var, r_var
+
+def mip_encoding(r_o: Tensor, r_d: Tensor, ts: Tensor, kind: str = "cylinder", layout: str = "reference") -> Tensor:
+  """``r_o, r_d [B,H,W,3]``, shared ``ts[T]`` -> IPE latent ``[T,B,H,W,96]`` (appended to BOTH MLP inputs, nerf.py:342,357).
+
+  layout == "reference": what the reference computes (CommonNeRF.mip_encoding + CylinderGaussian), bug for bug --
+    the last segment ends at 1e10 (nerf.py:258) and ``lift_gaussian`` (utils.py:60-73) moves the xyz axis of the covariance
+    to the front instead of the sample axis, after which ``integrated_pos_enc_diag`` (utils.py:42-44) reinterprets the
+    ``[3,B,H,W,16,T]`` variance as ``[T,B,H,W,48]``: the variance of feature (t',ray',c') is the element with the same FLAT
+    index of the ``[xyz, ray, k, t]`` array (``mip_reference_var_source``).  Only the cylinder runs in the reference: the
+    cone's ``hw**4`` overflows on the 1e10 segment and turns the whole image into NaN.
+  layout == "intended": the per-sample encoder the code was meant to be: variance laid out ``[T,B,H,W,(k,xyz)]`` and the
+    last segment capped to ``t[T-1] + (t[T-1] - t[T-2])``.  Restatement only (no reference run can pin it)."""
+  if layout == "reference":
+    end_val = torch.tensor([1e10], dtype=ts.dtype)
+  else:
+    end_val = ts[-1:] + (ts[-1:] - ts[-2:-1])
+  tse = torch.cat([ts, end_val], dim=-1)
+  t0, t1 = tse[..., :-1], tse[..., 1:]
+  rad = radii_x(r_d)
+  t_mean, t_var, r_var = _gaussian_moments(kind, t0, t1, rad)
+  # lift_gaussian, utils.py:60-73
+  mean = r_d[..., None] * t_mean[..., None, :]                                   # [B,H,W,3,T]
+  magn_sq = r_d.square().sum(dim=-1, keepdim=True).clamp(min=1e-10)
+  outer_diag = r_d.square()
+  null_outer_diag = 1 - outer_diag / magn_sq
+  t_cov_diag = t_var[..., None] * outer_diag[..., None, :]                        # [B,H,W,T,3]
+  xy_cov_diag = r_var[..., None] * null_outer_diag[..., None, :]
+  cov_diag = t_cov_diag + xy_cov_diag
+  mean = mean.movedim(-1, 0) + r_o                                                # [T,B,H,W,3]
+  cov = cov_diag.movedim(-1, 0) if layout == "reference" else cov_diag.movedim(-2, 0)
+  # integrated_pos_enc_diag, utils.py:39-48
+  scales = torch.exp2(torch.arange(0, MIP_DEG, dtype=mean.dtype))
+  out_shape = mean.shape[:-1] + (-1,)
+  y = (mean[..., None, :] * scales[..., None]).reshape(out_shape)
+  y_var = (cov[..., None, :] * scales[..., None].square()).reshape(out_shape)
+  return expected_sin(torch.cat([y, y + 0.5 * math.pi], dim=-1), torch.cat([y_var, y_var], dim=-1))
+
+def mip_reference_var_source(t: int, ray: int, c: int, T: int, R: int):
+  """The (xyz, ray, k, t) whose covariance the REFERENCE layout puts under feature ``c`` (< 48) of sample ``t`` of ray
+  ``ray`` (rays flattened over [B,H,W]; R of them): same flat index in ``[3,R,16,T]`` as in ``[T,R,48]``."""
+  flat = (t * R + ray) * 48 + c
+  ts_ = flat % T; flat //= T
+  k = flat % MIP_DEG; flat //= MIP_DEG
+  r = flat % R; x = flat // R
+  return x, r, k, ts_
+
+
+# ----------------------------------------------------------------------------
 # a-6  PlainNeRF  (reference src/nerf.py:326-361) with the View head of refl.py:190-207
 # ----------------------------------------------------------------------------
 def plain_from_pts(params: Params, pts: Tensor, ts: Tensor, r_o: Tensor, r_d: Tensor, *,
                    sigmoid: str = "upshifted", bg: str = "black",
                    density_noise: Optional[Tensor] = None,
                    quant: Optional[torch.dtype] = None, per_ray_ts: bool = False,
-                   pts_encode: Optional[Tensor] = None) -> Dict[str, Tensor]:
-  """Returns every stage so tests can localise a mismatch."""
+                   pts_encode: Optional[Tensor] = None, mip_latent: Optional[Tensor] = None) -> Dict[str, Tensor]:
+  """Returns every stage so tests can localise a mismatch.  ``mip_latent[T,...,96]`` (``mip_encoding``) is appended to
+  both MLP inputs (nerf.py:340-358)."""
   T = pts.shape[0]
   batches = pts.shape[:-1]
   p = pts.reshape(-1, 3)
   tables = hash_tables(params, "first.enc")
   enc = hash_encode(p, tables)                               # [N,35] = [p, feats]
   x0 = torch.cat([p, enc], dim=-1)                           # [N,38] = [p, p, feats]
+  if mip_latent is not None: x0 = torch.cat([x0, mip_latent.reshape(x0.shape[0], -1)], dim=-1)
   first_out = skip_mlp(x0, params, "first", "leaky_relu", quant=quant).reshape(batches + (-1,))
   density = first_out[..., 0]
   if density_noise is not None: density = density + density_noise
   intermediate = first_out[..., 1:]
   view = r_d.unsqueeze(0).expand_as(pts)
   elaz = dir_to_elev_azim(view)
-  x0r = torch.cat([pts, elaz, intermediate], dim=-1).reshape(-1, 5 + intermediate.shape[-1])
+  x0r = torch.cat([pts, elaz, intermediate] if mip_latent is None else [pts, elaz, mip_latent, intermediate], dim=-1)
+  x0r = x0r.reshape(-1, x0r.shape[-1])
   rgb_raw = skip_mlp(x0r, params, "refl.mlp", "sin", quant=quant).reshape(batches + (-1,))
   rgb = SIGMOIDS[sigmoid](rgb_raw)
   if per_ray_ts: alpha, weights = alpha_from_density_per_ray(density, ts, r_d)
@@ -314,8 +392,11 @@ def plain_from_pts(params: Params, pts: Tensor, ts: Tensor, r_o: Tensor, r_d: Te
               first_out=first_out, hash_feats=enc[:, 3:], elaz=elaz[0])
 
 
-def plain_forward(params: Params, rays: Tensor, ts: Tensor, **kw) -> Dict[str, Tensor]:
+def plain_forward(params: Params, rays: Tensor, ts: Tensor, *, mip: Optional[str] = None, mip_layout: str = "reference",
+                  **kw) -> Dict[str, Tensor]:
+  """``mip`` in (None, "cylinder", "cone") needs ``rays[B,H,W,6]`` (the radii difference neighbouring rows)."""
   pts, r_o, r_d = compute_pts(rays, ts)
+  if mip is not None: kw["mip_latent"] = mip_encoding(r_o, r_d, ts, mip, mip_layout)
   res = plain_from_pts(params, pts, ts, r_o, r_d, **kw)
   res["pts"] = pts
   return res
@@ -392,6 +473,44 @@ def dnerf_direct_forward(params: Params, rays: Tensor, times: Tensor, ts: Tensor
   return res
 
 
+def de_casteljau(coeffs: Tensor, t: Tensor, N: int) -> Tensor:
+  """nerf.py:1173-1178."""
+  betas = coeffs
+  m1t = 1 - t
+  for i in range(1, N): betas = betas[:-1] * m1t + betas[1:] * t
+  return betas.squeeze(0)
+
+
+def cubic_bezier(coeffs: Tensor, t: Tensor, N: int) -> Tensor:
+  """nerf.py:1201-1206."""
+  assert N == 4
+  m1t = 1 - t
+  m1t_sq, t_sq = m1t * m1t, t * t
+  k = torch.stack([m1t_sq * m1t, 3 * m1t_sq * t, 3 * t_sq * m1t, t_sq * t], dim=0)
+  return (k * coeffs).sum(dim=0)
+
+
+def dnerf_spline_forward(params: Params, rays: Tensor, times: Tensor, ts: Tensor, n: int, *, sigmoid: str = "upshifted",
+                         bg: str = "black", quant: Optional[torch.dtype] = None) -> Dict[str, Tensor]:
+  """DynamicNeRF with n Bezier control points (set_spline_estim nerf.py:1242-1260, spline_interpolate 1267-1278, forward
+  1292-1303): delta_estim = SkipConnMLP(in 3, HashEncoder of its own, 5 layers) -> (rigidity[1], points[n,3]);
+  dp = Bezier(points, t) (cubic_bezier for n == 4, de_casteljau otherwise); rigid_dp = dp * sigmoid(rigidity / 2)."""
+  pts, r_o, r_d = compute_pts(rays, ts)
+  t = times[None, :, None, None, None].expand(*pts.shape[:-1], 1)
+  p = pts.reshape(-1, 3)
+  x0 = torch.cat([p, hash_encode(p, hash_tables(params, "delta_estim.enc"))], dim=-1)
+  o = skip_mlp(x0, params, "delta_estim", "leaky_relu", quant=quant).reshape(pts.shape[:-1] + (1 + 3 * n,))
+  rigidity, ps = o[..., :1], o[..., 1:]
+  rig = (rigidity / 2).sigmoid()
+  ps = torch.stack(ps.split([3] * n, dim=-1), dim=0)
+  dp = (cubic_bezier if n == 4 else de_casteljau)(ps, t, n)
+  rigid_dp = dp * rig
+  canon = {k[len("canonical."):]: v for k, v in params.items() if k.startswith("canonical.")}
+  res = plain_from_pts(canon, pts + rigid_dp, ts, r_o, r_d, sigmoid=sigmoid, bg=bg, quant=quant)
+  res["rigid_dp"] = rigid_dp; res["pts"] = pts
+  return res
+
+
 # ----------------------------------------------------------------------------
 # a-7  inverse-CDF resampling, restated from the dead code at nerf.py:1745-1779
 # ----------------------------------------------------------------------------
@@ -433,7 +552,7 @@ def plain_coarse_fine(params: Params, rays: Tensor, ts_coarse: Tensor, u: Tensor
 # ----------------------------------------------------------------------------
 # deterministic synthetic inputs (shared by tests, golden generator, bench)
 # ----------------------------------------------------------------------------
-def make_plain_params(seed: int = 1337, intermediate: int = 64, sigma_gain: float = 1.0) -> Params:
+def make_plain_params(seed: int = 1337, intermediate: int = 64, sigma_gain: float = 1.0, mip: bool = False) -> Params:
   """Parameters with the reference's init *distributions* (first MLP: torch
   default U(+-1/sqrt(fan_in)), neural_blocks.py:258-259; View MLP: siren
   U(+-sqrt(6/fan_in)) with zero bias, 266-271; hash tables N(0,1),
@@ -449,18 +568,19 @@ def make_plain_params(seed: int = 1337, intermediate: int = 64, sigma_gain: floa
   def siren_linear(name, out_f, in_f):
     P[f"{name}.weight"] = uni((out_f, in_f), math.sqrt(6.0 / in_f)); P[f"{name}.bias"] = torch.zeros(out_f)
   I = intermediate
+  ML = 6 * MIP_DEG if mip else 0            # mip latent on both MLP inputs (nerf.py:255, 311-324)
   P["empty_latent"] = torch.zeros(1, 1, 1, 1, 0)
   P["first.enc.primes"] = torch.tensor([1, 2654435761, 805459861, 3674653429, 2097192037, 1434869437, 2165219737])
   for i in range(HASH_LEVELS):
     P[f"first.enc.embs.{i}.weight"] = torch.from_numpy(g.standard_normal((HASH_TABLE, HASH_FEAT)).astype(np.float32))
-  default_linear("first.init", 256, 38)
-  default_linear("first.layers.0", 256, 256 + 38)
+  default_linear("first.init", 256, 38 + ML)
+  default_linear("first.layers.0", 256, 256 + 38 + ML)
   for i in (1, 2, 3): default_linear(f"first.layers.{i}", 256, 256)
   default_linear("first.out", 1 + I, 256)
   if sigma_gain != 1.0:
     P["first.out.weight"][0] *= sigma_gain; P["first.out.bias"][0] *= sigma_gain
-  siren_linear("refl.mlp.init", 256, 5 + I)
-  siren_linear("refl.mlp.layers.0", 256, 256 + 5 + I)
+  siren_linear("refl.mlp.init", 256, 5 + ML + I)
+  siren_linear("refl.mlp.layers.0", 256, 256 + 5 + ML + I)
   for i in (1, 2, 3): siren_linear(f"refl.mlp.layers.{i}", 256, 256)
   siren_linear("refl.mlp.out", 3, 256)
   return P
@@ -503,6 +623,25 @@ def make_dnerf_params(seed: int = 9, intermediate: int = 64, sigma_gain: float =
   for i in range(5): xav(f"delta_estim.layers.{i}", 256, 260 if (i % 3 == 0 and i != 4) else 256)
   xav("delta_estim.out", 4, 256, out_scale)
   P["delta_estim.out.bias"] = torch.from_numpy(g.uniform(-0.2, 0.2, size=(4,)).astype(np.float32))
+  return P
+
+
+def make_dnerf_spline_params(seed: int = 9, n: int = 5, intermediate: int = 64, sigma_gain: float = 20.0, out_scale: float = 0.3) -> Params:
+  """DynamicNeRF(spline=n) over PlainNeRF+View: delta_estim has its own HashEncoder (N(0,1) tables), xavier Linears with
+  zero biases (nerf.py:1252-1255); the zero-initialised last layer (nerf.py:1256) gets small random values here so that
+  the deformation is exercised."""
+  g = np.random.default_rng(seed)
+  P: Params = {"canonical." + k: v for k, v in make_plain_params(seed + 1, intermediate, sigma_gain).items()}
+  def xav(name, o, i, scale=1.0):
+    a = math.sqrt(6.0 / (i + o)) * scale
+    P[f"{name}.weight"] = torch.from_numpy(g.uniform(-a, a, size=(o, i)).astype(np.float32)); P[f"{name}.bias"] = torch.zeros(o)
+  P["delta_estim.enc.primes"] = torch.tensor([1, 2654435761, 805459861, 3674653429, 2097192037, 1434869437, 2165219737])
+  for i in range(HASH_LEVELS):
+    P[f"delta_estim.enc.embs.{i}.weight"] = torch.from_numpy(g.standard_normal((HASH_TABLE, HASH_FEAT)).astype(np.float32))
+  xav("delta_estim.init", 256, 38)
+  for i in range(5): xav(f"delta_estim.layers.{i}", 256, 294 if (i % 3 == 0 and i != 4) else 256)
+  xav("delta_estim.out", 1 + 3 * n, 256, out_scale)
+  P["delta_estim.out.bias"] = torch.from_numpy(g.uniform(-0.2, 0.2, size=(1 + 3 * n,)).astype(np.float32))
   return P
 
 

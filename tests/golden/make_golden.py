@@ -108,6 +108,42 @@ def case_dnerf(name, seed, B, H, W, T, top=0, left=0):
   np.savez_compressed(os.path.join(HERE, name + ".npz"), **fx)
   print(name, "out", out.shape, "mean", float(out.mean()), "max|rigid_dp|", float(model.rigid_dp.abs().max()))
 
+def case_mip(name, seed, B, H, W, T, top=0, left=0):
+  """PlainNeRF(mip=CylinderGaussian()) built directly (runner.load_model rebuilds the refl head without the mip latent,
+  SURVEY.md a-4 (iii)); the cone variant renders NaN in the reference and cannot be pinned."""
+  runner, nerf, refl, utils, cameras = ref_shim.load()
+  params = O.make_plain_params(seed, 64, 20.0, mip=True)
+  rays = O.make_rays(B, H, W, size=800, seed=seed, crop_top=top, crop_left=left)
+  model = nerf.PlainNeRF(mip=utils.CylinderGaussian(), steps=T, t_near=2, t_far=6, intermediate_size=64,
+                         sigmoid_kind="upshifted", bg="black").eval()
+  model.load_state_dict({k: v.clone() for k, v in params.items()}, strict=True)
+  with torch.no_grad():
+    out = model(rays)
+    pts, ts, r_o, r_d, _ = nerf.compute_pts_ts(rays, 2, 6, T, perturb=0)
+    enc = model.mip_encoding(r_o, r_d, ts)
+    rad = utils.radii_x(r_d)
+  fx = dict(kind="plain_mip", mip="cylinder_ref", seed=seed, B=B, H=H, W=W, T=T, top=top, left=left, near=2.0, far=6.0,
+            sigmoid="upshifted", bg="black", ts=model.ts.numpy(), out=out.numpy(), alpha=model.alpha.numpy(),
+            weights=model.weights.numpy(), mip_enc=enc.numpy(), radii=rad.numpy())
+  np.savez_compressed(os.path.join(HERE, name + ".npz"), **fx)
+  print(name, "out", out.shape, "mean", float(out.mean()), "finite", bool(torch.isfinite(out).all()))
+
+def case_dnerf_spline(name, seed, n, B, H, W, T, top=0, left=0):
+  runner, nerf, refl, utils, cameras = ref_shim.load()
+  params = O.make_dnerf_spline_params(seed, n, 64)
+  rays = O.make_rays(B, H, W, size=800, seed=seed, crop_top=top, crop_left=left)
+  times = torch.linspace(0.1, 0.9, B)
+  canonical, args = ref_shim.build_model("plain", T)
+  model = nerf.DynamicNeRF(canonical=canonical, spline=n)
+  model.load_state_dict({k: v.clone() for k, v in params.items()}, strict=True)
+  model.eval()
+  with torch.no_grad(): out = model((rays, times))
+  fx = dict(kind="dnerf_spline", n=n, seed=seed, B=B, H=H, W=W, T=T, top=top, left=left, near=float(args.near), far=float(args.far),
+            sigmoid=args.sigmoid_kind, bg=args.bg, times=times.numpy(), ts=model.ts.numpy(), out=out.numpy(),
+            alpha=canonical.alpha.numpy(), weights=canonical.weights.numpy(), rigid_dp=model.rigid_dp.numpy())
+  np.savez_compressed(os.path.join(HERE, name + ".npz"), **fx)
+  print(name, "out", out.shape, "mean", float(out.mean()), "max|rigid_dp|", float(model.rigid_dp.abs().max()))
+
 def r_o_pts(rays, ts):
   r_o, r_d = rays.split([3, 3], dim=-1)
   pts = r_o.unsqueeze(0) + torch.tensordot(ts, r_d, dims=0)
@@ -139,6 +175,11 @@ def check_rays():
 
 if __name__ == "__main__":
   check_rays()
+  if "--new" in sys.argv:      # only the cases added after the first goldens were committed
+    case_mip("plain_mip_cylinder_t16", seed=61, B=2, H=5, W=4, T=16, top=398, left=397)
+    case_dnerf_spline("dnerf_spline5_t32", seed=71, n=5, B=2, H=3, W=4, T=32, top=398, left=397)
+    case_dnerf_spline("dnerf_spline4_t32", seed=72, n=4, B=2, H=3, W=3, T=32, top=398, left=397)
+    sys.exit(0)
   case_plain("plain_t16", seed=11, B=1, H=4, W=6, T=16)
   case_plain("plain_t16_sharp", seed=12, B=2, H=3, W=5, T=16, sigma_gain=20.0, top=390, left=380)
   case_plain("plain_t128", seed=1337, B=1, H=8, W=8, T=128, sigma_gain=20.0, top=396, left=396, stages=False)
@@ -146,3 +187,6 @@ if __name__ == "__main__":
   case_volsdf("volsdf_mlp_t32", seed=32, sdf_kind="mlp", B=1, H=3, W=4, T=32, top=398, left=397)
   case_dnerf("dnerf_direct_t64", seed=51, B=2, H=3, W=4, T=64, top=398, left=397)
   case_plain("plain_t64_train", seed=21, B=1, H=4, W=4, T=64, sigma_gain=20.0, train=True, top=300, left=420, stages=False)
+  case_mip("plain_mip_cylinder_t16", seed=61, B=2, H=5, W=4, T=16, top=398, left=397)
+  case_dnerf_spline("dnerf_spline5_t32", seed=71, n=5, B=2, H=3, W=4, T=32, top=398, left=397)
+  case_dnerf_spline("dnerf_spline4_t32", seed=72, n=4, B=2, H=3, W=3, T=32, top=398, left=397)

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
   assert len(names) >= 10
   for n in names: assert hasattr(l, n), f"{n} declared in include/nerf_b200.h but not exported"
   assert sorted(_lib.EXPORTS) == names, "ctypes binding table and header disagree"
-  assert _lib.lib().nf_version() == _lib.ABI_VERSION == 3
+  assert _lib.lib().nf_version() == _lib.ABI_VERSION == 4
 
 def test_descriptor_host_logic():
   l = _lib.lib()
@@ -39,6 +39,15 @@ def test_descriptor_host_logic():
   bad = N.describe_plain(); bad.refl.in_dims = 70
   assert l.nf_packed_bytes(C.byref(bad)) == -1
   bad = N.describe_plain(); bad.struct_bytes = 8
+  assert l.nf_param_count(C.byref(bad)) == -1
+  # Mip widens both MLP inputs by 96; the spline deformation MLP brings its own hash tables
+  m = N.describe_plain(mip="cylinder_ref")
+  assert m.density.in_dims == 38 + 96 and m.refl.in_dims == 5 + 96 + 64 and l.nf_param_count(C.byref(m)) == 32
+  s5 = N.describe_dyn(spline=5)
+  assert s5.deform.out_dims == 16 and l.nf_param_count(C.byref(s5)) == 2 * 6 + 2 * 6 + 2 * 7 + 8 + 8
+  bad = N.describe_dyn(spline=5); bad.deform.out_dims = 4
+  assert l.nf_param_count(C.byref(bad)) == -1 and b"spline" in l.nf_last_error()
+  bad = N.describe_plain(mip="cone"); bad.refl.in_dims = 69
   assert l.nf_param_count(C.byref(bad)) == -1
 
 def test_module_state_dict_names_are_the_references():

@@ -361,3 +361,76 @@ def test_dnerf_direct_matches_reference_golden():
   # the tensor pipeline does not take this kind yet: loud refusal, no fallback
   canon.precision = "fp16"
   with pytest.raises(RuntimeError): m((rays.to(DEV), torch.from_numpy(fx["times"]).to(DEV)))
+
+
+def test_dnerf_spline_matches_reference_golden():
+  """DynamicNeRF(spline=n): hash-encoded deformation MLP -> n Bezier control points (de_casteljau for n = 5, the closed
+  cubic form for n = 4), fp32 pipeline, against goldens produced by running the reference."""
+  import nerf_atlas_b200 as N
+  for name in ("dnerf_spline5_t32", "dnerf_spline4_t32"):
+    fx = load_golden(name)
+    n = int(fx["n"])
+    P = O.make_dnerf_spline_params(int(fx["seed"]), n, 64)
+    rays = O.make_rays(int(fx["B"]), int(fx["H"]), int(fx["W"]), 800, int(fx["seed"]), int(fx["top"]), int(fx["left"]))
+    canon = N.FusedPlainNeRF(steps=int(fx["T"]), t_near=float(fx["near"]), t_far=float(fx["far"]), intermediate_size=64,
+                             sigmoid_kind=str(fx["sigmoid"]), bg=str(fx["bg"]), precision="fp32")
+    m = N.FusedDynamicNeRF(canon, spline=n)
+    m.load_state_dict(P, strict=True)                      # reference names: delta_estim.(enc.)*, canonical.*
+    m = m.to(DEV).eval()
+    with torch.no_grad(): out = m((rays.to(DEV), torch.from_numpy(fx["times"]).to(DEV)))
+    assert out.shape == fx["out"].shape
+    assert np.abs(out.cpu().numpy() - fx["out"]).max() <= 5e-5, (name, np.abs(out.cpu().numpy() - fx["out"]).max())
+    assert np.abs(m.nerf.weights.cpu().numpy() - fx["weights"]).max() <= 2e-4
+
+# ---------------------------------------------------------------- Mip-NeRF IPE (config 3)
+def _mip_engine(P, mip, device):
+  import nerf_atlas_b200 as N
+  eng = N.RenderEngine(N.describe_plain(64, "upshifted", "black", mip=mip), "fp32")
+  eng._params = plain_param_list(P, device); eng.pack(eng._params)
+  return eng
+
+def test_mip_cylinder_matches_reference_golden_bug_for_bug():
+  """PlainNeRF(mip=CylinderGaussian()) exactly as the reference renders it (variance layout bug + 1e10 last segment):
+  radii bit-exact, RGB within the fp32 bar, the module surface, and a sharded render == the whole crop."""
+  import nerf_atlas_b200 as N
+  fx = load_golden("plain_mip_cylinder_t16")
+  P = O.make_plain_params(int(fx["seed"]), 64, 20.0, mip=True)
+  rays = O.make_rays(int(fx["B"]), int(fx["H"]), int(fx["W"]), 800, int(fx["seed"]), int(fx["top"]), int(fx["left"])).to(DEV)
+  e = _mip_engine(P, "cylinder_ref", DEV)
+  rad = e.ray_radii(rays)
+  assert np.array_equal(rad.cpu().numpy()[..., None], fx["radii"]), "radii_x must be bit-exact"
+  flat, ts = rays.reshape(-1, 6), torch.from_numpy(fx["ts"]).to(DEV)
+  rgb, alpha, w = e.render(flat, ts, radius=rad.reshape(-1))
+  out = rgb.cpu().numpy().reshape(fx["out"].shape)
+  assert np.isfinite(out).all()
+  assert np.abs(out - fx["out"]).max() <= 3e-5, np.abs(out - fx["out"]).max()
+  assert np.abs(w.cpu().numpy().T.reshape(fx["weights"].shape) - fx["weights"]).max() <= 2e-4
+  # a shard of the crop needs the whole crop for the reference's cross-ray variance gather
+  cut = 13
+  a, _, _ = e.render(flat[:cut].contiguous(), ts, radius=rad.reshape(-1)[:cut].contiguous(), crop=(flat, rad.reshape(-1), 0), want_weights=False)
+  b, _, _ = e.render(flat[cut:].contiguous(), ts, radius=rad.reshape(-1)[cut:].contiguous(), crop=(flat, rad.reshape(-1), cut), want_weights=False)
+  assert torch.equal(torch.cat([a, b]), rgb)
+  # the tensor pipeline refuses (x0 is 134 / 165 wide): no silent fallback
+  with pytest.raises(RuntimeError): e.render(flat, ts, radius=rad.reshape(-1), precision="fp16")
+  with pytest.raises(ValueError): e.render(flat, ts)                                    # radius is required
+  # module surface: mip given as the reference's own encoder object name or as a string
+  m = N.FusedPlainNeRF(steps=int(fx["T"]), t_near=2, t_far=6, intermediate_size=64, sigmoid_kind="upshifted", precision="fp32", mip="cylinder_ref")
+  m.load_state_dict(P, strict=True); m = m.to(DEV).eval()
+  assert m.total_latent_size() == 96 and m.mip_size() == 96
+  with torch.no_grad(): o2 = m(rays)
+  assert np.abs(o2.cpu().numpy() - fx["out"]).max() <= 3e-5
+
+@pytest.mark.parametrize("kind", ["cylinder", "cone"])
+def test_mip_intended_encoder_vs_oracle(kind):
+  """The per-sample IPE the reference meant to compute (restatement; the reference's cone renders NaN): vs the oracle."""
+  P = O.make_plain_params(62, 64, 20.0, mip=True)
+  rays = O.make_rays(2, 7, 9, seed=5, crop_top=300, crop_left=420)
+  for T in (16, 100, 128):
+    ts = torch.linspace(2, 6, T)
+    with torch.no_grad(): ref = O.plain_forward(P, rays, ts, mip=kind, mip_layout="intended")
+    e = _mip_engine(P, kind, DEV)
+    rad = e.ray_radii(rays.to(DEV))
+    rgb, _, w = e.render(rays.reshape(-1, 6).to(DEV), ts.to(DEV), radius=rad.reshape(-1))
+    out = rgb.cpu().numpy().reshape(ref["out"].shape)
+    assert np.isfinite(out).all()
+    assert np.abs(out - ref["out"].numpy()).max() <= 5e-5, (kind, T, np.abs(out - ref["out"].numpy()).max())

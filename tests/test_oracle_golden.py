@@ -69,6 +69,59 @@ def test_dnerf_direct_oracle_matches_reference_bit_exact(golden_dir):
   for k in ("out", "alpha", "weights", "rigid_dp"):
     assert np.array_equal(res[k].numpy(), fx[k]), f"dnerf: {k} differs from the reference run"
 
+def test_mip_cylinder_oracle_matches_reference_bit_exact(golden_dir):
+  """PlainNeRF(mip=CylinderGaussian()) as the reference runs it, bugs included: IPE latent, radii, RGB."""
+  fx = load(golden_dir, "plain_mip_cylinder_t16")
+  params = O.make_plain_params(int(fx["seed"]), 64, 20.0, mip=True)
+  rays = O.make_rays(int(fx["B"]), int(fx["H"]), int(fx["W"]), 800, int(fx["seed"]), int(fx["top"]), int(fx["left"]))
+  ts = O.compute_ts(float(fx["near"]), float(fx["far"]), int(fx["T"]))
+  with torch.no_grad():
+    res = O.plain_forward(params, rays, ts, mip="cylinder", mip_layout="reference", sigmoid=str(fx["sigmoid"]), bg=str(fx["bg"]))
+    enc = O.mip_encoding(rays[..., :3], rays[..., 3:], ts, "cylinder", "reference")
+  assert np.array_equal(O.radii_x(rays[..., 3:]).numpy(), fx["radii"])
+  assert np.array_equal(enc.numpy(), fx["mip_enc"])
+  for k in ("out", "alpha", "weights"):
+    assert np.array_equal(res[k].numpy(), fx[k]), f"mip: {k} differs from the reference run"
+  # the closed form of the reference's accidental layout (what the CUDA kernel implements) == the reshape it restates
+  T, R = int(fx["T"]), rays.reshape(-1, 6).shape[0]
+  rd = rays[..., 3:].reshape(R, 3); rad = O.radii_x(rays[..., 3:]).reshape(R)
+  tse = torch.cat([ts, torch.tensor([1e10])]); t_var = (tse[1:] - tse[:-1]).square() / 12
+  magn = rd.square().sum(-1).clamp(min=1e-10)
+  g = np.random.default_rng(0)
+  for _ in range(200):
+    t, r, c = int(g.integers(T)), int(g.integers(R)), int(g.integers(96))
+    x, rv, k, tv = O.mip_reference_var_source(t, r, c % 48, T, R)
+    cov = t_var[tv] * rd[rv, x] ** 2 + (rad[rv] * rad[rv] / 4) * (1 - rd[rv, x] ** 2 / magn[rv])
+    kk, xx = (c % 48) // 3, (c % 48) % 3
+    y = (rd[r, xx] * ((tse[t + 1] + tse[t]) / 2) + rays[..., :3].reshape(R, 3)[r, xx]) * 2.0 ** kk
+    if c >= 48: y = y + 0.5 * np.pi
+    f = torch.exp(-0.5 * (cov * (2.0 ** k) ** 2)) * torch.sin(y)
+    assert abs(float(f) - float(enc.reshape(T, R, 96)[t, r, c])) <= 1e-6, (t, r, c)
+
+def test_mip_intended_layout_is_per_sample():
+  """The intended encoder: the latent of a sample depends on that sample's own ray and segment only (shuffling the other
+  rays of the crop does not change it, apart from the radius, which differences neighbouring rows)."""
+  rays = O.make_rays(1, 6, 5, seed=4, crop_top=100, crop_left=200)
+  ts = torch.linspace(2, 6, 24)
+  for kind in ("cylinder", "cone"):
+    enc = O.mip_encoding(rays[..., :3], rays[..., 3:], ts, kind, "intended")
+    assert enc.shape == (24, 1, 6, 5, 96) and torch.isfinite(enc).all()
+    sub = O.mip_encoding(rays[:, :4, 1:3, :3], rays[:, :4, 1:3, 3:], ts, kind, "intended")
+    assert torch.equal(sub[:, :, :3], enc[:, :, :3, 1:3])          # rows 0..2 keep their H-neighbours in the sub-crop
+    assert float(enc[-1].abs().max()) > 1e-3                        # capped last segment: not the 1e10 wash-out
+
+@pytest.mark.parametrize("name", ["dnerf_spline5_t32", "dnerf_spline4_t32"])
+def test_dnerf_spline_oracle_matches_reference_bit_exact(golden_dir, name):
+  fx = load(golden_dir, name)
+  n = int(fx["n"])
+  params = O.make_dnerf_spline_params(int(fx["seed"]), n, 64)
+  rays = O.make_rays(int(fx["B"]), int(fx["H"]), int(fx["W"]), 800, int(fx["seed"]), int(fx["top"]), int(fx["left"]))
+  ts = O.compute_ts(float(fx["near"]), float(fx["far"]), int(fx["T"]))
+  with torch.no_grad():
+    res = O.dnerf_spline_forward(params, rays, torch.from_numpy(fx["times"]), ts, n, sigmoid=str(fx["sigmoid"]), bg=str(fx["bg"]))
+  for k in ("out", "alpha", "weights", "rigid_dp"):
+    assert np.array_equal(res[k].numpy(), fx[k]), f"{name}: {k} differs from the reference run"
+
 def test_hash_resolutions_decrease():
   # operator-precedence quirk of neural_blocks.py:126-128: scale < 1, resolutions 16 -> 6.28
   r = O.hash_resolutions()
