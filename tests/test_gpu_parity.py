@@ -244,11 +244,11 @@ def test_c_abi_error_codes(eng):
   l = _lib.lib()
   rays = torch.zeros(4, 6, device=DEV); ts = torch.linspace(2, 6, 8, device=DEV); rgb = torch.zeros(4, 3, device=DEV)
   v = lambda t: C.c_void_p(t.data_ptr())
-  rc = l.nf_render_forward(C.byref(eng.desc), v(eng.packed), v(rays), 4, v(ts), 8, 5, None, None, v(rgb), None, None, 1, None)
+  rc = l.nf_render_forward(C.byref(eng.desc), v(eng.packed), v(rays), 4, v(ts), 8, 5, None, None, None, v(rgb), None, None, 1, None)
   assert rc == -1 and b"ts_ray_stride" in l.nf_last_error()
-  rc = l.nf_render_forward(C.byref(eng.desc), v(eng.packed), None, 4, v(ts), 8, 0, None, None, v(rgb), None, None, 1, None)
+  rc = l.nf_render_forward(C.byref(eng.desc), v(eng.packed), None, 4, v(ts), 8, 0, None, None, None, v(rgb), None, None, 1, None)
   assert rc == -1
-  rc = l.nf_render_forward(C.byref(eng.desc), v(eng.packed), v(rays), 4, v(ts), 8, 0, None, None, v(rgb), None, None, 7, None)
+  rc = l.nf_render_forward(C.byref(eng.desc), v(eng.packed), v(rays), 4, v(ts), 8, 0, None, None, None, v(rgb), None, None, 7, None)
   assert rc == -1 and b"precision" in l.nf_last_error()
   with pytest.raises(RuntimeError): eng.render(rays.cpu(), ts)
 
