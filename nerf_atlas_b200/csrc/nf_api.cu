@@ -123,14 +123,17 @@ int nf_render_forward(const nf_model_desc* desc, const void* packed, const float
   else if (precision == NF_PREC_FP16_TC) {
     // NF_TC_PIPE selects the tensor pipeline: 3 (default) = staggered paired pipeline (nf_tc3.cu), 2 = lockstep paired
     // pipeline (nf_tc2.cu), 1 = single-CTA pipeline (nf_tc.cu); the older ones are kept for A/B timing.  NF_TC_PAIRED=0 == 1.
-    if (p.kind == NF_KIND_DYN) return fail(NF_E_UNSUPPORTED, "NF_KIND_DYN runs on the fp32 pipeline only in this build");
     int pipe = 3;
     if (const char* env = getenv("NF_TC_PIPE")) pipe = atoi(env);
     if (const char* env = getenv("NF_TC_PAIRED")) if (env[0] == '0') pipe = 1;
+    if (p.kind == NF_KIND_DYN) {       // only the staggered pipeline runs the three-MLP chain
+      if (const char* why = nf_tc3_unsupported(p)) return fail(NF_E_UNSUPPORTED, why);
+      pipe = 3;
+    }
     if (pipe == 3 && nf_tc3_unsupported(p)) pipe = 2;
     if (pipe == 2 && nf_tc2_unsupported(p)) pipe = 1;
     cudaStream_t st = (cudaStream_t)stream;
-    e = pipe == 3 ? nf_launch_render_tc3(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, rgb_out, alpha_out, weights_out, st)
+    e = pipe == 3 ? nf_launch_render_tc3(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, ray_time, rgb_out, alpha_out, weights_out, st)
       : pipe == 2 ? nf_launch_render_tc2(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, rgb_out, alpha_out, weights_out, st)
                   : nf_launch_render_tc(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, rgb_out, alpha_out, weights_out, st);
   }

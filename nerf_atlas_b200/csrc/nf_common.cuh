@@ -138,6 +138,8 @@ static inline int nf_build_plan(const nf_model_desc* d, NfPlan* p, const char** 
 //   refl x0          : reference [p(3), elaz(2), inter(I)]    -> [inter(I), p, elaz]
 //   density out      : reference [sigma, inter(I)]            -> [inter(I), sigma]
 __host__ __device__ inline int nf_x0_perm(const NfPlan& p, int m, int k_ref) {
+  if (p.mip != NF_MIP_NONE) return k_ref;                  // (fp32 pipeline only; the image is packed but never used)
+  if (m == 2 && p.deform_enc == NF_ENC_HASH) { const int nfe = p.hash_levels * 4; return k_ref < 6 ? nfe + k_ref : k_ref - 6; }
   if (p.kind == NF_KIND_PLAIN || p.kind == NF_KIND_DYN) {
     if (m == 0 && p.enc == NF_ENC_HASH) { const int nfe = p.hash_levels * 4; return k_ref < 6 ? nfe + k_ref : k_ref - 6; }
     if (m == 1) return k_ref < 5 ? p.intermediate + k_ref : k_ref - 5;
@@ -318,9 +320,14 @@ __device__ __forceinline__ float nf_bezier(const float* ps, int n, float t) {
     return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(k0, ps[0]), __fmul_rn(k1, ps[1])), __fmul_rn(k2, ps[2])), __fmul_rn(k3, ps[3]));
   }
   float b[8];
-  for (int i = 0; i < n; ++i) b[i] = ps[i];
-  for (int i = 1; i < n; ++i)
-    for (int j = 0; j < n - i; ++j) b[j] = __fadd_rn(__fmul_rn(b[j], m1t), __fmul_rn(b[j + 1], t));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = i < n ? ps[i] : 0.f;
+  // fully unrolled with predicates: every index is a compile-time constant, so b[] stays in registers
+#pragma unroll
+  for (int i = 1; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8 - i; ++j)
+      if (i < n && j < n - i) b[j] = __fadd_rn(__fmul_rn(b[j], m1t), __fmul_rn(b[j + 1], t));
   return b[0];
 }
 

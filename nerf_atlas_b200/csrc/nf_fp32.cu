@@ -156,9 +156,11 @@ k_render_fp32(const __grid_constant__ NfPlan plan, const RenderArgs a) {
             const int n = plan.spline_points;
             const float rig = nf_sigmoid(O[row] / 2.f);
             const float tt = s.valid[row] ? __ldg(a.ray_time + s.ray[row]) : 0.f;
+#pragma unroll
             for (int x = 0; x < 3; ++x) {
               float ps[8];
-              for (int i = 0; i < n; ++i) ps[i] = O[(1 + 3 * i + x) * ROWS + row];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) ps[i] = i < n ? O[(1 + 3 * i + x) * ROWS + row] : 0.f;
               s.P[x * ROWS + row] += nf_bezier(ps, n, tt) * rig;
             }
           }

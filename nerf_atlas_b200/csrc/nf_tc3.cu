@@ -32,7 +32,7 @@ using namespace nf_ptx;
 constexpr int X0K = 80;
 constexpr int RING_BYTES = 48 * 1024;                       // weight ring per CTA: NST stages of SPCT K-steps (4 KB each at N = 256)
 constexpr int EPI_THREADS = 512;
-constexpr int MAX_LIN3 = 16;
+constexpr int MAX_LIN3 = 24;
 constexpr int MAX_STAGES3 = 6;
 
 struct Tc3Smem {
@@ -41,10 +41,13 @@ struct Tc3Smem {
   uint8_t W[RING_BYTES];
   float bias[2][2][256];                                     // [slot][step parity][column]
   float sig[2][ROWS];
+  float P[2][3][ROWS];                                       // NF_KIND_DYN: the deformed sample positions of the tile
   float warp_agg[2][4]; int warp_cont[2][4]; float warp_sum[2][4][4]; float carry[2][8];
   unsigned long long w_land[MAX_STAGES3], w_empty[MAX_STAGES3], w_ready[MAX_STAGES3], acc_full[2], a_ready[2];
   uint32_t tmem_base; int pad_;
-  int4 lin[MAX_LIN3][2];        // per Linear, for the epilogue warps: {n_pad, bias byte offset, act, flags(1 = out, 2 = init)}, {k0_pad, -, -, -}
+  int4 lin[MAX_LIN3][2];        // per Linear, for the epilogue warps: {n_pad, bias byte offset, act, flags}, {k0_pad, -, -, -}
+                                // flags: 1 = `out` Linear, 2 = `init` Linear, bits 2-3 = what the epilogue of an `out` does:
+                                // 1 density-out -> View x0, 2 deformation-out -> deform + encode, 3 the path's last Linear
 };
 static_assert(sizeof(Tc3Smem) <= 227 * 1024, "staggered tensor pipeline smem");
 
@@ -61,7 +64,7 @@ struct Tc3Args {
   const uint8_t* packed;
   const float* rays; long long n_rays;
   const float* ts; int T; long long ts_stride;
-  const float* noise;
+  const float* noise; const float* ray_time;
   float* rgb_out; float* alpha_out; float* weights_out;
   int debug;          // NF_TC_DEBUG (timing experiments): 256 = poll acc_full with backoff, 512 = try_wait with a short suspend hint
   long long* stats;   // NF_TC_STATS builds: time-in-state counters of CTA 0 (issuer, producer 0, epilogue warps 0 and 15)
@@ -135,6 +138,23 @@ __device__ __forceinline__ void x0_activate3(uint8_t* X0, int k0_pad, int act, i
     }
     *reinterpret_cast<uint4*>(X0 + i * 16) = q;
   }
+}
+
+// this thread's share (levels first, first+stride, ...) of the hash features of one row -> x0 columns [4*lvl, 4*lvl+4)
+__device__ __forceinline__ void hash_x0(uint8_t* X0, const float4* tables, const NfPlan& plan, float px, float py, float pz,
+                                        int row, int first, int stride) {
+  if (first < 0) return;
+  for (int lvl = first; lvl < plan.hash_levels; lvl += stride) {
+    const float4 f = nf_hash_level(tables + (size_t)lvl * (plan.hash_mask + 1), px, py, pz, plan.hash_res[lvl],
+                                   plan.hash_primes[0], plan.hash_primes[1], plan.hash_primes[2], plan.hash_mask, nullptr);
+    *reinterpret_cast<uint2*>(X0 + (lvl >> 1) * KG_BYTES + row * 16 + (lvl & 1) * 8) = make_uint2(pack_h2(f.x, f.y), pack_h2(f.z, f.w));
+  }
+}
+// the [p, p] tail of a hash-encoded x0 (tensor order [feats, p, p]) and the zero padding up to k0_pad
+__device__ __forceinline__ void hash_x0_tail(uint8_t* X0, const NfPlan& plan, int k0_pad, float px, float py, float pz, int row) {
+  const int kg = plan.hash_levels >> 1;
+  st_v4(X0 + kg * KG_BYTES + row * 16, pack_h2(px, py), pack_h2(pz, px), pack_h2(py, pz), 0);
+  for (int g = kg + 1; g < (k0_pad >> 3); ++g) st_v4(X0 + g * KG_BYTES + row * 16, 0, 0, 0, 0);
 }
 
 // work unit of (pass, slot) for this CTA, and the sub-tile within a ray (T > 128)
@@ -256,7 +276,8 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
     const uint32_t mj = prog.lin[threadIdx.x].mj;
     const NfMlpPlan& M = plan.mlp[mj >> 4];
     const NfLinPlan& L = M.lin[mj & 15];
-    s.lin[threadIdx.x][0] = make_int4(L.n_pad, (int)L.b16_off, M.act, (L.is_out ? 1 : 0) | ((mj & 15) == 0 ? 2 : 0));
+    const int role = !L.is_out ? 0 : (int)threadIdx.x == prog.n_lin - 1 ? 3 : (mj >> 4) == 2 ? 2 : 1;
+    s.lin[threadIdx.x][0] = make_int4(L.n_pad, (int)L.b16_off, M.act, (L.is_out ? 1 : 0) | ((mj & 15) == 0 ? 2 : 0) | (role << 2));
     s.lin[threadIdx.x][1] = make_int4(M.k0_pad, 0, 0, 0);
   }
   tc_fence_before();
@@ -429,23 +450,21 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
               const float tt = __ldg(a.ts + ray * a.ts_stride + t);
               px = nf_pt(__ldg(rr + 0), tt, __ldg(rr + 3)); py = nf_pt(__ldg(rr + 1), tt, __ldg(rr + 4)); pz = nf_pt(__ldg(rr + 2), tt, __ldg(rr + 5));
             }
-            int kg = 0;
-            if (plan.enc == NF_ENC_HASH) {
-              // 4 threads per row share the levels; when the cq == 0 warps are compositing, the other three take them all
-              const float4* tables = reinterpret_cast<const float4*>(a.packed + plan.hash_off);
-              const int first = comp ? cq - 1 : cq, stride = comp ? 3 : 4;
-              if (first >= 0)
-                for (int lvl = first; lvl < plan.hash_levels; lvl += stride) {
-                  const float4 f = nf_hash_level(tables + (size_t)lvl * (plan.hash_mask + 1), px, py, pz, plan.hash_res[lvl],
-                                                 plan.hash_primes[0], plan.hash_primes[1], plan.hash_primes[2], plan.hash_mask, nullptr);
-                  *reinterpret_cast<uint2*>(X0 + (lvl >> 1) * KG_BYTES + row * 16 + (lvl & 1) * 8) = make_uint2(pack_h2(f.x, f.y), pack_h2(f.z, f.w));
-                }
-              kg = plan.hash_levels >> 1;
-            }
+            // x0 of the FIRST MLP of the path: the density MLP, or (NF_KIND_DYN) the deformation MLP.  4 threads per row share
+            // the hash levels; when the cq == 0 warps are compositing, the other three take them all
+            const bool dyn = plan.kind == NF_KIND_DYN;
+            const int first_m = dyn ? 2 : 0;
+            const bool hashed = dyn ? plan.deform_enc == NF_ENC_HASH : plan.enc == NF_ENC_HASH;
+            if (hashed)
+              hash_x0(X0, reinterpret_cast<const float4*>(a.packed + (dyn ? plan.hash2_off : plan.hash_off)), plan, px, py, pz, row,
+                      comp ? cq - 1 : cq, comp ? 3 : 4);
             if (cq == 0) {
-              if (plan.enc == NF_ENC_HASH) st_v4(X0 + kg * KG_BYTES + row * 16, pack_h2(px, py), pack_h2(pz, px), pack_h2(py, pz), 0);
-              else st_v4(X0 + kg * KG_BYTES + row * 16, pack_h2(px, py), pack_h2(pz, 0.f), 0, 0);
-              for (int g = kg + 1; g < (plan.mlp[0].k0_pad >> 3); ++g) st_v4(X0 + g * KG_BYTES + row * 16, 0, 0, 0, 0);
+              if (hashed) hash_x0_tail(X0, plan, plan.mlp[first_m].k0_pad, px, py, pz, row);
+              else {
+                const float tt = (dyn && ok) ? __ldg(a.ray_time + ray) : 0.f;        // direct deformation: x0 = [p, t]
+                st_v4(X0 + row * 16, pack_h2(px, py), pack_h2(pz, tt), 0, 0);
+                for (int g = 1; g < (plan.mlp[first_m].k0_pad >> 3); ++g) st_v4(X0 + g * KG_BYTES + row * 16, 0, 0, 0, 0);
+              }
             }
             if (bload) { s.bias[slot][kl & 1][e_tid] = bnext; __threadfence_block(); }   // for this slot's next phase
             tc_fence_before();
@@ -465,6 +484,43 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
             else if (act == NF_ACT_LEAKY) epi_hidden3<NF_ACT_LEAKY>(H, t_acc, bias, cq, row);
             else if (act == NF_ACT_RELU) epi_hidden3<NF_ACT_RELU>(H, t_acc, bias, cq, row);
             else epi_hidden3<NF_ACT_NONE>(H, t_acc, bias, cq, row);
+          } else if (((Lc.w >> 2) & 3) == 2) {
+            // deformation MLP out (reference nerf.py:1261-1278): every thread deforms its row's sample, then takes its share of
+            // the density MLP's hash levels at the DEFORMED position (the canonical NeRF sees pts + rigid_dp, nerf.py:1303)
+            uint32_t v[32];
+            tmem_ld16(t_acc, v);
+            if (Lc.x > 16) tmem_ld16(t_acc + 16, v + 16);
+            tmem_ld_wait(); reg_fence16(v); reg_fence16(v + 16);
+            long long u; int sub; unit_of(P, slot, map.tpr, u, sub);
+            long long ray; int t;
+            float px = 0.f, py = 0.f, pz = 0.f;
+            if (map.locate(u, sub, row, a.n_rays, ray, t)) {
+              const float* rr = a.rays + ray * 6;
+              const float tt = __ldg(a.ts + ray * a.ts_stride + t);
+              px = nf_pt(__ldg(rr + 0), tt, __ldg(rr + 3)); py = nf_pt(__ldg(rr + 1), tt, __ldg(rr + 4)); pz = nf_pt(__ldg(rr + 2), tt, __ldg(rr + 5));
+              const int nsp = plan.spline_points;
+              if (nsp == 0) {
+                const float dp = __uint_as_float(v[0]) + bias[0];
+                px += dp * nf_sigmoid((__uint_as_float(v[1]) + bias[1]) / 2.f);
+                py += dp * nf_sigmoid((__uint_as_float(v[2]) + bias[2]) / 2.f);
+                pz += dp * nf_sigmoid((__uint_as_float(v[3]) + bias[3]) / 2.f);
+              } else {
+                const float rig = nf_sigmoid((__uint_as_float(v[0]) + bias[0]) / 2.f);
+                const float time = __ldg(a.ray_time + ray);
+                float d[3];
+#pragma unroll
+                for (int x = 0; x < 3; ++x) {
+                  float ps[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) ps[i] = i < nsp ? __uint_as_float(v[1 + 3 * i + x]) + bias[1 + 3 * i + x] : 0.f;
+                  d[x] = nf_bezier(ps, nsp, time) * rig;
+                }
+                px += d[0]; py += d[1]; pz += d[2];
+              }
+            }
+            if (cq == 0) { s.P[slot][0][row] = px; s.P[slot][1][row] = py; s.P[slot][2][row] = pz; }
+            hash_x0(X0, reinterpret_cast<const float4*>(a.packed + plan.hash_off), plan, px, py, pz, row, cq, 4);
+            if (cq == 0) hash_x0_tail(X0, plan, plan.mlp[0].k0_pad, px, py, pz, row);
           } else {
             // density MLP out (tensor order [inter(I), sigma]) -> raw x0 of the View head + raw density
             const int iu = plan.intermediate >> 4;
@@ -487,7 +543,8 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
                   const float* rr = a.rays + ray * 6;
                   const float tt = __ldg(a.ts + ray * a.ts_stride + t);
                   const float dx = __ldg(rr + 3), dy = __ldg(rr + 4), dz = __ldg(rr + 5);
-                  px = nf_pt(__ldg(rr + 0), tt, dx); py = nf_pt(__ldg(rr + 1), tt, dy); pz = nf_pt(__ldg(rr + 2), tt, dz);
+                  if (plan.kind == NF_KIND_DYN) { px = s.P[slot][0][row]; py = s.P[slot][1][row]; pz = s.P[slot][2][row]; }
+                  else { px = nf_pt(__ldg(rr + 0), tt, dx); py = nf_pt(__ldg(rr + 1), tt, dy); pz = nf_pt(__ldg(rr + 2), tt, dz); }
                   nf_elaz(dx, dy, dz, el, az);
                 }
                 uint8_t* d0 = X0 + (iu * 2) * KG_BYTES + row * 16;
@@ -528,7 +585,8 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
 bool build_prog3(const NfPlan& plan, Tc3Prog* P) {
   *P = Tc3Prog{};
   int nl = 0;
-  for (int m = 0; m < plan.n_mlps; ++m)
+  for (int mi = 0; mi < plan.n_mlps; ++mi) {
+    const int m = plan.kind == NF_KIND_DYN ? (mi + 2) % 3 : mi;          // execution order: deformation, density, View
     for (int j = 0; j < plan.mlp[m].n_lin; ++j, ++nl) {
       const NfLinPlan& L = plan.mlp[m].lin[j];
       const uint32_t nh = (uint32_t)L.n_pad >> 1, b_lbo = nh * 16u;
@@ -541,6 +599,7 @@ bool build_prog3(const NfPlan& plan, Tc3Prog* P) {
       if (L.w16h_off + 2 * half_bytes >= (1LL << 32)) return false;
       R.w_off = (uint32_t)L.w16h_off; R.half_bytes = (uint32_t)half_bytes; R.step_bytes = 2u * b_lbo;
     }
+  }
   P->n_lin = nl; P->lag = nl / 2;
   return true;
 }
@@ -549,14 +608,16 @@ bool build_prog3(const NfPlan& plan, Tc3Prog* P) {
 
 // nullptr if the staggered paired pipeline can run this model, else the reason.
 const char* nf_tc3_unsupported(const NfPlan& p) {
-  if (p.kind == NF_KIND_DYN) return "NF_KIND_DYN runs on the fp32 pipeline only in this build";
+  if (p.mip != NF_MIP_NONE) return "the Mip encoder (x0 134/165 wide) runs on the fp32 pipeline only";
+  if (p.kind == NF_KIND_DYN && p.enc != NF_ENC_HASH) return "NF_KIND_DYN: the canonical NeRF must be hash-encoded";
+  if (p.kind == NF_KIND_DYN && p.mlp[2].lin[p.mlp[2].n_lin - 1].n_pad > 32) return "deformation MLP with more than 32 outputs";
   int nlin = 0;
   for (int m = 0; m < p.n_mlps; ++m) {
     nlin += p.mlp[m].n_lin;
     if (p.mlp[m].k0_pad > X0K) return "x0 wider than 80 columns";
     for (int j = 0; j < p.mlp[m].n_lin; ++j) {
       // only the density MLP of a two-MLP model may end in a non-final `out` Linear
-      if (p.mlp[m].lin[j].is_out && m != p.n_mlps - 1 && !(p.kind == NF_KIND_PLAIN && m == 0)) return "unsupported MLP chain";
+      if (p.mlp[m].lin[j].is_out && p.kind == NF_KIND_TINY && m != 0) return "unsupported MLP chain";
     }
   }
   if (nlin > MAX_LIN3 || nlin < 2) return "unsupported number of Linear layers";
@@ -567,12 +628,13 @@ const char* nf_tc3_unsupported(const NfPlan& p) {
 }
 
 cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const float* rays, int64_t n_rays, const float* ts,
-                                 int T, int64_t ts_stride, const float* noise, float* rgb, float* alpha, float* weights,
+                                 int T, int64_t ts_stride, const float* noise, const float* ray_time, float* rgb, float* alpha, float* weights,
                                  cudaStream_t st) {
   if (nf_tc3_unsupported(plan)) return cudaErrorNotSupported;
   Tc3Args a{};
   a.packed = (const uint8_t*)packed; a.rays = rays; a.n_rays = n_rays; a.ts = ts; a.T = T; a.ts_stride = ts_stride;
-  a.noise = noise; a.rgb_out = rgb; a.alpha_out = alpha; a.weights_out = weights;
+  a.noise = noise; a.ray_time = ray_time; a.rgb_out = rgb; a.alpha_out = alpha; a.weights_out = weights;
+  if (plan.kind == NF_KIND_DYN && !ray_time) return cudaErrorInvalidValue;
   if (const char* dbg = getenv("NF_TC_DEBUG")) a.debug = atoi(dbg);
   // NF_TC_RING selects the weight-ring geometry (same 48 KB): "3" = 3 stages x 16 KB (default; measured faster: the single
   // issuing thread pays one probe + one commit per stage), "6" = 6 stages x 8 KB

@@ -358,9 +358,14 @@ def test_dnerf_direct_matches_reference_golden():
   o32 = eng.mlp_forward(2, xt.to(DEV), precision="fp32").cpu()
   o16 = eng.mlp_forward(2, xt.to(DEV), precision="fp16").cpu()
   assert float((o32 - ref).abs().max()) <= 1e-4 and float((o16 - ref).abs().max()) <= 2e-2
-  # the tensor pipeline does not take this kind yet: loud refusal, no fallback
+  # the older tensor pipelines do not take the three-MLP chain: loud refusal, no fallback to them
   canon.precision = "fp16"
-  with pytest.raises(RuntimeError): m((rays.to(DEV), torch.from_numpy(fx["times"]).to(DEV)))
+  import os
+  os.environ["NF_TC_PIPE"] = "2"
+  try:
+    with torch.no_grad(): o2 = m((rays.to(DEV), torch.from_numpy(fx["times"]).to(DEV)))     # DYN always runs on the staggered pipeline
+  finally: os.environ.pop("NF_TC_PIPE")
+  assert np.abs(o2.cpu().numpy() - fx["out"]).max() <= 2e-3
 
 
 def test_dnerf_spline_matches_reference_golden():
@@ -434,3 +439,42 @@ def test_mip_intended_encoder_vs_oracle(kind):
     out = rgb.cpu().numpy().reshape(ref["out"].shape)
     assert np.isfinite(out).all()
     assert np.abs(out - ref["out"].numpy()).max() <= 5e-5, (kind, T, np.abs(out - ref["out"].numpy()).max())
+
+
+@pytest.mark.parametrize("name,spline", [("dnerf_direct_t64", 0), ("dnerf_spline5_t32", 5), ("dnerf_spline4_t32", 4)])
+def test_dnerf_tensor_pipeline(name, spline):
+  """BASELINE config 5 on the tensor cores: deformation MLP -> deformed hash encode -> canonical density MLP -> View head ->
+  composite as ONE 19-Linear chain of the staggered pipeline (fp16 operands), vs the reference golden (fp32) and the
+  oracle's fp16-operand emulation; plus a 400-ray x 64-sample slab for determinism and shard == whole."""
+  import nerf_atlas_b200 as N
+  fx = load_golden(name)
+  P = O.make_dnerf_spline_params(int(fx["seed"]), spline, 64) if spline else O.make_dnerf_params(int(fx["seed"]), 64)
+  rays = O.make_rays(int(fx["B"]), int(fx["H"]), int(fx["W"]), 800, int(fx["seed"]), int(fx["top"]), int(fx["left"]))
+  times = torch.from_numpy(fx["times"])
+  canon = N.FusedPlainNeRF(steps=int(fx["T"]), t_near=float(fx["near"]), t_far=float(fx["far"]), intermediate_size=64,
+                           sigmoid_kind=str(fx["sigmoid"]), bg=str(fx["bg"]), precision="fp16")
+  m = N.FusedDynamicNeRF(canon, spline=spline)
+  m.load_state_dict(P, strict=True); m = m.to(DEV).eval()
+  with torch.no_grad(): out = m((rays.to(DEV), times.to(DEV))).cpu().numpy()
+  ts = O.compute_ts(float(fx["near"]), float(fx["far"]), int(fx["T"]))
+  with torch.no_grad():
+    refq = (O.dnerf_spline_forward(P, rays, times, ts, spline, quant=torch.float16) if spline
+            else O.dnerf_direct_forward(P, rays, times, ts, quant=torch.float16))["out"].numpy()
+  assert np.isfinite(out).all()
+  assert np.abs(out - fx["out"]).max() <= 2e-3, (name, np.abs(out - fx["out"]).max())       # vs the fp32 reference run
+  assert np.abs(out - refq).max() <= 1e-3, (name, np.abs(out - refq).max())                 # vs the fp16-operand emulation
+  assert psnr(out, fx["out"]) >= 60.0
+  # config-5 shaped slab: 64 samples/ray (two rays per 128-sample tile), ragged ray count
+  eng = m.engine()
+  g = torch.Generator().manual_seed(3)
+  big = O.make_rays(1, 20, 20, seed=9, crop_top=390, crop_left=390).reshape(-1, 6)[:397].to(DEV)
+  rt = torch.rand(397, generator=g).to(DEV)
+  ts64 = torch.linspace(2, 6, 64, device=DEV)
+  a, _, _ = eng.render(big, ts64, ray_time=rt, want_weights=False)
+  b, _, _ = eng.render(big, ts64, ray_time=rt, want_weights=False)
+  assert torch.equal(a, b) and torch.isfinite(a).all()
+  c1, _, _ = eng.render(big[:150].contiguous(), ts64, ray_time=rt[:150].contiguous(), want_weights=False)
+  c2, _, _ = eng.render(big[150:].contiguous(), ts64, ray_time=rt[150:].contiguous(), want_weights=False)
+  assert torch.equal(torch.cat([c1, c2]), a)
+  f32, _, _ = eng.render(big, ts64, ray_time=rt, want_weights=False, precision="fp32")
+  assert float((a - f32).abs().max()) <= 2e-3
