@@ -100,6 +100,26 @@ __device__ __forceinline__ void wait_acc(uint32_t bar, uint32_t parity, int debu
   mbar_wait_suspend(bar, parity);
 }
 
+// sin on the FMA pipe: the MUFU unit retires 16 sines per cycle per SM, so a 128 x 256 sin epilogue cannot finish in less than
+// 2048 cycles -- as long as the layer's MMAs.  A share of every 16 columns (NF_SIN_POLY_PAIRS of the 8 column pairs) takes
+// this route instead: revolutions t = x / 2pi, r = t - rint(t) in [-0.5, 0.5] (magic-number rounding), then an odd degree-9
+// minimax polynomial for sin(2 pi r): max error 6.3e-6, far inside the fp16 rounding of the result (2.4e-4).
+// MEASURED (profiles/r01_sin_poly_sweep.txt): 0 pairs 113.8 ms/frame, 2 pairs 115.0, 3 pairs 116.2, 4 pairs 119.7 -- the sin
+// epilogue is not MUFU-throughput-bound but issue/latency-bound, so the extra FMA-pipe instructions only cost.  Default 0.
+#ifndef NF_SIN_POLY_PAIRS
+#define NF_SIN_POLY_PAIRS 0
+#endif
+__device__ __forceinline__ float sin_poly(float x) {
+  const float t = x * 0.15915494309189535f;
+  const float k = (t + 12582912.f) - 12582912.f;
+  const float r = t - k, r2 = r * r;
+  float p = fmaf(32.78138732910156f, r2, -74.47799682617188f);
+  p = fmaf(p, r2, 81.36681365966797f);
+  p = fmaf(p, r2, -41.331214904785156f);
+  p = fmaf(p, r2, 6.283055782318115f);
+  return p * r;
+}
+
 // ---- epilogue of a hidden Linear: H <- fp16(act(acc + bias)), bias from shared memory ---------------------
 template <int ACT>
 __device__ __forceinline__ void epi_hidden3(uint8_t* __restrict__ H, uint32_t t_acc, const float* __restrict__ bias_s, int cq, int row) {
@@ -117,9 +137,55 @@ __device__ __forceinline__ void epi_hidden3(uint8_t* __restrict__ H, uint32_t t_
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float4 b = b4[i];                                 // same address in every lane: one broadcast wavefront
-      o[2 * i]     = act_pack_t<ACT>(__uint_as_float(v[u & 1][4 * i]) + b.x, __uint_as_float(v[u & 1][4 * i + 1]) + b.y);
-      o[2 * i + 1] = act_pack_t<ACT>(__uint_as_float(v[u & 1][4 * i + 2]) + b.z, __uint_as_float(v[u & 1][4 * i + 3]) + b.w);
+      const float x0 = __uint_as_float(v[u & 1][4 * i]) + b.x, x1 = __uint_as_float(v[u & 1][4 * i + 1]) + b.y;
+      const float x2 = __uint_as_float(v[u & 1][4 * i + 2]) + b.z, x3 = __uint_as_float(v[u & 1][4 * i + 3]) + b.w;
+      if (ACT == NF_ACT_SIN && 2 * i < NF_SIN_POLY_PAIRS) o[2 * i] = pack_h2(sin_poly(x0), sin_poly(x1));
+      else o[2 * i] = act_pack_t<ACT>(x0, x1);
+      if (ACT == NF_ACT_SIN && 2 * i + 1 < NF_SIN_POLY_PAIRS) o[2 * i + 1] = pack_h2(sin_poly(x2), sin_poly(x3));
+      else o[2 * i + 1] = act_pack_t<ACT>(x2, x3);
     }
+    uint8_t* dst = H + (col >> 3) * KG_BYTES + row * 16;
+    st_v4(dst, o[0], o[1], o[2], o[3]); st_v4(dst + KG_BYTES, o[4], o[5], o[6], o[7]);
+  }
+}
+
+// sin epilogue, software-pipelined by hand across the 16-column units: the 16 MUFU.SINs of unit u are ISSUED first, then the
+// warp waits for unit u+1's TMEM load and does its bias add + range scaling while the MUFU results arrive, and only then packs
+// and stores unit u.  (ptxas cannot do this itself: the TMEM wait is an ordering point.)
+__device__ __forceinline__ float mufu_sin(float t) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(t)); return y; }
+__device__ __forceinline__ void epi_hidden3_sin_pipelined(uint8_t* __restrict__ H, uint32_t t_acc, const float* __restrict__ bias_s, int cq, int row) {
+  uint32_t v[16];
+  float x[16], y[16];
+  tmem_ld16(t_acc + cq * 64, v);
+  tmem_ld_wait(); reg_fence16(v);
+  {
+    const float4* b4 = reinterpret_cast<const float4*>(bias_s + cq * 64);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 b = b4[i];
+      x[4 * i] = __uint_as_float(v[4 * i]) + b.x; x[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b.y;
+      x[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b.z; x[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b.w;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int col = cq * 64 + u * 16;
+    if (u < 3) tmem_ld16(t_acc + col + 16, v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) y[i] = mufu_sin(x[i]);            // issue the unit's sines ...
+    if (u < 3) {
+      tmem_ld_wait(); reg_fence16(v);                                      // ... and prepare the next unit while they execute
+      const float4* b4 = reinterpret_cast<const float4*>(bias_s + col + 16);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 b = b4[i];
+        x[4 * i] = __uint_as_float(v[4 * i]) + b.x; x[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b.y;
+        x[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b.z; x[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b.w;
+      }
+    }
+    uint32_t o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = pack_h2(y[2 * i], y[2 * i + 1]);
     uint8_t* dst = H + (col >> 3) * KG_BYTES + row * 16;
     st_v4(dst, o[0], o[1], o[2], o[3]); st_v4(dst + KG_BYTES, o[4], o[5], o[6], o[7]);
   }
@@ -337,6 +403,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
       const uint32_t a_lbo = (uint32_t)(KG_BYTES >> 4) << 16, kstep4 = (uint32_t)(2 * KG_BYTES) >> 4;
       int li0 = 0, li1 = 0;
       bool w_ok = false;                               // ring stage `stage` is known to be full
+      const bool no_mma = (a.debug & 2) != 0;
       ST_DECL;
       for (int k = 0; k < nsteps + lag; ++k) {
 #pragma unroll 1
@@ -361,7 +428,9 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
             w_ok = mbar_test_wait(bar_wready + nstage * 8u, nphase);       // consumed on the next iteration
             tc_fence_after();
             const uint32_t b4 = (w4 + stage * (uint32_t)(STAGE_BYTES >> 4)) | bhi;
-            if (gs0 + SPCT <= total && (gs0 + SPCT <= k0s || gs0 >= k0s)) {
+            if (no_mma) {
+              // timing experiment (NF_TC_DEBUG & 2): every barrier and copy, but no tensor work
+            } else if (gs0 + SPCT <= total && (gs0 + SPCT <= k0s || gs0 >= k0s)) {
               // fast path: a full chunk fed from one buffer -> back-to-back MMAs, operands differ by constants
               const uint32_t a4 = gs0 < k0s ? x4 + gs0 * kstep4 : h4 + (gs0 - k0s) * kstep4;
               umma2_f16(d_tmem, umma_desc_lo(a4), umma_desc_lo(b4), idesc, gs0 > 0 ? 1u : 0u);
@@ -406,6 +475,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
         const uint32_t t_acc = t_lane + (uint32_t)slot * 256u;
         const uint32_t a_ready_leader = leader_addr(smem_u32(&s.a_ready[slot]));
         const bool has_next = kl < nsteps;              // Linear j of this slot runs after this phase
+        const int comp_cq = 2 * slot, tail_cq = 2 * slot + 1;
         // bias of Linear j (consumed by this slot's NEXT phase): in flight across the acc_full wait
         float bnext = 0.f; bool bload = false;
         if (has_next) {
@@ -424,8 +494,11 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
 
         if (j == 0) {
           // ---------- tile boundary: composite of pass P-1 (cq == 0 warps) while the others start encoding pass P ----------
+          // Duties that only one warp per lane quarter can do rotate with the slot, so that no column quarter becomes the
+          // critical path (measured: the composite is ~4.9 K cycles, the View-x0 unit ~1.5 K, the x0 tail ~1.4 K):
+          //   composite: cq == 2 * slot;  x0 tail / View-x0 unit: cq == 2 * slot + 1
           const bool comp = P >= 1;
-          if (comp && cq == 0) {
+          if (comp && cq == comp_cq) {
             long long u; int sub; unit_of(P - 1, slot, map.tpr, u, sub);
             uint32_t v[16];
             tmem_ld16(t_acc, v); tmem_ld_wait(); reg_fence16(v);
@@ -438,7 +511,9 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
               cr = __uint_as_float(v[0]) + bias[0]; cg = __uint_as_float(v[1]) + bias[1]; cb = __uint_as_float(v[2]) + bias[2];
             }
             cr = nf_feat_act_fn(cr, plan.feat_act); cg = nf_feat_act_fn(cg, plan.feat_act); cb = nf_feat_act_fn(cb, plan.feat_act);
+            ST_ADD(6);
             composite_tile3(s, slot, plan, a, map, u, sub, row, lane, q, cr, cg, cb);
+            ST_ADD(5);
           }
           if (has_next) {
             long long u; int sub; unit_of(P, slot, map.tpr, u, sub);
@@ -457,8 +532,8 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
             const bool hashed = dyn ? plan.deform_enc == NF_ENC_HASH : plan.enc == NF_ENC_HASH;
             if (hashed)
               hash_x0(X0, reinterpret_cast<const float4*>(a.packed + (dyn ? plan.hash2_off : plan.hash_off)), plan, px, py, pz, row,
-                      comp ? cq - 1 : cq, comp ? 3 : 4);
-            if (cq == 0) {
+                      comp ? (cq == comp_cq ? -1 : ((cq - comp_cq - 1) & 3)) : cq, comp ? 3 : 4);
+            if (cq == tail_cq) {
               if (hashed) hash_x0_tail(X0, plan, plan.mlp[first_m].k0_pad, px, py, pz, row);
               else {
                 const float tt = (dyn && ok) ? __ldg(a.ray_time + ray) : 0.f;        // direct deformation: x0 = [p, t]
@@ -475,12 +550,22 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
           ST_ADD(1);
         } else {
           // ---------- epilogue of Linear j-1 ----------
+          if (j == n - 2 && cq == 1 && P + 1 < passes) {
+            // the next tile's rays are a first touch (HBM, ~2 K cycles): pull them into L2 two phases before phase 0 needs them
+            long long u; int sub; unit_of(P + 1, slot, map.tpr, u, sub);
+            long long ray; int t;
+            if (map.locate(u, sub, row, a.n_rays, ray, t)) {
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(a.rays + ray * 6));
+              if (a.ts_stride) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.ts + ray * a.ts_stride + t));
+              if (a.noise) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.noise + ray * a.T + t));
+            }
+          }
           const int4 Lc = s.lin[j - 1][0];
           const int act = Lc.z;
           const bool is_out = (Lc.w & 1) != 0;
           if (!is_out) {
             if (Lc.w & 2) x0_activate3(X0, s.lin[j - 1][1].x, act, e_tid);       // init consumed raw x0; the skip Linear wants act(x0)
-            if (act == NF_ACT_SIN) epi_hidden3<NF_ACT_SIN>(H, t_acc, bias, cq, row);
+            if (act == NF_ACT_SIN) { if (a.debug & 2048) epi_hidden3<NF_ACT_SIN>(H, t_acc, bias, cq, row); else epi_hidden3_sin_pipelined(H, t_acc, bias, cq, row); }
             else if (act == NF_ACT_LEAKY) epi_hidden3<NF_ACT_LEAKY>(H, t_acc, bias, cq, row);
             else if (act == NF_ACT_RELU) epi_hidden3<NF_ACT_RELU>(H, t_acc, bias, cq, row);
             else epi_hidden3<NF_ACT_NONE>(H, t_acc, bias, cq, row);
@@ -518,13 +603,16 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
                 px += d[0]; py += d[1]; pz += d[2];
               }
             }
-            if (cq == 0) { s.P[slot][0][row] = px; s.P[slot][1][row] = py; s.P[slot][2][row] = pz; }
+            if (cq == tail_cq) { s.P[slot][0][row] = px; s.P[slot][1][row] = py; s.P[slot][2][row] = pz; }
             hash_x0(X0, reinterpret_cast<const float4*>(a.packed + plan.hash_off), plan, px, py, pz, row, cq, 4);
-            if (cq == 0) hash_x0_tail(X0, plan, plan.mlp[0].k0_pad, px, py, pz, row);
+            if (cq == tail_cq) hash_x0_tail(X0, plan, plan.mlp[0].k0_pad, px, py, pz, row);
           } else {
             // density MLP out (tensor order [inter(I), sigma]) -> raw x0 of the View head + raw density
             const int iu = plan.intermediate >> 4;
-            for (int un = cq; un <= iu; un += 4) {
+            for (int un0 = cq; un0 < iu + 4; un0 += 4) {
+              // units 0..iu-1 (intermediate columns) are dealt round-robin; the last unit (sigma + View x0 tail) goes to tail_cq
+              int un = un0;
+              if (un0 >= iu) { if (cq != tail_cq) break; un = iu; }
               uint32_t v[16];
               tmem_ld16(t_acc + un * 16, v); tmem_ld_wait(); reg_fence16(v);
               if (un < iu) {
@@ -669,7 +757,7 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
     long long h[64];
     cudaMemcpy(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost);
     const char* names[5] = {"issuer  [total, wait_a, wait_w, issue+other, n_w_waits]", "producer0 [total, wait_empty, copy, other, n]",
-                            "epi w0  [total, wait_acc, phase0, leaky, sin, dens_out, other]", "epi w15 [same]", "epi w0 of the peer CTA [same]"};
+                            "epi w0  [total, wait_acc, phase0-encode, leaky, sin, dens_out, other+composite, colour-read]", "epi w15 [same]", "epi w0 of the peer CTA [same]"};
     for (int r = 0; r < 5; ++r) {
       printf("STATS %s:", names[r]);
       for (int i = 0; i < 8; ++i) printf(" %lld", h[r * 8 + i]);

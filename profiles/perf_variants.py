@@ -14,9 +14,7 @@ from oracle import nerf_oracle as O   # synthetic inputs only
 VARIANTS = [
   ("pipe2_lockstep", {"NF_TC_PIPE": "2"}),
   ("pipe3_ring3x16", {"NF_TC_PIPE": "3", "NF_TC_RING": "3"}),
-  ("pipe3_ring3x16_producer_backoff", {"NF_TC_PIPE": "3", "NF_TC_RING": "3", "NF_TC_DEBUG": "1024"}),
-  ("pipe3_ring3x16_hint64", {"NF_TC_PIPE": "3", "NF_TC_RING": "3", "NF_TC_DEBUG": "512"}),
-  ("pipe3_ring3x16_hint64_producer_backoff", {"NF_TC_PIPE": "3", "NF_TC_RING": "3", "NF_TC_DEBUG": "1536"}),
+  ("pipe3_ring3x16_plain_sin_epilogue", {"NF_TC_PIPE": "3", "NF_TC_RING": "3", "NF_TC_DEBUG": "2048"}),
   ("pipe3_ring6x8", {"NF_TC_PIPE": "3", "NF_TC_RING": "6"}),
   ("pipe1_single_cta", {"NF_TC_PIPE": "1"}),
 ]
