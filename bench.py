@@ -8,7 +8,7 @@ One step = one full forward render of one synthetic 800x800 view at 128 samples/
 head, hash encoder, I=64: the configuration BASELINE.json's metric is quoted on) per GPU.  Prints ONE
 JSON line (contract in the task statement): `value` = whole-job rays/s with rays resident in HBM,
 `e2e` = the same through the public FusedPlainNeRF.forward call with pinned HOST rays in and HOST rgb
-out, `roofline` for the dominant kernel (k_render_tc, tensor-bound), `cpu_baseline` = the CPU oracle
+out, `roofline` for the dominant kernel (k_render_tc3, the staggered paired tcgen05 pipeline; tensor-bound), `cpu_baseline` = the CPU oracle
 port timed on this box's host cores on a bounded sample.
 """
 import argparse, json, os, statistics, subprocess, sys, threading, time
@@ -171,7 +171,8 @@ def run_ours(args):
   value = total_rays / (ms * 1e-3)
   e2e = total_rays / (ms_e2e * 1e-3)
   peak, peak_src = peaks()
-  # dominant kernel = k_render_tc2 (paired pipeline): exactly one launch per step; its average duration IS the step (events on the launch stream)
+  # dominant kernel = k_render_tc3 (staggered paired pipeline): exactly one launch per step; its average duration IS the step
+  # (events on the launch stream)
   kern_ms = ms / args.steps
   achieved = RAYS_PER_FRAME * T * FLOP_PER_SAMPLE / (kern_ms * 1e-3) / 1e12
   traffic = None
@@ -187,7 +188,7 @@ def run_ours(args):
     line = {
       "metric": "rays_per_sec_800x800x128", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
       "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-      "dtype": "f16 operands / f32 accumulate (tcgen05 kind::f16)", "data": "synthetic",
+      "dtype": "f16", "dtype_note": "fp16 operands, fp32 accumulate in TMEM (tcgen05 kind::f16); everything outside the GEMMs fp32", "data": "synthetic",
       "config": {"workload": "PlainNeRF+View (hash enc, I=64) forward render, one 800x800 view x 128 samples/ray per GPU per step, near 2 far 6",
                  "rays_per_step_per_gpu": RAYS_PER_FRAME, "samples_per_ray": T, "weights": "seeded random init (reference distributions)",
                  "l2": f"inputs rotate over {N_VIEWS} distinct views = {N_VIEWS * RAYS_PER_FRAME * 24 / 1e6:.0f} MB of rays > 126 MB L2",
@@ -197,7 +198,7 @@ def run_ours(args):
               "ms_per_step": ms_e2e / args.steps, "api": "FusedPlainNeRF.forward(rays) with pinned host rays in, host rgb out"},
       "gpu_launches": args.steps,
       "clocks": clocks,
-      "roofline": {"bound": "tensor", "kernel": "k_render_tc2 (paired cta_group::2 pipeline)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+      "roofline": {"bound": "tensor", "kernel": "k_render_tc3 (staggered paired cta_group::2 pipeline)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                    "traffic": traffic, "peak_source": peak_src,
                    "algorithmic": f"{FLOP_PER_SAMPLE} FLOP/sample x {RAYS_PER_FRAME * T} samples per launch"},
     }

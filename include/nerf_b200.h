@@ -164,6 +164,15 @@ int nf_render_forward(const nf_model_desc* desc, const void* packed,
                       int32_t precision, void* stream);
 
 /* ---- stages of the path, exported for parity tests and micro-benchmarks -- */
+/* Camera rays of a crop: runner.render's pixel grid + NeRFCamera.sample_positions with_noise=False
+ * (reference runner.py:490-505, src/cameras.py:45-66):  pixel (row top+h, column left+w) of view b ->
+ *   d = [(u - size/2) / focal, -(v - size/2) / focal, -1],  u = column, v = row
+ *   r_d[c] = (d0*R[c][0] + d1*R[c][1]) + d2*R[c][2]  (R = cam_to_world[b,:3,:3]; NOT normalised),  r_o = cam_to_world[b,:3,3]
+ * cam_to_world is a DEVICE pointer to [B,3,4] fp32; rays_out[B,H,W,6].  Bit-exact against the reference camera.
+ * scalar_div_as_reciprocal = 0: IEEE division by fp32(focal) (what torch does on the CPU); 1: multiply by 1.0f/focal (what
+ * torch's CUDA kernel does when dividing by a Python scalar) -- pick the device the reference ran on. */
+int nf_generate_rays(const float* cam_to_world, int64_t B, float focal, int32_t size, int32_t top, int32_t left,
+                     int32_t H, int32_t W, int32_t scalar_div_as_reciprocal, float* rays_out, void* stream);
 /* radii_x (reference src/utils.py:77-81) on a crop of rays[B,H,W,6] (H >= 3): radius_out[B,H,W] = |r_d[h] - r_d[h+1]| * 2/sqrt(12),
  * the last row repeating difference H-3 exactly like the reference's `dx[:, -2:-1, :]`. */
 int nf_ray_radii(const float* rays, int64_t B, int32_t H, int32_t W, float* radius_out, void* stream);

@@ -142,6 +142,15 @@ int nf_render_forward(const nf_model_desc* desc, const void* packed, const float
   return 0;
 }
 
+int nf_generate_rays(const float* cam_to_world, int64_t B, float focal, int32_t size, int32_t top, int32_t left,
+                     int32_t H, int32_t W, int32_t scalar_div_as_reciprocal, float* rays_out, void* stream) {
+  if (B < 0 || H < 0 || W < 0 || size <= 0 || !(focal > 0.f)) return fail(NF_E_BADARG, "nf_generate_rays: bad size / focal");
+  if (B == 0 || H == 0 || W == 0) return 0;
+  if (!cam_to_world || !rays_out) return fail(NF_E_BADARG, "nf_generate_rays: null pointer");
+  cudaError_t e = nf_launch_generate_rays(cam_to_world, B, focal, size, top, left, H, W, scalar_div_as_reciprocal ? 1 : 0, rays_out, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nf_generate_rays");
+}
+
 int nf_ray_radii(const float* rays, int64_t B, int32_t H, int32_t W, float* radius_out, void* stream) {
   if (B < 0 || H < 0 || W < 0) return fail(NF_E_BADARG, "nf_ray_radii: negative size");
   if (B == 0 || W == 0 || H == 0) return 0;

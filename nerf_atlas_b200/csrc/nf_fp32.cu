@@ -431,6 +431,27 @@ __global__ void k_sample_pdf(const float* __restrict__ ts, int T, const float* _
   }
 }
 
+// runner.render's pixel grid + NeRFCamera.sample_positions (reference runner.py:490-505, src/cameras.py:45-66): one thread per ray
+__global__ void k_generate_rays(const float* __restrict__ c2w, long long B, float focal, float half, int top, int left, int H, int W,
+                                int recip, float* __restrict__ out) {
+  const long long total = B * H * W;
+  const float inv = __fdiv_rn(1.f, focal);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W); const int h = (int)((i / W) % H); const long long b = i / ((long long)W * H);
+    const float u = (float)(left + w), v = (float)(top + h);
+    const float a0 = __fsub_rn(u, half), a1 = __fsub_rn(v, half);
+    const float d0 = recip ? __fmul_rn(a0, inv) : __fdiv_rn(a0, focal);
+    const float d1 = -(recip ? __fmul_rn(a1, inv) : __fdiv_rn(a1, focal));
+    const float* M = c2w + b * 12;
+    float* o = out + i * 6;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      o[c] = __ldg(M + c * 4 + 3);
+      o[3 + c] = __fadd_rn(__fadd_rn(__fmul_rn(d0, __ldg(M + c * 4)), __fmul_rn(d1, __ldg(M + c * 4 + 1))), __fmul_rn(-1.f, __ldg(M + c * 4 + 2)));
+    }
+  }
+}
+
 // radii_x, reference src/utils.py:77-81: one thread per ray of the [B,H,W] crop
 __global__ void k_ray_radii(const float* __restrict__ rays, long long B, int H, int W, float* __restrict__ out) {
   const long long total = B * H * W;
@@ -470,6 +491,16 @@ int num_sms() {
 cudaError_t nf_launch_pack_fp32(const float* W, const float* b, float* Wt, float* bp, int n, int k, int n_pad, cudaStream_t st) {
   const int total = k * n_pad;
   k_pack_fp32<<<(total + 255) / 256, 256, 0, st>>>(W, b, Wt, bp, n, k, n_pad);
+  return cudaGetLastError();
+}
+
+cudaError_t nf_launch_generate_rays(const float* c2w, int64_t B, float focal, int size, int top, int left, int H, int W, int recip,
+                                    float* out, cudaStream_t st) {
+  const long long total = B * H * W;
+  if (total == 0) return cudaSuccess;
+  const long long want = (total + 255) / 256;
+  const int grid = (int)(want < (long long)num_sms() * 8 ? want : (long long)num_sms() * 8);
+  k_generate_rays<<<grid, 256, 0, st>>>(c2w, B, focal, (float)size * 0.5f, top, left, H, W, recip, out);
   return cudaGetLastError();
 }
 

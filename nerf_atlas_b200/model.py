@@ -169,6 +169,24 @@ class RenderEngine:
   def _need_packed(self):
     if self.packed is None: raise RuntimeError("RenderEngine.pack(params) has not been called")
 
+  @staticmethod
+  def generate_rays(cam_to_world: torch.Tensor, focal: float, size: int, crop=None, reference_device: str = "cpu") -> torch.Tensor:
+    """runner.render's pixel grid + NeRFCamera.sample_positions(with_noise=False) (reference runner.py:490-505,
+    src/cameras.py:45-66) in one launch: cam_to_world[B,3,4] (CUDA) -> rays[B,H,W,6]; crop = (top, left, H, W), default the
+    whole size x size image.  ``reference_device``: "cpu" = IEEE division by focal, "cuda" = torch's CUDA scalar-division
+    (multiply by 1/focal); the two differ in the last bit of r_d."""
+    _chk(cam_to_world, "cam_to_world")
+    if cam_to_world.dim() != 3 or tuple(cam_to_world.shape[1:]) != (3, 4): raise ValueError("cam_to_world must be [B,3,4]")
+    t, l, h, w = crop if crop is not None else (0, 0, size, size)
+    B = cam_to_world.shape[0]
+    rays = torch.empty(B, h, w, 6, dtype=torch.float32, device=cam_to_world.device)
+    lib = _lib.lib()
+    with torch.cuda.device(cam_to_world.device):
+      rc = lib.nf_generate_rays(_ptr(cam_to_world), B, float(focal), int(size), int(t), int(l), int(h), int(w),
+                                1 if reference_device == "cuda" else 0, _ptr(rays), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc, "nf_generate_rays")
+    return rays
+
   def ray_radii(self, rays_bhw: torch.Tensor) -> torch.Tensor:
     """radii_x (reference src/utils.py:77-81) of a crop rays[B,H,W,6] -> [B,H,W]."""
     _chk(rays_bhw, "rays")

@@ -645,12 +645,9 @@ def make_dnerf_spline_params(seed: int = 9, n: int = 5, intermediate: int = 64, 
   return P
 
 
-def make_rays(n_views: int, h: int, w: int, size: int = 800, seed: int = 0,
-              crop_top: int = 0, crop_left: int = 0, radius: float = 4.0) -> Tensor:
-  """``rays[B,H,W,6]`` exactly as runner.render + NeRFCamera.sample_positions build
-  them (reference runner.py:495-505, src/cameras.py:45-66; ``with_noise=False``):
-  lego-like geometry, focal from camera_angle_x=0.6911112 (loaders.py:83), camera
-  on a radius-4 sphere looking at the origin.  r_d is NOT normalised."""
+def make_cameras(n_views: int, size: int = 800, seed: int = 0, radius: float = 4.0):
+  """(cam_to_world[B,3,4] fp32, focal) of ``make_rays``: lego-like geometry, focal from camera_angle_x=0.6911112
+  (loaders.py:83), cameras on a radius-4 sphere looking at the origin."""
   g = np.random.default_rng(seed)
   focal = 0.5 * size / math.tan(0.5 * 0.6911112)
   c2w = []
@@ -662,7 +659,14 @@ def make_rays(n_views: int, h: int, w: int, size: int = 800, seed: int = 0,
     up = np.cross(right, fwd)
     m = np.eye(4); m[:3, 0], m[:3, 1], m[:3, 2], m[:3, 3] = right, up, -fwd, eye
     c2w.append(m[:3, :4])
-  c2w = torch.from_numpy(np.stack(c2w).astype(np.float32))
+  return torch.from_numpy(np.stack(c2w).astype(np.float32)), focal
+
+
+def make_rays(n_views: int, h: int, w: int, size: int = 800, seed: int = 0,
+              crop_top: int = 0, crop_left: int = 0, radius: float = 4.0) -> Tensor:
+  """``rays[B,H,W,6]`` exactly as runner.render + NeRFCamera.sample_positions build
+  them (reference runner.py:495-505, src/cameras.py:45-66; ``with_noise=False``).  r_d is NOT normalised."""
+  c2w, focal = make_cameras(n_views, size, seed, radius)
   ii, jj = torch.meshgrid(torch.arange(size, dtype=torch.float), torch.arange(size, dtype=torch.float), indexing="ij")
   positions = torch.stack([ii.transpose(-1, -2), jj.transpose(-1, -2)], dim=-1)
   positions = positions[crop_top:crop_top + h, crop_left:crop_left + w, :]

@@ -478,3 +478,19 @@ def test_dnerf_tensor_pipeline(name, spline):
   assert torch.equal(torch.cat([c1, c2]), a)
   f32, _, _ = eng.render(big, ts64, ray_time=rt, want_weights=False, precision="fp32")
   assert float((a - f32).abs().max()) <= 2e-3
+
+
+# ---------------------------------------------------------------- camera rays (SURVEY f-2)
+def test_generate_rays_bit_exact_vs_reference_camera():
+  """nf_generate_rays == runner.render's pixel grid + NeRFCamera.sample_positions (make_rays is checked against the
+  reference camera with torch.equal when the goldens are generated): whole image, crops, several views; then rendering
+  from generated rays == rendering from the oracle's rays."""
+  import nerf_atlas_b200 as N
+  for size, B, crop in ((800, 2, None), (800, 3, (123, 456, 37, 41)), (64, 1, (0, 0, 64, 64)), (400, 2, (399, 0, 1, 400))):
+    c2w, focal = O.make_cameras(B, size, seed=size + B)
+    t, l, h, w = crop if crop else (0, 0, size, size)
+    ref = O.make_rays(B, h, w, size=size, seed=size + B, crop_top=t, crop_left=l)
+    got = N.RenderEngine.generate_rays(c2w.to(DEV), focal, size, crop)
+    assert got.shape == ref.shape and torch.equal(got.cpu(), ref), (size, B, crop)
+  alt = N.RenderEngine.generate_rays(c2w.to(DEV), focal, size, crop, reference_device="cuda")     # torch-CUDA scalar division
+  assert float((alt.cpu() - ref).abs().max()) <= 2e-7
