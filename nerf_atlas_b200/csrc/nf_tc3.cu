@@ -31,7 +31,6 @@ using namespace nf_ptx;
 
 constexpr int X0K = 80;
 constexpr int RING_BYTES = 48 * 1024;                       // weight ring per CTA: NST stages of SPCT K-steps (4 KB each at N = 256)
-constexpr int EPI_THREADS = 512;
 constexpr int MAX_LIN3 = 24;
 constexpr int MAX_STAGES3 = 6;
 
@@ -121,17 +120,21 @@ __device__ __forceinline__ float sin_poly(float x) {
 }
 
 // ---- epilogue of a hidden Linear: H <- fp16(act(acc + bias)), bias from shared memory ---------------------
-template <int ACT>
+template <int ACT, int NCQ>
 __device__ __forceinline__ void epi_hidden3(uint8_t* __restrict__ H, uint32_t t_acc, const float* __restrict__ bias_s, int cq, int row) {
-  // this warp's 64-column quarter = 4 units of 16 columns; unit u+1's TMEM load is in flight while unit u is converted
+  // the 16 units of 16 columns are dealt round-robin to the NCQ warps of a lane quarter (unit = cq, cq + NCQ, ...); the next
+  // unit's TMEM load is in flight while this one is converted
   uint32_t v[2][16];
-  tmem_ld16(t_acc + cq * 64, v[0]);
+  tmem_ld16(t_acc + cq * 16, v[0]);
+  constexpr int MAXU = (16 + NCQ - 1) / NCQ;
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int col = cq * 64 + u * 16;
+  for (int u = 0; u < MAXU; ++u) {
+    const int un = cq + u * NCQ;
+    if (un >= 16) break;
+    const int col = un * 16;
     tmem_ld_wait();
     reg_fence16(v[u & 1]);
-    if (u < 3) tmem_ld16(t_acc + col + 16, v[(u + 1) & 1]);
+    if (un + NCQ < 16) tmem_ld16(t_acc + col + NCQ * 16, v[(u + 1) & 1]);
     const float4* b4 = reinterpret_cast<const float4*>(bias_s + col);
     uint32_t o[8];
 #pragma unroll
@@ -153,13 +156,14 @@ __device__ __forceinline__ void epi_hidden3(uint8_t* __restrict__ H, uint32_t t_
 // warp waits for unit u+1's TMEM load and does its bias add + range scaling while the MUFU results arrive, and only then packs
 // and stores unit u.  (ptxas cannot do this itself: the TMEM wait is an ordering point.)
 __device__ __forceinline__ float mufu_sin(float t) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(t)); return y; }
+template <int NCQ>
 __device__ __forceinline__ void epi_hidden3_sin_pipelined(uint8_t* __restrict__ H, uint32_t t_acc, const float* __restrict__ bias_s, int cq, int row) {
   uint32_t v[16];
   float x[16], y[16];
-  tmem_ld16(t_acc + cq * 64, v);
+  tmem_ld16(t_acc + cq * 16, v);
   tmem_ld_wait(); reg_fence16(v);
   {
-    const float4* b4 = reinterpret_cast<const float4*>(bias_s + cq * 64);
+    const float4* b4 = reinterpret_cast<const float4*>(bias_s + cq * 16);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float4 b = b4[i];
@@ -167,15 +171,19 @@ __device__ __forceinline__ void epi_hidden3_sin_pipelined(uint8_t* __restrict__ 
       x[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b.z; x[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b.w;
     }
   }
+  constexpr int MAXU = (16 + NCQ - 1) / NCQ;
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int col = cq * 64 + u * 16;
-    if (u < 3) tmem_ld16(t_acc + col + 16, v);
+  for (int u = 0; u < MAXU; ++u) {
+    const int un = cq + u * NCQ;
+    if (un >= 16) break;
+    const int col = un * 16;
+    const bool more = un + NCQ < 16;
+    if (more) tmem_ld16(t_acc + col + NCQ * 16, v);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) y[i] = mufu_sin(x[i]);            // issue the unit's sines ...
-    if (u < 3) {
+    for (int i = 0; i < 16; ++i) y[i] = mufu_sin(x[i]);                // issue the unit's sines ...
+    if (more) {
       tmem_ld_wait(); reg_fence16(v);                                      // ... and prepare the next unit while they execute
-      const float4* b4 = reinterpret_cast<const float4*>(bias_s + col + 16);
+      const float4* b4 = reinterpret_cast<const float4*>(bias_s + col + NCQ * 16);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float4 b = b4[i];
@@ -192,9 +200,9 @@ __device__ __forceinline__ void epi_hidden3_sin_pipelined(uint8_t* __restrict__ 
 }
 
 // x0 raw -> act(x0), in place (the `init` Linear consumed the raw form; the skip Linear wants the activated one)
-__device__ __forceinline__ void x0_activate3(uint8_t* X0, int k0_pad, int act, int g_tid) {
+__device__ __forceinline__ void x0_activate3(uint8_t* X0, int k0_pad, int act, int g_tid, int n_threads) {
   const int n16 = (k0_pad >> 3) * ROWS;             // 16-byte groups
-  for (int i = g_tid; i < n16; i += EPI_THREADS) {
+  for (int i = g_tid; i < n16; i += n_threads) {
     uint4 q = *reinterpret_cast<uint4*>(X0 + i * 16);
     uint32_t* w = reinterpret_cast<uint32_t*>(&q);
 #pragma unroll
@@ -308,13 +316,15 @@ __device__ __forceinline__ void composite_tile3(Tc3Smem& s, int slot, const NfPl
 }
 
 // =====================================================================================================
-// NST ring stages of SPCT K-steps each (NST * SPCT * 4 KB = 48 KB).  Warps 0-15 encode/epilogue, 16..16+NST-1 weight
-// producers (one stage each; warp 16 also owns the TMEM allocation), warp 16+NST the MMA issuer (highest warp id).
-template <int NST, int SPCT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EPI_THREADS + 32 * (NST + 1), 1)
+// NST ring stages of SPCT K-steps each (NST * SPCT * 4 KB = 48 KB); NCQ epilogue warps per TMEM lane quarter.  Warps
+// 0..4*NCQ-1 encode/epilogue, then NST weight producers (one stage each; the first also owns the TMEM allocation), then the
+// MMA issuer (highest warp id).
+template <int NST, int SPCT, int NCQ>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (4 * NCQ + NST + 1), 1)
 k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Prog prog, const Tc3Args a) {
   static_assert(NST * SPCT * 4096 == RING_BYTES && NST <= MAX_STAGES3, "ring geometry");
   constexpr int STAGE_BYTES = SPCT * 4096;
+  constexpr int EPIW = 4 * NCQ, EPI_THREADS = 32 * EPIW;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Tc3Smem& s = *reinterpret_cast<Tc3Smem*>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -329,10 +339,10 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
   // ---- one-time setup ----
   if (threadIdx.x == 0) {
     for (int i = 0; i < NST; ++i) { mbar_init(smem_u32(&s.w_land[i]), 1); mbar_init(smem_u32(&s.w_empty[i]), 1); mbar_init(smem_u32(&s.w_ready[i]), 2); }
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s.acc_full[i]), 1); mbar_init(smem_u32(&s.a_ready[i]), 32); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s.acc_full[i]), 1); mbar_init(smem_u32(&s.a_ready[i]), 2 * EPIW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 16) {
+  if (warp == EPIW) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
@@ -352,11 +362,11 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
   tc_fence_after();
   if (s.tmem_base != 0) __trap();
 
-  if (warp >= 16 && warp < 16 + NST) {
+  if (warp >= EPIW && warp < EPIW + NST) {
     // ================= weight producers (both CTAs): one ring stage each =================
     // The ring carries, step by step, slot 0's Linear then slot 1's (half a round behind); entry g goes to stage g % NST.
     if (elect_one()) {
-      const int p = warp - 16;
+      const int p = warp - EPIW;
       const uint32_t ready_leader = leader_addr(smem_u32(&s.w_ready[p]));
       const uint32_t bar_empty = smem_u32(&s.w_empty[p]), bar_land = smem_u32(&s.w_land[p]), dst = smem_u32(s.W + p * STAGE_BYTES);
       int rs = 0, li0 = 0, li1 = 0; uint32_t use = 0;
@@ -391,7 +401,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
       }
       ST_FLUSH(8, blockIdx.x == 0 && p == 0);
     }
-  } else if (warp == 16 + NST) {
+  } else if (warp == EPIW + NST) {
     // ================= MMA issuer (leader CTA only): one thread, tight nested loops =================
     // The probe of the NEXT ring stage is issued before the current chunk's MMAs, so its ~150-cycle latency is hidden.
     if (crank == 0 && elect_one()) {
@@ -475,7 +485,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
         const uint32_t t_acc = t_lane + (uint32_t)slot * 256u;
         const uint32_t a_ready_leader = leader_addr(smem_u32(&s.a_ready[slot]));
         const bool has_next = kl < nsteps;              // Linear j of this slot runs after this phase
-        const int comp_cq = 2 * slot, tail_cq = 2 * slot + 1;
+        const int comp_cq = (NCQ / 2) * slot, tail_cq = comp_cq + 1;
         // bias of Linear j (consumed by this slot's NEXT phase): in flight across the acc_full wait
         float bnext = 0.f; bool bload = false;
         if (has_next) {
@@ -532,7 +542,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
             const bool hashed = dyn ? plan.deform_enc == NF_ENC_HASH : plan.enc == NF_ENC_HASH;
             if (hashed)
               hash_x0(X0, reinterpret_cast<const float4*>(a.packed + (dyn ? plan.hash2_off : plan.hash_off)), plan, px, py, pz, row,
-                      comp ? (cq == comp_cq ? -1 : ((cq - comp_cq - 1) & 3)) : cq, comp ? 3 : 4);
+                      comp ? (cq == comp_cq ? -1 : ((cq - comp_cq - 1 + NCQ) % NCQ)) : cq, comp ? NCQ - 1 : NCQ);
             if (cq == tail_cq) {
               if (hashed) hash_x0_tail(X0, plan, plan.mlp[first_m].k0_pad, px, py, pz, row);
               else {
@@ -564,11 +574,11 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
           const int act = Lc.z;
           const bool is_out = (Lc.w & 1) != 0;
           if (!is_out) {
-            if (Lc.w & 2) x0_activate3(X0, s.lin[j - 1][1].x, act, e_tid);       // init consumed raw x0; the skip Linear wants act(x0)
-            if (act == NF_ACT_SIN) { if (a.debug & 2048) epi_hidden3<NF_ACT_SIN>(H, t_acc, bias, cq, row); else epi_hidden3_sin_pipelined(H, t_acc, bias, cq, row); }
-            else if (act == NF_ACT_LEAKY) epi_hidden3<NF_ACT_LEAKY>(H, t_acc, bias, cq, row);
-            else if (act == NF_ACT_RELU) epi_hidden3<NF_ACT_RELU>(H, t_acc, bias, cq, row);
-            else epi_hidden3<NF_ACT_NONE>(H, t_acc, bias, cq, row);
+            if (Lc.w & 2) x0_activate3(X0, s.lin[j - 1][1].x, act, e_tid, EPI_THREADS);       // init consumed raw x0; the skip Linear wants act(x0)
+            if (act == NF_ACT_SIN) { if (a.debug & 2048) epi_hidden3<NF_ACT_SIN, NCQ>(H, t_acc, bias, cq, row); else epi_hidden3_sin_pipelined<NCQ>(H, t_acc, bias, cq, row); }
+            else if (act == NF_ACT_LEAKY) epi_hidden3<NF_ACT_LEAKY, NCQ>(H, t_acc, bias, cq, row);
+            else if (act == NF_ACT_RELU) epi_hidden3<NF_ACT_RELU, NCQ>(H, t_acc, bias, cq, row);
+            else epi_hidden3<NF_ACT_NONE, NCQ>(H, t_acc, bias, cq, row);
           } else if (((Lc.w >> 2) & 3) == 2) {
             // deformation MLP out (reference nerf.py:1261-1278): every thread deforms its row's sample, then takes its share of
             // the density MLP's hash levels at the DEFORMED position (the canonical NeRF sees pts + rigid_dp, nerf.py:1303)
@@ -604,12 +614,12 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
               }
             }
             if (cq == tail_cq) { s.P[slot][0][row] = px; s.P[slot][1][row] = py; s.P[slot][2][row] = pz; }
-            hash_x0(X0, reinterpret_cast<const float4*>(a.packed + plan.hash_off), plan, px, py, pz, row, cq, 4);
+            hash_x0(X0, reinterpret_cast<const float4*>(a.packed + plan.hash_off), plan, px, py, pz, row, cq, NCQ);
             if (cq == tail_cq) hash_x0_tail(X0, plan, plan.mlp[0].k0_pad, px, py, pz, row);
           } else {
             // density MLP out (tensor order [inter(I), sigma]) -> raw x0 of the View head + raw density
             const int iu = plan.intermediate >> 4;
-            for (int un0 = cq; un0 < iu + 4; un0 += 4) {
+            for (int un0 = cq; un0 < iu + NCQ; un0 += NCQ) {
               // units 0..iu-1 (intermediate columns) are dealt round-robin; the last unit (sigma + View x0 tail) goes to tail_cq
               int un = un0;
               if (un0 >= iu) { if (cq != tail_cq) break; un = iu; }
@@ -654,7 +664,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
       }
     }
     ST_FLUSH(16, blockIdx.x == 0 && warp == 0 && lane == 0);
-    ST_FLUSH(24, blockIdx.x == 0 && warp == 15 && lane == 0);
+    ST_FLUSH(24, blockIdx.x == 0 && warp == EPIW - 1 && lane == 0);
     ST_FLUSH(32, blockIdx.x == 1 && warp == 0 && lane == 0);
   }
   // ---- teardown ----
@@ -664,7 +674,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
-  if (warp == 16) {
+  if (warp == EPIW) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(0), "r"(512) : "memory");
   }
@@ -725,11 +735,15 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
   if (plan.kind == NF_KIND_DYN && !ray_time) return cudaErrorInvalidValue;
   if (const char* dbg = getenv("NF_TC_DEBUG")) a.debug = atoi(dbg);
   // NF_TC_RING selects the weight-ring geometry (same 48 KB): "3" = 3 stages x 16 KB (default; measured faster: the single
-  // issuing thread pays one probe + one commit per stage), "6" = 6 stages x 8 KB
-  int ring = 3;
+  // issuing thread pays one probe + one commit per stage), "6" = 6 stages x 8 KB.  NF_TC_EPIW selects the number of epilogue
+  // warps: 16 (default) or 24 (6 per TMEM lane quarter; 72 registers per thread).
+  int ring = 3, epiw = 16;
   if (const char* r = getenv("NF_TC_RING")) ring = atoi(r);
-  const void* fn = ring == 3 ? (const void*)k_render_tc3<3, 4> : (const void*)k_render_tc3<6, 2>;
-  const int threads = EPI_THREADS + 32 * ((ring == 3 ? 3 : 6) + 1);
+  if (const char* r = getenv("NF_TC_EPIW")) epiw = atoi(r);
+  if (ring != 6) ring = 3;
+  if (epiw != 24 || ring != 3) epiw = 16;
+  const void* fn = epiw == 24 ? (const void*)k_render_tc3<3, 4, 6> : ring == 3 ? (const void*)k_render_tc3<3, 4, 4> : (const void*)k_render_tc3<6, 2, 4>;
+  const int threads = 32 * (epiw + ring + 1);
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tc3Smem));
   if (e != cudaSuccess) return e;
   const NfTileMap map(T, ROWS);
@@ -749,8 +763,9 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
   cudaMemsetAsync(d_stats, 0, 64 * sizeof(long long), st);
   a.stats = d_stats;
 #endif
-  if (ring == 3) k_render_tc3<3, 4><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a);
-  else k_render_tc3<6, 2><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a);
+  if (epiw == 24) k_render_tc3<3, 4, 6><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a);
+  else if (ring == 3) k_render_tc3<3, 4, 4><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a);
+  else k_render_tc3<6, 2, 4><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a);
 #ifdef NF_TC_STATS
   if (getenv("NF_TC_STATS_PRINT")) {
     cudaStreamSynchronize(st);

@@ -14,6 +14,8 @@ from oracle import nerf_oracle as O   # synthetic inputs only
 VARIANTS = [
   ("pipe2_lockstep", {"NF_TC_PIPE": "2"}),
   ("pipe3_ring3x16", {"NF_TC_PIPE": "3", "NF_TC_RING": "3"}),
+  ("pipe3_ring3x16_24_epilogue_warps", {"NF_TC_PIPE": "3", "NF_TC_RING": "3", "NF_TC_EPIW": "24"}),
+  ("pipe3_ring3x16_24_epilogue_warps_plain_sin", {"NF_TC_PIPE": "3", "NF_TC_RING": "3", "NF_TC_EPIW": "24", "NF_TC_DEBUG": "2048"}),
   ("pipe3_ring3x16_plain_sin_epilogue", {"NF_TC_PIPE": "3", "NF_TC_RING": "3", "NF_TC_DEBUG": "2048"}),
   ("pipe3_ring6x8", {"NF_TC_PIPE": "3", "NF_TC_RING": "6"}),
   ("pipe1_single_cta", {"NF_TC_PIPE": "1"}),
@@ -30,7 +32,7 @@ def main():
   ts = torch.linspace(2, 6, 128, device=dev)
   base = None; rows = []
   for name, env in VARIANTS:
-    for k in ("NF_TC_PIPE", "NF_TC_RING", "NF_TC_DEBUG"): os.environ.pop(k, None)
+    for k in ("NF_TC_PIPE", "NF_TC_RING", "NF_TC_DEBUG", "NF_TC_EPIW"): os.environ.pop(k, None)
     os.environ.update(env)
     try:
       for i in range(2): eng.render(views[i % len(views)], ts, None, want_weights=False)

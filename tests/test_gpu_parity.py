@@ -157,8 +157,8 @@ def test_tiny_nerf_vs_oracle():
 
 # ---------------------------------------------------------------- every tensor pipeline / ring geometry
 @pytest.mark.parametrize("env", [{"NF_TC_PIPE": "3", "NF_TC_RING": "6"}, {"NF_TC_PIPE": "3", "NF_TC_RING": "3"},
-                                 {"NF_TC_PIPE": "2"}, {"NF_TC_PIPE": "1"}],
-                         ids=["pipe3_ring6", "pipe3_ring3", "pipe2", "pipe1"])
+                                 {"NF_TC_PIPE": "3", "NF_TC_EPIW": "24"}, {"NF_TC_PIPE": "2"}, {"NF_TC_PIPE": "1"}],
+                         ids=["pipe3_ring6", "pipe3_ring3", "pipe3_epiw24", "pipe2", "pipe1"])
 def test_tensor_pipeline_variants_vs_oracle(P, env, monkeypatch):
   """The C ABI reads NF_TC_PIPE / NF_TC_RING at every call: 3 = staggered paired pipeline (default; ring 6x8 KB or
   3x16 KB), 2 = lockstep paired pipeline, 1 = single-CTA pipeline.  All must meet the same bars, incl. rays spanning two
