@@ -69,6 +69,13 @@ enum nf_mip {
                               index of the [xyz, ray, k, t] covariance array (utils.py:73 moves the wrong axis, 42-44
                               reinterpret) -- needs every ray of the crop: nf_mip_args.rays_all / radius_all */
 };
+/* RGB head */
+enum nf_refl {
+  NF_REFL_VIEW = 0,        /* refl.View (reference src/refl.py:190-207): x0 = [p, elaz(view), latent] */
+  NF_REFL_POSITIONAL = 1   /* refl.Positional (reference src/refl.py:230-245; makefile:12 `--refl-kind pos`): view independent,
+                              x0 = [p, p, hash'(p), latent] with the head's OWN HashEncoder, 5 layers, LeakyReLU.  fp32 pipeline only
+                              (x0 is 102 wide) */
+};
 /* arithmetic of the MLP contractions */
 enum nf_precision {
   NF_PREC_FP32 = 0, /* CUDA-core fp32 FMA; the exact mode (matches the reference's SGEMM to ~1e-6) */
@@ -104,6 +111,7 @@ typedef struct nf_model_desc {
   nf_mlp_desc deform;        /* NF_KIND_DYN: DynamicNeRF.delta_estim (direct: in 4 = xyz,t, out 4; spline: in 38, out 1+3n) */
   int32_t mip;               /* enum nf_mip (NF_PREC_FP32 only: x0 is 134 / 165 wide) */
   int32_t deform_enc;        /* NF_KIND_DYN: encoder of `deform`: NF_ENC_NONE (direct) or NF_ENC_HASH (spline; its own tables) */
+  int32_t refl_kind;         /* enum nf_refl */
   int32_t spline_points;     /* NF_KIND_DYN: 0 = direct_predict (nerf.py:1261-1266); n in 2..8 = spline_interpolate with n
                                 Bezier control points (nerf.py:1267-1278; de_casteljau 1173-1178, cubic_bezier 1201-1206) */
 } nf_model_desc;
@@ -128,6 +136,7 @@ const char* nf_last_error(void);
  *   deform MLP : same order                                   (NF_KIND_DYN only)
  *   hash tables: embs[0].weight ... embs[levels-1].weight      (NF_ENC_HASH only)
  *   deform hash: delta_estim.enc.embs[0..levels-1].weight      (NF_KIND_DYN with deform_enc == NF_ENC_HASH only)
+ *   refl hash  : refl.mlp.enc.embs[0..levels-1].weight         (NF_REFL_POSITIONAL only)
  *   fourier    : enc.basis [3, freqs]                          (NF_ENC_FOURIER only)
  *   beta       : VolSDF.scale (scalar)                         (NF_DENS_LAPLACE only)
  * Each is the live fp32 nn.Parameter storage ([out,in] row-major for weights). */

@@ -37,6 +37,7 @@ int nf_param_count(const nf_model_desc* desc) {
   for (int m = 0; m < p.n_mlps; ++m) n += 2 * p.mlp[m].n_lin;
   if (p.enc == NF_ENC_HASH) n += p.hash_levels;
   if (p.kind == NF_KIND_DYN && p.deform_enc == NF_ENC_HASH) n += p.hash_levels;
+  if (p.refl_kind == NF_REFL_POSITIONAL) n += p.hash_levels;
   if (p.enc == NF_ENC_FOURIER) n += 1;
   if (p.density_act == NF_DENS_LAPLACE) n += 1;
   return n;
@@ -86,6 +87,15 @@ int nf_pack_weights(const nf_model_desc* desc, const float* const* params, int32
       if (e != cudaSuccess) return cuda_fail(e, "pack deformation hash tables");
     }
   }
+  if (p.refl_kind == NF_REFL_POSITIONAL) {
+    const size_t per = (size_t)(p.hash_mask + 1) * 4 * sizeof(float);
+    for (int l = 0; l < p.hash_levels; ++l) {
+      const float* t = params[pi++];
+      if (!t) return fail(NF_E_BADARG, "nf_pack_weights: null refl hash table");
+      cudaError_t e = cudaMemcpyAsync(base + p.hash3_off + l * per, t, per, cudaMemcpyDeviceToDevice, st);
+      if (e != cudaSuccess) return cuda_fail(e, "pack refl hash tables");
+    }
+  }
   if (p.enc == NF_ENC_FOURIER) {
     const float* b = params[pi++];
     if (!b) return fail(NF_E_BADARG, "nf_pack_weights: null fourier basis");
@@ -117,6 +127,8 @@ int nf_render_forward(const nf_model_desc* desc, const void* packed, const float
       return fail(NF_E_BADARG, "nf_render_forward: NF_MIP_CYLINDER_REF needs the whole crop (rays_all, radius_all, n_rays_all, ray_base)");
     if (precision != NF_PREC_FP32) return fail(NF_E_UNSUPPORTED, "the Mip encoder (x0 134/165 wide) runs on the fp32 pipeline only in this build");
   }
+  if (p.refl_kind != NF_REFL_VIEW && precision != NF_PREC_FP32)
+    return fail(NF_E_UNSUPPORTED, "the Positional head (x0 102 wide) runs on the fp32 pipeline only in this build");
   cudaError_t e;
   if (precision == NF_PREC_FP32)
     e = nf_launch_render_fp32(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, ray_time, mip, rgb_out, alpha_out, weights_out, (cudaStream_t)stream);

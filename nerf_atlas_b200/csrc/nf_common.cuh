@@ -43,6 +43,8 @@ struct NfPlan {
   int64_t scale_off;    // byte offset: fp32 beta (VolSDF.scale)
   int32_t fourier_freqs, mip;
   int32_t deform_enc, spline_points;
+  int32_t refl_kind, pad4_;
+  int64_t hash3_off;    // byte offset: fp32 [levels][table][4], tables of the Positional head's own HashEncoder
   int64_t hash2_off;    // byte offset: fp32 [levels][table][4], tables of the spline deformation MLP's own HashEncoder
   int64_t total_bytes;
   NfMlpPlan mlp[3];     // [0] density, [1] refl, [2] deformation (NF_KIND_DYN; executed first)
@@ -62,6 +64,10 @@ static inline int nf_build_plan(const nf_model_desc* d, NfPlan* p, const char** 
   if (d->mip < NF_MIP_NONE || d->mip > NF_MIP_CYLINDER_REF) { *why = "unknown mip kind"; return NF_E_BADARG; }
   if (d->mip != NF_MIP_NONE && d->kind == NF_KIND_TINY) { *why = "mip: not for NF_KIND_TINY"; return NF_E_UNSUPPORTED; }
   p->mip = d->mip;
+  if (d->refl_kind != NF_REFL_VIEW && d->refl_kind != NF_REFL_POSITIONAL) { *why = "unknown refl kind"; return NF_E_BADARG; }
+  if (d->refl_kind == NF_REFL_POSITIONAL && (d->kind == NF_KIND_TINY || d->enc != NF_ENC_HASH)) {
+    *why = "the Positional head needs a hash-encoded PlainNeRF / DynamicNeRF"; return NF_E_UNSUPPORTED; }
+  p->refl_kind = d->refl_kind;
   if (d->kind == NF_KIND_DYN) {
     p->deform_enc = d->deform_enc; p->spline_points = d->spline_points;
     if (d->spline_points == 0 ? d->deform_enc != NF_ENC_NONE : (d->deform_enc != NF_ENC_HASH || d->enc != NF_ENC_HASH)) {
@@ -85,6 +91,7 @@ static inline int nf_build_plan(const nf_model_desc* d, NfPlan* p, const char** 
   if (d->enc == NF_ENC_HASH) p->hash_off = take((int64_t)d->hash_levels * d->hash_table_size * 4 * sizeof(float));
   if (d->enc == NF_ENC_FOURIER) p->fourier_off = take((int64_t)3 * d->fourier_freqs * sizeof(float));
   if (d->kind == NF_KIND_DYN && d->deform_enc == NF_ENC_HASH) p->hash2_off = take((int64_t)d->hash_levels * d->hash_table_size * 4 * sizeof(float));
+  if (d->refl_kind == NF_REFL_POSITIONAL) p->hash3_off = take((int64_t)d->hash_levels * d->hash_table_size * 4 * sizeof(float));
   p->scale_off = take(sizeof(float));
   for (int m = 0; m < p->n_mlps; ++m) {
     const nf_mlp_desc& md = m == 0 ? d->density : m == 1 ? d->refl : d->deform;
@@ -121,7 +128,8 @@ static inline int nf_build_plan(const nf_model_desc* d, NfPlan* p, const char** 
   if (d->kind == NF_KIND_PLAIN || d->kind == NF_KIND_DYN) {
     const int ml = d->mip != NF_MIP_NONE ? NF_MIP_FEATS : 0;
     if (d->density.out_dims != 1 + d->intermediate) { *why = "density MLP out must be 1+intermediate"; return NF_E_BADARG; }
-    if (d->refl.in_dims != 5 + ml + d->intermediate || d->refl.out_dims != 3) { *why = "refl MLP must map 5(+96 mip)+intermediate -> 3"; return NF_E_BADARG; }
+    const int rin = (d->refl_kind == NF_REFL_POSITIONAL ? 6 + d->hash_levels * 4 : 5) + ml + d->intermediate;
+    if (d->refl.in_dims != rin || d->refl.out_dims != 3) { *why = "refl MLP must map [p, elaz | p, hash(p)] (+96 mip) + intermediate -> 3"; return NF_E_BADARG; }
     const int want = (d->enc == NF_ENC_HASH ? 6 + d->hash_levels * 4 : d->enc == NF_ENC_FOURIER ? 3 + 2 * d->fourier_freqs : 3) + ml;
     if (d->density.in_dims != want) { *why = "density MLP in_dims does not match the encoder"; return NF_E_BADARG; }
   } else {
@@ -138,7 +146,7 @@ static inline int nf_build_plan(const nf_model_desc* d, NfPlan* p, const char** 
 //   refl x0          : reference [p(3), elaz(2), inter(I)]    -> [inter(I), p, elaz]
 //   density out      : reference [sigma, inter(I)]            -> [inter(I), sigma]
 __host__ __device__ inline int nf_x0_perm(const NfPlan& p, int m, int k_ref) {
-  if (p.mip != NF_MIP_NONE) return k_ref;                  // (fp32 pipeline only; the image is packed but never used)
+  if (p.mip != NF_MIP_NONE || (m == 1 && p.refl_kind != NF_REFL_VIEW)) return k_ref;   // (fp32 pipeline only; the image is packed but never used)
   if (m == 2 && p.deform_enc == NF_ENC_HASH) { const int nfe = p.hash_levels * 4; return k_ref < 6 ? nfe + k_ref : k_ref - 6; }
   if (p.kind == NF_KIND_PLAIN || p.kind == NF_KIND_DYN) {
     if (m == 0 && p.enc == NF_ENC_HASH) { const int nfe = p.hash_levels * 4; return k_ref < 6 ? nfe + k_ref : k_ref - 6; }

@@ -207,19 +207,36 @@ k_render_fp32(const __grid_constant__ NfPlan plan, const RenderArgs a) {
       int ob = mlp_fp32(plan.mlp[0], a.packed, s);
       const float* rgb_raw;
       if (plan.kind == NF_KIND_PLAIN || plan.kind == NF_KIND_DYN) {
-        // ---- glue: sigma_raw, x0 of the View head = [pts, elaz(view), intermediate] (nerf.py:344-358, refl.py:205-207)
+        // ---- glue: sigma_raw, x0 of the RGB head (nerf.py:344-358): View = [pts, elaz(view), (mip), intermediate] (refl.py:205-207),
+        //      Positional = [pts, pts, hash'(pts), (mip), intermediate] with the head's own tables (refl.py:230-245)
         const float* O = s.H[ob];
+        const int ml = plan.mip != NF_MIP_NONE ? NF_MIP_FEATS : 0;
+        const bool pos_head = plan.refl_kind == NF_REFL_POSITIONAL;
+        const int base = pos_head ? 6 + plan.hash_levels * 4 : 5;
         if (tid < ROWS) {
           const int row = tid;
           s.sig[row] = O[row];
-          float el = 0.f, az = 0.f;
-          if (s.valid[row]) { const float* r = a.rays + s.ray[row] * 6; nf_elaz(__ldg(r + 3), __ldg(r + 4), __ldg(r + 5), el, az); }
           s.X0[0 * ROWS + row] = s.P[row]; s.X0[1 * ROWS + row] = s.P[ROWS + row]; s.X0[2 * ROWS + row] = s.P[2 * ROWS + row];
-          s.X0[3 * ROWS + row] = el; s.X0[4 * ROWS + row] = az;
+          if (pos_head) {
+            s.X0[3 * ROWS + row] = s.P[row]; s.X0[4 * ROWS + row] = s.P[ROWS + row]; s.X0[5 * ROWS + row] = s.P[2 * ROWS + row];
+          } else {
+            float el = 0.f, az = 0.f;
+            if (s.valid[row]) { const float* r = a.rays + s.ray[row] * 6; nf_elaz(__ldg(r + 3), __ldg(r + 4), __ldg(r + 5), el, az); }
+            s.X0[3 * ROWS + row] = el; s.X0[4 * ROWS + row] = az;
+          }
         }
-        const int ml = plan.mip != NF_MIP_NONE ? NF_MIP_FEATS : 0;
-        for (int i = tid; i < ml * ROWS; i += THREADS) s.X0[5 * ROWS + i] = s.M[i];
-        for (int i = tid; i < plan.intermediate * ROWS; i += THREADS) s.X0[(5 + ml) * ROWS + i] = O[ROWS + i];
+        if (pos_head) {
+          const int row = tid % ROWS, part = tid / ROWS;
+          const float4* tables = reinterpret_cast<const float4*>(a.packed + plan.hash3_off);
+          for (int lvl = part; lvl < plan.hash_levels; lvl += THREADS / ROWS) {
+            const float4 f = nf_hash_level(tables + (size_t)lvl * (plan.hash_mask + 1), s.P[row], s.P[ROWS + row], s.P[2 * ROWS + row], plan.hash_res[lvl],
+                                           plan.hash_primes[0], plan.hash_primes[1], plan.hash_primes[2], plan.hash_mask, nullptr);
+            float* x = s.X0 + (6 + lvl * 4) * ROWS + row;
+            x[0] = f.x; x[ROWS] = f.y; x[2 * ROWS] = f.z; x[3 * ROWS] = f.w;
+          }
+        }
+        for (int i = tid; i < ml * ROWS; i += THREADS) s.X0[base * ROWS + i] = s.M[i];
+        for (int i = tid; i < plan.intermediate * ROWS; i += THREADS) s.X0[(base + ml) * ROWS + i] = O[ROWS + i];
         __syncthreads();
         // ---- stage 2: View MLP
         ob = mlp_fp32(plan.mlp[1], a.packed, s);

@@ -45,7 +45,7 @@ MIP_FEATS = 96   # 2 x 16 degrees x 3 axes (reference src/utils.py:104-111, src/
 
 
 def describe_plain(intermediate: int = 64, sigmoid: str = "upshifted", bg: str = "black",
-                   hash_levels: int = 8, hash_table: int = 1 << 16, mip: Optional[str] = None) -> ModelDesc:
+                   hash_levels: int = 8, hash_table: int = 1 << 16, mip: Optional[str] = None, refl_kind: str = "view") -> ModelDesc:
   """PlainNeRF + View head as built by runner.load_model (reference src/nerf.py:310-324,
   src/refl.py:190-204, runner.py:1182-1183).  ``mip`` in (None, "cylinder", "cone", "cylinder_ref"): the IPE latent
   widens both MLP inputs by 96 (nerf.py:255,311-324)."""
@@ -55,7 +55,9 @@ def describe_plain(intermediate: int = 64, sigmoid: str = "upshifted", bg: str =
   d.mip = _lib.MIP[mip]
   ml = MIP_FEATS if d.mip else 0
   d.density = _mlp(6 + 4 * hash_levels + ml, 4, 1 + intermediate, "leaky_relu")
-  d.refl = _mlp(5 + ml + intermediate, 4, 3, "sin")
+  d.refl_kind = _lib.REFL[refl_kind]
+  if refl_kind == "pos": d.refl = _mlp(6 + 4 * hash_levels + ml + intermediate, 5, 3, "leaky_relu")   # refl.Positional (refl.py:230-245)
+  else: d.refl = _mlp(5 + ml + intermediate, 4, 3, "sin")                                             # refl.View (refl.py:190-207)
   d.intermediate = intermediate
   d.enc = _lib.ENC["hash"]
   d.hash_levels, d.hash_table_size, d.hash_feat = hash_levels, hash_table, 4
@@ -355,6 +357,15 @@ class ViewHead(nn.Module):
     self.mlp = SkipConnParams(5 + latent_size, out_features, 4, init="siren")
 
 
+class PositionalHead(nn.Module):
+  """Parameters of refl.Positional (reference src/refl.py:230-245): view-independent colour from [p, hash'(p), latent]."""
+  def __init__(self, latent_size: int, out_features: int = 3, act: str = "thin"):
+    super().__init__()
+    self.latent_size, self.out_features = latent_size, out_features
+    self.act = act
+    self.mlp = SkipConnParams(38 + latent_size, out_features, 5, enc=HashParams())
+
+
 _ACT_NAMES = {"sigmoid": "normal", "thin_sigmoid": "thin", "tanh": "tanh", "cyclic_sigmoid": "cyclic",
               "upshifted_sigmoid": "upshifted", "fat_sigmoid": "fat", "leaky_relu": "leaky_relu", "relu": "relu",
               "sin": "sin", "upshifted_softplus": "upshifted_softplus", "upshifted_relu": "upshifted_relu"}
@@ -427,7 +438,7 @@ class FusedNeRF(nn.Module):
 
   def engine(self) -> RenderEngine:
     key = (self.kind, self.sigmoid_kind if not hasattr(self, "refl") else _sigmoid_name(self.refl.act), self.bg, self.precision,
-           getattr(self, "mip", None))
+           getattr(self, "mip", None), getattr(self, "refl_kind", "view"))
     if self._engine is None or self._engine_key != key:
       self._engine, self._engine_key = RenderEngine(self._describe(), self.precision), key
     return self._engine
@@ -466,11 +477,13 @@ class FusedPlainNeRF(FusedNeRF):
   """Drop-in for PlainNeRF + View (reference src/nerf.py:310-361)."""
   kind = "plain"
 
-  def __init__(self, out_features: int = 3, **kwargs):
+  def __init__(self, out_features: int = 3, refl_kind: str = "view", **kwargs):
     kwargs.setdefault("sigmoid_kind", "thin")
     super().__init__(**kwargs)
     if out_features != 3: raise NotImplementedError("out_features != 3")
-    self.refl = ViewHead(latent_size=self.mip_size() + self.intermediate_size, out_features=out_features, act=self.sigmoid_kind)
+    if refl_kind not in _lib.REFL: raise NotImplementedError(f"refl kind {refl_kind!r} (view | pos)")
+    head = PositionalHead if refl_kind == "pos" else ViewHead          # runner.load_model: refl.load(args, refl_kind, ...) (runner.py:1182-1183)
+    self.refl = head(latent_size=self.mip_size() + self.intermediate_size, out_features=out_features, act=self.sigmoid_kind)
     self.first = SkipConnParams(38 + self.mip_size(), 1 + self.intermediate_size, 4, enc=HashParams())
 
   @classmethod
@@ -484,7 +497,8 @@ class FusedPlainNeRF(FusedNeRF):
     bg = [k for k, v in {"black": "black", "white": "white"}.items() if getattr(ref.sky_color, "__name__", "") == v]
     if not bg: raise NotImplementedError("background kind of the reference model")
     self.bg = bg[0]
-    if type(ref.refl).__name__ not in ("View", "ViewHead"): raise NotImplementedError(f"refl head {type(ref.refl).__name__}")
+    if type(ref.refl).__name__ not in ("View", "ViewHead", "Positional", "PositionalHead"):
+      raise NotImplementedError(f"refl head {type(ref.refl).__name__}")
     self.refl, self.first = ref.refl, ref.first
     return self
 
@@ -492,13 +506,17 @@ class FusedPlainNeRF(FusedNeRF):
     enc = self.first.enc
     levels = len(enc.embs)
     return describe_plain(self.intermediate_size, _sigmoid_name(self.refl.act), self.bg, levels, enc.embs[0].weight.shape[0],
-                          mip=getattr(self, "mip", None))
+                          mip=getattr(self, "mip", None), refl_kind=self.refl_kind)
+
+  @property
+  def refl_kind(self) -> str: return "pos" if type(self.refl).__name__ in ("Positional", "PositionalHead") else "view"
 
   def _param_list(self) -> List[torch.Tensor]:
     ps: List[torch.Tensor] = []
     for mlp in (self.first, self.refl.mlp):
       for lin in _linears_of(mlp): ps += [lin.weight, lin.bias]
     ps += [e.weight for e in self.first.enc.embs]
+    if self.refl_kind == "pos": ps += [e.weight for e in self.refl.mlp.enc.embs]
     return ps
 
 

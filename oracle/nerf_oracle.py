@@ -381,9 +381,17 @@ def plain_from_pts(params: Params, pts: Tensor, ts: Tensor, r_o: Tensor, r_d: Te
   intermediate = first_out[..., 1:]
   view = r_d.unsqueeze(0).expand_as(pts)
   elaz = dir_to_elev_azim(view)
-  x0r = torch.cat([pts, elaz, intermediate] if mip_latent is None else [pts, elaz, mip_latent, intermediate], dim=-1)
+  lat = [intermediate] if mip_latent is None else [mip_latent, intermediate]
+  if "refl.mlp.enc.embs.0.weight" in params:
+    # refl.Positional (refl.py:230-245): view independent, [p, enc'(p) = [p, feats'], latent], LeakyReLU, its own hash tables
+    enc2 = hash_encode(p, hash_tables(params, "refl.mlp.enc")).reshape(batches + (-1,))
+    x0r = torch.cat([pts, enc2] + lat, dim=-1)
+    head_act = "leaky_relu"
+  else:
+    x0r = torch.cat([pts, elaz] + lat, dim=-1)                # refl.View (refl.py:205-207)
+    head_act = "sin"
   x0r = x0r.reshape(-1, x0r.shape[-1])
-  rgb_raw = skip_mlp(x0r, params, "refl.mlp", "sin", quant=quant).reshape(batches + (-1,))
+  rgb_raw = skip_mlp(x0r, params, "refl.mlp", head_act, quant=quant).reshape(batches + (-1,))
   rgb = SIGMOIDS[sigmoid](rgb_raw)
   if per_ray_ts: alpha, weights = alpha_from_density_per_ray(density, ts, r_d)
   else: alpha, weights = alpha_from_density(density, ts, r_d)
@@ -552,7 +560,8 @@ def plain_coarse_fine(params: Params, rays: Tensor, ts_coarse: Tensor, u: Tensor
 # ----------------------------------------------------------------------------
 # deterministic synthetic inputs (shared by tests, golden generator, bench)
 # ----------------------------------------------------------------------------
-def make_plain_params(seed: int = 1337, intermediate: int = 64, sigma_gain: float = 1.0, mip: bool = False) -> Params:
+def make_plain_params(seed: int = 1337, intermediate: int = 64, sigma_gain: float = 1.0, mip: bool = False,
+                      refl_kind: str = "view") -> Params:
   """Parameters with the reference's init *distributions* (first MLP: torch
   default U(+-1/sqrt(fan_in)), neural_blocks.py:258-259; View MLP: siren
   U(+-sqrt(6/fan_in)) with zero bias, 266-271; hash tables N(0,1),
@@ -579,6 +588,16 @@ def make_plain_params(seed: int = 1337, intermediate: int = 64, sigma_gain: floa
   default_linear("first.out", 1 + I, 256)
   if sigma_gain != 1.0:
     P["first.out.weight"][0] *= sigma_gain; P["first.out.bias"][0] *= sigma_gain
+  if refl_kind == "pos":
+    # refl.Positional (refl.py:230-237): own HashEncoder, 5 layers, torch-default init
+    P["refl.mlp.enc.primes"] = P["first.enc.primes"].clone()
+    for i in range(HASH_LEVELS):
+      P[f"refl.mlp.enc.embs.{i}.weight"] = torch.from_numpy(g.standard_normal((HASH_TABLE, HASH_FEAT)).astype(np.float32))
+    w = 38 + ML + I
+    default_linear("refl.mlp.init", 256, w)
+    for i in range(5): default_linear(f"refl.mlp.layers.{i}", 256, 256 + w if (i % 3 == 0 and i != 4) else 256)
+    default_linear("refl.mlp.out", 3, 256)
+    return P
   siren_linear("refl.mlp.init", 256, 5 + ML + I)
   siren_linear("refl.mlp.layers.0", 256, 256 + 5 + ML + I)
   for i in (1, 2, 3): siren_linear(f"refl.mlp.layers.{i}", 256, 256)

@@ -14,18 +14,18 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "..", ".."))
 from oracle import nerf_oracle as O, ref_shim
 
-def ref_plain(params, steps, train=False):
+def ref_plain(params, steps, train=False, refl_kind="view"):
   runner, nerf, refl, utils, cameras = ref_shim.load()
-  model, args = ref_shim.build_model("plain", steps)
+  model, args = ref_shim.build_model("plain", steps, extra=("--refl-kind", refl_kind))
   sd = {k: v.clone() for k, v in params.items()}
   model.load_state_dict(sd, strict=True)
   model.train(train)
   return model, args
 
-def case_plain(name, seed, B, H, W, T, sigma_gain=1.0, train=False, top=0, left=0, stages=True):
-  params = O.make_plain_params(seed, 64, sigma_gain)
+def case_plain(name, seed, B, H, W, T, sigma_gain=1.0, train=False, top=0, left=0, stages=True, refl_kind="view"):
+  params = O.make_plain_params(seed, 64, sigma_gain, refl_kind=refl_kind)
   rays = O.make_rays(B, H, W, size=800, seed=seed, crop_top=top, crop_left=left)
-  model, args = ref_plain(params, T, train)
+  model, args = ref_plain(params, T, train, refl_kind)
   runner, nerf, refl, utils, cameras = ref_shim.load()
   draws = {}
   if train:
@@ -40,7 +40,7 @@ def case_plain(name, seed, B, H, W, T, sigma_gain=1.0, train=False, top=0, left=
   finally:
     if train: torch.rand_like, torch.randn_like = o_rand, o_randn
   fx = dict(
-    kind="plain", seed=seed, B=B, H=H, W=W, T=T, sigma_gain=sigma_gain, train=int(train), top=top, left=left,
+    kind="plain", refl_kind=refl_kind, seed=seed, B=B, H=H, W=W, T=T, sigma_gain=sigma_gain, train=int(train), top=top, left=left,
     near=float(args.near), far=float(args.far), sigmoid=args.sigmoid_kind, bg=args.bg,
     ts=model.ts.numpy(), out=out.numpy(), alpha=model.alpha.numpy(), weights=model.weights.numpy(),
   )
@@ -175,6 +175,9 @@ def check_rays():
 
 if __name__ == "__main__":
   check_rays()
+  if "--pos" in sys.argv:
+    case_plain("plain_pos_t16", seed=81, B=1, H=4, W=5, T=16, sigma_gain=20.0, top=398, left=397, stages=False, refl_kind="pos")
+    sys.exit(0)
   if "--new" in sys.argv:      # only the cases added after the first goldens were committed
     case_mip("plain_mip_cylinder_t16", seed=61, B=2, H=5, W=4, T=16, top=398, left=397)
     case_dnerf_spline("dnerf_spline5_t32", seed=71, n=5, B=2, H=3, W=4, T=32, top=398, left=397)
@@ -190,3 +193,4 @@ if __name__ == "__main__":
   case_mip("plain_mip_cylinder_t16", seed=61, B=2, H=5, W=4, T=16, top=398, left=397)
   case_dnerf_spline("dnerf_spline5_t32", seed=71, n=5, B=2, H=3, W=4, T=32, top=398, left=397)
   case_dnerf_spline("dnerf_spline4_t32", seed=72, n=4, B=2, H=3, W=3, T=32, top=398, left=397)
+  case_plain("plain_pos_t16", seed=81, B=1, H=4, W=5, T=16, sigma_gain=20.0, top=398, left=397, stages=False, refl_kind="pos")

@@ -47,6 +47,8 @@ def test_descriptor_host_logic():
   assert s5.deform.out_dims == 16 and l.nf_param_count(C.byref(s5)) == 2 * 6 + 2 * 6 + 2 * 7 + 8 + 8
   bad = N.describe_dyn(spline=5); bad.deform.out_dims = 4
   assert l.nf_param_count(C.byref(bad)) == -1 and b"spline" in l.nf_last_error()
+  pos = N.describe_plain(refl_kind="pos")
+  assert pos.refl.in_dims == 38 + 64 and pos.refl.n_layers == 5 and l.nf_param_count(C.byref(pos)) == 2 * 6 + 2 * 7 + 8 + 8
   bad = N.describe_plain(mip="cone"); bad.refl.in_dims = 69
   assert l.nf_param_count(C.byref(bad)) == -1
 

@@ -494,3 +494,29 @@ def test_generate_rays_bit_exact_vs_reference_camera():
     assert got.shape == ref.shape and torch.equal(got.cpu(), ref), (size, B, crop)
   alt = N.RenderEngine.generate_rays(c2w.to(DEV), focal, size, crop, reference_device="cuda")     # torch-CUDA scalar division
   assert float((alt.cpu() - ref).abs().max()) <= 2e-7
+
+
+# ---------------------------------------------------------------- Positional RGB head (SURVEY f-3)
+def test_positional_head_matches_reference_golden():
+  """PlainNeRF + refl.Positional (`--refl-kind pos`, reference makefile:12): fp32 pipeline vs a golden from the reference run;
+  module surface with the reference's state_dict names; the tensor pipeline refuses (x0 is 102 wide) instead of falling back."""
+  import nerf_atlas_b200 as N
+  fx = load_golden("plain_pos_t16")
+  P = O.make_plain_params(int(fx["seed"]), 64, float(fx["sigma_gain"]), refl_kind="pos")
+  rays = O.make_rays(int(fx["B"]), int(fx["H"]), int(fx["W"]), 800, int(fx["seed"]), int(fx["top"]), int(fx["left"])).to(DEV)
+  m = N.FusedPlainNeRF(steps=int(fx["T"]), t_near=float(fx["near"]), t_far=float(fx["far"]), intermediate_size=64,
+                       sigmoid_kind=str(fx["sigmoid"]), bg=str(fx["bg"]), precision="fp32", refl_kind="pos")
+  m.load_state_dict(P, strict=True); m = m.to(DEV).eval()
+  with torch.no_grad(): out = m(rays)
+  assert np.abs(out.cpu().numpy() - fx["out"]).max() <= 3e-5, np.abs(out.cpu().numpy() - fx["out"]).max()
+  assert np.abs(m.weights.cpu().numpy() - fx["weights"]).max() <= 2e-4
+  m.precision = "fp16"
+  with pytest.raises(RuntimeError):
+    with torch.no_grad(): m(rays)
+  # a larger ragged slab vs the oracle, 128 samples per ray
+  big = O.make_rays(1, 9, 11, seed=82, crop_top=300, crop_left=300)
+  ts = torch.linspace(2, 6, 128)
+  with torch.no_grad(): ref = O.plain_forward(P, big, ts)
+  m.precision = "fp32"; m.steps = 128
+  with torch.no_grad(): o2 = m(big.to(DEV))
+  assert np.abs(o2.cpu().numpy() - ref["out"].numpy()).max() <= 3e-5

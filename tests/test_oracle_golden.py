@@ -122,6 +122,16 @@ def test_dnerf_spline_oracle_matches_reference_bit_exact(golden_dir, name):
   for k in ("out", "alpha", "weights", "rigid_dp"):
     assert np.array_equal(res[k].numpy(), fx[k]), f"{name}: {k} differs from the reference run"
 
+def test_positional_head_oracle_matches_reference_bit_exact(golden_dir):
+  """PlainNeRF with `--refl-kind pos` (refl.Positional, the head of the reference's default makefile target)."""
+  fx = load(golden_dir, "plain_pos_t16")
+  params = O.make_plain_params(int(fx["seed"]), 64, float(fx["sigma_gain"]), refl_kind="pos")
+  rays = O.make_rays(int(fx["B"]), int(fx["H"]), int(fx["W"]), 800, int(fx["seed"]), int(fx["top"]), int(fx["left"]))
+  ts = O.compute_ts(float(fx["near"]), float(fx["far"]), int(fx["T"]))
+  with torch.no_grad(): res = O.plain_forward(params, rays, ts, sigmoid=str(fx["sigmoid"]), bg=str(fx["bg"]))
+  for k in ("out", "alpha", "weights"):
+    assert np.array_equal(res[k].numpy(), fx[k]), f"pos head: {k} differs from the reference run"
+
 def test_hash_resolutions_decrease():
   # operator-precedence quirk of neural_blocks.py:126-128: scale < 1, resolutions 16 -> 6.28
   r = O.hash_resolutions()
