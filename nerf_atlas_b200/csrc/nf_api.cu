@@ -125,10 +125,7 @@ int nf_render_forward(const nf_model_desc* desc, const void* packed, const float
     if (ts_ray_stride != 0) return fail(NF_E_UNSUPPORTED, "nf_render_forward: the Mip encoder needs a shared ts[T]");
     if (p.mip == NF_MIP_CYLINDER_REF && (!mip->rays_all || !mip->radius_all || mip->ray_base < 0 || mip->ray_base + n_rays > mip->n_rays_all))
       return fail(NF_E_BADARG, "nf_render_forward: NF_MIP_CYLINDER_REF needs the whole crop (rays_all, radius_all, n_rays_all, ray_base)");
-    if (precision != NF_PREC_FP32) return fail(NF_E_UNSUPPORTED, "the Mip encoder (x0 134/165 wide) runs on the fp32 pipeline only in this build");
   }
-  if (p.refl_kind != NF_REFL_VIEW && precision != NF_PREC_FP32)
-    return fail(NF_E_UNSUPPORTED, "the Positional head (x0 102 wide) runs on the fp32 pipeline only in this build");
   cudaError_t e;
   if (precision == NF_PREC_FP32)
     e = nf_launch_render_fp32(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, ray_time, mip, rgb_out, alpha_out, weights_out, (cudaStream_t)stream);
@@ -138,14 +135,15 @@ int nf_render_forward(const nf_model_desc* desc, const void* packed, const float
     int pipe = 3;
     if (const char* env = getenv("NF_TC_PIPE")) pipe = atoi(env);
     if (const char* env = getenv("NF_TC_PAIRED")) if (env[0] == '0') pipe = 1;
-    if (p.kind == NF_KIND_DYN) {       // only the staggered pipeline runs the three-MLP chain
+    if (p.kind == NF_KIND_DYN || p.mip != NF_MIP_NONE || p.refl_kind != NF_REFL_VIEW) {
+      // only the staggered pipeline runs the three-MLP chain and the wide-x0 (single-tile) mode
       if (const char* why = nf_tc3_unsupported(p)) return fail(NF_E_UNSUPPORTED, why);
       pipe = 3;
     }
     if (pipe == 3 && nf_tc3_unsupported(p)) pipe = 2;
     if (pipe == 2 && nf_tc2_unsupported(p)) pipe = 1;
     cudaStream_t st = (cudaStream_t)stream;
-    e = pipe == 3 ? nf_launch_render_tc3(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, ray_time, rgb_out, alpha_out, weights_out, st)
+    e = pipe == 3 ? nf_launch_render_tc3(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, ray_time, mip, rgb_out, alpha_out, weights_out, st)
       : pipe == 2 ? nf_launch_render_tc2(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, rgb_out, alpha_out, weights_out, st)
                   : nf_launch_render_tc(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, rgb_out, alpha_out, weights_out, st);
   }

@@ -145,12 +145,35 @@ static inline int nf_build_plan(const nf_model_desc* d, NfPlan* p, const char** 
 //   density x0 (hash): reference [p(3), p(3), feats(4L)]      -> [feats(4L), p, p]
 //   refl x0          : reference [p(3), elaz(2), inter(I)]    -> [inter(I), p, elaz]
 //   density out      : reference [sigma, inter(I)]            -> [inter(I), sigma]
+// With a Mip latent (96 columns) and/or the Positional head the wide parts keep 8-column alignment:
+//   density x0 + mip : reference [p, p, feats(4L), mip(96)]            -> [feats(4L), p, p, pad(2), mip(96)]
+//   View x0 + mip    : reference [p, elaz, mip(96), inter(I)]          -> [inter(I), p, elaz, pad(3), mip(96)]
+//   Positional x0    : reference [p, p, feats'(4L), (mip), inter(I)]   -> [inter(I), feats'(4L), p, p, pad(2), (mip)]
+__host__ __device__ inline int nf_mip_col(const NfPlan& p, int m) {       // first tensor-order column of the mip latent in MLP m's x0
+  const int nfe = p.hash_levels * 4;
+  if (m == 0) return nf_round_up(6 + nfe, 8);
+  return p.refl_kind == NF_REFL_POSITIONAL ? p.intermediate + nfe + 8 : p.intermediate + 8;
+}
 __host__ __device__ inline int nf_x0_perm(const NfPlan& p, int m, int k_ref) {
-  if (p.mip != NF_MIP_NONE || (m == 1 && p.refl_kind != NF_REFL_VIEW)) return k_ref;   // (fp32 pipeline only; the image is packed but never used)
-  if (m == 2 && p.deform_enc == NF_ENC_HASH) { const int nfe = p.hash_levels * 4; return k_ref < 6 ? nfe + k_ref : k_ref - 6; }
+  const int ml = p.mip != NF_MIP_NONE ? NF_MIP_FEATS : 0;
+  const int nfe = p.hash_levels * 4;
+  if (m == 2 && p.deform_enc == NF_ENC_HASH) return k_ref < 6 ? nfe + k_ref : k_ref - 6;
   if (p.kind == NF_KIND_PLAIN || p.kind == NF_KIND_DYN) {
-    if (m == 0 && p.enc == NF_ENC_HASH) { const int nfe = p.hash_levels * 4; return k_ref < 6 ? nfe + k_ref : k_ref - 6; }
-    if (m == 1) return k_ref < 5 ? p.intermediate + k_ref : k_ref - 5;
+    if (m == 0 && p.enc == NF_ENC_HASH) {
+      if (k_ref >= 6 + nfe) return nf_mip_col(p, 0) + (k_ref - 6 - nfe);
+      return k_ref < 6 ? nfe + k_ref : k_ref - 6;
+    }
+    if (m == 1 && p.refl_kind == NF_REFL_POSITIONAL) {
+      if (k_ref < 6) return p.intermediate + nfe + k_ref;
+      if (k_ref < 6 + nfe) return p.intermediate + (k_ref - 6);
+      if (k_ref < 6 + nfe + ml) return nf_mip_col(p, 1) + (k_ref - 6 - nfe);
+      return k_ref - (6 + nfe + ml);
+    }
+    if (m == 1) {
+      if (k_ref < 5) return p.intermediate + k_ref;
+      if (k_ref < 5 + ml) return nf_mip_col(p, 1) + (k_ref - 5);
+      return k_ref - 5 - ml;
+    }
   }
   return k_ref;
 }

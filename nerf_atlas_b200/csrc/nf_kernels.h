@@ -28,5 +28,5 @@ cudaError_t nf_launch_render_tc2(const NfPlan& plan, const void* packed, const f
 // staggered paired pipeline (slot 1 half a round behind slot 0, biases in shared memory), nf_tc3.cu
 const char* nf_tc3_unsupported(const NfPlan& plan);
 cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const float* rays, int64_t n_rays, const float* ts,
-                                 int T, int64_t ts_stride, const float* noise, const float* ray_time, float* rgb, float* alpha, float* weights,
-                                 cudaStream_t st);
+                                 int T, int64_t ts_stride, const float* noise, const float* ray_time, const nf_mip_args* mip,
+                                 float* rgb, float* alpha, float* weights, cudaStream_t st);

@@ -17,6 +17,9 @@
 // A slot's life is a cycle of n = n_lin phases; phase j >= 1 = epilogue of Linear j-1, phase 0 = composite of the previous
 // tile (result of Linear n-1) + encode of the next one.  After phase j the issuer runs Linear j for that slot.
 //
+// Wide x0 (the Mip latent: 144 / 176 columns; the Positional head: 112): the two 80-column x0 buffers are too small, so the
+// kernel runs ONE tile in flight per CTA ("single" mode) and keeps x0 in the idle slot's 64 KB activation buffer.
+//
 // Warp roles as in nf_tc2.cu: 0-15 encode/epilogue (TMEM lane quarter q = warp % 4, column quarter cq = warp / 4), 16/18/19
 // weight producers (one ring stage each), 17 the MMA issuer (leader CTA only).
 #include <cstdio>
@@ -57,7 +60,7 @@ struct __align__(16) Tc3Lin {
   uint32_t bhi, mj, w_off, half_bytes;       // mj = m * 16 + j; w_off = byte offset of rank 0's half image, half_bytes = its size
   uint32_t step_bytes, pad0_, pad1_, pad2_;  // bytes of one K-step (16 K-columns) of a half image
 };
-struct __align__(16) Tc3Prog { int32_t n_lin, lag, pad0_, pad1_; Tc3Lin lin[MAX_LIN3]; };
+struct __align__(16) Tc3Prog { int32_t n_lin, lag, single, pad1_; Tc3Lin lin[MAX_LIN3]; };   // single: one tile in flight, x0 (up to 256 wide) lives in slot 1's H buffer
 
 struct Tc3Args {
   const uint8_t* packed;
@@ -66,6 +69,7 @@ struct Tc3Args {
   const float* noise; const float* ray_time;
   float* rgb_out; float* alpha_out; float* weights_out;
   int debug;          // NF_TC_DEBUG (timing experiments): 256 = poll acc_full with backoff, 512 = try_wait with a short suspend hint
+  NfMipIn mip;        // Mip encoder inputs (plan.mip != NF_MIP_NONE)
   long long* stats;   // NF_TC_STATS builds: time-in-state counters of CTA 0 (issuer, producer 0, epilogue warps 0 and 15)
 };
 
@@ -224,18 +228,29 @@ __device__ __forceinline__ void hash_x0(uint8_t* X0, const float4* tables, const
     *reinterpret_cast<uint2*>(X0 + (lvl >> 1) * KG_BYTES + row * 16 + (lvl & 1) * 8) = make_uint2(pack_h2(f.x, f.y), pack_h2(f.z, f.w));
   }
 }
-// the [p, p] tail of a hash-encoded x0 (tensor order [feats, p, p]) and the zero padding up to k0_pad
-__device__ __forceinline__ void hash_x0_tail(uint8_t* X0, const NfPlan& plan, int k0_pad, float px, float py, float pz, int row) {
+// the [p, p] tail of a hash-encoded x0 (tensor order [feats, p, p]) and the zero padding up to k0_pad; the Mip latent's
+// column groups [mip0, mip0 + 12) are written by the Mip writers and skipped here
+__device__ __forceinline__ void hash_x0_tail(uint8_t* X0, const NfPlan& plan, int k0_pad, float px, float py, float pz, int row, int mip_col = -1) {
   const int kg = plan.hash_levels >> 1;
   st_v4(X0 + kg * KG_BYTES + row * 16, pack_h2(px, py), pack_h2(pz, px), pack_h2(py, pz), 0);
-  for (int g = kg + 1; g < (k0_pad >> 3); ++g) st_v4(X0 + g * KG_BYTES + row * 16, 0, 0, 0, 0);
+  const int m0 = mip_col >= 0 ? mip_col >> 3 : 1 << 20;
+  for (int g = kg + 1; g < (k0_pad >> 3); ++g)
+    if (g < m0 || g >= m0 + NF_MIP_FEATS / 8) st_v4(X0 + g * KG_BYTES + row * 16, 0, 0, 0, 0);
+}
+// this thread's share (features first, first + stride, ...) of the Mip latent of one row -> x0 columns [col0, col0 + 96)
+__device__ __forceinline__ void mip_x0(uint8_t* X0, const NfMipIn& mip, int col0, bool ok, long long ray, int t, int row, int first, int stride) {
+  for (int c = first; c < NF_MIP_FEATS; c += stride) {
+    const float f = ok ? nf_mip_feature(mip, ray, t, c) : 0.f;
+    const int col = col0 + c;
+    *reinterpret_cast<__half*>(X0 + (col >> 3) * KG_BYTES + row * 16 + (col & 7) * 2) = __float2half_rn(f);
+  }
 }
 
 // work unit of (pass, slot) for this CTA, and the sub-tile within a ray (T > 128)
-__device__ __forceinline__ void unit_of(int pass, int slot, int tpr, long long& u, int& sub) {
+__device__ __forceinline__ void unit_of(int pass, int slot, int tpr, int nslot, long long& u, int& sub) {
   const int trip = tpr == 1 ? pass : pass / tpr;
   sub = pass - trip * tpr;
-  u = ((long long)trip * gridDim.x + blockIdx.x) * 2 + slot;
+  u = ((long long)trip * gridDim.x + blockIdx.x) * nslot + slot;     // nslot = tiles in flight per CTA (2; 1 in single mode)
 }
 
 // ---- composite of one tile by the 4 cq == 0 warps (thread = row); reference nerf.py:60-80 ----
@@ -331,7 +346,9 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
   const uint32_t crank = cluster_ctarank();
   const NfTileMap map(a.T, ROWS);
   const long long units = map.units(a.n_rays);
-  const int trips = (int)((units + 2LL * gridDim.x - 1) / (2LL * gridDim.x));     // every CTA, every slot: same trip count
+  const bool single = prog.single != 0;            // one tile in flight: slot 1 never runs
+  const int nslot = single ? 1 : 2;
+  const int trips = (int)((units + (long long)nslot * gridDim.x - 1) / ((long long)nslot * gridDim.x));   // every CTA, every slot: same trip count
   const int passes = trips * map.tpr;
   const int n = prog.n_lin, lag = prog.lag;
   const int nsteps = passes * n;                   // MMA steps (Linears) per slot
@@ -375,7 +392,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
 #pragma unroll 1
         for (int slot = 0; slot < 2; ++slot) {
           const int kl = k - (slot ? lag : 0);
-          if (kl < 0 || kl >= nsteps) continue;
+          if (kl < 0 || kl >= nsteps || (slot && single)) continue;
           const int li = slot ? li1 : li0;
           const uint32_t steps = prog.lin[li].k0_steps + prog.lin[li].h_steps, sb = prog.lin[li].step_bytes;
           const uint8_t* src = a.packed + prog.lin[li].w_off + (size_t)crank * prog.lin[li].half_bytes;
@@ -419,7 +436,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
 #pragma unroll 1
         for (uint32_t slot = 0; slot < 2; ++slot) {
           const int kl = k - (slot ? lag : 0);
-          if (kl < 0 || kl >= nsteps) continue;
+          if (kl < 0 || kl >= nsteps || (slot && single)) continue;
           const int li = slot ? li1 : li0;
           const uint4 r0 = *reinterpret_cast<const uint4*>(&prog.lin[li].k0_steps);
           const uint32_t bhi = prog.lin[li].bhi;
@@ -429,7 +446,8 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
           ST_ADD(0);
           tc_fence_after();
           const uint32_t d_tmem = slot * 256u;
-          const uint32_t x4 = (base4 + (uint32_t)(offsetof(Tc3Smem, X0) >> 4) + slot * (uint32_t)(sizeof(s.X0[0]) >> 4)) | a_lbo;
+          const uint32_t x4 = (single ? base4 + (uint32_t)((offsetof(Tc3Smem, H) + sizeof(s.H[0])) >> 4)
+                                      : base4 + (uint32_t)(offsetof(Tc3Smem, X0) >> 4) + slot * (uint32_t)(sizeof(s.X0[0]) >> 4)) | a_lbo;
           const uint32_t h4 = (base4 + (uint32_t)(offsetof(Tc3Smem, H) >> 4) + slot * (uint32_t)(sizeof(s.H[0]) >> 4)) | a_lbo;
 #pragma unroll 1
           for (uint32_t gs0 = 0; gs0 < total; gs0 += SPCT) {
@@ -479,9 +497,9 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
 #pragma unroll 1
       for (int slot = 0; slot < 2; ++slot) {
         const int kl = k - (slot ? lag : 0);
-        if (kl < 0 || kl > nsteps) continue;
+        if (kl < 0 || kl > nsteps || (slot && single)) continue;
         const int j = slot ? j1 : j0, P = slot ? P1 : P0;
-        uint8_t* H = s.H[slot]; uint8_t* X0 = s.X0[slot];
+        uint8_t* H = s.H[slot]; uint8_t* X0 = single ? s.H[1] : s.X0[slot];
         const uint32_t t_acc = t_lane + (uint32_t)slot * 256u;
         const uint32_t a_ready_leader = leader_addr(smem_u32(&s.a_ready[slot]));
         const bool has_next = kl < nsteps;              // Linear j of this slot runs after this phase
@@ -509,7 +527,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
           //   composite: cq == 2 * slot;  x0 tail / View-x0 unit: cq == 2 * slot + 1
           const bool comp = P >= 1;
           if (comp && cq == comp_cq) {
-            long long u; int sub; unit_of(P - 1, slot, map.tpr, u, sub);
+            long long u; int sub; unit_of(P - 1, slot, map.tpr, nslot, u, sub);
             uint32_t v[16];
             tmem_ld16(t_acc, v); tmem_ld_wait(); reg_fence16(v);
             tc_fence_before();
@@ -526,7 +544,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
             ST_ADD(5);
           }
           if (has_next) {
-            long long u; int sub; unit_of(P, slot, map.tpr, u, sub);
+            long long u; int sub; unit_of(P, slot, map.tpr, nslot, u, sub);
             long long ray; int t;
             const bool ok = map.locate(u, sub, row, a.n_rays, ray, t);
             float px = 0.f, py = 0.f, pz = 0.f;
@@ -543,8 +561,10 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
             if (hashed)
               hash_x0(X0, reinterpret_cast<const float4*>(a.packed + (dyn ? plan.hash2_off : plan.hash_off)), plan, px, py, pz, row,
                       comp ? (cq == comp_cq ? -1 : ((cq - comp_cq - 1 + NCQ) % NCQ)) : cq, comp ? NCQ - 1 : NCQ);
+            const int mip0 = (plan.mip != NF_MIP_NONE && !dyn) ? nf_mip_col(plan, 0) : -1;
+            if (mip0 >= 0) mip_x0(X0, a.mip, mip0, ok, ray, t, row, comp ? (cq == comp_cq ? NF_MIP_FEATS : ((cq - comp_cq - 1 + NCQ) % NCQ)) : cq, comp ? NCQ - 1 : NCQ);
             if (cq == tail_cq) {
-              if (hashed) hash_x0_tail(X0, plan, plan.mlp[first_m].k0_pad, px, py, pz, row);
+              if (hashed) hash_x0_tail(X0, plan, plan.mlp[first_m].k0_pad, px, py, pz, row, mip0);
               else {
                 const float tt = (dyn && ok) ? __ldg(a.ray_time + ray) : 0.f;        // direct deformation: x0 = [p, t]
                 st_v4(X0 + row * 16, pack_h2(px, py), pack_h2(pz, tt), 0, 0);
@@ -562,7 +582,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
           // ---------- epilogue of Linear j-1 ----------
           if (j == n - 2 && cq == 1 && P + 1 < passes) {
             // the next tile's rays are a first touch (HBM, ~2 K cycles): pull them into L2 two phases before phase 0 needs them
-            long long u; int sub; unit_of(P + 1, slot, map.tpr, u, sub);
+            long long u; int sub; unit_of(P + 1, slot, map.tpr, nslot, u, sub);
             long long ray; int t;
             if (map.locate(u, sub, row, a.n_rays, ray, t)) {
               asm volatile("prefetch.global.L2 [%0];" ::"l"(a.rays + ray * 6));
@@ -586,7 +606,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
             tmem_ld16(t_acc, v);
             if (Lc.x > 16) tmem_ld16(t_acc + 16, v + 16);
             tmem_ld_wait(); reg_fence16(v); reg_fence16(v + 16);
-            long long u; int sub; unit_of(P, slot, map.tpr, u, sub);
+            long long u; int sub; unit_of(P, slot, map.tpr, nslot, u, sub);
             long long ray; int t;
             float px = 0.f, py = 0.f, pz = 0.f;
             if (map.locate(u, sub, row, a.n_rays, ray, t)) {
@@ -617,8 +637,28 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
             hash_x0(X0, reinterpret_cast<const float4*>(a.packed + plan.hash_off), plan, px, py, pz, row, cq, NCQ);
             if (cq == tail_cq) hash_x0_tail(X0, plan, plan.mlp[0].k0_pad, px, py, pz, row);
           } else {
-            // density MLP out (tensor order [inter(I), sigma]) -> raw x0 of the View head + raw density
+            // density MLP out (tensor order [inter(I), sigma]) -> raw x0 of the RGB head + raw density
             const int iu = plan.intermediate >> 4;
+            const bool pos_head = plan.refl_kind == NF_REFL_POSITIONAL;
+            const int mip1 = plan.mip != NF_MIP_NONE ? nf_mip_col(plan, 1) : -1;
+            if (pos_head || mip1 >= 0) {
+              // wide RGB-head inputs (single mode): every thread takes a share of its row's Positional hash features and Mip latent
+              long long u; int sub; unit_of(P, slot, map.tpr, nslot, u, sub);
+              long long ray; int t;
+              const bool ok = map.locate(u, sub, row, a.n_rays, ray, t);
+              if (pos_head) {
+                float px = 0.f, py = 0.f, pz = 0.f;
+                if (ok) {
+                  const float* rr = a.rays + ray * 6;
+                  const float tt = __ldg(a.ts + ray * a.ts_stride + t);
+                  px = nf_pt(__ldg(rr + 0), tt, __ldg(rr + 3)); py = nf_pt(__ldg(rr + 1), tt, __ldg(rr + 4)); pz = nf_pt(__ldg(rr + 2), tt, __ldg(rr + 5));
+                }
+                uint8_t* Xh = X0 + (plan.intermediate >> 3) * KG_BYTES;                     // columns [I, I + 4L): the head's own hash features
+                hash_x0(Xh, reinterpret_cast<const float4*>(a.packed + plan.hash3_off), plan, px, py, pz, row, cq, NCQ);
+                if (cq == tail_cq) hash_x0_tail(Xh, plan, plan.mlp[1].k0_pad - plan.intermediate, px, py, pz, row, mip1 >= 0 ? mip1 - plan.intermediate : -1);
+              }
+              if (mip1 >= 0) mip_x0(X0, a.mip, mip1, ok, ray, t, row, cq, NCQ);
+            }
             for (int un0 = cq; un0 < iu + NCQ; un0 += NCQ) {
               // units 0..iu-1 (intermediate columns) are dealt round-robin; the last unit (sigma + View x0 tail) goes to tail_cq
               int un = un0;
@@ -634,20 +674,25 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
                 st_v4(d0, o[0], o[1], o[2], o[3]); st_v4(d0 + KG_BYTES, o[4], o[5], o[6], o[7]);
               } else {
                 s.sig[slot][row] = __uint_as_float(v[0]) + bias[plan.intermediate];
-                long long u; int sub; unit_of(P, slot, map.tpr, u, sub);
-                long long ray; int t;
-                float px = 0.f, py = 0.f, pz = 0.f, el = 0.f, az = 0.f;
-                if (map.locate(u, sub, row, a.n_rays, ray, t)) {
-                  const float* rr = a.rays + ray * 6;
-                  const float tt = __ldg(a.ts + ray * a.ts_stride + t);
-                  const float dx = __ldg(rr + 3), dy = __ldg(rr + 4), dz = __ldg(rr + 5);
-                  if (plan.kind == NF_KIND_DYN) { px = s.P[slot][0][row]; py = s.P[slot][1][row]; pz = s.P[slot][2][row]; }
-                  else { px = nf_pt(__ldg(rr + 0), tt, dx); py = nf_pt(__ldg(rr + 1), tt, dy); pz = nf_pt(__ldg(rr + 2), tt, dz); }
-                  nf_elaz(dx, dy, dz, el, az);
+                if (!pos_head) {
+                  long long u; int sub; unit_of(P, slot, map.tpr, nslot, u, sub);
+                  long long ray; int t;
+                  float px = 0.f, py = 0.f, pz = 0.f, el = 0.f, az = 0.f;
+                  if (map.locate(u, sub, row, a.n_rays, ray, t)) {
+                    const float* rr = a.rays + ray * 6;
+                    const float tt = __ldg(a.ts + ray * a.ts_stride + t);
+                    const float dx = __ldg(rr + 3), dy = __ldg(rr + 4), dz = __ldg(rr + 5);
+                    if (plan.kind == NF_KIND_DYN) { px = s.P[slot][0][row]; py = s.P[slot][1][row]; pz = s.P[slot][2][row]; }
+                    else { px = nf_pt(__ldg(rr + 0), tt, dx); py = nf_pt(__ldg(rr + 1), tt, dy); pz = nf_pt(__ldg(rr + 2), tt, dz); }
+                    nf_elaz(dx, dy, dz, el, az);
+                  }
+                  uint8_t* d0 = X0 + (iu * 2) * KG_BYTES + row * 16;
+                  st_v4(d0, pack_h2(px, py), pack_h2(pz, el), pack_h2(az, 0.f), 0);
+                  // columns I+8 .. : the Mip latent (written above), then zero padding up to k0_pad
+                  const int m0 = mip1 >= 0 ? mip1 >> 3 : 1 << 20;
+                  for (int g = iu * 2 + 1; g < (plan.mlp[1].k0_pad >> 3); ++g)
+                    if (g < m0 || g >= m0 + NF_MIP_FEATS / 8) st_v4(X0 + g * KG_BYTES + row * 16, 0, 0, 0, 0);
                 }
-                uint8_t* d0 = X0 + (iu * 2) * KG_BYTES + row * 16;
-                st_v4(d0, pack_h2(px, py), pack_h2(pz, el), pack_h2(az, 0.f), 0);
-                st_v4(d0 + KG_BYTES, 0, 0, 0, 0);
               }
             }
           }
@@ -699,6 +744,7 @@ bool build_prog3(const NfPlan& plan, Tc3Prog* P) {
     }
   }
   P->n_lin = nl; P->lag = nl / 2;
+  for (int m = 0; m < plan.n_mlps; ++m) if (plan.mlp[m].k0_pad > X0K) P->single = 1;
   return true;
 }
 
@@ -706,13 +752,16 @@ bool build_prog3(const NfPlan& plan, Tc3Prog* P) {
 
 // nullptr if the staggered paired pipeline can run this model, else the reason.
 const char* nf_tc3_unsupported(const NfPlan& p) {
-  if (p.mip != NF_MIP_NONE) return "the Mip encoder (x0 134/165 wide) runs on the fp32 pipeline only";
+  const bool wide = p.mip != NF_MIP_NONE || p.refl_kind != NF_REFL_VIEW;
+  if (wide && p.kind != NF_KIND_PLAIN) return "Mip / Positional on the tensor pipeline: PlainNeRF only (DynamicNeRF runs them on the fp32 pipeline)";
+  if (wide && p.enc != NF_ENC_HASH) return "Mip / Positional on the tensor pipeline need the hash-encoded density MLP";
   if (p.kind == NF_KIND_DYN && p.enc != NF_ENC_HASH) return "NF_KIND_DYN: the canonical NeRF must be hash-encoded";
   if (p.kind == NF_KIND_DYN && p.mlp[2].lin[p.mlp[2].n_lin - 1].n_pad > 32) return "deformation MLP with more than 32 outputs";
   int nlin = 0;
   for (int m = 0; m < p.n_mlps; ++m) {
     nlin += p.mlp[m].n_lin;
-    if (p.mlp[m].k0_pad > X0K) return "x0 wider than 80 columns";
+    if (p.mlp[m].k0_pad > 256) return "x0 wider than 256 columns";
+    if (p.mlp[m].k0_pad > X0K && !wide) return "x0 wider than 80 columns";       // e.g. the Fourier-encoded SDF MLP (259)
     for (int j = 0; j < p.mlp[m].n_lin; ++j) {
       // only the density MLP of a two-MLP model may end in a non-final `out` Linear
       if (p.mlp[m].lin[j].is_out && p.kind == NF_KIND_TINY && m != 0) return "unsupported MLP chain";
@@ -726,13 +775,17 @@ const char* nf_tc3_unsupported(const NfPlan& p) {
 }
 
 cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const float* rays, int64_t n_rays, const float* ts,
-                                 int T, int64_t ts_stride, const float* noise, const float* ray_time, float* rgb, float* alpha, float* weights,
-                                 cudaStream_t st) {
+                                 int T, int64_t ts_stride, const float* noise, const float* ray_time, const nf_mip_args* mip,
+                                 float* rgb, float* alpha, float* weights, cudaStream_t st) {
   if (nf_tc3_unsupported(plan)) return cudaErrorNotSupported;
   Tc3Args a{};
   a.packed = (const uint8_t*)packed; a.rays = rays; a.n_rays = n_rays; a.ts = ts; a.T = T; a.ts_stride = ts_stride;
   a.noise = noise; a.ray_time = ray_time; a.rgb_out = rgb; a.alpha_out = alpha; a.weights_out = weights;
   if (plan.kind == NF_KIND_DYN && !ray_time) return cudaErrorInvalidValue;
+  if (plan.mip != NF_MIP_NONE) {
+    if (!mip || !mip->radius || ts_stride != 0) return cudaErrorInvalidValue;
+    a.mip = NfMipIn{plan.mip, ts, T, rays, mip->radius, mip->rays_all, mip->radius_all, (long long)mip->n_rays_all, (long long)mip->ray_base};
+  }
   if (const char* dbg = getenv("NF_TC_DEBUG")) a.debug = atoi(dbg);
   // NF_TC_RING selects the weight-ring geometry (same 48 KB): "3" = 3 stages x 16 KB (default; measured faster: the single
   // issuing thread pays one probe + one commit per stage), "6" = 6 stages x 8 KB.  NF_TC_EPIW selects the number of epilogue
@@ -751,11 +804,12 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
   if (units == 0) return cudaSuccess;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  long long want = (units + 3) / 4 * 2;                      // 2 CTAs x 2 slots per cluster
-  const int grid = (int)(want < (sms / 2) * 2 ? want : (sms / 2) * 2);
   Tc3Prog prog;
   if (!build_prog3(plan, &prog)) return cudaErrorNotSupported;
-  const long long trips = (units + 2LL * grid - 1) / (2LL * grid);
+  const long long nslot = prog.single ? 1 : 2;
+  long long want = (units + 2 * nslot - 1) / (2 * nslot) * 2;                      // 2 CTAs x nslot tiles per cluster
+  const int grid = (int)(want < (sms / 2) * 2 ? want : (sms / 2) * 2);
+  const long long trips = (units + nslot * grid - 1) / (nslot * grid);
   if (trips * map.tpr * prog.n_lin + prog.lag >= (1LL << 30)) return cudaErrorNotSupported;   // 32-bit step counters in the kernel
 #ifdef NF_TC_STATS
   static long long* d_stats = nullptr;
