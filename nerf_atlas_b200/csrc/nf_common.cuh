@@ -314,15 +314,15 @@ __device__ __forceinline__ float nf_mip_cov(const float* __restrict__ ray6, int 
   const float od = __fmul_rn(d, d);
   return __fadd_rn(__fmul_rn(t_var, od), __fmul_rn(r_var, __fsub_rn(1.f, __fdiv_rn(od, magn))));
 }
-// feature c (0..95) of sample t of local ray `ray`: [ (k, xyz) sin | (k, xyz) sin(. + pi/2) ]
-__device__ __forceinline__ float nf_mip_feature(const NfMipIn& m, long long ray, int t, int c) {
-  const int cc = c >= 48 ? c - 48 : c, k = cc / 3, x = cc - 3 * k;
+// features cc and cc + 48 (cc in 0..47) of sample t of local ray `ray`: [ (k, xyz) sin | (k, xyz) sin(. + pi/2) ]; they share
+// the mean, the variance and the exponential
+__device__ __forceinline__ void nf_mip_feature_pair(const NfMipIn& m, long long ray, int t, int cc, float& f_sin, float& f_cos) {
+  const int k = cc / 3, x = cc - 3 * k;
   float t0, t1, t_mean, t_var, r_var;
   nf_mip_segment(m, t, t0, t1);
   nf_mip_moments(m.mode, t0, t1, __ldg(m.radius + ray), t_mean, t_var, r_var);
   const float* r6 = m.rays + ray * 6;
-  float y = __fmul_rn(__fadd_rn(__fmul_rn(__ldg(r6 + 3 + x), t_mean), __ldg(r6 + x)), (float)(1 << k));
-  if (c >= 48) y = __fadd_rn(y, 1.5707963267948966f);
+  const float y = __fmul_rn(__fadd_rn(__fmul_rn(__ldg(r6 + 3 + x), t_mean), __ldg(r6 + x)), (float)(1 << k));
   float cov; int kv = k;
   if (m.mode == NF_MIP_CYLINDER_REF) {
     // the reference's layout: same flat index in [xyz, ray, k, t] as (t, ray, c) has in [t, ray, 48]
@@ -337,8 +337,14 @@ __device__ __forceinline__ float nf_mip_feature(const NfMipIn& m, long long ray,
   } else {
     cov = nf_mip_cov(r6, x, t_var, r_var);
   }
-  const float yv = __fmul_rn(cov, (float)(1u << (2 * kv)));
-  return __fmul_rn(expf(__fmul_rn(-0.5f, yv)), sinf(y));
+  const float e = expf(__fmul_rn(-0.5f, __fmul_rn(cov, (float)(1u << (2 * kv)))));
+  f_sin = __fmul_rn(e, sinf(y));
+  f_cos = __fmul_rn(e, sinf(__fadd_rn(y, 1.5707963267948966f)));
+}
+__device__ __forceinline__ float nf_mip_feature(const NfMipIn& m, long long ray, int t, int c) {
+  float a, b;
+  nf_mip_feature_pair(m, ray, t, c >= 48 ? c - 48 : c, a, b);
+  return c >= 48 ? b : a;
 }
 
 // ---- Bezier spline of the deformation, reference src/nerf.py:1173-1178 (de_casteljau), 1201-1206 (cubic_bezier) ----

@@ -196,9 +196,11 @@ k_render_fp32(const __grid_constant__ NfPlan plan, const RenderArgs a) {
         if (plan.mip != NF_MIP_NONE) {
           // Mip IPE of the UNdeformed ray segment (nerf.py:340: mip_encoding(r_o, r_d, ts)), kept in s.M for the View head
           const int base = plan.mlp[0].in_dims - NF_MIP_FEATS;
-          for (int c = part; c < NF_MIP_FEATS; c += THREADS / ROWS) {
-            const float f = s.valid[row] ? nf_mip_feature(a.mip, s.ray[row], s.t[row], c) : 0.f;
-            s.M[c * ROWS + row] = f; s.X0[(base + c) * ROWS + row] = f;
+          for (int cc = part; cc < NF_MIP_FEATS / 2; cc += THREADS / ROWS) {
+            float fs = 0.f, fc = 0.f;
+            if (s.valid[row]) nf_mip_feature_pair(a.mip, s.ray[row], s.t[row], cc, fs, fc);
+            s.M[cc * ROWS + row] = fs; s.X0[(base + cc) * ROWS + row] = fs;
+            s.M[(cc + 48) * ROWS + row] = fc; s.X0[(base + cc + 48) * ROWS + row] = fc;
           }
         }
       }

@@ -239,10 +239,12 @@ __device__ __forceinline__ void hash_x0_tail(uint8_t* X0, const NfPlan& plan, in
 }
 // this thread's share (features first, first + stride, ...) of the Mip latent of one row -> x0 columns [col0, col0 + 96)
 __device__ __forceinline__ void mip_x0(uint8_t* X0, const NfMipIn& mip, int col0, bool ok, long long ray, int t, int row, int first, int stride) {
-  for (int c = first; c < NF_MIP_FEATS; c += stride) {
-    const float f = ok ? nf_mip_feature(mip, ray, t, c) : 0.f;
-    const int col = col0 + c;
-    *reinterpret_cast<__half*>(X0 + (col >> 3) * KG_BYTES + row * 16 + (col & 7) * 2) = __float2half_rn(f);
+  for (int cc = first; cc < NF_MIP_FEATS / 2; cc += stride) {            // (sin, cos) pairs share mean, variance and exponential
+    float fs = 0.f, fc = 0.f;
+    if (ok) nf_mip_feature_pair(mip, ray, t, cc, fs, fc);
+    const int c0 = col0 + cc, c1 = c0 + NF_MIP_FEATS / 2;
+    *reinterpret_cast<__half*>(X0 + (c0 >> 3) * KG_BYTES + row * 16 + (c0 & 7) * 2) = __float2half_rn(fs);
+    *reinterpret_cast<__half*>(X0 + (c1 >> 3) * KG_BYTES + row * 16 + (c1 & 7) * 2) = __float2half_rn(fc);
   }
 }
 

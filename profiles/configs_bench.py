@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Secondary timings (not the bench line): the other BASELINE.json configurations on one B200, tensor pipeline.
+"""Secondary timings (not the bench line): the other BASELINE.json configurations on one B200, tensor pipeline
+(+ config 3, Mip IPE 800x800x128, and the Positional head, both in the single-tile wide-x0 mode).
     python profiles/configs_bench.py > gpurun_out/configs.json
 (2) PlainNeRF coarse 64 + fine 64+128 on 800x800; (4) VolSDF (SIREN SDF) 256 samples/ray; (5) D-NeRF 400x400x64."""
 import json, os, sys
@@ -50,4 +51,22 @@ rows.append({"config": "5: D-NeRF direct deformation + canonical PlainNeRF, 400x
 canon.precision = "fp32"
 ms32 = timed(f, reps=1)
 rows.append({"config": "5 (fp32 CUDA-core pipeline, for comparison)", "ms_per_frame": ms32, "rays_per_s": 160000 / ms32 * 1e3, "samples_per_ray": 64})
+# (3) PlainNeRF + Mip IPE (cylinder as intended, and the reference's bug-compatible layout), 800x800x128, tensor pipeline (single-tile mode)
+for mip in ("cylinder", "cylinder_ref", "cone"):
+  Pm = O.make_plain_params(61, 64, 1.0, mip=True)
+  em = N.RenderEngine(N.describe_plain(64, "upshifted", "black", mip=mip), "fp16"); em._p = plain_param_list(Pm, dev); em.pack(em._p)
+  r4 = rays800.reshape(1, 800, 800, 6)
+  rad = em.ray_radii(r4).reshape(-1)
+  ts128 = torch.linspace(2, 6, 128, device=dev)
+  ms = timed(lambda: em.render(rays800, ts128, radius=rad, want_weights=False), reps=2)
+  rows.append({"config": f"3: PlainNeRF + Mip IPE ({mip}), 800x800x128", "ms_per_frame": ms, "rays_per_s": 640000 / ms * 1e3, "samples_per_ray": 128})
+# Positional head (--refl-kind pos), 800x800x128
+Pp = O.make_plain_params(81, 64, 1.0, refl_kind="pos")
+mp = N.FusedPlainNeRF(steps=128, t_near=2, t_far=6, intermediate_size=64, sigmoid_kind="upshifted", precision="fp16", refl_kind="pos", keep_weights=False)
+mp.load_state_dict(Pp, strict=True); mp = mp.to(dev).eval()
+r4 = rays800.reshape(1, 800, 800, 6)
+def fp():
+  with torch.no_grad(): return mp(r4)
+ms = timed(fp, reps=2)
+rows.append({"config": "PlainNeRF + Positional head, 800x800x128", "ms_per_frame": ms, "rays_per_s": 640000 / ms * 1e3, "samples_per_ray": 128})
 for r in rows: print(json.dumps(r), flush=True)
