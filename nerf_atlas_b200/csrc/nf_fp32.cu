@@ -327,6 +327,27 @@ __global__ void k_sample_points(const float* __restrict__ rays, long long n_rays
   }
 }
 
+// T % 4 == 0: one thread per 4 consecutive samples of a ray = 48 contiguous, 16-byte aligned output bytes (three float4 stores)
+__global__ void k_sample_points4(const float* __restrict__ rays, long long n_rays, const float* __restrict__ ts,
+                                 int T, long long ts_stride, float* __restrict__ pts) {
+  const int q = T >> 2;
+  const long long total = n_rays * q;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long ray = i / q; const int t0 = (int)(i - ray * q) * 4;
+    const float* r = rays + ray * 6;
+    const float ox = __ldg(r), oy = __ldg(r + 1), oz = __ldg(r + 2), dx = __ldg(r + 3), dy = __ldg(r + 4), dz = __ldg(r + 5);
+    const float* tp = ts + ray * ts_stride + t0;
+    float o[12];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float tt = __ldg(tp + k);
+      o[3 * k] = nf_pt(ox, tt, dx); o[3 * k + 1] = nf_pt(oy, tt, dy); o[3 * k + 2] = nf_pt(oz, tt, dz);
+    }
+    float4* dst = reinterpret_cast<float4*>(pts + (ray * T + t0) * 3);
+    dst[0] = make_float4(o[0], o[1], o[2], o[3]); dst[1] = make_float4(o[4], o[5], o[6], o[7]); dst[2] = make_float4(o[8], o[9], o[10], o[11]);
+  }
+}
+
 __global__ void k_hash_encode(const __grid_constant__ NfPlan plan, const uint8_t* __restrict__ packed,
                               const float* __restrict__ pts, long long n, float* __restrict__ feats,
                               uint16_t* __restrict__ idx_out) {
@@ -361,25 +382,41 @@ __global__ void k_composite(int density_act, const float* __restrict__ beta_ptr,
     const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
     const float* tsr = ts + ray * ts_stride;
     float carry = 1.f, cr = 0.f, cg = 0.f, cb = 0.f, wsum = 0.f;
-    for (int base = 0; base < T; base += 32) {
-      const int t = base + lane;
-      float al = 0.f, fr = 0.f, fg = 0.f, fb = 0.f;
-      if (t < T) {
-        al = nf_alpha(__ldg(sigma_raw + ray * T + t), nf_delta(tsr, t, T, nrm), density_act, beta);
-        const float* f = feats + (ray * T + t) * 3;
-        fr = __ldg(f); fg = __ldg(f + 1); fb = __ldg(f + 2);
-      }
-      float p = t < T ? (1.f - al) + 1e-10f : 1.f;   // inclusive product scan of (1 - alpha + 1e-10)
+    for (int base0 = 0; base0 < T; base0 += 128) {
+      // all loads of up to four 32-sample chunks are issued before the first (dependent) scan: the kernel is latency-bound otherwise
+      float sg[4], fr[4], fg[4], fb[4], d0[4], d1[4];
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { const float q = __shfl_up_sync(0xffffffffu, p, d); if (lane >= d) p *= q; }
-      float excl = __shfl_up_sync(0xffffffffu, p, 1); if (lane == 0) excl = 1.f;
-      const float w = al * (carry * excl);
-      carry *= __shfl_sync(0xffffffffu, p, 31);
-      if (t < T) {
-        if (alpha_out) alpha_out[ray * T + t] = al;
-        if (weights_out) weights_out[ray * T + t] = w;
-        cr += w * fr; cg += w * fg; cb += w * fb;
-        if (t < T - 1) wsum += w;
+      for (int q = 0; q < 4; ++q) {
+        const int t = base0 + q * 32 + lane;
+        sg[q] = fr[q] = fg[q] = fb[q] = d0[q] = d1[q] = 0.f;
+        if (t < T) {
+          sg[q] = __ldg(sigma_raw + ray * T + t);
+          const float* f = feats + (ray * T + t) * 3;
+          fr[q] = __ldg(f); fg[q] = __ldg(f + 1); fb[q] = __ldg(f + 2);
+          d0[q] = __ldg(tsr + t); d1[q] = t + 1 < T ? __ldg(tsr + t + 1) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int t = base0 + q * 32 + lane;
+        if (base0 + q * 32 >= T) break;
+        float al = 0.f;
+        if (t < T) {
+          const float dl = (t == T - 1) ? 1e10f : fmaxf(__fsub_rn(d1[q], d0[q]), 1e-5f);
+          al = nf_alpha(sg[q], __fmul_rn(dl, nrm), density_act, beta);
+        }
+        float p = t < T ? (1.f - al) + 1e-10f : 1.f;   // inclusive product scan of (1 - alpha + 1e-10)
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const float qq = __shfl_up_sync(0xffffffffu, p, d); if (lane >= d) p *= qq; }
+        float excl = __shfl_up_sync(0xffffffffu, p, 1); if (lane == 0) excl = 1.f;
+        const float w = al * (carry * excl);
+        carry *= __shfl_sync(0xffffffffu, p, 31);
+        if (t < T) {
+          if (alpha_out) alpha_out[ray * T + t] = al;
+          if (weights_out) weights_out[ray * T + t] = w;
+          cr += w * fr[q]; cg += w * fg[q]; cb += w * fb[q];
+          if (t < T - 1) wsum += w;
+        }
       }
     }
 #pragma unroll
@@ -568,7 +605,13 @@ cudaError_t nf_launch_sample_points(const float* rays, int64_t n_rays, const flo
   if (total == 0) return cudaSuccess;
   const long long want = (total + 255) / 256;
   const int grid = (int)(want < (long long)num_sms() * 8 ? want : (long long)num_sms() * 8);
-  k_sample_points<<<grid, 256, 0, st>>>(rays, n_rays, ts, T, ts_stride, pts);
+  if ((T & 3) == 0 && ((uintptr_t)pts & 15) == 0) {
+    const long long want4 = (total / 4 + 255) / 256;
+    const int grid4 = (int)(want4 < (long long)num_sms() * 16 ? want4 : (long long)num_sms() * 16);
+    k_sample_points4<<<grid4, 256, 0, st>>>(rays, n_rays, ts, T, ts_stride, pts);
+  } else {
+    k_sample_points<<<grid, 256, 0, st>>>(rays, n_rays, ts, T, ts_stride, pts);
+  }
   return cudaGetLastError();
 }
 
