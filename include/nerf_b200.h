@@ -210,6 +210,18 @@ int nf_sample_pdf(const float* ts_coarse, int32_t T, const float* weights, int64
 int nf_mlp_forward(const nf_model_desc* desc, const void* packed, int32_t which,
                    const float* x0, int64_t n, float* out, int32_t precision, void* stream);
 
+/* ---- backward of the non-GEMM stages (first blocks of the training half; the reference differentiates these ops through
+ *      PyTorch autograd, runner.py:820) --------------------------------------------------------------------------- */
+/* Backward of nf_composite: d_rgb[R,3] -> d_sigma_raw_out[R,T], d_feats_out[R,T,3] (same inputs as the forward; T <= 2048).
+ * The gradient with respect to VolSDF's beta is not produced. */
+int nf_composite_backward(const nf_model_desc* desc, const void* packed, const float* sigma_raw, const float* feats,
+                          const float* rays, int64_t n_rays, const float* ts, int32_t T, int64_t ts_ray_stride,
+                          const float* d_rgb, float* d_sigma_raw_out, float* d_feats_out, void* stream);
+/* Backward of nf_hash_encode with respect to the tables: d_feats[N, levels*feat] is scatter-ADDED (trilinear weights, float4
+ * atomics) into d_tables[levels][table][feat], which the caller zeroes (or accumulates into across micro-batches). */
+int nf_hash_encode_backward(const nf_model_desc* desc, const float* pts, int64_t n, const float* d_feats, float* d_tables,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif

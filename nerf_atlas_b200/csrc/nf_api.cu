@@ -225,4 +225,29 @@ int nf_mlp_forward(const nf_model_desc* desc, const void* packed, int32_t which,
   return e == cudaSuccess ? 0 : cuda_fail(e, "nf_mlp_forward");
 }
 
+int nf_composite_backward(const nf_model_desc* desc, const void* packed, const float* sigma_raw, const float* feats,
+                          const float* rays, int64_t n_rays, const float* ts, int32_t T, int64_t ts_ray_stride,
+                          const float* d_rgb, float* d_sigma_raw_out, float* d_feats_out, void* stream) {
+  NfPlan p; if (int rc = plan_of(desc, &p)) return rc;
+  if (n_rays < 0) return fail(NF_E_BADARG, "n_rays < 0");
+  if (n_rays == 0) return 0;
+  if (!sigma_raw || !feats || !rays || !ts || !d_rgb || !d_sigma_raw_out || !d_feats_out) return fail(NF_E_BADARG, "nf_composite_backward: null pointer");
+  if (p.density_act == NF_DENS_LAPLACE && !packed) return fail(NF_E_BADARG, "nf_composite_backward: packed (beta) required for the Laplace density");
+  if (int rc = check_ts(T, ts_ray_stride)) return rc;
+  if (T > 2048) return fail(NF_E_UNSUPPORTED, "nf_composite_backward: T <= 2048");
+  cudaError_t e = nf_launch_composite_bwd(p, packed, sigma_raw, feats, rays, n_rays, ts, T, ts_ray_stride, d_rgb, d_sigma_raw_out, d_feats_out, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nf_composite_backward");
+}
+
+int nf_hash_encode_backward(const nf_model_desc* desc, const float* pts, int64_t n, const float* d_feats, float* d_tables, void* stream) {
+  NfPlan p; if (int rc = plan_of(desc, &p)) return rc;
+  if (p.enc != NF_ENC_HASH) return fail(NF_E_BADARG, "nf_hash_encode_backward: model has no hash encoder");
+  if (n < 0) return fail(NF_E_BADARG, "n < 0");
+  if (n == 0) return 0;
+  if (!pts || !d_feats || !d_tables) return fail(NF_E_BADARG, "nf_hash_encode_backward: null pointer");
+  if (((uintptr_t)d_tables & 15) || ((uintptr_t)d_feats & 15)) return fail(NF_E_BADARG, "nf_hash_encode_backward: d_tables / d_feats must be 16-byte aligned");
+  cudaError_t e = nf_launch_hash_encode_bwd(p, pts, n, d_feats, d_tables, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nf_hash_encode_backward");
+}
+
 }  // extern "C"

@@ -30,3 +30,8 @@ const char* nf_tc3_unsupported(const NfPlan& plan);
 cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const float* rays, int64_t n_rays, const float* ts,
                                  int T, int64_t ts_stride, const float* noise, const float* ray_time, const nf_mip_args* mip,
                                  float* rgb, float* alpha, float* weights, cudaStream_t st);
+// backward of the non-GEMM stages (nf_bwd.cu)
+cudaError_t nf_launch_composite_bwd(const NfPlan& plan, const void* packed, const float* sigma_raw, const float* feats, const float* rays,
+                                    int64_t n_rays, const float* ts, int T, int64_t ts_stride, const float* d_rgb, float* d_sigma,
+                                    float* d_feats, cudaStream_t st);
+cudaError_t nf_launch_hash_encode_bwd(const NfPlan& plan, const float* pts, int64_t n, const float* d_feats, float* d_tables, cudaStream_t st);

@@ -272,6 +272,29 @@ class RenderEngine:
     _lib.check(rc, "nf_composite")
     return rgb, alpha, weights
 
+  def composite_backward(self, sigma_raw: torch.Tensor, feats: torch.Tensor, rays: torch.Tensor, ts: torch.Tensor, d_rgb: torch.Tensor):
+    """Backward of ``composite``: d_rgb[R,3] -> (d_sigma_raw[R,T], d_feats[R,T,3])."""
+    for t, n in ((sigma_raw, "sigma_raw"), (feats, "feats"), (rays, "rays"), (ts, "ts"), (d_rgb, "d_rgb")): _chk(t, n)
+    R, T = sigma_raw.shape
+    stride = 0 if ts.dim() == 1 else T
+    d_sigma = torch.empty_like(sigma_raw); d_feats = torch.empty_like(feats)
+    with torch.cuda.device(rays.device):
+      rc = self.lib.nf_composite_backward(C.byref(self.desc), _ptr(self.packed), _ptr(sigma_raw), _ptr(feats), _ptr(rays), R, _ptr(ts), T, stride,
+                                          _ptr(d_rgb), _ptr(d_sigma), _ptr(d_feats), self._stream())
+    _lib.check(rc, "nf_composite_backward")
+    return d_sigma, d_feats
+
+  def hash_encode_backward(self, pts: torch.Tensor, d_feats: torch.Tensor, d_tables: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Backward of ``hash_encode`` w.r.t. the tables: scatter-adds into (and returns) d_tables[levels, table, 4]."""
+    _chk(pts, "pts"); _chk(d_feats, "d_feats")
+    L, table = self.desc.hash_levels, self.desc.hash_table_size
+    if d_tables is None: d_tables = torch.zeros(L, table, 4, dtype=torch.float32, device=pts.device)
+    _chk(d_tables, "d_tables")
+    with torch.cuda.device(pts.device):
+      rc = self.lib.nf_hash_encode_backward(C.byref(self.desc), _ptr(pts), pts.shape[0], _ptr(d_feats), _ptr(d_tables), self._stream())
+    _lib.check(rc, "nf_hash_encode_backward")
+    return d_tables
+
   def sample_pdf(self, ts_coarse: torch.Tensor, weights: torch.Tensor, u: torch.Tensor) -> torch.Tensor:
     """ts_coarse[T], weights[R,T] (coarse pass), u[R,Nf] in [0,1) -> sorted per-ray ts[R, T+Nf] for the fine pass."""
     _chk(ts_coarse, "ts_coarse"); _chk(weights, "weights"); _chk(u, "u")
