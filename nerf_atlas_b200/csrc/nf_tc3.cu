@@ -336,7 +336,9 @@ __device__ __forceinline__ void composite_tile3(Tc3Smem& s, int slot, const NfPl
 // NST ring stages of SPCT K-steps each (NST * SPCT * 4 KB = 48 KB); NCQ epilogue warps per TMEM lane quarter.  Warps
 // 0..4*NCQ-1 encode/epilogue, then NST weight producers (one stage each; the first also owns the TMEM allocation), then the
 // MMA issuer (highest warp id).
-template <int NST, int SPCT, int NCQ>
+// WIDE: the single-tile wide-x0 mode (Mip latent, Positional head) is compiled in.  The common path uses the WIDE = false
+// instantiation: with the wide code merely branched around, it ran 3.9 % slower (measured by bisection on one box).
+template <int NST, int SPCT, int NCQ, bool WIDE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (4 * NCQ + NST + 1), 1)
 k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Prog prog, const Tc3Args a) {
   static_assert(NST * SPCT * 4096 == RING_BYTES && NST <= MAX_STAGES3, "ring geometry");
@@ -348,7 +350,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
   const uint32_t crank = cluster_ctarank();
   const NfTileMap map(a.T, ROWS);
   const long long units = map.units(a.n_rays);
-  const bool single = prog.single != 0;            // one tile in flight: slot 1 never runs
+  const bool single = WIDE && prog.single != 0;    // one tile in flight: slot 1 never runs
   const int nslot = single ? 1 : 2;
   const int trips = (int)((units + (long long)nslot * gridDim.x - 1) / ((long long)nslot * gridDim.x));   // every CTA, every slot: same trip count
   const int passes = trips * map.tpr;
@@ -563,7 +565,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
             if (hashed)
               hash_x0(X0, reinterpret_cast<const float4*>(a.packed + (dyn ? plan.hash2_off : plan.hash_off)), plan, px, py, pz, row,
                       comp ? (cq == comp_cq ? -1 : ((cq - comp_cq - 1 + NCQ) % NCQ)) : cq, comp ? NCQ - 1 : NCQ);
-            const int mip0 = (plan.mip != NF_MIP_NONE && !dyn) ? nf_mip_col(plan, 0) : -1;
+            const int mip0 = (WIDE && plan.mip != NF_MIP_NONE && !dyn) ? nf_mip_col(plan, 0) : -1;
             if (mip0 >= 0) mip_x0(X0, a.mip, mip0, ok, ray, t, row, comp ? (cq == comp_cq ? NF_MIP_FEATS : ((cq - comp_cq - 1 + NCQ) % NCQ)) : cq, comp ? NCQ - 1 : NCQ);
             if (cq == tail_cq) {
               if (hashed) hash_x0_tail(X0, plan, plan.mlp[first_m].k0_pad, px, py, pz, row, mip0);
@@ -641,8 +643,8 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
           } else {
             // density MLP out (tensor order [inter(I), sigma]) -> raw x0 of the RGB head + raw density
             const int iu = plan.intermediate >> 4;
-            const bool pos_head = plan.refl_kind == NF_REFL_POSITIONAL;
-            const int mip1 = plan.mip != NF_MIP_NONE ? nf_mip_col(plan, 1) : -1;
+            const bool pos_head = WIDE && plan.refl_kind == NF_REFL_POSITIONAL;
+            const int mip1 = (WIDE && plan.mip != NF_MIP_NONE) ? nf_mip_col(plan, 1) : -1;
             if (pos_head || mip1 >= 0) {
               // wide RGB-head inputs (single mode): every thread takes a share of its row's Positional hash features and Mip latent
               long long u; int sub; unit_of(P, slot, map.tpr, nslot, u, sub);
@@ -797,7 +799,13 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
   if (const char* r = getenv("NF_TC_EPIW")) epiw = atoi(r);
   if (ring != 6) ring = 3;
   if (epiw != 24 || ring != 3) epiw = 16;
-  const void* fn = epiw == 24 ? (const void*)k_render_tc3<3, 4, 6> : ring == 3 ? (const void*)k_render_tc3<3, 4, 4> : (const void*)k_render_tc3<6, 2, 4>;
+  Tc3Prog prog;
+  if (!build_prog3(plan, &prog)) return cudaErrorNotSupported;
+  const bool wide = prog.single != 0 || plan.mip != NF_MIP_NONE || plan.refl_kind != NF_REFL_VIEW;
+  if (wide) { ring = 3; epiw = 16; }
+  const void* fn = wide ? (const void*)k_render_tc3<3, 4, 4, true>
+                 : epiw == 24 ? (const void*)k_render_tc3<3, 4, 6, false>
+                 : ring == 3 ? (const void*)k_render_tc3<3, 4, 4, false> : (const void*)k_render_tc3<6, 2, 4, false>;
   const int threads = 32 * (epiw + ring + 1);
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tc3Smem));
   if (e != cudaSuccess) return e;
@@ -806,8 +814,6 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
   if (units == 0) return cudaSuccess;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  Tc3Prog prog;
-  if (!build_prog3(plan, &prog)) return cudaErrorNotSupported;
   const long long nslot = prog.single ? 1 : 2;
   long long want = (units + 2 * nslot - 1) / (2 * nslot) * 2;                      // 2 CTAs x nslot tiles per cluster
   const int grid = (int)(want < (sms / 2) * 2 ? want : (sms / 2) * 2);
@@ -819,9 +825,10 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
   cudaMemsetAsync(d_stats, 0, 64 * sizeof(long long), st);
   a.stats = d_stats;
 #endif
-  if (epiw == 24) k_render_tc3<3, 4, 6><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a);
-  else if (ring == 3) k_render_tc3<3, 4, 4><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a);
-  else k_render_tc3<6, 2, 4><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a);
+  if (wide) k_render_tc3<3, 4, 4, true><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a);
+  else if (epiw == 24) k_render_tc3<3, 4, 6, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a);
+  else if (ring == 3) k_render_tc3<3, 4, 4, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a);
+  else k_render_tc3<6, 2, 4, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a);
 #ifdef NF_TC_STATS
   if (getenv("NF_TC_STATS_PRINT")) {
     cudaStreamSynchronize(st);
