@@ -338,7 +338,8 @@ __device__ __forceinline__ void composite_tile3(Tc3Smem& s, int slot, const NfPl
 // MMA issuer (highest warp id).
 // WIDE: the single-tile wide-x0 mode (Mip latent, Positional head) is compiled in.  The common path uses the WIDE = false
 // instantiation: with the wide code merely branched around, it ran 3.9 % slower (measured by bisection on one box).
-template <int NST, int SPCT, int NCQ, bool WIDE>
+// DYN: the DynamicNeRF chain (deformation-out epilogue, Bezier, re-encode) is compiled in; same reason.
+template <int NST, int SPCT, int NCQ, bool WIDE, bool DYN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (4 * NCQ + NST + 1), 1)
 k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Prog prog, const Tc3Args a) {
   static_assert(NST * SPCT * 4096 == RING_BYTES && NST <= MAX_STAGES3, "ring geometry");
@@ -559,7 +560,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
             }
             // x0 of the FIRST MLP of the path: the density MLP, or (NF_KIND_DYN) the deformation MLP.  4 threads per row share
             // the hash levels; when the cq == 0 warps are compositing, the other three take them all
-            const bool dyn = plan.kind == NF_KIND_DYN;
+            const bool dyn = DYN && plan.kind == NF_KIND_DYN;
             const int first_m = dyn ? 2 : 0;
             const bool hashed = dyn ? plan.deform_enc == NF_ENC_HASH : plan.enc == NF_ENC_HASH;
             if (hashed)
@@ -603,7 +604,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
             else if (act == NF_ACT_LEAKY) epi_hidden3<NF_ACT_LEAKY, NCQ>(H, t_acc, bias, cq, row);
             else if (act == NF_ACT_RELU) epi_hidden3<NF_ACT_RELU, NCQ>(H, t_acc, bias, cq, row);
             else epi_hidden3<NF_ACT_NONE, NCQ>(H, t_acc, bias, cq, row);
-          } else if (((Lc.w >> 2) & 3) == 2) {
+          } else if (DYN && ((Lc.w >> 2) & 3) == 2) {
             // deformation MLP out (reference nerf.py:1261-1278): every thread deforms its row's sample, then takes its share of
             // the density MLP's hash levels at the DEFORMED position (the canonical NeRF sees pts + rigid_dp, nerf.py:1303)
             uint32_t v[32];
@@ -686,7 +687,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
                     const float* rr = a.rays + ray * 6;
                     const float tt = __ldg(a.ts + ray * a.ts_stride + t);
                     const float dx = __ldg(rr + 3), dy = __ldg(rr + 4), dz = __ldg(rr + 5);
-                    if (plan.kind == NF_KIND_DYN) { px = s.P[slot][0][row]; py = s.P[slot][1][row]; pz = s.P[slot][2][row]; }
+                    if (DYN && plan.kind == NF_KIND_DYN) { px = s.P[slot][0][row]; py = s.P[slot][1][row]; pz = s.P[slot][2][row]; }
                     else { px = nf_pt(__ldg(rr + 0), tt, dx); py = nf_pt(__ldg(rr + 1), tt, dy); pz = nf_pt(__ldg(rr + 2), tt, dz); }
                     nf_elaz(dx, dy, dz, el, az);
                   }
@@ -803,9 +804,12 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
   if (!build_prog3(plan, &prog)) return cudaErrorNotSupported;
   const bool wide = prog.single != 0 || plan.mip != NF_MIP_NONE || plan.refl_kind != NF_REFL_VIEW;
   if (wide) { ring = 3; epiw = 16; }
-  const void* fn = wide ? (const void*)k_render_tc3<3, 4, 4, true>
-                 : epiw == 24 ? (const void*)k_render_tc3<3, 4, 6, false>
-                 : ring == 3 ? (const void*)k_render_tc3<3, 4, 4, false> : (const void*)k_render_tc3<6, 2, 4, false>;
+  const bool dynk = plan.kind == NF_KIND_DYN;
+  if (dynk) { ring = 3; epiw = 16; }
+  const void* fn = wide ? (const void*)k_render_tc3<3, 4, 4, true, false>
+                 : dynk ? (const void*)k_render_tc3<3, 4, 4, false, true>
+                 : epiw == 24 ? (const void*)k_render_tc3<3, 4, 6, false, false>
+                 : ring == 3 ? (const void*)k_render_tc3<3, 4, 4, false, false> : (const void*)k_render_tc3<6, 2, 4, false, false>;
   const int threads = 32 * (epiw + ring + 1);
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tc3Smem));
   if (e != cudaSuccess) return e;
@@ -825,10 +829,11 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
   cudaMemsetAsync(d_stats, 0, 64 * sizeof(long long), st);
   a.stats = d_stats;
 #endif
-  if (wide) k_render_tc3<3, 4, 4, true><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a);
-  else if (epiw == 24) k_render_tc3<3, 4, 6, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a);
-  else if (ring == 3) k_render_tc3<3, 4, 4, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a);
-  else k_render_tc3<6, 2, 4, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a);
+  if (wide) k_render_tc3<3, 4, 4, true, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a);
+  else if (dynk) k_render_tc3<3, 4, 4, false, true><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a);
+  else if (epiw == 24) k_render_tc3<3, 4, 6, false, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a);
+  else if (ring == 3) k_render_tc3<3, 4, 4, false, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a);
+  else k_render_tc3<6, 2, 4, false, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a);
 #ifdef NF_TC_STATS
   if (getenv("NF_TC_STATS_PRINT")) {
     cudaStreamSynchronize(st);
