@@ -135,7 +135,7 @@ int nf_render_forward(const nf_model_desc* desc, const void* packed, const float
     int pipe = 3;
     if (const char* env = getenv("NF_TC_PIPE")) pipe = atoi(env);
     if (const char* env = getenv("NF_TC_PAIRED")) if (env[0] == '0') pipe = 1;
-    if (p.kind == NF_KIND_DYN || p.mip != NF_MIP_NONE || p.refl_kind != NF_REFL_VIEW) {
+    if (p.kind == NF_KIND_DYN || p.mip != NF_MIP_NONE || p.refl_kind != NF_REFL_VIEW || p.enc == NF_ENC_FOURIER) {
       // only the staggered pipeline runs the three-MLP chain and the wide-x0 (single-tile) mode
       if (const char* why = nf_tc3_unsupported(p)) return fail(NF_E_UNSUPPORTED, why);
       pipe = 3;

@@ -18,7 +18,8 @@
 // tile (result of Linear n-1) + encode of the next one.  After phase j the issuer runs Linear j for that slot.
 //
 // Wide x0 (the Mip latent: 144 / 176 columns; the Positional head: 112): the two 80-column x0 buffers are too small, so the
-// kernel runs ONE tile in flight per CTA ("single" mode) and keeps x0 in the idle slot's 64 KB activation buffer.
+// kernel runs ONE tile in flight per CTA ("single" mode) and keeps x0 in the idle slot's 64 KB activation buffer (the Fourier-
+// encoded SDF MLP's 272 columns spill over into the two unused 20 KB x0 buffers that follow it in shared memory).
 //
 // Warp roles as in nf_tc2.cu: 0-15 encode/epilogue (TMEM lane quarter q = warp % 4, column quarter cq = warp / 4), 16/18/19
 // weight producers (one ring stage each), 17 the MMA issuer (leader CTA only).
@@ -52,6 +53,7 @@ struct Tc3Smem {
                                 // 1 density-out -> View x0, 2 deformation-out -> deform + encode, 3 the path's last Linear
 };
 static_assert(sizeof(Tc3Smem) <= 227 * 1024, "staggered tensor pipeline smem");
+static_assert(offsetof(Tc3Smem, X0) == offsetof(Tc3Smem, H) + sizeof(Tc3Smem::H), "single mode: wide x0 runs from H[1] on into X0[]");
 
 // Host-built program (kernel parameter => uniform constant loads in the issuing thread).  One record per Linear:
 // MMA shape/steps (issuer), this Linear's weight image (producers), (mlp, layer) (epilogue).
@@ -568,7 +570,25 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
                       comp ? (cq == comp_cq ? -1 : ((cq - comp_cq - 1 + NCQ) % NCQ)) : cq, comp ? NCQ - 1 : NCQ);
             const int mip0 = (WIDE && plan.mip != NF_MIP_NONE && !dyn) ? nf_mip_col(plan, 0) : -1;
             if (mip0 >= 0) mip_x0(X0, a.mip, mip0, ok, ray, t, row, comp ? (cq == comp_cq ? NF_MIP_FEATS : ((cq - comp_cq - 1 + NCQ) % NCQ)) : cq, comp ? NCQ - 1 : NCQ);
-            if (cq == tail_cq) {
+            const bool fourier = WIDE && !dyn && plan.enc == NF_ENC_FOURIER;
+            if (fourier) {
+              // x0 = [p, sin(p B), cos(p B)], B = basis[3][F] (reference src/neural_blocks.py:36-55, src/utils.py:14-17); reference
+              // column order, element-wise half stores (columns are not 8-aligned); the frequencies are shared like the hash levels
+              const float* Bm = reinterpret_cast<const float*>(a.packed + plan.fourier_off);
+              const int F = plan.fourier_freqs;
+              const int first = comp ? (cq == comp_cq ? F : ((cq - comp_cq - 1 + NCQ) % NCQ)) : cq, stride = comp ? NCQ - 1 : NCQ;
+              for (int f = first; f < F; f += stride) {
+                const float m = fmaf(pz, __ldg(Bm + 2 * F + f), fmaf(py, __ldg(Bm + F + f), __fmul_rn(px, __ldg(Bm + f))));
+                const int c0 = 3 + f, c1 = 3 + F + f;
+                *reinterpret_cast<__half*>(X0 + (c0 >> 3) * KG_BYTES + row * 16 + (c0 & 7) * 2) = __float2half_rn(ok ? sinf(m) : 0.f);
+                *reinterpret_cast<__half*>(X0 + (c1 >> 3) * KG_BYTES + row * 16 + (c1 & 7) * 2) = __float2half_rn(ok ? cosf(m) : 0.f);
+              }
+              if (cq == tail_cq) {
+                const float pv[3] = {px, py, pz};
+                for (int c = 0; c < 3; ++c) *reinterpret_cast<__half*>(X0 + row * 16 + c * 2) = __float2half_rn(pv[c]);
+                for (int c = 3 + 2 * F; c < plan.mlp[0].k0_pad; ++c) *reinterpret_cast<__half*>(X0 + (c >> 3) * KG_BYTES + row * 16 + (c & 7) * 2) = __float2half_rn(0.f);
+              }
+            } else if (cq == tail_cq) {
               if (hashed) hash_x0_tail(X0, plan, plan.mlp[first_m].k0_pad, px, py, pz, row, mip0);
               else {
                 const float tt = (dyn && ok) ? __ldg(a.ray_time + ray) : 0.f;        // direct deformation: x0 = [p, t]
@@ -760,20 +780,21 @@ const char* nf_tc3_unsupported(const NfPlan& p) {
   const bool wide = p.mip != NF_MIP_NONE || p.refl_kind != NF_REFL_VIEW;
   if (wide && p.kind != NF_KIND_PLAIN) return "Mip / Positional on the tensor pipeline: PlainNeRF only (DynamicNeRF runs them on the fp32 pipeline)";
   if (wide && p.enc != NF_ENC_HASH) return "Mip / Positional on the tensor pipeline need the hash-encoded density MLP";
+  const bool fourier = p.enc == NF_ENC_FOURIER && p.kind == NF_KIND_PLAIN;        // the Fourier-encoded SDF MLP of VolSDF: x0 259 -> 272
   if (p.kind == NF_KIND_DYN && p.enc != NF_ENC_HASH) return "NF_KIND_DYN: the canonical NeRF must be hash-encoded";
   if (p.kind == NF_KIND_DYN && p.mlp[2].lin[p.mlp[2].n_lin - 1].n_pad > 32) return "deformation MLP with more than 32 outputs";
   int nlin = 0;
   for (int m = 0; m < p.n_mlps; ++m) {
     nlin += p.mlp[m].n_lin;
-    if (p.mlp[m].k0_pad > 256) return "x0 wider than 256 columns";
-    if (p.mlp[m].k0_pad > X0K && !wide) return "x0 wider than 80 columns";       // e.g. the Fourier-encoded SDF MLP (259)
+    if (p.mlp[m].k0_pad > (fourier ? 400 : 256)) return "x0 too wide for the single-tile mode";
+    if (p.mlp[m].k0_pad > X0K && !wide && !fourier) return "x0 wider than 80 columns";
     for (int j = 0; j < p.mlp[m].n_lin; ++j) {
       // only the density MLP of a two-MLP model may end in a non-final `out` Linear
       if (p.mlp[m].lin[j].is_out && p.kind == NF_KIND_TINY && m != 0) return "unsupported MLP chain";
     }
   }
   if (nlin > MAX_LIN3 || nlin < 2) return "unsupported number of Linear layers";
-  if (p.enc == NF_ENC_FOURIER) return "Fourier-encoded density MLP (x0 is 259 wide) runs on the fp32 pipeline only";
+  if (p.enc == NF_ENC_FOURIER && !fourier) return "Fourier-encoded density MLP: PlainNeRF / VolSDF kind only";
   if (p.enc == NF_ENC_HASH && (p.hash_levels & 1)) return "odd number of hash levels";
   if (p.kind == NF_KIND_PLAIN && (p.intermediate & 15)) return "intermediate_size not a multiple of 16";
   return nullptr;
