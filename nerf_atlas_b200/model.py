@@ -628,6 +628,8 @@ class FusedDynamicNeRF(nn.Module):
     super().__init__()
     if refl_latent: raise NotImplementedError("refl_latent variant of DynamicNeRF")
     if spline and not 2 <= spline <= 8: raise NotImplementedError("spline points must be in 2..8")
+    if canonical.mip_size() or canonical.refl_kind != "view":
+      raise NotImplementedError("DynamicNeRF over a Mip / Positional canonical NeRF is not built")
     self.canonical = canonical
     self.spline = spline
     if spline: self.delta_estim = SkipConnParams(38, 1 + 3 * spline, 5, init="xavier", enc=HashParams())
@@ -637,7 +639,7 @@ class FusedDynamicNeRF(nn.Module):
     self._engine_key = None
 
   @classmethod
-  def from_reference(cls, ref, precision: str = "fp32") -> "FusedDynamicNeRF":
+  def from_reference(cls, ref, precision: str = "fp16") -> "FusedDynamicNeRF":
     if getattr(ref, "refl_latent", 0): raise NotImplementedError("refl_latent variant of DynamicNeRF")
     self = cls.__new__(cls); nn.Module.__init__(self)
     self.spline = int(getattr(ref, "spline", 0))
