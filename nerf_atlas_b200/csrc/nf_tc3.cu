@@ -250,6 +250,30 @@ __device__ __forceinline__ void mip_x0(uint8_t* X0, const NfMipIn& mip, int col0
   }
 }
 
+// ---- tile <-> (ray, t) map of this kernel: the SAMPLE STREAM of a unit is cut into 128-row tiles ----------------------
+// A unit = rpu whole rays = tpu whole tiles (rpu * Tp == tpu * 128, Tp = per-ray stride in the stream).  Tp = T packs rays back
+// to back, so a tile may hold the tail of one ray and the head of the next (T = 192: 2 rays in 3 tiles instead of 4; T = 160:
+// 4 rays in 5 tiles instead of 8).  Otherwise (T not a multiple of 32) Tp pads every ray to whole tiles / a divisor of 128 as
+// the other kernels do.  All carries stay inside a unit, which one slot walks tile by tile.
+struct NfStreamMap {
+  int T, Tp, tpr, rpu;        // tpr = tiles per unit (the name the schedule code uses), rpu = rays per unit
+  __host__ __device__ static int gcd(int a, int b) { while (b) { const int r = a % b; a = b; b = r; } return a; }
+  __host__ __device__ NfStreamMap(int T_, int rows) : T(T_) {
+    Tp = T_;
+    // packing needs warp-aligned rays (T % 32 == 0): the in-warp scan/reduction trees then see every ray at the same lanes, so
+    // a ray's rounding does not depend on its position in the unit (a sharded render must equal the whole bit for bit)
+    if ((T_ & 31) != 0 || T_ / gcd(T_, rows) > 64) Tp = T_ <= rows ? rows / (rows / T_) : (T_ + rows - 1) / rows * rows;
+    const int g = gcd(Tp, rows);
+    tpr = Tp / g; rpu = rows / g;
+  }
+  __host__ __device__ long long units(long long n_rays) const { return (n_rays + rpu - 1) / rpu; }
+  __device__ __forceinline__ bool locate(long long u, int sub, int r, long long n_rays, long long& ray, int& t) const {
+    const int q = sub * ROWS + r, rl = q / Tp;
+    t = q - rl * Tp; ray = u * rpu + rl;
+    return t < T && ray < n_rays;
+  }
+};
+
 // work unit of (pass, slot) for this CTA, and the sub-tile within a ray (T > 128)
 __device__ __forceinline__ void unit_of(int pass, int slot, int tpr, int nslot, long long& u, int& sub) {
   const int trip = tpr == 1 ? pass : pass / tpr;
@@ -257,12 +281,14 @@ __device__ __forceinline__ void unit_of(int pass, int slot, int tpr, int nslot, 
   u = ((long long)trip * gridDim.x + blockIdx.x) * nslot + slot;     // nslot = tiles in flight per CTA (2; 1 in single mode)
 }
 
-// ---- composite of one tile by the 4 cq == 0 warps (thread = row); reference nerf.py:60-80 ----
-__device__ __forceinline__ void composite_tile3(Tc3Smem& s, int slot, const NfPlan& plan, const Tc3Args& a, const NfTileMap& map,
+// ---- composite of one tile by four warps (thread = row); reference nerf.py:60-80 ----
+// A tile holds up to 128 / Tp + 2 ray segments; the first may continue a ray from the previous tile of the unit (carry in), the
+// last may be unfinished (carry out).  Products and sums are LEFT folds in sample order -- 32-sample chunk by chunk, across
+// tile boundaries -- so a ray's result does not depend on where in a unit it happens to sit.
+__device__ __forceinline__ void composite_tile3(Tc3Smem& s, int slot, const NfPlan& plan, const Tc3Args& a, const NfStreamMap& map,
                                                 long long u, int sub, int row, int lane, int q, float cr, float cg, float cb) {
   long long ray; int t;
-  const bool valid = map.locate(u, sub, row, a.n_rays, ray, t);
-  if (!valid) t = 0;
+  const bool valid = map.locate(u, sub, row, a.n_rays, ray, t);       // t is the position within the (padded) ray even when invalid
   float al = 0.f;
   if (valid) {
     float sr = s.sig[slot][row];
@@ -280,22 +306,26 @@ __device__ __forceinline__ void composite_tile3(Tc3Smem& s, int slot, const NfPl
   }
   float excl = __shfl_up_sync(0xffffffffu, incl, 1);
   if (lane == 0 || t == 0) excl = 1.f;
-  if (lane == 31) { s.warp_agg[slot][q] = incl; s.warp_cont[slot][q] = t > 31; }
+  if (lane == 31) s.warp_agg[slot][q] = incl;             // product over the last ray segment of this warp
+  float* carry = s.carry[slot];
+  const float carry_T = carry[0];                          // read before anyone overwrites it (the writes come after the 2nd barrier)
   named_bar(3 + slot, 128);
-  float c = 1.f; bool open = true;
-  for (int v = q - 1; v >= 0 && open; --v) { c *= s.warp_agg[slot][v]; open = s.warp_cont[slot][v] != 0; }
-  if (open && sub > 0) c *= s.carry[slot][0];
-  const float trans = excl * (t > lane ? c : 1.f);
+  // transmittance entering this warp for a ray that began before it: left fold from the ray's first chunk in this tile
+  float c = 1.f;
+  if (t > lane) {
+    const int first = row - t;                             // row of the ray's sample 0 (negative: it began in an earlier tile)
+    c = first < 0 ? carry_T : 1.f;
+    for (int v = first < 0 ? 0 : first >> 5; v < q; ++v) c *= s.warp_agg[slot][v];
+  }
+  const float trans = excl * c;
   const float w = al * trans;
   if (valid) {
     if (a.alpha_out) a.alpha_out[ray * a.T + t] = al;
     if (a.weights_out) a.weights_out[ray * a.T + t] = w;
   }
   const float wr = w * cr, wg = w * cg, wb = w * cb, wl = (valid && t < a.T - 1) ? w : 0.f;
-  const int row_thread = q * 32 + lane;
-  float* carry = s.carry[slot];
   float* wrgb = reinterpret_cast<float*>(s.H[slot]);          // H[slot] is dead between the last Linear's MMA and the next tile
-  const bool fast = (a.T & 31) == 0;
+  const bool fast = (map.Tp & 31) == 0;                       // no warp straddles two rays: per-warp sums suffice
   if (fast) {
     float x0 = wr, x1 = wg, x2 = wb, x3 = wl;
 #pragma unroll
@@ -305,31 +335,37 @@ __device__ __forceinline__ void composite_tile3(Tc3Smem& s, int slot, const NfPl
     }
     if (lane == 0) { float* ws = s.warp_sum[slot][q]; ws[0] = x0; ws[1] = x1; ws[2] = x2; ws[3] = x3; }
   } else {
-    float* wq = wrgb + row_thread * 4;
+    float* wq = wrgb + row * 4;
     wq[0] = wr; wq[1] = wg; wq[2] = wb; wq[3] = wl;
   }
+  // thread i owns ray segment i of this tile
+  const int q0 = sub * ROWS;
+  const int rl_first = q0 / map.Tp;
+  const int rl = rl_first + row;
+  const int seg_begin = rl * map.Tp - q0, seg_end = seg_begin + map.Tp;      // rows of the segment, before clipping to the tile
+  const bool owner = seg_begin < ROWS && rl < map.rpu;
+  const bool cont = owner && seg_begin < 0, ends = owner && seg_end <= ROWS;
+  float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f, pT = 1.f;
+  if (cont) { pT = carry_T; o0 = carry[1]; o1 = carry[2]; o2 = carry[3]; o3 = carry[4]; }
   named_bar(3 + slot, 128);
-  const int nseg = a.T <= ROWS ? map.rpt : 1;
-  const int row0 = a.T <= ROWS ? row_thread * a.T : 0;
-  if (row_thread < nseg) {
-    long long r; int t0;
-    if (map.locate(u, sub, row0, a.n_rays, r, t0)) {
-      float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-      if (sub > 0) { o0 = carry[1]; o1 = carry[2]; o2 = carry[3]; o3 = carry[4]; }
-      if (fast) {
-        const int wpr = a.T <= ROWS ? a.T / 32 : 4;
-        for (int v = 0; v < wpr; ++v) { const float* ws = s.warp_sum[slot][row_thread * wpr + v]; o0 += ws[0]; o1 += ws[1]; o2 += ws[2]; o3 += ws[3]; }
-      } else {
-        const int nrow = a.T <= ROWS ? a.T : min(ROWS, a.T - sub * ROWS);
-        for (int i = 0; i < nrow; ++i) { const float* x = wrgb + (row0 + i) * 4; o0 += x[0]; o1 += x[1]; o2 += x[2]; o3 += x[3]; }
-      }
-      if (sub == map.tpr - 1) {
+  if (owner) {
+    const int rb = seg_begin < 0 ? 0 : seg_begin, re = seg_end > ROWS ? ROWS : seg_end;
+    if (fast) {
+      for (int v = rb >> 5; v < (re >> 5); ++v) { const float* ws = s.warp_sum[slot][v]; o0 += ws[0]; o1 += ws[1]; o2 += ws[2]; o3 += ws[3]; }
+    } else {
+      for (int i = rb; i < re; ++i) { const float* x = wrgb + i * 4; o0 += x[0]; o1 += x[1]; o2 += x[2]; o3 += x[3]; }
+    }
+    const long long r = u * map.rpu + rl;
+    if (ends) {
+      if (r < a.n_rays) {
         const float skyv = plan.bg == NF_BG_WHITE ? 1.f - o3 : 0.f;
         a.rgb_out[r * 3 + 0] = o0 + skyv; a.rgb_out[r * 3 + 1] = o1 + skyv; a.rgb_out[r * 3 + 2] = o2 + skyv;
-      } else {
-        carry[1] = o0; carry[2] = o1; carry[3] = o2; carry[4] = o3;
-        carry[0] = (sub > 0 ? carry[0] : 1.f) * s.warp_agg[slot][0] * s.warp_agg[slot][1] * s.warp_agg[slot][2] * s.warp_agg[slot][3];
       }
+    } else {
+      // the unfinished last segment: carry the sums and the transmittance (left fold over its chunks; it starts warp-aligned or
+      // at row 0, and in the non-fast case its first warp's aggregate is that of the warp's last segment = this ray)
+      for (int v = rb >> 5; v < 4; ++v) pT *= s.warp_agg[slot][v];
+      carry[0] = pT; carry[1] = o0; carry[2] = o1; carry[3] = o2; carry[4] = o3;
     }
   }
 }
@@ -351,7 +387,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
   Tc3Smem& s = *reinterpret_cast<Tc3Smem*>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();
-  const NfTileMap map(a.T, ROWS);
+  const NfStreamMap map(a.T, ROWS);
   const long long units = map.units(a.n_rays);
   const bool single = WIDE && prog.single != 0;    // one tile in flight: slot 1 never runs
   const int nslot = single ? 1 : 2;
@@ -834,7 +870,7 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
   const int threads = 32 * (epiw + ring + 1);
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tc3Smem));
   if (e != cudaSuccess) return e;
-  const NfTileMap map(T, ROWS);
+  const NfStreamMap map(T, ROWS);
   const long long units = map.units(n_rays);
   if (units == 0) return cudaSuccess;
   int dev = 0, sms = 148;

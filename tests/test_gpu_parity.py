@@ -165,7 +165,7 @@ def test_tensor_pipeline_variants_vs_oracle(P, env, monkeypatch):
   tiles (T = 256), ragged tiles (T = 100), several rays per tile (T = 32), noise, per-ray ts and the white background."""
   for k, v in env.items(): monkeypatch.setenv(k, v)
   e = plain_engine(P, DEV, precision="fp16")
-  for T, nr in ((128, 1500), (256, 333), (100, 77), (32, 1001)):
+  for T, nr in ((128, 1500), (256, 333), (192, 301), (160, 203), (100, 77), (32, 1001)):   # 192 / 160: rays packed across tile boundaries
     rays = O.make_rays(1, 40, 40, seed=T, crop_top=380, crop_left=380).reshape(-1, 6)[:nr]
     ts = torch.linspace(2, 6, T)
     with torch.no_grad():
