@@ -54,3 +54,60 @@ class ShardedRenderer:
     parts = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(parts, pad, group=self.group)
     return torch.cat([p[: b[1] - b[0]] for p, b in zip(parts, bounds)], dim=0)
+
+
+class GradientAllReducer:
+  """The one collective of data-parallel training: every rank renders its block of the step's rays,
+  back-propagates the SUM of its per-ray losses, and the flattened fp32 gradient is all-reduced (sum) once per optimiser step
+  and divided by the global ray count, so that every rank applies the gradient of the mean loss over ALL rays -- what the
+  single-process reference computes (loss = mean over the crop, runner.py:600-602, 820-824).
+
+  One flat fp32 bucket (2.7 M parameters for Plain+View = 10.8 MB: a single NCCL all-reduce over NVLink; NVSwitch makes the cost
+  latency-, not link-bound, so there is nothing to gain from splitting it).  ``begin()`` launches the all-reduce asynchronously
+  (on NCCL: on the communicator's own stream, overlapping whatever the caller still has to run, e.g. the tail of backward of
+  another parameter group); ``finish()`` waits and scatters the averaged gradient back into ``p.grad``.
+  Host-side plumbing only: torch.distributed (NCCL on GPUs, gloo in the CPU tests)."""
+
+  def __init__(self, params, group: Optional[dist.ProcessGroup] = None):
+    self.params = [p for p in params if p.requires_grad]
+    self.group = group
+    self._flat: Optional[torch.Tensor] = None
+    self._work = None
+    self._count: Optional[torch.Tensor] = None
+
+  def _world(self) -> int:
+    return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+
+  def begin(self, n_local_rays: int):
+    """Call after backward of the local SUM loss.  n_local_rays = rays this rank contributed to the step."""
+    ps = self.params
+    if not ps: return
+    dev = ps[0].device
+    total = sum(p.numel() for p in ps)
+    if self._flat is None or self._flat.numel() != total + 1 or self._flat.device != dev:
+      self._flat = torch.empty(total + 1, dtype=torch.float32, device=dev)     # last element carries the ray count
+    off = 0
+    for p in ps:
+      n = p.numel()
+      if p.grad is None: self._flat[off:off + n].zero_()
+      else: self._flat[off:off + n].copy_(p.grad.reshape(-1))
+      off += n
+    self._flat[total] = float(n_local_rays)
+    if self._world() > 1: self._work = dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+  def finish(self) -> int:
+    """Waits for the all-reduce; p.grad <- (sum over ranks of local grads) / (global ray count).  Returns that count."""
+    ps = self.params
+    if not ps or self._flat is None: return 0
+    if self._work is not None: self._work.wait(); self._work = None
+    total = self._flat.numel() - 1
+    n_rays = float(self._flat[total].item())
+    scale = 1.0 / max(n_rays, 1.0)
+    off = 0
+    for p in ps:
+      n = p.numel()
+      g = self._flat[off:off + n].reshape(p.shape) * scale
+      if p.grad is None: p.grad = g.clone()
+      else: p.grad.copy_(g)
+      off += n
+    return int(n_rays)

@@ -107,3 +107,52 @@ dist.barrier(); dist.destroy_process_group(); print("ok")
   for p in procs:
     out, _ = p.communicate(timeout=180)
     assert p.returncode == 0 and "ok" in out, out
+
+
+def test_gloo_world2_gradient_allreduce_equals_full_batch():
+  """Training-time collective: two gloo ranks with UNEQUAL ray blocks back-propagate their local sum losses through
+  the reference algorithm (the CPU oracle stands in for the fused backward, which is not built), all-reduce the flat gradient
+  once, and end up with the gradient of the mean loss over all rays -- equal to the single-process full-batch gradient."""
+  code = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["NF_ROOT"])
+from nerf_atlas_b200.shard import GradientAllReducer, shard_rays
+from oracle import nerf_oracle as O          # test infrastructure: the differentiable stand-in model
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % os.environ["NF_PORT"], rank=int(os.environ["NF_RANK"]), world_size=2)
+rank = dist.get_rank()
+torch.manual_seed(0)
+names = ["first.out.weight", "first.out.bias", "refl.mlp.out.weight", "refl.mlp.layers.1.weight", "first.enc.embs.2.weight"]
+def build():
+  P = O.make_plain_params(5, 64, 20.0)
+  for n in names: P[n] = P[n].clone().requires_grad_(True)
+  return P
+rays = O.make_rays(1, 3, 7, seed=2, crop_top=398, crop_left=396).reshape(-1, 6)      # 21 rays
+target = torch.rand(21, 3)
+ts = torch.linspace(2, 6, 12)
+# single-process reference: mean loss over all rays
+P = build()
+loss = ((O.plain_forward(P, rays, ts)["out"] - target) ** 2).sum(-1).mean()
+loss.backward()
+full = [P[n].grad.clone() for n in names]
+# two ranks, unequal blocks: 8 and 13 rays
+s, e = (0, 8) if rank == 0 else (8, 21)
+Q = build()
+local = ((O.plain_forward(Q, rays[s:e], ts)["out"] - target[s:e]) ** 2).sum(-1).sum()
+local.backward()
+ar = GradientAllReducer([Q[n] for n in names])
+ar.begin(e - s)
+assert ar.finish() == 21
+for n, g in zip(names, full):
+  err = float((Q[n].grad - g).abs().max()); scale = float(g.abs().max())
+  assert err <= 1e-6 + 1e-5 * scale, (n, err, scale)
+dist.barrier(); dist.destroy_process_group(); print("ok")
+'''
+  import socket
+  sk = socket.socket(); sk.bind(("127.0.0.1", 0)); port = sk.getsockname()[1]; sk.close()
+  procs = []
+  for r in range(2):
+    env = dict(os.environ, NF_ROOT=ROOT, NF_PORT=str(port), NF_RANK=str(r))
+    procs.append(subprocess.Popen([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+  for p in procs:
+    out, _ = p.communicate(timeout=300)
+    assert p.returncode == 0 and "ok" in out, out
