@@ -222,6 +222,12 @@ int nf_composite_backward(const nf_model_desc* desc, const void* packed, const f
 int nf_hash_encode_backward(const nf_model_desc* desc, const float* pts, int64_t n, const float* d_feats, float* d_tables,
                             void* stream);
 
+/* One torch.optim.Adam step on one fp32 tensor of n elements, in place (the reference's optimiser, runner.py:448-458: Adam,
+ * eps 1e-7, L2 weight_decay added to the gradient; the cosine learning-rate schedule of runner.py:1289 stays on the host and
+ * arrives as `lr`).  step = 1 for the first update.  All pointers 16-byte aligned device pointers. */
+int nf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                 float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

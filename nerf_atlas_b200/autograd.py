@@ -46,3 +46,39 @@ def hash_encode(engine: RenderEngine, pts: torch.Tensor, tables) -> torch.Tensor
   """feats[N, 4 L] of HashEncoder (reference src/neural_blocks.py:139-193) with gradients to the L embedding tables
   (``tables`` = the live ``emb.weight`` tensors the engine was packed from)."""
   return _HashEncode.apply(engine, pts, *tables)
+
+
+class FusedAdam(torch.optim.Optimizer):
+  """torch.optim.Adam semantics (the reference's optimiser: runner.py:448-458 -- Adam, eps 1e-7, L2 weight_decay) with the
+  update of every tensor done by one hand-written kernel (`nf_adam_step`: 16 B read + 12 B written per element) instead of
+  the ~10 element-wise launches of the eager implementation.  Learning-rate schedulers (runner.py:1289 CosineAnnealingLR) work
+  unchanged: they write ``group["lr"]``."""
+
+  def __init__(self, params, lr: float = 5e-4, betas=(0.9, 0.999), eps: float = 1e-7, weight_decay: float = 0.0):
+    super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+
+  @torch.no_grad()
+  def step(self, closure=None):
+    import ctypes as C
+    from . import _lib
+    loss = None
+    if closure is not None:
+      with torch.enable_grad(): loss = closure()
+    lib = _lib.lib()
+    for group in self.param_groups:
+      b1, b2 = group["betas"]
+      for p in group["params"]:
+        if p.grad is None: continue
+        if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous(): raise RuntimeError("FusedAdam: contiguous fp32 CUDA parameters only")
+        st = self.state[p]
+        if not st:
+          st["step"] = 0; st["exp_avg"] = torch.zeros_like(p); st["exp_avg_sq"] = torch.zeros_like(p)
+        st["step"] += 1
+        g = p.grad.contiguous()
+        with torch.cuda.device(p.device):
+          rc = lib.nf_adam_step(C.c_void_p(p.data_ptr()), C.c_void_p(g.data_ptr()), C.c_void_p(st["exp_avg"].data_ptr()),
+                                C.c_void_p(st["exp_avg_sq"].data_ptr()), p.numel(), float(group["lr"]), float(b1), float(b2),
+                                float(group["eps"]), float(group["weight_decay"]), int(st["step"]),
+                                C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(rc, "nf_adam_step")
+    return loss

@@ -250,4 +250,14 @@ int nf_hash_encode_backward(const nf_model_desc* desc, const float* pts, int64_t
   return e == cudaSuccess ? 0 : cuda_fail(e, "nf_hash_encode_backward");
 }
 
+int nf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                 float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step, void* stream) {
+  if (n < 0 || step < 1) return fail(NF_E_BADARG, "nf_adam_step: n >= 0 and step >= 1");
+  if (n == 0) return 0;
+  if (!param || !grad || !exp_avg || !exp_avg_sq) return fail(NF_E_BADARG, "nf_adam_step: null pointer");
+  if ((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) != 0) return fail(NF_E_BADARG, "nf_adam_step: pointers must be 16-byte aligned");
+  cudaError_t e = nf_launch_adam_step(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nf_adam_step");
+}
+
 }  // extern "C"

@@ -4,6 +4,7 @@
 //                       reference src/nerf.py:22-27,60-80,96-103)
 //   k_hash_encode_bwd : d feats[N, 4L] -> d tables[L][table][4] (scatter-add)  (HashEncoder, reference src/neural_blocks.py:139-193)
 // Both are HBM/L2-bound stage kernels; the fused backward of the MLP chain is not built yet.
+#include <cmath>
 #include "nf_common.cuh"
 #include "nf_kernels.h"
 
@@ -120,6 +121,35 @@ __global__ void k_hash_encode_bwd(const __grid_constant__ NfPlan plan, const flo
   }
 }
 
+// torch.optim.Adam.step for one tensor (the reference's optimiser: runner.py:448-458, eps 1e-7, L2 weight decay added to the
+// gradient): exp_avg.lerp_(g, 1-b1); exp_avg_sq = b2*exp_avg_sq + (1-b2) g*g; p -= (lr / bc1) * exp_avg / (sqrt(exp_avg_sq)/sqrt(bc2) + eps).
+// HBM-bound: 16 B read + 12 B written per element, float4-vectorised.
+__global__ void k_adam_step(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+                            float step_size, float beta1, float beta2, float eps, float wd, float inv_bc2_sqrt) {
+  const long long n4 = n >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4 + (n & 3); i += (long long)gridDim.x * blockDim.x) {
+    if (i < n4) {
+      float4 P = reinterpret_cast<float4*>(p)[i], M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
+      const float4 G = __ldg(reinterpret_cast<const float4*>(g) + i);
+      float* pp = &P.x; float* mm = &M.x; float* vv = &V.x; const float* gg = &G.x;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float gr = gg[k] + wd * pp[k];
+        mm[k] = mm[k] + (1.f - beta1) * (gr - mm[k]);
+        vv[k] = beta2 * vv[k] + (1.f - beta2) * gr * gr;
+        pp[k] = pp[k] - step_size * (mm[k] / (sqrtf(vv[k]) * inv_bc2_sqrt + eps));
+      }
+      reinterpret_cast<float4*>(p)[i] = P; reinterpret_cast<float4*>(m)[i] = M; reinterpret_cast<float4*>(v)[i] = V;
+    } else {
+      const long long j = n4 * 4 + (i - n4);
+      const float gr = g[j] + wd * p[j];
+      m[j] = m[j] + (1.f - beta1) * (gr - m[j]);
+      v[j] = beta2 * v[j] + (1.f - beta2) * gr * gr;
+      p[j] = p[j] - step_size * (m[j] / (sqrtf(v[j]) * inv_bc2_sqrt + eps));
+    }
+  }
+}
+
 int bwd_num_sms() {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -146,5 +176,15 @@ cudaError_t nf_launch_hash_encode_bwd(const NfPlan& plan, const float* pts, int6
   const long long want = (total + 255) / 256;
   const int grid = (int)(want < (long long)bwd_num_sms() * 16 ? want : (long long)bwd_num_sms() * 16);
   k_hash_encode_bwd<<<grid, 256, 0, st>>>(plan, pts, n, d_feats, d_tables);
+  return cudaGetLastError();
+}
+
+cudaError_t nf_launch_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                                float wd, int step, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+  const long long want = ((n >> 2) + 3 + 255) / 256;
+  const int grid = (int)(want < (long long)bwd_num_sms() * 16 ? want : (long long)bwd_num_sms() * 16);
+  k_adam_step<<<grid, 256, 0, st>>>(p, g, m, v, n, (float)(lr / bc1), beta1, beta2, eps, wd, (float)(1.0 / sqrt(bc2)));
   return cudaGetLastError();
 }

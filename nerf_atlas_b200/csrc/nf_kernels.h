@@ -35,3 +35,5 @@ cudaError_t nf_launch_composite_bwd(const NfPlan& plan, const void* packed, cons
                                     int64_t n_rays, const float* ts, int T, int64_t ts_stride, const float* d_rgb, float* d_sigma,
                                     float* d_feats, cudaStream_t st);
 cudaError_t nf_launch_hash_encode_bwd(const NfPlan& plan, const float* pts, int64_t n, const float* d_feats, float* d_tables, cudaStream_t st);
+cudaError_t nf_launch_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                                float wd, int step, cudaStream_t st);

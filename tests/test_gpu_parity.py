@@ -629,3 +629,23 @@ def test_gradients_flow_end_to_end_through_native_stage_ops(P):
     eng.pack(eng._params[:24] + live, force=True)
     loss = loss_fn(); loss.backward()
   assert float(loss.detach()) < first, (first, float(loss.detach()))
+
+
+def test_fused_adam_matches_torch_adam():
+  """nf_adam_step vs torch.optim.Adam with the reference's hyper-parameters (eps 1e-7, weight decay) over several steps, odd sizes."""
+  import nerf_atlas_b200 as N
+  g = torch.Generator().manual_seed(0)
+  shapes = [(256, 294), (65, 256), (3,), (1, 1, 7), (65536, 4)]
+  pa = [torch.randn(*s, generator=g).to(DEV).requires_grad_(True) for s in shapes]
+  pb = [p.detach().clone().requires_grad_(True) for p in pa]
+  oa = N.autograd.FusedAdam(pa, lr=5e-4, eps=1e-7, weight_decay=1e-5)
+  ob = torch.optim.Adam(pb, lr=5e-4, eps=1e-7, weight_decay=1e-5)
+  sched_a = torch.optim.lr_scheduler.CosineAnnealingLR(oa, T_max=10, eta_min=5e-5)
+  sched_b = torch.optim.lr_scheduler.CosineAnnealingLR(ob, T_max=10, eta_min=5e-5)
+  for it in range(6):
+    for x, y in zip(pa, pb):
+      gr = torch.randn(x.shape, generator=g).to(DEV) * (0.1 + it)
+      x.grad = gr.clone(); y.grad = gr.clone()
+    oa.step(); ob.step(); sched_a.step(); sched_b.step()
+  for x, y in zip(pa, pb):
+    assert float((x.detach() - y.detach()).abs().max()) <= 1e-6 * max(float(y.detach().abs().max()), 1.0), x.shape
