@@ -156,3 +156,28 @@ dist.barrier(); dist.destroy_process_group(); print("ok")
   for p in procs:
     out, _ = p.communicate(timeout=300)
     assert p.returncode == 0 and "ok" in out, out
+
+
+def test_header_enums_match_the_python_binding():
+  """ABI drift guard: every enum value the ctypes layer uses equals the header's."""
+  src = open(os.path.join(ROOT, "include", "nerf_b200.h")).read()
+  src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+  vals = {}
+  for body in re.findall(r"enum\s+\w+\s*\{(.*?)\}", src, flags=re.S):
+    for name, v in re.findall(r"(NF_[A-Z0-9_]+)\s*=\s*(-?\d+)", body): vals[name] = int(v)
+  expect = {
+    "NF_ACT_NONE": _lib.ACT["none"], "NF_ACT_LEAKY": _lib.ACT["leaky_relu"], "NF_ACT_SIN": _lib.ACT["sin"], "NF_ACT_RELU": _lib.ACT["relu"],
+    "NF_ENC_NONE": _lib.ENC["none"], "NF_ENC_HASH": _lib.ENC["hash"], "NF_ENC_FOURIER": _lib.ENC["fourier"],
+    "NF_DENS_SOFTPLUS_M1": _lib.DENSITY["softplus"], "NF_DENS_RELU": _lib.DENSITY["relu"], "NF_DENS_LAPLACE": _lib.DENSITY["laplace"],
+    "NF_BG_BLACK": _lib.BG["black"], "NF_BG_WHITE": _lib.BG["white"],
+    "NF_KIND_PLAIN": _lib.KIND["plain"], "NF_KIND_TINY": _lib.KIND["tiny"], "NF_KIND_DYN": _lib.KIND["dyn"],
+    "NF_PREC_FP32": _lib.PRECISION["fp32"], "NF_PREC_FP16_TC": _lib.PRECISION["fp16"],
+    "NF_MIP_NONE": _lib.MIP[None], "NF_MIP_CYLINDER": _lib.MIP["cylinder"], "NF_MIP_CONE": _lib.MIP["cone"], "NF_MIP_CYLINDER_REF": _lib.MIP["cylinder_ref"],
+    "NF_REFL_VIEW": _lib.REFL["view"], "NF_REFL_POSITIONAL": _lib.REFL["pos"],
+  }
+  for k, v in expect.items(): assert vals.get(k) == v, (k, vals.get(k), v)
+  feat = {"NORMAL": "normal", "THIN": "thin", "TANH": "tanh", "CYCLIC": "cyclic", "UPSHIFTED": "upshifted", "FAT": "fat", "LEAKY_RELU": "leaky_relu",
+          "RELU": "relu", "SIN": "sin", "UPSHIFTED_SOFTPLUS": "upshifted_softplus", "UPSHIFTED_RELU": "upshifted_relu"}
+  for k, v in feat.items(): assert vals.get("NF_FEAT_" + k) == _lib.FEAT[v], k
+  m = re.search(r"#define\s+NF_ABI_VERSION\s+(\d+)", src)
+  assert m and int(m.group(1)) == _lib.ABI_VERSION
