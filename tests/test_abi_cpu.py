@@ -229,3 +229,18 @@ def test_from_reference_adopts_live_reference_models():
     assert l.nf_param_count(C.byref(d)) == len(f._param_list()) and d.spline_points == spline
   # what is not built says so
   with pytest.raises(NotImplementedError): N.FusedPlainNeRF.from_reference(nerf.PlainNeRF(mip=utils.ConicGaussian(), steps=4))
+
+
+def test_integration_md_struct_matches_the_binding():
+  """The ctypes stub a maintainer would copy from INTEGRATION.md declares nf_model_desc with the same fields, in the same order,
+  as the binding the tests run through; and the header declares them in that order too."""
+  src = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+  m = re.search(r"class ModelDesc\(C.Structure\):.*?_fields_ = \[(.*?)\]\n\n", src, flags=re.S)
+  assert m, "ModelDesc stub not found in INTEGRATION.md"
+  real = [f[0] for f in _lib.ModelDesc._fields_]
+  assert re.findall(r'\("(\w+)"', m.group(1)) == real
+  hdr = open(os.path.join(ROOT, "include", "nerf_b200.h")).read()
+  body = re.search(r"typedef struct nf_model_desc \{(.*?)\} nf_model_desc;", hdr, flags=re.S).group(1)
+  body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+  fields = re.findall(r"(?:int32_t|uint32_t|float|nf_mlp_desc)\s+(\w+)", body)
+  assert fields == real, (fields, real)
