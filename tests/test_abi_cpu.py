@@ -268,3 +268,35 @@ def test_modules_pickle_without_the_library_handle(tmp_path):
     r.engine()                                        # and the engine comes back lazily
   assert mods[1].mip == "cylinder" and mods[1].refl_kind == "pos" and mods[1].first.init.weight.shape == (256, 38 + 96)
   assert mods[1].refl.mlp.init.weight.shape == (256, 38 + 96 + 64)
+
+
+def test_sample_stream_tiling_arithmetic():
+  """The tile <-> (ray, t) arithmetic of the staggered pipeline (NfStreamMap in csrc/nf_tc3.cu), restated: for every T a unit is
+  `rpu` whole rays = `tpr` whole 128-row tiles, every (ray, t) of a unit appears exactly once, rays are packed across tile
+  boundaries only when T % 32 == 0 (warp-aligned, so that a ray's rounding is placement independent), and at most one segment per
+  tile continues from the previous tile / stays unfinished."""
+  from math import gcd
+  ROWS = 128
+  def smap(T):
+    Tp = T
+    if T % 32 != 0 or T // gcd(T, ROWS) > 64: Tp = ROWS // (ROWS // T) if T <= ROWS else (T + ROWS - 1) // ROWS * ROWS
+    g = gcd(Tp, ROWS)
+    return Tp, Tp // g, ROWS // g
+  for T in (1, 7, 16, 32, 48, 64, 96, 100, 128, 160, 192, 224, 256, 300, 384, 1000, 2048):
+    Tp, tpr, rpu = smap(T)
+    assert rpu * Tp == tpr * ROWS and Tp >= T
+    seen = set()
+    for sub in range(tpr):
+      cont = unfinished = 0
+      segs = set()
+      for r in range(ROWS):
+        q = sub * ROWS + r; rl, t = divmod(q, Tp)
+        if t < T: assert (rl, t) not in seen; seen.add((rl, t))
+        segs.add(rl)
+      for rl in segs:
+        cont += rl * Tp < sub * ROWS
+        unfinished += (rl + 1) * Tp > (sub + 1) * ROWS
+      assert cont <= 1 and unfinished <= 1
+    assert seen == {(rl, t) for rl in range(rpu) for t in range(T)}
+    if Tp == T and T > 32: assert T % 32 == 0
+  assert smap(192) == (192, 3, 2) and smap(160) == (160, 5, 4) and smap(100) == (128, 1, 1) and smap(64) == (64, 1, 2) and smap(256) == (256, 2, 1)
