@@ -453,6 +453,7 @@ class FusedNeRF(nn.Module):
   def __getstate__(self):
     st = self.__dict__.copy(); st["_engine"] = None; st["_engine_key"] = None
     st["alpha"] = st["weights"] = st["ts"] = None
+    if "scale_post_act" in st: st["scale_post_act"] = None
     return st
 
   # ---- implemented by subclasses ----
@@ -590,6 +591,11 @@ class FusedVolSDF(FusedNeRF):
     if getattr(ref, "secondary", None) is not None: raise NotImplementedError("VolSDF secondary lighting")
     self.scale, self.sdf = ref.scale, ref.sdf
     return self
+
+  def forward(self, rays: torch.Tensor) -> torch.Tensor:
+    out = super().forward(rays)
+    self.scale_post_act = self.scale          # scale_act is the identity (nerf.py:884,1000-1001); read by runner.py:707
+    return out
 
   def _sdf_net(self):
     u = self.sdf.underlying
