@@ -594,7 +594,9 @@ class FusedVolSDF(FusedNeRF):
 
   def forward(self, rays: torch.Tensor) -> torch.Tensor:
     out = super().forward(rays)
-    self.scale_post_act = self.scale          # scale_act is the identity (nerf.py:884,1000-1001); read by runner.py:707
+    # scale_act is the identity (nerf.py:884,1000-1001); read by runner.py:707.  Bypass nn.Module.__setattr__: assigning a
+    # Parameter the normal way would register it a second time and add a key to the state_dict.
+    object.__setattr__(self, "scale_post_act", self.scale)
     return out
 
   def _sdf_net(self):
