@@ -129,6 +129,11 @@ typedef struct nf_mip_args {
 int nf_version(void);
 const char* nf_last_error(void);
 
+/* NULL if nf_render_forward(..., NF_PREC_FP16_TC) can run `desc` on the tcgen05 pipeline, else the reason (a static string, or
+ * nf_last_error() text for an invalid descriptor).  Host-only: no CUDA call, usable without a GPU.  There is no silent
+ * fallback to NF_PREC_FP32: an unsupported descriptor makes nf_render_forward fail with NF_E_UNSUPPORTED. */
+const char* nf_tensor_pipeline_support(const nf_model_desc* desc);
+
 /* ---- parameters -------------------------------------------------------- */
 /* Number of parameter pointers nf_pack_weights expects for `desc`, in this order:
  *   density MLP: init.weight, init.bias, layers[0].weight, layers[0].bias, ..., out.weight, out.bias

@@ -39,6 +39,7 @@ class MipArgs(C.Structure):
 EXPORTS = {
   "nf_version": (C.c_int, []),
   "nf_last_error": (C.c_char_p, []),
+  "nf_tensor_pipeline_support": (C.c_char_p, [C.POINTER(ModelDesc)]),
   "nf_param_count": (C.c_int, [C.POINTER(ModelDesc)]),
   "nf_packed_bytes": (C.c_int64, [C.POINTER(ModelDesc)]),
   "nf_pack_weights": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),

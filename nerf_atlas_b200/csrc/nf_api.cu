@@ -31,6 +31,12 @@ extern "C" {
 int nf_version(void) { return NF_ABI_VERSION; }
 const char* nf_last_error(void) { return g_err.c_str(); }
 
+const char* nf_tensor_pipeline_support(const nf_model_desc* desc) {
+  NfPlan p;
+  if (plan_of(desc, &p)) return g_err.c_str();
+  return nf_tc3_unsupported(p);          // the staggered pipeline is the superset of what the older tensor pipelines run
+}
+
 int nf_param_count(const nf_model_desc* desc) {
   NfPlan p; if (int rc = plan_of(desc, &p)) return rc;
   int n = 0;

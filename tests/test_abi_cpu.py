@@ -300,3 +300,22 @@ def test_sample_stream_tiling_arithmetic():
     assert seen == {(rl, t) for rl in range(rpu) for t in range(T)}
     if Tp == T and T > 32: assert T % 32 == 0
   assert smap(192) == (192, 3, 2) and smap(160) == (160, 5, 4) and smap(100) == (128, 1, 1) and smap(64) == (64, 1, 2) and smap(256) == (256, 2, 1)
+
+
+def test_which_models_the_tensor_pipeline_takes():
+  """nf_tensor_pipeline_support (host-only): every model kind of the path runs on tcgen05; what does not says why."""
+  l = _lib.lib()
+  ok = lambda d: l.nf_tensor_pipeline_support(C.byref(d))
+  for d in (N.describe_plain(), N.describe_tiny(), N.describe_volsdf("siren"), N.describe_volsdf("mlp"), N.describe_dyn(), N.describe_dyn(spline=5),
+            N.describe_dyn(spline=8), N.describe_plain(mip="cylinder"), N.describe_plain(mip="cone"), N.describe_plain(mip="cylinder_ref"),
+            N.describe_plain(refl_kind="pos"), N.describe_plain(mip="cylinder", refl_kind="pos"), N.describe_plain(32)):
+    assert ok(d) is None, ok(d)
+  assert b"wider than 80" in ok(N.describe_plain(128))       # intermediate_size 128: View x0 is 133 wide (fp32 pipeline only for now)
+  bad = N.describe_plain(); bad.intermediate = 40; bad.density.out_dims = 41; bad.refl.in_dims = 45
+  assert b"multiple of 16" in ok(bad)
+  bad = N.describe_plain(hash_levels=7)
+  assert b"odd number of hash levels" in ok(bad)
+  dm = N.describe_dyn(); dm.mip = _lib.MIP["cylinder"]; dm.density.in_dims += 96; dm.refl.in_dims += 96
+  assert b"PlainNeRF only" in ok(dm)
+  bad = N.describe_plain(); bad.density.hidden = 128
+  assert b"hidden_size" in ok(bad)            # invalid descriptor: the plan builder's message
