@@ -190,3 +190,28 @@ def test_fp16_operand_emulation_every_model_kind_within_stated_tolerance(golden_
     d = np.abs(out.numpy() - fx["out"])
     psnr = -10 * np.log10(max(np.mean(d.astype(np.float64) ** 2), 1e-30))
     assert d.max() < 1e-3 and psnr > 70, (name, d.max(), psnr)
+
+
+def test_oracle_autograd_matches_the_reference_backward(golden_dir):
+  """Gradients (SURVEY f-1): torch autograd through the oracle's restatement == loss.backward() through the reference's own
+  modules (golden `plain_t16_grads`, runner.py:600-602,820).  This pins the parity target of the fused backward before it exists."""
+  fx = load(golden_dir, "plain_t16_grads")
+  P = O.make_plain_params(int(fx["seed"]), 64, 20.0)
+  names = [k[len("grad."):] for k in fx if k.startswith("grad.") and not k.startswith("grad.emb")]
+  for n in names + ["first.enc.embs.0.weight", "first.enc.embs.7.weight"]: P[n] = P[n].clone().requires_grad_(True)
+  rays = O.make_rays(int(fx["B"]), int(fx["H"]), int(fx["W"]), 800, int(fx["seed"]), int(fx["top"]), int(fx["left"]))
+  ts = O.compute_ts(float(fx["near"]), float(fx["far"]), int(fx["T"]))
+  out = O.plain_forward(P, rays, ts, sigmoid=str(fx["sigmoid"]), bg=str(fx["bg"]))["out"]
+  assert np.array_equal(out.detach().numpy(), fx["out"])
+  loss = torch.nn.functional.mse_loss(out, torch.from_numpy(fx["target"]))
+  assert abs(float(loss) - float(fx["loss"])) <= 1e-7
+  loss.backward()
+  for n in names:
+    g = P[n].grad.numpy(); ref = fx["grad." + n]
+    if g.ndim == 2 and g.shape[0] == 256: g = g[::16]
+    assert np.abs(g - ref).max() <= 1e-6 * max(np.abs(ref).max(), 1e-3), n
+  for lvl in (0, 7):
+    g = P[f"first.enc.embs.{lvl}.weight"].grad
+    rows = torch.nonzero(g.abs().sum(1)).squeeze(1).numpy()
+    assert np.array_equal(rows, fx[f"grad.emb{lvl}.rows"]), lvl
+    assert np.abs(g[rows].numpy() - fx[f"grad.emb{lvl}.vals"]).max() <= 1e-6 * max(np.abs(fx[f"grad.emb{lvl}.vals"]).max(), 1e-3)
