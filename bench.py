@@ -68,9 +68,10 @@ def cpu_port_rays_per_s(steps, warmup, tile=CPU_TILE):
     for i in range(warmup + steps):
       rays = O.make_rays(1, tile, tile, size=SIZE, seed=i, crop_top=368, crop_left=368)
       t0 = time.perf_counter()
-      O.plain_forward(P, rays, ts)
+      out = O.plain_forward(P, rays, ts)
       if i >= warmup: times.append(time.perf_counter() - t0)
   dt = sum(times) / len(times)
+  cpu_port_rays_per_s.last = (rays, out["out"])          # the last crop and its fp32 CPU render: reused as the live parity check
   return tile * tile / dt, cores, dt, f"{steps} steps x ({tile}x{tile} crop of the 800x800 view) x {T} samples/ray, fp32, torch CPU, {cores} threads"
 
 
@@ -210,6 +211,17 @@ def run_ours(args):
         line["torch_eager_gpu"] = {"error": str(ex)[:200]}
     if cpu_v is not None:
       line["cpu_baseline"] = {"value": cpu_v, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample}
+      try:
+        # the metric's "PSNR vs reference render": the same crop the CPU port just rendered in fp32, through the fused pipeline
+        import math
+        c_rays, c_ref = cpu_port_rays_per_s.last
+        got = eng.render(c_rays.reshape(-1, 6).contiguous().to(dev), ts, None, want_weights=False)[0].reshape(c_ref.shape).cpu()
+        err = (got - c_ref).abs()
+        mse = float(((got - c_ref).double() ** 2).mean())
+        line["parity"] = {"max_abs_err_vs_cpu_fp32": float(err.max()), "psnr_db": (-10 * math.log10(mse)) if mse > 0 else float("inf"),
+                          "rays": int(c_rays.reshape(-1, 6).shape[0]), "tolerance": "max|d rgb| <= 1e-3, PSNR >= 70 dB"}
+      except Exception as ex:
+        line["parity"] = {"error": str(ex)[:200]}
     print(json.dumps(line), flush=True)
   if world > 1: dist.destroy_process_group()
 
