@@ -467,6 +467,12 @@ class FusedNeRF(nn.Module):
       self._engine, self._engine_key = RenderEngine(self._describe(), self.precision), key
     return self._engine
 
+  def render_views(self, cam_to_world: torch.Tensor, focal: float, size: int, crop=None, reference_device: str = "cpu") -> torch.Tensor:
+    """runner.render without the host-side pixel grid (reference runner.py:490-509): cam_to_world[B,3,4] (CUDA), focal, image size
+    and an optional crop (top, left, H, W) -> rgb[B,H,W,3]; the rays come from `nf_generate_rays` (bit-exact with
+    NeRFCamera.sample_positions), so a frame needs 48 bytes of input per view instead of 24 bytes per ray."""
+    return self(RenderEngine.generate_rays(cam_to_world, focal, size, crop, reference_device))
+
   def forward(self, rays: torch.Tensor) -> torch.Tensor:
     if not rays.is_cuda: raise RuntimeError("FusedNeRF.forward needs CUDA rays: the fused path has no CPU fallback")
     if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:

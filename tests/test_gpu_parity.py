@@ -511,6 +511,14 @@ def test_generate_rays_bit_exact_vs_reference_camera():
     assert got.shape == ref.shape and torch.equal(got.cpu(), ref), (size, B, crop)
   alt = N.RenderEngine.generate_rays(c2w.to(DEV), focal, size, crop, reference_device="cuda")     # torch-CUDA scalar division
   assert float((alt.cpu() - ref).abs().max()) <= 2e-7
+  # module level: render straight from the cameras == render from the reference camera's rays
+  m = N.FusedPlainNeRF(steps=32, t_near=2, t_far=6, intermediate_size=64, sigmoid_kind="upshifted", precision="fp16")
+  m.load_state_dict(O.make_plain_params(3, 64, 20.0), strict=True); m = m.to(DEV).eval()
+  c2w, focal = O.make_cameras(2, 64, seed=5)
+  with torch.no_grad():
+    a = m.render_views(c2w.to(DEV), focal, 64, (10, 20, 8, 12))
+    b = m(O.make_rays(2, 8, 12, size=64, seed=5, crop_top=10, crop_left=20).to(DEV))
+  assert a.shape == (2, 8, 12, 3) and torch.equal(a, b)
 
 
 # ---------------------------------------------------------------- Positional RGB head (SURVEY f-3)
