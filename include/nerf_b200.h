@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NF_ABI_VERSION 4
+#define NF_ABI_VERSION 5
 
 /* error codes (negative; positive values are cudaError_t) */
 #define NF_E_BADARG    (-1)
@@ -45,7 +45,8 @@ enum nf_density_act {
 /* feature activation = the sigmoid family of reference src/utils.py:484-518 */
 enum nf_feat_act { NF_FEAT_NORMAL = 0, NF_FEAT_THIN = 1, NF_FEAT_TANH = 2, NF_FEAT_CYCLIC = 3, NF_FEAT_UPSHIFTED = 4,
                    NF_FEAT_FAT = 5, NF_FEAT_LEAKY_RELU = 6, NF_FEAT_RELU = 7, NF_FEAT_SIN = 8,
-                   NF_FEAT_UPSHIFTED_SOFTPLUS = 9, NF_FEAT_UPSHIFTED_RELU = 10 };
+                   NF_FEAT_UPSHIFTED_SOFTPLUS = 9, NF_FEAT_UPSHIFTED_RELU = 10,
+                   NF_FEAT_SOFTMAX = 11 /* nn.Softmax(dim=-1) over the three colour channels (utils.py:507) */ };
 /* background (reference src/nerf.py:96-109) */
 enum nf_bg { NF_BG_BLACK = 0, NF_BG_WHITE = 1 };
 /* model family */
@@ -128,6 +129,13 @@ typedef struct nf_mip_args {
 /* ---- library ----------------------------------------------------------- */
 int nf_version(void);
 const char* nf_last_error(void);
+/* How the library was built: the default build reads NO environment variable and contains only the product kernels;
+ * NF_BUILD_EXPERIMENTS builds additionally compile the superseded pipelines and the NF_TC_* timing switches (A/B timing,
+ * profiles/perf_variants.py) -- never ship one. */
+#define NF_BUILD_EXPERIMENTS 1
+#define NF_BUILD_STATS 2
+#define NF_BUILD_TRACE 4
+int nf_build_flags(void);
 
 /* NULL if nf_render_forward(..., NF_PREC_FP16_TC) can run `desc` on the tcgen05 pipeline, else the reason (a static string, or
  * nf_last_error() text for an invalid descriptor).  Host-only: no CUDA call, usable without a GPU.  There is no silent

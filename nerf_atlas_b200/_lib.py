@@ -7,13 +7,13 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, os.environ.get("NF_LIB", "libnerf_b200.so"))
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 # enums of include/nerf_b200.h
 ACT = {"none": 0, "leaky_relu": 1, "sin": 2, "relu": 3}
 ENC = {"none": 0, "hash": 1, "fourier": 2}
 DENSITY = {"softplus": 0, "relu": 1, "laplace": 2}
 FEAT = {"normal": 0, "thin": 1, "tanh": 2, "cyclic": 3, "upshifted": 4, "fat": 5, "leaky_relu": 6, "relu": 7,
-        "sin": 8, "upshifted_softplus": 9, "upshifted_relu": 10}
+        "sin": 8, "upshifted_softplus": 9, "upshifted_relu": 10, "softmax": 11}
 BG = {"black": 0, "white": 1}
 KIND = {"plain": 0, "tiny": 1, "dyn": 2}
 PRECISION = {"fp32": 0, "fp16": 1}
@@ -39,6 +39,7 @@ class MipArgs(C.Structure):
 EXPORTS = {
   "nf_version": (C.c_int, []),
   "nf_last_error": (C.c_char_p, []),
+  "nf_build_flags": (C.c_int, []),
   "nf_tensor_pipeline_support": (C.c_char_p, [C.POINTER(ModelDesc)]),
   "nf_param_count": (C.c_int, [C.POINTER(ModelDesc)]),
   "nf_packed_bytes": (C.c_int64, [C.POINTER(ModelDesc)]),
@@ -77,6 +78,10 @@ def lib():
     if l.nf_version() != ABI_VERSION: raise RuntimeError("libnerf_b200.so: ABI version mismatch")
     _lib = l
   return _lib
+
+def has_experiments() -> bool:
+  """True for an NF_EXPERIMENTS build (the NF_TC_* environment switches and the superseded pipelines exist)."""
+  return bool(lib().nf_build_flags() & 1)
 
 def check(rc: int, what: str):
   if rc != 0:

@@ -81,4 +81,7 @@ class FusedAdam(torch.optim.Optimizer):
                                 float(group["eps"]), float(group["weight_decay"]), int(st["step"]),
                                 C.c_void_p(torch.cuda.current_stream().cuda_stream))
         _lib.check(rc, "nf_adam_step")
+        # the kernel wrote through the raw pointer: tell autograd (saved-tensor checks) and RenderEngine.pack (whose cache key
+        # is (data_ptr, _version)) that the parameter changed, exactly as an in-place torch op would
+        torch.autograd.graph.increment_version(p)
     return loss

@@ -8,21 +8,22 @@ import os, subprocess, sys, hashlib
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["nf_api.cu", "nf_fp32.cu", "nf_tc.cu", "nf_tc2.cu", "nf_tc3.cu", "nf_bwd.cu"]
+EXPERIMENTS = bool(os.environ.get("NF_EXPERIMENTS"))   # A/B-timing build: superseded pipelines + NF_TC_* environment switches (libnerf_b200_exp.so)
+SOURCES = ["nf_api.cu", "nf_fp32.cu", "nf_tc.cu", "nf_tc3.cu", "nf_bwd.cu"] + (["nf_tc2.cu"] if EXPERIMENTS else [])
 HEADERS = ["nf_common.cuh", "nf_kernels.h", "nf_tc_ptx.cuh", os.path.join("..", "..", "include", "nerf_b200.h")]
 TRACE = bool(os.environ.get("NF_TC_TRACE"))     # debug build: clock64 timeline of one tile (profiles/)
 STATS = bool(os.environ.get("NF_TC_STATS"))     # debug build: time-in-state counters of the staggered pipeline (nf_tc3.cu)
 DEFS = os.environ.get("NF_BUILD_DEFS", "")      # experiments: extra -D flags, e.g. NF_BUILD_DEFS="NF_SIN_POLY_PAIRS=2" NF_BUILD_TAG=poly2
-TAG = os.environ.get("NF_BUILD_TAG", "")
+TAG = os.environ.get("NF_BUILD_TAG", "") or ("exp" if EXPERIMENTS else "")
 LIB = os.path.join(HERE, "libnerf_b200_trace.so" if TRACE else "libnerf_b200_stats.so" if STATS else f"libnerf_b200_{TAG}.so" if TAG else "libnerf_b200.so")
 STAMP = LIB + ".stamp"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC", "--shared", "-Xptxas", "-v"] + ([f"-DNF_TC_TRACE={os.environ.get('NF_TC_TRACE')}"] if TRACE else []) + (["-DNF_TC_STATS=1"] if STATS else []) + [f"-D{d}" for d in DEFS.split()]
+         "-Xcompiler", "-fPIC", "--shared", "-Xptxas", "-v"] + ([f"-DNF_TC_TRACE={os.environ.get('NF_TC_TRACE')}"] if TRACE else []) + (["-DNF_TC_STATS=1"] if STATS else []) + (["-DNF_EXPERIMENTS=1"] if EXPERIMENTS else []) + [f"-D{d}" for d in DEFS.split()]
 
 def _digest() -> str:
   h = hashlib.sha256()
-  for f in SOURCES + HEADERS:
+  for f in sorted(set(SOURCES + ["nf_tc2.cu"])) + HEADERS:
     with open(os.path.join(CSRC, f), "rb") as fh: h.update(fh.read())
   h.update(" ".join(FLAGS).encode())
   return h.hexdigest()

@@ -29,6 +29,19 @@ int check_ts(int32_t T, int64_t ts_stride) {
 extern "C" {
 
 int nf_version(void) { return NF_ABI_VERSION; }
+int nf_build_flags(void) {
+  int f = 0;
+#ifdef NF_EXPERIMENTS
+  f |= NF_BUILD_EXPERIMENTS;
+#endif
+#ifdef NF_TC_STATS
+  f |= NF_BUILD_STATS;
+#endif
+#ifdef NF_TC_TRACE
+  f |= NF_BUILD_TRACE;
+#endif
+  return f;
+}
 const char* nf_last_error(void) { return g_err.c_str(); }
 
 const char* nf_tensor_pipeline_support(const nf_model_desc* desc) {
@@ -136,21 +149,27 @@ int nf_render_forward(const nf_model_desc* desc, const void* packed, const float
   if (precision == NF_PREC_FP32)
     e = nf_launch_render_fp32(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, ray_time, mip, rgb_out, alpha_out, weights_out, (cudaStream_t)stream);
   else if (precision == NF_PREC_FP16_TC) {
-    // NF_TC_PIPE selects the tensor pipeline: 3 (default) = staggered paired pipeline (nf_tc3.cu), 2 = lockstep paired
-    // pipeline (nf_tc2.cu), 1 = single-CTA pipeline (nf_tc.cu); the older ones are kept for A/B timing.  NF_TC_PAIRED=0 == 1.
+    // The staggered paired pipeline (nf_tc3.cu) is the product path; the single-CTA pipeline (nf_tc.cu) takes the few
+    // descriptors it cannot (odd hash levels, intermediate % 16 != 0).  Only NF_EXPERIMENTS builds (A/B timing,
+    // profiles/perf_variants.py) read NF_TC_PIPE: 3 = staggered, 2 = lockstep paired (nf_tc2.cu), 1 = single CTA.
     int pipe = 3;
+#ifdef NF_EXPERIMENTS
     if (const char* env = getenv("NF_TC_PIPE")) pipe = atoi(env);
     if (const char* env = getenv("NF_TC_PAIRED")) if (env[0] == '0') pipe = 1;
+#endif
     if (p.kind == NF_KIND_DYN || p.mip != NF_MIP_NONE || p.refl_kind != NF_REFL_VIEW || p.enc == NF_ENC_FOURIER) {
       // only the staggered pipeline runs the three-MLP chain and the wide-x0 (single-tile) mode
       if (const char* why = nf_tc3_unsupported(p)) return fail(NF_E_UNSUPPORTED, why);
       pipe = 3;
     }
-    if (pipe == 3 && nf_tc3_unsupported(p)) pipe = 2;
-    if (pipe == 2 && nf_tc2_unsupported(p)) pipe = 1;
+    if (pipe == 3 && nf_tc3_unsupported(p)) pipe = 1;
     cudaStream_t st = (cudaStream_t)stream;
+#ifdef NF_EXPERIMENTS
+    if (pipe == 2 && nf_tc2_unsupported(p)) pipe = 1;
+    if (pipe == 2) e = nf_launch_render_tc2(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, rgb_out, alpha_out, weights_out, st);
+    else
+#endif
     e = pipe == 3 ? nf_launch_render_tc3(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, ray_time, mip, rgb_out, alpha_out, weights_out, st)
-      : pipe == 2 ? nf_launch_render_tc2(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, rgb_out, alpha_out, weights_out, st)
                   : nf_launch_render_tc(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, rgb_out, alpha_out, weights_out, st);
   }
   else return fail(NF_E_BADARG, "unknown precision");

@@ -86,6 +86,8 @@ static inline int nf_build_plan(const nf_model_desc* d, NfPlan* p, const char** 
     p->fourier_freqs = d->fourier_freqs;
   } else if (d->enc != NF_ENC_NONE) { *why = "unsupported encoder"; return NF_E_UNSUPPORTED; }
   if (d->density_act < 0 || d->density_act > NF_DENS_LAPLACE) { *why = "unknown density activation"; return NF_E_BADARG; }
+  if (d->feat_act < 0 || d->feat_act > NF_FEAT_SOFTMAX) { *why = "unknown feature activation (enum nf_feat_act)"; return NF_E_BADARG; }
+  if (d->bg < 0 || d->bg > NF_BG_WHITE) { *why = "unknown background (enum nf_bg)"; return NF_E_BADARG; }
   int64_t off = 0;
   auto take = [&](int64_t bytes) { int64_t o = off; off += (bytes + 1023) / 1024 * 1024; return o; };
   if (d->enc == NF_ENC_HASH) p->hash_off = take((int64_t)d->hash_levels * d->hash_table_size * 4 * sizeof(float));
@@ -208,8 +210,20 @@ __device__ __forceinline__ float nf_feat_act_fn(float v, int kind) {
     case NF_FEAT_SIN:       return sinf(v);
     case NF_FEAT_UPSHIFTED_SOFTPLUS: return nf_softplus(v) + 1e-2f;
     case NF_FEAT_UPSHIFTED_RELU:     return fmaxf(v, 0.f) + 1e-2f;
-    default: return v;
+    default: return v;      // unreachable: nf_build_plan rejects unknown kinds; NF_FEAT_SOFTMAX goes through nf_feat_act3
   }
+}
+// the three colour channels of one sample; nn.Softmax(dim=-1) (reference src/utils.py:507) couples them: exp(v - max) / sum in
+// torch's order (max-subtracted exponentials, one division per channel)
+__device__ __forceinline__ void nf_feat_act3(float& r, float& g, float& b, int kind) {
+  if (kind == NF_FEAT_SOFTMAX) {
+    const float m = fmaxf(r, fmaxf(g, b));
+    const float er = expf(r - m), eg = expf(g - m), eb = expf(b - m);
+    const float s = er + eg + eb;
+    r = er / s; g = eg / s; b = eb / s;
+    return;
+  }
+  r = nf_feat_act_fn(r, kind); g = nf_feat_act_fn(g, kind); b = nf_feat_act_fn(b, kind);
 }
 // raw density -> sigma, reference src/nerf.py:64-65
 // `beta` is only used by NF_DENS_LAPLACE (VolSDF): sigma = relu(Psi_beta(-sdf) / beta), reference src/nerf.py:1000-1003,

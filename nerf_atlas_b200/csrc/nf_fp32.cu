@@ -270,9 +270,9 @@ k_render_fp32(const __grid_constant__ NfPlan plan, const RenderArgs a) {
             const float al = nf_alpha(sr, nf_delta(tsr, t, a.T, nrm), plan.density_act, beta);
             const float w = al * trans;
             trans *= (1.f - al) + 1e-10f;
-            cr += w * nf_feat_act_fn(rgb_raw[0 * ROWS + row], plan.feat_act);
-            cg += w * nf_feat_act_fn(rgb_raw[1 * ROWS + row], plan.feat_act);
-            cb += w * nf_feat_act_fn(rgb_raw[2 * ROWS + row], plan.feat_act);
+            float fr = rgb_raw[0 * ROWS + row], fg = rgb_raw[1 * ROWS + row], fb = rgb_raw[2 * ROWS + row];
+            nf_feat_act3(fr, fg, fb, plan.feat_act);
+            cr += w * fr; cg += w * fg; cb += w * fb;
             if (t < a.T - 1) wsum += w;
             if (a.alpha_out) a.alpha_out[ray * a.T + t] = al;
             if (a.weights_out) a.weights_out[ray * a.T + t] = w;

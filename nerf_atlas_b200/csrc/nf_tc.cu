@@ -507,7 +507,7 @@ k_render_tc(const __grid_constant__ NfPlan plan, const __grid_constant__ TcProg 
                 } else {
                   cr = __uint_as_float(v[0]) + bias[0]; cg = __uint_as_float(v[1]) + bias[1]; cb = __uint_as_float(v[2]) + bias[2];
                 }
-                cr = nf_feat_act_fn(cr, plan.feat_act); cg = nf_feat_act_fn(cg, plan.feat_act); cb = nf_feat_act_fn(cb, plan.feat_act);
+                nf_feat_act3(cr, cg, cb, plan.feat_act);
                 composite_tile(s, plan, a, map, sub, row, lane, q, cr, cg, cb);
               }
             }
@@ -608,7 +608,9 @@ void build_prog(const NfPlan& plan, int m_begin, int m_end, TcProg* P) {
 }
 
 cudaError_t launch_tc(const NfPlan& plan, TcArgs a, long long units, cudaStream_t st) {
-  if (const char* dbg = getenv("NF_TC_DEBUG")) a.debug = atoi(dbg);
+#ifdef NF_EXPERIMENTS
+  if (const char* dbg = getenv("NF_TC_DEBUG")) a.debug = atoi(dbg);       // timing experiments only: some bits change results
+#endif
   if (tc_unsupported(plan, a.mlp_only ? a.which : -1)) return cudaErrorNotSupported;
   cudaError_t e = cudaFuncSetAttribute(k_render_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcSmem));
   if (e != cudaSuccess) return e;

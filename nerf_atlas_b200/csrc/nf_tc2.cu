@@ -454,7 +454,7 @@ k_render_tc2(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc2Pro
                 } else {
                   cr = __uint_as_float(v[0]) + __ldg(bias); cg = __uint_as_float(v[1]) + __ldg(bias + 1); cb = __uint_as_float(v[2]) + __ldg(bias + 2);
                 }
-                cr = nf_feat_act_fn(cr, plan.feat_act); cg = nf_feat_act_fn(cg, plan.feat_act); cb = nf_feat_act_fn(cb, plan.feat_act);
+                nf_feat_act3(cr, cg, cb, plan.feat_act);
                 composite_tile2(s, slot, plan, a, map, sub, row, lane, q, cr, cg, cb);
               }
             }
@@ -521,7 +521,9 @@ cudaError_t nf_launch_render_tc2(const NfPlan& plan, const void* packed, const f
   Tc2Args a{};
   a.packed = (const uint8_t*)packed; a.rays = rays; a.n_rays = n_rays; a.ts = ts; a.T = T; a.ts_stride = ts_stride;
   a.noise = noise; a.rgb_out = rgb; a.alpha_out = alpha; a.weights_out = weights;
+#ifdef NF_EXPERIMENTS
   if (const char* dbg = getenv("NF_TC_DEBUG")) a.debug = atoi(dbg);
+#endif
   cudaError_t e = cudaFuncSetAttribute(k_render_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tc2Smem));
   if (e != cudaSuccess) return e;
   const NfTileMap map(T, ROWS);

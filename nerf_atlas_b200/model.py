@@ -398,6 +398,7 @@ def _sigmoid_name(act) -> str:
   if isinstance(act, str): return act
   name = getattr(act, "__name__", None)
   if name in _ACT_NAMES: return _ACT_NAMES[name]
+  if type(act).__name__ == "Softmax" and getattr(act, "dim", None) == -1: return "softmax"      # nn.Softmax(dim=-1), utils.py:507
   raise NotImplementedError(f"feature activation {act!r} is not supported by the fused path")
 
 

@@ -22,7 +22,8 @@ def test_library_exports_every_declared_symbol():
   assert len(names) >= 10
   for n in names: assert hasattr(l, n), f"{n} declared in include/nerf_b200.h but not exported"
   assert sorted(_lib.EXPORTS) == names, "ctypes binding table and header disagree"
-  assert _lib.lib().nf_version() == _lib.ABI_VERSION == 4
+  assert _lib.lib().nf_version() == _lib.ABI_VERSION == 5
+  assert _lib.lib().nf_build_flags() == 0 or os.environ.get('NF_LIB'), 'the default library must be the product build (no experiment hooks)'
 
 def test_descriptor_host_logic():
   l = _lib.lib()
@@ -177,7 +178,8 @@ def test_header_enums_match_the_python_binding():
   }
   for k, v in expect.items(): assert vals.get(k) == v, (k, vals.get(k), v)
   feat = {"NORMAL": "normal", "THIN": "thin", "TANH": "tanh", "CYCLIC": "cyclic", "UPSHIFTED": "upshifted", "FAT": "fat", "LEAKY_RELU": "leaky_relu",
-          "RELU": "relu", "SIN": "sin", "UPSHIFTED_SOFTPLUS": "upshifted_softplus", "UPSHIFTED_RELU": "upshifted_relu"}
+          "RELU": "relu", "SIN": "sin", "UPSHIFTED_SOFTPLUS": "upshifted_softplus", "UPSHIFTED_RELU": "upshifted_relu", "SOFTMAX": "softmax"}
+  assert set(_lib.FEAT) == set(__import__("oracle.nerf_oracle", fromlist=["SIGMOIDS"]).SIGMOIDS)   # the whole family of reference src/utils.py:497-511
   for k, v in feat.items(): assert vals.get("NF_FEAT_" + k) == _lib.FEAT[v], k
   m = re.search(r"#define\s+NF_ABI_VERSION\s+(\d+)", src)
   assert m and int(m.group(1)) == _lib.ABI_VERSION

@@ -124,7 +124,32 @@ def test_render_all_T_vs_oracle(P, T):
     e = plain_engine(P, DEV, precision=precision)
     rgb, alpha, w = e.render(rays.to(DEV), ts.to(DEV))
     assert np.abs(rgb.cpu().numpy() - r["out"].numpy()).max() <= tol, (precision, T)
-    assert np.abs(w.cpu().numpy() - r["weights"].t().numpy()).max() <= 5e-3 if precision == "fp16" else 1e-4
+    assert np.abs(w.cpu().numpy() - r["weights"].t().numpy()).max() <= (5e-3 if precision == "fp16" else 1e-4), (precision, T)
+
+# every member of the reference's sigmoid family (src/utils.py:484-518) x both pipelines x both backgrounds
+@pytest.mark.parametrize("kind", sorted(O.SIGMOIDS))
+@pytest.mark.parametrize("bg", ["black", "white"])
+def test_every_feature_activation_vs_oracle(P, kind, bg):
+  # a larger final-layer gain so that the activations leave their linear range (raw colours of order +-3)
+  Pk = dict(P); Pk["refl.mlp.out.weight"] = P["refl.mlp.out.weight"] * 8.0
+  Pk["refl.mlp.out.bias"] = torch.tensor([0.5, -1.0, 2.0])
+  rays = O.make_rays(1, 4, 6, seed=11, crop_top=390, crop_left=400).reshape(-1, 6)
+  ts = torch.linspace(2, 6, 64)
+  with torch.no_grad():
+    ref = O.plain_forward(Pk, rays, ts, sigmoid=kind, bg=bg)
+    refq = O.plain_forward(Pk, rays, ts, sigmoid=kind, bg=bg, quant=torch.float16)
+  assert float(ref["rgb"].std()) > 1e-2                     # the activation is exercised, not a constant
+  scale = max(1.0, float(ref["out"].abs().max()))
+  for precision, r, tol in (("fp32", ref, 2e-5), ("fp16", refq, 3e-4), ("fp16", ref, 1e-3)):
+    e = plain_engine(Pk, DEV, kind, bg, precision)
+    rgb, alpha, w = e.render(rays.to(DEV), ts.to(DEV))
+    assert np.abs(rgb.cpu().numpy() - r["out"].numpy()).max() <= tol * scale, (kind, bg, precision)
+
+def test_unknown_feature_activation_is_rejected(P):
+  import nerf_atlas_b200 as N, ctypes as C
+  d = N.describe_plain(64, "upshifted", "black"); d.feat_act = 12
+  assert N._lib.lib().nf_packed_bytes(C.byref(d)) == -1      # NF_E_BADARG, not a silent identity
+  assert b"feature activation" in N._lib.lib().nf_last_error()
 
 def test_render_per_ray_ts_noise_white_bg(P):
   g = torch.Generator().manual_seed(5)
@@ -156,13 +181,15 @@ def test_tiny_nerf_vs_oracle():
     assert np.abs(rgb.cpu().numpy() - r["out"].numpy()).max() <= tol, precision
 
 # ---------------------------------------------------------------- every tensor pipeline / ring geometry
-@pytest.mark.parametrize("env", [{"NF_TC_PIPE": "3", "NF_TC_RING": "6"}, {"NF_TC_PIPE": "3", "NF_TC_RING": "3"},
-                                 {"NF_TC_PIPE": "3", "NF_TC_EPIW": "24"}, {"NF_TC_PIPE": "2"}, {"NF_TC_PIPE": "1"}],
-                         ids=["pipe3_ring6", "pipe3_ring3", "pipe3_epiw24", "pipe2", "pipe1"])
+@pytest.mark.parametrize("env", [{}, {"NF_TC_PIPE": "3", "NF_TC_RING": "6"}, {"NF_TC_PIPE": "3", "NF_TC_EPIW": "24"}, {"NF_TC_PIPE": "2"}, {"NF_TC_PIPE": "1"}],
+                         ids=["product", "pipe3_ring6", "pipe3_epiw24", "pipe2", "pipe1"])
 def test_tensor_pipeline_variants_vs_oracle(P, env, monkeypatch):
-  """The C ABI reads NF_TC_PIPE / NF_TC_RING at every call: 3 = staggered paired pipeline (default; ring 6x8 KB or
-  3x16 KB), 2 = lockstep paired pipeline, 1 = single-CTA pipeline.  All must meet the same bars, incl. rays spanning two
-  tiles (T = 256), ragged tiles (T = 100), several rays per tile (T = 32), noise, per-ray ts and the white background."""
+  """The product build runs the staggered paired pipeline and reads no environment variable.  An NF_EXPERIMENTS build
+  (NF_LIB=libnerf_b200_exp.so) also selects: ring 6x8 KB, 24 epilogue warps, 2 = lockstep paired pipeline, 1 = single-CTA
+  pipeline.  All must meet the same bars, incl. rays spanning two tiles (T = 256), ragged tiles (T = 100), several rays per
+  tile (T = 32), noise, per-ray ts and the white background."""
+  import nerf_atlas_b200 as N
+  if env and not N._lib.has_experiments(): pytest.skip("timing-experiment variants exist only in NF_EXPERIMENTS builds")
   for k, v in env.items(): monkeypatch.setenv(k, v)
   e = plain_engine(P, DEV, precision="fp16")
   for T, nr in ((128, 1500), (256, 333), (192, 301), (160, 203), (100, 77), (32, 1001)):   # 192 / 160: rays packed across tile boundaries
@@ -657,3 +684,23 @@ def test_fused_adam_matches_torch_adam():
     oa.step(); ob.step(); sched_a.step(); sched_b.step()
   for x, y in zip(pa, pb):
     assert float((x.detach() - y.detach()).abs().max()) <= 1e-6 * max(float(y.detach().abs().max()), 1.0), x.shape
+
+
+def test_fused_adam_step_is_seen_by_the_next_render(P):
+  """FusedAdam writes parameters through raw pointers; the next forward must re-pack them (the pack cache keys on
+  (data_ptr, _version)): render -> step -> render differs and equals a forced re-pack."""
+  import nerf_atlas_b200 as N
+  m = N.FusedPlainNeRF(steps=32, t_near=2, t_far=6, intermediate_size=64, sigmoid_kind="upshifted", precision="fp16")
+  m.load_state_dict(P, strict=True); m = m.to(DEV).eval()
+  rays = O.make_rays(1, 4, 4, seed=1, crop_top=398, crop_left=398).to(DEV)
+  with torch.no_grad(): a = m(rays).clone()
+  opt = N.autograd.FusedAdam(m.parameters(), lr=1e-2)
+  g = torch.Generator().manual_seed(1)
+  for p in m.parameters():
+    if p.requires_grad and p.numel(): p.grad = torch.randn(p.shape, generator=g).to(DEV)
+  opt.step()
+  with torch.no_grad(): b = m(rays).clone()
+  assert float((a - b).abs().max()) > 1e-4, "the render still uses the stale packed weights"
+  m.engine().pack(m._param_list(), force=True)
+  with torch.no_grad(): c = m(rays)
+  assert torch.equal(b, c)
