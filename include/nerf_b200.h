@@ -223,6 +223,55 @@ int nf_sample_pdf(const float* ts_coarse, int32_t T, const float* weights, int64
 int nf_mlp_forward(const nf_model_desc* desc, const void* packed, int32_t which,
                    const float* x0, int64_t n, float* out, int32_t precision, void* stream);
 
+/* ---- training: forward with an activation stash, backward of the whole path ------------------------------------------
+ * What the reference gets from PyTorch autograd (loss.backward(), runner.py:820) for model(rays): gradients of every
+ * parameter of the path given d loss / d rgb.  NF_PREC_FP16_TC only (tcgen05 forward AND backward), PlainNeRF + View.
+ *   1. nf_train_layout_of()    -> workspace size (total_bytes) and where everything lives in it
+ *   2. nf_render_forward_aux() with aux.train_ws: the normal forward, plus the stash (per 128-sample tile and Linear: the
+ *      input operand as the MMA consumed it, fp16; cos of the pre-activations for sin MLPs; raw density / colours per sample)
+ *   3. nf_render_backward()    -> gradients in the reference's parameter layout
+ * The layout is public so that parity tests can read every intermediate of the backward out of the workspace. */
+#define NF_TRAIN_LIN_MAX 24
+typedef struct nf_train_lin {  /* one Linear, in execution order (density MLP, then the RGB head) */
+  int32_t m, j, n, n_pad, k0_pad, k_hidden, act, x0_raw;   /* (mlp, index), out features (padded to 16), x0 / hidden input columns */
+  int64_t a_off, a_tile;       /* input operand stash: fp16 [tile][(k0_pad + k_hidden)/8][128][8], K order [x0 | hidden]; bytes per tile */
+  int64_t c_off;               /* cos(pre-activation) of the hidden input, fp16 [tile][32][128][8]; -1 unless the MLP is sin-activated */
+  int64_t g_off, g_tile;       /* d loss / d output of the Linear (loss-scaled), fp16 [tile][n_pad/8][128][8] */
+  int64_t dw_off, db_off;      /* fp32 dWt[n_pad][k0_pad + k_hidden], db[n_pad] (tensor column orders, loss-scaled) */
+} nf_train_lin;
+typedef struct nf_train_layout {
+  int32_t n_lin, T, rpu, tpr;          /* a work unit = rpu rays = tpr tiles of 128 samples (sample-stream tiling) */
+  int64_t n_rays, n_tiles;
+  int64_t sigma_off, rgbraw_off;       /* fp32 [R,T], [R,T,3]: raw density (noise included), raw colours */
+  int64_t dsigma_off, drgbraw_off;     /* fp32 gradients of those (written by the backward) */
+  int64_t dx0_off;                     /* fp32 [n_tiles*128][32]: gradient of the density MLP's hash features */
+  int64_t scale_off;                   /* float[4]: loss scale S, 1/S, max|g| (bits), - */
+  int64_t dw_begin, dw_end;
+  int64_t total_bytes;                 /* = the workspace size */
+  nf_train_lin lin[NF_TRAIN_LIN_MAX];
+} nf_train_layout;
+int nf_train_layout_of(const nf_model_desc* desc, int64_t n_rays, int32_t T, nf_train_layout* out);
+
+/* Optional inputs / outputs of the forward (all nullable; struct_bytes = sizeof(nf_render_aux)). */
+typedef struct nf_render_aux {
+  int32_t struct_bytes, reserved;
+  void* train_ws;            /* training forward: workspace of nf_train_layout_of(desc, n_rays, T).total_bytes bytes, 1024-aligned */
+  int64_t train_ws_bytes;
+} nf_render_aux;
+/* nf_render_forward with the optional extras of nf_render_aux (aux == NULL: identical to nf_render_forward). */
+int nf_render_forward_aux(const nf_model_desc* desc, const void* packed,
+                          const float* rays, int64_t n_rays,
+                          const float* ts, int32_t T, int64_t ts_ray_stride,
+                          const float* density_noise, const float* ray_time, const nf_mip_args* mip,
+                          float* rgb_out, float* alpha_out, float* weights_out,
+                          const nf_render_aux* aux, int32_t precision, void* stream);
+/* Backward of the render that filled `train_ws` (same desc, packed, rays, ts): d_rgb[R,3] -> one gradient per parameter, in
+ * the order of nf_pack_weights (grads_host[i] == NULL skips parameter i; every other gradient buffer is OVERWRITTEN, shapes as
+ * the parameters).  Replaces loss.backward() through PlainNeRF.forward (reference runner.py:820, src/nerf.py:326-361). */
+int nf_render_backward(const nf_model_desc* desc, const void* packed, void* train_ws, int64_t train_ws_bytes,
+                       const float* rays, int64_t n_rays, const float* ts, int32_t T, int64_t ts_ray_stride,
+                       const float* d_rgb, float* const* grads_host, int32_t n_grads, void* stream);
+
 /* ---- backward of the non-GEMM stages (first blocks of the training half; the reference differentiates these ops through
  *      PyTorch autograd, runner.py:820) --------------------------------------------------------------------------- */
 /* Backward of nf_composite: d_rgb[R,3] -> d_sigma_raw_out[R,T], d_feats_out[R,T,3] (same inputs as the forward; T <= 2048).

@@ -36,6 +36,20 @@ class MipArgs(C.Structure):
   _fields_ = [("radius", C.c_void_p), ("rays_all", C.c_void_p), ("radius_all", C.c_void_p), ("n_rays_all", C.c_int64),
               ("ray_base", C.c_int64)]
 
+TRAIN_LIN_MAX = 24
+
+class TrainLin(C.Structure):
+  _fields_ = [(n, C.c_int32) for n in ("m", "j", "n", "n_pad", "k0_pad", "k_hidden", "act", "x0_raw")] + \
+             [(n, C.c_int64) for n in ("a_off", "a_tile", "c_off", "g_off", "g_tile", "dw_off", "db_off")]
+
+class TrainLayout(C.Structure):
+  _fields_ = [(n, C.c_int32) for n in ("n_lin", "T", "rpu", "tpr")] + \
+             [(n, C.c_int64) for n in ("n_rays", "n_tiles", "sigma_off", "rgbraw_off", "dsigma_off", "drgbraw_off", "dx0_off",
+                                       "scale_off", "dw_begin", "dw_end", "total_bytes")] + [("lin", TrainLin * TRAIN_LIN_MAX)]
+
+class RenderAux(C.Structure):
+  _fields_ = [("struct_bytes", C.c_int32), ("reserved", C.c_int32), ("train_ws", C.c_void_p), ("train_ws_bytes", C.c_int64)]
+
 EXPORTS = {
   "nf_version": (C.c_int, []),
   "nf_last_error": (C.c_char_p, []),
@@ -46,6 +60,12 @@ EXPORTS = {
   "nf_pack_weights": (C.c_int, [C.POINTER(ModelDesc), C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
   "nf_render_forward": (C.c_int, [C.POINTER(ModelDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int64,
                                   C.c_void_p, C.c_void_p, C.POINTER(MipArgs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+  "nf_render_forward_aux": (C.c_int, [C.POINTER(ModelDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int64,
+                                      C.c_void_p, C.c_void_p, C.POINTER(MipArgs), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(RenderAux),
+                                      C.c_int32, C.c_void_p]),
+  "nf_train_layout_of": (C.c_int, [C.POINTER(ModelDesc), C.c_int64, C.c_int32, C.POINTER(TrainLayout)]),
+  "nf_render_backward": (C.c_int, [C.POINTER(ModelDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
+                                   C.c_int64, C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
   "nf_generate_rays": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_void_p, C.c_void_p]),
   "nf_ray_radii": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),

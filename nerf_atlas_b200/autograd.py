@@ -1,7 +1,13 @@
-"""Differentiable wrappers of the two non-GEMM stages (first blocks): the hash-grid encoder and the alpha
-composite, forward AND backward in hand-written CUDA through the C ABI (`nf_hash_encode[_backward]`, `nf_composite[_backward]`).
-The reference differentiates the same ops implicitly through PyTorch autograd (runner.py:820).  The fused backward of the MLP
-chain is not built yet, so `FusedNeRF.forward` still refuses to run with grad enabled in training mode."""
+"""Autograd surface of the fused path.  The reference differentiates `model(rays)` implicitly through PyTorch
+autograd (`loss.backward()`, runner.py:820); here
+
+* ``fused_render`` is ONE differentiable op for the whole path -- training forward with an activation stash
+  (`nf_render_forward_aux`), backward of composite, both MLPs (tcgen05: dX chain and dW GEMMs) and the hash tables
+  (`nf_render_backward`) -- with gradients for every parameter in the reference's layout; `FusedNeRF.forward` uses it whenever
+  grad is enabled;
+* ``composite`` / ``hash_encode`` are the differentiable stand-alone stages (`nf_composite[_backward]`,
+  `nf_hash_encode[_backward]`);
+* ``FusedAdam`` is torch.optim.Adam with the reference's hyper-parameters on `nf_adam_step`."""
 from __future__ import annotations
 import torch
 from .model import RenderEngine
@@ -10,6 +16,8 @@ from .model import RenderEngine
 class _Composite(torch.autograd.Function):
   @staticmethod
   def forward(ctx, engine: RenderEngine, sigma_raw, feats, rays, ts):
+    if engine.desc.density_act == 2:   # NF_DENS_LAPLACE: the gradient with respect to VolSDF's learned beta is not produced
+      raise NotImplementedError("autograd.composite: the Laplace density (VolSDF) has no backward for beta; use softplus / relu")
     rgb, _, _ = engine.composite(sigma_raw, feats, rays, ts, want_weights=False)
     ctx.engine = engine
     ctx.save_for_backward(sigma_raw, feats, rays, ts)
@@ -25,7 +33,14 @@ class _Composite(torch.autograd.Function):
 class _HashEncode(torch.autograd.Function):
   @staticmethod
   def forward(ctx, engine: RenderEngine, pts, *tables):
-    feats, _ = engine.hash_encode(pts)          # reads the engine's packed snapshot of `tables` (engine.pack must be current)
+    if pts.requires_grad: raise NotImplementedError("autograd.hash_encode: no gradient with respect to pts (tables only)")
+    # the encoder reads the engine's packed snapshot: refuse to run on tables that are not the ones currently packed
+    packed = {k[0] for k in (engine._key or ())}
+    if any(t.data_ptr() not in packed for t in tables):
+      raise RuntimeError("autograd.hash_encode: `tables` are not the tensors the engine was packed from (engine.pack(...) first)")
+    if any((t.data_ptr(), t._version, t.device) not in set(engine._key) for t in tables):
+      raise RuntimeError("autograd.hash_encode: the tables changed since engine.pack(...): re-pack before encoding")
+    feats, _ = engine.hash_encode(pts)
     ctx.engine = engine
     ctx.save_for_backward(pts)
     return feats
@@ -35,6 +50,42 @@ class _HashEncode(torch.autograd.Function):
     (pts,) = ctx.saved_tensors
     d_tables = ctx.engine.hash_encode_backward(pts, d_feats.contiguous())
     return (None, None) + tuple(d_tables[l] for l in range(d_tables.shape[0]))
+
+
+class _FusedRender(torch.autograd.Function):
+  """rays[R,6], ts -> rgb[R,3] (+ alpha, weights [R,T], not differentiable) with gradients to the packed parameters."""
+  @staticmethod
+  def forward(ctx, engine: RenderEngine, rays, ts, noise, want_weights, *params):
+    engine.pack(params)
+    R = rays.shape[0]; T = ts.shape[-1]
+    lay = engine.train_layout(R, T)
+    ws = RenderEngine.train_workspace(lay, rays.device)
+    rgb, alpha, weights = engine.render(rays, ts, noise, want_weights=want_weights, train_ws=ws)
+    ctx.engine, ctx.ws, ctx.params = engine, ws, params
+    ctx.pack_key = engine._key
+    ctx.save_for_backward(rays, ts)
+    if not want_weights: alpha = weights = rays.new_empty(0)
+    ctx.mark_non_differentiable(alpha, weights)
+    return rgb, alpha, weights
+
+  @staticmethod
+  def backward(ctx, d_rgb, _d_alpha, _d_weights):
+    rays, ts = ctx.saved_tensors
+    if ctx.ws is None: raise RuntimeError("fused_render: backward called twice (the activation stash is freed after the first)")
+    if ctx.engine._key != ctx.pack_key:
+      raise RuntimeError("fused_render: the parameters were modified or re-packed between forward and backward")
+    grads = [torch.empty_like(p) if need else None for p, need in zip(ctx.params, ctx.needs_input_grad[5:])]
+    ctx.engine.render_backward(ctx.ws, rays, ts, d_rgb.contiguous().to(torch.float32), grads)
+    ctx.ws = None                                           # several GB: free it as soon as it has been consumed
+    return (None, None, None, None, None) + tuple(grads)
+
+
+def fused_render(engine: RenderEngine, rays: torch.Tensor, ts: torch.Tensor, params, density_noise=None, want_weights: bool = True):
+  """The whole render path as one differentiable op: gradients flow to ``params`` (the live parameter tensors in
+  `nf_pack_weights` order).  Not differentiable with respect to rays / ts / noise (camera training is out of scope)."""
+  if rays.requires_grad or ts.requires_grad: raise NotImplementedError("fused_render: gradients with respect to rays / ts are not built")
+  rgb, alpha, weights = _FusedRender.apply(engine, rays, ts, density_noise, want_weights, *params)
+  return (rgb, alpha, weights) if want_weights else (rgb, None, None)
 
 
 def composite(engine: RenderEngine, sigma_raw: torch.Tensor, feats: torch.Tensor, rays: torch.Tensor, ts: torch.Tensor) -> torch.Tensor:

@@ -86,6 +86,8 @@ int nf_pack_weights(const nf_model_desc* desc, const float* const* params, int32
       if (e != cudaSuccess) return cuda_fail(e, "pack fp32");
       e = nf_launch_pack_fp16(p, m, j, W, b, packed, st);
       if (e != cudaSuccess) return cuda_fail(e, "pack fp16");
+      e = nf_launch_pack_w16t(p, m, j, W, packed, st);
+      if (e != cudaSuccess) return cuda_fail(e, "pack fp16 (transposed)");
     }
   }
   if (p.enc == NF_ENC_HASH) {
@@ -133,7 +135,53 @@ int nf_pack_weights(const nf_model_desc* desc, const float* const* params, int32
 int nf_render_forward(const nf_model_desc* desc, const void* packed, const float* rays, int64_t n_rays,
                       const float* ts, int32_t T, int64_t ts_ray_stride, const float* density_noise, const float* ray_time,
                       const nf_mip_args* mip, float* rgb_out, float* alpha_out, float* weights_out, int32_t precision, void* stream) {
+  return nf_render_forward_aux(desc, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, ray_time, mip, rgb_out, alpha_out,
+                               weights_out, nullptr, precision, stream);
+}
+
+int nf_train_layout_of(const nf_model_desc* desc, int64_t n_rays, int32_t T, nf_train_layout* out) {
   NfPlan p; if (int rc = plan_of(desc, &p)) return rc;
+  if (!out || n_rays < 0 || T < 1) return fail(NF_E_BADARG, "nf_train_layout_of: bad argument");
+  if (const char* why = nf_train_unsupported(p)) return fail(NF_E_UNSUPPORTED, why);
+  if (int rc = nf_build_train_plan(p, n_rays, T, out)) return fail(rc, "nf_train_layout_of: too many Linear layers");
+  return 0;
+}
+
+int nf_render_backward(const nf_model_desc* desc, const void* packed, void* train_ws, int64_t train_ws_bytes,
+                       const float* rays, int64_t n_rays, const float* ts, int32_t T, int64_t ts_ray_stride,
+                       const float* d_rgb, float* const* grads, int32_t n_grads, void* stream) {
+  NfPlan p; if (int rc = plan_of(desc, &p)) return rc;
+  if (const char* why = nf_train_unsupported(p)) return fail(NF_E_UNSUPPORTED, why);
+  if (n_rays < 0) return fail(NF_E_BADARG, "n_rays < 0");
+  if (int rc = check_ts(T, ts_ray_stride)) return rc;
+  if (!packed || !train_ws || !rays || !ts || !d_rgb || !grads) return fail(NF_E_BADARG, "nf_render_backward: null pointer");
+  if (n_grads != nf_param_count(desc)) return fail(NF_E_BADARG, "nf_render_backward: wrong number of gradient pointers");
+  if (((uintptr_t)train_ws & 1023) != 0) return fail(NF_E_BADARG, "nf_render_backward: train_ws must be 1024-byte aligned");
+  NfTrainPlan tp;
+  if (int rc = nf_build_train_plan(p, n_rays, T, &tp)) return fail(rc, "nf_render_backward: too many Linear layers");
+  if (train_ws_bytes < tp.total_bytes) return fail(NF_E_SMALLBUF, "nf_render_backward: workspace too small");
+  if (T > 2048) return fail(NF_E_UNSUPPORTED, "nf_render_backward: T <= 2048");
+  if (n_rays == 0) return 0;
+  cudaError_t e = nf_launch_render_backward(p, tp, packed, train_ws, rays, ts, ts_ray_stride, d_rgb, grads, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nf_render_backward");
+}
+
+int nf_render_forward_aux(const nf_model_desc* desc, const void* packed, const float* rays, int64_t n_rays,
+                          const float* ts, int32_t T, int64_t ts_ray_stride, const float* density_noise, const float* ray_time,
+                          const nf_mip_args* mip, float* rgb_out, float* alpha_out, float* weights_out, const nf_render_aux* aux,
+                          int32_t precision, void* stream) {
+  NfPlan p; if (int rc = plan_of(desc, &p)) return rc;
+  if (aux && aux->struct_bytes != (int32_t)sizeof(nf_render_aux)) return fail(NF_E_BADARG, "bad nf_render_aux (struct_bytes)");
+  NfTrainPlan tp; const NfTrainPlan* train = nullptr;
+  if (aux && aux->train_ws) {
+    if (precision != NF_PREC_FP16_TC) return fail(NF_E_UNSUPPORTED, "training forward: NF_PREC_FP16_TC only");
+    if (const char* why = nf_train_unsupported(p)) return fail(NF_E_UNSUPPORTED, why);
+    if (n_rays < 0 || T < 1) return fail(NF_E_BADARG, "bad n_rays / T");
+    if (int rc = nf_build_train_plan(p, n_rays, T, &tp)) return fail(rc, "training forward: too many Linear layers");
+    if (aux->train_ws_bytes < tp.total_bytes) return fail(NF_E_SMALLBUF, "training forward: workspace too small (nf_train_layout_of().total_bytes)");
+    if (((uintptr_t)aux->train_ws & 1023) != 0) return fail(NF_E_BADARG, "training forward: train_ws must be 1024-byte aligned");
+    train = &tp;
+  }
   if (n_rays < 0) return fail(NF_E_BADARG, "n_rays < 0");
   if (n_rays == 0) return 0;
   if (!packed || !rays || !ts || !rgb_out) return fail(NF_E_BADARG, "nf_render_forward: null pointer");
@@ -169,7 +217,8 @@ int nf_render_forward(const nf_model_desc* desc, const void* packed, const float
     if (pipe == 2) e = nf_launch_render_tc2(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, rgb_out, alpha_out, weights_out, st);
     else
 #endif
-    e = pipe == 3 ? nf_launch_render_tc3(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, ray_time, mip, rgb_out, alpha_out, weights_out, st)
+    if (train && pipe != 3) return fail(NF_E_UNSUPPORTED, "training forward: the staggered pipeline only");
+    e = pipe == 3 ? nf_launch_render_tc3(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, ray_time, mip, rgb_out, alpha_out, weights_out, st, train, train ? aux->train_ws : nullptr)
                   : nf_launch_render_tc(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, rgb_out, alpha_out, weights_out, st);
   }
   else return fail(NF_E_BADARG, "unknown precision");

@@ -25,6 +25,31 @@ __device__ __forceinline__ float dens_act_grad(float d, int kind, float beta) {
   return x > 20.f ? 1.f : 1.f / (1.f + expf(-x));
 }
 
+// d act(v) / d v for the sigmoid family (reference src/utils.py:484-518); `d` = gradient with respect to the activated colours
+__device__ __forceinline__ void feat_act3_bwd(float r, float g, float b, int kind, float& dr, float& dg, float& db) {
+  if (kind == NF_FEAT_SOFTMAX) {
+    float yr = r, yg = g, yb = b; nf_feat_act3(yr, yg, yb, kind);
+    const float dot = dr * yr + dg * yg + db * yb;
+    dr = yr * (dr - dot); dg = yg * (dg - dot); db = yb * (db - dot);
+    return;
+  }
+  auto one = [kind](float v) -> float {
+    switch (kind) {
+      case NF_FEAT_NORMAL: case NF_FEAT_UPSHIFTED: { const float s = nf_sigmoid(v); return s * (1.f - s); }
+      case NF_FEAT_THIN: { const float s = nf_sigmoid(v); return s * (1.f - s) * (1.f - 2e-2f); }
+      case NF_FEAT_FAT:  { const float s = nf_sigmoid(v); return s * (1.f - s) * (1.f + 2e-2f); }
+      case NF_FEAT_TANH: { const float t = tanhf(v); return 1.f - t * t; }
+      case NF_FEAT_CYCLIC: return cosf(v / 5.f) / 5.f / 2.f * (1.f - 2e-2f);
+      case NF_FEAT_LEAKY_RELU: return v > 0.f ? 1.f : 0.01f;
+      case NF_FEAT_RELU: case NF_FEAT_UPSHIFTED_RELU: return v > 0.f ? 1.f : 0.f;
+      case NF_FEAT_SIN: return cosf(v);
+      case NF_FEAT_UPSHIFTED_SOFTPLUS: return v > 20.f ? 1.f : nf_sigmoid(v);
+      default: return 1.f;
+    }
+  };
+  dr *= one(r); dg *= one(g); db *= one(b);
+}
+
 // Warp per ray.  Pass 1 (forward order): the transmittance entering every 32-sample chunk.  Pass 2 (reverse order):
 //   dL/dw_t = A_t = g . f_t - [white bg, t < T-1] (g_r + g_g + g_b)
 //   dL/dalpha_t = T_t A_t - (sum_{u>t} w_u A_u) / (1 - alpha_t + 1e-10)
@@ -32,7 +57,9 @@ __device__ __forceinline__ float dens_act_grad(float d, int kind, float beta) {
 __global__ void k_composite_bwd(int density_act, const float* __restrict__ beta_ptr, int bg, const float* __restrict__ sigma_raw,
                                 const float* __restrict__ feats, const float* __restrict__ rays, long long n_rays,
                                 const float* __restrict__ ts, int T, long long ts_stride, const float* __restrict__ d_rgb,
-                                float* __restrict__ d_sigma, float* __restrict__ d_feats) {
+                                float* __restrict__ d_sigma, float* __restrict__ d_feats, int feat_act) {
+  // feat_act >= 0: `feats` are the RAW colours (the training stash); the activation is applied here and d_feats is the
+  // gradient with respect to the raw values.  feat_act < 0: `feats` are already activated (the stand-alone stage).
   __shared__ float s_carry[8][BWD_MAX_CHUNKS];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
@@ -71,6 +98,8 @@ __global__ void k_composite_bwd(int density_act, const float* __restrict__ beta_
         const float* f = feats + (ray * T + t) * 3;
         fr = __ldg(f); fg = __ldg(f + 1); fb = __ldg(f + 2);
       }
+      const float rr = fr, rg = fg, rb = fb;
+      if (feat_act >= 0) nf_feat_act3(fr, fg, fb, feat_act);
       float p = t < T ? (1.f - al) + 1e-10f : 1.f;
       const float om = p;
 #pragma unroll
@@ -88,7 +117,9 @@ __global__ void k_composite_bwd(int density_act, const float* __restrict__ beta_
         const float dalpha = trans * A - later / om;
         d_sigma[ray * T + t] = dalpha * delta * (1.f - al) * dens_act_grad(sr, density_act, beta);
         float* df = d_feats + (ray * T + t) * 3;
-        df[0] = w * gr; df[1] = w * gg; df[2] = w * gb;
+        float d0 = w * gr, d1 = w * gg, d2 = w * gb;
+        if (feat_act >= 0) feat_act3_bwd(rr, rg, rb, feat_act, d0, d1, d2);
+        df[0] = d0; df[1] = d1; df[2] = d2;
       }
       suffix += __shfl_sync(0xffffffffu, sfx, 0);
     }
@@ -160,13 +191,13 @@ int bwd_num_sms() {
 
 cudaError_t nf_launch_composite_bwd(const NfPlan& plan, const void* packed, const float* sigma_raw, const float* feats, const float* rays,
                                     int64_t n_rays, const float* ts, int T, int64_t ts_stride, const float* d_rgb, float* d_sigma,
-                                    float* d_feats, cudaStream_t st) {
+                                    float* d_feats, cudaStream_t st, int feat_act) {
   if (n_rays == 0) return cudaSuccess;
   if (T > 32 * BWD_MAX_CHUNKS) return cudaErrorInvalidValue;
   const long long want = (n_rays * 32 + 255) / 256;
   const int grid = (int)(want < (long long)bwd_num_sms() * 8 ? want : (long long)bwd_num_sms() * 8);
   const float* beta = (plan.density_act == NF_DENS_LAPLACE && packed) ? reinterpret_cast<const float*>((const uint8_t*)packed + plan.scale_off) : nullptr;
-  k_composite_bwd<<<grid, 256, 0, st>>>(plan.density_act, beta, plan.bg, sigma_raw, feats, rays, n_rays, ts, T, ts_stride, d_rgb, d_sigma, d_feats);
+  k_composite_bwd<<<grid, 256, 0, st>>>(plan.density_act, beta, plan.bg, sigma_raw, feats, rays, n_rays, ts, T, ts_stride, d_rgb, d_sigma, d_feats, feat_act);
   return cudaGetLastError();
 }
 

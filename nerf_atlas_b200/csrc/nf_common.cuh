@@ -27,6 +27,8 @@ struct NfLinPlan {
   int64_t w16_off;    // byte offset: fp16 UMMA-canonical image [K_tc/8][n_pad][8], K order = [x0 (k0_pad) | hidden]
   int64_t b16_off;    // byte offset: fp32 bias[n_pad] in tensor-path column order
   int64_t w16h_off;   // byte offset: the same image split for a CTA pair: [rank 0..1][K_tc/8][n_pad/2][8]
+  int64_t w16t_off;   // byte offset: the TRANSPOSED fp16 images of the backward (dX = dZ W): [n_pad/8][k0_pad][8] (x0 part, if any)
+                      // followed by [n_pad/8][256][8] (hidden part, if any): the reduction dimension is the Linear's OUTPUT
 };
 struct NfMlpPlan {
   int32_t n_lin, in_dims, k0_pad, act, out_dims, pad_;
@@ -120,6 +122,7 @@ static inline int nf_build_plan(const nf_model_desc* d, NfPlan* p, const char** 
       L.w16_off = take((int64_t)k_tc * L.n_pad * sizeof(__half));
       L.b16_off = take((int64_t)L.n_pad * sizeof(float));
       L.w16h_off = take((int64_t)k_tc * L.n_pad * sizeof(__half));
+      L.w16t_off = take((int64_t)k_tc * L.n_pad * sizeof(__half));
     }
   }
   if (d->kind == NF_KIND_DYN) {
@@ -183,6 +186,15 @@ __host__ __device__ inline int nf_out_perm(const NfPlan& p, int m, int n_ref) {
   if ((p.kind == NF_KIND_PLAIN || p.kind == NF_KIND_DYN) && m == 0) return n_ref == 0 ? p.intermediate : n_ref - 1;
   return n_ref;
 }
+
+// ---- training workspace (nf_render_forward_aux with a train workspace -> nf_render_backward) --------------------------
+// The tensor pipeline's training forward stashes, per 128-sample tile and per Linear (execution order), the INPUT operand of
+// the Linear exactly as the MMA consumed it (fp16, UMMA canonical K-major image [K/8][128][8], K order = [x0 | hidden]) and,
+// for sin-activated MLPs, the cosine of the pre-activation behind every hidden input.  The backward adds the gradient with
+// respect to every Linear's output (G, same image, loss-scaled fp16).  dW = G^T A then reads both stashes as MN-major operands.
+#define NF_TRAIN_MAX_LIN NF_TRAIN_LIN_MAX
+typedef nf_train_lin NfTrainLin;          // the layout is public (include/nerf_b200.h): parity tests decode the stash
+typedef nf_train_layout NfTrainPlan;
 
 #ifdef __CUDACC__
 // ---- activations --------------------------------------------------------------
@@ -409,4 +421,68 @@ struct NfTileMap {
     ray = u; t = s * rows + r; return t < T && ray < n_rays;
   }
 };
+// ---- tile <-> (ray, t) map of this kernel: the SAMPLE STREAM of a unit is cut into 128-row tiles ----------------------
+// A unit = rpu whole rays = tpu whole tiles (rpu * Tp == tpu * 128, Tp = per-ray stride in the stream).  Tp = T packs rays back
+// to back, so a tile may hold the tail of one ray and the head of the next (T = 192: 2 rays in 3 tiles instead of 4; T = 160:
+// 4 rays in 5 tiles instead of 8).  Otherwise (T not a multiple of 32) Tp pads every ray to whole tiles / a divisor of 128 as
+// the other kernels do.  All carries stay inside a unit, which one slot walks tile by tile.
+struct NfStreamMap {
+  int T, Tp, tpr, rpu;        // tpr = tiles per unit (the name the schedule code uses), rpu = rays per unit
+  __host__ __device__ static int gcd(int a, int b) { while (b) { const int r = a % b; a = b; b = r; } return a; }
+  __host__ __device__ NfStreamMap(int T_, int rows) : T(T_) {
+    Tp = T_;
+    // packing needs warp-aligned rays (T % 32 == 0): the in-warp scan/reduction trees then see every ray at the same lanes, so
+    // a ray's rounding does not depend on its position in the unit (a sharded render must equal the whole bit for bit)
+    if ((T_ & 31) != 0 || T_ / gcd(T_, rows) > 64) Tp = T_ <= rows ? rows / (rows / T_) : (T_ + rows - 1) / rows * rows;
+    const int g = gcd(Tp, rows);
+    tpr = Tp / g; rpu = rows / g;
+  }
+  __host__ __device__ long long units(long long n_rays) const { return (n_rays + rpu - 1) / rpu; }
+  __device__ __forceinline__ bool locate(long long u, int sub, int r, long long n_rays, long long& ray, int& t) const {
+    const int q = sub * NF_TC_ROWS + r, rl = q / Tp;
+    t = q - rl * Tp; ray = u * rpu + rl;
+    return t < T && ray < n_rays;
+  }
+};
+
+
+// ---- training workspace layout (host) ------------------------------------------------------------------------------
+static inline int nf_build_train_plan(const NfPlan& p, int64_t n_rays, int T, NfTrainPlan* tp) {
+  *tp = NfTrainPlan{};
+  const NfStreamMap map(T, NF_TC_ROWS);
+  tp->T = T; tp->rpu = map.rpu; tp->tpr = map.tpr; tp->n_rays = n_rays;
+  tp->n_tiles = map.units(n_rays) * map.tpr;
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) { int64_t o = off; off += (bytes + 1023) / 1024 * 1024; return o; };
+  tp->scale_off = take(16);
+  tp->sigma_off = take(n_rays * T * 4); tp->rgbraw_off = take(n_rays * T * 12);
+  tp->dsigma_off = take(n_rays * T * 4); tp->drgbraw_off = take(n_rays * T * 12);
+  tp->dx0_off = take(tp->n_tiles * NF_TC_ROWS * 32 * 4);
+  int nl = 0;
+  for (int mi = 0; mi < p.n_mlps; ++mi) {
+    const int m = p.kind == NF_KIND_DYN ? (mi + 2) % 3 : mi;          // execution order (as build_prog3)
+    for (int j = 0; j < p.mlp[m].n_lin; ++j, ++nl) {
+      if (nl >= NF_TRAIN_MAX_LIN) return NF_E_UNSUPPORTED;
+      const NfLinPlan& L = p.mlp[m].lin[j];
+      NfTrainLin& R = tp->lin[nl];
+      R.m = m; R.j = j; R.n = L.n; R.n_pad = L.n_pad; R.k0_pad = L.k0_pad; R.k_hidden = L.k_hidden; R.act = p.mlp[m].act; R.x0_raw = L.x0_raw;
+      R.a_tile = (int64_t)(L.k0_pad + L.k_hidden) * 256; R.g_tile = (int64_t)L.n_pad * 256;
+    }
+  }
+  tp->n_lin = nl;
+  tp->dw_begin = off;
+  for (int i = 0; i < nl; ++i) {
+    NfTrainLin& R = tp->lin[i];
+    R.dw_off = take((int64_t)R.n_pad * (R.k0_pad + R.k_hidden) * 4); R.db_off = take((int64_t)R.n_pad * 4);
+  }
+  tp->dw_end = off;
+  for (int i = 0; i < nl; ++i) {
+    NfTrainLin& R = tp->lin[i];
+    R.a_off = take(tp->n_tiles * R.a_tile);
+    R.c_off = (R.act == NF_ACT_SIN && R.k_hidden) ? take(tp->n_tiles * 65536) : -1;
+    R.g_off = take(tp->n_tiles * R.g_tile);
+  }
+  tp->total_bytes = off;
+  return 0;
+}
 #endif  // __CUDACC__

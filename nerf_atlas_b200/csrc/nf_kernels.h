@@ -29,11 +29,16 @@ cudaError_t nf_launch_render_tc2(const NfPlan& plan, const void* packed, const f
 const char* nf_tc3_unsupported(const NfPlan& plan);
 cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const float* rays, int64_t n_rays, const float* ts,
                                  int T, int64_t ts_stride, const float* noise, const float* ray_time, const nf_mip_args* mip,
-                                 float* rgb, float* alpha, float* weights, cudaStream_t st);
+                                 float* rgb, float* alpha, float* weights, cudaStream_t st, const NfTrainPlan* train = nullptr, void* ws = nullptr);
+// training (nf_tc3.cu TRAIN instantiation + nf_train.cu): transposed weight images, the backward of the MLP chain on tcgen05
+const char* nf_train_unsupported(const NfPlan& plan);
+cudaError_t nf_launch_pack_w16t(const NfPlan& plan, int m, int j, const float* W, void* packed, cudaStream_t st);
+cudaError_t nf_launch_render_backward(const NfPlan& plan, const NfTrainPlan& tp, const void* packed, void* ws, const float* rays,
+                                      const float* ts, int64_t ts_stride, const float* d_rgb, float* const* grads, cudaStream_t st);
 // backward of the non-GEMM stages (nf_bwd.cu)
 cudaError_t nf_launch_composite_bwd(const NfPlan& plan, const void* packed, const float* sigma_raw, const float* feats, const float* rays,
                                     int64_t n_rays, const float* ts, int T, int64_t ts_stride, const float* d_rgb, float* d_sigma,
-                                    float* d_feats, cudaStream_t st);
+                                    float* d_feats, cudaStream_t st, int feat_act = -1);
 cudaError_t nf_launch_hash_encode_bwd(const NfPlan& plan, const float* pts, int64_t n, const float* d_feats, float* d_tables, cudaStream_t st);
 cudaError_t nf_launch_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                                 float wd, int step, cudaStream_t st);

@@ -64,6 +64,11 @@ struct __align__(16) Tc3Lin {
 };
 struct __align__(16) Tc3Prog { int32_t n_lin, lag, single, pad1_; Tc3Lin lin[MAX_LIN3]; };   // single: one tile in flight, x0 (up to 256 wide) lives in slot 1's H buffer
 
+// Training forward (TRAIN instantiation): where every Linear's input operand (and, for sin MLPs, the cosine of its
+// pre-activation) of every tile goes (NfTrainPlan, nf_common.cuh).  Offsets in 256-byte units from Tc3Args::ws.
+struct __align__(16) Tc3TrainLin { uint32_t a_off256, c_off256, a_tile256, k0; int32_t skip0, skip1, pad0_, pad1_; };   // k0 = columns of THIS Linear's x0 part; skip0/1: for an `init` Linear, the Linears of its MLP that consume act(x0) (-1: none)
+struct __align__(16) Tc3Train { Tc3TrainLin lin[MAX_LIN3]; long long n_tiles; float* sigma_out; float* rgbraw_out; };
+
 struct Tc3Args {
   const uint8_t* packed;
   const float* rays; long long n_rays;
@@ -72,6 +77,7 @@ struct Tc3Args {
   float* rgb_out; float* alpha_out; float* weights_out;
   int debug;          // NF_TC_DEBUG (timing experiments): 256 = poll acc_full with backoff, 512 = try_wait with a short suspend hint
   NfMipIn mip;        // Mip encoder inputs (plan.mip != NF_MIP_NONE)
+  uint8_t* ws;        // TRAIN: the training workspace (activation stash)
   long long* stats;   // NF_TC_STATS builds: time-in-state counters of CTA 0 (issuer, producer 0, epilogue warps 0 and 15)
 };
 
@@ -126,8 +132,14 @@ __device__ __forceinline__ float sin_poly(float x) {
 }
 
 // ---- epilogue of a hidden Linear: H <- fp16(act(acc + bias)), bias from shared memory ---------------------
-template <int ACT, int NCQ>
-__device__ __forceinline__ void epi_hidden3(uint8_t* __restrict__ H, uint32_t t_acc, const float* __restrict__ bias_s, int cq, int row) {
+__device__ __forceinline__ void st_global_v4(uint8_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");   // streaming: the stash is read once, much later
+}
+// gA (TRAIN, nullable): global image of the same tile -- the activated output is ALSO stashed there (the backward's dW operand
+// and LeakyReLU' mask); gC (TRAIN, sin MLPs): cos of the pre-activation (the backward's sin').
+template <int ACT, int NCQ, bool TRAIN = false>
+__device__ __forceinline__ void epi_hidden3(uint8_t* __restrict__ H, uint32_t t_acc, const float* __restrict__ bias_s, int cq, int row,
+                                            uint8_t* __restrict__ gA = nullptr, uint8_t* __restrict__ gC = nullptr) {
   // the 16 units of 16 columns are dealt round-robin to the NCQ warps of a lane quarter (unit = cq, cq + NCQ, ...); the next
   // unit's TMEM load is in flight while this one is converted
   uint32_t v[2][16];
@@ -155,6 +167,22 @@ __device__ __forceinline__ void epi_hidden3(uint8_t* __restrict__ H, uint32_t t_
     }
     uint8_t* dst = H + (col >> 3) * KG_BYTES + row * 16;
     st_v4(dst, o[0], o[1], o[2], o[3]); st_v4(dst + KG_BYTES, o[4], o[5], o[6], o[7]);
+    if (TRAIN && gA) {
+      uint8_t* g = gA + (col >> 3) * KG_BYTES + row * 16;
+      st_global_v4(g, o[0], o[1], o[2], o[3]); st_global_v4(g + KG_BYTES, o[4], o[5], o[6], o[7]);
+      if (ACT == NF_ACT_SIN && gC) {
+        const float4* b4c = reinterpret_cast<const float4*>(bias_s + col);
+        uint32_t c[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 b = b4c[i];
+          c[2 * i] = pack_h2(__cosf(__uint_as_float(v[u & 1][4 * i]) + b.x), __cosf(__uint_as_float(v[u & 1][4 * i + 1]) + b.y));
+          c[2 * i + 1] = pack_h2(__cosf(__uint_as_float(v[u & 1][4 * i + 2]) + b.z), __cosf(__uint_as_float(v[u & 1][4 * i + 3]) + b.w));
+        }
+        uint8_t* gc = gC + (col >> 3) * KG_BYTES + row * 16;
+        st_global_v4(gc, c[0], c[1], c[2], c[3]); st_global_v4(gc + KG_BYTES, c[4], c[5], c[6], c[7]);
+      }
+    }
   }
 }
 
@@ -206,10 +234,13 @@ __device__ __forceinline__ void epi_hidden3_sin_pipelined(uint8_t* __restrict__ 
 }
 
 // x0 raw -> act(x0), in place (the `init` Linear consumed the raw form; the skip Linear wants the activated one)
-__device__ __forceinline__ void x0_activate3(uint8_t* X0, int k0_pad, int act, int g_tid, int n_threads) {
+// gRaw / gAct0 / gAct1 (TRAIN, nullable): stash of the raw x0 (the `init` Linear's operand) and of act(x0) (the skip Linears')
+__device__ __forceinline__ void x0_activate3(uint8_t* X0, int k0_pad, int act, int g_tid, int n_threads,
+                                             uint8_t* gRaw = nullptr, uint8_t* gAct0 = nullptr, uint8_t* gAct1 = nullptr) {
   const int n16 = (k0_pad >> 3) * ROWS;             // 16-byte groups
   for (int i = g_tid; i < n16; i += n_threads) {
     uint4 q = *reinterpret_cast<uint4*>(X0 + i * 16);
+    if (gRaw) st_global_v4(gRaw + i * 16, q.x, q.y, q.z, q.w);
     uint32_t* w = reinterpret_cast<uint32_t*>(&q);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -217,6 +248,8 @@ __device__ __forceinline__ void x0_activate3(uint8_t* X0, int k0_pad, int act, i
       w[k] = pack_h2(tc_act(f.x, act), tc_act(f.y, act));
     }
     *reinterpret_cast<uint4*>(X0 + i * 16) = q;
+    if (gAct0) st_global_v4(gAct0 + i * 16, q.x, q.y, q.z, q.w);
+    if (gAct1) st_global_v4(gAct1 + i * 16, q.x, q.y, q.z, q.w);
   }
 }
 
@@ -250,30 +283,6 @@ __device__ __forceinline__ void mip_x0(uint8_t* X0, const NfMipIn& mip, int col0
   }
 }
 
-// ---- tile <-> (ray, t) map of this kernel: the SAMPLE STREAM of a unit is cut into 128-row tiles ----------------------
-// A unit = rpu whole rays = tpu whole tiles (rpu * Tp == tpu * 128, Tp = per-ray stride in the stream).  Tp = T packs rays back
-// to back, so a tile may hold the tail of one ray and the head of the next (T = 192: 2 rays in 3 tiles instead of 4; T = 160:
-// 4 rays in 5 tiles instead of 8).  Otherwise (T not a multiple of 32) Tp pads every ray to whole tiles / a divisor of 128 as
-// the other kernels do.  All carries stay inside a unit, which one slot walks tile by tile.
-struct NfStreamMap {
-  int T, Tp, tpr, rpu;        // tpr = tiles per unit (the name the schedule code uses), rpu = rays per unit
-  __host__ __device__ static int gcd(int a, int b) { while (b) { const int r = a % b; a = b; b = r; } return a; }
-  __host__ __device__ NfStreamMap(int T_, int rows) : T(T_) {
-    Tp = T_;
-    // packing needs warp-aligned rays (T % 32 == 0): the in-warp scan/reduction trees then see every ray at the same lanes, so
-    // a ray's rounding does not depend on its position in the unit (a sharded render must equal the whole bit for bit)
-    if ((T_ & 31) != 0 || T_ / gcd(T_, rows) > 64) Tp = T_ <= rows ? rows / (rows / T_) : (T_ + rows - 1) / rows * rows;
-    const int g = gcd(Tp, rows);
-    tpr = Tp / g; rpu = rows / g;
-  }
-  __host__ __device__ long long units(long long n_rays) const { return (n_rays + rpu - 1) / rpu; }
-  __device__ __forceinline__ bool locate(long long u, int sub, int r, long long n_rays, long long& ray, int& t) const {
-    const int q = sub * ROWS + r, rl = q / Tp;
-    t = q - rl * Tp; ray = u * rpu + rl;
-    return t < T && ray < n_rays;
-  }
-};
-
 // work unit of (pass, slot) for this CTA, and the sub-tile within a ray (T > 128)
 __device__ __forceinline__ void unit_of(int pass, int slot, int tpr, int nslot, long long& u, int& sub) {
   const int trip = tpr == 1 ? pass : pass / tpr;
@@ -286,13 +295,15 @@ __device__ __forceinline__ void unit_of(int pass, int slot, int tpr, int nslot, 
 // last may be unfinished (carry out).  Products and sums are LEFT folds in sample order -- 32-sample chunk by chunk, across
 // tile boundaries -- so a ray's result does not depend on where in a unit it happens to sit.
 __device__ __forceinline__ void composite_tile3(Tc3Smem& s, int slot, const NfPlan& plan, const Tc3Args& a, const NfStreamMap& map,
-                                                long long u, int sub, int row, int lane, int q, float cr, float cg, float cb) {
+                                                long long u, int sub, int row, int lane, int q, float cr, float cg, float cb,
+                                                float* sigma_out = nullptr) {
   long long ray; int t;
   const bool valid = map.locate(u, sub, row, a.n_rays, ray, t);       // t is the position within the (padded) ray even when invalid
   float al = 0.f;
   if (valid) {
     float sr = s.sig[slot][row];
     if (a.noise) sr += __ldg(a.noise + ray * a.T + t);
+    if (sigma_out) sigma_out[ray * a.T + t] = sr;                     // TRAIN: the raw density the composite consumed (noise included)
     const float* rr = a.rays + ray * 6;
     const float dx = __ldg(rr + 3), dy = __ldg(rr + 4), dz = __ldg(rr + 5);
     const float beta = plan.density_act == NF_DENS_LAPLACE ? __ldg(reinterpret_cast<const float*>(a.packed + plan.scale_off)) : 1.f;
@@ -377,9 +388,11 @@ __device__ __forceinline__ void composite_tile3(Tc3Smem& s, int slot, const NfPl
 // WIDE: the single-tile wide-x0 mode (Mip latent, Positional head) is compiled in.  The common path uses the WIDE = false
 // instantiation: with the wide code merely branched around, it ran 3.9 % slower (measured by bisection on one box).
 // DYN: the DynamicNeRF chain (deformation-out epilogue, Bezier, re-encode) is compiled in; same reason.
-template <int NST, int SPCT, int NCQ, bool WIDE, bool DYN>
+// TRAIN: the training forward -- every Linear's input operand (+ cos for sin MLPs) and the raw density / colours of every
+// sample are stashed in the training workspace for nf_render_backward (nf_train.cu).
+template <int NST, int SPCT, int NCQ, bool WIDE, bool DYN, bool TRAIN = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (4 * NCQ + NST + 1), 1)
-k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Prog prog, const Tc3Args a) {
+k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Prog prog, const Tc3Args a, const __grid_constant__ Tc3Train tr) {
   static_assert(NST * SPCT * 4096 == RING_BYTES && NST <= MAX_STAGES3, "ring geometry");
   constexpr int STAGE_BYTES = SPCT * 4096;
   constexpr int EPIW = 4 * NCQ, EPI_THREADS = 32 * EPIW;
@@ -581,9 +594,13 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
             } else {
               cr = __uint_as_float(v[0]) + bias[0]; cg = __uint_as_float(v[1]) + bias[1]; cb = __uint_as_float(v[2]) + bias[2];
             }
+            if (TRAIN) {
+              long long ray; int t;
+              if (map.locate(u, sub, row, a.n_rays, ray, t)) { float* o = tr.rgbraw_out + (ray * a.T + t) * 3; o[0] = cr; o[1] = cg; o[2] = cb; }
+            }
             nf_feat_act3(cr, cg, cb, plan.feat_act);
             ST_ADD(6);
-            composite_tile3(s, slot, plan, a, map, u, sub, row, lane, q, cr, cg, cb);
+            composite_tile3(s, slot, plan, a, map, u, sub, row, lane, q, cr, cg, cb, TRAIN ? tr.sigma_out : nullptr);
             ST_ADD(5);
           }
           if (has_next) {
@@ -655,11 +672,33 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
           const int act = Lc.z;
           const bool is_out = (Lc.w & 1) != 0;
           if (!is_out) {
+            if (TRAIN) {
+              // this phase writes the hidden input of Linear j (and, after an `init`, activates x0): stash all of it
+              long long u; int sub; unit_of(P, slot, map.tpr, nslot, u, sub);
+              const long long g = u * map.tpr + sub;
+              const bool st_ok = g < tr.n_tiles;
+              const Tc3TrainLin& Tn = tr.lin[j];
+              uint8_t* tileA = a.ws + ((size_t)Tn.a_off256 + (size_t)g * Tn.a_tile256) * 256;
+              uint8_t* gA = st_ok ? tileA + (size_t)Tn.k0 * 256 : nullptr;
+              uint8_t* gC = (st_ok && Tn.c_off256) ? a.ws + ((size_t)Tn.c_off256 + (size_t)g * 256) * 256 : nullptr;
+              if (Lc.w & 2) {
+                const Tc3TrainLin& Ti = tr.lin[j - 1];
+                uint8_t* gRaw = st_ok ? a.ws + ((size_t)Ti.a_off256 + (size_t)g * Ti.a_tile256) * 256 : nullptr;
+                uint8_t* g0 = (st_ok && Ti.skip0 >= 0) ? a.ws + ((size_t)tr.lin[Ti.skip0].a_off256 + (size_t)g * tr.lin[Ti.skip0].a_tile256) * 256 : nullptr;
+                uint8_t* g1 = (st_ok && Ti.skip1 >= 0) ? a.ws + ((size_t)tr.lin[Ti.skip1].a_off256 + (size_t)g * tr.lin[Ti.skip1].a_tile256) * 256 : nullptr;
+                x0_activate3(X0, s.lin[j - 1][1].x, act, e_tid, EPI_THREADS, gRaw, g0, g1);
+              }
+              if (act == NF_ACT_SIN) epi_hidden3<NF_ACT_SIN, NCQ, true>(H, t_acc, bias, cq, row, gA, gC);
+              else if (act == NF_ACT_LEAKY) epi_hidden3<NF_ACT_LEAKY, NCQ, true>(H, t_acc, bias, cq, row, gA, nullptr);
+              else if (act == NF_ACT_RELU) epi_hidden3<NF_ACT_RELU, NCQ, true>(H, t_acc, bias, cq, row, gA, nullptr);
+              else epi_hidden3<NF_ACT_NONE, NCQ, true>(H, t_acc, bias, cq, row, gA, nullptr);
+            } else {
             if (Lc.w & 2) x0_activate3(X0, s.lin[j - 1][1].x, act, e_tid, EPI_THREADS);       // init consumed raw x0; the skip Linear wants act(x0)
             if (act == NF_ACT_SIN) { if (a.debug & 2048) epi_hidden3<NF_ACT_SIN, NCQ>(H, t_acc, bias, cq, row); else epi_hidden3_sin_pipelined<NCQ>(H, t_acc, bias, cq, row); }
             else if (act == NF_ACT_LEAKY) epi_hidden3<NF_ACT_LEAKY, NCQ>(H, t_acc, bias, cq, row);
             else if (act == NF_ACT_RELU) epi_hidden3<NF_ACT_RELU, NCQ>(H, t_acc, bias, cq, row);
             else epi_hidden3<NF_ACT_NONE, NCQ>(H, t_acc, bias, cq, row);
+            }
           } else if (DYN && ((Lc.w >> 2) & 3) == 2) {
             // deformation MLP out (reference nerf.py:1261-1278): every thread deforms its row's sample, then takes its share of
             // the density MLP's hash levels at the DEFORMED position (the canonical NeRF sees pts + rigid_dp, nerf.py:1303)
@@ -836,11 +875,24 @@ const char* nf_tc3_unsupported(const NfPlan& p) {
   return nullptr;
 }
 
+// nullptr if the training forward/backward (activation stash + nf_train.cu) can run this model, else the reason.
+const char* nf_train_unsupported(const NfPlan& p) {
+  if (const char* why = nf_tc3_unsupported(p)) return why;
+  if (p.kind != NF_KIND_PLAIN) return "training: PlainNeRF + View only (DynamicNeRF needs the gradient with respect to the sample position)";
+  if (p.mip != NF_MIP_NONE || p.refl_kind != NF_REFL_VIEW || p.enc == NF_ENC_FOURIER) return "training: wide-x0 models (Mip, Positional, Fourier SDF) are not built";
+  if (p.kind == NF_KIND_PLAIN && p.enc != NF_ENC_HASH) return "training: PlainNeRF needs the hash-encoded density MLP (the SIREN SDF needs d/dp)";
+  if (p.density_act == NF_DENS_LAPLACE) return "training: the gradient of VolSDF's beta is not built";
+  for (int m = 0; m < p.n_mlps; ++m) if (p.mlp[m].act != NF_ACT_LEAKY && p.mlp[m].act != NF_ACT_SIN) return "training: LeakyReLU / sin MLPs only";
+  return nullptr;
+}
+
 cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const float* rays, int64_t n_rays, const float* ts,
                                  int T, int64_t ts_stride, const float* noise, const float* ray_time, const nf_mip_args* mip,
-                                 float* rgb, float* alpha, float* weights, cudaStream_t st) {
+                                 float* rgb, float* alpha, float* weights, cudaStream_t st, const NfTrainPlan* tp, void* ws) {
   if (nf_tc3_unsupported(plan)) return cudaErrorNotSupported;
+  if (tp && nf_train_unsupported(plan)) return cudaErrorNotSupported;
   Tc3Args a{};
+  a.ws = (uint8_t*)ws;
   a.packed = (const uint8_t*)packed; a.rays = rays; a.n_rays = n_rays; a.ts = ts; a.T = T; a.ts_stride = ts_stride;
   a.noise = noise; a.ray_time = ray_time; a.rgb_out = rgb; a.alpha_out = alpha; a.weights_out = weights;
   if (plan.kind == NF_KIND_DYN && !ray_time) return cudaErrorInvalidValue;
@@ -867,7 +919,27 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
   if (wide) { ring = 3; epiw = 16; }
   const bool dynk = plan.kind == NF_KIND_DYN;
   if (dynk) { ring = 3; epiw = 16; }
-  const void* fn = wide ? (const void*)k_render_tc3<3, 4, 4, true, false>
+  const bool train = tp != nullptr;
+  if (train) { ring = 3; epiw = 16; }
+  Tc3Train tr{};
+  if (train) {
+    tr.n_tiles = tp->n_tiles;
+    tr.sigma_out = (float*)((uint8_t*)ws + tp->sigma_off); tr.rgbraw_out = (float*)((uint8_t*)ws + tp->rgbraw_off);
+    for (int i = 0; i < tp->n_lin; ++i) {
+      const NfTrainLin& L = tp->lin[i];
+      Tc3TrainLin& R = tr.lin[i];
+      R.a_off256 = (uint32_t)(L.a_off >> 8); R.c_off256 = L.c_off < 0 ? 0u : (uint32_t)(L.c_off >> 8);
+      R.a_tile256 = (uint32_t)(L.a_tile >> 8); R.k0 = (uint32_t)L.k0_pad; R.skip0 = R.skip1 = -1;
+      if ((L.a_off >> 8) >= (1LL << 32) || (L.c_off >> 8) >= (1LL << 32)) return cudaErrorNotSupported;
+    }
+    for (int i = 0; i < tp->n_lin; ++i) {
+      if (tp->lin[i].j != 0) continue;                       // an `init`: which later Linears of its MLP re-concatenate act(x0)?
+      for (int k = i + 1; k < tp->n_lin && tp->lin[k].m == tp->lin[i].m; ++k)
+        if (tp->lin[k].k0_pad) { if (tr.lin[i].skip0 < 0) tr.lin[i].skip0 = k; else if (tr.lin[i].skip1 < 0) tr.lin[i].skip1 = k; else return cudaErrorNotSupported; }
+    }
+  }
+  const void* fn = train ? (const void*)k_render_tc3<3, 4, 4, false, false, true>
+                 : wide ? (const void*)k_render_tc3<3, 4, 4, true, false>
                  : dynk ? (const void*)k_render_tc3<3, 4, 4, false, true>
 #ifdef NF_EXPERIMENTS
                  : epiw == 24 ? (const void*)k_render_tc3<3, 4, 6, false, false>
@@ -893,13 +965,14 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
   cudaMemsetAsync(d_stats, 0, 64 * sizeof(long long), st);
   a.stats = d_stats;
 #endif
-  if (wide) k_render_tc3<3, 4, 4, true, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a);
-  else if (dynk) k_render_tc3<3, 4, 4, false, true><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a);
+  if (train) k_render_tc3<3, 4, 4, false, false, true><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
+  else if (wide) k_render_tc3<3, 4, 4, true, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
+  else if (dynk) k_render_tc3<3, 4, 4, false, true><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
 #ifdef NF_EXPERIMENTS
-  else if (epiw == 24) k_render_tc3<3, 4, 6, false, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a);
-  else if (ring == 6) k_render_tc3<6, 2, 4, false, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a);
+  else if (epiw == 24) k_render_tc3<3, 4, 6, false, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
+  else if (ring == 6) k_render_tc3<6, 2, 4, false, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
 #endif
-  else k_render_tc3<3, 4, 4, false, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a);
+  else k_render_tc3<3, 4, 4, false, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
 #ifdef NF_TC_STATS
   if (getenv("NF_TC_STATS_PRINT")) {
     cudaStreamSynchronize(st);

@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import ModelDesc, MlpDesc, MipArgs
+from ._lib import ModelDesc, MlpDesc, MipArgs, RenderAux, TrainLayout
 
 HASH_PRIMES = [1, 2654435761, 805459861, 3674653429, 2097192037, 1434869437, 2165219737]
 
@@ -200,9 +200,39 @@ class RenderEngine:
     _lib.check(rc, "nf_ray_radii")
     return out
 
+  # ---- training (include/nerf_b200.h: nf_train_layout_of / nf_render_forward_aux / nf_render_backward) ----
+  def train_layout(self, n_rays: int, T: int) -> TrainLayout:
+    """Where the training forward stashes what the backward needs (``total_bytes`` = the workspace size)."""
+    lay = TrainLayout()
+    _lib.check(self.lib.nf_train_layout_of(C.byref(self.desc), int(n_rays), int(T), C.byref(lay)), "nf_train_layout_of")
+    return lay
+
+  @staticmethod
+  def train_workspace(layout: TrainLayout, device) -> torch.Tensor:
+    raw = torch.empty(int(layout.total_bytes) + 1024, dtype=torch.uint8, device=device)
+    off = (-raw.data_ptr()) % 1024
+    return raw[off:off + int(layout.total_bytes)]
+
+  def render_backward(self, ws: torch.Tensor, rays: torch.Tensor, ts: torch.Tensor, d_rgb: torch.Tensor, grads: Sequence[Optional[torch.Tensor]]):
+    """Backward of the ``render(..., train_ws=ws)`` call that filled ``ws``: d_rgb[R,3] -> ``grads[i]`` (same order and shapes
+    as the packed parameters; None entries are skipped, the others overwritten)."""
+    self._need_packed()
+    _chk(rays, "rays"); _chk(ts, "ts"); _chk(d_rgb, "d_rgb"); _chk(ws, "ws", torch.uint8)
+    R = rays.shape[0]
+    T, stride = (ts.shape[0], 0) if ts.dim() == 1 else (ts.shape[1], ts.shape[1])
+    if tuple(d_rgb.shape) != (R, 3): raise ValueError("d_rgb must be [R,3]")
+    if len(grads) != self.n_params: raise ValueError(f"expected {self.n_params} gradient slots, got {len(grads)}")
+    for g in grads:
+      if g is not None: _chk(g, "grad")
+    arr = (C.c_void_p * len(grads))(*[None if g is None else g.data_ptr() for g in grads])
+    with torch.cuda.device(rays.device):
+      rc = self.lib.nf_render_backward(C.byref(self.desc), _ptr(self.packed), _ptr(ws), ws.numel(), _ptr(rays), R, _ptr(ts), T, stride,
+                                       _ptr(d_rgb), arr, len(grads), self._stream())
+    _lib.check(rc, "nf_render_backward")
+
   def render(self, rays: torch.Tensor, ts: torch.Tensor, density_noise: Optional[torch.Tensor] = None,
              want_weights: bool = True, precision: Optional[str] = None, ray_time: Optional[torch.Tensor] = None,
-             radius: Optional[torch.Tensor] = None, crop: Optional[tuple] = None):
+             radius: Optional[torch.Tensor] = None, crop: Optional[tuple] = None, train_ws: Optional[torch.Tensor] = None):
     """rays[R,6], ts[T] (shared) or ts[R,T] (per ray) -> rgb[R,3], alpha[R,T]|None, weights[R,T]|None.
     Mip models: ``radius[R]`` (``ray_radii``); "cylinder_ref" also takes ``crop = (rays_all[R_all,6], radius_all[R_all],
     ray_base)`` when ``rays`` is a shard of a larger crop (default: the call's rays are the whole crop)."""
@@ -230,11 +260,15 @@ class RenderEngine:
       rays_all, radius_all, base = crop if crop is not None else (rays, radius, 0)
       _chk(rays_all, "rays_all"); _chk(radius_all, "radius_all")
       mip = MipArgs(radius.data_ptr(), rays_all.data_ptr(), radius_all.data_ptr(), rays_all.shape[0], base)
+    aux = None
+    if train_ws is not None:
+      _chk(train_ws, "train_ws", torch.uint8)
+      aux = RenderAux(C.sizeof(RenderAux), 0, train_ws.data_ptr(), train_ws.numel())
     with torch.cuda.device(rays.device):
-      rc = self.lib.nf_render_forward(C.byref(self.desc), _ptr(self.packed), _ptr(rays), R, _ptr(ts), T, stride,
-                                      _ptr(density_noise), _ptr(ray_time), C.byref(mip) if mip is not None else None,
-                                      _ptr(rgb), _ptr(alpha), _ptr(weights),
-                                      _lib.PRECISION[precision or self.precision], self._stream())
+      rc = self.lib.nf_render_forward_aux(C.byref(self.desc), _ptr(self.packed), _ptr(rays), R, _ptr(ts), T, stride,
+                                          _ptr(density_noise), _ptr(ray_time), C.byref(mip) if mip is not None else None,
+                                          _ptr(rgb), _ptr(alpha), _ptr(weights), C.byref(aux) if aux is not None else None,
+                                          _lib.PRECISION[precision or self.precision], self._stream())
     _lib.check(rc, "nf_render_forward")
     return rgb, alpha, weights
 
@@ -455,6 +489,7 @@ class FusedNeRF(nn.Module):
     st = self.__dict__.copy(); st["_engine"] = None; st["_engine_key"] = None
     st["alpha"] = st["weights"] = st["ts"] = None
     if "scale_post_act" in st: st["scale_post_act"] = None
+    st.pop("_scaled_basis", None); st.pop("_scaled_basis_key", None)
     return st
 
   # ---- implemented by subclasses ----
@@ -474,29 +509,46 @@ class FusedNeRF(nn.Module):
     NeRFCamera.sample_positions), so a frame needs 48 bytes of input per view instead of 24 bytes per ray."""
     return self(RenderEngine.generate_rays(cam_to_world, focal, size, crop, reference_device))
 
-  def forward(self, rays: torch.Tensor) -> torch.Tensor:
-    if not rays.is_cuda: raise RuntimeError("FusedNeRF.forward needs CUDA rays: the fused path has no CPU fallback")
-    if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-      raise NotImplementedError("backward of the fused pipeline is not built yet (SURVEY.md f-1); "
-                                "call under torch.no_grad() / model.eval()")
-    B = rays.shape[:-1]
-    flat = rays.reshape(-1, 6).to(torch.float32).contiguous()
-    # reference src/nerf.py:29-47 -- linspace on the rays' device; jitter with ONE rand[T] for all rays
-    ts = torch.linspace(self.t_near, self.t_far, steps=self.steps, device=rays.device, dtype=torch.float32)
+  def _sample_ts(self, device, n_rays: int, with_noise: bool):
+    """reference src/nerf.py:29-47 -- linspace on the rays' device; in training mode stratified jitter with ONE rand[T] shared
+    by all rays, and (src/nerf.py:347-348) randn * noise_std added to the raw density."""
+    ts = torch.linspace(self.t_near, self.t_far, steps=self.steps, device=device, dtype=torch.float32)
     noise = None
     if self.training:
       mids = 0.5 * (ts[:-1] + ts[1:])
       lower, upper = torch.cat([mids, ts[-1:]]), torch.cat([ts[:1], mids])
       ts = lower + (upper - lower) * torch.rand_like(lower)
-      if self.noise_std > 0 and self.kind == "plain":       # reference src/nerf.py:347-348
-        noise = torch.randn(flat.shape[0], self.steps, device=rays.device) * self.noise_std
+      if with_noise and self.noise_std > 0:
+        noise = torch.randn(n_rays, self.steps, device=device) * self.noise_std
+    return ts, noise
+
+  def _wants_grad(self, params) -> bool:
+    """Autograd flows to the parameters (loss.backward(), reference runner.py:820) when grad mode is on and the module is in
+    training mode -- or always / never with ``self.differentiable = True / False``.  The differentiable call stashes ~1.7 MB
+    of activations per 128 samples for the backward, so an evaluation render that forgot ``torch.no_grad()`` stays cheap."""
+    if not torch.is_grad_enabled() or not any(p.requires_grad for p in params): return False
+    d = getattr(self, "differentiable", None)
+    return self.training if d is None else bool(d)
+
+  def forward(self, rays: torch.Tensor) -> torch.Tensor:
+    if not rays.is_cuda: raise RuntimeError("FusedNeRF.forward needs CUDA rays: the fused path has no CPU fallback")
+    B = rays.shape[:-1]
+    flat = rays.reshape(-1, 6).to(torch.float32).contiguous()
+    ts, noise = self._sample_ts(rays.device, flat.shape[0], with_noise=self.kind == "plain")
     eng = self.engine()
-    eng.pack(self._param_list())
+    params = self._param_list()
     radius = None
     if self.mip_size():
       if rays.dim() != 4: raise ValueError("a Mip model needs rays[B,H,W,6]: the pixel radius differences neighbouring rows (utils.py:77-81)")
       radius = eng.ray_radii(rays.to(torch.float32).contiguous()).reshape(-1)
-    rgb, alpha, weights = eng.render(flat, ts, noise, want_weights=self.keep_weights, radius=radius)
+    if self._wants_grad(params):
+      if rays.requires_grad: raise NotImplementedError("gradients with respect to the rays (--train-parts camera) are not built")
+      if radius is not None: raise NotImplementedError("training a Mip model through the fused path is not built")
+      from .autograd import fused_render
+      rgb, alpha, weights = fused_render(eng, flat.detach(), ts, params, noise, want_weights=self.keep_weights)
+    else:
+      eng.pack(params)
+      rgb, alpha, weights = eng.render(flat, ts, noise, want_weights=self.keep_weights, radius=radius)
     self.ts = ts
     if self.keep_weights:   # the reference keeps [T,B,H,W]; these are transposed views of the [R,T] buffers
       self.alpha = alpha.reshape(*B, self.steps).movedim(-1, 0)
@@ -628,7 +680,17 @@ class FusedVolSDF(FusedNeRF):
     ps: List[torch.Tensor] = []
     for mlp in (net, self.sdf.refl.mlp):
       for lin in _linears_of(mlp): ps += [lin.weight, lin.bias]
-    if kind == "mlp": ps.append(net.enc.basis)
+    if kind == "mlp":
+      # FourierEncoder computes fourier(x, extra_scale * basis) and runner --inc-fourier-freqs grows extra_scale every step
+      # (reference src/neural_blocks.py:50-55, runner.py:826-829): pack the scaled basis
+      es = getattr(net.enc, "extra_scale", 1)
+      if isinstance(es, torch.Tensor) or float(es) != 1.0:
+        key = (float(es), net.enc.basis.data_ptr(), net.enc.basis._version)
+        if getattr(self, "_scaled_basis_key", None) != key:
+          with torch.no_grad(): self._scaled_basis = (es * net.enc.basis).to(torch.float32).contiguous()
+          self._scaled_basis_key = key
+        ps.append(self._scaled_basis)
+      else: ps.append(net.enc.basis)
     ps.append(self.scale.reshape(1) if self.scale.dim() == 0 else self.scale)
     return ps
 
@@ -697,13 +759,19 @@ class FusedDynamicNeRF(nn.Module):
     c = self.canonical
     if not rays.is_cuda: raise RuntimeError("FusedDynamicNeRF.forward needs CUDA rays: the fused path has no CPU fallback")
     if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
-      raise NotImplementedError("backward of the fused pipeline is not built yet (SURVEY.md f-1)")
+      raise NotImplementedError("training DynamicNeRF through the fused path is not built (the deformation needs d/d pts); "
+                                "call under torch.no_grad()")
     B = rays.shape[:-1]
     flat = rays.reshape(-1, 6).to(torch.float32).contiguous()
-    ts = torch.linspace(c.t_near, c.t_far, steps=c.steps, device=rays.device, dtype=torch.float32)
+    # training-mode semantics as the reference: jittered ts (nerf.py:1292-1296, perturb = 1 if self.training) and density noise
+    # when the CANONICAL NeRF is in training mode (nerf.py:347-348)
+    tr = c.training; c.training = self.training
+    try: ts, _ = c._sample_ts(rays.device, flat.shape[0], with_noise=False)
+    finally: c.training = tr
+    noise = torch.randn(flat.shape[0], c.steps, device=rays.device) * c.noise_std if (c.training and c.noise_std > 0) else None
     ray_time = t.to(torch.float32).reshape(-1, 1, 1).expand(B).reshape(-1).contiguous()        # nerf.py:1301
     eng = self.engine(); eng.pack(self._param_list())
-    rgb, alpha, weights = eng.render(flat, ts, None, want_weights=c.keep_weights, ray_time=ray_time)
+    rgb, alpha, weights = eng.render(flat, ts, noise, want_weights=c.keep_weights, ray_time=ray_time)
     c.ts = self.ts = ts
     if c.keep_weights:
       c.alpha = alpha.reshape(*B, c.steps).movedim(-1, 0); c.weights = weights.reshape(*B, c.steps).movedim(-1, 0)

