@@ -17,6 +17,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SIZE, T = 800, 128
+TRAIN_RAYS = 4096                    # rays per GPU per optimiser step of the training leg (x 128 samples = 524 288 samples)
 RAYS_PER_FRAME = SIZE * SIZE
 FLOP_PER_SAMPLE = 1_192_960          # 2 x unpadded GEMM MACs, Plain+View, I=64
 N_VIEWS = 16                         # rotated inputs: 16 x 15.4 MB of rays = 246 MB > 126 MB L2
@@ -94,6 +95,87 @@ def torch_eager_gpu_rays_per_s(dev, tile=200, reps=3):
   return tile * tile / (ms * 1e-3), f"{tile}x{tile}-ray tiles x {T} samples, eager fp32 torch ops on the GPU (oracle port), TF32 off, peak mem {torch.cuda.max_memory_allocated(dev) / 2**30:.1f} GiB"
 
 
+def train_leg(O, dev, world, rank, steps, warmup, barrier):
+  """One optimiser step of the reference's training loop (runner.py:600-602,820-824) per step, natively: training forward
+  (jittered ts, density noise, activation stash) -> MSE -> fused backward (tcgen05 dX + dW) -> ONE NCCL all-reduce of the flat
+  gradient (N > 1) -> FusedAdam.  TRAIN_RAYS rays x T samples per GPU per step (weak scaling: the global batch grows with N)."""
+  import torch
+  import torch.distributed as dist
+  import nerf_atlas_b200 as N
+  model = N.FusedPlainNeRF(steps=T, t_near=2, t_far=6, intermediate_size=64, sigmoid_kind="upshifted", precision="fp16")
+  model.load_state_dict(O.make_plain_params(1337, 64, 1.0), strict=True)          # its own copy: the render legs keep the seeded weights
+  model = model.to(dev).train()
+  opt = N.autograd.FusedAdam(model.parameters(), lr=5e-4, eps=1e-7)
+  red = N.GradientAllReducer(model.parameters())
+  g = torch.Generator().manual_seed(17 + rank)
+  n_batches = 8
+  view = O.make_rays(1, SIZE, SIZE, size=SIZE, seed=500 + rank).reshape(-1, 6)
+  batches = [view[torch.randperm(view.shape[0], generator=g)[:TRAIN_RAYS]].reshape(1, 64, 64, 6).contiguous().to(dev) for _ in range(n_batches)]
+  targets = [torch.rand(1, 64, 64, 3, generator=g).to(dev) for _ in range(n_batches)]
+  ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+  ar_ms = []
+  def step(i, timed=False):
+    opt.zero_grad(set_to_none=True)
+    out = model(batches[i % n_batches])
+    loss = ((out - targets[i % n_batches]) ** 2).sum() / 3.0            # SUM over this rank's rays; the reducer divides by the global count
+    loss.backward()
+    if timed: ev[2].record()
+    red.begin(TRAIN_RAYS, TRAIN_RAYS * world); red.finish()
+    if timed: ev[3].record()
+    opt.step()
+    return loss
+  for i in range(warmup): step(i)
+  barrier()
+  ev[0].record()
+  for i in range(steps): loss = step(warmup + i, timed=(i == steps - 1))
+  ev[1].record()
+  torch.cuda.synchronize()
+  ms = ev[0].elapsed_time(ev[1]); ar = ev[2].elapsed_time(ev[3])
+  if world > 1:
+    t = torch.tensor([ms, ar], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms, ar = float(t[0]), float(t[1])
+  barrier()
+  per = ms / steps
+  flops = 3 * FLOP_PER_SAMPLE * TRAIN_RAYS * T                          # forward + dX + dW GEMMs
+  n_par = sum(p.numel() for p in model.parameters() if p.requires_grad)
+  return {"it_per_sec": 1e3 / per, "ms_per_step": per, "rays_per_sec": world * TRAIN_RAYS * 1e3 / per, "rays_per_step_per_gpu": TRAIN_RAYS,
+          "samples_per_ray": T, "steps": steps, "achieved_tflops_per_gpu": flops / (per * 1e-3) / 1e12,
+          "allreduce_ms_per_step": ar if world > 1 else 0.0, "allreduce_bytes": 4 * n_par if world > 1 else 0,
+          "final_loss_per_ray": float(loss) / TRAIN_RAYS,
+          "what": "native training step: k_render_tc3<TRAIN> + nf_render_backward (k_composite_bwd, k_bwd_chain, k_bwd_dw, k_unpack_grads, "
+                  "k_hash_bwd_tiles) + " + ("ncclAllReduce(flat fp32 gradient) + " if world > 1 else "") + "nf_adam_step"}
+
+
+def strong_leg(eng, O, dev, world, rank, ts, steps, warmup, barrier):
+  """STRONG scaling: ONE 800x800 frame cut into `world` row-aligned ray blocks (shard_rays), every rank renders its block, the
+  RGB blocks are all-gathered (12 B/ray over NVLink) so that every rank holds the frame."""
+  import torch
+  import torch.distributed as dist
+  import nerf_atlas_b200 as N
+  frames = [O.make_rays(1, SIZE, SIZE, size=SIZE, seed=900 + v).reshape(-1, 6) for v in range(4)]
+  s, e = N.shard_rays(RAYS_PER_FRAME, rank, world, align=SIZE)
+  mine = [f[s:e].contiguous().to(dev) for f in frames]
+  rows = (RAYS_PER_FRAME // SIZE + world - 1) // world * SIZE
+  full = torch.empty(world * rows, 3, device=dev)
+  pad = torch.zeros(rows, 3, device=dev)
+  def step(i):
+    rgb = eng.render(mine[i % 4], ts, None, want_weights=False)[0]
+    pad[: e - s] = rgb
+    if world > 1: dist.all_gather_into_tensor(full, pad)
+  for i in range(warmup): step(i)
+  barrier()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for i in range(steps): step(warmup + i)
+  e1.record(); torch.cuda.synchronize()
+  ms = e0.elapsed_time(e1)
+  if world > 1:
+    t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+  barrier()
+  return {"scaling": "strong", "rays_per_sec": RAYS_PER_FRAME * steps / (ms * 1e-3), "ms_per_frame": ms / steps, "rays_per_gpu": e - s,
+          "collective": "all_gather of 12 B/ray RGB blocks" if world > 1 else None,
+          "what": "one 800x800x128 frame per step, cut into row-aligned blocks (one per GPU)"}
+
+
 def run_reference(args):
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0: return
@@ -167,6 +249,14 @@ def run_ours(args):
     ms = timed(step_resident, args.steps, args.warmup)
     ms_e2e = timed(step_e2e, args.steps, max(3, args.warmup))
   clocks = cs.summary()
+  # further legs, outside the headline's timed regions: the native training step and (N > 1) strong scaling of one frame
+  train = strong = None
+  if not args.no_train:
+    try: train = train_leg(O, dev, world, rank, steps=max(5, args.steps), warmup=3, barrier=barrier)
+    except Exception as ex: train = {"error": str(ex)[:300]}
+  if world > 1:
+    try: strong = strong_leg(eng, O, dev, world, rank, ts, steps=max(5, args.steps), warmup=3, barrier=barrier)
+    except Exception as ex: strong = {"error": str(ex)[:300]}
 
   total_rays = world * RAYS_PER_FRAME * args.steps
   value = total_rays / (ms * 1e-3)
@@ -203,7 +293,9 @@ def run_ours(args):
                    "traffic": traffic, "peak_source": peak_src,
                    "algorithmic": f"{FLOP_PER_SAMPLE} FLOP/sample x {RAYS_PER_FRAME * T} samples per launch"},
     }
-    if world == 1 and args.torch_eager_gpu:
+    if train is not None: line["train"] = train
+    if strong is not None: line["strong_scaling"] = strong
+    if world == 1 and not args.no_torch_eager_gpu:
       try:
         v, how = torch_eager_gpu_rays_per_s(dev)
         line["torch_eager_gpu"] = {"value": v, "unit": "rays/s", "sample": how, "note": "informational: reference algorithm as eager PyTorch on this GPU"}
@@ -233,7 +325,9 @@ def main():
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
   ap.add_argument("--no-cpu-baseline", action="store_true")
-  ap.add_argument("--torch-eager-gpu", action="store_true", help="also time the reference algorithm as eager PyTorch on the GPU (informational)")
+  ap.add_argument("--no-torch-eager-gpu", action="store_true", help="skip timing the reference algorithm as eager PyTorch fp32 on this GPU (the north-star's 10x denominator; ~20 s)")
+  ap.add_argument("--torch-eager-gpu", action="store_true", help="(default now; kept for compatibility)")
+  ap.add_argument("--no-train", action="store_true", help="skip the native training-step leg")
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
   if args.impl == "reference": run_reference(args)

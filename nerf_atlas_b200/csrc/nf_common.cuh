@@ -26,7 +26,8 @@ struct NfLinPlan {
   int64_t b_off;      // byte offset: fp32 bias[n_pad]
   int64_t w16_off;    // byte offset: fp16 UMMA-canonical image [K_tc/8][n_pad][8], K order = [x0 (k0_pad) | hidden]
   int64_t b16_off;    // byte offset: fp32 bias[n_pad] in tensor-path column order
-  int64_t w16h_off;   // byte offset: the same image split for a CTA pair: [rank 0..1][K_tc/8][n_pad/2][8]
+  int64_t w16h_off;   // byte offset: the same image split for a CTA pair, plus one K-step (16 rows) carrying the bias as fp16 hi / lo
+                      // halves (rows K_tc, K_tc + 1; the rest zero): [rank 0..1][(K_tc + 16)/8][n_pad/2][8]
   int64_t w16t_off;   // byte offset: the TRANSPOSED fp16 images of the backward (dX = dZ W): [n_pad/8][k0_pad][8] (x0 part, if any)
                       // followed by [n_pad/8][256][8] (hidden part, if any): the reduction dimension is the Linear's OUTPUT
 };
@@ -121,7 +122,7 @@ static inline int nf_build_plan(const nf_model_desc* d, NfPlan* p, const char** 
       L.b_off = take((int64_t)L.n_pad * sizeof(float));
       L.w16_off = take((int64_t)k_tc * L.n_pad * sizeof(__half));
       L.b16_off = take((int64_t)L.n_pad * sizeof(float));
-      L.w16h_off = take((int64_t)k_tc * L.n_pad * sizeof(__half));
+      L.w16h_off = take((int64_t)(k_tc + 16) * L.n_pad * sizeof(__half));
       L.w16t_off = take((int64_t)k_tc * L.n_pad * sizeof(__half));
     }
   }

@@ -542,10 +542,18 @@ __global__ void k_pack_fp16(const __grid_constant__ NfPlan plan, int m, int j, c
     const __half h = __float2half_rn(W[i]);
     img[(size_t)(k_tc >> 3) * (L.n_pad * 8) + n_tc * 8 + (k_tc & 7)] = h;
     const int nh = L.n_pad >> 1, rank = n_tc / nh, nl = n_tc - rank * nh;        // CTA-pair split along N
-    imgh[(size_t)rank * (k_total >> 3) * (nh * 8) + (size_t)(k_tc >> 3) * (nh * 8) + nl * 8 + (k_tc & 7)] = h;
+    imgh[(size_t)rank * ((k_total + 16) >> 3) * (nh * 8) + (size_t)(k_tc >> 3) * (nh * 8) + nl * 8 + (k_tc & 7)] = h;
   }
-  for (int n_ref = blockIdx.x * blockDim.x + threadIdx.x; n_ref < L.n; n_ref += gridDim.x * blockDim.x)
-    b16[L.is_out ? nf_out_perm(plan, m, n_ref) : n_ref] = b[n_ref];
+  for (int n_ref = blockIdx.x * blockDim.x + threadIdx.x; n_ref < L.n; n_ref += gridDim.x * blockDim.x) {
+    const int n_tc = L.is_out ? nf_out_perm(plan, m, n_ref) : n_ref;
+    b16[n_tc] = b[n_ref];
+    // the bias K-step of the pair images: rows k_total (fp16 hi) and k_total + 1 (fp16 lo) against a [1, 1, 0, ...] operand
+    const int nh = L.n_pad >> 1, rank = n_tc / nh, nl = n_tc - rank * nh;
+    const __half hi = __float2half_rn(b[n_ref]);
+    const __half lo = __float2half_rn(b[n_ref] - __half2float(hi));
+    __half* row = imgh + (size_t)rank * ((k_total + 16) >> 3) * (nh * 8) + (size_t)(k_total >> 3) * (nh * 8) + nl * 8;
+    row[0] = hi; row[1] = lo;
+  }
 }
 
 int tc_num_sms() {
@@ -648,7 +656,7 @@ cudaError_t nf_launch_pack_fp16(const NfPlan& plan, int m, int j, const float* W
   const NfLinPlan& L = plan.mlp[m].lin[j];
   cudaError_t e = cudaMemsetAsync((uint8_t*)packed + L.w16_off, 0, (size_t)(L.k0_pad + L.k_hidden) * L.n_pad * sizeof(__half), st);
   if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync((uint8_t*)packed + L.w16h_off, 0, (size_t)(L.k0_pad + L.k_hidden) * L.n_pad * sizeof(__half), st);
+  e = cudaMemsetAsync((uint8_t*)packed + L.w16h_off, 0, (size_t)(L.k0_pad + L.k_hidden + 16) * L.n_pad * sizeof(__half), st);
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync((uint8_t*)packed + L.b16_off, 0, (size_t)L.n_pad * sizeof(float), st);
   if (e != cudaSuccess) return e;

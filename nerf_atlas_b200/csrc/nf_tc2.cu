@@ -235,7 +235,7 @@ k_render_tc2(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc2Pro
       for (int j = 0; j < plan.mlp[m].n_lin; ++j) {
         const NfLinPlan& L = plan.mlp[m].lin[j];
         const int steps = (L.k0_pad + L.k_hidden) >> 4, nh = L.n_pad >> 1;
-        const int64_t half_bytes = (int64_t)(L.k0_pad + L.k_hidden) * nh * 2;
+        const int64_t half_bytes = (int64_t)(L.k0_pad + L.k_hidden + 16) * nh * 2;     // the pair images end in a bias K-step (nf_tc3.cu); unused here
         for (int c = 0; c < L.n_chunks; ++c, ++nc)
           s.chunks[nc] = make_uint2((uint32_t)(L.w16h_off + crank * half_bytes + (int64_t)c * (2 * SPC) * nh * 16),
                                     (uint32_t)min(SPC, steps - SPC * c) * 2u * (uint32_t)nh * 16u);

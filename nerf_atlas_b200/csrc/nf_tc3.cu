@@ -33,6 +33,17 @@
 namespace {
 using namespace nf_ptx;
 
+// Biases ride in the MMA: every Linear's weight image carries one extra K-step (16 rows: fp16 hi and lo halves of the fp32 bias,
+// then zeros) that is multiplied with a constant [1, 1, 0, ...] block, so the accumulator already holds W x + b and no epilogue
+// adds (or loads) a bias.  NF_BIAS_IN_MMA=0 builds the earlier form (bias added by the epilogue warps from shared memory) for A/B.
+#ifndef NF_BIAS_IN_MMA
+#define NF_BIAS_IN_MMA 1
+#endif
+#if NF_BIAS_IN_MMA
+#define ADDB(x, i) (x)
+#else
+#define ADDB(x, i) ((x) + bias[i])
+#endif
 constexpr int X0K = 80;
 constexpr int RING_BYTES = 48 * 1024;                       // weight ring per CTA: NST stages of SPCT K-steps (4 KB each at N = 256)
 constexpr int MAX_LIN3 = 24;
@@ -42,7 +53,11 @@ struct Tc3Smem {
   uint8_t H[2][ROWS * 256 * 2];
   uint8_t X0[2][ROWS * X0K * 2];
   uint8_t W[RING_BYTES];
+#if NF_BIAS_IN_MMA
+  uint8_t ones[2 * ROWS * 16];                               // A operand of the bias K-step: [2 K-groups][128 rows][8 halves] = [1, 1, 0, ...] per row
+#else
   float bias[2][2][256];                                     // [slot][step parity][column]
+#endif
   float sig[2][ROWS];
   float P[2][3][ROWS];                                       // NF_KIND_DYN: the deformed sample positions of the tile
   float warp_agg[2][4]; int warp_cont[2][4]; float warp_sum[2][4][4]; float carry[2][8];
@@ -153,13 +168,20 @@ __device__ __forceinline__ void epi_hidden3(uint8_t* __restrict__ H, uint32_t t_
     tmem_ld_wait();
     reg_fence16(v[u & 1]);
     if (un + NCQ < 16) tmem_ld16(t_acc + col + NCQ * 16, v[(u + 1) & 1]);
+#if !NF_BIAS_IN_MMA
     const float4* b4 = reinterpret_cast<const float4*>(bias_s + col);
+#endif
     uint32_t o[8];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
+#if NF_BIAS_IN_MMA
+      const float x0 = __uint_as_float(v[u & 1][4 * i]), x1 = __uint_as_float(v[u & 1][4 * i + 1]);
+      const float x2 = __uint_as_float(v[u & 1][4 * i + 2]), x3 = __uint_as_float(v[u & 1][4 * i + 3]);
+#else
       const float4 b = b4[i];                                 // same address in every lane: one broadcast wavefront
       const float x0 = __uint_as_float(v[u & 1][4 * i]) + b.x, x1 = __uint_as_float(v[u & 1][4 * i + 1]) + b.y;
       const float x2 = __uint_as_float(v[u & 1][4 * i + 2]) + b.z, x3 = __uint_as_float(v[u & 1][4 * i + 3]) + b.w;
+#endif
       if (ACT == NF_ACT_SIN && 2 * i < NF_SIN_POLY_PAIRS) o[2 * i] = pack_h2(sin_poly(x0), sin_poly(x1));
       else o[2 * i] = act_pack_t<ACT>(x0, x1);
       if (ACT == NF_ACT_SIN && 2 * i + 1 < NF_SIN_POLY_PAIRS) o[2 * i + 1] = pack_h2(sin_poly(x2), sin_poly(x3));
@@ -171,11 +193,17 @@ __device__ __forceinline__ void epi_hidden3(uint8_t* __restrict__ H, uint32_t t_
       uint8_t* g = gA + (col >> 3) * KG_BYTES + row * 16;
       st_global_v4(g, o[0], o[1], o[2], o[3]); st_global_v4(g + KG_BYTES, o[4], o[5], o[6], o[7]);
       if (ACT == NF_ACT_SIN && gC) {
+#if !NF_BIAS_IN_MMA
         const float4* b4c = reinterpret_cast<const float4*>(bias_s + col);
+#endif
         uint32_t c[8];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
+#if NF_BIAS_IN_MMA
+          const float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+#else
           const float4 b = b4c[i];
+#endif
           c[2 * i] = pack_h2(__cosf(__uint_as_float(v[u & 1][4 * i]) + b.x), __cosf(__uint_as_float(v[u & 1][4 * i + 1]) + b.y));
           c[2 * i + 1] = pack_h2(__cosf(__uint_as_float(v[u & 1][4 * i + 2]) + b.z), __cosf(__uint_as_float(v[u & 1][4 * i + 3]) + b.w));
         }
@@ -196,6 +224,10 @@ __device__ __forceinline__ void epi_hidden3_sin_pipelined(uint8_t* __restrict__ 
   float x[16], y[16];
   tmem_ld16(t_acc + cq * 16, v);
   tmem_ld_wait(); reg_fence16(v);
+#if NF_BIAS_IN_MMA
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[i]);
+#else
   {
     const float4* b4 = reinterpret_cast<const float4*>(bias_s + cq * 16);
 #pragma unroll
@@ -205,6 +237,7 @@ __device__ __forceinline__ void epi_hidden3_sin_pipelined(uint8_t* __restrict__ 
       x[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b.z; x[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b.w;
     }
   }
+#endif
   constexpr int MAXU = (16 + NCQ - 1) / NCQ;
 #pragma unroll
   for (int u = 0; u < MAXU; ++u) {
@@ -217,6 +250,10 @@ __device__ __forceinline__ void epi_hidden3_sin_pipelined(uint8_t* __restrict__ 
     for (int i = 0; i < 16; ++i) y[i] = mufu_sin(x[i]);                // issue the unit's sines ...
     if (more) {
       tmem_ld_wait(); reg_fence16(v);                                      // ... and prepare the next unit while they execute
+#if NF_BIAS_IN_MMA
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[i]);
+#else
       const float4* b4 = reinterpret_cast<const float4*>(bias_s + col + NCQ * 16);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -224,6 +261,7 @@ __device__ __forceinline__ void epi_hidden3_sin_pipelined(uint8_t* __restrict__ 
         x[4 * i] = __uint_as_float(v[4 * i]) + b.x; x[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b.y;
         x[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b.z; x[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b.w;
       }
+#endif
     }
     uint32_t o[8];
 #pragma unroll
@@ -419,6 +457,11 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
+#if NF_BIAS_IN_MMA
+  for (int i = threadIdx.x; i < 2 * ROWS; i += blockDim.x)
+    *reinterpret_cast<uint4*>(s.ones + i * 16) = i < ROWS ? make_uint4(0x3C003C00u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async();
+#endif
   if (threadIdx.x < prog.n_lin) {
     // the epilogue's per-Linear facts, copied once from the kernel parameters (dependent indexed constant loads cost
     // ~250 cycles each when they miss the constant cache: ~600 cycles per phase before this table existed)
@@ -450,7 +493,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
           const int kl = k - (slot ? lag : 0);
           if (kl < 0 || kl >= nsteps || (slot && single)) continue;
           const int li = slot ? li1 : li0;
-          const uint32_t steps = prog.lin[li].k0_steps + prog.lin[li].h_steps, sb = prog.lin[li].step_bytes;
+          const uint32_t steps = prog.lin[li].k0_steps + prog.lin[li].h_steps + NF_BIAS_IN_MMA, sb = prog.lin[li].step_bytes;
           const uint8_t* src = a.packed + prog.lin[li].w_off + (size_t)crank * prog.lin[li].half_bytes;
           for (uint32_t st0 = 0; st0 < steps; st0 += SPCT) {
             if (rs == p) {
@@ -484,6 +527,9 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
       const uint32_t bar_wready = smem_u32(&s.w_ready[0]), bar_wempty = smem_u32(&s.w_empty[0]);
       const uint32_t bar_a = smem_u32(&s.a_ready[0]), bar_acc = smem_u32(&s.acc_full[0]);
       const uint32_t a_lbo = (uint32_t)(KG_BYTES >> 4) << 16, kstep4 = (uint32_t)(2 * KG_BYTES) >> 4;
+#if NF_BIAS_IN_MMA
+      const uint32_t ones4 = (base4 + (uint32_t)(offsetof(Tc3Smem, ones) >> 4)) | a_lbo;
+#endif
       int li0 = 0, li1 = 0;
       bool w_ok = false;                               // ring stage `stage` is known to be full
       const bool no_mma = (a.debug & 2) != 0;
@@ -496,7 +542,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
           const int li = slot ? li1 : li0;
           const uint4 r0 = *reinterpret_cast<const uint4*>(&prog.lin[li].k0_steps);
           const uint32_t bhi = prog.lin[li].bhi;
-          const uint32_t k0s = r0.x, total = r0.x + r0.y, idesc = r0.z, bstep4 = r0.w;
+          const uint32_t k0s = r0.x, kend = r0.x + r0.y, total = kend + NF_BIAS_IN_MMA, idesc = r0.z, bstep4 = r0.w;   // steps [kend, total): the bias step
           ST_ADD(2);
           mbar_wait(bar_a + slot * 8u, (a_par >> slot) & 1u); a_par ^= 1u << slot;
           ST_ADD(0);
@@ -514,7 +560,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
             const uint32_t b4 = (w4 + stage * (uint32_t)(STAGE_BYTES >> 4)) | bhi;
             if (no_mma) {
               // timing experiment (NF_TC_DEBUG & 2): every barrier and copy, but no tensor work
-            } else if (gs0 + SPCT <= total && (gs0 + SPCT <= k0s || gs0 >= k0s)) {
+            } else if (gs0 + SPCT <= k0s || (gs0 >= k0s && gs0 + SPCT <= kend)) {
               // fast path: a full chunk fed from one buffer -> back-to-back MMAs, operands differ by constants
               const uint32_t a4 = gs0 < k0s ? x4 + gs0 * kstep4 : h4 + (gs0 - k0s) * kstep4;
               umma2_f16(d_tmem, umma_desc_lo(a4), umma_desc_lo(b4), idesc, gs0 > 0 ? 1u : 0u);
@@ -525,7 +571,11 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
               const uint32_t nst = total - gs0 < (uint32_t)SPCT ? total - gs0 : (uint32_t)SPCT;
               for (uint32_t i = 0; i < nst; ++i) {
                 const uint32_t gs = gs0 + i;
+#if NF_BIAS_IN_MMA
+                const uint32_t a4 = gs < k0s ? x4 + gs * kstep4 : gs < kend ? h4 + (gs - k0s) * kstep4 : ones4;
+#else
                 const uint32_t a4 = gs < k0s ? x4 + gs * kstep4 : h4 + (gs - k0s) * kstep4;
+#endif
                 umma2_f16(d_tmem, umma_desc_lo(a4), umma_desc_lo(b4 + i * bstep4), idesc, gs > 0 ? 1u : 0u);
               }
             }
@@ -561,6 +611,9 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
         const bool has_next = kl < nsteps;              // Linear j of this slot runs after this phase
         const int comp_cq = (NCQ / 2) * slot, tail_cq = comp_cq + 1;
         // bias of Linear j (consumed by this slot's NEXT phase): in flight across the acc_full wait
+#if NF_BIAS_IN_MMA
+        const float* bias = nullptr; (void)bias;
+#else
         float bnext = 0.f; bool bload = false;
         if (has_next) {
           const int4 Ln = s.lin[j][0];
@@ -568,6 +621,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
           if (bload) bnext = __ldg(reinterpret_cast<const float*>(a.packed + (uint32_t)Ln.y) + e_tid);
         }
         const float* bias = s.bias[slot][(kl & 1) ^ 1];   // bias of the Linear whose result this phase consumes
+#endif
         if (kl > 0) {
           ST_ADD(5);
           wait_acc(smem_u32(&s.acc_full[slot]), (acc_par >> slot) & 1u, a.debug);
@@ -589,10 +643,10 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
             tc_fence_before();
             float cr, cg, cb;
             if (plan.kind == NF_KIND_TINY) {
-              s.sig[slot][row] = __uint_as_float(v[0]) + bias[0];
-              cr = __uint_as_float(v[1]) + bias[1]; cg = __uint_as_float(v[2]) + bias[2]; cb = __uint_as_float(v[3]) + bias[3];
+              s.sig[slot][row] = ADDB(__uint_as_float(v[0]), 0);
+              cr = ADDB(__uint_as_float(v[1]), 1); cg = ADDB(__uint_as_float(v[2]), 2); cb = ADDB(__uint_as_float(v[3]), 3);
             } else {
-              cr = __uint_as_float(v[0]) + bias[0]; cg = __uint_as_float(v[1]) + bias[1]; cb = __uint_as_float(v[2]) + bias[2];
+              cr = ADDB(__uint_as_float(v[0]), 0); cg = ADDB(__uint_as_float(v[1]), 1); cb = ADDB(__uint_as_float(v[2]), 2);
             }
             if (TRAIN) {
               long long ray; int t;
@@ -649,7 +703,9 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
                 for (int g = 1; g < (plan.mlp[first_m].k0_pad >> 3); ++g) st_v4(X0 + g * KG_BYTES + row * 16, 0, 0, 0, 0);
               }
             }
+#if !NF_BIAS_IN_MMA
             if (bload) { s.bias[slot][kl & 1][e_tid] = bnext; __threadfence_block(); }   // for this slot's next phase
+#endif
             tc_fence_before();
             fence_proxy_async();
             __syncwarp();
@@ -715,19 +771,19 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
               px = nf_pt(__ldg(rr + 0), tt, __ldg(rr + 3)); py = nf_pt(__ldg(rr + 1), tt, __ldg(rr + 4)); pz = nf_pt(__ldg(rr + 2), tt, __ldg(rr + 5));
               const int nsp = plan.spline_points;
               if (nsp == 0) {
-                const float dp = __uint_as_float(v[0]) + bias[0];
-                px += dp * nf_sigmoid((__uint_as_float(v[1]) + bias[1]) / 2.f);
-                py += dp * nf_sigmoid((__uint_as_float(v[2]) + bias[2]) / 2.f);
-                pz += dp * nf_sigmoid((__uint_as_float(v[3]) + bias[3]) / 2.f);
+                const float dp = ADDB(__uint_as_float(v[0]), 0);
+                px += dp * nf_sigmoid(ADDB(__uint_as_float(v[1]), 1) / 2.f);
+                py += dp * nf_sigmoid(ADDB(__uint_as_float(v[2]), 2) / 2.f);
+                pz += dp * nf_sigmoid(ADDB(__uint_as_float(v[3]), 3) / 2.f);
               } else {
-                const float rig = nf_sigmoid((__uint_as_float(v[0]) + bias[0]) / 2.f);
+                const float rig = nf_sigmoid(ADDB(__uint_as_float(v[0]), 0) / 2.f);
                 const float time = __ldg(a.ray_time + ray);
                 float d[3];
 #pragma unroll
                 for (int x = 0; x < 3; ++x) {
                   float ps[8];
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) ps[i] = i < nsp ? __uint_as_float(v[1 + 3 * i + x]) + bias[1 + 3 * i + x] : 0.f;
+                  for (int i = 0; i < 8; ++i) ps[i] = i < nsp ? ADDB(__uint_as_float(v[1 + 3 * i + x]), 1 + 3 * i + x) : 0.f;
                   d[x] = nf_bezier(ps, nsp, time) * rig;
                 }
                 px += d[0]; py += d[1]; pz += d[2];
@@ -769,11 +825,11 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
                 uint32_t o[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                  o[i] = pack_h2(__uint_as_float(v[2 * i]) + bias[un * 16 + 2 * i], __uint_as_float(v[2 * i + 1]) + bias[un * 16 + 2 * i + 1]);
+                  o[i] = pack_h2(ADDB(__uint_as_float(v[2 * i]), un * 16 + 2 * i), ADDB(__uint_as_float(v[2 * i + 1]), un * 16 + 2 * i + 1));
                 uint8_t* d0 = X0 + (un * 2) * KG_BYTES + row * 16;
                 st_v4(d0, o[0], o[1], o[2], o[3]); st_v4(d0 + KG_BYTES, o[4], o[5], o[6], o[7]);
               } else {
-                s.sig[slot][row] = __uint_as_float(v[0]) + bias[plan.intermediate];
+                s.sig[slot][row] = ADDB(__uint_as_float(v[0]), plan.intermediate);
                 if (!pos_head) {
                   long long u; int sub; unit_of(P, slot, map.tpr, nslot, u, sub);
                   long long ray; int t;
@@ -796,7 +852,9 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
               }
             }
           }
+#if !NF_BIAS_IN_MMA
           if (bload) { s.bias[slot][kl & 1][e_tid] = bnext; __threadfence_block(); }     // for this slot's next phase
+#endif
           tc_fence_before();
           fence_proxy_async();
           __syncwarp();
@@ -838,7 +896,7 @@ bool build_prog3(const NfPlan& plan, Tc3Prog* P) {
       R.idesc = (1u << 4) | ((uint32_t)(L.n_pad >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);   // M = 256 across the pair
       R.bstep4 = (2u * b_lbo) >> 4; R.bhi = (b_lbo >> 4) << 16;
       R.mj = (uint32_t)(m * 16 + j);
-      const int64_t half_bytes = (int64_t)(L.k0_pad + L.k_hidden) * nh * 2;
+      const int64_t half_bytes = (int64_t)(L.k0_pad + L.k_hidden + 16) * nh * 2;     // + the bias K-step
       if (L.w16h_off + 2 * half_bytes >= (1LL << 32)) return false;
       R.w_off = (uint32_t)L.w16h_off; R.half_bytes = (uint32_t)half_bytes; R.step_bytes = 2u * b_lbo;
     }

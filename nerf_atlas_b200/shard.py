@@ -78,36 +78,39 @@ class GradientAllReducer:
   def _world(self) -> int:
     return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
 
-  def begin(self, n_local_rays: int):
-    """Call after backward of the local SUM loss.  n_local_rays = rays this rank contributed to the step."""
+  def _layout(self):
+    """Slots padded to 4 floats so that every gradient view stays 16-byte aligned (nf_adam_step's requirement)."""
+    offs, off = [], 0
+    for p in self.params:
+      offs.append(off); off += (p.numel() + 3) // 4 * 4
+    return offs, off
+
+  def begin(self, n_local_rays: int, n_global_rays: Optional[int] = None):
+    """Call after backward of the local SUM loss.  n_local_rays = rays this rank contributed to the step; n_global_rays (optional)
+    = the step's total over all ranks when the caller knows it (deterministic shards): ``finish`` then needs no host read-back."""
     ps = self.params
     if not ps: return
     dev = ps[0].device
-    total = sum(p.numel() for p in ps)
-    if self._flat is None or self._flat.numel() != total + 1 or self._flat.device != dev:
-      self._flat = torch.empty(total + 1, dtype=torch.float32, device=dev)     # last element carries the ray count
-    off = 0
-    for p in ps:
-      n = p.numel()
-      if p.grad is None: self._flat[off:off + n].zero_()
-      else: self._flat[off:off + n].copy_(p.grad.reshape(-1))
-      off += n
-    self._flat[total] = float(n_local_rays)
+    offs, total = self._layout()
+    if self._flat is None or self._flat.numel() != total + 4 or self._flat.device != dev:
+      self._flat = torch.zeros(total + 4, dtype=torch.float32, device=dev)      # [g_0 | g_1 | ... | ray count]
+      self._views = [self._flat[o:o + p.numel()].view(p.shape) for o, p in zip(offs, ps)]
+    have = [(v, p.grad) for v, p in zip(self._views, ps) if p.grad is not None and p.grad.data_ptr() != v.data_ptr()]
+    if have: torch._foreach_copy_([v for v, _ in have], [g for _, g in have])   # batched copy into the bucket
+    for v, p in zip(self._views, ps):
+      if p.grad is None: v.zero_()
+    self._flat[total:].fill_(float(n_local_rays))
+    self._n_global, self._total = n_global_rays, total
     if self._world() > 1: self._work = dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
   def finish(self) -> int:
-    """Waits for the all-reduce; p.grad <- (sum over ranks of local grads) / (global ray count).  Returns that count."""
+    """Waits for the all-reduce; p.grad <- (sum over ranks of local grads) / (global ray count).  Returns that count.
+    The gradients become VIEWS of the flat bucket (no copy back)."""
     ps = self.params
     if not ps or self._flat is None: return 0
     if self._work is not None: self._work.wait(); self._work = None
-    total = self._flat.numel() - 1
-    n_rays = float(self._flat[total].item())
-    scale = 1.0 / max(n_rays, 1.0)
-    off = 0
-    for p in ps:
-      n = p.numel()
-      g = self._flat[off:off + n].reshape(p.shape) * scale
-      if p.grad is None: p.grad = g.clone()
-      else: p.grad.copy_(g)
-      off += n
+    total = self._total
+    n_rays = float(self._n_global) if self._n_global is not None else float(self._flat[total].item())
+    self._flat[:total].mul_(1.0 / max(n_rays, 1.0))
+    for v, p in zip(self._views, ps): p.grad = v
     return int(n_rays)
