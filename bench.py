@@ -92,7 +92,27 @@ def torch_eager_gpu_rays_per_s(dev, tile=200, reps=3):
     for _ in range(reps): O.plain_forward(P, rays, ts)
     e1.record(); torch.cuda.synchronize()
   ms = e0.elapsed_time(e1) / reps
-  return tile * tile / (ms * 1e-3), f"{tile}x{tile}-ray tiles x {T} samples, eager fp32 torch ops on the GPU (oracle port), TF32 off, peak mem {torch.cuda.max_memory_allocated(dev) / 2**30:.1f} GiB"
+  how = f"{tile}x{tile}-ray tiles x {T} samples, eager fp32 torch ops on the GPU (oracle port), TF32 off, peak mem {torch.cuda.max_memory_allocated(dev) / 2**30:.1f} GiB"
+  # the same algorithm's TRAINING step (forward + autograd backward + torch.optim.Adam, runner.py:600-602,820-824) on TRAIN_RAYS rays
+  train = None
+  try:
+    Pt = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and v.numel() else v) for k, v in P.items()}
+    opt = torch.optim.Adam([v for v in Pt.values() if v.requires_grad], lr=5e-4, eps=1e-7)
+    tr_rays = rays.reshape(-1, 6)[:TRAIN_RAYS].contiguous(); tgt = torch.rand(TRAIN_RAYS, 3, device=dev)
+    def tstep():
+      opt.zero_grad(set_to_none=True)
+      loss = torch.nn.functional.mse_loss(O.plain_forward(Pt, tr_rays, ts)["out"], tgt)
+      loss.backward(); opt.step()
+    tstep(); torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps): tstep()
+    e1.record(); torch.cuda.synchronize()
+    tms = e0.elapsed_time(e1) / reps
+    train = {"it_per_sec": 1e3 / tms, "ms_per_step": tms, "rays_per_sec": TRAIN_RAYS * 1e3 / tms, "rays_per_step": TRAIN_RAYS}
+  except Exception as ex:
+    train = {"error": str(ex)[:200]}
+  torch_eager_gpu_rays_per_s.train = train
+  return tile * tile / (ms * 1e-3), how
 
 
 def train_leg(O, dev, world, rank, steps, warmup, barrier):
@@ -298,7 +318,9 @@ def run_ours(args):
     if world == 1 and not args.no_torch_eager_gpu:
       try:
         v, how = torch_eager_gpu_rays_per_s(dev)
-        line["torch_eager_gpu"] = {"value": v, "unit": "rays/s", "sample": how, "note": "informational: reference algorithm as eager PyTorch on this GPU"}
+        line["torch_eager_gpu"] = {"value": v, "unit": "rays/s", "sample": how,
+                                   "note": "the reference's algorithm as eager PyTorch fp32 on this GPU (oracle port; the unmodified reference cannot travel to the box): the denominator of the north-star's >= 10x target",
+                                   "ours_over_eager": value / v, "train": getattr(torch_eager_gpu_rays_per_s, "train", None)}
       except Exception as ex:  # e.g. out of memory at this tile size
         line["torch_eager_gpu"] = {"error": str(ex)[:200]}
     if cpu_v is not None:

@@ -7,19 +7,22 @@ import numpy as np, torch
 from oracle import nerf_oracle as O
 import test_gpu_training as TT
 
-def main(T=16, R=12, seed=91):
+def main(T=16, R=12, seed=91, sigmoid="upshifted", bg="black", with_noise=False):
+  print(f"==== T={T} R={R} seed={seed} {sigmoid} {bg} noise={with_noise}")
   P = O.make_plain_params(seed, 64, 20.0)
   rays = O.make_rays(1, 20, 20, 800, seed, 390, 390).reshape(-1, 6)[:R]
   ts = torch.linspace(2, 6, T)
-  target = torch.rand(R, 3, generator=torch.Generator().manual_seed(1))
+  gen = torch.Generator().manual_seed(1)
+  target = torch.rand(R, 3, generator=gen)
+  noise = torch.randn(T, R, generator=gen) * 0.2 if with_noise else None
   rec = []; recq = []
-  _, _, g_ref = TT.oracle_grads(P, rays, ts, target, record=rec)
+  _, _, g_ref = TT.oracle_grads(P, rays, ts, target, sigmoid, bg, noise, record=rec)
   # fp16-operand emulation: quantised forward, autograd straight through the casts
   orig = O.plain_forward
   O.plain_forward = lambda *a, **k: orig(*a, quant=torch.float16, **k)
-  try: _, _, g_q = TT.oracle_grads(P, rays, ts, target, record=recq)
+  try: _, _, g_q = TT.oracle_grads(P, rays, ts, target, sigmoid, bg, noise, record=recq)
   finally: O.plain_forward = orig
-  eng, lay, ws, rgb, grads = TT.run_native(P, rays, ts, target)
+  eng, lay, ws, rgb, grads = TT.run_native(P, rays, ts, target, sigmoid, bg, noise)
   n_tiles = int(lay.n_tiles)
   S = float(ws[lay.scale_off: lay.scale_off + 4].view(torch.float32).item())
   print("scale", S, "tiles", n_tiles)
@@ -42,5 +45,7 @@ def main(T=16, R=12, seed=91):
     print(f"{name:28s} rel-max-err vs fp32 {e32:.2e}  vs fp16-emulation {e16:.2e}  cos {cos:.6f}  finite {bool(torch.isfinite(g).all())}")
 
 if __name__ == "__main__":
-  main()
-  main(T=128, R=301, seed=1337)
+  main(T=64, R=397, seed=1337, sigmoid="thin", bg="white", with_noise=True)
+  main(T=64, R=397, seed=1337, sigmoid="upshifted", bg="white", with_noise=False)
+  main(T=64, R=397, seed=1337, sigmoid="upshifted", bg="black", with_noise=True)
+  main(T=100, R=233, seed=1337, sigmoid="fat", bg="white")

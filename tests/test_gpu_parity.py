@@ -618,6 +618,8 @@ def test_hash_encode_backward_vs_oracle_autograd(P):
   enc.backward(d_feats)
   eng = plain_engine(P, DEV, precision="fp32")
   live = [t.detach().to(DEV).requires_grad_(True) for t in tabs]
+  with pytest.raises(RuntimeError): N.autograd.hash_encode(eng, pts.to(DEV), live)      # not the tensors the engine was packed from
+  eng.pack(eng._params[:24] + live, force=True)
   feats = N.autograd.hash_encode(eng, pts.to(DEV), live)
   assert float((feats.detach().cpu() - enc.detach()).abs().max()) <= 1e-5
   feats.backward(d_feats.to(DEV))
@@ -654,6 +656,7 @@ def test_gradients_flow_end_to_end_through_native_stage_ops(P):
   lin1, lin2 = lin1.to(DEV), lin2.to(DEV)
   eng = plain_engine(P, DEV, precision="fp32")
   live = [t.detach().to(DEV).requires_grad_(True) for t in tabs]
+  eng.pack(eng._params[:24] + live, force=True)       # the encoder reads the packed snapshot: pack the tensors that get the gradients
   def loss_fn():
     sig, rgb = head(N.autograd.hash_encode(eng, pts.to(DEV), live))
     out = N.autograd.composite(eng, sig.contiguous(), rgb.contiguous(), rays.to(DEV), ts.to(DEV))
