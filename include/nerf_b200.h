@@ -48,7 +48,8 @@ enum nf_feat_act { NF_FEAT_NORMAL = 0, NF_FEAT_THIN = 1, NF_FEAT_TANH = 2, NF_FE
                    NF_FEAT_UPSHIFTED_SOFTPLUS = 9, NF_FEAT_UPSHIFTED_RELU = 10,
                    NF_FEAT_SOFTMAX = 11 /* nn.Softmax(dim=-1) over the three colour channels (utils.py:507) */ };
 /* background (reference src/nerf.py:96-109) */
-enum nf_bg { NF_BG_BLACK = 0, NF_BG_WHITE = 1 };
+enum nf_bg { NF_BG_BLACK = 0, NF_BG_WHITE = 1,
+             NF_BG_RANDOM = 2 /* random_color (nerf.py:100-103): rand * (1 - sum_{t<T-1} w_t), one draw per ray, passed in (nf_render_aux.bg_rand) */ };
 /* model family */
 enum nf_kind {
   NF_KIND_PLAIN = 0, /* density MLP -> [raw density | sdf, intermediate(I)] -> View head -> composite:
@@ -257,6 +258,16 @@ typedef struct nf_render_aux {
   int32_t struct_bytes, reserved;
   void* train_ws;            /* training forward: workspace of nf_train_layout_of(desc, n_rays, T).total_bytes bytes, 1024-aligned */
   int64_t train_ws_bytes;
+  const float* pts;          /* from_pts (reference src/nerf.py:340-361; called by DynamicNeRF 1303, render_keyframes 1317): explicit
+                                sample positions [R,T,3] (ray-major) instead of r_o + ts r_d; ts still gives the segment lengths,
+                                rays the origin / view direction.  Not with Mip, NF_KIND_DYN or a training workspace. */
+  const float* bg_rand;      /* NF_BG_RANDOM: uniform draws [R] (the reference's rand_like(summed), nerf.py:101-102) */
+  /* NF_KIND_DYN side channels the runner's regularisers and visualisations read after forward (runner.py:523-531,694-700,769,
+   * 777-781), all [R,T,C] ray-major (the reference keeps [T,B,H,W,C]): */
+  float* pts_out;            /* C = 3: the UNdeformed sample positions (model.pts) */
+  float* dp_out;             /* direct: C = 1, spline: C = 3 (model.dp; the reference's direct split names the 1-channel output dp) */
+  float* rigid_dp_out;       /* C = 3 (model.rigid_dp = dp * rigidity) */
+  float* rigidity_out;       /* direct: C = 3, spline: C = 1 (model.rigidity = sigmoid(raw / 2)) */
 } nf_render_aux;
 /* nf_render_forward with the optional extras of nf_render_aux (aux == NULL: identical to nf_render_forward). */
 int nf_render_forward_aux(const nf_model_desc* desc, const void* packed,

@@ -14,7 +14,7 @@ ENC = {"none": 0, "hash": 1, "fourier": 2}
 DENSITY = {"softplus": 0, "relu": 1, "laplace": 2}
 FEAT = {"normal": 0, "thin": 1, "tanh": 2, "cyclic": 3, "upshifted": 4, "fat": 5, "leaky_relu": 6, "relu": 7,
         "sin": 8, "upshifted_softplus": 9, "upshifted_relu": 10, "softmax": 11}
-BG = {"black": 0, "white": 1}
+BG = {"black": 0, "white": 1, "random": 2}
 KIND = {"plain": 0, "tiny": 1, "dyn": 2}
 PRECISION = {"fp32": 0, "fp16": 1}
 REFL = {"view": 0, "pos": 1}
@@ -48,7 +48,9 @@ class TrainLayout(C.Structure):
                                        "scale_off", "dw_begin", "dw_end", "total_bytes")] + [("lin", TrainLin * TRAIN_LIN_MAX)]
 
 class RenderAux(C.Structure):
-  _fields_ = [("struct_bytes", C.c_int32), ("reserved", C.c_int32), ("train_ws", C.c_void_p), ("train_ws_bytes", C.c_int64)]
+  _fields_ = [("struct_bytes", C.c_int32), ("reserved", C.c_int32), ("train_ws", C.c_void_p), ("train_ws_bytes", C.c_int64),
+              ("pts", C.c_void_p), ("bg_rand", C.c_void_p), ("pts_out", C.c_void_p), ("dp_out", C.c_void_p),
+              ("rigid_dp_out", C.c_void_p), ("rigidity_out", C.c_void_p)]
 
 EXPORTS = {
   "nf_version": (C.c_int, []),

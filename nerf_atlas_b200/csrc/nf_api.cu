@@ -185,6 +185,11 @@ int nf_render_forward_aux(const nf_model_desc* desc, const void* packed, const f
   if (n_rays < 0) return fail(NF_E_BADARG, "n_rays < 0");
   if (n_rays == 0) return 0;
   if (!packed || !rays || !ts || !rgb_out) return fail(NF_E_BADARG, "nf_render_forward: null pointer");
+  if (p.bg == NF_BG_RANDOM && !(aux && aux->bg_rand)) return fail(NF_E_BADARG, "NF_BG_RANDOM needs nf_render_aux.bg_rand (one uniform draw per ray)");
+  const bool side = aux && (aux->pts_out || aux->dp_out || aux->rigid_dp_out || aux->rigidity_out);
+  if (side && p.kind != NF_KIND_DYN && (aux->dp_out || aux->rigid_dp_out || aux->rigidity_out)) return fail(NF_E_BADARG, "dp / rigid_dp / rigidity outputs exist for NF_KIND_DYN only");
+  if (aux && aux->pts && p.kind == NF_KIND_DYN) return fail(NF_E_UNSUPPORTED, "from_pts (explicit sample positions) is not built for NF_KIND_DYN");
+  if (train && (aux->pts || p.bg == NF_BG_RANDOM)) return fail(NF_E_UNSUPPORTED, "training forward: explicit pts / random background are not built");
   if (int rc = check_ts(T, ts_ray_stride)) return rc;
   if (p.kind == NF_KIND_DYN && !ray_time) return fail(NF_E_BADARG, "nf_render_forward: ray_time is required for NF_KIND_DYN");
   if (p.mip != NF_MIP_NONE) {
@@ -195,7 +200,7 @@ int nf_render_forward_aux(const nf_model_desc* desc, const void* packed, const f
   }
   cudaError_t e;
   if (precision == NF_PREC_FP32)
-    e = nf_launch_render_fp32(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, ray_time, mip, rgb_out, alpha_out, weights_out, (cudaStream_t)stream);
+    e = nf_launch_render_fp32(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, ray_time, mip, rgb_out, alpha_out, weights_out, (cudaStream_t)stream, aux);
   else if (precision == NF_PREC_FP16_TC) {
     // The staggered paired pipeline (nf_tc3.cu) is the product path; the single-CTA pipeline (nf_tc.cu) takes the few
     // descriptors it cannot (odd hash levels, intermediate % 16 != 0).  Only NF_EXPERIMENTS builds (A/B timing,
@@ -218,7 +223,12 @@ int nf_render_forward_aux(const nf_model_desc* desc, const void* packed, const f
     else
 #endif
     if (train && pipe != 3) return fail(NF_E_UNSUPPORTED, "training forward: the staggered pipeline only");
-    e = pipe == 3 ? nf_launch_render_tc3(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, ray_time, mip, rgb_out, alpha_out, weights_out, st, train, train ? aux->train_ws : nullptr)
+    const bool want_aux = aux && (aux->pts || aux->bg_rand || side);
+    if (want_aux && pipe != 3) return fail(NF_E_UNSUPPORTED, "explicit pts / random background / side channels: staggered tensor pipeline or NF_PREC_FP32 only");
+    if (want_aux && (p.mip != NF_MIP_NONE || p.refl_kind != NF_REFL_VIEW || p.enc == NF_ENC_FOURIER) && (aux->pts || p.bg == NF_BG_RANDOM))
+      return fail(NF_E_UNSUPPORTED, "explicit pts / random background with a wide-x0 model (Mip, Positional, Fourier SDF): NF_PREC_FP32 only");
+    if (aux && aux->pts_out && p.kind != NF_KIND_DYN) return fail(NF_E_UNSUPPORTED, "pts_out on the tensor pipeline: NF_KIND_DYN only (use nf_sample_points)");
+    e = pipe == 3 ? nf_launch_render_tc3(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, ray_time, mip, rgb_out, alpha_out, weights_out, st, train, train ? aux->train_ws : nullptr, aux)
                   : nf_launch_render_tc(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, rgb_out, alpha_out, weights_out, st);
   }
   else return fail(NF_E_BADARG, "unknown precision");
@@ -269,6 +279,7 @@ int nf_composite(const nf_model_desc* desc, const void* packed, const float* sig
   if (n_rays < 0) return fail(NF_E_BADARG, "n_rays < 0");
   if (n_rays == 0) return 0;
   if (!sigma_raw || !feats || !rays || !ts || !rgb_out) return fail(NF_E_BADARG, "nf_composite: null pointer");
+  if (p.bg == NF_BG_RANDOM) return fail(NF_E_UNSUPPORTED, "nf_composite: NF_BG_RANDOM exists on the fused path only (nf_render_forward_aux)");
   if (p.density_act == NF_DENS_LAPLACE && !packed) return fail(NF_E_BADARG, "nf_composite: packed (beta) required for the Laplace density");
   if (int rc = check_ts(T, ts_ray_stride)) return rc;
   cudaError_t e = nf_launch_composite(p, packed, sigma_raw, feats, rays, n_rays, ts, T, ts_ray_stride, rgb_out, alpha_out, weights_out, (cudaStream_t)stream);
@@ -306,6 +317,7 @@ int nf_composite_backward(const nf_model_desc* desc, const void* packed, const f
   if (n_rays < 0) return fail(NF_E_BADARG, "n_rays < 0");
   if (n_rays == 0) return 0;
   if (!sigma_raw || !feats || !rays || !ts || !d_rgb || !d_sigma_raw_out || !d_feats_out) return fail(NF_E_BADARG, "nf_composite_backward: null pointer");
+  if (p.bg == NF_BG_RANDOM) return fail(NF_E_UNSUPPORTED, "nf_composite_backward: NF_BG_RANDOM is not built");
   if (p.density_act == NF_DENS_LAPLACE && !packed) return fail(NF_E_BADARG, "nf_composite_backward: packed (beta) required for the Laplace density");
   if (int rc = check_ts(T, ts_ray_stride)) return rc;
   if (T > 2048) return fail(NF_E_UNSUPPORTED, "nf_composite_backward: T <= 2048");

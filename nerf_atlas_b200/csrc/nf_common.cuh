@@ -90,7 +90,7 @@ static inline int nf_build_plan(const nf_model_desc* d, NfPlan* p, const char** 
   } else if (d->enc != NF_ENC_NONE) { *why = "unsupported encoder"; return NF_E_UNSUPPORTED; }
   if (d->density_act < 0 || d->density_act > NF_DENS_LAPLACE) { *why = "unknown density activation"; return NF_E_BADARG; }
   if (d->feat_act < 0 || d->feat_act > NF_FEAT_SOFTMAX) { *why = "unknown feature activation (enum nf_feat_act)"; return NF_E_BADARG; }
-  if (d->bg < 0 || d->bg > NF_BG_WHITE) { *why = "unknown background (enum nf_bg)"; return NF_E_BADARG; }
+  if (d->bg < 0 || d->bg > NF_BG_RANDOM) { *why = "unknown background (enum nf_bg)"; return NF_E_BADARG; }
   int64_t off = 0;
   auto take = [&](int64_t bytes) { int64_t o = off; off += (bytes + 1023) / 1024 * 1024; return o; };
   if (d->enc == NF_ENC_HASH) p->hash_off = take((int64_t)d->hash_levels * d->hash_table_size * 4 * sizeof(float));

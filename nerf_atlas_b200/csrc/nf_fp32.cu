@@ -89,6 +89,8 @@ struct RenderArgs {
   const float* noise; const float* ray_time;
   float* rgb_out; float* alpha_out; float* weights_out;
   NfMipIn mip;
+  const float* pts; const float* bg_rand;                                    // nf_render_aux: from_pts, random background
+  float* pts_out; float* dp_out; float* rigid_dp_out; float* rigidity_out;   // nf_render_aux: DynamicNeRF side channels
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -112,6 +114,8 @@ k_render_fp32(const __grid_constant__ NfPlan plan, const RenderArgs a) {
             const float* r = a.rays + ray * 6;
             const float tt = __ldg(a.ts + ray * a.ts_stride + t);
             px = nf_pt(__ldg(r + 0), tt, __ldg(r + 3)); py = nf_pt(__ldg(r + 1), tt, __ldg(r + 4)); pz = nf_pt(__ldg(r + 2), tt, __ldg(r + 5));
+            if (a.pts) { const float* pp = a.pts + (ray * a.T + t) * 3; px = __ldg(pp); py = __ldg(pp + 1); pz = __ldg(pp + 2); }   // from_pts
+            if (a.pts_out) { float* o = a.pts_out + (ray * a.T + t) * 3; o[0] = px; o[1] = py; o[2] = pz; }
           }
           s.ray[row] = ray; s.t[row] = t; s.valid[row] = ok;
           s.P[row] = px; s.P[ROWS + row] = py; s.P[2 * ROWS + row] = pz;
@@ -147,11 +151,16 @@ k_render_fp32(const __grid_constant__ NfPlan plan, const RenderArgs a) {
         const int ob = mlp_fp32(plan.mlp[2], a.packed, s);
         if (tid < ROWS) {
           const float* O = s.H[ob]; const int row = tid;
+          const long long sidx = s.valid[row] ? s.ray[row] * a.T + s.t[row] : -1;
           if (plan.spline_points == 0) {
             const float dp = O[row];
-            s.P[row] += dp * nf_sigmoid(O[1 * ROWS + row] / 2.f);
-            s.P[ROWS + row] += dp * nf_sigmoid(O[2 * ROWS + row] / 2.f);
-            s.P[2 * ROWS + row] += dp * nf_sigmoid(O[3 * ROWS + row] / 2.f);
+            const float r0 = nf_sigmoid(O[1 * ROWS + row] / 2.f), r1 = nf_sigmoid(O[2 * ROWS + row] / 2.f), r2 = nf_sigmoid(O[3 * ROWS + row] / 2.f);
+            s.P[row] += dp * r0; s.P[ROWS + row] += dp * r1; s.P[2 * ROWS + row] += dp * r2;
+            if (sidx >= 0) {
+              if (a.dp_out) a.dp_out[sidx] = dp;
+              if (a.rigidity_out) { float* o = a.rigidity_out + sidx * 3; o[0] = r0; o[1] = r1; o[2] = r2; }
+              if (a.rigid_dp_out) { float* o = a.rigid_dp_out + sidx * 3; o[0] = dp * r0; o[1] = dp * r1; o[2] = dp * r2; }
+            }
           } else {
             const int n = plan.spline_points;
             const float rig = nf_sigmoid(O[row] / 2.f);
@@ -161,8 +170,14 @@ k_render_fp32(const __grid_constant__ NfPlan plan, const RenderArgs a) {
               float ps[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) ps[i] = i < n ? O[(1 + 3 * i + x) * ROWS + row] : 0.f;
-              s.P[x * ROWS + row] += nf_bezier(ps, n, tt) * rig;
+              const float d = nf_bezier(ps, n, tt);
+              s.P[x * ROWS + row] += d * rig;
+              if (sidx >= 0) {
+                if (a.dp_out) a.dp_out[sidx * 3 + x] = d;
+                if (a.rigid_dp_out) a.rigid_dp_out[sidx * 3 + x] = d * rig;
+              }
             }
+            if (sidx >= 0 && a.rigidity_out) a.rigidity_out[sidx] = rig;
           }
         }
         __syncthreads();
@@ -278,7 +293,8 @@ k_render_fp32(const __grid_constant__ NfPlan plan, const RenderArgs a) {
             if (a.weights_out) a.weights_out[ray * a.T + t] = w;
           }
           if (sub == map.tpr - 1) {
-            const float skyv = plan.bg == NF_BG_WHITE ? 1.f - wsum : 0.f;
+            float skyv = plan.bg == NF_BG_WHITE ? 1.f - wsum : 0.f;
+            if (plan.bg == NF_BG_RANDOM && a.bg_rand) skyv = __ldg(a.bg_rand + ray) * (1.f - wsum);      // random_color (nerf.py:100-103)
             a.rgb_out[ray * out_ch + 0] = cr + skyv; a.rgb_out[ray * out_ch + 1] = cg + skyv; a.rgb_out[ray * out_ch + 2] = cb + skyv;
           } else { s.carry[0] = trans; s.carry[1] = cr; s.carry[2] = cg; s.carry[3] = cb; s.carry[4] = wsum; }
         }
@@ -571,7 +587,7 @@ cudaError_t nf_launch_ray_radii(const float* rays, int64_t B, int H, int W, floa
 
 cudaError_t nf_launch_render_fp32(const NfPlan& plan, const void* packed, const float* rays, int64_t n_rays, const float* ts,
                                   int T, int64_t ts_stride, const float* noise, const float* ray_time, const nf_mip_args* mip,
-                                  float* rgb, float* alpha, float* weights, cudaStream_t st) {
+                                  float* rgb, float* alpha, float* weights, cudaStream_t st, const nf_render_aux* aux) {
   static_assert(sizeof(Fp32Smem) <= 227 * 1024, "fp32 pipeline smem");
   cudaError_t e = cudaFuncSetAttribute(k_render_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Fp32Smem));
   if (e != cudaSuccess) return e;
@@ -586,6 +602,11 @@ cudaError_t nf_launch_render_fp32(const NfPlan& plan, const void* packed, const 
     if (plan.mip == NF_MIP_CYLINDER_REF && (!mip->rays_all || !mip->radius_all || mip->ray_base < 0 || mip->ray_base + n_rays > mip->n_rays_all))
       return cudaErrorInvalidValue;
   }
+  if (aux) {
+    a.pts = aux->pts; a.bg_rand = aux->bg_rand;
+    a.pts_out = aux->pts_out; a.dp_out = aux->dp_out; a.rigid_dp_out = aux->rigid_dp_out; a.rigidity_out = aux->rigidity_out;
+  }
+  if (plan.bg == NF_BG_RANDOM && !a.bg_rand) return cudaErrorInvalidValue;
   k_render_fp32<<<grid, THREADS, sizeof(Fp32Smem), st>>>(plan, a);
   return cudaGetLastError();
 }

@@ -6,7 +6,7 @@ cudaError_t nf_launch_pack_fp32(const float* W, const float* b, float* Wt, float
 cudaError_t nf_launch_pack_fp16(const NfPlan& plan, int m, int j, const float* W, const float* b, void* packed, cudaStream_t st);
 cudaError_t nf_launch_render_fp32(const NfPlan& plan, const void* packed, const float* rays, int64_t n_rays, const float* ts,
                                   int T, int64_t ts_stride, const float* noise, const float* ray_time, const nf_mip_args* mip,
-                                  float* rgb, float* alpha, float* weights, cudaStream_t st);
+                                  float* rgb, float* alpha, float* weights, cudaStream_t st, const nf_render_aux* aux = nullptr);
 cudaError_t nf_launch_generate_rays(const float* c2w, int64_t B, float focal, int size, int top, int left, int H, int W, int recip,
                                     float* out, cudaStream_t st);
 cudaError_t nf_launch_ray_radii(const float* rays, int64_t B, int H, int W, float* out, cudaStream_t st);
@@ -29,7 +29,8 @@ cudaError_t nf_launch_render_tc2(const NfPlan& plan, const void* packed, const f
 const char* nf_tc3_unsupported(const NfPlan& plan);
 cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const float* rays, int64_t n_rays, const float* ts,
                                  int T, int64_t ts_stride, const float* noise, const float* ray_time, const nf_mip_args* mip,
-                                 float* rgb, float* alpha, float* weights, cudaStream_t st, const NfTrainPlan* train = nullptr, void* ws = nullptr);
+                                 float* rgb, float* alpha, float* weights, cudaStream_t st, const NfTrainPlan* train = nullptr, void* ws = nullptr,
+                                 const nf_render_aux* aux = nullptr);
 // training (nf_tc3.cu TRAIN instantiation + nf_train.cu): transposed weight images, the backward of the MLP chain on tcgen05
 const char* nf_train_unsupported(const NfPlan& plan);
 cudaError_t nf_launch_pack_w16t(const NfPlan& plan, int m, int j, const float* W, void* packed, cudaStream_t st);

@@ -93,6 +93,9 @@ struct Tc3Args {
   int debug;          // NF_TC_DEBUG (timing experiments): 256 = poll acc_full with backoff, 512 = try_wait with a short suspend hint
   NfMipIn mip;        // Mip encoder inputs (plan.mip != NF_MIP_NONE)
   uint8_t* ws;        // TRAIN: the training workspace (activation stash)
+  const float* pts;   // AUX: explicit sample positions [R,T,3] (from_pts, reference nerf.py:340-361) instead of r_o + ts r_d
+  const float* bg_rand;   // AUX / DYN: NF_BG_RANDOM draws [R]
+  float* pts_out; float* dp_out; float* rigid_dp_out; float* rigidity_out;   // DYN side channels (runner.py:694-700,769,777-781)
   long long* stats;   // NF_TC_STATS builds: time-in-state counters of CTA 0 (issuer, producer 0, epilogue warps 0 and 15)
 };
 
@@ -407,7 +410,8 @@ __device__ __forceinline__ void composite_tile3(Tc3Smem& s, int slot, const NfPl
     const long long r = u * map.rpu + rl;
     if (ends) {
       if (r < a.n_rays) {
-        const float skyv = plan.bg == NF_BG_WHITE ? 1.f - o3 : 0.f;
+        float skyv = plan.bg == NF_BG_WHITE ? 1.f - o3 : 0.f;
+        if (plan.bg == NF_BG_RANDOM && a.bg_rand) skyv = __ldg(a.bg_rand + r) * (1.f - o3);      // random_color (nerf.py:100-103)
         a.rgb_out[r * 3 + 0] = o0 + skyv; a.rgb_out[r * 3 + 1] = o1 + skyv; a.rgb_out[r * 3 + 2] = o2 + skyv;
       }
     } else {
@@ -428,7 +432,9 @@ __device__ __forceinline__ void composite_tile3(Tc3Smem& s, int slot, const NfPl
 // DYN: the DynamicNeRF chain (deformation-out epilogue, Bezier, re-encode) is compiled in; same reason.
 // TRAIN: the training forward -- every Linear's input operand (+ cos for sin MLPs) and the raw density / colours of every
 // sample are stashed in the training workspace for nf_render_backward (nf_train.cu).
-template <int NST, int SPCT, int NCQ, bool WIDE, bool DYN, bool TRAIN = false>
+// AUX: explicit sample positions (from_pts) and the random background are compiled in (kept out of the common instantiation for
+// the same reason as WIDE / DYN).
+template <int NST, int SPCT, int NCQ, bool WIDE, bool DYN, bool TRAIN = false, bool AUX = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (4 * NCQ + NST + 1), 1)
 k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Prog prog, const Tc3Args a, const __grid_constant__ Tc3Train tr) {
   static_assert(NST * SPCT * 4096 == RING_BYTES && NST <= MAX_STAGES3, "ring geometry");
@@ -666,6 +672,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
               const float* rr = a.rays + ray * 6;
               const float tt = __ldg(a.ts + ray * a.ts_stride + t);
               px = nf_pt(__ldg(rr + 0), tt, __ldg(rr + 3)); py = nf_pt(__ldg(rr + 1), tt, __ldg(rr + 4)); pz = nf_pt(__ldg(rr + 2), tt, __ldg(rr + 5));
+              if (AUX && a.pts) { const float* pp = a.pts + (ray * a.T + t) * 3; px = __ldg(pp); py = __ldg(pp + 1); pz = __ldg(pp + 2); }
             }
             // x0 of the FIRST MLP of the path: the density MLP, or (NF_KIND_DYN) the deformation MLP.  4 threads per row share
             // the hash levels; when the cq == 0 warps are compositing, the other three take them all
@@ -770,11 +777,20 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
               const float tt = __ldg(a.ts + ray * a.ts_stride + t);
               px = nf_pt(__ldg(rr + 0), tt, __ldg(rr + 3)); py = nf_pt(__ldg(rr + 1), tt, __ldg(rr + 4)); pz = nf_pt(__ldg(rr + 2), tt, __ldg(rr + 5));
               const int nsp = plan.spline_points;
+              const bool side = cq == tail_cq;                      // one warp per lane quarter writes the side channels
+              const long long sidx = ray * a.T + t;
+              if (side && a.pts_out) { float* o = a.pts_out + sidx * 3; o[0] = px; o[1] = py; o[2] = pz; }
               if (nsp == 0) {
                 const float dp = ADDB(__uint_as_float(v[0]), 0);
-                px += dp * nf_sigmoid(ADDB(__uint_as_float(v[1]), 1) / 2.f);
-                py += dp * nf_sigmoid(ADDB(__uint_as_float(v[2]), 2) / 2.f);
-                pz += dp * nf_sigmoid(ADDB(__uint_as_float(v[3]), 3) / 2.f);
+                const float r0 = nf_sigmoid(ADDB(__uint_as_float(v[1]), 1) / 2.f), r1 = nf_sigmoid(ADDB(__uint_as_float(v[2]), 2) / 2.f),
+                            r2 = nf_sigmoid(ADDB(__uint_as_float(v[3]), 3) / 2.f);
+                px += dp * r0; py += dp * r1; pz += dp * r2;
+                if (side) {
+                  // the reference's split names the 1-channel output dp and the 3-channel one rigidity (nerf.py:1231,1261-1266)
+                  if (a.dp_out) a.dp_out[sidx] = dp;
+                  if (a.rigidity_out) { float* o = a.rigidity_out + sidx * 3; o[0] = r0; o[1] = r1; o[2] = r2; }
+                  if (a.rigid_dp_out) { float* o = a.rigid_dp_out + sidx * 3; o[0] = dp * r0; o[1] = dp * r1; o[2] = dp * r2; }
+                }
               } else {
                 const float rig = nf_sigmoid(ADDB(__uint_as_float(v[0]), 0) / 2.f);
                 const float time = __ldg(a.ray_time + ray);
@@ -784,9 +800,14 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
                   float ps[8];
 #pragma unroll
                   for (int i = 0; i < 8; ++i) ps[i] = i < nsp ? ADDB(__uint_as_float(v[1 + 3 * i + x]), 1 + 3 * i + x) : 0.f;
-                  d[x] = nf_bezier(ps, nsp, time) * rig;
+                  d[x] = nf_bezier(ps, nsp, time);
                 }
-                px += d[0]; py += d[1]; pz += d[2];
+                if (side) {
+                  if (a.dp_out) { float* o = a.dp_out + sidx * 3; o[0] = d[0]; o[1] = d[1]; o[2] = d[2]; }
+                  if (a.rigidity_out) a.rigidity_out[sidx] = rig;
+                  if (a.rigid_dp_out) { float* o = a.rigid_dp_out + sidx * 3; o[0] = d[0] * rig; o[1] = d[1] * rig; o[2] = d[2] * rig; }
+                }
+                px += d[0] * rig; py += d[1] * rig; pz += d[2] * rig;
               }
             }
             if (cq == tail_cq) { s.P[slot][0][row] = px; s.P[slot][1][row] = py; s.P[slot][2][row] = pz; }
@@ -840,6 +861,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
                     const float dx = __ldg(rr + 3), dy = __ldg(rr + 4), dz = __ldg(rr + 5);
                     if (DYN && plan.kind == NF_KIND_DYN) { px = s.P[slot][0][row]; py = s.P[slot][1][row]; pz = s.P[slot][2][row]; }
                     else { px = nf_pt(__ldg(rr + 0), tt, dx); py = nf_pt(__ldg(rr + 1), tt, dy); pz = nf_pt(__ldg(rr + 2), tt, dz); }
+                    if (AUX && a.pts) { const float* pp = a.pts + (ray * a.T + t) * 3; px = __ldg(pp); py = __ldg(pp + 1); pz = __ldg(pp + 2); }
                     nf_elaz(dx, dy, dz, el, az);
                   }
                   uint8_t* d0 = X0 + (iu * 2) * KG_BYTES + row * 16;
@@ -940,17 +962,25 @@ const char* nf_train_unsupported(const NfPlan& p) {
   if (p.mip != NF_MIP_NONE || p.refl_kind != NF_REFL_VIEW || p.enc == NF_ENC_FOURIER) return "training: wide-x0 models (Mip, Positional, Fourier SDF) are not built";
   if (p.kind == NF_KIND_PLAIN && p.enc != NF_ENC_HASH) return "training: PlainNeRF needs the hash-encoded density MLP (the SIREN SDF needs d/dp)";
   if (p.density_act == NF_DENS_LAPLACE) return "training: the gradient of VolSDF's beta is not built";
+  if (p.bg == NF_BG_RANDOM) return "training: the random background is not built";
   for (int m = 0; m < p.n_mlps; ++m) if (p.mlp[m].act != NF_ACT_LEAKY && p.mlp[m].act != NF_ACT_SIN) return "training: LeakyReLU / sin MLPs only";
   return nullptr;
 }
 
 cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const float* rays, int64_t n_rays, const float* ts,
                                  int T, int64_t ts_stride, const float* noise, const float* ray_time, const nf_mip_args* mip,
-                                 float* rgb, float* alpha, float* weights, cudaStream_t st, const NfTrainPlan* tp, void* ws) {
+                                 float* rgb, float* alpha, float* weights, cudaStream_t st, const NfTrainPlan* tp, void* ws,
+                                 const nf_render_aux* aux) {
   if (nf_tc3_unsupported(plan)) return cudaErrorNotSupported;
   if (tp && nf_train_unsupported(plan)) return cudaErrorNotSupported;
   Tc3Args a{};
   a.ws = (uint8_t*)ws;
+  if (aux) {
+    a.pts = aux->pts; a.bg_rand = aux->bg_rand;
+    a.pts_out = aux->pts_out; a.dp_out = aux->dp_out; a.rigid_dp_out = aux->rigid_dp_out; a.rigidity_out = aux->rigidity_out;
+  }
+  const bool want_aux = a.pts != nullptr || plan.bg == NF_BG_RANDOM;
+  if (plan.bg == NF_BG_RANDOM && !a.bg_rand) return cudaErrorInvalidValue;
   a.packed = (const uint8_t*)packed; a.rays = rays; a.n_rays = n_rays; a.ts = ts; a.T = T; a.ts_stride = ts_stride;
   a.noise = noise; a.ray_time = ray_time; a.rgb_out = rgb; a.alpha_out = alpha; a.weights_out = weights;
   if (plan.kind == NF_KIND_DYN && !ray_time) return cudaErrorInvalidValue;
@@ -979,6 +1009,12 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
   if (dynk) { ring = 3; epiw = 16; }
   const bool train = tp != nullptr;
   if (train) { ring = 3; epiw = 16; }
+  if (want_aux) {
+    // from_pts / random background: the AUX instantiation of the plain two-tile kernel, or the DynamicNeRF one (background only)
+    if (wide || train || (dynk && a.pts)) return cudaErrorNotSupported;
+    ring = 3; epiw = 16;
+  }
+  const bool auxk = want_aux && !dynk;
   Tc3Train tr{};
   if (train) {
     tr.n_tiles = tp->n_tiles;
@@ -997,6 +1033,7 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
     }
   }
   const void* fn = train ? (const void*)k_render_tc3<3, 4, 4, false, false, true>
+                 : auxk ? (const void*)k_render_tc3<3, 4, 4, false, false, false, true>
                  : wide ? (const void*)k_render_tc3<3, 4, 4, true, false>
                  : dynk ? (const void*)k_render_tc3<3, 4, 4, false, true>
 #ifdef NF_EXPERIMENTS
@@ -1024,6 +1061,7 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
   a.stats = d_stats;
 #endif
   if (train) k_render_tc3<3, 4, 4, false, false, true><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
+  else if (auxk) k_render_tc3<3, 4, 4, false, false, false, true><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
   else if (wide) k_render_tc3<3, 4, 4, true, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
   else if (dynk) k_render_tc3<3, 4, 4, false, true><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
 #ifdef NF_EXPERIMENTS

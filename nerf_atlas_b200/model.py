@@ -2,8 +2,8 @@
 
 ``FusedPlainNeRF`` / ``FusedTinyNeRF`` are ``nn.Module``s that ``runner.py`` can use in place of
 ``src.nerf.PlainNeRF`` / ``TinyNeRF`` (reference src/nerf.py:278-361): same constructor keywords,
-``forward(rays[B,H,W,6]) -> rgb[B,H,W,3]``, ``from_pts`` is intentionally absent (the fused
-pipeline never materialises ``pts``), and the attributes the runner reads or writes afterwards
+``forward(rays[B,H,W,6]) -> rgb[B,H,W,3]``, the inner entry ``from_pts(pts, ts, r_o, r_d)``, autograd to the
+parameters in training mode (``loss.backward()`` runs the native backward), and the attributes the runner reads or writes afterwards
 (SURVEY.md section 8b): ``steps/t_near/t_far``, ``ts``, ``alpha``, ``weights``, ``nerf``, ``refl``,
 ``intermediate_size``, ``set_bg``, ``set_sigmoid``, ``set_refl``, ``total_latent_size``.
 Parameters keep the reference's ``state_dict`` names, so checkpoints interchange.
@@ -232,10 +232,13 @@ class RenderEngine:
 
   def render(self, rays: torch.Tensor, ts: torch.Tensor, density_noise: Optional[torch.Tensor] = None,
              want_weights: bool = True, precision: Optional[str] = None, ray_time: Optional[torch.Tensor] = None,
-             radius: Optional[torch.Tensor] = None, crop: Optional[tuple] = None, train_ws: Optional[torch.Tensor] = None):
+             radius: Optional[torch.Tensor] = None, crop: Optional[tuple] = None, train_ws: Optional[torch.Tensor] = None,
+             pts: Optional[torch.Tensor] = None, bg_rand: Optional[torch.Tensor] = None, side: Optional[dict] = None):
     """rays[R,6], ts[T] (shared) or ts[R,T] (per ray) -> rgb[R,3], alpha[R,T]|None, weights[R,T]|None.
     Mip models: ``radius[R]`` (``ray_radii``); "cylinder_ref" also takes ``crop = (rays_all[R_all,6], radius_all[R_all],
-    ray_base)`` when ``rays`` is a shard of a larger crop (default: the call's rays are the whole crop)."""
+    ray_base)`` when ``rays`` is a shard of a larger crop (default: the call's rays are the whole crop).
+    ``pts[R,T,3]``: explicit sample positions (from_pts).  ``bg_rand[R]``: the draws of the "random" background.
+    ``side`` (a dict, DynamicNeRF): filled with pts [R,T,3], dp, rigid_dp [R,T,3], rigidity (ray-major side channels)."""
     self._need_packed()
     _chk(rays, "rays"); _chk(ts, "ts")
     if rays.dim() != 2 or rays.shape[1] != 6: raise ValueError("rays must be [R,6]")
@@ -261,9 +264,26 @@ class RenderEngine:
       _chk(rays_all, "rays_all"); _chk(radius_all, "radius_all")
       mip = MipArgs(radius.data_ptr(), rays_all.data_ptr(), radius_all.data_ptr(), rays_all.shape[0], base)
     aux = None
+    if train_ws is not None or pts is not None or bg_rand is not None or side is not None:
+      aux = RenderAux(); aux.struct_bytes = C.sizeof(RenderAux)
     if train_ws is not None:
       _chk(train_ws, "train_ws", torch.uint8)
-      aux = RenderAux(C.sizeof(RenderAux), 0, train_ws.data_ptr(), train_ws.numel())
+      aux.train_ws, aux.train_ws_bytes = train_ws.data_ptr(), train_ws.numel()
+    if pts is not None:
+      _chk(pts, "pts")
+      if tuple(pts.shape) != (R, T, 3): raise ValueError("pts must be [R,T,3]")
+      aux.pts = pts.data_ptr()
+    if bg_rand is not None:
+      _chk(bg_rand, "bg_rand")
+      if bg_rand.numel() != R: raise ValueError("bg_rand must be [R]")
+      aux.bg_rand = bg_rand.data_ptr()
+    if side is not None:
+      if self.desc.kind != _lib.KIND["dyn"]: raise ValueError("side channels exist for DynamicNeRF only")
+      direct = self.desc.spline_points == 0
+      f = lambda c: torch.empty(R, T, c, dtype=torch.float32, device=rays.device)
+      side.update(pts=f(3), dp=f(1 if direct else 3), rigid_dp=f(3), rigidity=f(3 if direct else 1))
+      aux.pts_out, aux.dp_out = side["pts"].data_ptr(), side["dp"].data_ptr()
+      aux.rigid_dp_out, aux.rigidity_out = side["rigid_dp"].data_ptr(), side["rigidity"].data_ptr()
     with torch.cuda.device(rays.device):
       rc = self.lib.nf_render_forward_aux(C.byref(self.desc), _ptr(self.packed), _ptr(rays), R, _ptr(ts), T, stride,
                                           _ptr(density_noise), _ptr(ray_time), C.byref(mip) if mip is not None else None,
@@ -530,11 +550,34 @@ class FusedNeRF(nn.Module):
     d = getattr(self, "differentiable", None)
     return self.training if d is None else bool(d)
 
+  def from_pts(self, pts: torch.Tensor, ts: torch.Tensor, r_o: torch.Tensor, r_d: torch.Tensor, refl_latent=None) -> torch.Tensor:
+    """The reference's inner entry (src/nerf.py:340-361; called by DynamicNeRF.forward 1303, render_keyframes 1317, BendyNeRF
+    710): explicit sample positions ``pts[T,B,H,W,3]`` instead of r_o + ts r_d; ``ts[T]`` gives the segment lengths, ``r_d`` the
+    view direction (and the ray norm of the deltas).  Density noise is added in training mode exactly as in ``forward``."""
+    if refl_latent is not None: raise NotImplementedError("refl_latent is not supported by the fused path")
+    if self.mip_size(): raise NotImplementedError("from_pts of a Mip model")
+    if not pts.is_cuda: raise RuntimeError("FusedNeRF.from_pts needs CUDA tensors: the fused path has no CPU fallback")
+    T = pts.shape[0]; B = pts.shape[1:-1]
+    flat_pts = pts.to(torch.float32).movedim(0, -2).reshape(-1, T, 3).contiguous()         # [R,T,3]
+    rays = torch.cat([r_o.expand(*B, 3), r_d.expand(*B, 3)], dim=-1).reshape(-1, 6).to(torch.float32).contiguous()
+    R = rays.shape[0]
+    noise = torch.randn(R, T, device=pts.device) * self.noise_std if (self.training and self.noise_std > 0 and self.kind == "plain") else None
+    eng = self.engine(); params = self._param_list()
+    if self._wants_grad(params) or pts.requires_grad: raise NotImplementedError("from_pts is not differentiable on the fused path")
+    eng.pack(params)
+    bg_rand = torch.rand(R, device=pts.device) if self.bg == "random" else None
+    rgb, alpha, weights = eng.render(rays, ts.to(torch.float32).contiguous(), noise, want_weights=self.keep_weights, pts=flat_pts, bg_rand=bg_rand)
+    self.ts = ts
+    if self.keep_weights:
+      self.alpha = alpha.reshape(*B, T).movedim(-1, 0); self.weights = weights.reshape(*B, T).movedim(-1, 0)
+    return rgb.reshape(*B, 3)
+
   def forward(self, rays: torch.Tensor) -> torch.Tensor:
     if not rays.is_cuda: raise RuntimeError("FusedNeRF.forward needs CUDA rays: the fused path has no CPU fallback")
     B = rays.shape[:-1]
     flat = rays.reshape(-1, 6).to(torch.float32).contiguous()
     ts, noise = self._sample_ts(rays.device, flat.shape[0], with_noise=self.kind == "plain")
+    bg_rand = torch.rand(flat.shape[0], device=rays.device) if self.bg == "random" else None     # random_color (nerf.py:100-103)
     eng = self.engine()
     params = self._param_list()
     radius = None
@@ -544,11 +587,12 @@ class FusedNeRF(nn.Module):
     if self._wants_grad(params):
       if rays.requires_grad: raise NotImplementedError("gradients with respect to the rays (--train-parts camera) are not built")
       if radius is not None: raise NotImplementedError("training a Mip model through the fused path is not built")
+      if bg_rand is not None: raise NotImplementedError("training with the random background through the fused path is not built")
       from .autograd import fused_render
       rgb, alpha, weights = fused_render(eng, flat.detach(), ts, params, noise, want_weights=self.keep_weights)
     else:
       eng.pack(params)
-      rgb, alpha, weights = eng.render(flat, ts, noise, want_weights=self.keep_weights, radius=radius)
+      rgb, alpha, weights = eng.render(flat, ts, noise, want_weights=self.keep_weights, radius=radius, bg_rand=bg_rand)
     self.ts = ts
     if self.keep_weights:   # the reference keeps [T,B,H,W]; these are transposed views of the [R,T] buffers
       self.alpha = alpha.reshape(*B, self.steps).movedim(-1, 0)
@@ -577,7 +621,7 @@ class FusedPlainNeRF(FusedNeRF):
     FusedNeRF.__init__(self, steps=ref.steps, t_near=ref.t_near, t_far=ref.t_far, intermediate_size=ref.intermediate_size,
                        sigmoid_kind=_sigmoid_name(ref.refl.act), precision=precision, keep_weights=keep_weights,
                        mip=getattr(ref, "mip", None))
-    bg = [k for k, v in {"black": "black", "white": "white"}.items() if getattr(ref.sky_color, "__name__", "") == v]
+    bg = [k for k, v in {"black": "black", "white": "white", "random": "random_color"}.items() if getattr(ref.sky_color, "__name__", "") == v]
     if not bg: raise NotImplementedError("background kind of the reference model")
     self.bg = bg[0]
     if type(ref.refl).__name__ not in ("View", "ViewHead", "Positional", "PositionalHead"):
@@ -771,8 +815,14 @@ class FusedDynamicNeRF(nn.Module):
     noise = torch.randn(flat.shape[0], c.steps, device=rays.device) * c.noise_std if (c.training and c.noise_std > 0) else None
     ray_time = t.to(torch.float32).reshape(-1, 1, 1).expand(B).reshape(-1).contiguous()        # nerf.py:1301
     eng = self.engine(); eng.pack(self._param_list())
-    rgb, alpha, weights = eng.render(flat, ts, noise, want_weights=c.keep_weights, ray_time=ray_time)
+    side = {} if getattr(self, "keep_side", True) else None
+    bg_rand = torch.rand(flat.shape[0], device=rays.device) if c.bg == "random" else None
+    rgb, alpha, weights = eng.render(flat, ts, noise, want_weights=c.keep_weights, ray_time=ray_time, side=side, bg_rand=bg_rand)
     c.ts = self.ts = ts
+    if side is not None:
+      # what the runner's regularisers / visualisations read after forward (runner.py:523-531,694-700,769,777-781), in the
+      # reference's [T,B,H,W,C] layout (transposed views of the ray-major buffers)
+      for k, v in side.items(): setattr(self, k, v.reshape(*B, c.steps, v.shape[-1]).movedim(-2, 0))
     if c.keep_weights:
       c.alpha = alpha.reshape(*B, c.steps).movedim(-1, 0); c.weights = weights.reshape(*B, c.steps).movedim(-1, 0)
     return rgb.reshape(*B, 3)

@@ -712,3 +712,76 @@ def test_fused_adam_step_is_seen_by_the_next_render(P):
   m.engine().pack(m._param_list(), force=True)
   with torch.no_grad(): c = m(rays)
   assert torch.equal(b, c)
+
+
+# ---------------------------------------------------------------- boundary: from_pts, side channels, random background
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("fp16", 1e-3)])
+def test_from_pts_equals_forward_and_takes_arbitrary_points(P, precision, tol):
+  """PlainNeRF.from_pts (reference src/nerf.py:340-361): with the golden's own pts it must reproduce forward exactly; with
+  displaced points it must follow the oracle's from_pts."""
+  import nerf_atlas_b200 as N
+  fx, params, rays = _case("plain_t16_sharp")
+  m = N.FusedPlainNeRF(steps=int(fx["T"]), t_near=float(fx["near"]), t_far=float(fx["far"]), intermediate_size=64,
+                       sigmoid_kind=str(fx["sigmoid"]), bg=str(fx["bg"]), precision=precision)
+  m.load_state_dict(params, strict=True); m = m.to(DEV).eval()
+  with torch.no_grad():
+    out_fwd = m(rays.to(DEV))
+    w_fwd = m.weights.clone()
+    pts = torch.from_numpy(fx["pts"]).to(DEV)                      # [T,B,H,W,3], exactly what the reference's compute_pts_ts produced
+    r_o, r_d = rays[..., :3].to(DEV), rays[..., 3:].to(DEV)
+    out_pts = m.from_pts(pts, torch.from_numpy(fx["ts"]).to(DEV), r_o, r_d)
+  assert torch.equal(out_fwd, out_pts) and torch.equal(w_fwd, m.weights)
+  assert np.abs(out_pts.cpu().numpy() - fx["out"]).max() <= tol
+  # displaced points (what DynamicNeRF / render_keyframes feed it)
+  g = torch.Generator().manual_seed(0)
+  pts2 = torch.from_numpy(fx["pts"]) + 0.05 * torch.randn(fx["pts"].shape, generator=g)
+  ts = torch.from_numpy(fx["ts"])
+  with torch.no_grad():
+    ref = O.plain_from_pts(params, pts2, ts, rays[..., :3], rays[..., 3:], sigmoid=str(fx["sigmoid"]), bg=str(fx["bg"]))["out"]
+    got = m.from_pts(pts2.to(DEV), ts.to(DEV), r_o, r_d)
+  assert float((got.cpu() - ref).abs().max()) <= tol
+  assert float((got - out_fwd).abs().max()) > 1e-3
+
+
+@pytest.mark.parametrize("name,spline", [("dnerf_direct_t64", 0), ("dnerf_spline5_t32", 5)])
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_dnerf_side_channels_match_reference_golden(name, spline, precision):
+  """model.pts / dp / rigid_dp / rigidity after forward (reference src/nerf.py:1261-1303; read by runner.py:523-531,694-700,
+  769,777-781) against the values the reference itself retained (golden)."""
+  import nerf_atlas_b200 as N
+  fx = load_golden(name)
+  params = O.make_dnerf_spline_params(int(fx["seed"]), spline, 64) if spline else O.make_dnerf_params(int(fx["seed"]), 64)
+  rays = O.make_rays(int(fx["B"]), int(fx["H"]), int(fx["W"]), 800, int(fx["seed"]), int(fx["top"]), int(fx["left"]))
+  times = torch.from_numpy(fx["times"])
+  canon = N.FusedPlainNeRF(steps=int(fx["T"]), t_near=float(fx["near"]), t_far=float(fx["far"]), intermediate_size=64,
+                           sigmoid_kind=str(fx["sigmoid"]), bg=str(fx["bg"]), precision=precision)
+  m = N.FusedDynamicNeRF(canon, spline=spline)
+  m.load_state_dict(params, strict=True); m = m.to(DEV).eval()
+  with torch.no_grad(): out = m((rays.to(DEV), times.to(DEV)))
+  tol = 5e-5 if precision == "fp32" else 2e-3
+  assert np.abs(out.cpu().numpy() - fx["out"]).max() <= tol
+  pts_ref = O.compute_pts(rays, torch.from_numpy(fx["ts"]))[0]                    # bit-exact restatement of compute_pts_ts (pinned by the goldens)
+  assert tuple(m.pts.shape) == tuple(pts_ref.shape) and torch.equal(m.pts.cpu(), pts_ref)
+  rd = m.rigid_dp.cpu().numpy()
+  assert rd.shape == fx["rigid_dp"].shape
+  scale = max(float(np.abs(fx["rigid_dp"]).max()), 1e-3)
+  assert np.abs(rd - fx["rigid_dp"]).max() <= (1e-5 if precision == "fp32" else 5e-3) * scale
+  # dp * rigidity == rigid_dp, in the reference's channel layout (direct: dp 1 channel, rigidity 3; spline: dp 3, rigidity 1)
+  assert m.dp.shape[-1] == (1 if spline == 0 else 3) and m.rigidity.shape[-1] == (3 if spline == 0 else 1)
+  assert float((m.dp * m.rigidity - m.rigid_dp).abs().max()) <= 1e-6 * scale + 1e-7
+  assert float(m.rigidity.min()) > 0 and float(m.rigidity.max()) < 1
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("fp16", 1e-3)])
+def test_random_background_vs_oracle(P, precision, tol):
+  """random_color (reference src/nerf.py:100-103): rand * (1 - sum_{t<T-1} w_t), one draw per ray, passed in explicitly."""
+  import nerf_atlas_b200 as N
+  rays = O.make_rays(1, 5, 6, seed=4, crop_top=395, crop_left=395).reshape(-1, 6)
+  ts = torch.linspace(2, 6, 48)
+  u = torch.rand(rays.shape[0], generator=torch.Generator().manual_seed(2))
+  with torch.no_grad(): ref = O.plain_forward(P, rays, ts, bg="black")
+  want = ref["out"] + (u * (1 - ref["weights"][:-1].sum(0)))[:, None]
+  e = plain_engine(P, DEV, bg="random", precision=precision)
+  rgb, _, _ = e.render(rays.to(DEV), ts.to(DEV), bg_rand=u.to(DEV))
+  assert float((rgb.cpu() - want).abs().max()) <= tol
+  with pytest.raises(RuntimeError): e.render(rays.to(DEV), ts.to(DEV))          # the draws are an explicit input
