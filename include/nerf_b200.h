@@ -196,6 +196,13 @@ int nf_render_forward(const nf_model_desc* desc, const void* packed,
  * torch's CUDA kernel does when dividing by a Python scalar) -- pick the device the reference ran on. */
 int nf_generate_rays(const float* cam_to_world, int64_t B, float focal, int32_t size, int32_t top, int32_t left,
                      int32_t H, int32_t W, int32_t scalar_div_as_reciprocal, float* rays_out, void* stream);
+/* Camera rays of a DTU / IDR camera (BASELINE config 4): runner.render's pixel grid + DTUCamera.sample_positions (reference
+ * src/cameras.py:159-174,189-223): pixel (u = column, v = row) scaled by (1600, 1200) / size, lifted through the intrinsics
+ * (fx, skew, cx, fy, cy), transformed by pose[b] (4x4, camera to world), r_d = normalize(world - r_o): UNIT-norm directions.
+ * pose[B,4,4] and intrinsic[B,intr_rows,intr_cols] (>= 3x3) are DEVICE pointers.  Matches the reference camera to 1e-6 (its
+ * torch.bmm fixes no summation order, so the last bit is not pinned). */
+int nf_generate_rays_dtu(const float* pose, const float* intrinsic, int32_t intr_rows, int32_t intr_cols, int64_t B, int32_t size,
+                         int32_t top, int32_t left, int32_t H, int32_t W, float* rays_out, void* stream);
 /* radii_x (reference src/utils.py:77-81) on a crop of rays[B,H,W,6] (H >= 3): radius_out[B,H,W] = |r_d[h] - r_d[h+1]| * 2/sqrt(12),
  * the last row repeating difference H-3 exactly like the reference's `dx[:, -2:-1, :]`. */
 int nf_ray_radii(const float* rays, int64_t B, int32_t H, int32_t W, float* radius_out, void* stream);

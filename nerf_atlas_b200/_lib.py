@@ -70,6 +70,8 @@ EXPORTS = {
                                    C.c_int64, C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
   "nf_generate_rays": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_void_p, C.c_void_p]),
+  "nf_generate_rays_dtu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                     C.c_void_p, C.c_void_p]),
   "nf_ray_radii": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
   "nf_sample_points": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
   "nf_hash_encode": (C.c_int, [C.POINTER(ModelDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -245,6 +245,15 @@ int nf_generate_rays(const float* cam_to_world, int64_t B, float focal, int32_t 
   return e == cudaSuccess ? 0 : cuda_fail(e, "nf_generate_rays");
 }
 
+int nf_generate_rays_dtu(const float* pose, const float* intrinsic, int32_t intr_rows, int32_t intr_cols, int64_t B, int32_t size,
+                         int32_t top, int32_t left, int32_t H, int32_t W, float* rays_out, void* stream) {
+  if (B < 0 || H < 0 || W < 0 || size <= 0 || intr_rows < 3 || intr_cols < 3) return fail(NF_E_BADARG, "nf_generate_rays_dtu: bad size / intrinsic shape");
+  if (B == 0 || H == 0 || W == 0) return 0;
+  if (!pose || !intrinsic || !rays_out) return fail(NF_E_BADARG, "nf_generate_rays_dtu: null pointer");
+  cudaError_t e = nf_launch_generate_rays_dtu(pose, intrinsic, intr_rows, intr_cols, B, size, top, left, H, W, rays_out, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nf_generate_rays_dtu");
+}
+
 int nf_ray_radii(const float* rays, int64_t B, int32_t H, int32_t W, float* radius_out, void* stream) {
   if (B < 0 || H < 0 || W < 0) return fail(NF_E_BADARG, "nf_ray_radii: negative size");
   if (B == 0 || W == 0 || H == 0) return 0;

@@ -524,6 +524,36 @@ __global__ void k_generate_rays(const float* __restrict__ c2w, long long B, floa
   }
 }
 
+// DTUCamera.sample_positions (reference src/cameras.py:159-174 lift, 189-223): pixel (u, v) scaled to the 1600 x 1200 original,
+// lifted through the intrinsics, moved to world space by the pose (the reference's bmm, K = 4), direction = normalised difference
+// to the camera centre -- UNIT-norm r_d, unlike NeRFCamera.  pose [B,4,4] (rows 0..2 used), intrinsic [B,ir,ic] (ir, ic >= 3).
+__global__ void k_generate_rays_dtu(const float* __restrict__ pose, const float* __restrict__ intr, int ir, int ic, long long B, float sx, float sy,
+                                    int top, int left, int H, int W, float* __restrict__ out) {
+  const long long total = B * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W); const int h = (int)((i / W) % H); const long long b = i / ((long long)W * H);
+    const float u = __fmul_rn((float)(left + w), sx), v = __fmul_rn((float)(top + h), sy);
+    const float* K = intr + b * ir * ic;
+    const float fx = __ldg(K), sk = __ldg(K + 1), cx = __ldg(K + 2), fy = __ldg(K + ic + 1), cy = __ldg(K + ic + 2);
+    // x_lift = (x - cx + cy*sk/fy - sk*y/fy) / fx * z,  y_lift = (y - cy) / fy * z,  z = 1  (operation order as written in lift())
+    const float xl = __fdiv_rn(__fsub_rn(__fadd_rn(__fsub_rn(u, cx), __fdiv_rn(__fmul_rn(cy, sk), fy)), __fdiv_rn(__fmul_rn(sk, v), fy)), fx);
+    const float yl = __fdiv_rn(__fsub_rn(v, cy), fy);
+    const float* P = pose + b * 16;
+    float d[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float t = __ldg(P + c * 4 + 3);
+      float acc = __fmul_rn(__ldg(P + c * 4), xl);
+      acc = fmaf(__ldg(P + c * 4 + 1), yl, acc); acc = fmaf(__ldg(P + c * 4 + 2), 1.f, acc); acc = fmaf(t, 1.f, acc);
+      d[c] = __fsub_rn(acc, t);
+    }
+    const float nrm = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2]))), 1e-12f);
+    float* o = out + i * 6;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { o[c] = __ldg(P + c * 4 + 3); o[3 + c] = __fdiv_rn(d[c], nrm); }
+  }
+}
+
 // radii_x, reference src/utils.py:77-81: one thread per ray of the [B,H,W] crop
 __global__ void k_ray_radii(const float* __restrict__ rays, long long B, int H, int W, float* __restrict__ out) {
   const long long total = B * H * W;
@@ -573,6 +603,16 @@ cudaError_t nf_launch_generate_rays(const float* c2w, int64_t B, float focal, in
   const long long want = (total + 255) / 256;
   const int grid = (int)(want < (long long)num_sms() * 8 ? want : (long long)num_sms() * 8);
   k_generate_rays<<<grid, 256, 0, st>>>(c2w, B, focal, (float)size * 0.5f, top, left, H, W, recip, out);
+  return cudaGetLastError();
+}
+
+cudaError_t nf_launch_generate_rays_dtu(const float* pose, const float* intr, int ir, int ic, int64_t B, int size, int top, int left, int H, int W,
+                                        float* out, cudaStream_t st) {
+  const long long total = B * H * W;
+  if (total == 0) return cudaSuccess;
+  const long long want = (total + 255) / 256;
+  const int grid = (int)(want < (long long)num_sms() * 8 ? want : (long long)num_sms() * 8);
+  k_generate_rays_dtu<<<grid, 256, 0, st>>>(pose, intr, ir, ic, B, 1600.f / (float)size, 1200.f / (float)size, top, left, H, W, out);
   return cudaGetLastError();
 }
 

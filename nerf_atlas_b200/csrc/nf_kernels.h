@@ -9,6 +9,8 @@ cudaError_t nf_launch_render_fp32(const NfPlan& plan, const void* packed, const 
                                   float* rgb, float* alpha, float* weights, cudaStream_t st, const nf_render_aux* aux = nullptr);
 cudaError_t nf_launch_generate_rays(const float* c2w, int64_t B, float focal, int size, int top, int left, int H, int W, int recip,
                                     float* out, cudaStream_t st);
+cudaError_t nf_launch_generate_rays_dtu(const float* pose, const float* intr, int ir, int ic, int64_t B, int size, int top, int left, int H, int W,
+                                        float* out, cudaStream_t st);
 cudaError_t nf_launch_ray_radii(const float* rays, int64_t B, int H, int W, float* out, cudaStream_t st);
 cudaError_t nf_launch_render_tc(const NfPlan& plan, const void* packed, const float* rays, int64_t n_rays, const float* ts,
                                 int T, int64_t ts_stride, const float* noise, float* rgb, float* alpha, float* weights,

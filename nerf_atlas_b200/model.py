@@ -189,6 +189,23 @@ class RenderEngine:
     _lib.check(rc, "nf_generate_rays")
     return rays
 
+  @staticmethod
+  def generate_rays_dtu(pose: torch.Tensor, intrinsic: torch.Tensor, size: int, crop=None) -> torch.Tensor:
+    """runner.render's pixel grid + DTUCamera.sample_positions (reference src/cameras.py:189-223): pose[B,4,4], intrinsic[B,r,c]
+    (CUDA) -> rays[B,H,W,6] with unit-norm r_d; crop = (top, left, H, W), default the whole size x size image."""
+    _chk(pose, "pose"); _chk(intrinsic, "intrinsic")
+    if pose.dim() != 3 or tuple(pose.shape[1:]) != (4, 4): raise ValueError("pose must be [B,4,4]")
+    if intrinsic.dim() != 3 or intrinsic.shape[0] != pose.shape[0] or min(intrinsic.shape[1:]) < 3: raise ValueError("intrinsic must be [B,>=3,>=3]")
+    t, l, h, w = crop if crop is not None else (0, 0, size, size)
+    B = pose.shape[0]
+    rays = torch.empty(B, h, w, 6, dtype=torch.float32, device=pose.device)
+    lib = _lib.lib()
+    with torch.cuda.device(pose.device):
+      rc = lib.nf_generate_rays_dtu(_ptr(pose), _ptr(intrinsic), intrinsic.shape[1], intrinsic.shape[2], B, int(size), int(t), int(l), int(h), int(w),
+                                    _ptr(rays), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc, "nf_generate_rays_dtu")
+    return rays
+
   def ray_radii(self, rays_bhw: torch.Tensor) -> torch.Tensor:
     """radii_x (reference src/utils.py:77-81) of a crop rays[B,H,W,6] -> [B,H,W]."""
     _chk(rays_bhw, "rays")

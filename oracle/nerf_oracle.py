@@ -681,6 +681,25 @@ def make_cameras(n_views: int, size: int = 800, seed: int = 0, radius: float = 4
   return torch.from_numpy(np.stack(c2w).astype(np.float32)), focal
 
 
+def dtu_rays(pose: Tensor, intrinsic: Tensor, size: int, top: int, left: int, h: int, w: int) -> Tensor:
+  """runner.render's pixel grid (runner.py:495-503) + DTUCamera.sample_positions (reference src/cameras.py:159-174 lift,
+  189-223): pose[B,4,4], intrinsic[B,>=3,>=3] -> rays[B,h,w,6] with unit-norm r_d."""
+  B = pose.shape[0]
+  jj, ii = torch.meshgrid(torch.arange(left, left + w, dtype=torch.float32), torch.arange(top, top + h, dtype=torch.float32), indexing="xy")
+  norm = torch.tensor([1600, 1200], dtype=torch.float32) / size
+  u = (jj * norm[0]).reshape(1, -1).expand(B, -1); v = (ii * norm[1]).reshape(1, -1).expand(B, -1)
+  fx, fy = intrinsic[:, 0, 0, None], intrinsic[:, 1, 1, None]
+  cx, cy, sk = intrinsic[:, 0, 2, None], intrinsic[:, 1, 2, None], intrinsic[:, 0, 1, None]
+  z = torch.ones_like(u)
+  x_lift = (u - cx + cy * sk / fy - sk * v / fy) / fx * z
+  y_lift = (v - cy) / fy * z
+  points = torch.stack([x_lift, y_lift, z, torch.ones_like(z)], dim=-1)
+  world = torch.bmm(pose, points.permute(0, 2, 1)).permute(0, 2, 1)[..., :3]
+  r_o = pose[:, None, :3, 3].expand_as(world)
+  r_d = F.normalize(world - r_o, dim=-1)
+  return torch.cat([r_o, r_d], dim=-1).reshape(B, h, w, 6)
+
+
 def make_rays(n_views: int, h: int, w: int, size: int = 800, seed: int = 0,
               crop_top: int = 0, crop_left: int = 0, radius: float = 4.0) -> Tensor:
   """``rays[B,H,W,6]`` exactly as runner.render + NeRFCamera.sample_positions build

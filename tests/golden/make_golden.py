@@ -199,8 +199,31 @@ def check_rays():
   assert torch.equal(ref, rays), "make_rays != reference camera"
   print("make_rays == NeRFCamera.sample_positions: ok")
 
+def case_dtu_rays(name, seed=5, B=2, size=400, top=37, left=101, H=6, W=9):
+  """DTUCamera.sample_positions (reference src/cameras.py:189-223) on runner.render's pixel grid: IDR-style poses / intrinsics
+  (focal ~ 2900 px of the 1600 x 1200 original, principal point near the centre, a little skew), unit-norm r_d."""
+  runner, nerf, refl, utils, cameras = ref_shim.load()
+  g = np.random.default_rng(seed)
+  pose = np.zeros((B, 4, 4), np.float32); intr = np.zeros((B, 4, 4), np.float32)
+  for b in range(B):
+    q, _ = np.linalg.qr(g.normal(size=(3, 3)))
+    if np.linalg.det(q) < 0: q[:, 0] = -q[:, 0]
+    pose[b, :3, :3] = q; pose[b, :3, 3] = g.normal(size=3) * 1.5; pose[b, 3, 3] = 1
+    intr[b] = np.eye(4); intr[b, 0, 0] = 2892.3 + 10 * g.normal(); intr[b, 1, 1] = 2883.2 + 10 * g.normal()
+    intr[b, 0, 2] = 823.2 + 5 * g.normal(); intr[b, 1, 2] = 619.1 + 5 * g.normal(); intr[b, 0, 1] = 0.3 * g.normal()
+  cam = cameras.DTUCamera(pose=torch.from_numpy(pose), intrinsic=torch.from_numpy(intr))
+  ii, jj = torch.meshgrid(torch.arange(size, dtype=torch.float), torch.arange(size, dtype=torch.float), indexing="ij")
+  positions = torch.stack([ii.transpose(-1, -2), jj.transpose(-1, -2)], dim=-1)[top:top + H, left:left + W, :]     # runner.py:495-503
+  rays = cam.sample_positions(positions, size=size, with_noise=False)
+  assert rays.shape == (B, H, W, 6)
+  np.savez_compressed(os.path.join(HERE, name + ".npz"), pose=pose, intrinsic=intr, size=size, top=top, left=left, H=H, W=W, rays=rays.numpy())
+  print(name, rays.shape, "|r_d| =", float(rays[..., 3:].norm(dim=-1).mean()))
+
 if __name__ == "__main__":
   check_rays()
+  if "--dtu" in sys.argv:
+    case_dtu_rays("dtu_rays")
+    sys.exit(0)
   if "--grads" in sys.argv:
     case_plain_grads("plain_t16_grads", seed=91, B=1, H=3, W=4, T=16, top=398, left=397)
     sys.exit(0)
@@ -224,3 +247,4 @@ if __name__ == "__main__":
   case_dnerf_spline("dnerf_spline4_t32", seed=72, n=4, B=2, H=3, W=3, T=32, top=398, left=397)
   case_plain("plain_pos_t16", seed=81, B=1, H=4, W=5, T=16, sigma_gain=20.0, top=398, left=397, stages=False, refl_kind="pos")
   case_plain_grads("plain_t16_grads", seed=91, B=1, H=3, W=4, T=16, top=398, left=397)
+  case_dtu_rays("dtu_rays")

@@ -785,3 +785,19 @@ def test_random_background_vs_oracle(P, precision, tol):
   rgb, _, _ = e.render(rays.to(DEV), ts.to(DEV), bg_rand=u.to(DEV))
   assert float((rgb.cpu() - want).abs().max()) <= tol
   with pytest.raises(RuntimeError): e.render(rays.to(DEV), ts.to(DEV))          # the draws are an explicit input
+
+
+def test_generate_rays_dtu_vs_reference_camera():
+  """nf_generate_rays_dtu vs the reference's DTUCamera (golden written by running it): origins bit-exact, unit directions to 1e-6
+  (the reference's torch.bmm fixes no summation order), and a whole 400 x 400 frame against the oracle restatement."""
+  import nerf_atlas_b200 as N
+  fx = load_golden("dtu_rays")
+  pose, intr = torch.from_numpy(fx["pose"]).to(DEV), torch.from_numpy(fx["intrinsic"]).to(DEV)
+  crop = (int(fx["top"]), int(fx["left"]), int(fx["H"]), int(fx["W"]))
+  rays = N.RenderEngine.generate_rays_dtu(pose, intr, int(fx["size"]), crop).cpu().numpy()
+  assert rays.shape == fx["rays"].shape
+  assert np.array_equal(rays[..., :3], fx["rays"][..., :3])
+  assert np.abs(rays[..., 3:] - fx["rays"][..., 3:]).max() <= 1e-6
+  full = N.RenderEngine.generate_rays_dtu(pose, intr, 400).cpu()
+  ref = O.dtu_rays(pose.cpu(), intr.cpu(), 400, 0, 0, 400, 400)
+  assert float((full - ref).abs().max()) <= 1e-6 and float((full[..., 3:].norm(dim=-1) - 1).abs().max()) <= 1e-6

@@ -215,3 +215,12 @@ def test_oracle_autograd_matches_the_reference_backward(golden_dir):
     rows = torch.nonzero(g.abs().sum(1)).squeeze(1).numpy()
     assert np.array_equal(rows, fx[f"grad.emb{lvl}.rows"]), lvl
     assert np.abs(g[rows].numpy() - fx[f"grad.emb{lvl}.vals"]).max() <= 1e-6 * max(np.abs(fx[f"grad.emb{lvl}.vals"]).max(), 1e-3)
+
+
+def test_dtu_rays_oracle_matches_reference_camera(golden_dir):
+  """DTUCamera.sample_positions (reference src/cameras.py:189-223) restated; golden = the reference camera's own output."""
+  fx = load(golden_dir, "dtu_rays")
+  rays = O.dtu_rays(torch.from_numpy(fx["pose"]), torch.from_numpy(fx["intrinsic"]), int(fx["size"]), int(fx["top"]), int(fx["left"]),
+                    int(fx["H"]), int(fx["W"]))
+  assert np.array_equal(rays.numpy(), fx["rays"])
+  assert np.abs(np.linalg.norm(fx["rays"][..., 3:], axis=-1) - 1).max() < 1e-6
