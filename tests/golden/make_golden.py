@@ -219,8 +219,71 @@ def case_dtu_rays(name, seed=5, B=2, size=400, top=37, left=101, H=6, W=9):
   np.savez_compressed(os.path.join(HERE, name + ".npz"), pose=pose, intrinsic=intr, size=size, top=top, left=left, H=H, W=W, rays=rays.numpy())
   print(name, rays.shape, "|r_d| =", float(rays[..., 3:].norm(dim=-1).mean()))
 
+def analytic_scene(rays):
+  """Procedural target (SURVEY 8d weight set T; there is no dataset in the container): a unit sphere at the origin, shaded
+  with a position-dependent albedo and a fixed light, on black -- intersected analytically per ray."""
+  o, d = rays[..., :3], torch.nn.functional.normalize(rays[..., 3:], dim=-1)
+  b = (o * d).sum(-1); c = (o * o).sum(-1) - 1.0
+  disc = b * b - c
+  hit = disc > 0
+  t = -b - disc.clamp(min=0).sqrt()
+  p = o + t[..., None] * d
+  n = torch.nn.functional.normalize(p, dim=-1)
+  light = torch.nn.functional.normalize(torch.tensor([0.4, -0.3, 0.85]), dim=0)
+  albedo = 0.5 + 0.5 * torch.sin(3.0 * p + torch.tensor([0.0, 2.0, 4.0]))
+  col = albedo * (0.25 + 0.75 * (n * light).sum(-1, keepdim=True).clamp(min=0))
+  return torch.where(hit[..., None], col, torch.zeros_like(col))
+
+def case_trained(name, seed=1337, iters=400, T=64, crop=24, views=6, lr=2e-3):
+  """Weight set T: the REFERENCE model trained by the reference's own forward / autograd / Adam (runner.py:448-458:
+  Adam, eps 1e-7; mse loss 600-602; training-mode jitter + density noise) on the procedural scene, then rendered in eval mode.
+  The fixture stores the trained parameters as deltas to the seeded initialisation (MLP weights dense, hash tables as the
+  touched rows) plus the reference's eval render and the largest pre-activation magnitude it saw."""
+  runner, nerf, refl, utils, cameras = ref_shim.load()
+  params = O.make_plain_params(seed, 64, 1.0)
+  model, args = ref_plain(params, T, train=True)
+  for p in model.parameters(): p.requires_grad_(p.dtype.is_floating_point and p.numel() > 0)
+  opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=lr, eps=1e-7)
+  sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=iters, eta_min=lr / 20)         # runner.py:1289
+  g = np.random.default_rng(seed)
+  torch.manual_seed(seed)
+  size = 800
+  for it in range(iters):
+    v = int(g.integers(0, views)); top = int(g.integers(250, 550 - crop)); left = int(g.integers(250, 550 - crop))
+    rays = O.make_rays(views, crop, crop, size=size, seed=seed, crop_top=top, crop_left=left)[v:v + 1]
+    opt.zero_grad()
+    loss = torch.nn.functional.mse_loss(model(rays), analytic_scene(rays))
+    loss.backward(); opt.step(); sched.step()
+    if it % 50 == 0 or it == iters - 1: print(name, "iter", it, "loss", float(loss.detach()), flush=True)
+  model.eval()
+  # eval render of a held-out crop through the reference, recording the largest |pre-activation| (fp16 operand range check)
+  H = W = 16; top, left = 392, 392
+  rays = O.make_rays(views, H, W, size=size, seed=seed, crop_top=top, crop_left=left)[:2]
+  hmax = [0.0]
+  def hook(mod, inp, out): hmax[0] = max(hmax[0], float(out.detach().abs().max()))
+  hs = [m.register_forward_hook(hook) for m in model.modules() if isinstance(m, torch.nn.Linear)]
+  with torch.no_grad(): out = model(rays)
+  for h in hs: h.remove()
+  sd = {k: v.detach() for k, v in model.state_dict().items()}
+  fx = dict(kind="plain_trained", seed=seed, iters=iters, T=T, B=2, H=H, W=W, top=top, left=left, views=views, near=float(args.near), far=float(args.far),
+            sigmoid=args.sigmoid_kind, bg=args.bg, ts=model.ts.numpy(), out=out.numpy(), alpha=model.alpha.numpy(), weights=model.weights.numpy(),
+            final_loss=float(loss), max_abs_preactivation=hmax[0], target=analytic_scene(rays).numpy())
+  for k, v in sd.items():
+    if not v.dtype.is_floating_point or v.numel() == 0: continue
+    if ".embs." in k:
+      rows = torch.nonzero((v != params[k]).any(dim=1)).squeeze(1)
+      fx["rows." + k] = rows.numpy().astype(np.int32); fx["vals." + k] = v[rows].numpy()
+    else: fx["param." + k] = v.numpy()
+  np.savez_compressed(os.path.join(HERE, name + ".npz"), **fx)
+  print(name, "final loss", float(loss), "max|h|", hmax[0], "psnr vs target", float(-10 * torch.log10(torch.nn.functional.mse_loss(out, analytic_scene(rays)))),
+        "table rows stored", sum(len(fx[k]) for k in fx if k.startswith("rows.")))
+
 if __name__ == "__main__":
   check_rays()
+  if "--trained" in sys.argv:
+    torch.set_num_threads(int(os.environ.get("GOLDEN_THREADS", "8")))
+    case_trained(os.environ.get("GOLDEN_NAME", "plain_trained_t64"), iters=int(os.environ.get("GOLDEN_ITERS", "400")), lr=float(os.environ.get("GOLDEN_LR", "2e-3")))
+    sys.exit(0)
   if "--dtu" in sys.argv:
     case_dtu_rays("dtu_rays")
     sys.exit(0)
@@ -248,3 +311,4 @@ if __name__ == "__main__":
   case_plain("plain_pos_t16", seed=81, B=1, H=4, W=5, T=16, sigma_gain=20.0, top=398, left=397, stages=False, refl_kind="pos")
   case_plain_grads("plain_t16_grads", seed=91, B=1, H=3, W=4, T=16, top=398, left=397)
   case_dtu_rays("dtu_rays")
+  case_trained("plain_trained_t64")

@@ -73,3 +73,13 @@ def volsdf_engine(P, sdf_kind, device, sigmoid="upshifted", precision="fp16"):
   eng._params = volsdf_param_list(P, sdf_kind, device)
   eng.pack(eng._params)
   return eng
+
+def trained_params(fx):
+  """Weight set T (tests/golden/make_golden.py case_trained): the seeded initialisation + the stored deltas = the parameters the
+  REFERENCE reached by training itself on the procedural scene."""
+  P = O.make_plain_params(int(fx["seed"]), 64, 1.0)
+  for k in fx:
+    if k.startswith("param."): P[k[6:]] = torch.from_numpy(fx[k])
+    elif k.startswith("rows."):
+      t = P[k[5:]].clone(); t[torch.from_numpy(fx[k]).long()] = torch.from_numpy(fx["vals." + k[5:]]); P[k[5:]] = t
+  return P

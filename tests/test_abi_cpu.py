@@ -246,6 +246,21 @@ def test_integration_md_struct_matches_the_binding():
   body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
   fields = re.findall(r"(?:int32_t|uint32_t|float|nf_mlp_desc)\s+(\w+)", body)
   assert fields == real, (fields, real)
+  # the training / aux structs: INTEGRATION.md stub == binding == header, field for field
+  def header_fields(name):
+    b = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), hdr, flags=re.S).group(1)
+    b = re.sub(r"/\*.*?\*/", "", b, flags=re.S)
+    out = []
+    for decl in b.split(";"):
+      mm = re.match(r"\s*(?:const\s+)?(?:int32_t|int64_t|float|void|nf_train_lin)\s*\*?\s*(.*)", decl.strip(), flags=re.S)
+      if mm and mm.group(1): out += [re.sub(r"[\[\]\*\sA-Z_0-9]*$", "", x.strip().lstrip("*")) or x.strip() for x in mm.group(1).split(",")]
+    return [re.match(r"\*?\s*(\w+)", x).group(1) for x in out if x]
+  for cls, cname in ((_lib.TrainLin, "nf_train_lin"), (_lib.TrainLayout, "nf_train_layout"), (_lib.RenderAux, "nf_render_aux")):
+    real = [f[0] for f in cls._fields_]
+    assert header_fields(cname) == real, (cname, header_fields(cname), real)
+    m = re.search(r"class %s\(C.Structure\):.*?_fields_ = (.*?)\n(?:class|\n)" % cls.__name__, src, flags=re.S)
+    assert m, cls.__name__
+    assert re.findall(r'"(\w+)"', m.group(1)) == real, cls.__name__
 
 
 def test_modules_pickle_without_the_library_handle(tmp_path):
@@ -321,3 +336,36 @@ def test_which_models_the_tensor_pipeline_takes():
   assert b"PlainNeRF only" in ok(dm)
   bad = N.describe_plain(); bad.density.hidden = 128
   assert b"hidden_size" in ok(bad)            # invalid descriptor: the plan builder's message
+
+
+def test_train_layout_host_logic():
+  """nf_train_layout_of is host-only: the stash regions tile the workspace without overlap, tile counts follow the sample-stream
+  tiling, and models the backward does not take are refused with a reason (no silent fallback)."""
+  import ctypes as C
+  import nerf_atlas_b200 as N
+  lib = _lib.lib()
+  d = N.describe_plain(64, "upshifted", "black")
+  for R, T in ((4096, 128), (12, 16), (50, 192), (33, 100), (1, 1)):
+    lay = _lib.TrainLayout()
+    assert lib.nf_train_layout_of(C.byref(d), R, T, C.byref(lay)) == 0
+    assert lay.n_lin == 12 and lay.n_rays == R and lay.T == T
+    units = (R + lay.rpu - 1) // lay.rpu
+    assert lay.n_tiles == units * lay.tpr and lay.n_tiles * 128 >= R * T
+    regions = [(lay.scale_off, 16), (lay.sigma_off, R * T * 4), (lay.rgbraw_off, R * T * 12), (lay.dsigma_off, R * T * 4),
+               (lay.drgbraw_off, R * T * 12), (lay.dx0_off, lay.n_tiles * 128 * 32 * 4)]
+    for i in range(lay.n_lin):
+      L = lay.lin[i]
+      assert L.a_tile == (L.k0_pad + L.k_hidden) * 256 and L.g_tile == L.n_pad * 256
+      regions += [(L.a_off, lay.n_tiles * L.a_tile), (L.g_off, lay.n_tiles * L.g_tile), (L.dw_off, L.n_pad * (L.k0_pad + L.k_hidden) * 4), (L.db_off, L.n_pad * 4)]
+      assert (L.c_off >= 0) == (L.act == _lib.ACT["sin"] and L.k_hidden > 0)
+      if L.c_off >= 0: regions.append((L.c_off, lay.n_tiles * 65536))
+      assert lay.dw_begin <= L.dw_off and L.db_off + L.n_pad * 4 <= lay.dw_end
+    regions.sort()
+    for (o0, n0), (o1, _) in zip(regions, regions[1:]): assert o0 % 1024 == 0 and o0 + n0 <= o1, (R, T, o0, n0, o1)
+    assert regions[-1][0] + regions[-1][1] <= lay.total_bytes
+  assert [(lay.lin[i].m, lay.lin[i].j) for i in range(12)] == [(0, j) for j in range(6)] + [(1, j) for j in range(6)]
+  for bad in (N.describe_volsdf("siren"), N.describe_dyn(), N.describe_plain(64, "upshifted", "black", mip="cylinder"), N.describe_tiny(),
+              N.describe_plain(64, "upshifted", "black", refl_kind="pos"), N.describe_plain(64, "upshifted", "random")):
+    lay = _lib.TrainLayout()
+    assert lib.nf_train_layout_of(C.byref(bad), 16, 16, C.byref(lay)) == -2        # NF_E_UNSUPPORTED
+    assert b"training" in lib.nf_last_error()

@@ -224,3 +224,20 @@ def test_dtu_rays_oracle_matches_reference_camera(golden_dir):
                     int(fx["H"]), int(fx["W"]))
   assert np.array_equal(rays.numpy(), fx["rays"])
   assert np.abs(np.linalg.norm(fx["rays"][..., 3:], axis=-1) - 1).max() < 1e-6
+
+
+def test_oracle_matches_reference_on_trained_weights(golden_dir):
+  """Weight set T: parameters the reference reached by training itself; the oracle reproduces the reference's eval
+  render bit for bit, the fp16-operand emulation stays inside the stated bar, and every pre-activation is far inside fp16 range."""
+  from helpers import trained_params
+  fx = load(golden_dir, "plain_trained_t64")
+  P = trained_params(fx)
+  rays = O.make_rays(int(fx["views"]), int(fx["H"]), int(fx["W"]), 800, int(fx["seed"]), int(fx["top"]), int(fx["left"]))[: int(fx["B"])]
+  ts = torch.from_numpy(fx["ts"])
+  with torch.no_grad():
+    ref = O.plain_forward(P, rays, ts, sigmoid=str(fx["sigmoid"]), bg=str(fx["bg"]))
+    q = O.plain_forward(P, rays, ts, sigmoid=str(fx["sigmoid"]), bg=str(fx["bg"]), quant=torch.float16)
+  assert np.array_equal(ref["out"].numpy(), fx["out"]) and np.array_equal(ref["weights"].numpy(), fx["weights"])
+  d = np.abs(q["out"].numpy() - fx["out"])
+  assert d.max() <= 1e-3 and -10 * np.log10(np.mean(d.astype(np.float64) ** 2)) >= 70
+  assert float(fx["max_abs_preactivation"]) < 65504 / 16          # |h| < fp16 max with a wide margin (SURVEY 8d range check)
