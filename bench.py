@@ -196,6 +196,69 @@ def strong_leg(eng, O, dev, world, rank, ts, steps, warmup, barrier):
           "what": "one 800x800x128 frame per step, cut into row-aligned blocks (one per GPU)"}
 
 
+def run_config(args):
+  """`--config N` (N = 2..5): the other configurations BASELINE.json names, one JSON line each in the same shape (rays resident in
+  HBM, tensor pipeline, 1 GPU).  Not the headline metric; the driver's default run stays the 800x800x128 Plain+View line."""
+  import torch
+  import nerf_atlas_b200 as N
+  from oracle import nerf_oracle as O
+  sys.path.insert(0, os.path.join(ROOT, "tests"))
+  from helpers import plain_param_list, volsdf_param_list
+  dev = torch.device("cuda", 0); torch.cuda.set_device(0)
+  n_views = 4
+  views = [O.make_rays(1, SIZE, SIZE, size=SIZE, seed=40 + v).reshape(-1, 6).contiguous().to(dev) for v in range(n_views)]
+  c = args.config
+  if c == 2:
+    P = O.make_plain_params(1337, 64, 1.0)
+    eng = N.RenderEngine(N.describe_plain(64, "upshifted", "black"), "fp16"); eng._p = plain_param_list(P, dev); eng.pack(eng._p)
+    tsc = torch.linspace(2, 6, 64, device=dev); u = torch.rand(RAYS_PER_FRAME, 128, device=dev)
+    fn = lambda i: eng.render_coarse_fine(views[i % n_views], tsc, u, want_weights=False)
+    rays, spr, fps, name, launches = RAYS_PER_FRAME, 64 + 192, 1_192_960, "PlainNeRF coarse 64 + fine 64+128 (restated sample_pdf), 800x800", 3
+  elif c == 3:
+    P = O.make_plain_params(61, 64, 1.0, mip=True)
+    eng = N.RenderEngine(N.describe_plain(64, "upshifted", "black", mip="cone"), "fp16"); eng._p = plain_param_list(P, dev); eng.pack(eng._p)
+    rads = [eng.ray_radii(v.reshape(1, SIZE, SIZE, 6)).reshape(-1) for v in views]
+    ts128 = torch.linspace(2, 6, T, device=dev)
+    fn = lambda i: eng.render(views[i % n_views], ts128, radius=rads[i % n_views], want_weights=False)
+    rays, spr, fps, name, launches = RAYS_PER_FRAME, T, 1_389_568, "PlainNeRF + Mip conical-frustum IPE (intended encoder), 800x800x128", 1
+  elif c == 4:
+    P = O.make_volsdf_params(7, "siren", 64, 0.1)
+    eng = N.RenderEngine(N.describe_volsdf("siren", 64, "upshifted"), "fp16"); eng._p = volsdf_param_list(P, "siren", dev); eng.pack(eng._p)
+    # DTU-style camera: unit-norm directions from nf_generate_rays_dtu, near 0.3 far 1.8 (makefile:184), 256 samples per ray
+    pose = torch.eye(4, device=dev).repeat(n_views, 1, 1); pose[:, 2, 3] = -1.0; pose[:, 0, 3] = torch.linspace(-0.2, 0.2, n_views, device=dev)
+    intr = torch.eye(4, device=dev).repeat(n_views, 1, 1); intr[:, 0, 0] = intr[:, 1, 1] = 2890.0; intr[:, 0, 2] = 800.0; intr[:, 1, 2] = 600.0
+    vr = N.RenderEngine.generate_rays_dtu(pose, intr, SIZE).reshape(n_views, -1, 6)
+    ts256 = torch.linspace(0.3, 1.8, 256, device=dev)
+    fn = lambda i: eng.render(vr[i % n_views], ts256, want_weights=False)
+    rays, spr, fps, name, launches = RAYS_PER_FRAME, 256, 1_289_728, "VolSDF volume branch (SIREN SDF + View, Laplace density), DTU-style unit rays 800x800, 256 samples/ray", 1
+  elif c == 5:
+    Pd = O.make_dnerf_params(9, 64)
+    canon = N.FusedPlainNeRF(steps=64, t_near=2, t_far=6, intermediate_size=64, sigmoid_kind="upshifted", precision="fp16", keep_weights=False)
+    m = N.FusedDynamicNeRF(canon); m.load_state_dict(Pd, strict=True); m = m.to(dev).eval(); m.keep_side = False
+    r400 = [O.make_rays(1, 400, 400, size=400, seed=70 + v).to(dev) for v in range(n_views)]
+    tt = torch.tensor([0.4], device=dev)
+    def fn(i):
+      with torch.no_grad(): return m((r400[i % n_views], tt))
+    rays, spr, fps, name, launches = 160000, 64, 1_856_512, "D-NeRF (direct deformation MLP + canonical PlainNeRF fused in one kernel), 400x400x64", 1
+  else: raise SystemExit("--config must be 2, 3, 4 or 5")
+  for i in range(max(3, args.warmup)): fn(i)
+  torch.cuda.synchronize()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  with ClockSampler(0) as cs:
+    e0.record()
+    for i in range(args.steps): fn(i)
+    e1.record(); torch.cuda.synchronize()
+  ms = e0.elapsed_time(e1) / args.steps
+  peak, peak_src = peaks()
+  ach = rays * spr * fps / (ms * 1e-3) / 1e12
+  print(json.dumps({"metric": f"rays_per_sec_config{c}", "value": rays / (ms * 1e-3), "unit": "rays/s", "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
+                    "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+                    "config": {"workload": name, "rays_per_step": rays, "samples_per_ray": spr, "l2": f"inputs rotate over {n_views} views"},
+                    "msamples_per_sec": rays * spr / (ms * 1e-3) / 1e6, "gpu_launches": launches * args.steps, "clocks": cs.summary(),
+                    "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                                 "algorithmic": f"{fps} FLOP/sample x {rays * spr} samples per step"}}), flush=True)
+
+
 def run_reference(args):
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0: return
@@ -350,9 +413,11 @@ def main():
   ap.add_argument("--no-torch-eager-gpu", action="store_true", help="skip timing the reference algorithm as eager PyTorch fp32 on this GPU (the north-star's 10x denominator; ~20 s)")
   ap.add_argument("--torch-eager-gpu", action="store_true", help="(default now; kept for compatibility)")
   ap.add_argument("--no-train", action="store_true", help="skip the native training-step leg")
+  ap.add_argument("--config", type=int, default=1, help="1 (default) = the headline 800x800x128 Plain+View line; 2..5 = the other BASELINE.json configurations")
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
   if args.impl == "reference": run_reference(args)
+  elif args.config != 1: run_config(args)
   else: run_ours(args)
 
 

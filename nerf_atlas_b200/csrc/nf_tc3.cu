@@ -69,6 +69,8 @@ struct Tc3Smem {
 };
 static_assert(sizeof(Tc3Smem) <= 227 * 1024, "staggered tensor pipeline smem");
 static_assert(offsetof(Tc3Smem, X0) == offsetof(Tc3Smem, H) + sizeof(Tc3Smem::H), "single mode: wide x0 runs from H[1] on into X0[]");
+static_assert(offsetof(Tc3Smem, W) == offsetof(Tc3Smem, X0) + sizeof(Tc3Smem::X0), "shared wide x0 runs from X0[0] on into the first 12 KB of W");
+constexpr int SHARED_X0_COLS = (2 * ROWS * X0K * 2 + 12 * 1024) / (ROWS * 2);          // 208 columns
 
 // Host-built program (kernel parameter => uniform constant loads in the issuing thread).  One record per Linear:
 // MMA shape/steps (issuer), this Linear's weight image (producers), (mlp, layer) (epilogue).
@@ -77,7 +79,11 @@ struct __align__(16) Tc3Lin {
   uint32_t bhi, mj, w_off, half_bytes;       // mj = m * 16 + j; w_off = byte offset of rank 0's half image, half_bytes = its size
   uint32_t step_bytes, pad0_, pad1_, pad2_;  // bytes of one K-step (16 K-columns) of a half image
 };
-struct __align__(16) Tc3Prog { int32_t n_lin, lag, single, pad1_; Tc3Lin lin[MAX_LIN3]; };   // single: one tile in flight, x0 (up to 256 wide) lives in slot 1's H buffer
+// single: 0 = two tiles in flight, one 80-column x0 buffer per slot; 1 = ONE tile in flight, x0 (up to 256 + 144 columns) in slot
+// 1's H buffer; 2 = two tiles in flight SHARING one wide x0 buffer (up to 208 columns: the two X0 buffers + the first 12 KB of
+// the ring region; the ring shrinks to 3 x 12 KB).  Sharing works because x0 is only live while a slot is in the first two
+// Linears of an MLP: with slot 1 three Linears behind slot 0 the two live windows never meet (checked on the host).
+struct __align__(16) Tc3Prog { int32_t n_lin, lag, single, pad1_; Tc3Lin lin[MAX_LIN3]; };
 
 // Training forward (TRAIN instantiation): where every Linear's input operand (and, for sin MLPs, the cosine of its
 // pre-activation) of every tile goes (NfTrainPlan, nf_common.cuh).  Offsets in 256-byte units from Tc3Args::ws.
@@ -314,10 +320,21 @@ __device__ __forceinline__ void hash_x0_tail(uint8_t* X0, const NfPlan& plan, in
     if (g < m0 || g >= m0 + NF_MIP_FEATS / 8) st_v4(X0 + g * KG_BYTES + row * 16, 0, 0, 0, 0);
 }
 // this thread's share (features first, first + stride, ...) of the Mip latent of one row -> x0 columns [col0, col0 + 96)
-__device__ __forceinline__ void mip_x0(uint8_t* X0, const NfMipIn& mip, int col0, bool ok, long long ray, int t, int row, int first, int stride) {
+#ifndef NF_MIP_INLINE
+#define NF_MIP_INLINE 0
+#endif
+#if NF_MIP_INLINE
+__device__ __forceinline__
+#else
+__device__ __noinline__          // a call keeps the Mip row state (NfMipRow) out of the main loop's register allocation
+#endif
+void mip_x0(uint8_t* X0, const NfMipIn& mip, int col0, bool ok, long long ray, int t, int row, int first, int stride) {
+  NfMipRow R;
+  const bool per_row = mip.mode != NF_MIP_CYLINDER_REF;               // the reference layout gathers its variance per feature
+  if (ok && per_row && first < NF_MIP_FEATS / 2) nf_mip_row(mip, ray, t, R);
   for (int cc = first; cc < NF_MIP_FEATS / 2; cc += stride) {            // (sin, cos) pairs share mean, variance and exponential
     float fs = 0.f, fc = 0.f;
-    if (ok) nf_mip_feature_pair(mip, ray, t, cc, fs, fc);
+    if (ok) { if (per_row) nf_mip_pair_of_row<true>(R, cc, fs, fc); else nf_mip_feature_pair<true>(mip, ray, t, cc, fs, fc); }
     const int c0 = col0 + cc, c1 = c0 + NF_MIP_FEATS / 2;
     *reinterpret_cast<__half*>(X0 + (c0 >> 3) * KG_BYTES + row * 16 + (c0 & 7) * 2) = __float2half_rn(fs);
     *reinterpret_cast<__half*>(X0 + (c1 >> 3) * KG_BYTES + row * 16 + (c1 & 7) * 2) = __float2half_rn(fc);
@@ -434,11 +451,13 @@ __device__ __forceinline__ void composite_tile3(Tc3Smem& s, int slot, const NfPl
 // sample are stashed in the training workspace for nf_render_backward (nf_train.cu).
 // AUX: explicit sample positions (from_pts) and the random background are compiled in (kept out of the common instantiation for
 // the same reason as WIDE / DYN).
-template <int NST, int SPCT, int NCQ, bool WIDE, bool DYN, bool TRAIN = false, bool AUX = false>
+// WIDE: 0 = no wide-x0 code, 1 = wide x0 without the Mip encoder (Positional head, Fourier SDF), 2 = with it.
+template <int NST, int SPCT, int NCQ, int WIDE, bool DYN, bool TRAIN = false, bool AUX = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (4 * NCQ + NST + 1), 1)
 k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Prog prog, const Tc3Args a, const __grid_constant__ Tc3Train tr) {
-  static_assert(NST * SPCT * 4096 == RING_BYTES && NST <= MAX_STAGES3, "ring geometry");
+  static_assert(NST * SPCT * 4096 <= RING_BYTES && NST <= MAX_STAGES3, "ring geometry");
   constexpr int STAGE_BYTES = SPCT * 4096;
+  constexpr int RING_OFF = RING_BYTES - NST * SPCT * 4096;     // a smaller ring sits at the END of the region (shared wide x0 in front)
   constexpr int EPIW = 4 * NCQ, EPI_THREADS = 32 * EPIW;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Tc3Smem& s = *reinterpret_cast<Tc3Smem*>(smem_raw);
@@ -446,7 +465,8 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
   const uint32_t crank = cluster_ctarank();
   const NfStreamMap map(a.T, ROWS);
   const long long units = map.units(a.n_rays);
-  const bool single = WIDE && prog.single != 0;    // one tile in flight: slot 1 never runs
+  const bool single = WIDE && prog.single == 1;    // one tile in flight: slot 1 never runs
+  const bool shared_x0 = WIDE && prog.single == 2; // two tiles in flight, one wide x0 buffer
   const int nslot = single ? 1 : 2;
   const int trips = (int)((units + (long long)nslot * gridDim.x - 1) / ((long long)nslot * gridDim.x));   // every CTA, every slot: same trip count
   const int passes = trips * map.tpr;
@@ -490,7 +510,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
     if (elect_one()) {
       const int p = warp - EPIW;
       const uint32_t ready_leader = leader_addr(smem_u32(&s.w_ready[p]));
-      const uint32_t bar_empty = smem_u32(&s.w_empty[p]), bar_land = smem_u32(&s.w_land[p]), dst = smem_u32(s.W + p * STAGE_BYTES);
+      const uint32_t bar_empty = smem_u32(&s.w_empty[p]), bar_land = smem_u32(&s.w_land[p]), dst = smem_u32(s.W + RING_OFF + p * STAGE_BYTES);
       int rs = 0, li0 = 0, li1 = 0; uint32_t use = 0;
       ST_DECL;
       for (int k = 0; k < nsteps + lag; ++k) {
@@ -529,7 +549,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
     if (crank == 0 && elect_one()) {
       uint32_t stage = 0, phase = 0, a_par = 0;
       const uint32_t base4 = smem_u32(smem_raw) >> 4;
-      const uint32_t w4 = base4 + (uint32_t)(offsetof(Tc3Smem, W) >> 4);
+      const uint32_t w4 = base4 + (uint32_t)((offsetof(Tc3Smem, W) + RING_OFF) >> 4);
       const uint32_t bar_wready = smem_u32(&s.w_ready[0]), bar_wempty = smem_u32(&s.w_empty[0]);
       const uint32_t bar_a = smem_u32(&s.a_ready[0]), bar_acc = smem_u32(&s.acc_full[0]);
       const uint32_t a_lbo = (uint32_t)(KG_BYTES >> 4) << 16, kstep4 = (uint32_t)(2 * KG_BYTES) >> 4;
@@ -555,7 +575,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
           tc_fence_after();
           const uint32_t d_tmem = slot * 256u;
           const uint32_t x4 = (single ? base4 + (uint32_t)((offsetof(Tc3Smem, H) + sizeof(s.H[0])) >> 4)
-                                      : base4 + (uint32_t)(offsetof(Tc3Smem, X0) >> 4) + slot * (uint32_t)(sizeof(s.X0[0]) >> 4)) | a_lbo;
+                                      : base4 + (uint32_t)(offsetof(Tc3Smem, X0) >> 4) + (shared_x0 ? 0u : slot * (uint32_t)(sizeof(s.X0[0]) >> 4))) | a_lbo;
           const uint32_t h4 = (base4 + (uint32_t)(offsetof(Tc3Smem, H) >> 4) + slot * (uint32_t)(sizeof(s.H[0]) >> 4)) | a_lbo;
 #pragma unroll 1
           for (uint32_t gs0 = 0; gs0 < total; gs0 += SPCT) {
@@ -611,7 +631,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
         const int kl = k - (slot ? lag : 0);
         if (kl < 0 || kl > nsteps || (slot && single)) continue;
         const int j = slot ? j1 : j0, P = slot ? P1 : P0;
-        uint8_t* H = s.H[slot]; uint8_t* X0 = single ? s.H[1] : s.X0[slot];
+        uint8_t* H = s.H[slot]; uint8_t* X0 = single ? s.H[1] : shared_x0 ? s.X0[0] : s.X0[slot];
         const uint32_t t_acc = t_lane + (uint32_t)slot * 256u;
         const uint32_t a_ready_leader = leader_addr(smem_u32(&s.a_ready[slot]));
         const bool has_next = kl < nsteps;              // Linear j of this slot runs after this phase
@@ -682,7 +702,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
             if (hashed)
               hash_x0(X0, reinterpret_cast<const float4*>(a.packed + (dyn ? plan.hash2_off : plan.hash_off)), plan, px, py, pz, row,
                       comp ? (cq == comp_cq ? -1 : ((cq - comp_cq - 1 + NCQ) % NCQ)) : cq, comp ? NCQ - 1 : NCQ);
-            const int mip0 = (WIDE && plan.mip != NF_MIP_NONE && !dyn) ? nf_mip_col(plan, 0) : -1;
+            const int mip0 = (WIDE == 2 && plan.mip != NF_MIP_NONE && !dyn) ? nf_mip_col(plan, 0) : -1;
             if (mip0 >= 0) mip_x0(X0, a.mip, mip0, ok, ray, t, row, comp ? (cq == comp_cq ? NF_MIP_FEATS : ((cq - comp_cq - 1 + NCQ) % NCQ)) : cq, comp ? NCQ - 1 : NCQ);
             const bool fourier = WIDE && !dyn && plan.enc == NF_ENC_FOURIER;
             if (fourier) {
@@ -817,7 +837,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
             // density MLP out (tensor order [inter(I), sigma]) -> raw x0 of the RGB head + raw density
             const int iu = plan.intermediate >> 4;
             const bool pos_head = WIDE && plan.refl_kind == NF_REFL_POSITIONAL;
-            const int mip1 = (WIDE && plan.mip != NF_MIP_NONE) ? nf_mip_col(plan, 1) : -1;
+            const int mip1 = (WIDE == 2 && plan.mip != NF_MIP_NONE) ? nf_mip_col(plan, 1) : -1;
             if (pos_head || mip1 >= 0) {
               // wide RGB-head inputs (single mode): every thread takes a share of its row's Positional hash features and Mip latent
               long long u; int sub; unit_of(P, slot, map.tpr, nslot, u, sub);
@@ -924,7 +944,26 @@ bool build_prog3(const NfPlan& plan, Tc3Prog* P) {
     }
   }
   P->n_lin = nl; P->lag = nl / 2;
-  for (int m = 0; m < plan.n_mlps; ++m) if (plan.mlp[m].k0_pad > X0K) P->single = 1;
+  int kmax = 0;
+  for (int m = 0; m < plan.n_mlps; ++m) kmax = plan.mlp[m].k0_pad > kmax ? plan.mlp[m].k0_pad : kmax;
+  if (kmax > X0K) {
+    P->single = 1;
+    if (kmax <= SHARED_X0_COLS && plan.kind == NF_KIND_PLAIN) {
+      // shared wide x0: writers = the phases that produce / activate an MLP's x0, consumers = the Linears that read it.  Slot 1
+      // runs `lag` phases behind slot 0 and is served second within a step: when slot 0 writes at phase s, slot 1's Linear
+      // s - lag - 1 may still be in flight; when slot 1 writes at phase s, slot 0's Linear s + lag may be.
+      bool writer[MAX_LIN3] = {}, consumer[MAX_LIN3] = {};
+      int li = 0;
+      for (int mi = 0; mi < plan.n_mlps; ++mi)
+        for (int j = 0; j < plan.mlp[mi].n_lin; ++j, ++li)
+          if (plan.mlp[mi].lin[j].k0_pad) { consumer[li] = true; writer[li] = true; if (j == 0) writer[(li + 1) % nl] = true; }
+      const int lag = 3;
+      bool ok = nl > 2 * lag + 2;
+      for (int sph = 0; sph < nl && ok; ++sph)
+        if (writer[sph] && (consumer[((sph - lag - 1) % nl + nl) % nl] || consumer[(sph + lag) % nl] || consumer[((sph - lag) % nl + nl) % nl])) ok = false;
+      if (ok) { P->single = 2; P->lag = lag; }
+    }
+  }
   return true;
 }
 
@@ -1005,6 +1044,8 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
   if (!build_prog3(plan, &prog)) return cudaErrorNotSupported;
   const bool wide = prog.single != 0 || plan.mip != NF_MIP_NONE || plan.refl_kind != NF_REFL_VIEW;
   if (wide) { ring = 3; epiw = 16; }
+  const bool wide_shared = wide && prog.single == 2;     // two tiles in flight over one wide x0 buffer, 3 x 12 KB ring
+  const bool mipk = plan.mip != NF_MIP_NONE;
   const bool dynk = plan.kind == NF_KIND_DYN;
   if (dynk) { ring = 3; epiw = 16; }
   const bool train = tp != nullptr;
@@ -1032,15 +1073,17 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
         if (tp->lin[k].k0_pad) { if (tr.lin[i].skip0 < 0) tr.lin[i].skip0 = k; else if (tr.lin[i].skip1 < 0) tr.lin[i].skip1 = k; else return cudaErrorNotSupported; }
     }
   }
-  const void* fn = train ? (const void*)k_render_tc3<3, 4, 4, false, false, true>
-                 : auxk ? (const void*)k_render_tc3<3, 4, 4, false, false, false, true>
-                 : wide ? (const void*)k_render_tc3<3, 4, 4, true, false>
-                 : dynk ? (const void*)k_render_tc3<3, 4, 4, false, true>
+  const void* fn = train ? (const void*)k_render_tc3<3, 4, 4, 0, false, true>
+                 : auxk ? (const void*)k_render_tc3<3, 4, 4, 0, false, false, true>
+                 : (wide_shared && mipk) ? (const void*)k_render_tc3<3, 3, 4, 2, false>
+                 : wide_shared ? (const void*)k_render_tc3<3, 3, 4, 1, false>
+                 : wide ? (const void*)k_render_tc3<3, 4, 4, 2, false>
+                 : dynk ? (const void*)k_render_tc3<3, 4, 4, 0, true>
 #ifdef NF_EXPERIMENTS
-                 : epiw == 24 ? (const void*)k_render_tc3<3, 4, 6, false, false>
-                 : ring == 6 ? (const void*)k_render_tc3<6, 2, 4, false, false>
+                 : epiw == 24 ? (const void*)k_render_tc3<3, 4, 6, 0, false>
+                 : ring == 6 ? (const void*)k_render_tc3<6, 2, 4, 0, false>
 #endif
-                 : (const void*)k_render_tc3<3, 4, 4, false, false>;
+                 : (const void*)k_render_tc3<3, 4, 4, 0, false>;
   const int threads = 32 * (epiw + ring + 1);
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tc3Smem));
   if (e != cudaSuccess) return e;
@@ -1049,7 +1092,7 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
   if (units == 0) return cudaSuccess;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const long long nslot = prog.single ? 1 : 2;
+  const long long nslot = prog.single == 1 ? 1 : 2;
   long long want = (units + 2 * nslot - 1) / (2 * nslot) * 2;                      // 2 CTAs x nslot tiles per cluster
   const int grid = (int)(want < (sms / 2) * 2 ? want : (sms / 2) * 2);
   const long long trips = (units + nslot * grid - 1) / (nslot * grid);
@@ -1060,15 +1103,17 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
   cudaMemsetAsync(d_stats, 0, 64 * sizeof(long long), st);
   a.stats = d_stats;
 #endif
-  if (train) k_render_tc3<3, 4, 4, false, false, true><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
-  else if (auxk) k_render_tc3<3, 4, 4, false, false, false, true><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
-  else if (wide) k_render_tc3<3, 4, 4, true, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
-  else if (dynk) k_render_tc3<3, 4, 4, false, true><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
+  if (train) k_render_tc3<3, 4, 4, 0, false, true><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
+  else if (auxk) k_render_tc3<3, 4, 4, 0, false, false, true><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
+  else if (wide_shared && mipk) k_render_tc3<3, 3, 4, 2, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
+  else if (wide_shared) k_render_tc3<3, 3, 4, 1, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
+  else if (wide) k_render_tc3<3, 4, 4, 2, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
+  else if (dynk) k_render_tc3<3, 4, 4, 0, true><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
 #ifdef NF_EXPERIMENTS
-  else if (epiw == 24) k_render_tc3<3, 4, 6, false, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
-  else if (ring == 6) k_render_tc3<6, 2, 4, false, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
+  else if (epiw == 24) k_render_tc3<3, 4, 6, 0, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
+  else if (ring == 6) k_render_tc3<6, 2, 4, 0, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
 #endif
-  else k_render_tc3<3, 4, 4, false, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
+  else k_render_tc3<3, 4, 4, 0, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
 #ifdef NF_TC_STATS
   if (getenv("NF_TC_STATS_PRINT")) {
     cudaStreamSynchronize(st);
