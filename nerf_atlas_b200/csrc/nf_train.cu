@@ -387,87 +387,103 @@ bool build_bw_prog(const NfPlan& plan, const NfTrainPlan& tp, BwProg* P) {
 }
 
 // =====================================================================================================================
-// k_bwd_dw: dWt_l += G_l^T A_l over tiles, MN-major operands straight from the stashes
+// k_bwd_dw: dWt_l += G_l^T A_l over tiles, MN-major operands straight from the stashes, CTA pairs (cta_group::2)
 // =====================================================================================================================
-constexpr int DW_STAGE_G = 32 * 1024, DW_STAGE_B = 64 * 1024, DW_NST = 2;
-constexpr int DW_THREADS = 32 * 6;                 // loader, issuer, 4 writers
-constexpr int DW_MAX_ITEMS = 96, DW_MAX_CTAS = 160;
+// A 256 x 256 fp32 dW block is exactly the TMEM of one SM, so a single CTA would have to cut it in two and read one operand
+// twice.  A CTA pair holds it whole (M = 256 across the pair: rank r accumulates rows 128 r ..), and each CTA stages only ITS
+// half of both operands -- G features [128 r, 128 r + 128) and A-stash columns [N/2 r, N/2 r + N/2) -- so every stash byte is
+// read from HBM exactly once.
+constexpr int DW_STAGE_G = 32 * 1024, DW_STAGE_B = 32 * 1024, DW_NST = 3;
+constexpr int DW_THREADS = 32 * (DW_NST + 5);      // one loader warp per ring stage, issuer (leader CTA), 4 writers
+constexpr int DW_MAX_ITEMS = 64, DW_MAX_PAIRS = 80;
 
 struct DwSmem {
   uint8_t G[DW_NST][DW_STAGE_G];
   uint8_t B[DW_NST][DW_STAGE_B];
-  uint8_t ones[2 * ROWS * 16];                     // [2][128][8] halves of 1.0: db = G^T 1
-  unsigned long long full[DW_NST], empty[DW_NST], acc_full, d_free;
+  uint8_t ones[ROWS * 16];                         // [1 K-group of 8 columns][128 samples][8] halves of 1.0: this CTA's half of the N = 16 bias operand
+  unsigned long long land[DW_NST], full[DW_NST], empty[DW_NST], acc_full, d_free;
   uint32_t tmem_base; uint32_t pad_;
 };
-struct __align__(16) DwItem {     // one [<=128 rows] x [n columns] block of a Linear's dWt
-  uint32_t g_off256, g_tile256, g_sub, g_bytes;          // G stash: tile stride, byte offset of this row block within a tile, bytes to load
-  uint32_t b_off256, b_tile256, b_sub, b_bytes;          // A stash: same for the column block
-  uint32_t n, bias, rows, ld;                            // MMA N; 1 = db rides along; valid rows; leading dimension of dWt
-  uint32_t out_off4, db_off4, pad0_, pad1_;              // float offsets (from ws) of dWt[row0][col0] and db[row0]
+static_assert(sizeof(DwSmem) <= 227 * 1024, "dW smem");
+struct __align__(16) DwItem {     // one [n_pad rows] x [n columns] block of a Linear's dWt
+  uint32_t g_off256, g_tile256, b_off256, b_tile256;
+  uint32_t g_sub[2], g_bytes[2];                         // per CTA rank: byte offset within a G tile, bytes (0: nothing for this rank)
+  uint32_t b_sub[2], b_bytes[2];                         // per CTA rank: byte offset within an A-stash tile, bytes
+  uint32_t n, bias, rows, ld;                            // MMA N; 1 = db rides along; valid rows (n_pad); leading dimension of dWt
+  uint32_t out_off4, db_off4, pad0_, pad1_;              // float offsets (from ws) of dWt[0][col0] and db[0]
 };
 struct __align__(16) DwProg {
-  int32_t n_items, n_ctas, pad0_, pad1_;
+  int32_t n_items, n_pairs, pad0_, pad1_;
   DwItem item[DW_MAX_ITEMS];
-  int32_t cta_item[DW_MAX_CTAS + 1]; int32_t cta_tile[DW_MAX_CTAS + 1];   // CTA c runs (item, tile) from [c] up to [c+1]
+  int32_t pair_item[DW_MAX_PAIRS + 1]; int32_t pair_tile[DW_MAX_PAIRS + 1];   // pair c runs (item, tile) from [c] up to [c+1]
 };
-struct DwArgs { uint8_t* ws; long long n_tiles; int swap_lbo_sbo; };
+struct DwArgs { uint8_t* ws; long long n_tiles; };
 
-__global__ void __launch_bounds__(DW_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DW_THREADS, 1)
 k_bwd_dw(const __grid_constant__ DwProg prog, const DwArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   DwSmem& s = *reinterpret_cast<DwSmem*>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < 2 * ROWS * 4; i += DW_THREADS) reinterpret_cast<uint32_t*>(s.ones)[i] = 0x3C003C00u;
+  const uint32_t crank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  for (int i = threadIdx.x; i < ROWS * 4; i += DW_THREADS) reinterpret_cast<uint32_t*>(s.ones)[i] = 0x3C003C00u;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < DW_NST; ++i) { mbar_init(smem_u32(&s.full[i]), 1); mbar_init(smem_u32(&s.empty[i]), 1); }
-    mbar_init(smem_u32(&s.acc_full), 1); mbar_init(smem_u32(&s.d_free), 4);
+    for (int i = 0; i < DW_NST; ++i) { mbar_init(smem_u32(&s.land[i]), 1); mbar_init(smem_u32(&s.full[i]), 2); mbar_init(smem_u32(&s.empty[i]), 1); }
+    mbar_init(smem_u32(&s.acc_full), 1); mbar_init(smem_u32(&s.d_free), 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(512) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem = s.tmem_base;
-  const int it_b = prog.cta_item[blockIdx.x], it_e = prog.cta_item[blockIdx.x + 1];
-  const long long t_b = prog.cta_tile[blockIdx.x], t_e = prog.cta_tile[blockIdx.x + 1];
+  const int it_b = prog.pair_item[pair], it_e = prog.pair_item[pair + 1];
+  const long long t_b = prog.pair_tile[pair], t_e = prog.pair_tile[pair + 1];
 
-  if (warp == 0) {
-    // ================= loader =================
+  if (warp < DW_NST) {
+    // ================= loaders (both CTAs), one warp per ring stage: this rank's halves of G and of the A stash =================
+    // (a loader waits for its own copy to land before it tells the leader, so one thread per stage keeps DW_NST copies in flight)
     if (elect_one()) {
+      const uint32_t mine = (uint32_t)warp;
       uint32_t stage = 0, use = 0;
       for (int it = it_b; it <= it_e && it < prog.n_items; ++it) {
         const DwItem& I = prog.item[it];
         const long long t0 = it == it_b ? t_b : 0, t1 = it == it_e ? t_e : a.n_tiles;
+        const uint32_t gb = I.g_bytes[crank], bb = I.b_bytes[crank];
         for (long long t = t0; t < t1; ++t) {
-          mbar_wait(smem_u32(&s.empty[stage]), ((use / DW_NST) & 1u) ^ 1u);
-          mbar_expect_tx(smem_u32(&s.full[stage]), I.g_bytes + I.b_bytes);
-          bulk_g2s(smem_u32(s.G[stage]), a.ws + ((size_t)I.g_off256 + (size_t)t * I.g_tile256) * 256 + I.g_sub, I.g_bytes, smem_u32(&s.full[stage]));
-          bulk_g2s(smem_u32(s.B[stage]), a.ws + ((size_t)I.b_off256 + (size_t)t * I.b_tile256) * 256 + I.b_sub, I.b_bytes, smem_u32(&s.full[stage]));
+          if (stage == mine) {
+            const uint32_t par = (use / DW_NST) & 1u;
+            mbar_wait(smem_u32(&s.empty[stage]), par ^ 1u);
+            mbar_expect_tx(smem_u32(&s.land[stage]), gb + bb);
+            if (gb) bulk_g2s(smem_u32(s.G[stage]), a.ws + ((size_t)I.g_off256 + (size_t)t * I.g_tile256) * 256 + I.g_sub[crank], gb, smem_u32(&s.land[stage]));
+            if (bb) bulk_g2s(smem_u32(s.B[stage]), a.ws + ((size_t)I.b_off256 + (size_t)t * I.b_tile256) * 256 + I.b_sub[crank], bb, smem_u32(&s.land[stage]));
+            mbar_wait(smem_u32(&s.land[stage]), par);                         // landed in THIS CTA ...
+            mbar_arrive_cluster_relaxed(leader_addr(smem_u32(&s.full[stage])));   // ... tell the leader's MMA thread
+          }
           ++use; if (++stage == DW_NST) stage = 0;
         }
       }
     }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (elect_one()) {
-      uint32_t stage = 0, use = 0, free_par = 0; bool first_item = true;
+  } else if (warp == DW_NST) {
+    // ================= MMA issuer (leader CTA) =================
+    if (crank == 0 && elect_one()) {
+      uint32_t stage = 0, use = 0, free_par = 0; bool first_run = true;
       // MN-major canonical layout of a [K/8][128][8] image read "transposed": cores of 8 samples x 8 features, 128 B each;
       // along the samples (the MMA's K) cores are 128 B apart (LBO), along the features (M / N) 2048 B apart (SBO)
-      const uint32_t lbo = a.swap_lbo_sbo ? (uint32_t)KG_BYTES : 128u, sbo = a.swap_lbo_sbo ? 128u : (uint32_t)KG_BYTES;
-      const uint64_t hi = ((uint64_t)(0x4000u | (sbo >> 4)) << 32) | ((uint64_t)(lbo >> 4) << 16);
+      const uint64_t hi = ((uint64_t)(0x4000u | ((uint32_t)KG_BYTES >> 4)) << 32) | ((uint64_t)(128u >> 4) << 16);
       for (int it = it_b; it <= it_e && it < prog.n_items; ++it) {
         const DwItem& I = prog.item[it];
         const long long t0 = it == it_b ? t_b : 0, t1 = it == it_e ? t_e : a.n_tiles;
         if (t0 >= t1) continue;
-        if (!first_item) { mbar_wait(smem_u32(&s.d_free), free_par); free_par ^= 1u; tc_fence_after(); }
-        first_item = false;
-        const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((I.n >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
-        const uint32_t idesc1 = (1u << 4) | (1u << 15) | (1u << 16) | ((16u >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
+        if (!first_run) { mbar_wait(smem_u32(&s.d_free), free_par); free_par ^= 1u; tc_fence_after(); }
+        first_run = false;
+        const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((I.n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+        const uint32_t idesc1 = (1u << 4) | (1u << 15) | (1u << 16) | ((16u >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
         for (long long t = t0; t < t1; ++t) {
           mbar_wait(smem_u32(&s.full[stage]), (use / DW_NST) & 1u);
           tc_fence_after();
@@ -475,19 +491,19 @@ k_bwd_dw(const __grid_constant__ DwProg prog, const DwArgs a) {
 #pragma unroll 1
           for (uint32_t k = 0; k < 8; ++k) {                     // 16 samples per MMA
             const uint32_t acc = (t > t0 || k > 0) ? 1u : 0u;
-            umma_f16(tmem, hi | (uint64_t)(g4 + k * 16u), hi | (uint64_t)(b4 + k * 16u), idesc, acc);
-            if (I.bias) umma_f16(tmem + I.n, hi | (uint64_t)(g4 + k * 16u), hi | (uint64_t)(o4 + k * 16u), idesc1, acc);
+            umma2_f16(tmem, hi | (uint64_t)(g4 + k * 16u), hi | (uint64_t)(b4 + k * 16u), idesc, acc);
+            if (I.bias) umma2_f16(tmem + I.n, hi | (uint64_t)(g4 + k * 16u), hi | (uint64_t)(o4 + k * 16u), idesc1, acc);
           }
-          umma_commit(smem_u32(&s.empty[stage]));
+          umma2_commit_mc(smem_u32(&s.empty[stage]));
           ++use; if (++stage == DW_NST) stage = 0;
         }
-        umma_commit(smem_u32(&s.acc_full));
+        umma2_commit_mc(smem_u32(&s.acc_full));
       }
     }
   } else {
-    // ================= writers: TMEM -> fp32 atomics into dWt / db =================
+    // ================= writers (both CTAs): TMEM -> fp32 atomics into dWt / db; rank r owns rows 128 r .. =================
     const int q = warp & 3;
-    const int row = q * 32 + lane;
+    const int row = (int)crank * ROWS + q * 32 + lane;
     const uint32_t t_lane = tmem + ((uint32_t)(q * 32) << 16);
     float* wsf = reinterpret_cast<float*>(a.ws);
     uint32_t par = 0;
@@ -514,61 +530,65 @@ k_bwd_dw(const __grid_constant__ DwProg prog, const DwArgs a) {
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&s.d_free));
+      if (lane == 0) mbar_arrive_cluster_relaxed(leader_addr(smem_u32(&s.d_free)));
     }
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();
   if (warp == 0) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
   }
 }
+static_assert(((DW_NST + 1) & 3) == 0, "the four writer warps must cover the four TMEM lane quarters (warp % 4)");
 
-bool build_dw_prog(const NfTrainPlan& tp, int n_ctas, DwProg* P) {
+bool build_dw_prog(const NfTrainPlan& tp, int n_pairs, DwProg* P) {
   *P = DwProg{};
   int ni = 0;
   long long cost[DW_MAX_ITEMS];
   for (int li = 0; li < tp.n_lin; ++li) {
     const NfTrainLin& L = tp.lin[li];
     const int kt = L.k0_pad + L.k_hidden;
-    for (int r0 = 0; r0 < L.n_pad; r0 += 128) {
-      bool bias_done = false;
-      // column blocks: the x0 part (<= 128 columns), the hidden part (256)
-      const int blocks[2][2] = {{0, L.k0_pad}, {L.k0_pad, L.k_hidden}};
-      for (int b = 0; b < 2; ++b) {
-        const int c0 = blocks[b][0], nc = blocks[b][1];
-        if (!nc) continue;
-        if (ni >= DW_MAX_ITEMS || nc > 256) return false;
-        DwItem& I = P->item[ni];
-        const int rows = L.n_pad - r0 < 128 ? L.n_pad - r0 : 128;
-        I.g_off256 = (uint32_t)(L.g_off >> 8); I.g_tile256 = (uint32_t)(L.g_tile >> 8); I.g_sub = (uint32_t)r0 * 256u; I.g_bytes = (uint32_t)rows * 256u;
-        I.b_off256 = (uint32_t)(L.a_off >> 8); I.b_tile256 = (uint32_t)(L.a_tile >> 8); I.b_sub = (uint32_t)c0 * 256u; I.b_bytes = (uint32_t)nc * 256u;
-        I.n = (uint32_t)nc; I.bias = bias_done ? 0u : 1u; bias_done = true; I.rows = (uint32_t)rows; I.ld = (uint32_t)kt;
-        const int64_t o = L.dw_off / 4 + (int64_t)r0 * kt + c0, ob = L.db_off / 4 + r0;
-        if (o >= (1LL << 32) || ob >= (1LL << 32)) return false;
-        I.out_off4 = (uint32_t)o; I.db_off4 = (uint32_t)ob;
-        cost[ni] = (long long)(I.g_bytes + I.b_bytes) / 256;
-        ++ni;
+    bool bias_done = false;
+    // column blocks: the x0 part (<= 256 columns), the hidden part (256)
+    const int blocks[2][2] = {{0, L.k0_pad}, {L.k0_pad, L.k_hidden}};
+    for (int b = 0; b < 2; ++b) {
+      const int c0 = blocks[b][0], nc = blocks[b][1];
+      if (!nc) continue;
+      if (ni >= DW_MAX_ITEMS || nc > 256 || (nc & 15) || L.n_pad > 256) return false;
+      DwItem& I = P->item[ni];
+      I.g_off256 = (uint32_t)(L.g_off >> 8); I.g_tile256 = (uint32_t)(L.g_tile >> 8);
+      I.b_off256 = (uint32_t)(L.a_off >> 8); I.b_tile256 = (uint32_t)(L.a_tile >> 8);
+      for (int r = 0; r < 2; ++r) {
+        const int rows = L.n_pad - 128 * r < 0 ? 0 : (L.n_pad - 128 * r < 128 ? L.n_pad - 128 * r : 128);
+        I.g_sub[r] = (uint32_t)(128 * r) * 256u; I.g_bytes[r] = (uint32_t)rows * 256u;
+        I.b_sub[r] = (uint32_t)(c0 + r * (nc / 2)) * 256u; I.b_bytes[r] = (uint32_t)(nc / 2) * 256u;
       }
+      I.n = (uint32_t)nc; I.bias = bias_done ? 0u : 1u; bias_done = true; I.rows = (uint32_t)L.n_pad; I.ld = (uint32_t)kt;
+      const int64_t o = L.dw_off / 4 + c0, ob = L.db_off / 4;
+      if (o >= (1LL << 32) || ob >= (1LL << 32) || (L.a_off >> 8) >= (1LL << 32) || (L.g_off >> 8) >= (1LL << 32)) return false;
+      I.out_off4 = (uint32_t)o; I.db_off4 = (uint32_t)ob;
+      cost[ni] = (long long)(L.n_pad + nc) + 32;           // bytes / 256 per tile (+ a fixed per-tile overhead)
+      ++ni;
     }
   }
   P->n_items = ni;
-  if (n_ctas > DW_MAX_CTAS) n_ctas = DW_MAX_CTAS;
+  if (n_pairs > DW_MAX_PAIRS) n_pairs = DW_MAX_PAIRS;
   long long total = 0;
   for (int i = 0; i < ni; ++i) total += cost[i] * tp.n_tiles;
-  if (total == 0) { P->n_ctas = 0; return true; }
-  if ((long long)n_ctas > (long long)ni * tp.n_tiles) n_ctas = (int)((long long)ni * tp.n_tiles);
-  P->n_ctas = n_ctas;
-  // CTA c starts at the first (item, tile) whose preceding cost reaches c * total / n_ctas
+  if (total == 0) { P->n_pairs = 0; return true; }
+  if ((long long)n_pairs > (long long)ni * tp.n_tiles) n_pairs = (int)((long long)ni * tp.n_tiles);
+  P->n_pairs = n_pairs;
+  // pair c starts at the first (item, tile) whose preceding cost reaches c * total / n_pairs
   int it = 0; long long acc = 0;                       // acc = cost of all items before `it`
-  for (int c = 0; c <= n_ctas; ++c) {
-    const long long want = c == n_ctas ? total : (total * c) / n_ctas;
+  for (int c = 0; c <= n_pairs; ++c) {
+    const long long want = c == n_pairs ? total : (total * c) / n_pairs;
     while (it < ni && acc + cost[it] * tp.n_tiles <= want) { acc += cost[it] * tp.n_tiles; ++it; }
     long long tile = it < ni ? (want - acc + cost[it] - 1) / cost[it] : 0;
     if (it < ni && tile >= tp.n_tiles) { acc += cost[it] * tp.n_tiles; ++it; tile = 0; }
     if (tile >= (1LL << 31)) return false;
-    P->cta_item[c] = it; P->cta_tile[c] = (int32_t)tile;
+    P->pair_item[c] = it; P->pair_tile[c] = (int32_t)tile;
   }
   return true;
 }
@@ -676,10 +696,10 @@ cudaError_t nf_launch_render_backward(const NfPlan& plan, const NfTrainPlan& tp,
   // 4. dW / db
   {
     DwProg prog;
-    if (!build_dw_prog(tp, sms, &prog)) return cudaErrorNotSupported;
-    DwArgs a{}; a.ws = ws; a.n_tiles = tp.n_tiles; a.swap_lbo_sbo = 0;
+    if (!build_dw_prog(tp, sms / 2, &prog)) return cudaErrorNotSupported;
+    DwArgs a{}; a.ws = ws; a.n_tiles = tp.n_tiles;
     if ((e = cudaFuncSetAttribute(k_bwd_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DwSmem))) != cudaSuccess) return e;
-    if (prog.n_ctas > 0) k_bwd_dw<<<prog.n_ctas, DW_THREADS, sizeof(DwSmem), st>>>(prog, a);
+    if (prog.n_pairs > 0) k_bwd_dw<<<2 * prog.n_pairs, DW_THREADS, sizeof(DwSmem), st>>>(prog, a);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   // 5. reference layout
