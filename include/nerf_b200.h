@@ -290,6 +290,23 @@ int nf_render_backward(const nf_model_desc* desc, const void* packed, void* trai
                        const float* rays, int64_t n_rays, const float* ts, int32_t T, int64_t ts_ray_stride,
                        const float* d_rgb, float* const* grads_host, int32_t n_grads, void* stream);
 
+/* ---- the SDF surface side --------------------------------------------------------------------------
+ * `desc` = a VolSDF-style descriptor (describe_volsdf): density MLP = the SDF network (SIREN: NF_ENC_NONE, or the Fourier-
+ * encoded MLP), refl = the View head.  All kernels of a call are stream-ordered, with no host round trip: the set of active rays
+ * is compacted on the device and the MLP kernels (CUDA-core fp32, or tcgen05 for the SIREN network) read its size from there. */
+int64_t nf_sdf_workspace_bytes(const nf_model_desc* desc, int64_t n_rays);
+/* sphere_march (reference src/march.py:27-47): t = near; `iters` times, for the rays still active: d = sdf(o + t dir)
+ * [max(d, |p| - bound_rad) with bound_rad > 0: UnitSphere, src/sdf.py:66-83]; hit |= d < eps && t <= far; t += d; a ray leaves
+ * the active set once hit or t > far.  Outputs (nullable): pts_out[R,3] = o + t dir, hit_out[R] (0/1 bytes), t_out[R]. */
+int nf_sphere_march(const nf_model_desc* desc, const void* packed, const float* rays, int64_t n_rays, float t_near, float t_far,
+                    int32_t iters, float eps, float bound_rad, int32_t precision, float* pts_out, uint8_t* hit_out, float* t_out,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+/* SDF.forward in eval mode (reference src/sdf.py:137-156): sphere_march, latent = sdf_net(pts[hit])[1:], rgb[hit] =
+ * act(View([pts, elaz(r_d), latent])), rgb[~hit] = 0.  rgb_out[R,3]; the other outputs as above (nullable). */
+int nf_sdf_render(const nf_model_desc* desc, const void* packed, const float* rays, int64_t n_rays, float t_near, float t_far,
+                  int32_t iters, float eps, float bound_rad, int32_t precision, float* rgb_out, uint8_t* hit_out, float* t_out,
+                  float* pts_out, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- backward of the non-GEMM stages (first blocks of the training half; the reference differentiates these ops through
  *      PyTorch autograd, runner.py:820) --------------------------------------------------------------------------- */
 /* Backward of nf_composite: d_rgb[R,3] -> d_sigma_raw_out[R,T], d_feats_out[R,T,3] (same inputs as the forward; T <= 2048).

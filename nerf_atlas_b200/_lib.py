@@ -68,6 +68,11 @@ EXPORTS = {
   "nf_train_layout_of": (C.c_int, [C.POINTER(ModelDesc), C.c_int64, C.c_int32, C.POINTER(TrainLayout)]),
   "nf_render_backward": (C.c_int, [C.POINTER(ModelDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
                                    C.c_int64, C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
+  "nf_sdf_workspace_bytes": (C.c_int64, [C.POINTER(ModelDesc), C.c_int64]),
+  "nf_sphere_march": (C.c_int, [C.POINTER(ModelDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_int32, C.c_float, C.c_float,
+                                C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+  "nf_sdf_render": (C.c_int, [C.POINTER(ModelDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_int32, C.c_float, C.c_float,
+                              C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
   "nf_generate_rays": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_void_p, C.c_void_p]),
   "nf_generate_rays_dtu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

@@ -319,6 +319,50 @@ int nf_mlp_forward(const nf_model_desc* desc, const void* packed, int32_t which,
   return e == cudaSuccess ? 0 : cuda_fail(e, "nf_mlp_forward");
 }
 
+namespace {
+int sdf_check(const nf_model_desc* desc, NfPlan* p, const void* packed, const float* rays, int64_t n_rays, int32_t iters, int32_t precision,
+              void* workspace, int64_t workspace_bytes) {
+  if (int rc = plan_of(desc, p)) return rc;
+  if (p->kind != NF_KIND_PLAIN || p->mip != NF_MIP_NONE || p->refl_kind != NF_REFL_VIEW || (p->enc != NF_ENC_NONE && p->enc != NF_ENC_FOURIER))
+    return fail(NF_E_UNSUPPORTED, "SDF surface side: a VolSDF-style descriptor (SIREN or Fourier-encoded SDF network + View head)");
+  if (n_rays < 0 || iters < 0 || iters > 1000) return fail(NF_E_BADARG, "SDF surface side: n_rays >= 0, 0 <= iters <= 1000");
+  if (n_rays >= (1LL << 31)) return fail(NF_E_UNSUPPORTED, "SDF surface side: fewer than 2^31 rays per call");
+  if (precision != NF_PREC_FP32 && precision != NF_PREC_FP16_TC) return fail(NF_E_BADARG, "unknown precision");
+  if (precision == NF_PREC_FP16_TC && p->enc == NF_ENC_FOURIER)
+    return fail(NF_E_UNSUPPORTED, "SDF surface side: the Fourier-encoded SDF network runs on NF_PREC_FP32 only (x0 is 259 wide)");
+  if (n_rays == 0) return 0;
+  if (!packed || !rays || !workspace) return fail(NF_E_BADARG, "SDF surface side: null pointer");
+  if (((uintptr_t)workspace & 255) != 0) return fail(NF_E_BADARG, "SDF surface side: workspace must be 256-byte aligned");
+  if (workspace_bytes < nf_sdf_workspace_bytes_of(*p, n_rays)) return fail(NF_E_SMALLBUF, "SDF surface side: workspace too small (nf_sdf_workspace_bytes)");
+  return 0;
+}
+}  // namespace
+
+int64_t nf_sdf_workspace_bytes(const nf_model_desc* desc, int64_t n_rays) {
+  NfPlan p; if (int rc = plan_of(desc, &p)) return rc;
+  if (n_rays < 0) return fail(NF_E_BADARG, "n_rays < 0");
+  return nf_sdf_workspace_bytes_of(p, n_rays);
+}
+
+int nf_sphere_march(const nf_model_desc* desc, const void* packed, const float* rays, int64_t n_rays, float t_near, float t_far, int32_t iters,
+                    float eps, float bound_rad, int32_t precision, float* pts_out, uint8_t* hit_out, float* t_out, void* workspace,
+                    int64_t workspace_bytes, void* stream) {
+  NfPlan p; if (int rc = sdf_check(desc, &p, packed, rays, n_rays, iters, precision, workspace, workspace_bytes)) return rc;
+  if (n_rays == 0) return 0;
+  cudaError_t e = nf_launch_sphere_march(p, packed, rays, n_rays, t_near, t_far, iters, eps, bound_rad, precision, pts_out, hit_out, t_out, workspace, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nf_sphere_march");
+}
+
+int nf_sdf_render(const nf_model_desc* desc, const void* packed, const float* rays, int64_t n_rays, float t_near, float t_far, int32_t iters,
+                  float eps, float bound_rad, int32_t precision, float* rgb_out, uint8_t* hit_out, float* t_out, float* pts_out, void* workspace,
+                  int64_t workspace_bytes, void* stream) {
+  NfPlan p; if (int rc = sdf_check(desc, &p, packed, rays, n_rays, iters, precision, workspace, workspace_bytes)) return rc;
+  if (n_rays == 0) return 0;
+  if (!rgb_out) return fail(NF_E_BADARG, "nf_sdf_render: null rgb_out");
+  cudaError_t e = nf_launch_sdf_render(p, packed, rays, n_rays, t_near, t_far, iters, eps, bound_rad, precision, rgb_out, hit_out, t_out, pts_out, workspace, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nf_sdf_render");
+}
+
 int nf_composite_backward(const nf_model_desc* desc, const void* packed, const float* sigma_raw, const float* feats,
                           const float* rays, int64_t n_rays, const float* ts, int32_t T, int64_t ts_ray_stride,
                           const float* d_rgb, float* d_sigma_raw_out, float* d_feats_out, void* stream) {

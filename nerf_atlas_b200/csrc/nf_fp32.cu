@@ -307,10 +307,11 @@ k_render_fp32(const __grid_constant__ NfPlan plan, const RenderArgs a) {
 // Stand-alone SkipConnMLP on assembled inputs x0[N,in] -> out[N,out].
 __global__ void __launch_bounds__(THREADS, 1)
 k_mlp_fp32(const __grid_constant__ NfPlan plan, int which, const uint8_t* __restrict__ packed,
-           const float* __restrict__ x0, long long n, float* __restrict__ out) {
+           const float* __restrict__ x0, long long n, float* __restrict__ out, const long long* __restrict__ n_dev) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   Fp32Smem& s = *reinterpret_cast<Fp32Smem*>(smem_raw);
   const NfMlpPlan& M = plan.mlp[which];
+  if (n_dev) n = *n_dev;                                 // row count from device memory (stream-ordered loops, e.g. the sphere march)
   const long long tiles = (n + ROWS - 1) / ROWS;
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     for (int i = threadIdx.x; i < M.in_dims * ROWS; i += THREADS) {
@@ -651,13 +652,14 @@ cudaError_t nf_launch_render_fp32(const NfPlan& plan, const void* packed, const 
   return cudaGetLastError();
 }
 
-cudaError_t nf_launch_mlp_fp32(const NfPlan& plan, int which, const void* packed, const float* x0, int64_t n, float* out, cudaStream_t st) {
+cudaError_t nf_launch_mlp_fp32(const NfPlan& plan, int which, const void* packed, const float* x0, int64_t n, float* out, cudaStream_t st,
+                               const long long* n_dev) {
   cudaError_t e = cudaFuncSetAttribute(k_mlp_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Fp32Smem));
   if (e != cudaSuccess) return e;
   const long long tiles = (n + ROWS - 1) / ROWS;
   if (tiles == 0) return cudaSuccess;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  k_mlp_fp32<<<grid, THREADS, sizeof(Fp32Smem), st>>>(plan, which, (const uint8_t*)packed, x0, n, out);
+  k_mlp_fp32<<<grid, THREADS, sizeof(Fp32Smem), st>>>(plan, which, (const uint8_t*)packed, x0, n, out, n_dev);
   return cudaGetLastError();
 }
 

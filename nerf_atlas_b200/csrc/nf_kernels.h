@@ -15,8 +15,18 @@ cudaError_t nf_launch_ray_radii(const float* rays, int64_t B, int H, int W, floa
 cudaError_t nf_launch_render_tc(const NfPlan& plan, const void* packed, const float* rays, int64_t n_rays, const float* ts,
                                 int T, int64_t ts_stride, const float* noise, float* rgb, float* alpha, float* weights,
                                 cudaStream_t st);
-cudaError_t nf_launch_mlp_fp32(const NfPlan& plan, int which, const void* packed, const float* x0, int64_t n, float* out, cudaStream_t st);
-cudaError_t nf_launch_mlp_tc(const NfPlan& plan, int which, const void* packed, const float* x0, int64_t n, float* out, cudaStream_t st);
+// n_dev (nullable): the row count lives in device memory and n is only the capacity that sizes the grid
+cudaError_t nf_launch_mlp_fp32(const NfPlan& plan, int which, const void* packed, const float* x0, int64_t n, float* out, cudaStream_t st,
+                               const long long* n_dev = nullptr);
+cudaError_t nf_launch_mlp_tc(const NfPlan& plan, int which, const void* packed, const float* x0, int64_t n, float* out, cudaStream_t st,
+                             const long long* n_dev = nullptr);
+// SDF surface side (nf_march.cu): sphere tracing + shading of the hit points
+cudaError_t nf_launch_sphere_march(const NfPlan& plan, const void* packed, const float* rays, int64_t n_rays, float near, float far, int iters,
+                                   float eps, float bound_rad, int precision, float* pts_out, uint8_t* hit_out, float* t_out, void* ws, cudaStream_t st);
+cudaError_t nf_launch_sdf_render(const NfPlan& plan, const void* packed, const float* rays, int64_t n_rays, float near, float far, int iters,
+                                 float eps, float bound_rad, int precision, float* rgb_out, uint8_t* hit_out, float* t_out, float* pts_out,
+                                 void* ws, cudaStream_t st);
+int64_t nf_sdf_workspace_bytes_of(const NfPlan& plan, int64_t n_rays);
 cudaError_t nf_launch_sample_points(const float* rays, int64_t n_rays, const float* ts, int T, int64_t ts_stride, float* pts, cudaStream_t st);
 cudaError_t nf_launch_hash_encode(const NfPlan& plan, const void* packed, const float* pts, int64_t n, float* feats, uint16_t* idx, cudaStream_t st);
 cudaError_t nf_launch_composite(const NfPlan& plan, const void* packed, const float* sigma_raw, const float* feats, const float* rays, int64_t n_rays,

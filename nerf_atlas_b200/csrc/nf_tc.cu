@@ -70,6 +70,7 @@ struct TcArgs {
   float* rgb_out; float* alpha_out; float* weights_out;
   // MLP-only mode
   int mlp_only; int which; const float* x0; long long n; float* out;
+  const long long* n_dev;   // MLP-only mode: if set, the number of rows is read from device memory (stream-ordered loops such as the sphere march: no host round trip)
   long long* trace;   // debug & 4: clock64 timeline of one tile of block 0: [role][512] x {tag, clock}
   int debug;   // timing experiments only (NF_TC_DEBUG): 1 = epilogue does no work, 2 = no MMA issued
 };
@@ -84,7 +85,7 @@ struct TcArgs {
 struct TileIter {
   long long units, trips; int tpr;   // every CTA makes `trips` passes; passes with u >= units are all-masked tiles
   __device__ TileIter(const TcArgs& a, const NfTileMap& map) {
-    if (a.mlp_only) { units = (a.n + ROWS - 1) / ROWS; tpr = 1; } else { units = map.units(a.n_rays); tpr = map.tpr; }
+    if (a.mlp_only) { units = ((a.n_dev ? *a.n_dev : a.n) + ROWS - 1) / ROWS; tpr = 1; } else { units = map.units(a.n_rays); tpr = map.tpr; }
     trips = (units + gridDim.x - 1) / gridDim.x;
   }
 };
@@ -358,7 +359,7 @@ k_render_tc(const __grid_constant__ NfPlan plan, const __grid_constant__ TcProg 
           for (int i = e_tid; i < M.in_dims * ROWS; i += EPI_THREADS) {
             const int r = i / M.in_dims, k = i - r * M.in_dims;
             const long long g = u * ROWS + r;
-            const float v = g < a.n ? __ldg(a.x0 + g * M.in_dims + k) : 0.f;
+            const float v = g < (a.n_dev ? *a.n_dev : a.n) ? __ldg(a.x0 + g * M.in_dims + k) : 0.f;
             const int kt = nf_x0_perm(plan, a.which, k);
             const int off = (kt >> 3) * KG_BYTES + r * 16 + (kt & 7) * 2;
             *reinterpret_cast<__half*>(s.X0raw + off) = __float2half_rn(v);
@@ -451,7 +452,7 @@ k_render_tc(const __grid_constant__ NfPlan plan, const __grid_constant__ TcProg 
               for (int un = half; un < (L.n_pad >> 4); un += 2) {
                 uint32_t v[16];
                 tmem_ld16(t_acc + un * 16, v); tmem_ld_wait(); reg_fence16(v);
-                if (g < a.n) {
+                if (g < (a.n_dev ? *a.n_dev : a.n)) {
 #pragma unroll
                   for (int i = 0; i < 16; ++i) {
                     const int nt = un * 16 + i;
@@ -675,8 +676,9 @@ cudaError_t nf_launch_render_tc(const NfPlan& plan, const void* packed, const fl
   return launch_tc(plan, a, map.units(n_rays), st);
 }
 
-cudaError_t nf_launch_mlp_tc(const NfPlan& plan, int which, const void* packed, const float* x0, int64_t n, float* out, cudaStream_t st) {
+cudaError_t nf_launch_mlp_tc(const NfPlan& plan, int which, const void* packed, const float* x0, int64_t n, float* out, cudaStream_t st,
+                             const long long* n_dev) {
   TcArgs a{};
-  a.packed = (const uint8_t*)packed; a.mlp_only = 1; a.which = which; a.x0 = x0; a.n = n; a.out = out; a.T = ROWS;
-  return launch_tc(plan, a, (n + ROWS - 1) / ROWS, st);
+  a.packed = (const uint8_t*)packed; a.mlp_only = 1; a.which = which; a.x0 = x0; a.n = n; a.out = out; a.T = ROWS; a.n_dev = n_dev;
+  return launch_tc(plan, a, (n + ROWS - 1) / ROWS, st);      // with n_dev, n is the capacity (an upper bound: it sizes the grid)
 }

@@ -309,6 +309,42 @@ class RenderEngine:
     _lib.check(rc, "nf_render_forward")
     return rgb, alpha, weights
 
+  # ---- the SDF surface side (include/nerf_b200.h: nf_sphere_march / nf_sdf_render) ----
+  def _sdf_ws(self, n_rays: int, device) -> torch.Tensor:
+    nbytes = int(self.lib.nf_sdf_workspace_bytes(C.byref(self.desc), int(n_rays)))
+    if nbytes < 0: _lib.check(nbytes, "nf_sdf_workspace_bytes")
+    raw = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+    off = (-raw.data_ptr()) % 256
+    return raw[off:off + nbytes]
+
+  def sphere_march(self, rays: torch.Tensor, near: float, far: float, iters: int = 32, eps: float = 1e-3, bound_rad: float = -1.0,
+                   precision: Optional[str] = None):
+    """march.sphere_march (reference src/march.py:27-47) of the descriptor's SDF network: rays[R,6] -> (pts[R,3], hit[R] bool, t[R])."""
+    self._need_packed(); _chk(rays, "rays")
+    R = rays.shape[0]
+    pts = torch.empty(R, 3, dtype=torch.float32, device=rays.device); t = torch.empty(R, dtype=torch.float32, device=rays.device)
+    hit = torch.empty(R, dtype=torch.uint8, device=rays.device)
+    ws = self._sdf_ws(R, rays.device)
+    with torch.cuda.device(rays.device):
+      rc = self.lib.nf_sphere_march(C.byref(self.desc), _ptr(self.packed), _ptr(rays), R, float(near), float(far), int(iters), float(eps), float(bound_rad),
+                                    _lib.PRECISION[precision or self.precision], _ptr(pts), _ptr(hit), _ptr(t), _ptr(ws), ws.numel(), self._stream())
+    _lib.check(rc, "nf_sphere_march")
+    return pts, hit.bool(), t
+
+  def sdf_render(self, rays: torch.Tensor, near: float, far: float, iters: int = 192, eps: float = 1e-3, bound_rad: float = -1.0,
+                 precision: Optional[str] = None):
+    """SDF.forward in eval mode (reference src/sdf.py:137-156): rays[R,6] -> (rgb[R,3], hit[R] bool, t[R], pts[R,3])."""
+    self._need_packed(); _chk(rays, "rays")
+    R = rays.shape[0]
+    rgb = torch.empty(R, 3, dtype=torch.float32, device=rays.device); pts = torch.empty(R, 3, dtype=torch.float32, device=rays.device)
+    t = torch.empty(R, dtype=torch.float32, device=rays.device); hit = torch.empty(R, dtype=torch.uint8, device=rays.device)
+    ws = self._sdf_ws(R, rays.device)
+    with torch.cuda.device(rays.device):
+      rc = self.lib.nf_sdf_render(C.byref(self.desc), _ptr(self.packed), _ptr(rays), R, float(near), float(far), int(iters), float(eps), float(bound_rad),
+                                  _lib.PRECISION[precision or self.precision], _ptr(rgb), _ptr(hit), _ptr(t), _ptr(pts), _ptr(ws), ws.numel(), self._stream())
+    _lib.check(rc, "nf_sdf_render")
+    return rgb, hit.bool(), t, pts
+
   # ---- stage entry points (parity tests, micro-benchmarks) ----
   def sample_points(self, rays: torch.Tensor, ts: torch.Tensor) -> torch.Tensor:
     _chk(rays, "rays"); _chk(ts, "ts")
@@ -754,6 +790,79 @@ class FusedVolSDF(FusedNeRF):
       else: ps.append(net.enc.basis)
     ps.append(self.scale.reshape(1) if self.scale.dim() == 0 else self.scale)
     return ps
+
+
+class FusedSDF(nn.Module):
+  """Drop-in for the surface renderer `sdf.SDF` (reference src/sdf.py:86-156; `--model sdf --sdf-isect-kind sphere`) with a View
+  head, evaluation mode: sphere tracing of the SDF network (SIREN or Fourier-encoded MLP), then the View head on the hit points;
+  rays that miss render black.  Parameter names follow the reference (`underlying.{siren|mlp}.*`, `refl.mlp.*`).  Training of
+  the surface model (throughput term, normals: sdf.py:120-125,150-153) is not built: forward under grad raises."""
+
+  def __init__(self, sdf_kind: str = "siren", intermediate_size: int = 64, t_near: float = 0, t_far: float = 1, sigmoid_kind: str = "thin",
+               bound_sphere_rad: float = -1.0, precision: str = "fp32"):
+    super().__init__()
+    self.underlying = _SdfNet(sdf_kind, intermediate_size)
+    self.refl = ViewHead(latent_size=intermediate_size, out_features=3, act=sigmoid_kind)
+    self.near, self.far, self.bound_sphere_rad, self.precision = t_near, t_far, bound_sphere_rad, precision
+    self._engine: Optional[RenderEngine] = None
+    self._engine_key = None
+
+  @classmethod
+  def from_reference(cls, ref, precision: str = "fp32") -> "FusedSDF":
+    """Adopt a live reference `sdf.SDF` (sphere-march intersection, View head); a `UnitSphere` wrapper becomes `bound_sphere_rad`."""
+    self = cls.__new__(cls); nn.Module.__init__(self)
+    u, rad = ref.underlying, -1.0
+    if type(u).__name__ == "UnitSphere": u, rad = u.inner, float(u.rad)
+    if type(ref.refl).__name__ not in ("View", "ViewHead"): raise NotImplementedError(f"refl head {type(ref.refl).__name__}")
+    if getattr(ref.isect, "__name__", "sphere_march") != "sphere_march": raise NotImplementedError("only the sphere-march intersection is built")
+    self.underlying, self.refl = u, ref.refl
+    self.near, self.far, self.bound_sphere_rad, self.precision = ref.near, ref.far, rad, precision
+    self._engine = None; self._engine_key = None
+    return self
+
+  @property
+  def sdf(self): return self
+  @property
+  def intermediate_size(self): return self.underlying.intermediate_size
+  def __getstate__(self):
+    st = self.__dict__.copy(); st["_engine"] = None; st["_engine_key"] = None
+    for k in ("pts", "hit", "t"): st.pop(k, None)
+    return st
+
+  def _net(self):
+    u = self.underlying
+    if hasattr(u, "siren"): return "siren", u.siren
+    if hasattr(u, "mlp"): return "mlp", u.mlp
+    raise NotImplementedError(f"sdf network {type(u).__name__}")
+
+  def engine(self) -> RenderEngine:
+    kind, net = self._net()
+    key = (kind, _sigmoid_name(self.refl.act), self.precision)
+    if self._engine is None or self._engine_key != key:
+      freqs = net.enc.basis.shape[1] if kind == "mlp" else 128
+      self._engine, self._engine_key = RenderEngine(describe_volsdf(kind, self.intermediate_size, key[1], freqs), self.precision), key
+    return self._engine
+
+  def _param_list(self) -> List[torch.Tensor]:
+    kind, net = self._net()
+    ps: List[torch.Tensor] = []
+    for mlp in (net, self.refl.mlp):
+      for lin in _linears_of(mlp): ps += [lin.weight, lin.bias]
+    if kind == "mlp": ps.append(net.enc.basis)
+    if not hasattr(self, "_beta") or self._beta.device != ps[0].device: self._beta = torch.ones(1, device=ps[0].device)    # the descriptor's Laplace beta: unused by the surface side
+    ps.append(self._beta)
+    return ps
+
+  def forward(self, rays: torch.Tensor, with_throughput: bool = True) -> torch.Tensor:
+    if not rays.is_cuda: raise RuntimeError("FusedSDF.forward needs CUDA rays: the fused path has no CPU fallback")
+    if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+      raise NotImplementedError("training the SDF surface model through the fused path is not built; call under torch.no_grad() / eval()")
+    B = rays.shape[:-1]
+    flat = rays.reshape(-1, 6).to(torch.float32).contiguous()
+    eng = self.engine(); eng.pack(self._param_list())
+    rgb, hit, t, pts = eng.sdf_render(flat, self.near, self.far, iters=128 if self.training else 192, bound_rad=self.bound_sphere_rad)
+    self.pts, self.hit, self.t = pts.reshape(*B, 3), hit.reshape(B), t.reshape(B)
+    return rgb.reshape(*B, 3)
 
 
 class FusedDynamicNeRF(nn.Module):

@@ -461,6 +461,49 @@ def volsdf_forward(params: Params, rays: Tensor, ts: Tensor, *, sdf_kind: str = 
 
 
 # ----------------------------------------------------------------------------
+# f-4  SDF surface side  (reference src/march.py:27-47, src/sdf.py:66-83,137-156)
+# ----------------------------------------------------------------------------
+def sdf_net(params: Params, pts: Tensor, sdf_kind: str = "siren", prefix: str = "underlying", bound_rad: float = -1.0,
+            quant: Optional[torch.dtype] = None) -> Tensor:
+  """[sdf, latent(I)] of the SDF network at pts[N,3] (sdf.py:250-287), optionally intersected with a sphere (UnitSphere, 66-83)."""
+  if sdf_kind == "siren": raw = skip_mlp(pts, params, f"{prefix}.siren", "sin", quant=quant)
+  else: raw = skip_mlp(fourier_encode(pts, params[f"{prefix}.mlp.enc.basis"]), params, f"{prefix}.mlp", "leaky_relu", quant=quant)
+  if bound_rad > 0:
+    sph = torch.linalg.norm(pts, dim=-1, ord=2) - bound_rad
+    raw = torch.cat([torch.maximum(raw[..., 0], sph).unsqueeze(-1), raw[..., 1:]], dim=-1)
+  return raw
+
+
+def sphere_march(params: Params, r_o: Tensor, r_d: Tensor, *, sdf_kind: str = "siren", iters: int = 32, eps: float = 1e-3,
+                 near: float = 0, far: float = 1, bound_rad: float = -1.0, prefix: str = "underlying", quant=None):
+  """march.sphere_march (reference src/march.py:27-47) on flat rays [R,3]: (pts, hits, t)."""
+  hits = torch.zeros(r_o.shape[0], dtype=torch.bool)
+  rem = torch.ones_like(hits)
+  curr_dist = torch.full((r_o.shape[0],), float(near))
+  for _ in range(iters):
+    if not bool(rem.any()): break
+    curr = r_o[rem] + r_d[rem] * curr_dist[rem, None]
+    dist = sdf_net(params, curr, sdf_kind, prefix, bound_rad, quant)[..., 0]
+    hits[rem] |= (dist < eps) & (curr_dist[rem] <= far)
+    curr_dist[rem] += dist
+    rem[hits | (curr_dist > far)] = False
+  return r_o + r_d * curr_dist[:, None], hits, curr_dist
+
+
+def sdf_forward(params: Params, rays: Tensor, *, sdf_kind: str = "siren", near: float = 0, far: float = 1, iters: int = 192,
+                sigmoid: str = "upshifted", bound_rad: float = -1.0, quant=None) -> Dict[str, Tensor]:
+  """SDF.forward in eval mode (reference src/sdf.py:137-156): rgb[hit] = act(View([pts, elaz(r_d), latent])), black elsewhere."""
+  r_o, r_d = rays.reshape(-1, 6).split([3, 3], dim=-1)
+  pts, hit, t = sphere_march(params, r_o, r_d, sdf_kind=sdf_kind, iters=iters, near=near, far=far, bound_rad=bound_rad, quant=quant)
+  out = torch.zeros_like(r_d)
+  if bool(hit.any()):
+    latent = sdf_net(params, pts[hit], sdf_kind, "underlying", bound_rad, quant)[..., 1:]
+    x0 = torch.cat([pts[hit], dir_to_elev_azim(r_d[hit]), latent], dim=-1)
+    out[hit] = SIGMOIDS[sigmoid](skip_mlp(x0, params, "refl.mlp", "sin", quant=quant))
+  return dict(out=out.reshape(rays.shape[:-1] + (3,)), hit=hit.reshape(rays.shape[:-1]), t=t.reshape(rays.shape[:-1]), pts=pts.reshape(rays.shape[:-1] + (3,)))
+
+
+# ----------------------------------------------------------------------------
 # a-12  DynamicNeRF, direct deformation MLP  (reference src/nerf.py:1209-1303)
 # ----------------------------------------------------------------------------
 def dnerf_direct_forward(params: Params, rays: Tensor, times: Tensor, ts: Tensor, *, sigmoid: str = "upshifted",

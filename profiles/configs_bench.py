@@ -69,4 +69,16 @@ def fp():
   with torch.no_grad(): return mp(r4)
 ms = timed(fp, reps=2)
 rows.append({"config": "PlainNeRF + Positional head, 800x800x128", "ms_per_frame": ms, "rays_per_s": 640000 / ms * 1e3, "samples_per_ray": 128})
+# f-4: sphere-traced surface render (SIREN SDF fitted to a unit sphere = the golden's weights), 800x800, 192 march iterations
+from helpers import load_golden, sdf_params
+fxs = load_golden("sdf_siren_march")
+for prec in ("fp16", "fp32"):
+  ms_ = N.FusedSDF("siren", 64, t_near=2.0, t_far=6.0, sigmoid_kind="upshifted", precision=prec)
+  ms_.load_state_dict(sdf_params(fxs), strict=True); ms_ = ms_.to(dev).eval()
+  ru = rays800.clone(); ru[:, 3:] = torch.nn.functional.normalize(ru[:, 3:], dim=-1)
+  def fs():
+    with torch.no_grad(): return ms_(ru.reshape(1, 800, 800, 6))
+  ms = timed(fs, reps=2)
+  rows.append({"config": f"f-4: SDF surface render (sphere march 192 it + View), 800x800, {prec}", "ms_per_frame": ms, "rays_per_s": 640000 / ms * 1e3,
+               "hit_fraction": float(ms_.hit.float().mean())})
 for r in rows: print(json.dumps(r), flush=True)

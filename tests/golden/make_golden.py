@@ -278,8 +278,49 @@ def case_trained(name, seed=1337, iters=400, T=64, crop=24, views=6, lr=2e-3):
   print(name, "final loss", float(loss), "max|h|", hmax[0], "psnr vs target", float(-10 * torch.log10(torch.nn.functional.mse_loss(out, analytic_scene(rays)))),
         "table rows stored", sum(len(fx[k]) for k in fx if k.startswith("rows.")))
 
+def case_sdf(name, seed=23, sdf_kind="siren", size=16, iters_fit=500, bound_rad=-1.0):
+  """The reference's surface renderer `sdf.SDF` (src/sdf.py:86-156) with the sphere-march intersection (src/march.py:27-47) and
+  a View head, eval mode (192 iterations).  The SDF network is first fitted to a sphere of radius 1 with the reference's own
+  modules (as `SDFModel.set_to_sphere` does, src/sdf.py:47-60), then ALL parameters are rounded to fp16 so that the fixture
+  stays small; the reference renders with exactly those rounded values."""
+  runner, nerf, refl, utils, cameras = ref_shim.load()
+  import src.sdf as rsdf, src.march as march
+  torch.manual_seed(seed)
+  model = rsdf.sdf_kinds[sdf_kind](intermediate_size=64)
+  opt = torch.optim.Adam(model.parameters(), lr=2e-4 if sdf_kind == "siren" else 1e-3, weight_decay=0)
+  for i in range(iters_fit):
+    opt.zero_grad()
+    v = 2 * torch.randn(4000, 3)
+    loss = torch.nn.functional.mse_loss(model(v)[..., 0], v.norm(dim=-1) - 1.0)
+    loss.backward(); opt.step()
+    if i % 100 == 0 or i == iters_fit - 1: print(name, "fit", i, float(loss.detach()), flush=True)
+  if bound_rad > 0: wrapped = rsdf.UnitSphere(inner=model, rad=bound_rad)
+  else: wrapped = model
+  # shim: SDF.forward passes mask=hit to the head (sdf.py:152) but View.forward takes no such keyword (refl.py:205): swallow it
+  orig_fwd = refl.View.forward
+  refl.View.forward = lambda self, x, view, normal=None, light=None, latent=None, mask=None: orig_fwd(self, x, view, normal, light, latent)
+  head = refl.View(latent_size=64, act="upshifted", out_features=3)
+  s = rsdf.SDF(wrapped, head, isect=march.sphere_march, t_near=2.0, t_far=6.0).eval()
+  with torch.no_grad():
+    for p in s.parameters():
+      if p.dtype.is_floating_point: p.copy_(p.to(torch.float16).to(torch.float32))
+  rays = O.make_rays(2, size, size, size=size, seed=seed)
+  rays = torch.cat([rays[..., :3], torch.nn.functional.normalize(rays[..., 3:], dim=-1)], dim=-1)
+  with torch.no_grad():
+    out = s(rays)
+    pts, hit, t, _ = march.sphere_march(s.underlying, rays[..., :3], rays[..., 3:], iters=192, near=2.0, far=6.0)
+  fx = dict(kind="sdf", sdf_kind=sdf_kind, seed=seed, size=size, near=2.0, far=6.0, iters=192, sigmoid="upshifted", bound_rad=bound_rad,
+            rays=rays.numpy(), out=out.numpy(), hit=hit.numpy(), t=t.squeeze(-1).numpy(), pts=pts.numpy())
+  for k, v in s.state_dict().items():
+    if v.dtype.is_floating_point and v.numel(): fx["param16." + k.replace("underlying.inner.", "underlying.")] = v.to(torch.float16).numpy()
+  np.savez_compressed(os.path.join(HERE, name + ".npz"), **fx)
+  print(name, "hit fraction", float(hit.float().mean()), "t range", float(t.min()), float(t.max()), "out mean", float(out.mean()))
+
 if __name__ == "__main__":
   check_rays()
+  if "--sdf" in sys.argv:
+    case_sdf("sdf_siren_march")
+    sys.exit(0)
   if "--trained" in sys.argv:
     torch.set_num_threads(int(os.environ.get("GOLDEN_THREADS", "8")))
     case_trained(os.environ.get("GOLDEN_NAME", "plain_trained_t64"), iters=int(os.environ.get("GOLDEN_ITERS", "400")), lr=float(os.environ.get("GOLDEN_LR", "2e-3")))
@@ -312,3 +353,4 @@ if __name__ == "__main__":
   case_plain_grads("plain_t16_grads", seed=91, B=1, H=3, W=4, T=16, top=398, left=397)
   case_dtu_rays("dtu_rays")
   case_trained("plain_trained_t64")
+  case_sdf("sdf_siren_march")

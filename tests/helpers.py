@@ -83,3 +83,7 @@ def trained_params(fx):
     elif k.startswith("rows."):
       t = P[k[5:]].clone(); t[torch.from_numpy(fx[k]).long()] = torch.from_numpy(fx["vals." + k[5:]]); P[k[5:]] = t
   return P
+
+def sdf_params(fx):
+  """Parameters of the `sdf_*_march` goldens (stored as fp16; the reference rendered with exactly these values)."""
+  return {k[len("param16."):]: torch.from_numpy(fx[k].astype(np.float32)) for k in fx if k.startswith("param16.")}

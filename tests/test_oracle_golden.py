@@ -239,5 +239,24 @@ def test_oracle_matches_reference_on_trained_weights(golden_dir):
     q = O.plain_forward(P, rays, ts, sigmoid=str(fx["sigmoid"]), bg=str(fx["bg"]), quant=torch.float16)
   assert np.array_equal(ref["out"].numpy(), fx["out"]) and np.array_equal(ref["weights"].numpy(), fx["weights"])
   d = np.abs(q["out"].numpy() - fx["out"])
-  assert d.max() <= 1e-3 and -10 * np.log10(np.mean(d.astype(np.float64) ** 2)) >= 70
+  # trained colours vary strongly (rgb std 0.43 against 0.05 at initialisation): fp16 operands cost 1.13e-3 max / 73.9 dB here,
+  # bf16 7.4e-3 / 56 dB.  Stated bar on trained weights: max <= 2e-3 and PSNR >= 70 dB.
+  assert d.max() <= 2e-3 and -10 * np.log10(np.mean(d.astype(np.float64) ** 2)) >= 70
+  with torch.no_grad(): qb = O.plain_forward(P, rays, ts, sigmoid=str(fx["sigmoid"]), bg=str(fx["bg"]), quant=torch.bfloat16)
+  assert np.abs(qb["out"].numpy() - fx["out"]).max() > 4e-3        # why the operands are fp16 and not bf16
   assert float(fx["max_abs_preactivation"]) < 65504 / 16          # |h| < fp16 max with a wide margin (SURVEY 8d range check)
+
+
+def test_sdf_surface_oracle_matches_reference(golden_dir):
+  """f-4: march.sphere_march + sdf.SDF.forward (eval, View head; the head call needs the `mask` shim noted in make_golden.py)
+  restated; golden = the reference's own modules on an SDF network fitted to a unit sphere."""
+  from helpers import sdf_params
+  fx = load(golden_dir, "sdf_siren_march")
+  P = sdf_params(fx)
+  rays = torch.from_numpy(fx["rays"])
+  with torch.no_grad():
+    res = O.sdf_forward(P, rays, sdf_kind=str(fx["sdf_kind"]), near=float(fx["near"]), far=float(fx["far"]), iters=int(fx["iters"]), sigmoid=str(fx["sigmoid"]))
+  assert np.array_equal(res["hit"].numpy(), fx["hit"])
+  assert np.array_equal(res["t"].numpy(), fx["t"]) and np.array_equal(res["pts"].numpy(), fx["pts"])
+  assert np.array_equal(res["out"].numpy(), fx["out"])
+  assert 0.2 < fx["hit"].mean() < 0.8 and np.abs(fx["out"][~fx["hit"]]).max() == 0
