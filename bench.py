@@ -365,6 +365,7 @@ def run_ours(args):
       "dtype": "f16", "dtype_note": "fp16 operands, fp32 accumulate in TMEM (tcgen05 kind::f16); everything outside the GEMMs fp32", "data": "synthetic",
       "config": {"workload": "PlainNeRF+View (hash enc, I=64) forward render, one 800x800 view x 128 samples/ray per GPU per step, near 2 far 6",
                  "rays_per_step_per_gpu": RAYS_PER_FRAME, "samples_per_ray": T, "weights": "seeded random init (reference distributions)",
+                 "outputs": "value: rgb only (want_weights=False; the per-sample alpha / weights the reference also keeps cost +1 KiB/ray of HBM writes, ~+1 %); e2e: FusedPlainNeRF.forward with keep_weights=False",
                  "l2": f"inputs rotate over {N_VIEWS} distinct views = {N_VIEWS * RAYS_PER_FRAME * 24 / 1e6:.0f} MB of rays > 126 MB L2",
                  "parallelism": f"ray-sharded x{world} (one view per GPU per step), no data-path collective"},
       "msamples_per_sec": value * T / 1e6,

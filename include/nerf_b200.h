@@ -75,8 +75,8 @@ enum nf_mip {
 enum nf_refl {
   NF_REFL_VIEW = 0,        /* refl.View (reference src/refl.py:190-207): x0 = [p, elaz(view), latent] */
   NF_REFL_POSITIONAL = 1   /* refl.Positional (reference src/refl.py:230-245; makefile:12 `--refl-kind pos`): view independent,
-                              x0 = [p, p, hash'(p), latent] with the head's OWN HashEncoder, 5 layers, LeakyReLU.  fp32 pipeline only
-                              (x0 is 102 wide) */
+                              x0 = [p, p, hash'(p), latent] with the head's OWN HashEncoder, 5 layers, LeakyReLU.  Both pipelines
+                              (tensor pipeline: x0 is 112 columns wide, two tiles in flight over one shared x0 buffer) */
 };
 /* arithmetic of the MLP contractions */
 enum nf_precision {
@@ -111,7 +111,7 @@ typedef struct nf_model_desc {
   int32_t bg;                /* enum nf_bg */
   int32_t fourier_freqs;     /* NF_ENC_FOURIER: columns of the basis [3, freqs] (x0 = [p, sin(pB), cos(pB)]) */
   nf_mlp_desc deform;        /* NF_KIND_DYN: DynamicNeRF.delta_estim (direct: in 4 = xyz,t, out 4; spline: in 38, out 1+3n) */
-  int32_t mip;               /* enum nf_mip (NF_PREC_FP32 only: x0 is 134 / 165 wide) */
+  int32_t mip;               /* enum nf_mip (both pipelines; tensor pipeline: x0 is 144 / 176 columns wide, shared-x0 mode) */
   int32_t deform_enc;        /* NF_KIND_DYN: encoder of `deform`: NF_ENC_NONE (direct) or NF_ENC_HASH (spline; its own tables) */
   int32_t refl_kind;         /* enum nf_refl */
   int32_t spline_points;     /* NF_KIND_DYN: 0 = direct_predict (nerf.py:1261-1266); n in 2..8 = spline_interpolate with n
@@ -227,7 +227,8 @@ int nf_composite(const nf_model_desc* desc, const void* packed, const float* sig
 int nf_sample_pdf(const float* ts_coarse, int32_t T, const float* weights, int64_t n_rays,
                   const float* u, int32_t n_fine, float* ts_out, void* stream);
 /* One SkipConnMLP.forward (reference src/neural_blocks.py:279-296) on assembled inputs
- * x0[N,in_dims] -> out[N,out_dims]; which = 0 density MLP, 1 refl MLP. */
+ * x0[N,in_dims] -> out[N,out_dims]; which = 0 density MLP (or the SDF network), 1 refl MLP, 2 deformation MLP (NF_KIND_DYN).
+ * NF_PREC_FP16_TC: MLPs whose x0 fits 80 columns (the single-CTA tcgen05 kernel of nf_tc.cu). */
 int nf_mlp_forward(const nf_model_desc* desc, const void* packed, int32_t which,
                    const float* x0, int64_t n, float* out, int32_t precision, void* stream);
 
