@@ -74,9 +74,14 @@ enum nf_mip {
 /* RGB head */
 enum nf_refl {
   NF_REFL_VIEW = 0,        /* refl.View (reference src/refl.py:190-207): x0 = [p, elaz(view), latent] */
-  NF_REFL_POSITIONAL = 1   /* refl.Positional (reference src/refl.py:230-245; makefile:12 `--refl-kind pos`): view independent,
+  NF_REFL_POSITIONAL = 1,  /* refl.Positional (reference src/refl.py:230-245; makefile:12 `--refl-kind pos`): view independent,
                               x0 = [p, p, hash'(p), latent] with the head's OWN HashEncoder, 5 layers, LeakyReLU.  Both pipelines
                               (tensor pipeline: x0 is 112 columns wide, two tiles in flight over one shared x0 buffer) */
+  NF_REFL_POSLINVIEW = 2   /* refl.PosLinearView (reference src/refl.py:248-290; `--refl-kind pos-linear-view`): rgb = (sigmoid(view) / 2
+                              + 1/2) * pos, with  [pos(3), im(I2)] = act(pos_mlp([p, p, hash'(p), latent]))  (own HashEncoder, 2 layers,
+                              hidden 256, LeakyReLU; the feature activation on all 3 + I2 outputs) and  view = view_mlp([p,
+                              normalize(r_d), latent, im])  (2 layers, hidden 128, sin).  `refl` describes pos_mlp, `refl_view`
+                              view_mlp.  NF_PREC_FP32 only; not with NF_KIND_DYN, Mip or the softmax activation. */
 };
 /* arithmetic of the MLP contractions */
 enum nf_precision {
@@ -116,6 +121,7 @@ typedef struct nf_model_desc {
   int32_t refl_kind;         /* enum nf_refl */
   int32_t spline_points;     /* NF_KIND_DYN: 0 = direct_predict (nerf.py:1261-1266); n in 2..8 = spline_interpolate with n
                                 Bezier control points (nerf.py:1267-1278; de_casteljau 1173-1178, cubic_bezier 1201-1206) */
+  nf_mlp_desc refl_view;     /* NF_REFL_POSLINVIEW: PosLinearView.view (hidden 128: evaluated as 256 with zero-padded weights, exact) */
 } nf_model_desc;
 
 /* Per-call inputs of the Mip encoder (nf_model_desc.mip != NF_MIP_NONE); all device pointers. */
@@ -146,11 +152,12 @@ const char* nf_tensor_pipeline_support(const nf_model_desc* desc);
 /* ---- parameters -------------------------------------------------------- */
 /* Number of parameter pointers nf_pack_weights expects for `desc`, in this order:
  *   density MLP: init.weight, init.bias, layers[0].weight, layers[0].bias, ..., out.weight, out.bias
- *   refl MLP   : same order                                   (NF_KIND_PLAIN, NF_KIND_DYN)
+ *   refl MLP   : same order                                   (NF_KIND_PLAIN, NF_KIND_DYN; NF_REFL_POSLINVIEW: PosLinearView.pos)
  *   deform MLP : same order                                   (NF_KIND_DYN only)
+ *   view MLP   : same order                                   (NF_REFL_POSLINVIEW only: PosLinearView.view)
  *   hash tables: embs[0].weight ... embs[levels-1].weight      (NF_ENC_HASH only)
  *   deform hash: delta_estim.enc.embs[0..levels-1].weight      (NF_KIND_DYN with deform_enc == NF_ENC_HASH only)
- *   refl hash  : refl.mlp.enc.embs[0..levels-1].weight         (NF_REFL_POSITIONAL only)
+ *   refl hash  : refl.mlp.enc.embs[0..levels-1].weight         (NF_REFL_POSITIONAL; NF_REFL_POSLINVIEW: refl.pos.enc.embs)
  *   fourier    : enc.basis [3, freqs]                          (NF_ENC_FOURIER only)
  *   beta       : VolSDF.scale (scalar)                         (NF_DENS_LAPLACE only)
  * Each is the live fp32 nn.Parameter storage ([out,in] row-major for weights). */

@@ -17,7 +17,7 @@ FEAT = {"normal": 0, "thin": 1, "tanh": 2, "cyclic": 3, "upshifted": 4, "fat": 5
 BG = {"black": 0, "white": 1, "random": 2}
 KIND = {"plain": 0, "tiny": 1, "dyn": 2}
 PRECISION = {"fp32": 0, "fp16": 1}
-REFL = {"view": 0, "pos": 1}
+REFL = {"view": 0, "pos": 1, "pos-linear-view": 2}
 MIP = {None: 0, "none": 0, "cylinder": 1, "cone": 2, "cylinder_ref": 3}
 
 class MlpDesc(C.Structure):
@@ -30,7 +30,7 @@ class ModelDesc(C.Structure):
               ("hash_table_size", C.c_int32), ("hash_feat", C.c_int32), ("hash_primes", C.c_uint32 * 3),
               ("hash_res", C.c_float * 16), ("density_act", C.c_int32), ("feat_act", C.c_int32), ("bg", C.c_int32),
               ("fourier_freqs", C.c_int32), ("deform", MlpDesc), ("mip", C.c_int32), ("deform_enc", C.c_int32),
-              ("refl_kind", C.c_int32), ("spline_points", C.c_int32)]
+              ("refl_kind", C.c_int32), ("spline_points", C.c_int32), ("refl_view", MlpDesc)]
 
 class MipArgs(C.Structure):
   _fields_ = [("radius", C.c_void_p), ("rays_all", C.c_void_p), ("radius_all", C.c_void_p), ("n_rays_all", C.c_int64),

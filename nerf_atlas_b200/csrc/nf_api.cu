@@ -56,7 +56,7 @@ int nf_param_count(const nf_model_desc* desc) {
   for (int m = 0; m < p.n_mlps; ++m) n += 2 * p.mlp[m].n_lin;
   if (p.enc == NF_ENC_HASH) n += p.hash_levels;
   if (p.kind == NF_KIND_DYN && p.deform_enc == NF_ENC_HASH) n += p.hash_levels;
-  if (p.refl_kind == NF_REFL_POSITIONAL) n += p.hash_levels;
+  if (p.refl_kind != NF_REFL_VIEW) n += p.hash_levels;
   if (p.enc == NF_ENC_FOURIER) n += 1;
   if (p.density_act == NF_DENS_LAPLACE) n += 1;
   return n;
@@ -82,8 +82,11 @@ int nf_pack_weights(const nf_model_desc* desc, const float* const* params, int32
       const NfLinPlan& L = p.mlp[m].lin[j];
       const float* W = params[pi++]; const float* b = params[pi++];
       if (!W || !b) return fail(NF_E_BADARG, "nf_pack_weights: null parameter");
-      cudaError_t e = nf_launch_pack_fp32(W, b, (float*)(base + L.wt_off), (float*)(base + L.b_off), L.n, L.k_hidden + L.k_x0, L.n_pad, st);
+      // a narrower reference hidden size (PosLinearView.view: 128) is zero-padded to 256: exact, the extra units stay act(0) = 0
+      const int href = p.mlp[m].hidden_ref, kh_ref = L.k_hidden ? href : 0, n_ref = L.is_out ? L.n : href;
+      cudaError_t e = nf_launch_pack_fp32(W, b, (float*)(base + L.wt_off), (float*)(base + L.b_off), n_ref, kh_ref, L.k_hidden, L.k_x0, L.n_pad, st);
       if (e != cudaSuccess) return cuda_fail(e, "pack fp32");
+      if (href != NF_HIDDEN) continue;                     // the tensor pipeline does not take such a model (nf_tensor_pipeline_support)
       e = nf_launch_pack_fp16(p, m, j, W, b, packed, st);
       if (e != cudaSuccess) return cuda_fail(e, "pack fp16");
       e = nf_launch_pack_w16t(p, m, j, W, packed, st);
@@ -108,7 +111,7 @@ int nf_pack_weights(const nf_model_desc* desc, const float* const* params, int32
       if (e != cudaSuccess) return cuda_fail(e, "pack deformation hash tables");
     }
   }
-  if (p.refl_kind == NF_REFL_POSITIONAL) {
+  if (p.refl_kind != NF_REFL_VIEW) {
     const size_t per = (size_t)(p.hash_mask + 1) * 4 * sizeof(float);
     for (int l = 0; l < p.hash_levels; ++l) {
       const float* t = params[pi++];

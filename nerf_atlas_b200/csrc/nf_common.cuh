@@ -32,7 +32,7 @@ struct NfLinPlan {
                       // followed by [n_pad/8][256][8] (hidden part, if any): the reduction dimension is the Linear's OUTPUT
 };
 struct NfMlpPlan {
-  int32_t n_lin, in_dims, k0_pad, act, out_dims, pad_;
+  int32_t n_lin, in_dims, k0_pad, act, out_dims, hidden_ref;   // hidden_ref: the reference's hidden_size (< 256: zero-padded to 256)
   NfLinPlan lin[NF_MAX_LIN];
 };
 struct NfPlan {
@@ -50,7 +50,7 @@ struct NfPlan {
   int64_t hash3_off;    // byte offset: fp32 [levels][table][4], tables of the Positional head's own HashEncoder
   int64_t hash2_off;    // byte offset: fp32 [levels][table][4], tables of the spline deformation MLP's own HashEncoder
   int64_t total_bytes;
-  NfMlpPlan mlp[3];     // [0] density, [1] refl, [2] deformation (NF_KIND_DYN; executed first)
+  NfMlpPlan mlp[3];     // [0] density, [1] refl, [2] deformation (NF_KIND_DYN; executed first) or PosLinearView.view (NF_REFL_POSLINVIEW)
 };
 
 __host__ __device__ inline int nf_round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -67,9 +67,12 @@ static inline int nf_build_plan(const nf_model_desc* d, NfPlan* p, const char** 
   if (d->mip < NF_MIP_NONE || d->mip > NF_MIP_CYLINDER_REF) { *why = "unknown mip kind"; return NF_E_BADARG; }
   if (d->mip != NF_MIP_NONE && d->kind == NF_KIND_TINY) { *why = "mip: not for NF_KIND_TINY"; return NF_E_UNSUPPORTED; }
   p->mip = d->mip;
-  if (d->refl_kind != NF_REFL_VIEW && d->refl_kind != NF_REFL_POSITIONAL) { *why = "unknown refl kind"; return NF_E_BADARG; }
-  if (d->refl_kind == NF_REFL_POSITIONAL && (d->kind == NF_KIND_TINY || d->enc != NF_ENC_HASH)) {
-    *why = "the Positional head needs a hash-encoded PlainNeRF / DynamicNeRF"; return NF_E_UNSUPPORTED; }
+  if (d->refl_kind < NF_REFL_VIEW || d->refl_kind > NF_REFL_POSLINVIEW) { *why = "unknown refl kind"; return NF_E_BADARG; }
+  if (d->refl_kind != NF_REFL_VIEW && (d->kind == NF_KIND_TINY || d->enc != NF_ENC_HASH)) {
+    *why = "the Positional / PosLinearView heads need a hash-encoded PlainNeRF / DynamicNeRF"; return NF_E_UNSUPPORTED; }
+  if (d->refl_kind == NF_REFL_POSLINVIEW && (d->kind != NF_KIND_PLAIN || d->mip != NF_MIP_NONE || d->feat_act == NF_FEAT_SOFTMAX)) {
+    *why = "PosLinearView: PlainNeRF without Mip, any feature activation but softmax"; return NF_E_UNSUPPORTED; }
+  if (d->refl_kind == NF_REFL_POSLINVIEW) p->n_mlps = 3;
   p->refl_kind = d->refl_kind;
   if (d->kind == NF_KIND_DYN) {
     p->deform_enc = d->deform_enc; p->spline_points = d->spline_points;
@@ -96,12 +99,14 @@ static inline int nf_build_plan(const nf_model_desc* d, NfPlan* p, const char** 
   if (d->enc == NF_ENC_HASH) p->hash_off = take((int64_t)d->hash_levels * d->hash_table_size * 4 * sizeof(float));
   if (d->enc == NF_ENC_FOURIER) p->fourier_off = take((int64_t)3 * d->fourier_freqs * sizeof(float));
   if (d->kind == NF_KIND_DYN && d->deform_enc == NF_ENC_HASH) p->hash2_off = take((int64_t)d->hash_levels * d->hash_table_size * 4 * sizeof(float));
-  if (d->refl_kind == NF_REFL_POSITIONAL) p->hash3_off = take((int64_t)d->hash_levels * d->hash_table_size * 4 * sizeof(float));
+  if (d->refl_kind != NF_REFL_VIEW) p->hash3_off = take((int64_t)d->hash_levels * d->hash_table_size * 4 * sizeof(float));
   p->scale_off = take(sizeof(float));
   for (int m = 0; m < p->n_mlps; ++m) {
-    const nf_mlp_desc& md = m == 0 ? d->density : m == 1 ? d->refl : d->deform;
+    const nf_mlp_desc& md = m == 0 ? d->density : m == 1 ? d->refl : d->refl_kind == NF_REFL_POSLINVIEW ? d->refl_view : d->deform;
     NfMlpPlan& mp = p->mlp[m];
-    if (md.hidden != NF_HIDDEN) { *why = "hidden_size must be 256"; return NF_E_UNSUPPORTED; }
+    if (md.hidden != NF_HIDDEN && !(d->refl_kind == NF_REFL_POSLINVIEW && m == 2 && md.hidden >= 16 && md.hidden < NF_HIDDEN && (md.hidden & 15) == 0)) {
+      *why = "hidden_size must be 256 (PosLinearView.view: a multiple of 16 below 256, zero-padded)"; return NF_E_UNSUPPORTED; }
+    mp.hidden_ref = md.hidden;
     if (md.n_layers < 1 || md.n_layers + 2 > NF_MAX_LIN) { *why = "unsupported number of layers"; return NF_E_UNSUPPORTED; }
     if (md.in_dims < 1 || md.in_dims > 272 || md.out_dims < 1 || md.out_dims > 256 || md.skip < 1) { *why = "unsupported MLP dims"; return NF_E_UNSUPPORTED; }
     mp.n_lin = md.n_layers + 2; mp.in_dims = md.in_dims; mp.k0_pad = nf_round_up(md.in_dims, 16);
@@ -134,7 +139,12 @@ static inline int nf_build_plan(const nf_model_desc* d, NfPlan* p, const char** 
   if (d->kind == NF_KIND_PLAIN || d->kind == NF_KIND_DYN) {
     const int ml = d->mip != NF_MIP_NONE ? NF_MIP_FEATS : 0;
     if (d->density.out_dims != 1 + d->intermediate) { *why = "density MLP out must be 1+intermediate"; return NF_E_BADARG; }
-    const int rin = (d->refl_kind == NF_REFL_POSITIONAL ? 6 + d->hash_levels * 4 : 5) + ml + d->intermediate;
+    const int rin = (d->refl_kind != NF_REFL_VIEW ? 6 + d->hash_levels * 4 : 5) + ml + d->intermediate;
+    if (d->refl_kind == NF_REFL_POSLINVIEW) {
+      const int im = d->refl.out_dims - 3;                   // PosLinearView's own intermediate (refl.py:249,253)
+      if (d->refl.in_dims != rin || im < 1 || d->refl_view.in_dims != 6 + d->intermediate + im || d->refl_view.out_dims != 1) {
+        *why = "PosLinearView: pos MLP [p, p, hash'(p), latent] -> 3 + im, view MLP [p, dir, latent, im] -> 1"; return NF_E_BADARG; }
+    } else
     if (d->refl.in_dims != rin || d->refl.out_dims != 3) { *why = "refl MLP must map [p, elaz | p, hash(p)] (+96 mip) + intermediate -> 3"; return NF_E_BADARG; }
     const int want = (d->enc == NF_ENC_HASH ? 6 + d->hash_levels * 4 : d->enc == NF_ENC_FOURIER ? 3 + 2 * d->fourier_freqs : 3) + ml;
     if (d->density.in_dims != want) { *why = "density MLP in_dims does not match the encoder"; return NF_E_BADARG; }

@@ -228,7 +228,7 @@ k_render_fp32(const __grid_constant__ NfPlan plan, const RenderArgs a) {
         //      Positional = [pts, pts, hash'(pts), (mip), intermediate] with the head's own tables (refl.py:230-245)
         const float* O = s.H[ob];
         const int ml = plan.mip != NF_MIP_NONE ? NF_MIP_FEATS : 0;
-        const bool pos_head = plan.refl_kind == NF_REFL_POSITIONAL;
+        const bool pos_head = plan.refl_kind != NF_REFL_VIEW;          // Positional, and PosLinearView's `pos` MLP: the same x0
         const int base = pos_head ? 6 + plan.hash_levels * 4 : 5;
         if (tid < ROWS) {
           const int row = tid;
@@ -258,6 +258,43 @@ k_render_fp32(const __grid_constant__ NfPlan plan, const RenderArgs a) {
         // ---- stage 2: View MLP
         ob = mlp_fp32(plan.mlp[1], a.packed, s);
         rgb_raw = s.H[ob];
+        if (plan.refl_kind == NF_REFL_POSLINVIEW) {
+          // PosLinearView (refl.py:281-290): [pos(3), im] = act(pos_mlp(...)); linear = sigmoid(view_mlp([p, dir, latent, im])) / 2 + 1/2;
+          // rgb = linear * pos.  The density MLP's intermediate (the latent) still sits in X0 behind [p, p, hash'(p)].
+          const int I = plan.intermediate, im = plan.mlp[1].out_dims - 3, lat0 = 6 + plan.hash_levels * 4;
+          float* T = s.H[ob ^ 1];                                   // free buffer: [latent (I) | act(pos) (3 + im)]
+          const float* O2 = s.H[ob];
+          for (int i = tid; i < I * ROWS; i += THREADS) T[i] = s.X0[lat0 * ROWS + i];
+          for (int i = tid; i < (3 + im) * ROWS; i += THREADS) T[I * ROWS + i] = nf_feat_act_fn(O2[i], plan.feat_act);
+          __syncthreads();
+          if (tid < ROWS) {
+            const int row = tid;
+            float dx = 0.f, dy = 0.f, dz = 0.f;
+            if (s.valid[row]) {
+              const float* r = a.rays + s.ray[row] * 6;
+              dx = __ldg(r + 3); dy = __ldg(r + 4); dz = __ldg(r + 5);
+              const float nrm = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz))), 1e-12f);   // F.normalize
+              dx = __fdiv_rn(dx, nrm); dy = __fdiv_rn(dy, nrm); dz = __fdiv_rn(dz, nrm);
+            }
+            s.X0[0 * ROWS + row] = s.P[row]; s.X0[1 * ROWS + row] = s.P[ROWS + row]; s.X0[2 * ROWS + row] = s.P[2 * ROWS + row];
+            s.X0[3 * ROWS + row] = dx; s.X0[4 * ROWS + row] = dy; s.X0[5 * ROWS + row] = dz;
+          }
+          for (int i = tid; i < I * ROWS; i += THREADS) s.X0[6 * ROWS + i] = T[i];
+          for (int i = tid; i < im * ROWS; i += THREADS) s.X0[(6 + I) * ROWS + i] = T[(I + 3) * ROWS + i];
+          __syncthreads();
+          // the three colours leave T before the view MLP reuses the H buffers: park them behind x0
+          float* C = s.X0 + (6 + I + im) * ROWS;
+          for (int i = tid; i < 3 * ROWS; i += THREADS) C[i] = T[I * ROWS + i];
+          __syncthreads();
+          const int ov = mlp_fp32(plan.mlp[2], a.packed, s);
+          float* Rg = s.H[ov ^ 1];
+          if (tid < ROWS) {
+            const float lin = nf_sigmoid(s.H[ov][tid]) / 2.f + 0.5f;
+            Rg[tid] = __fmul_rn(lin, C[tid]); Rg[ROWS + tid] = __fmul_rn(lin, C[ROWS + tid]); Rg[2 * ROWS + tid] = __fmul_rn(lin, C[2 * ROWS + tid]);
+          }
+          __syncthreads();
+          rgb_raw = Rg;
+        }
       } else {
         const float* O = s.H[ob];
         if (tid < ROWS) s.sig[tid] = O[tid];
@@ -286,7 +323,7 @@ k_render_fp32(const __grid_constant__ NfPlan plan, const RenderArgs a) {
             const float w = al * trans;
             trans *= (1.f - al) + 1e-10f;
             float fr = rgb_raw[0 * ROWS + row], fg = rgb_raw[1 * ROWS + row], fb = rgb_raw[2 * ROWS + row];
-            nf_feat_act3(fr, fg, fb, plan.feat_act);
+            if (plan.refl_kind != NF_REFL_POSLINVIEW) nf_feat_act3(fr, fg, fb, plan.feat_act);      // PosLinearView's colours are final
             cr += w * fr; cg += w * fg; cb += w * fb;
             if (t < a.T - 1) wsum += w;
             if (a.alpha_out) a.alpha_out[ray * a.T + t] = al;
@@ -572,11 +609,12 @@ __global__ void k_ray_radii(const float* __restrict__ rays, long long B, int H, 
 // ---- packing -----------------------------------------------------------------------------------
 // W[n][k] (nn.Linear, row-major) -> Wt[k][n_pad] fp32, zero padded.
 __global__ void k_pack_fp32(const float* __restrict__ W, const float* __restrict__ b, float* __restrict__ Wt,
-                            float* __restrict__ bp, int n, int k, int n_pad) {
-  const int total = k * n_pad;
+                            float* __restrict__ bp, int n, int kh_ref, int kh_pad, int kx, int n_pad) {
+  const int total = (kh_pad + kx) * n_pad, k_ref = kh_ref + kx;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int kk = i / n_pad, nn = i - kk * n_pad;
-    Wt[i] = nn < n ? W[(size_t)nn * k + kk] : 0.f;
+    const int kr = kk < kh_pad ? (kk < kh_ref ? kk : -1) : kh_ref + (kk - kh_pad);     // padded hidden rows have no source column
+    Wt[i] = (nn < n && kr >= 0) ? W[(size_t)nn * k_ref + kr] : 0.f;
   }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) bp[i] = i < n ? b[i] : 0.f;
 }
@@ -591,9 +629,9 @@ int num_sms() {
 }  // namespace
 
 // ---- launchers (called from nf_api.cu) -------------------------------------------------------
-cudaError_t nf_launch_pack_fp32(const float* W, const float* b, float* Wt, float* bp, int n, int k, int n_pad, cudaStream_t st) {
-  const int total = k * n_pad;
-  k_pack_fp32<<<(total + 255) / 256, 256, 0, st>>>(W, b, Wt, bp, n, k, n_pad);
+cudaError_t nf_launch_pack_fp32(const float* W, const float* b, float* Wt, float* bp, int n_ref, int kh_ref, int kh_pad, int kx, int n_pad, cudaStream_t st) {
+  const int total = (kh_pad + kx) * n_pad;
+  k_pack_fp32<<<(total + 255) / 256, 256, 0, st>>>(W, b, Wt, bp, n_ref, kh_ref, kh_pad, kx, n_pad);
   return cudaGetLastError();
 }
 

@@ -2,7 +2,8 @@
 #pragma once
 #include "nf_common.cuh"
 
-cudaError_t nf_launch_pack_fp32(const float* W, const float* b, float* Wt, float* bp, int n, int k, int n_pad, cudaStream_t st);
+// W[n_ref][kh_ref + kx] (nn.Linear) -> Wt[kh_pad + kx][n_pad] (hidden rows kh_ref..kh_pad-1 and columns n_ref..n_pad-1 zero), bias[n_pad]
+cudaError_t nf_launch_pack_fp32(const float* W, const float* b, float* Wt, float* bp, int n_ref, int kh_ref, int kh_pad, int kx, int n_pad, cudaStream_t st);
 cudaError_t nf_launch_pack_fp16(const NfPlan& plan, int m, int j, const float* W, const float* b, void* packed, cudaStream_t st);
 cudaError_t nf_launch_render_fp32(const NfPlan& plan, const void* packed, const float* rays, int64_t n_rays, const float* ts,
                                   int T, int64_t ts_stride, const float* noise, const float* ray_time, const nf_mip_args* mip,

@@ -566,6 +566,7 @@ int tc_num_sms() {
 
 // nullptr if the tensor path can run this model, else the reason.
 const char* tc_unsupported(const NfPlan& p, int only_mlp = -1) {
+  if (p.refl_kind == NF_REFL_POSLINVIEW) return "PosLinearView runs on the fp32 pipeline only";
   if (p.kind == NF_KIND_DYN && only_mlp < 0) return "NF_KIND_DYN runs on the fp32 pipeline only in this build";
   int total = 0;
   for (int m = 0; m < p.n_mlps; ++m) {

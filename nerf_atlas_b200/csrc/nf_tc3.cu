@@ -971,6 +971,7 @@ bool build_prog3(const NfPlan& plan, Tc3Prog* P) {
 
 // nullptr if the staggered paired pipeline can run this model, else the reason.
 const char* nf_tc3_unsupported(const NfPlan& p) {
+  if (p.refl_kind == NF_REFL_POSLINVIEW) return "PosLinearView runs on the fp32 pipeline only (three-MLP head, hidden 128)";
   const bool wide = p.mip != NF_MIP_NONE || p.refl_kind != NF_REFL_VIEW;
   if (wide && p.kind != NF_KIND_PLAIN) return "Mip / Positional on the tensor pipeline: PlainNeRF only (DynamicNeRF runs them on the fp32 pipeline)";
   if (wide && p.enc != NF_ENC_HASH) return "Mip / Positional on the tensor pipeline need the hash-encoded density MLP";

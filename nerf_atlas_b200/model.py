@@ -45,7 +45,8 @@ MIP_FEATS = 96   # 2 x 16 degrees x 3 axes (reference src/utils.py:104-111, src/
 
 
 def describe_plain(intermediate: int = 64, sigmoid: str = "upshifted", bg: str = "black",
-                   hash_levels: int = 8, hash_table: int = 1 << 16, mip: Optional[str] = None, refl_kind: str = "view") -> ModelDesc:
+                   hash_levels: int = 8, hash_table: int = 1 << 16, mip: Optional[str] = None, refl_kind: str = "view",
+                   poslin_im: int = 64) -> ModelDesc:
   """PlainNeRF + View head as built by runner.load_model (reference src/nerf.py:310-324,
   src/refl.py:190-204, runner.py:1182-1183).  ``mip`` in (None, "cylinder", "cone", "cylinder_ref"): the IPE latent
   widens both MLP inputs by 96 (nerf.py:255,311-324)."""
@@ -57,6 +58,10 @@ def describe_plain(intermediate: int = 64, sigmoid: str = "upshifted", bg: str =
   d.density = _mlp(6 + 4 * hash_levels + ml, 4, 1 + intermediate, "leaky_relu")
   d.refl_kind = _lib.REFL[refl_kind]
   if refl_kind == "pos": d.refl = _mlp(6 + 4 * hash_levels + ml + intermediate, 5, 3, "leaky_relu")   # refl.Positional (refl.py:230-245)
+  elif refl_kind == "pos-linear-view":                                                                # refl.PosLinearView (refl.py:248-264)
+    im = poslin_im
+    d.refl = _mlp(6 + 4 * hash_levels + intermediate, 2, 3 + im, "leaky_relu")
+    d.refl_view = _mlp(6 + intermediate + im, 2, 1, "sin", hidden=128)
   else: d.refl = _mlp(5 + ml + intermediate, 4, 3, "sin")                                             # refl.View (refl.py:190-207)
   d.intermediate = intermediate
   d.enc = _lib.ENC["hash"]
@@ -496,6 +501,17 @@ class PositionalHead(nn.Module):
     self.mlp = SkipConnParams(38 + latent_size, out_features, 5, enc=HashParams())
 
 
+class PosLinearViewHead(nn.Module):
+  """Parameters of refl.PosLinearView (reference src/refl.py:248-290): `pos` (own hash tables, 2 layers, hidden 256) gives a
+  view-independent colour and an intermediate vector, `view` (2 layers, hidden 128, sin) a view-dependent scale in [1/2, 1]."""
+  def __init__(self, latent_size: int, out_features: int = 3, act: str = "thin", intermediate_size: int = 64):
+    super().__init__()
+    self.latent_size, self.out_features, self.im = latent_size, out_features, intermediate_size
+    self.act = act
+    self.pos = SkipConnParams(38 + latent_size, out_features + intermediate_size, 2, enc=HashParams())
+    self.view = SkipConnParams(6 + latent_size + intermediate_size, 1, 2, hidden_size=128, init="siren")
+
+
 _ACT_NAMES = {"sigmoid": "normal", "thin_sigmoid": "thin", "tanh": "tanh", "cyclic_sigmoid": "cyclic",
               "upshifted_sigmoid": "upshifted", "fat_sigmoid": "fat", "leaky_relu": "leaky_relu", "relu": "relu",
               "sin": "sin", "upshifted_softplus": "upshifted_softplus", "upshifted_relu": "upshifted_relu"}
@@ -662,7 +678,8 @@ class FusedPlainNeRF(FusedNeRF):
     super().__init__(**kwargs)
     if out_features != 3: raise NotImplementedError("out_features != 3")
     if refl_kind not in _lib.REFL: raise NotImplementedError(f"refl kind {refl_kind!r} (view | pos)")
-    head = PositionalHead if refl_kind == "pos" else ViewHead          # runner.load_model: refl.load(args, refl_kind, ...) (runner.py:1182-1183)
+    head = {"pos": PositionalHead, "pos-linear-view": PosLinearViewHead}.get(refl_kind, ViewHead)   # runner.load_model: refl.load(args, refl_kind, ...) (runner.py:1182-1183)
+    if refl_kind == "pos-linear-view": self.precision = "fp32"                                     # PosLinearView: the fp32 pipeline only
     self.refl = head(latent_size=self.mip_size() + self.intermediate_size, out_features=out_features, act=self.sigmoid_kind)
     self.first = SkipConnParams(38 + self.mip_size(), 1 + self.intermediate_size, 4, enc=HashParams())
 
@@ -677,7 +694,7 @@ class FusedPlainNeRF(FusedNeRF):
     bg = [k for k, v in {"black": "black", "white": "white", "random": "random_color"}.items() if getattr(ref.sky_color, "__name__", "") == v]
     if not bg: raise NotImplementedError("background kind of the reference model")
     self.bg = bg[0]
-    if type(ref.refl).__name__ not in ("View", "ViewHead", "Positional", "PositionalHead"):
+    if type(ref.refl).__name__ not in ("View", "ViewHead", "Positional", "PositionalHead", "PosLinearView", "PosLinearViewHead"):
       raise NotImplementedError(f"refl head {type(ref.refl).__name__}")
     self.refl, self.first = ref.refl, ref.first
     return self
@@ -686,17 +703,21 @@ class FusedPlainNeRF(FusedNeRF):
     enc = self.first.enc
     levels = len(enc.embs)
     return describe_plain(self.intermediate_size, _sigmoid_name(self.refl.act), self.bg, levels, enc.embs[0].weight.shape[0],
-                          mip=getattr(self, "mip", None), refl_kind=self.refl_kind)
+                          mip=getattr(self, "mip", None), refl_kind=self.refl_kind, poslin_im=int(getattr(self.refl, "im", 64)))
 
   @property
-  def refl_kind(self) -> str: return "pos" if type(self.refl).__name__ in ("Positional", "PositionalHead") else "view"
+  def refl_kind(self) -> str:
+    n = type(self.refl).__name__
+    return "pos" if n in ("Positional", "PositionalHead") else "pos-linear-view" if n in ("PosLinearView", "PosLinearViewHead") else "view"
 
   def _param_list(self) -> List[torch.Tensor]:
     ps: List[torch.Tensor] = []
-    for mlp in (self.first, self.refl.mlp):
+    plv = self.refl_kind == "pos-linear-view"
+    for mlp in ((self.first, self.refl.pos, self.refl.view) if plv else (self.first, self.refl.mlp)):
       for lin in _linears_of(mlp): ps += [lin.weight, lin.bias]
     ps += [e.weight for e in self.first.enc.embs]
     if self.refl_kind == "pos": ps += [e.weight for e in self.refl.mlp.enc.embs]
+    if plv: ps += [e.weight for e in self.refl.pos.enc.embs]
     return ps
 
 

@@ -382,6 +382,20 @@ def plain_from_pts(params: Params, pts: Tensor, ts: Tensor, r_o: Tensor, r_d: Te
   view = r_d.unsqueeze(0).expand_as(pts)
   elaz = dir_to_elev_azim(view)
   lat = [intermediate] if mip_latent is None else [mip_latent, intermediate]
+  if "refl.pos.init.weight" in params:
+    # refl.PosLinearView (refl.py:281-290): [pos, im] = act(pos_mlp([p, enc'(p), latent])); linear = sigmoid(view_mlp([p,
+    # normalize(view), latent, im])) / 2 + 1/2; rgb = linear * pos   (the feature activation is part of the head: no act afterwards)
+    enc2 = hash_encode(p, hash_tables(params, "refl.pos.enc")).reshape(batches + (-1,))
+    x0p = torch.cat([pts, enc2] + lat, dim=-1)
+    pos_out = SIGMOIDS[sigmoid](skip_mlp(x0p.reshape(-1, x0p.shape[-1]), params, "refl.pos", "leaky_relu", quant=quant)).reshape(batches + (-1,))
+    pos, im = pos_out[..., :3], pos_out[..., 3:]
+    x0v = torch.cat([pts, F.normalize(view, dim=-1)] + lat + [im], dim=-1)
+    lin_ = skip_mlp(x0v.reshape(-1, x0v.shape[-1]), params, "refl.view", "sin", quant=quant).reshape(batches + (-1,)).sigmoid()
+    rgb = (lin_ / 2 + 0.5) * pos
+    if per_ray_ts: alpha, weights = alpha_from_density_per_ray(density, ts, r_d)
+    else: alpha, weights = alpha_from_density(density, ts, r_d)
+    out = volumetric_integrate(weights, rgb) + sky(bg, weights)
+    return dict(out=out, alpha=alpha, weights=weights, rgb=rgb, density=density, first_out=first_out, hash_feats=enc[:, 3:], elaz=elaz[0])
   if "refl.mlp.enc.embs.0.weight" in params:
     # refl.Positional (refl.py:230-245): view independent, [p, enc'(p) = [p, feats'], latent], LeakyReLU, its own hash tables
     enc2 = hash_encode(p, hash_tables(params, "refl.mlp.enc")).reshape(batches + (-1,))
@@ -640,6 +654,18 @@ def make_plain_params(seed: int = 1337, intermediate: int = 64, sigma_gain: floa
     default_linear("refl.mlp.init", 256, w)
     for i in range(5): default_linear(f"refl.mlp.layers.{i}", 256, 256 + w if (i % 3 == 0 and i != 4) else 256)
     default_linear("refl.mlp.out", 3, 256)
+    return P
+  if refl_kind == "pos-linear-view":
+    # refl.PosLinearView (refl.py:248-264): pos = hash-encoded MLP (2 layers, hidden 256, torch-default init), view = siren MLP (2 layers, hidden 128)
+    P["refl.pos.enc.primes"] = P["first.enc.primes"].clone()
+    for i in range(HASH_LEVELS):
+      P[f"refl.pos.enc.embs.{i}.weight"] = torch.from_numpy(g.standard_normal((HASH_TABLE, HASH_FEAT)).astype(np.float32))
+    w, im = 38 + I, 64
+    default_linear("refl.pos.init", 256, w); default_linear("refl.pos.layers.0", 256, 256 + w); default_linear("refl.pos.layers.1", 256, 256)
+    default_linear("refl.pos.out", 3 + im, 256)
+    wv = 6 + I + im
+    siren_linear("refl.view.init", 128, wv); siren_linear("refl.view.layers.0", 128, 128 + wv); siren_linear("refl.view.layers.1", 128, 128)
+    siren_linear("refl.view.out", 1, 128)
     return P
   siren_linear("refl.mlp.init", 256, 5 + ML + I)
   siren_linear("refl.mlp.layers.0", 256, 256 + 5 + ML + I)

@@ -331,6 +331,9 @@ if __name__ == "__main__":
   if "--grads" in sys.argv:
     case_plain_grads("plain_t16_grads", seed=91, B=1, H=3, W=4, T=16, top=398, left=397)
     sys.exit(0)
+  if "--poslin" in sys.argv:
+    case_plain("plain_poslinview_t16", seed=83, B=1, H=4, W=5, T=16, sigma_gain=20.0, top=398, left=397, stages=False, refl_kind="pos-linear-view")
+    sys.exit(0)
   if "--pos" in sys.argv:
     case_plain("plain_pos_t16", seed=81, B=1, H=4, W=5, T=16, sigma_gain=20.0, top=398, left=397, stages=False, refl_kind="pos")
     sys.exit(0)
@@ -354,3 +357,4 @@ if __name__ == "__main__":
   case_dtu_rays("dtu_rays")
   case_trained("plain_trained_t64")
   case_sdf("sdf_siren_march")
+  case_plain("plain_poslinview_t16", seed=83, B=1, H=4, W=5, T=16, sigma_gain=20.0, top=398, left=397, stages=False, refl_kind="pos-linear-view")

@@ -857,3 +857,32 @@ def test_sdf_sphere_march_and_surface_render_vs_reference_golden(precision, hit_
   with torch.no_grad(): rp, rh, rt = O.sphere_march(P, flat.cpu()[:, :3], flat.cpu()[:, 3:], sdf_kind="siren", iters=24, near=2.0, far=6.0, bound_rad=1.5)
   assert float((h2.cpu() != rh).float().mean()) <= hit_tol
   assert float(((t2.cpu() - rt).abs() <= 20 * t_tol).float().mean()) >= 0.97         # unconverged rays after 24 steps: looser
+
+
+def test_poslinview_head_matches_reference_golden():
+  """PlainNeRF + refl.PosLinearView (`--refl-kind pos-linear-view`; reference src/refl.py:248-290): the fp32 pipeline (the view
+  sub-MLP's hidden 128 evaluated as 256 with zero-padded weights) vs a golden from the reference run and, on a larger ragged
+  slab with 128 samples per ray and the white background, vs the oracle; reference state_dict names; the tensor pipeline
+  refuses the model instead of falling back."""
+  import nerf_atlas_b200 as N, ctypes as C
+  fx = load_golden("plain_poslinview_t16")
+  P = O.make_plain_params(int(fx["seed"]), 64, float(fx["sigma_gain"]), refl_kind="pos-linear-view")
+  rays = O.make_rays(int(fx["B"]), int(fx["H"]), int(fx["W"]), 800, int(fx["seed"]), int(fx["top"]), int(fx["left"])).to(DEV)
+  m = N.FusedPlainNeRF(steps=int(fx["T"]), t_near=float(fx["near"]), t_far=float(fx["far"]), intermediate_size=64,
+                       sigmoid_kind=str(fx["sigmoid"]), bg=str(fx["bg"]), precision="fp32", refl_kind="pos-linear-view")
+  m.load_state_dict(P, strict=True); m = m.to(DEV).eval()
+  with torch.no_grad(): out = m(rays)
+  assert np.abs(out.cpu().numpy() - fx["out"]).max() <= 3e-5, np.abs(out.cpu().numpy() - fx["out"]).max()
+  assert np.abs(m.weights.cpu().numpy() - fx["weights"]).max() <= 2e-4
+  big = O.make_rays(1, 9, 11, seed=84, crop_top=300, crop_left=300)
+  ts = torch.linspace(2, 6, 128)
+  for kind, bg in (("upshifted", "white"), ("fat", "black"), ("leaky_relu", "black")):
+    with torch.no_grad(): ref = O.plain_forward(P, big, ts, sigmoid=kind, bg=bg)
+    m.steps = 128; m.set_sigmoid(kind); m.set_bg(bg)
+    with torch.no_grad(): o2 = m(big.to(DEV))
+    assert np.abs(o2.cpu().numpy() - ref["out"].numpy()).max() <= 3e-5 * max(1.0, float(ref["out"].abs().max())), (kind, bg)
+  why = N._lib.lib().nf_tensor_pipeline_support(C.byref(m.engine().desc))
+  assert why is not None and b"PosLinearView" in why
+  m.precision = "fp16"
+  with pytest.raises(RuntimeError):
+    with torch.no_grad(): m(rays)

@@ -260,3 +260,14 @@ def test_sdf_surface_oracle_matches_reference(golden_dir):
   assert np.array_equal(res["t"].numpy(), fx["t"]) and np.array_equal(res["pts"].numpy(), fx["pts"])
   assert np.array_equal(res["out"].numpy(), fx["out"])
   assert 0.2 < fx["hit"].mean() < 0.8 and np.abs(fx["out"][~fx["hit"]]).max() == 0
+
+
+def test_poslinview_head_oracle_matches_reference_bit_exact(golden_dir):
+  """PlainNeRF with `--refl-kind pos-linear-view` (refl.PosLinearView, reference src/refl.py:248-290; makefile `dnerf`, `gibson`)."""
+  fx = load(golden_dir, "plain_poslinview_t16")
+  params = O.make_plain_params(int(fx["seed"]), 64, float(fx["sigma_gain"]), refl_kind="pos-linear-view")
+  rays = O.make_rays(int(fx["B"]), int(fx["H"]), int(fx["W"]), 800, int(fx["seed"]), int(fx["top"]), int(fx["left"]))
+  ts = O.compute_ts(float(fx["near"]), float(fx["far"]), int(fx["T"]))
+  with torch.no_grad(): res = O.plain_forward(params, rays, ts, sigmoid=str(fx["sigmoid"]), bg=str(fx["bg"]))
+  for k in ("out", "alpha", "weights"):
+    assert np.array_equal(res[k].numpy(), fx[k]), f"pos-linear-view head: {k} differs from the reference run"
