@@ -58,10 +58,11 @@ struct Tc3Smem {
 #else
   float bias[2][2][256];                                     // [slot][step parity][column]
 #endif
-  float sig[2][ROWS];
+  float sig[2][2][ROWS];                                     // raw density per row: [slot][tile parity (boundary-warp mode; else 0)]
   float P[2][3][ROWS];                                       // NF_KIND_DYN: the deformed sample positions of the tile
   float warp_agg[2][4]; int warp_cont[2][4]; float warp_sum[2][4][4]; float carry[2][8];
   unsigned long long w_land[MAX_STAGES3], w_empty[MAX_STAGES3], w_ready[MAX_STAGES3], acc_full[2], a_ready[2];
+  unsigned long long bnd_full[2], x0_free[2];   // boundary-warp mode: the path's last Linear is complete / X0[slot] is no longer read
   uint32_t tmem_base; int pad_;
   int4 lin[MAX_LIN3][2];        // per Linear, for the epilogue warps: {n_pad, bias byte offset, act, flags}, {k0_pad, -, -, -}
                                 // flags: 1 = `out` Linear, 2 = `init` Linear, bits 2-3 = what the epilogue of an `out` does:
@@ -83,7 +84,7 @@ struct __align__(16) Tc3Lin {
 // 1's H buffer; 2 = two tiles in flight SHARING one wide x0 buffer (up to 208 columns: the two X0 buffers + the first 12 KB of
 // the ring region; the ring shrinks to 3 x 12 KB).  Sharing works because x0 is only live while a slot is in the first two
 // Linears of an MLP: with slot 1 three Linears behind slot 0 the two live windows never meet (checked on the host).
-struct __align__(16) Tc3Prog { int32_t n_lin, lag, single, pad1_; Tc3Lin lin[MAX_LIN3]; };
+struct __align__(16) Tc3Prog { int32_t n_lin, lag, single, x0_last; Tc3Lin lin[MAX_LIN3]; };   // x0_last: the last Linear of the chain that reads X0
 
 // Training forward (TRAIN instantiation): where every Linear's input operand (and, for sin MLPs, the cosine of its
 // pre-activation) of every tile goes (NfTrainPlan, nf_common.cuh).  Offsets in 256-byte units from Tc3Args::ws.
@@ -141,6 +142,13 @@ __device__ __forceinline__ void wait_acc(uint32_t bar, uint32_t parity, int debu
 // minimax polynomial for sin(2 pi r): max error 6.3e-6, far inside the fp16 rounding of the result (2.4e-4).
 // MEASURED (profiles/r01_sin_poly_sweep.txt): 0 pairs 113.8 ms/frame, 2 pairs 115.0, 3 pairs 116.2, 4 pairs 119.7 -- the sin
 // epilogue is not MUFU-throughput-bound but issue/latency-bound, so the extra FMA-pipe instructions only cost.  Default 0.
+// boundary-warp mode: the boundary warps also write the View head's [p, elaz] x0 tail (else the density-out epilogue does)
+#ifndef NF_BW
+#define NF_BW 1
+#endif
+#ifndef NF_BW_PRETAIL
+#define NF_BW_PRETAIL 1
+#endif
 #ifndef NF_SIN_POLY_PAIRS
 #define NF_SIN_POLY_PAIRS 0
 #endif
@@ -354,12 +362,12 @@ __device__ __forceinline__ void unit_of(int pass, int slot, int tpr, int nslot, 
 // tile boundaries -- so a ray's result does not depend on where in a unit it happens to sit.
 __device__ __forceinline__ void composite_tile3(Tc3Smem& s, int slot, const NfPlan& plan, const Tc3Args& a, const NfStreamMap& map,
                                                 long long u, int sub, int row, int lane, int q, float cr, float cg, float cb,
-                                                float* sigma_out = nullptr) {
+                                                const float* sig, float* sigma_out = nullptr, bool may_use_H = true) {
   long long ray; int t;
   const bool valid = map.locate(u, sub, row, a.n_rays, ray, t);       // t is the position within the (padded) ray even when invalid
   float al = 0.f;
   if (valid) {
-    float sr = s.sig[slot][row];
+    float sr = sig[row];
     if (a.noise) sr += __ldg(a.noise + ray * a.T + t);
     if (sigma_out) sigma_out[ray * a.T + t] = sr;                     // TRAIN: the raw density the composite consumed (noise included)
     const float* rr = a.rays + ray * 6;
@@ -394,7 +402,7 @@ __device__ __forceinline__ void composite_tile3(Tc3Smem& s, int slot, const NfPl
   }
   const float wr = w * cr, wg = w * cg, wb = w * cb, wl = (valid && t < a.T - 1) ? w : 0.f;
   float* wrgb = reinterpret_cast<float*>(s.H[slot]);          // H[slot] is dead between the last Linear's MMA and the next tile
-  const bool fast = (map.Tp & 31) == 0;                       // no warp straddles two rays: per-warp sums suffice
+  const bool fast = (map.Tp & 31) == 0 || !may_use_H;         // no warp straddles two rays: per-warp sums suffice (boundary-warp mode: always, H is live)
   if (fast) {
     float x0 = wr, x1 = wg, x2 = wb, x3 = wl;
 #pragma unroll
@@ -452,10 +460,15 @@ __device__ __forceinline__ void composite_tile3(Tc3Smem& s, int slot, const NfPl
 // AUX: explicit sample positions (from_pts) and the random background are compiled in (kept out of the common instantiation for
 // the same reason as WIDE / DYN).
 // WIDE: 0 = no wide-x0 code, 1 = wide x0 without the Mip encoder (Positional head, Fourier SDF), 2 = with it.
-template <int NST, int SPCT, int NCQ, int WIDE, bool DYN, bool TRAIN = false, bool AUX = false>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (4 * NCQ + NST + 1), 1)
+// BW ("boundary warps"): four more warps (one per TMEM lane quarter) own the tile boundary -- they encode the next tile's x0 as
+// soon as the chain's last x0 consumer is complete (x0_free), read the finished tile's colours when its last Linear is complete
+// (bnd_full), hand the slot back to the issuer and only then composite -- so the 16 epilogue warps never leave the MLP phases
+// and the ~7 K-cycle boundary is off both the slot's critical path and the epilogue warps' time.  Needs T % 32 == 0, WIDE == 0.
+template <int NST, int SPCT, int NCQ, int WIDE, bool DYN, bool TRAIN = false, bool AUX = false, bool BW = false>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (4 * NCQ + NST + 1 + (BW ? 4 : 0)), 1)
 k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Prog prog, const Tc3Args a, const __grid_constant__ Tc3Train tr) {
   static_assert(NST * SPCT * 4096 <= RING_BYTES && NST <= MAX_STAGES3, "ring geometry");
+  static_assert(!BW || (WIDE == 0 && NST == 3 && NCQ == 4), "boundary warps: plain two-tile mode, warp groups {0-15, 16-19, 20-23}");
   constexpr int STAGE_BYTES = SPCT * 4096;
   constexpr int RING_OFF = RING_BYTES - NST * SPCT * 4096;     // a smaller ring sits at the END of the region (shared wide x0 in front)
   constexpr int EPIW = 4 * NCQ, EPI_THREADS = 32 * EPIW;
@@ -477,6 +490,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
   if (threadIdx.x == 0) {
     for (int i = 0; i < NST; ++i) { mbar_init(smem_u32(&s.w_land[i]), 1); mbar_init(smem_u32(&s.w_empty[i]), 1); mbar_init(smem_u32(&s.w_ready[i]), 2); }
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s.acc_full[i]), 1); mbar_init(smem_u32(&s.a_ready[i]), 2 * EPIW); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s.bnd_full[i]), 1); mbar_init(smem_u32(&s.x0_free[i]), EPIW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == EPIW) {
@@ -504,7 +518,10 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
   tc_fence_after();
   if (s.tmem_base != 0) __trap();
 
-  if (warp >= EPIW && warp < EPIW + NST) {
+  if (warp >= EPIW && warp <= EPIW + NST) {
+  // BW: 24 warps start at 80 registers (768 x 80 = the CTA's pool); the producer / issuer warp group gives 32 of them to the epilogue warp groups
+  if (BW) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+  if (warp < EPIW + NST) {
     // ================= weight producers (both CTAs): one ring stage each =================
     // The ring carries, step by step, slot 0's Linear then slot 1's (half a round behind); entry g goes to stage g % NST.
     if (elect_one()) {
@@ -543,7 +560,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
       }
       ST_FLUSH(8, blockIdx.x == 0 && p == 0);
     }
-  } else if (warp == EPIW + NST) {
+  } else {
     // ================= MMA issuer (leader CTA only): one thread, tight nested loops =================
     // The probe of the NEXT ring stage is issued before the current chunk's MMAs, so its ~150-cycle latency is hidden.
     if (crank == 0 && elect_one()) {
@@ -551,7 +568,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
       const uint32_t base4 = smem_u32(smem_raw) >> 4;
       const uint32_t w4 = base4 + (uint32_t)((offsetof(Tc3Smem, W) + RING_OFF) >> 4);
       const uint32_t bar_wready = smem_u32(&s.w_ready[0]), bar_wempty = smem_u32(&s.w_empty[0]);
-      const uint32_t bar_a = smem_u32(&s.a_ready[0]), bar_acc = smem_u32(&s.acc_full[0]);
+      const uint32_t bar_a = smem_u32(&s.a_ready[0]), bar_acc = smem_u32(&s.acc_full[0]), bar_bnd = smem_u32(&s.bnd_full[0]);
       const uint32_t a_lbo = (uint32_t)(KG_BYTES >> 4) << 16, kstep4 = (uint32_t)(2 * KG_BYTES) >> 4;
 #if NF_BIAS_IN_MMA
       const uint32_t ones4 = (base4 + (uint32_t)(offsetof(Tc3Smem, ones) >> 4)) | a_lbo;
@@ -608,15 +625,17 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
             umma2_commit_mc(bar_wempty + stage * 8u);
             stage = nstage; phase = nphase;
           }
-          umma2_commit_mc(bar_acc + slot * 8u);
+          umma2_commit_mc((BW && li + 1 == n ? bar_bnd : bar_acc) + slot * 8u);      // BW: the path's last Linear reports to the boundary warps
           const int ln = li + 1 == n ? 0 : li + 1;
           if (slot) li1 = ln; else li0 = ln;
         }
       }
       ST_FLUSH(0, blockIdx.x == 0);
     }
-  } else {
+  }
+  } else if (!BW || warp < EPIW) {
     // ================= encode + epilogue: all 16 warps serve the two slots alternately =================
+    if (BW) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");   // 16 x 32 x 88 + 128 x 48 + 128 x 80 = 768 x 80: the pool is what the CTA was launched with
     // TMEM lane quarter q = warp % 4 (rows 32q..32q+31), column quarter cq = warp / 4 (64 accumulator columns).
     const int q = warp & 3, cq = warp >> 2;
     const int e_tid = warp * 32 + lane;
@@ -631,6 +650,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
         const int kl = k - (slot ? lag : 0);
         if (kl < 0 || kl > nsteps || (slot && single)) continue;
         const int j = slot ? j1 : j0, P = slot ? P1 : P0;
+        if (BW && j == 0) { if (slot) j1 = 1; else j0 = 1; continue; }      // the tile boundary belongs to the boundary warps
         uint8_t* H = s.H[slot]; uint8_t* X0 = single ? s.H[1] : shared_x0 ? s.X0[0] : s.X0[slot];
         const uint32_t t_acc = t_lane + (uint32_t)slot * 256u;
         const uint32_t a_ready_leader = leader_addr(smem_u32(&s.a_ready[slot]));
@@ -669,7 +689,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
             tc_fence_before();
             float cr, cg, cb;
             if (plan.kind == NF_KIND_TINY) {
-              s.sig[slot][row] = ADDB(__uint_as_float(v[0]), 0);
+              s.sig[slot][0][row] = ADDB(__uint_as_float(v[0]), 0);
               cr = ADDB(__uint_as_float(v[1]), 1); cg = ADDB(__uint_as_float(v[2]), 2); cb = ADDB(__uint_as_float(v[3]), 3);
             } else {
               cr = ADDB(__uint_as_float(v[0]), 0); cg = ADDB(__uint_as_float(v[1]), 1); cb = ADDB(__uint_as_float(v[2]), 2);
@@ -680,7 +700,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
             }
             nf_feat_act3(cr, cg, cb, plan.feat_act);
             ST_ADD(6);
-            composite_tile3(s, slot, plan, a, map, u, sub, row, lane, q, cr, cg, cb, TRAIN ? tr.sigma_out : nullptr);
+            composite_tile3(s, slot, plan, a, map, u, sub, row, lane, q, cr, cg, cb, s.sig[slot][0], TRAIN ? tr.sigma_out : nullptr);
             ST_ADD(5);
           }
           if (has_next) {
@@ -741,7 +761,8 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
           ST_ADD(1);
         } else {
           // ---------- epilogue of Linear j-1 ----------
-          if (j == n - 2 && cq == 1 && P + 1 < passes) {
+          if (BW && j - 1 == prog.x0_last && lane == 0) mbar_arrive(smem_u32(&s.x0_free[slot]));   // X0[slot] may take the next tile's x0
+          if (!BW && j == n - 2 && cq == 1 && P + 1 < passes) {
             // the next tile's rays are a first touch (HBM, ~2 K cycles): pull them into L2 two phases before phase 0 needs them
             long long u; int sub; unit_of(P + 1, slot, map.tpr, nslot, u, sub);
             long long ray; int t;
@@ -837,6 +858,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
             // density MLP out (tensor order [inter(I), sigma]) -> raw x0 of the RGB head + raw density
             const int iu = plan.intermediate >> 4;
             const bool pos_head = WIDE && plan.refl_kind == NF_REFL_POSITIONAL;
+            const bool pre_tail = BW && NF_BW_PRETAIL && !DYN && plan.kind == NF_KIND_PLAIN && plan.mlp[0].k0_pad <= plan.intermediate;   // the boundary warps wrote [p, elaz]
             const int mip1 = (WIDE == 2 && plan.mip != NF_MIP_NONE) ? nf_mip_col(plan, 1) : -1;
             if (pos_head || mip1 >= 0) {
               // wide RGB-head inputs (single mode): every thread takes a share of its row's Positional hash features and Mip latent
@@ -870,8 +892,8 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
                 uint8_t* d0 = X0 + (un * 2) * KG_BYTES + row * 16;
                 st_v4(d0, o[0], o[1], o[2], o[3]); st_v4(d0 + KG_BYTES, o[4], o[5], o[6], o[7]);
               } else {
-                s.sig[slot][row] = ADDB(__uint_as_float(v[0]), plan.intermediate);
-                if (!pos_head) {
+                s.sig[slot][BW ? (P & 1) : 0][row] = ADDB(__uint_as_float(v[0]), plan.intermediate);
+                if (!pos_head && !pre_tail) {
                   long long u; int sub; unit_of(P, slot, map.tpr, nslot, u, sub);
                   long long ray; int t;
                   float px = 0.f, py = 0.f, pz = 0.f, el = 0.f, az = 0.f;
@@ -911,6 +933,89 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
     ST_FLUSH(16, blockIdx.x == 0 && warp == 0 && lane == 0);
     ST_FLUSH(24, blockIdx.x == 0 && warp == EPIW - 1 && lane == 0);
     ST_FLUSH(32, blockIdx.x == 1 && warp == 0 && lane == 0);
+  } else {
+    // ================= boundary warps (BW): one per TMEM lane quarter, thread = row =================
+    // Per slot and tile boundary (tile P-1 -> tile P): [wait x0_free] encode tile P's x0 (+ the View head's [p, elaz] tail, whose
+    // columns the density MLP does not touch) -> [wait bnd_full] read tile P-1's colours out of TMEM -> hand the slot to the
+    // issuer -> composite tile P-1.  The two slots' boundaries alternate in the global step order (slot 1 lags by `lag`
+    // Linears), so one set of warps serves both in turn; every wait is for an event that depends only on earlier boundaries.
+    const int q = warp & 3, row = q * 32 + lane;
+    const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+    const bool dyn = DYN && plan.kind == NF_KIND_DYN;
+    const int first_m = dyn ? 2 : 0;
+    const bool hashed = dyn ? plan.deform_enc == NF_ENC_HASH : plan.enc == NF_ENC_HASH;
+    const bool pre_tail = NF_BW_PRETAIL && !DYN && plan.kind == NF_KIND_PLAIN && plan.mlp[0].k0_pad <= plan.intermediate;
+    ST_DECL;
+    for (int P = 0; P <= passes; ++P) {
+#pragma unroll 1
+      for (int slot = 0; slot < 2; ++slot) {
+        const bool comp = P >= 1, has_next = P < passes;
+        uint8_t* X0 = s.X0[slot];
+        if (has_next) {
+          long long u; int sub; unit_of(P, slot, map.tpr, 2, u, sub);
+          long long ray; int t;
+          const bool ok = map.locate(u, sub, row, a.n_rays, ray, t);
+          float px = 0.f, py = 0.f, pz = 0.f, el = 0.f, az = 0.f, tt_dyn = 0.f;
+          if (ok) {
+            const float* rr = a.rays + ray * 6;
+            const float tt = __ldg(a.ts + ray * a.ts_stride + t);
+            const float dx = __ldg(rr + 3), dy = __ldg(rr + 4), dz = __ldg(rr + 5);
+            px = nf_pt(__ldg(rr + 0), tt, dx); py = nf_pt(__ldg(rr + 1), tt, dy); pz = nf_pt(__ldg(rr + 2), tt, dz);
+            if (AUX && a.pts) { const float* pp = a.pts + (ray * a.T + t) * 3; px = __ldg(pp); py = __ldg(pp + 1); pz = __ldg(pp + 2); }
+            if (pre_tail) nf_elaz(dx, dy, dz, el, az);
+            if (dyn && !hashed) tt_dyn = __ldg(a.ray_time + ray);
+          }
+          ST_ADD(1);
+          if (P >= 1) mbar_wait_suspend(smem_u32(&s.x0_free[slot]), (uint32_t)(P - 1) & 1u);
+          ST_ADD(0);
+          if (hashed) {
+            hash_x0(X0, reinterpret_cast<const float4*>(a.packed + (dyn ? plan.hash2_off : plan.hash_off)), plan, px, py, pz, row, 0, 1);
+            hash_x0_tail(X0, plan, plan.mlp[first_m].k0_pad, px, py, pz, row);
+          } else {
+            st_v4(X0 + row * 16, pack_h2(px, py), pack_h2(pz, tt_dyn), 0, 0);                 // direct deformation: x0 = [p, t]; else [p]
+            for (int g = 1; g < (plan.mlp[first_m].k0_pad >> 3); ++g) st_v4(X0 + g * KG_BYTES + row * 16, 0, 0, 0, 0);
+          }
+          if (pre_tail) {
+            const int g0 = plan.intermediate >> 3;
+            st_v4(X0 + g0 * KG_BYTES + row * 16, pack_h2(px, py), pack_h2(pz, el), pack_h2(az, 0.f), 0);
+            for (int g = g0 + 1; g < (plan.mlp[1].k0_pad >> 3); ++g) st_v4(X0 + g * KG_BYTES + row * 16, 0, 0, 0, 0);
+          }
+          fence_proxy_async();
+          ST_ADD(1);
+        }
+        float cr = 0.f, cg = 0.f, cb = 0.f;
+        if (comp) {
+          mbar_wait_suspend(smem_u32(&s.bnd_full[slot]), (uint32_t)(P - 1) & 1u);
+          ST_ADD(2);
+          tc_fence_after();
+          uint32_t v[16];
+          tmem_ld16(t_lane + (uint32_t)slot * 256u, v); tmem_ld_wait(); reg_fence16(v);
+          tc_fence_before();
+          if (plan.kind == NF_KIND_TINY) {
+            s.sig[slot][(P - 1) & 1][row] = __uint_as_float(v[0]);
+            cr = __uint_as_float(v[1]); cg = __uint_as_float(v[2]); cb = __uint_as_float(v[3]);
+          } else {
+            cr = __uint_as_float(v[0]); cg = __uint_as_float(v[1]); cb = __uint_as_float(v[2]);
+          }
+        }
+        if (has_next) {
+          __syncwarp();
+          if (lane < 4) mbar_arrive_cluster_relaxed(leader_addr(smem_u32(&s.a_ready[slot])));      // 4 warps x 4 lanes = the 16 arrivals of a phase
+        }
+        ST_ADD(3);
+        if (comp) {
+          long long u; int sub; unit_of(P - 1, slot, map.tpr, 2, u, sub);
+          if (TRAIN) {
+            long long ray; int t;
+            if (map.locate(u, sub, row, a.n_rays, ray, t)) { float* o = tr.rgbraw_out + (ray * a.T + t) * 3; o[0] = cr; o[1] = cg; o[2] = cb; }
+          }
+          nf_feat_act3(cr, cg, cb, plan.feat_act);
+          composite_tile3(s, slot, plan, a, map, u, sub, row, lane, q, cr, cg, cb, s.sig[slot][(P - 1) & 1], TRAIN ? tr.sigma_out : nullptr, false);
+          ST_ADD(4);
+        }
+      }
+    }
+    ST_FLUSH(40, blockIdx.x == 0 && q == 0 && lane == 0);
   }
   // ---- teardown ----
 #ifdef NF_TC_STATS
@@ -944,6 +1049,8 @@ bool build_prog3(const NfPlan& plan, Tc3Prog* P) {
     }
   }
   P->n_lin = nl; P->lag = nl / 2;
+  P->x0_last = 0;
+  for (int i = 0; i < nl; ++i) if (P->lin[i].k0_steps) P->x0_last = i;
   int kmax = 0;
   for (int m = 0; m < plan.n_mlps; ++m) kmax = plan.mlp[m].k0_pad > kmax ? plan.mlp[m].k0_pad : kmax;
   if (kmax > X0K) {
@@ -1074,20 +1181,9 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
         if (tp->lin[k].k0_pad) { if (tr.lin[i].skip0 < 0) tr.lin[i].skip0 = k; else if (tr.lin[i].skip1 < 0) tr.lin[i].skip1 = k; else return cudaErrorNotSupported; }
     }
   }
-  const void* fn = train ? (const void*)k_render_tc3<3, 4, 4, 0, false, true>
-                 : auxk ? (const void*)k_render_tc3<3, 4, 4, 0, false, false, true>
-                 : (wide_shared && mipk) ? (const void*)k_render_tc3<3, 3, 4, 2, false>
-                 : wide_shared ? (const void*)k_render_tc3<3, 3, 4, 1, false>
-                 : wide ? (const void*)k_render_tc3<3, 4, 4, 2, false>
-                 : dynk ? (const void*)k_render_tc3<3, 4, 4, 0, true>
-#ifdef NF_EXPERIMENTS
-                 : epiw == 24 ? (const void*)k_render_tc3<3, 4, 6, 0, false>
-                 : ring == 6 ? (const void*)k_render_tc3<6, 2, 4, 0, false>
-#endif
-                 : (const void*)k_render_tc3<3, 4, 4, 0, false>;
-  const int threads = 32 * (epiw + ring + 1);
-  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tc3Smem));
-  if (e != cudaSuccess) return e;
+  // boundary-warp mode (four more warps own the tile boundary): the plain two-tile instantiations, warp-aligned rays
+  const bool bw = NF_BIAS_IN_MMA && NF_BW && !wide && (T & 31) == 0 && ring == 3 && epiw == 16;
+  const int threads = 32 * (epiw + ring + 1 + (bw ? 4 : 0));
   const NfStreamMap map(T, ROWS);
   const long long units = map.units(n_rays);
   if (units == 0) return cudaSuccess;
@@ -1104,25 +1200,38 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
   cudaMemsetAsync(d_stats, 0, 64 * sizeof(long long), st);
   a.stats = d_stats;
 #endif
-  if (train) k_render_tc3<3, 4, 4, 0, false, true><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
-  else if (auxk) k_render_tc3<3, 4, 4, 0, false, false, true><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
-  else if (wide_shared && mipk) k_render_tc3<3, 3, 4, 2, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
-  else if (wide_shared) k_render_tc3<3, 3, 4, 1, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
-  else if (wide) k_render_tc3<3, 4, 4, 2, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
-  else if (dynk) k_render_tc3<3, 4, 4, 0, true><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
+  cudaError_t e = cudaSuccess;
+  auto go = [&](auto kern) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tc3Smem));
+    if (e == cudaSuccess) kern<<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
+  };
+  if (bw) {
+    if (train) go(k_render_tc3<3, 4, 4, 0, false, true, false, true>);
+    else if (auxk) go(k_render_tc3<3, 4, 4, 0, false, false, true, true>);
+    else if (dynk) go(k_render_tc3<3, 4, 4, 0, true, false, false, true>);
+    else go(k_render_tc3<3, 4, 4, 0, false, false, false, true>);
+  }
+  else if (train) go(k_render_tc3<3, 4, 4, 0, false, true>);
+  else if (auxk) go(k_render_tc3<3, 4, 4, 0, false, false, true>);
+  else if (wide_shared && mipk) go(k_render_tc3<3, 3, 4, 2, false>);
+  else if (wide_shared) go(k_render_tc3<3, 3, 4, 1, false>);
+  else if (wide) go(k_render_tc3<3, 4, 4, 2, false>);
+  else if (dynk) go(k_render_tc3<3, 4, 4, 0, true>);
 #ifdef NF_EXPERIMENTS
-  else if (epiw == 24) k_render_tc3<3, 4, 6, 0, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
-  else if (ring == 6) k_render_tc3<6, 2, 4, 0, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
+  else if (epiw == 24) go(k_render_tc3<3, 4, 6, 0, false>);
+  else if (ring == 6) go(k_render_tc3<6, 2, 4, 0, false>);
 #endif
-  else k_render_tc3<3, 4, 4, 0, false><<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
+  else go(k_render_tc3<3, 4, 4, 0, false>);
+  if (e != cudaSuccess) return e;
 #ifdef NF_TC_STATS
   if (getenv("NF_TC_STATS_PRINT")) {
     cudaStreamSynchronize(st);
     long long h[64];
     cudaMemcpy(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost);
-    const char* names[5] = {"issuer  [total, wait_a, wait_w, issue+other, n_w_waits]", "producer0 [total, wait_empty, copy, other, n]",
-                            "epi w0  [total, wait_acc, phase0-encode, leaky, sin, dens_out, other+composite, colour-read]", "epi w15 [same]", "epi w0 of the peer CTA [same]"};
-    for (int r = 0; r < 5; ++r) {
+    const char* names[6] = {"issuer  [total, wait_a, wait_w, issue+other, n_w_waits]", "producer0 [total, wait_empty, copy, other, n]",
+                            "epi w0  [total, wait_acc, phase0-encode, leaky, sin, dens_out, other+composite, colour-read]", "epi w15 [same]", "epi w0 of the peer CTA [same]",
+                            "boundary warp 0 [total, wait x0_free, encode, wait bnd_full, colour read + arrive, composite]"};
+    for (int r = 0; r < 6; ++r) {
       printf("STATS %s:", names[r]);
       for (int i = 0; i < 8; ++i) printf(" %lld", h[r * 8 + i]);
       printf("\n");
