@@ -35,17 +35,13 @@ using namespace nf_ptx;
 
 // Biases ride in the MMA: every Linear's weight image carries one extra K-step (16 rows: fp16 hi and lo halves of the fp32 bias,
 // then zeros) that is multiplied with a constant [1, 1, 0, ...] block, so the accumulator already holds W x + b and no epilogue
-// adds (or loads) a bias.  NF_BIAS_IN_MMA=0 builds the earlier form (bias added by the epilogue warps from shared memory) for A/B.
-#ifndef NF_BIAS_IN_MMA
-#define NF_BIAS_IN_MMA 1
-#endif
-#if NF_BIAS_IN_MMA
-#define ADDB(x, i) (x)
-#else
-#define ADDB(x, i) ((x) + bias[i])
-#endif
+// adds (or loads) a bias.  Only the first 8-row K-group of that step is non-zero, so only IT is streamed: it rides at the end of the
+// Linear's last weight chunk (2 KB at N = 256) and the bias MMA reads it with a B descriptor whose LBO is 0 (both K-groups = the
+// same core matrices) against an A block [1, 1, 0, ... | 0 ...] of two 128-byte core matrices read with SBO = 0 (all 16 row groups
+// = the same core matrix).  A hidden Linear is then 4 ring stages instead of 4 + a one-step stage of its own.
 constexpr int X0K = 80;
-constexpr int RING_BYTES = 48 * 1024;                       // weight ring per CTA: NST stages of SPCT K-steps (4 KB each at N = 256)
+constexpr int BIAS_PIECE = 2048;                            // the bias K-group of the widest half image (128 rows x 16 B)
+constexpr int RING_BYTES = 3 * (4 * 4096 + BIAS_PIECE);     // weight ring per CTA: NST stages of SPCT K-steps (4 KB each at N = 256) + a bias piece
 constexpr int MAX_LIN3 = 24;
 constexpr int MAX_STAGES3 = 6;
 
@@ -53,15 +49,10 @@ struct Tc3Smem {
   uint8_t H[2][ROWS * 256 * 2];
   uint8_t X0[2][ROWS * X0K * 2];
   uint8_t W[RING_BYTES];
-#if NF_BIAS_IN_MMA
-  uint8_t ones[2 * ROWS * 16];                               // A operand of the bias K-step: [2 K-groups][128 rows][8 halves] = [1, 1, 0, ...] per row
-#else
-  float bias[2][2][256];                                     // [slot][step parity][column]
-#endif
+  uint8_t ones[256];                                         // A operand of the bias K-step: core matrix [8 rows][1, 1, 0, ...] + a zero core matrix (read with SBO = 0)
   float sig[2][2][ROWS];                                     // raw density per row: [slot][tile parity (boundary-warp mode; else 0)]
-  float P[2][3][ROWS];                                       // NF_KIND_DYN: the deformed sample positions of the tile
   float warp_agg[2][4]; int warp_cont[2][4]; float warp_sum[2][4][4]; float carry[2][8];
-  unsigned long long w_land[MAX_STAGES3], w_empty[MAX_STAGES3], w_ready[MAX_STAGES3], acc_full[2], a_ready[2];
+  unsigned long long w_land[MAX_STAGES3], w_empty[MAX_STAGES3], w_ready[MAX_STAGES3], acc_full[2], a_ready[4];   // a_ready[slot]: x0 + hidden columns 0-127 of the next Linear's operand are written; a_ready[2 + slot]: columns 128-255 too
   unsigned long long bnd_full[2], x0_free[2];   // boundary-warp mode: the path's last Linear is complete / X0[slot] is no longer read
   uint32_t tmem_base; int pad_;
   int4 lin[MAX_LIN3][2];        // per Linear, for the epilogue warps: {n_pad, bias byte offset, act, flags}, {k0_pad, -, -, -}
@@ -185,20 +176,11 @@ __device__ __forceinline__ void epi_hidden3(uint8_t* __restrict__ H, uint32_t t_
     tmem_ld_wait();
     reg_fence16(v[u & 1]);
     if (un + NCQ < 16) tmem_ld16(t_acc + col + NCQ * 16, v[(u + 1) & 1]);
-#if !NF_BIAS_IN_MMA
-    const float4* b4 = reinterpret_cast<const float4*>(bias_s + col);
-#endif
     uint32_t o[8];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-#if NF_BIAS_IN_MMA
       const float x0 = __uint_as_float(v[u & 1][4 * i]), x1 = __uint_as_float(v[u & 1][4 * i + 1]);
       const float x2 = __uint_as_float(v[u & 1][4 * i + 2]), x3 = __uint_as_float(v[u & 1][4 * i + 3]);
-#else
-      const float4 b = b4[i];                                 // same address in every lane: one broadcast wavefront
-      const float x0 = __uint_as_float(v[u & 1][4 * i]) + b.x, x1 = __uint_as_float(v[u & 1][4 * i + 1]) + b.y;
-      const float x2 = __uint_as_float(v[u & 1][4 * i + 2]) + b.z, x3 = __uint_as_float(v[u & 1][4 * i + 3]) + b.w;
-#endif
       if (ACT == NF_ACT_SIN && 2 * i < NF_SIN_POLY_PAIRS) o[2 * i] = pack_h2(sin_poly(x0), sin_poly(x1));
       else o[2 * i] = act_pack_t<ACT>(x0, x1);
       if (ACT == NF_ACT_SIN && 2 * i + 1 < NF_SIN_POLY_PAIRS) o[2 * i + 1] = pack_h2(sin_poly(x2), sin_poly(x3));
@@ -210,17 +192,10 @@ __device__ __forceinline__ void epi_hidden3(uint8_t* __restrict__ H, uint32_t t_
       uint8_t* g = gA + (col >> 3) * KG_BYTES + row * 16;
       st_global_v4(g, o[0], o[1], o[2], o[3]); st_global_v4(g + KG_BYTES, o[4], o[5], o[6], o[7]);
       if (ACT == NF_ACT_SIN && gC) {
-#if !NF_BIAS_IN_MMA
-        const float4* b4c = reinterpret_cast<const float4*>(bias_s + col);
-#endif
         uint32_t c[8];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-#if NF_BIAS_IN_MMA
           const float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-#else
-          const float4 b = b4c[i];
-#endif
           c[2 * i] = pack_h2(__cosf(__uint_as_float(v[u & 1][4 * i]) + b.x), __cosf(__uint_as_float(v[u & 1][4 * i + 1]) + b.y));
           c[2 * i + 1] = pack_h2(__cosf(__uint_as_float(v[u & 1][4 * i + 2]) + b.z), __cosf(__uint_as_float(v[u & 1][4 * i + 3]) + b.w));
         }
@@ -241,20 +216,8 @@ __device__ __forceinline__ void epi_hidden3_sin_pipelined(uint8_t* __restrict__ 
   float x[16], y[16];
   tmem_ld16(t_acc + cq * 16, v);
   tmem_ld_wait(); reg_fence16(v);
-#if NF_BIAS_IN_MMA
 #pragma unroll
   for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[i]);
-#else
-  {
-    const float4* b4 = reinterpret_cast<const float4*>(bias_s + cq * 16);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 b = b4[i];
-      x[4 * i] = __uint_as_float(v[4 * i]) + b.x; x[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b.y;
-      x[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b.z; x[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b.w;
-    }
-  }
-#endif
   constexpr int MAXU = (16 + NCQ - 1) / NCQ;
 #pragma unroll
   for (int u = 0; u < MAXU; ++u) {
@@ -267,24 +230,59 @@ __device__ __forceinline__ void epi_hidden3_sin_pipelined(uint8_t* __restrict__ 
     for (int i = 0; i < 16; ++i) y[i] = mufu_sin(x[i]);                // issue the unit's sines ...
     if (more) {
       tmem_ld_wait(); reg_fence16(v);                                      // ... and prepare the next unit while they execute
-#if NF_BIAS_IN_MMA
 #pragma unroll
       for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[i]);
-#else
-      const float4* b4 = reinterpret_cast<const float4*>(bias_s + col + NCQ * 16);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 b = b4[i];
-        x[4 * i] = __uint_as_float(v[4 * i]) + b.x; x[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b.y;
-        x[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b.z; x[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b.w;
-      }
-#endif
     }
     uint32_t o[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = pack_h2(y[2 * i], y[2 * i + 1]);
     uint8_t* dst = H + (col >> 3) * KG_BYTES + row * 16;
     st_v4(dst, o[0], o[1], o[2], o[3]); st_v4(dst + KG_BYTES, o[4], o[5], o[6], o[7]);
+  }
+}
+
+// Split hand-over (NCQ == 4): the warp first reads ALL 64 of its accumulator columns into registers -- from then on the
+// accumulator may be overwritten -- converts and stores its two units of columns 0-127, hands that half to the issuer
+// (a_ready[slot]: the next Linear's first eight hidden K-steps start), and then converts the two units of columns 128-255 while
+// those MMAs run (the caller arrives on a_ready[2 + slot] at the end of the phase).  With every load issued up front there is
+// no TMEM wait between units, so the sines of different units overlap without hand pipelining.
+#ifndef NF_SPLIT_HANDOFF
+#define NF_SPLIT_HANDOFF 1
+#endif
+template <int ACT, bool TRAIN>
+__device__ __forceinline__ void epi_hidden_split(uint8_t* __restrict__ H, uint32_t t_acc, int cq, int row, int lane, uint32_t a_lo_leader,
+                                                 uint8_t* __restrict__ gA = nullptr, uint8_t* __restrict__ gC = nullptr) {
+  uint32_t v[4][16];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) tmem_ld16(t_acc + (cq + 4 * u) * 16, v[u]);
+  tmem_ld_wait();
+#pragma unroll
+  for (int u = 0; u < 4; ++u) reg_fence16(v[u]);
+  tc_fence_before();
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int col = (cq + 4 * u) * 16;
+    uint32_t o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = act_pack_t<ACT>(__uint_as_float(v[u][2 * i]), __uint_as_float(v[u][2 * i + 1]));
+    uint8_t* dst = H + (col >> 3) * KG_BYTES + row * 16;
+    st_v4(dst, o[0], o[1], o[2], o[3]); st_v4(dst + KG_BYTES, o[4], o[5], o[6], o[7]);
+    if (TRAIN && gA) {
+      uint8_t* g = gA + (col >> 3) * KG_BYTES + row * 16;
+      st_global_v4(g, o[0], o[1], o[2], o[3]); st_global_v4(g + KG_BYTES, o[4], o[5], o[6], o[7]);
+      if (ACT == NF_ACT_SIN && gC) {
+        uint32_t c[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) c[i] = pack_h2(__cosf(__uint_as_float(v[u][2 * i])), __cosf(__uint_as_float(v[u][2 * i + 1])));
+        uint8_t* gc = gC + (col >> 3) * KG_BYTES + row * 16;
+        st_global_v4(gc, c[0], c[1], c[2], c[3]); st_global_v4(gc + KG_BYTES, c[4], c[5], c[6], c[7]);
+      }
+    }
+    if (u == 1) {
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster_relaxed(a_lo_leader);
+    }
   }
 }
 
@@ -449,7 +447,7 @@ __device__ __forceinline__ void composite_tile3(Tc3Smem& s, int slot, const NfPl
 }
 
 // =====================================================================================================
-// NST ring stages of SPCT K-steps each (NST * SPCT * 4 KB = 48 KB); NCQ epilogue warps per TMEM lane quarter.  Warps
+// NST ring stages of SPCT K-steps (+ a bias piece) each (3 x 18 KB); NCQ epilogue warps per TMEM lane quarter.  Warps
 // 0..4*NCQ-1 encode/epilogue, then NST weight producers (one stage each; the first also owns the TMEM allocation), then the
 // MMA issuer (highest warp id).
 // WIDE: the single-tile wide-x0 mode (Mip latent, Positional head) is compiled in.  The common path uses the WIDE = false
@@ -467,10 +465,10 @@ __device__ __forceinline__ void composite_tile3(Tc3Smem& s, int slot, const NfPl
 template <int NST, int SPCT, int NCQ, int WIDE, bool DYN, bool TRAIN = false, bool AUX = false, bool BW = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (4 * NCQ + NST + 1 + (BW ? 4 : 0)), 1)
 k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Prog prog, const Tc3Args a, const __grid_constant__ Tc3Train tr) {
-  static_assert(NST * SPCT * 4096 <= RING_BYTES && NST <= MAX_STAGES3, "ring geometry");
   static_assert(!BW || (WIDE == 0 && NST == 3 && NCQ == 4), "boundary warps: plain two-tile mode, warp groups {0-15, 16-19, 20-23}");
-  constexpr int STAGE_BYTES = SPCT * 4096;
-  constexpr int RING_OFF = RING_BYTES - NST * SPCT * 4096;     // a smaller ring sits at the END of the region (shared wide x0 in front)
+  constexpr int STAGE_BYTES = SPCT * 4096 + BIAS_PIECE;
+  static_assert(NST * STAGE_BYTES <= RING_BYTES && NST <= MAX_STAGES3, "ring geometry");
+  constexpr int RING_OFF = RING_BYTES - NST * STAGE_BYTES;     // a smaller ring sits at the END of the region (shared wide x0 in front)
   constexpr int EPIW = 4 * NCQ, EPI_THREADS = 32 * EPIW;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Tc3Smem& s = *reinterpret_cast<Tc3Smem*>(smem_raw);
@@ -489,7 +487,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
   // ---- one-time setup ----
   if (threadIdx.x == 0) {
     for (int i = 0; i < NST; ++i) { mbar_init(smem_u32(&s.w_land[i]), 1); mbar_init(smem_u32(&s.w_empty[i]), 1); mbar_init(smem_u32(&s.w_ready[i]), 2); }
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s.acc_full[i]), 1); mbar_init(smem_u32(&s.a_ready[i]), 2 * EPIW); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s.acc_full[i]), 1); mbar_init(smem_u32(&s.a_ready[i]), 2 * EPIW); mbar_init(smem_u32(&s.a_ready[2 + i]), 2 * EPIW); }
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s.bnd_full[i]), 1); mbar_init(smem_u32(&s.x0_free[i]), EPIW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -497,11 +495,8 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem_base)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
-#if NF_BIAS_IN_MMA
-  for (int i = threadIdx.x; i < 2 * ROWS; i += blockDim.x)
-    *reinterpret_cast<uint4*>(s.ones + i * 16) = i < ROWS ? make_uint4(0x3C003C00u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+  if (threadIdx.x < 16) *reinterpret_cast<uint4*>(s.ones + threadIdx.x * 16) = threadIdx.x < 8 ? make_uint4(0x3C003C00u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async();
-#endif
   if (threadIdx.x < prog.n_lin) {
     // the epilogue's per-Linear facts, copied once from the kernel parameters (dependent indexed constant loads cost
     // ~250 cycles each when they miss the constant cache: ~600 cycles per phase before this table existed)
@@ -536,11 +531,12 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
           const int kl = k - (slot ? lag : 0);
           if (kl < 0 || kl >= nsteps || (slot && single)) continue;
           const int li = slot ? li1 : li0;
-          const uint32_t steps = prog.lin[li].k0_steps + prog.lin[li].h_steps + NF_BIAS_IN_MMA, sb = prog.lin[li].step_bytes;
+          const uint32_t steps = prog.lin[li].k0_steps + prog.lin[li].h_steps, sb = prog.lin[li].step_bytes;
           const uint8_t* src = a.packed + prog.lin[li].w_off + (size_t)crank * prog.lin[li].half_bytes;
           for (uint32_t st0 = 0; st0 < steps; st0 += SPCT) {
             if (rs == p) {
-              const uint32_t bytes = (steps - st0 < (uint32_t)SPCT ? steps - st0 : (uint32_t)SPCT) * sb;
+              // the Linear's last chunk also carries the bias K-group (it follows the data steps in the image)
+              const uint32_t bytes = st0 + SPCT < steps ? (uint32_t)SPCT * sb : (steps - st0) * sb + (sb >> 1);
               const uint32_t par = use & 1u; ++use;
               ST_ADD(2);
               if (a.debug & 1024) mbar_wait_backoff(bar_empty, par ^ 1u); else mbar_wait(bar_empty, par ^ 1u);
@@ -570,9 +566,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
       const uint32_t bar_wready = smem_u32(&s.w_ready[0]), bar_wempty = smem_u32(&s.w_empty[0]);
       const uint32_t bar_a = smem_u32(&s.a_ready[0]), bar_acc = smem_u32(&s.acc_full[0]), bar_bnd = smem_u32(&s.bnd_full[0]);
       const uint32_t a_lbo = (uint32_t)(KG_BYTES >> 4) << 16, kstep4 = (uint32_t)(2 * KG_BYTES) >> 4;
-#if NF_BIAS_IN_MMA
-      const uint32_t ones4 = (base4 + (uint32_t)(offsetof(Tc3Smem, ones) >> 4)) | a_lbo;
-#endif
+      const uint64_t ones_desc = ((uint64_t)0x4000u << 32) | (base4 + (uint32_t)(offsetof(Tc3Smem, ones) >> 4)) | (8u << 16);   // SBO = 0, LBO = 128 B
       int li0 = 0, li1 = 0;
       bool w_ok = false;                               // ring stage `stage` is known to be full
       const bool no_mma = (a.debug & 2) != 0;
@@ -585,17 +579,26 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
           const int li = slot ? li1 : li0;
           const uint4 r0 = *reinterpret_cast<const uint4*>(&prog.lin[li].k0_steps);
           const uint32_t bhi = prog.lin[li].bhi;
-          const uint32_t k0s = r0.x, kend = r0.x + r0.y, total = kend + NF_BIAS_IN_MMA, idesc = r0.z, bstep4 = r0.w;   // steps [kend, total): the bias step
+          const uint32_t k0s = r0.x, kend = r0.x + r0.y, idesc = r0.z, bstep4 = r0.w;
           ST_ADD(2);
           mbar_wait(bar_a + slot * 8u, (a_par >> slot) & 1u); a_par ^= 1u << slot;
           ST_ADD(0);
+          // the second half of the hidden operand (columns 128-255) is handed over separately: the first eight hidden K-steps
+          // run while the epilogue warps still convert the second half (they read the whole accumulator into registers first)
+          bool hi_ok = false;
+          const uint32_t hi_from = r0.y ? k0s + 8u : 0u;
           tc_fence_after();
           const uint32_t d_tmem = slot * 256u;
           const uint32_t x4 = (single ? base4 + (uint32_t)((offsetof(Tc3Smem, H) + sizeof(s.H[0])) >> 4)
                                       : base4 + (uint32_t)(offsetof(Tc3Smem, X0) >> 4) + (shared_x0 ? 0u : slot * (uint32_t)(sizeof(s.X0[0]) >> 4))) | a_lbo;
           const uint32_t h4 = (base4 + (uint32_t)(offsetof(Tc3Smem, H) >> 4) + slot * (uint32_t)(sizeof(s.H[0]) >> 4)) | a_lbo;
 #pragma unroll 1
-          for (uint32_t gs0 = 0; gs0 < total; gs0 += SPCT) {
+          for (uint32_t gs0 = 0; gs0 < kend; gs0 += SPCT) {
+            if (!hi_ok && gs0 + SPCT > hi_from) {
+              ST_ADD(2);
+              mbar_wait(bar_a + (2u + slot) * 8u, (a_par >> (2u + slot)) & 1u); a_par ^= 1u << (2u + slot); hi_ok = true;
+              ST_ADD(0);
+            }
             if (!w_ok) { ST_ADD(2); mbar_wait(bar_wready + stage * 8u, phase); ST_ADD(1); ST_INC(3); }
             const uint32_t nstage = stage + 1 == NST ? 0u : stage + 1u, nphase = stage + 1 == NST ? phase ^ 1u : phase;
             w_ok = mbar_test_wait(bar_wready + nstage * 8u, nphase);       // consumed on the next iteration
@@ -611,16 +614,17 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
               for (uint32_t i = 1; i < SPCT; ++i)
                 umma2_f16(d_tmem, umma_desc_lo(a4 + i * kstep4), umma_desc_lo(b4 + i * bstep4), idesc, 1u);
             } else {
-              const uint32_t nst = total - gs0 < (uint32_t)SPCT ? total - gs0 : (uint32_t)SPCT;
+              const uint32_t nst = kend - gs0 < (uint32_t)SPCT ? kend - gs0 : (uint32_t)SPCT;
               for (uint32_t i = 0; i < nst; ++i) {
                 const uint32_t gs = gs0 + i;
-#if NF_BIAS_IN_MMA
-                const uint32_t a4 = gs < k0s ? x4 + gs * kstep4 : gs < kend ? h4 + (gs - k0s) * kstep4 : ones4;
-#else
                 const uint32_t a4 = gs < k0s ? x4 + gs * kstep4 : h4 + (gs - k0s) * kstep4;
-#endif
                 umma2_f16(d_tmem, umma_desc_lo(a4), umma_desc_lo(b4 + i * bstep4), idesc, gs > 0 ? 1u : 0u);
               }
+            }
+            if (gs0 + SPCT >= kend && !no_mma) {
+              // the bias K-step: its one non-zero K-group follows the chunk's data steps; LBO = 0 in the B descriptor
+              const uint32_t nst = kend - gs0;
+              umma2_f16(d_tmem, ones_desc, umma_desc_lo(w4 + stage * (uint32_t)(STAGE_BYTES >> 4) + nst * bstep4), idesc, 1u);
             }
             umma2_commit_mc(bar_wempty + stage * 8u);
             stage = nstage; phase = nphase;
@@ -653,21 +657,11 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
         if (BW && j == 0) { if (slot) j1 = 1; else j0 = 1; continue; }      // the tile boundary belongs to the boundary warps
         uint8_t* H = s.H[slot]; uint8_t* X0 = single ? s.H[1] : shared_x0 ? s.X0[0] : s.X0[slot];
         const uint32_t t_acc = t_lane + (uint32_t)slot * 256u;
-        const uint32_t a_ready_leader = leader_addr(smem_u32(&s.a_ready[slot]));
+        const uint32_t a_ready_leader = leader_addr(smem_u32(&s.a_ready[slot])), a_hi_leader = leader_addr(smem_u32(&s.a_ready[2 + slot]));
         const bool has_next = kl < nsteps;              // Linear j of this slot runs after this phase
         const int comp_cq = (NCQ / 2) * slot, tail_cq = comp_cq + 1;
         // bias of Linear j (consumed by this slot's NEXT phase): in flight across the acc_full wait
-#if NF_BIAS_IN_MMA
         const float* bias = nullptr; (void)bias;
-#else
-        float bnext = 0.f; bool bload = false;
-        if (has_next) {
-          const int4 Ln = s.lin[j][0];
-          bload = e_tid < Ln.x;
-          if (bload) bnext = __ldg(reinterpret_cast<const float*>(a.packed + (uint32_t)Ln.y) + e_tid);
-        }
-        const float* bias = s.bias[slot][(kl & 1) ^ 1];   // bias of the Linear whose result this phase consumes
-#endif
         if (kl > 0) {
           ST_ADD(5);
           wait_acc(smem_u32(&s.acc_full[slot]), (acc_par >> slot) & 1u, a.debug);
@@ -689,10 +683,10 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
             tc_fence_before();
             float cr, cg, cb;
             if (plan.kind == NF_KIND_TINY) {
-              s.sig[slot][0][row] = ADDB(__uint_as_float(v[0]), 0);
-              cr = ADDB(__uint_as_float(v[1]), 1); cg = ADDB(__uint_as_float(v[2]), 2); cb = ADDB(__uint_as_float(v[3]), 3);
+              s.sig[slot][0][row] = __uint_as_float(v[0]);
+              cr = __uint_as_float(v[1]); cg = __uint_as_float(v[2]); cb = __uint_as_float(v[3]);
             } else {
-              cr = ADDB(__uint_as_float(v[0]), 0); cg = ADDB(__uint_as_float(v[1]), 1); cb = ADDB(__uint_as_float(v[2]), 2);
+              cr = __uint_as_float(v[0]); cg = __uint_as_float(v[1]); cb = __uint_as_float(v[2]);
             }
             if (TRAIN) {
               long long ray; int t;
@@ -750,13 +744,10 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
                 for (int g = 1; g < (plan.mlp[first_m].k0_pad >> 3); ++g) st_v4(X0 + g * KG_BYTES + row * 16, 0, 0, 0, 0);
               }
             }
-#if !NF_BIAS_IN_MMA
-            if (bload) { s.bias[slot][kl & 1][e_tid] = bnext; __threadfence_block(); }   // for this slot's next phase
-#endif
             tc_fence_before();
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster_relaxed(a_ready_leader);
+            if (lane == 0) { mbar_arrive_cluster_relaxed(a_ready_leader); mbar_arrive_cluster_relaxed(a_hi_leader); }
           }
           ST_ADD(1);
         } else {
@@ -775,6 +766,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
           const int4 Lc = s.lin[j - 1][0];
           const int act = Lc.z;
           const bool is_out = (Lc.w & 1) != 0;
+          bool lo_done = false;                 // this phase has already handed over the first half of the operand
           if (!is_out) {
             if (TRAIN) {
               // this phase writes the hidden input of Linear j (and, after an `init`, activates x0): stash all of it
@@ -792,13 +784,17 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
                 uint8_t* g1 = (st_ok && Ti.skip1 >= 0) ? a.ws + ((size_t)tr.lin[Ti.skip1].a_off256 + (size_t)g * tr.lin[Ti.skip1].a_tile256) * 256 : nullptr;
                 x0_activate3(X0, s.lin[j - 1][1].x, act, e_tid, EPI_THREADS, gRaw, g0, g1);
               }
-              if (act == NF_ACT_SIN) epi_hidden3<NF_ACT_SIN, NCQ, true>(H, t_acc, bias, cq, row, gA, gC);
+              if (NF_SPLIT_HANDOFF && NCQ == 4 && act == NF_ACT_SIN) { epi_hidden_split<NF_ACT_SIN, true>(H, t_acc, cq, row, lane, a_ready_leader, gA, gC); lo_done = true; }
+              else if (NF_SPLIT_HANDOFF && NCQ == 4 && act == NF_ACT_LEAKY) { epi_hidden_split<NF_ACT_LEAKY, true>(H, t_acc, cq, row, lane, a_ready_leader, gA, nullptr); lo_done = true; }
+              else if (act == NF_ACT_SIN) epi_hidden3<NF_ACT_SIN, NCQ, true>(H, t_acc, bias, cq, row, gA, gC);
               else if (act == NF_ACT_LEAKY) epi_hidden3<NF_ACT_LEAKY, NCQ, true>(H, t_acc, bias, cq, row, gA, nullptr);
               else if (act == NF_ACT_RELU) epi_hidden3<NF_ACT_RELU, NCQ, true>(H, t_acc, bias, cq, row, gA, nullptr);
               else epi_hidden3<NF_ACT_NONE, NCQ, true>(H, t_acc, bias, cq, row, gA, nullptr);
             } else {
             if (Lc.w & 2) x0_activate3(X0, s.lin[j - 1][1].x, act, e_tid, EPI_THREADS);       // init consumed raw x0; the skip Linear wants act(x0)
-            if (act == NF_ACT_SIN) { if (a.debug & 2048) epi_hidden3<NF_ACT_SIN, NCQ>(H, t_acc, bias, cq, row); else epi_hidden3_sin_pipelined<NCQ>(H, t_acc, bias, cq, row); }
+            if (NF_SPLIT_HANDOFF && NCQ == 4 && act == NF_ACT_SIN) { epi_hidden_split<NF_ACT_SIN, false>(H, t_acc, cq, row, lane, a_ready_leader); lo_done = true; }
+            else if (NF_SPLIT_HANDOFF && NCQ == 4 && act == NF_ACT_LEAKY) { epi_hidden_split<NF_ACT_LEAKY, false>(H, t_acc, cq, row, lane, a_ready_leader); lo_done = true; }
+            else if (act == NF_ACT_SIN) { if (a.debug & 2048) epi_hidden3<NF_ACT_SIN, NCQ>(H, t_acc, bias, cq, row); else epi_hidden3_sin_pipelined<NCQ>(H, t_acc, bias, cq, row); }
             else if (act == NF_ACT_LEAKY) epi_hidden3<NF_ACT_LEAKY, NCQ>(H, t_acc, bias, cq, row);
             else if (act == NF_ACT_RELU) epi_hidden3<NF_ACT_RELU, NCQ>(H, t_acc, bias, cq, row);
             else epi_hidden3<NF_ACT_NONE, NCQ>(H, t_acc, bias, cq, row);
@@ -822,9 +818,9 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
               const long long sidx = ray * a.T + t;
               if (side && a.pts_out) { float* o = a.pts_out + sidx * 3; o[0] = px; o[1] = py; o[2] = pz; }
               if (nsp == 0) {
-                const float dp = ADDB(__uint_as_float(v[0]), 0);
-                const float r0 = nf_sigmoid(ADDB(__uint_as_float(v[1]), 1) / 2.f), r1 = nf_sigmoid(ADDB(__uint_as_float(v[2]), 2) / 2.f),
-                            r2 = nf_sigmoid(ADDB(__uint_as_float(v[3]), 3) / 2.f);
+                const float dp = __uint_as_float(v[0]);
+                const float r0 = nf_sigmoid(__uint_as_float(v[1]) / 2.f), r1 = nf_sigmoid(__uint_as_float(v[2]) / 2.f),
+                            r2 = nf_sigmoid(__uint_as_float(v[3]) / 2.f);
                 px += dp * r0; py += dp * r1; pz += dp * r2;
                 if (side) {
                   // the reference's split names the 1-channel output dp and the 3-channel one rigidity (nerf.py:1231,1261-1266)
@@ -833,14 +829,14 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
                   if (a.rigid_dp_out) { float* o = a.rigid_dp_out + sidx * 3; o[0] = dp * r0; o[1] = dp * r1; o[2] = dp * r2; }
                 }
               } else {
-                const float rig = nf_sigmoid(ADDB(__uint_as_float(v[0]), 0) / 2.f);
+                const float rig = nf_sigmoid(__uint_as_float(v[0]) / 2.f);
                 const float time = __ldg(a.ray_time + ray);
                 float d[3];
 #pragma unroll
                 for (int x = 0; x < 3; ++x) {
                   float ps[8];
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) ps[i] = i < nsp ? ADDB(__uint_as_float(v[1 + 3 * i + x]), 1 + 3 * i + x) : 0.f;
+                  for (int i = 0; i < 8; ++i) ps[i] = i < nsp ? __uint_as_float(v[1 + 3 * i + x]) : 0.f;
                   d[x] = nf_bezier(ps, nsp, time);
                 }
                 if (side) {
@@ -851,7 +847,9 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
                 px += d[0] * rig; py += d[1] * rig; pz += d[2] * rig;
               }
             }
-            if (cq == tail_cq) { s.P[slot][0][row] = px; s.P[slot][1][row] = py; s.P[slot][2][row] = pz; }
+            // the deformed point, for the View head's x0: parked as three floats in the last K-group of X0 (columns 72-79), which
+            // neither the density MLP's x0 (k0_pad <= 64, checked on the host) nor anything else touches until the density-out epilogue
+            if (cq == tail_cq) *reinterpret_cast<float4*>(X0 + (X0K / 8 - 1) * KG_BYTES + row * 16) = make_float4(px, py, pz, 0.f);
             hash_x0(X0, reinterpret_cast<const float4*>(a.packed + plan.hash_off), plan, px, py, pz, row, cq, NCQ);
             if (cq == tail_cq) hash_x0_tail(X0, plan, plan.mlp[0].k0_pad, px, py, pz, row);
           } else {
@@ -888,11 +886,11 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
                 uint32_t o[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                  o[i] = pack_h2(ADDB(__uint_as_float(v[2 * i]), un * 16 + 2 * i), ADDB(__uint_as_float(v[2 * i + 1]), un * 16 + 2 * i + 1));
+                  o[i] = pack_h2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
                 uint8_t* d0 = X0 + (un * 2) * KG_BYTES + row * 16;
                 st_v4(d0, o[0], o[1], o[2], o[3]); st_v4(d0 + KG_BYTES, o[4], o[5], o[6], o[7]);
               } else {
-                s.sig[slot][BW ? (P & 1) : 0][row] = ADDB(__uint_as_float(v[0]), plan.intermediate);
+                s.sig[slot][BW ? (P & 1) : 0][row] = __uint_as_float(v[0]);
                 if (!pos_head && !pre_tail) {
                   long long u; int sub; unit_of(P, slot, map.tpr, nslot, u, sub);
                   long long ray; int t;
@@ -901,7 +899,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
                     const float* rr = a.rays + ray * 6;
                     const float tt = __ldg(a.ts + ray * a.ts_stride + t);
                     const float dx = __ldg(rr + 3), dy = __ldg(rr + 4), dz = __ldg(rr + 5);
-                    if (DYN && plan.kind == NF_KIND_DYN) { px = s.P[slot][0][row]; py = s.P[slot][1][row]; pz = s.P[slot][2][row]; }
+                    if (DYN && plan.kind == NF_KIND_DYN) { const float4 pp = *reinterpret_cast<const float4*>(X0 + (X0K / 8 - 1) * KG_BYTES + row * 16); px = pp.x; py = pp.y; pz = pp.z; }
                     else { px = nf_pt(__ldg(rr + 0), tt, dx); py = nf_pt(__ldg(rr + 1), tt, dy); pz = nf_pt(__ldg(rr + 2), tt, dz); }
                     if (AUX && a.pts) { const float* pp = a.pts + (ray * a.T + t) * 3; px = __ldg(pp); py = __ldg(pp + 1); pz = __ldg(pp + 2); }
                     nf_elaz(dx, dy, dz, el, az);
@@ -916,13 +914,10 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
               }
             }
           }
-#if !NF_BIAS_IN_MMA
-          if (bload) { s.bias[slot][kl & 1][e_tid] = bnext; __threadfence_block(); }     // for this slot's next phase
-#endif
           tc_fence_before();
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster_relaxed(a_ready_leader);
+          if (lane == 0) { if (!lo_done) mbar_arrive_cluster_relaxed(a_ready_leader); mbar_arrive_cluster_relaxed(a_hi_leader); }
           if (is_out) ST_ADD(4); else if (act == NF_ACT_SIN) ST_ADD(3); else ST_ADD(2);
         }
         int jn = j + 1, Pn = P;
@@ -1000,7 +995,9 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
         }
         if (has_next) {
           __syncwarp();
-          if (lane < 4) mbar_arrive_cluster_relaxed(leader_addr(smem_u32(&s.a_ready[slot])));      // 4 warps x 4 lanes = the 16 arrivals of a phase
+          if (lane < 4) {                                                                           // 4 warps x 4 lanes = the 16 arrivals of a phase
+            mbar_arrive_cluster_relaxed(leader_addr(smem_u32(&s.a_ready[slot]))); mbar_arrive_cluster_relaxed(leader_addr(smem_u32(&s.a_ready[2 + slot])));
+          }
         }
         ST_ADD(3);
         if (comp) {
@@ -1049,6 +1046,9 @@ bool build_prog3(const NfPlan& plan, Tc3Prog* P) {
     }
   }
   P->n_lin = nl; P->lag = nl / 2;
+#ifdef NF_LAG
+  P->lag = NF_LAG < nl ? NF_LAG : nl / 2;       // experiment: how far slot 1 runs behind slot 0
+#endif
   P->x0_last = 0;
   for (int i = 0; i < nl; ++i) if (P->lin[i].k0_steps) P->x0_last = i;
   int kmax = 0;
@@ -1084,6 +1084,7 @@ const char* nf_tc3_unsupported(const NfPlan& p) {
   if (wide && p.enc != NF_ENC_HASH) return "Mip / Positional on the tensor pipeline need the hash-encoded density MLP";
   const bool fourier = p.enc == NF_ENC_FOURIER && p.kind == NF_KIND_PLAIN;        // the Fourier-encoded SDF MLP of VolSDF: x0 259 -> 272
   if (p.kind == NF_KIND_DYN && p.enc != NF_ENC_HASH) return "NF_KIND_DYN: the canonical NeRF must be hash-encoded";
+  if (p.kind == NF_KIND_DYN && p.mlp[0].k0_pad > 64) return "NF_KIND_DYN: density x0 wider than 64 columns (the deformed point is parked in X0 columns 72-79)";
   if (p.kind == NF_KIND_DYN && p.mlp[2].lin[p.mlp[2].n_lin - 1].n_pad > 32) return "deformation MLP with more than 32 outputs";
   int nlin = 0;
   for (int m = 0; m < p.n_mlps; ++m) {
@@ -1140,13 +1141,9 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
   int ring = 3, epiw = 16;
 #ifdef NF_EXPERIMENTS
   if (const char* dbg = getenv("NF_TC_DEBUG")) a.debug = atoi(dbg);
-  // NF_TC_RING selects the weight-ring geometry (same 48 KB): "3" = 3 stages x 16 KB (default; measured faster: the single
-  // issuing thread pays one probe + one commit per stage), "6" = 6 stages x 8 KB.  NF_TC_EPIW selects the number of epilogue
-  // warps: 16 (default) or 24 (6 per TMEM lane quarter; 72 registers per thread).
-  if (const char* r = getenv("NF_TC_RING")) ring = atoi(r);
+  // NF_TC_EPIW selects the number of epilogue warps: 16 (default) or 24 (6 per TMEM lane quarter; 72 registers per thread).
   if (const char* r = getenv("NF_TC_EPIW")) epiw = atoi(r);
-  if (ring != 6) ring = 3;
-  if (epiw != 24 || ring != 3) epiw = 16;
+  if (epiw != 24) epiw = 16;
 #endif
   Tc3Prog prog;
   if (!build_prog3(plan, &prog)) return cudaErrorNotSupported;
@@ -1182,7 +1179,7 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
     }
   }
   // boundary-warp mode (four more warps own the tile boundary): the plain two-tile instantiations, warp-aligned rays
-  const bool bw = NF_BIAS_IN_MMA && NF_BW && !wide && (T & 31) == 0 && ring == 3 && epiw == 16;
+  const bool bw = NF_BW && !wide && (T & 31) == 0 && ring == 3 && epiw == 16;
   const int threads = 32 * (epiw + ring + 1 + (bw ? 4 : 0));
   const NfStreamMap map(T, ROWS);
   const long long units = map.units(n_rays);
@@ -1219,7 +1216,6 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
   else if (dynk) go(k_render_tc3<3, 4, 4, 0, true>);
 #ifdef NF_EXPERIMENTS
   else if (epiw == 24) go(k_render_tc3<3, 4, 6, 0, false>);
-  else if (ring == 6) go(k_render_tc3<6, 2, 4, 0, false>);
 #endif
   else go(k_render_tc3<3, 4, 4, 0, false>);
   if (e != cudaSuccess) return e;

@@ -1,3 +1,2 @@
-timeout 180 python __graft_entry__.py --smoke 2>&1 | tail -5; echo "smoke rc=$?"
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
-timeout 300 python bench.py --steps 10 --warmup 3 2>&1 | tail -3
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
+python profiles/ab_time.py libnerf_b200.so libnerf_b200_nosplit.so libnerf_b200.so libnerf_b200_nosplit.so
