@@ -137,6 +137,15 @@ __device__ __forceinline__ void wait_acc(uint32_t bar, uint32_t parity, int debu
 #ifndef NF_BW
 #define NF_BW 1
 #endif
+// one MMA-issuing thread per slot (else one thread issues both slots' Linears in turn)
+#ifndef NF_REG_E
+#define NF_REG_E 88
+#define NF_REG_W4 40
+#define NF_REG_W6 40
+#endif
+#ifndef NF_TWO_ISSUERS
+#define NF_TWO_ISSUERS 0
+#endif
 #ifndef NF_BW_PRETAIL
 #define NF_BW_PRETAIL 1
 #endif
@@ -463,7 +472,7 @@ __device__ __forceinline__ void composite_tile3(Tc3Smem& s, int slot, const NfPl
 // (bnd_full), hand the slot back to the issuer and only then composite -- so the 16 epilogue warps never leave the MLP phases
 // and the ~7 K-cycle boundary is off both the slot's critical path and the epilogue warps' time.  Needs T % 32 == 0, WIDE == 0.
 template <int NST, int SPCT, int NCQ, int WIDE, bool DYN, bool TRAIN = false, bool AUX = false, bool BW = false>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (4 * NCQ + NST + 1 + (BW ? 4 : 0)), 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (4 * NCQ + NST + 1 + (BW ? 4 + 4 * NF_TWO_ISSUERS : 0)), 1)
 k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Prog prog, const Tc3Args a, const __grid_constant__ Tc3Train tr) {
   static_assert(!BW || (WIDE == 0 && NST == 3 && NCQ == 4), "boundary warps: plain two-tile mode, warp groups {0-15, 16-19, 20-23}");
   constexpr int STAGE_BYTES = SPCT * 4096 + BIAS_PIECE;
@@ -483,6 +492,8 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
   const int passes = trips * map.tpr;
   const int n = prog.n_lin, lag = prog.lag;
   const int nsteps = passes * n;                   // MMA steps (Linears) per slot
+  constexpr bool TWO = BW && NF_TWO_ISSUERS;        // one MMA-issuing thread per slot (a seventh warp group, its first warp issues slot 1)
+  constexpr int W_ISSB = 4 * NCQ + NST + 1 + 4;
 
   // ---- one-time setup ----
   if (threadIdx.x == 0) {
@@ -513,9 +524,95 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
   tc_fence_after();
   if (s.tmem_base != 0) __trap();
 
+  // ---- the MMA issuer: one thread per slot (mask bit s = this thread issues slot s's Linears) ----
+  // A single thread cannot keep the tensor pipe fed: a tcgen05.mma costs the issuing thread >= 76 cycles and a commit + barrier
+  // probe ~190 (profiles/r01_mma_issue_microbench.csv), i.e. >= 500 cycles per 4-MMA ring stage against 512 cycles of execution
+  // before any bookkeeping; measured ~140 cycles per MMA.  With one issuing thread per slot the per-Linear work (program record,
+  // a_ready waits, the accumulator commit) of one slot overlaps the other slot's issue, and at the seams both threads issue.
+  // The weight ring is ONE stream in the global order (step by step: slot 0's Linear, then slot 1's); a thread lets the other
+  // slot's chunks pass by counting them.  The probe of the NEXT ring stage is issued before the current chunk's MMAs, so its
+  // ~150-cycle latency is hidden.
+  auto run_issuer = [&](const uint32_t mask) {
+    uint32_t stage = 0, phase = 0, a_par = 0;
+    const uint32_t base4 = smem_u32(smem_raw) >> 4;
+    const uint32_t w4 = base4 + (uint32_t)((offsetof(Tc3Smem, W) + RING_OFF) >> 4);
+    const uint32_t bar_wready = smem_u32(&s.w_ready[0]), bar_wempty = smem_u32(&s.w_empty[0]);
+    const uint32_t bar_a = smem_u32(&s.a_ready[0]), bar_acc = smem_u32(&s.acc_full[0]), bar_bnd = smem_u32(&s.bnd_full[0]);
+    const uint32_t a_lbo = (uint32_t)(KG_BYTES >> 4) << 16, kstep4 = (uint32_t)(2 * KG_BYTES) >> 4;
+    const uint64_t ones_desc = ((uint64_t)0x4000u << 32) | (base4 + (uint32_t)(offsetof(Tc3Smem, ones) >> 4)) | (8u << 16);   // SBO = 0, LBO = 128 B
+    int li0 = 0, li1 = 0;
+    bool w_ok = false;                               // ring stage `stage` is known to be full
+    ST_DECL;
+    for (int k = 0; k < nsteps + lag; ++k) {
+#pragma unroll 1
+      for (uint32_t slot = 0; slot < 2; ++slot) {
+        const int kl = k - (slot ? lag : 0);
+        if (kl < 0 || kl >= nsteps || (slot && single)) continue;
+        const int li = slot ? li1 : li0;
+        const int ln = li + 1 == n ? 0 : li + 1;
+        if (slot) li1 = ln; else li0 = ln;
+        const uint4 r0 = *reinterpret_cast<const uint4*>(&prog.lin[li].k0_steps);
+        const uint32_t k0s = r0.x, hs = r0.y, idesc = r0.z, bstep4 = r0.w;
+        if (!((mask >> slot) & 1u)) {
+          // the other issuer's Linear: its chunks pass through the ring
+          stage += (k0s + SPCT - 1) / SPCT + (hs + SPCT - 1) / SPCT;
+          while (stage >= (uint32_t)NST) { stage -= NST; phase ^= 1u; }
+          w_ok = false;
+          continue;
+        }
+        const uint32_t bhi = prog.lin[li].bhi;
+        ST_ADD(2);
+        mbar_wait(bar_a + slot * 8u, (a_par >> slot) & 1u); a_par ^= 1u << slot;
+        ST_ADD(0);
+        tc_fence_after();
+        const uint32_t d_tmem = slot * 256u;
+        const uint32_t x4 = (single ? base4 + (uint32_t)((offsetof(Tc3Smem, H) + sizeof(s.H[0])) >> 4)
+                                    : base4 + (uint32_t)(offsetof(Tc3Smem, X0) >> 4) + (shared_x0 ? 0u : slot * (uint32_t)(sizeof(s.X0[0]) >> 4))) | a_lbo;
+        const uint32_t h4 = (base4 + (uint32_t)(offsetof(Tc3Smem, H) >> 4) + slot * (uint32_t)(sizeof(s.H[0]) >> 4)) | a_lbo;
+        // one ring stage: nst K-steps read from ONE activation buffer; `last`: the Linear's last chunk, followed by the bias
+        // K-step (its one non-zero K-group follows the chunk's data steps; LBO = 0 in the B descriptor)
+        auto chunk = [&](const uint32_t a4, const uint32_t nst, const uint32_t acc0, const bool last) {
+          if (!w_ok) { ST_ADD(2); mbar_wait(bar_wready + stage * 8u, phase); ST_ADD(1); ST_INC(3); }
+          const uint32_t nstage = stage + 1 == NST ? 0u : stage + 1u, nphase = stage + 1 == NST ? phase ^ 1u : phase;
+          w_ok = (last && mask != 3u) ? false : mbar_test_wait(bar_wready + nstage * 8u, nphase);       // consumed by the next chunk
+          tc_fence_after();
+          const uint32_t wb = w4 + stage * (uint32_t)(STAGE_BYTES >> 4), b4 = wb | bhi;
+          if (nst == (uint32_t)SPCT) {
+            umma2_f16(d_tmem, umma_desc_lo(a4), umma_desc_lo(b4), idesc, acc0);
+#pragma unroll
+            for (uint32_t i = 1; i < SPCT; ++i) umma2_f16(d_tmem, umma_desc_lo(a4 + i * kstep4), umma_desc_lo(b4 + i * bstep4), idesc, 1u);
+          } else {
+            for (uint32_t i = 0; i < nst; ++i) umma2_f16(d_tmem, umma_desc_lo(a4 + i * kstep4), umma_desc_lo(b4 + i * bstep4), idesc, i ? 1u : acc0);
+          }
+          if (last) umma2_f16(d_tmem, ones_desc, umma_desc_lo(wb + nst * bstep4), idesc, 1u);
+          umma2_commit_mc(bar_wempty + stage * 8u);
+          stage = nstage; phase = nphase;
+        };
+#pragma unroll 1
+        for (uint32_t c0 = 0; c0 < k0s; c0 += SPCT)
+          chunk(x4 + c0 * kstep4, k0s - c0 < (uint32_t)SPCT ? k0s - c0 : (uint32_t)SPCT, c0 ? 1u : 0u, hs == 0 && c0 + SPCT >= k0s);
+        // the second half of the hidden operand (columns 128-255) is handed over separately: the first eight hidden K-steps run
+        // while the epilogue warps still convert the second half (they read the whole accumulator into registers first)
+        bool hi_ok = false;
+#pragma unroll 1
+        for (uint32_t c0 = 0; c0 < hs || !hi_ok; c0 += SPCT) {
+          if (!hi_ok && (c0 + SPCT > 8u || c0 >= hs)) {
+            ST_ADD(2);
+            mbar_wait(bar_a + (2u + slot) * 8u, (a_par >> (2u + slot)) & 1u); a_par ^= 1u << (2u + slot); hi_ok = true;
+            ST_ADD(0);
+            tc_fence_after();
+          }
+          if (c0 < hs) chunk(h4 + c0 * kstep4, hs - c0 < (uint32_t)SPCT ? hs - c0 : (uint32_t)SPCT, (k0s || c0) ? 1u : 0u, c0 + SPCT >= hs);
+        }
+        umma2_commit_mc((BW && li + 1 == n ? bar_bnd : bar_acc) + slot * 8u);      // BW: the path's last Linear reports to the boundary warps
+      }
+    }
+    ST_FLUSH(0, blockIdx.x == 0 && (mask & 1u));
+  };
+
   if (warp >= EPIW && warp <= EPIW + NST) {
   // BW: 24 warps start at 80 registers (768 x 80 = the CTA's pool); the producer / issuer warp group gives 32 of them to the epilogue warp groups
-  if (BW) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+  if (BW) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(NF_REG_W4));          // register budget: see the epilogue branch (48 with one issuer)
   if (warp < EPIW + NST) {
     // ================= weight producers (both CTAs): one ring stage each =================
     // The ring carries, step by step, slot 0's Linear then slot 1's (half a round behind); entry g goes to stage g % NST.
@@ -531,24 +628,32 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
           const int kl = k - (slot ? lag : 0);
           if (kl < 0 || kl >= nsteps || (slot && single)) continue;
           const int li = slot ? li1 : li0;
-          const uint32_t steps = prog.lin[li].k0_steps + prog.lin[li].h_steps, sb = prog.lin[li].step_bytes;
+          // chunks never straddle the x0 part and the hidden part of a Linear (the issuer's chunks then read ONE buffer each):
+          // ceil(k0 / SPCT) chunks of x0 K-steps, then ceil(h / SPCT) chunks of hidden K-steps; the Linear's last chunk also
+          // carries the bias K-group (it follows the data steps in the image)
+          const uint32_t k0s = prog.lin[li].k0_steps, hs = prog.lin[li].h_steps, sb = prog.lin[li].step_bytes;
           const uint8_t* src = a.packed + prog.lin[li].w_off + (size_t)crank * prog.lin[li].half_bytes;
-          for (uint32_t st0 = 0; st0 < steps; st0 += SPCT) {
-            if (rs == p) {
-              // the Linear's last chunk also carries the bias K-group (it follows the data steps in the image)
-              const uint32_t bytes = st0 + SPCT < steps ? (uint32_t)SPCT * sb : (steps - st0) * sb + (sb >> 1);
-              const uint32_t par = use & 1u; ++use;
-              ST_ADD(2);
-              if (a.debug & 1024) mbar_wait_backoff(bar_empty, par ^ 1u); else mbar_wait(bar_empty, par ^ 1u);
-              ST_ADD(0);
-              mbar_expect_tx(bar_land, bytes);
-              bulk_g2s(dst, src + (size_t)st0 * sb, bytes, bar_land);
-              mbar_wait(bar_land, par);                                    // landed in THIS CTA ...
-              ST_ADD(1);
-              mbar_arrive_cluster_relaxed(ready_leader);                   // ... tell the leader's MMA thread
-              ST_INC(3);
+#pragma unroll 1
+          for (uint32_t part = 0; part < 2; ++part) {
+            const uint32_t steps = part ? hs : k0s, base = part ? k0s : 0u;
+            for (uint32_t st0 = 0; st0 < steps; st0 += SPCT) {
+              if (rs == p) {
+                const bool last = st0 + SPCT >= steps && (part == 1 || hs == 0);
+                const uint32_t nst = steps - st0 < (uint32_t)SPCT ? steps - st0 : (uint32_t)SPCT;
+                const uint32_t bytes = nst * sb + (last ? sb >> 1 : 0u);
+                const uint32_t par = use & 1u; ++use;
+                ST_ADD(2);
+                mbar_wait(bar_empty, par ^ 1u);
+                ST_ADD(0);
+                mbar_expect_tx(bar_land, bytes);
+                bulk_g2s(dst, src + (size_t)(base + st0) * sb, bytes, bar_land);
+                mbar_wait(bar_land, par);                                    // landed in THIS CTA ...
+                ST_ADD(1);
+                mbar_arrive_cluster_relaxed(ready_leader);                   // ... tell the leader's MMA threads
+                ST_INC(3);
+              }
+              if (++rs == NST) rs = 0;
             }
-            if (++rs == NST) rs = 0;
           }
           const int ln = li + 1 == n ? 0 : li + 1;
           if (slot) li1 = ln; else li0 = ln;
@@ -557,89 +662,18 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
       ST_FLUSH(8, blockIdx.x == 0 && p == 0);
     }
   } else {
-    // ================= MMA issuer (leader CTA only): one thread, tight nested loops =================
-    // The probe of the NEXT ring stage is issued before the current chunk's MMAs, so its ~150-cycle latency is hidden.
-    if (crank == 0 && elect_one()) {
-      uint32_t stage = 0, phase = 0, a_par = 0;
-      const uint32_t base4 = smem_u32(smem_raw) >> 4;
-      const uint32_t w4 = base4 + (uint32_t)((offsetof(Tc3Smem, W) + RING_OFF) >> 4);
-      const uint32_t bar_wready = smem_u32(&s.w_ready[0]), bar_wempty = smem_u32(&s.w_empty[0]);
-      const uint32_t bar_a = smem_u32(&s.a_ready[0]), bar_acc = smem_u32(&s.acc_full[0]), bar_bnd = smem_u32(&s.bnd_full[0]);
-      const uint32_t a_lbo = (uint32_t)(KG_BYTES >> 4) << 16, kstep4 = (uint32_t)(2 * KG_BYTES) >> 4;
-      const uint64_t ones_desc = ((uint64_t)0x4000u << 32) | (base4 + (uint32_t)(offsetof(Tc3Smem, ones) >> 4)) | (8u << 16);   // SBO = 0, LBO = 128 B
-      int li0 = 0, li1 = 0;
-      bool w_ok = false;                               // ring stage `stage` is known to be full
-      const bool no_mma = (a.debug & 2) != 0;
-      ST_DECL;
-      for (int k = 0; k < nsteps + lag; ++k) {
-#pragma unroll 1
-        for (uint32_t slot = 0; slot < 2; ++slot) {
-          const int kl = k - (slot ? lag : 0);
-          if (kl < 0 || kl >= nsteps || (slot && single)) continue;
-          const int li = slot ? li1 : li0;
-          const uint4 r0 = *reinterpret_cast<const uint4*>(&prog.lin[li].k0_steps);
-          const uint32_t bhi = prog.lin[li].bhi;
-          const uint32_t k0s = r0.x, kend = r0.x + r0.y, idesc = r0.z, bstep4 = r0.w;
-          ST_ADD(2);
-          mbar_wait(bar_a + slot * 8u, (a_par >> slot) & 1u); a_par ^= 1u << slot;
-          ST_ADD(0);
-          // the second half of the hidden operand (columns 128-255) is handed over separately: the first eight hidden K-steps
-          // run while the epilogue warps still convert the second half (they read the whole accumulator into registers first)
-          bool hi_ok = false;
-          const uint32_t hi_from = r0.y ? k0s + 8u : 0u;
-          tc_fence_after();
-          const uint32_t d_tmem = slot * 256u;
-          const uint32_t x4 = (single ? base4 + (uint32_t)((offsetof(Tc3Smem, H) + sizeof(s.H[0])) >> 4)
-                                      : base4 + (uint32_t)(offsetof(Tc3Smem, X0) >> 4) + (shared_x0 ? 0u : slot * (uint32_t)(sizeof(s.X0[0]) >> 4))) | a_lbo;
-          const uint32_t h4 = (base4 + (uint32_t)(offsetof(Tc3Smem, H) >> 4) + slot * (uint32_t)(sizeof(s.H[0]) >> 4)) | a_lbo;
-#pragma unroll 1
-          for (uint32_t gs0 = 0; gs0 < kend; gs0 += SPCT) {
-            if (!hi_ok && gs0 + SPCT > hi_from) {
-              ST_ADD(2);
-              mbar_wait(bar_a + (2u + slot) * 8u, (a_par >> (2u + slot)) & 1u); a_par ^= 1u << (2u + slot); hi_ok = true;
-              ST_ADD(0);
-            }
-            if (!w_ok) { ST_ADD(2); mbar_wait(bar_wready + stage * 8u, phase); ST_ADD(1); ST_INC(3); }
-            const uint32_t nstage = stage + 1 == NST ? 0u : stage + 1u, nphase = stage + 1 == NST ? phase ^ 1u : phase;
-            w_ok = mbar_test_wait(bar_wready + nstage * 8u, nphase);       // consumed on the next iteration
-            tc_fence_after();
-            const uint32_t b4 = (w4 + stage * (uint32_t)(STAGE_BYTES >> 4)) | bhi;
-            if (no_mma) {
-              // timing experiment (NF_TC_DEBUG & 2): every barrier and copy, but no tensor work
-            } else if (gs0 + SPCT <= k0s || (gs0 >= k0s && gs0 + SPCT <= kend)) {
-              // fast path: a full chunk fed from one buffer -> back-to-back MMAs, operands differ by constants
-              const uint32_t a4 = gs0 < k0s ? x4 + gs0 * kstep4 : h4 + (gs0 - k0s) * kstep4;
-              umma2_f16(d_tmem, umma_desc_lo(a4), umma_desc_lo(b4), idesc, gs0 > 0 ? 1u : 0u);
-#pragma unroll
-              for (uint32_t i = 1; i < SPCT; ++i)
-                umma2_f16(d_tmem, umma_desc_lo(a4 + i * kstep4), umma_desc_lo(b4 + i * bstep4), idesc, 1u);
-            } else {
-              const uint32_t nst = kend - gs0 < (uint32_t)SPCT ? kend - gs0 : (uint32_t)SPCT;
-              for (uint32_t i = 0; i < nst; ++i) {
-                const uint32_t gs = gs0 + i;
-                const uint32_t a4 = gs < k0s ? x4 + gs * kstep4 : h4 + (gs - k0s) * kstep4;
-                umma2_f16(d_tmem, umma_desc_lo(a4), umma_desc_lo(b4 + i * bstep4), idesc, gs > 0 ? 1u : 0u);
-              }
-            }
-            if (gs0 + SPCT >= kend && !no_mma) {
-              // the bias K-step: its one non-zero K-group follows the chunk's data steps; LBO = 0 in the B descriptor
-              const uint32_t nst = kend - gs0;
-              umma2_f16(d_tmem, ones_desc, umma_desc_lo(w4 + stage * (uint32_t)(STAGE_BYTES >> 4) + nst * bstep4), idesc, 1u);
-            }
-            umma2_commit_mc(bar_wempty + stage * 8u);
-            stage = nstage; phase = nphase;
-          }
-          umma2_commit_mc((BW && li + 1 == n ? bar_bnd : bar_acc) + slot * 8u);      // BW: the path's last Linear reports to the boundary warps
-          const int ln = li + 1 == n ? 0 : li + 1;
-          if (slot) li1 = ln; else li0 = ln;
-        }
-      }
-      ST_FLUSH(0, blockIdx.x == 0);
-    }
+    // ================= MMA issuer of slot 0 (leader CTA only) =================
+    if (crank == 0 && elect_one()) run_issuer(TWO ? 1u : 3u);
   }
+  } else if (TWO && warp >= W_ISSB) {
+    // ================= MMA issuer of slot 1 (leader CTA only) =================
+    if (NF_REG_W6) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(NF_REG_W6 ? NF_REG_W6 : 24));
+    if (warp == W_ISSB && crank == 0 && elect_one()) run_issuer(2u);
   } else if (!BW || warp < EPIW) {
     // ================= encode + epilogue: all 16 warps serve the two slots alternately =================
-    if (BW) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");   // 16 x 32 x 88 + 128 x 48 + 128 x 80 = 768 x 80: the pool is what the CTA was launched with
+    // The pool is what the CTA was launched with.  One issuer: 24 warps x 80 = 16 x 88 (epilogue) + 4 x 48 (producers, issuer) +
+    // 4 x 80 (boundary).  Two issuers: 28 warps x 72 = 16 x 88 + 4 x 40 + 4 x 72 + 4 x 40 (slot 1's issuer and three idle warps).
+    if (BW) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(NF_REG_E));
     // TMEM lane quarter q = warp % 4 (rows 32q..32q+31), column quarter cq = warp / 4 (64 accumulator columns).
     const int q = warp & 3, cq = warp >> 2;
     const int e_tid = warp * 32 + lane;
@@ -1180,7 +1214,7 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
   }
   // boundary-warp mode (four more warps own the tile boundary): the plain two-tile instantiations, warp-aligned rays
   const bool bw = NF_BW && !wide && (T & 31) == 0 && ring == 3 && epiw == 16;
-  const int threads = 32 * (epiw + ring + 1 + (bw ? 4 : 0));
+  const int threads = 32 * (epiw + ring + 1 + (bw ? 4 + 4 * NF_TWO_ISSUERS : 0));
   const NfStreamMap map(T, ROWS);
   const long long units = map.units(n_rays);
   if (units == 0) return cudaSuccess;
