@@ -138,6 +138,9 @@ __device__ __forceinline__ void wait_acc(uint32_t bar, uint32_t parity, int debu
 #define NF_BW 1
 #endif
 // one MMA-issuing thread per slot (else one thread issues both slots' Linears in turn)
+#ifndef NF_ISSUE_STRAIGHT
+#define NF_ISSUE_STRAIGHT 1
+#endif
 #ifndef NF_REG_E
 #define NF_REG_E 88
 #define NF_REG_W4 40
@@ -594,6 +597,32 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
         // the second half of the hidden operand (columns 128-255) is handed over separately: the first eight hidden K-steps run
         // while the epilogue warps still convert the second half (they read the whole accumulator into registers first)
         bool hi_ok = false;
+        if (NF_ISSUE_STRAIGHT && SPCT == 4 && hs == 16u && bstep4 == 256u) {
+          // the common shape (256 hidden inputs, 256 outputs: 10 of Plain+View's 12 Linears) as straight-line code: four full
+          // chunks, every descriptor a constant offset from two bases -- the single issuing thread retires ~1 instruction per
+          // 4-5 cycles, so instructions per chunk are what bounds the MMA issue rate
+          auto chunk4 = [&](const uint32_t a4, const uint32_t acc0, const bool last) {
+            if (!w_ok) { ST_ADD(2); mbar_wait(bar_wready + stage * 8u, phase); ST_ADD(1); ST_INC(3); }
+            const uint32_t nstage = stage + 1 == NST ? 0u : stage + 1u, nphase = stage + 1 == NST ? phase ^ 1u : phase;
+            w_ok = (last && mask != 3u) ? false : mbar_test_wait(bar_wready + nstage * 8u, nphase);
+            tc_fence_after();
+            const uint32_t wb = w4 + stage * (uint32_t)(STAGE_BYTES >> 4), b4 = wb | (128u << 16);     // LBO = 2048 B (128 rows x 16 B)
+            umma2_f16(d_tmem, umma_desc_lo(a4), umma_desc_lo(b4), idesc, acc0);
+#pragma unroll
+            for (uint32_t i = 1; i < 4; ++i) umma2_f16(d_tmem, umma_desc_lo(a4 + i * kstep4), umma_desc_lo(b4 + i * 256u), idesc, 1u);
+            if (last) umma2_f16(d_tmem, ones_desc, umma_desc_lo(wb + 4u * 256u), idesc, 1u);
+            umma2_commit_mc(bar_wempty + stage * 8u);
+            stage = nstage; phase = nphase;
+          };
+          chunk4(h4, k0s ? 1u : 0u, false);
+          chunk4(h4 + 4u * kstep4, 1u, false);
+          ST_ADD(2);
+          mbar_wait(bar_a + (2u + slot) * 8u, (a_par >> (2u + slot)) & 1u); a_par ^= 1u << (2u + slot);
+          ST_ADD(0);
+          tc_fence_after();
+          chunk4(h4 + 8u * kstep4, 1u, false);
+          chunk4(h4 + 12u * kstep4, 1u, true);
+        } else
 #pragma unroll 1
         for (uint32_t c0 = 0; c0 < hs || !hi_ok; c0 += SPCT) {
           if (!hi_ok && (c0 + SPCT > 8u || c0 >= hs)) {
