@@ -659,7 +659,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
       const int p = warp - EPIW;
       const uint32_t ready_leader = leader_addr(smem_u32(&s.w_ready[p]));
       const uint32_t bar_empty = smem_u32(&s.w_empty[p]), bar_land = smem_u32(&s.w_land[p]), dst = smem_u32(s.W + RING_OFF + p * STAGE_BYTES);
-      int rs = 0, li0 = 0, li1 = 0; uint32_t use = 0;
+      uint32_t rs = 0, use = 0; int li0 = 0, li1 = 0;            // rs: ring stage of the current Linear's first chunk
       ST_DECL;
       for (int k = 0; k < nsteps + lag; ++k) {
 #pragma unroll 1
@@ -668,32 +668,31 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
           if (kl < 0 || kl >= nsteps || (slot && single)) continue;
           const int li = slot ? li1 : li0;
           // chunks never straddle the x0 part and the hidden part of a Linear (the issuer's chunks then read ONE buffer each):
-          // ceil(k0 / SPCT) chunks of x0 K-steps, then ceil(h / SPCT) chunks of hidden K-steps; the Linear's last chunk also
-          // carries the bias K-group (it follows the data steps in the image)
+          // n0 = ceil(k0 / SPCT) chunks of x0 K-steps, then n1 = ceil(h / SPCT) chunks of hidden K-steps; the Linear's last chunk
+          // also carries the bias K-group (it follows the data steps in the image).  This thread's chunks of the Linear are
+          // first, first + NST, ... (no walk over the other stages' chunks: the bookkeeping between two copies sits between
+          // "stage empty" and the next copy's issue whenever the issuer is ahead)
           const uint32_t k0s = prog.lin[li].k0_steps, hs = prog.lin[li].h_steps, sb = prog.lin[li].step_bytes;
           const uint8_t* src = a.packed + prog.lin[li].w_off + (size_t)crank * prog.lin[li].half_bytes;
+          const uint32_t n0 = (k0s + SPCT - 1) / SPCT, nch = n0 + (hs + SPCT - 1) / SPCT;
 #pragma unroll 1
-          for (uint32_t part = 0; part < 2; ++part) {
-            const uint32_t steps = part ? hs : k0s, base = part ? k0s : 0u;
-            for (uint32_t st0 = 0; st0 < steps; st0 += SPCT) {
-              if (rs == p) {
-                const bool last = st0 + SPCT >= steps && (part == 1 || hs == 0);
-                const uint32_t nst = steps - st0 < (uint32_t)SPCT ? steps - st0 : (uint32_t)SPCT;
-                const uint32_t bytes = nst * sb + (last ? sb >> 1 : 0u);
-                const uint32_t par = use & 1u; ++use;
-                ST_ADD(2);
-                mbar_wait(bar_empty, par ^ 1u);
-                ST_ADD(0);
-                mbar_expect_tx(bar_land, bytes);
-                bulk_g2s(dst, src + (size_t)(base + st0) * sb, bytes, bar_land);
-                mbar_wait(bar_land, par);                                    // landed in THIS CTA ...
-                ST_ADD(1);
-                mbar_arrive_cluster_relaxed(ready_leader);                   // ... tell the leader's MMA threads
-                ST_INC(3);
-              }
-              if (++rs == NST) rs = 0;
-            }
+          for (uint32_t c = (uint32_t)p >= rs ? (uint32_t)p - rs : (uint32_t)p + NST - rs; c < nch; c += NST) {
+            const bool hid = c >= n0;
+            const uint32_t st0 = (hid ? c - n0 : c) * SPCT, steps = hid ? hs : k0s, base = hid ? k0s : 0u;
+            const uint32_t nst = steps - st0 < (uint32_t)SPCT ? steps - st0 : (uint32_t)SPCT;
+            const uint32_t bytes = nst * sb + (c + 1 == nch ? sb >> 1 : 0u);
+            const uint32_t par = use & 1u; ++use;
+            ST_ADD(2);
+            mbar_wait(bar_empty, par ^ 1u);
+            ST_ADD(0);
+            mbar_expect_tx(bar_land, bytes);
+            bulk_g2s(dst, src + (size_t)(base + st0) * sb, bytes, bar_land);
+            mbar_wait(bar_land, par);                                    // landed in THIS CTA ...
+            ST_ADD(1);
+            mbar_arrive_cluster_relaxed(ready_leader);                   // ... tell the leader's MMA thread
+            ST_INC(3);
           }
+          rs = (rs + nch) % NST;
           const int ln = li + 1 == n ? 0 : li + 1;
           if (slot) li1 = ln; else li0 = ln;
         }
