@@ -111,6 +111,9 @@ struct Tc3Args {
 #define ST_FLUSH(base, cond) do { } while (0)
 #endif
 
+#ifndef NF_ACC_POLL
+#define NF_ACC_POLL 0
+#endif
 // acc_full wait of the 16 epilogue warps.  Default: hardware-suspended try_wait (no issue slots burnt).
 __device__ __forceinline__ void wait_acc(uint32_t bar, uint32_t parity, int debug) {
   if (debug & 256) { mbar_wait_backoff(bar, parity); return; }
@@ -124,7 +127,14 @@ __device__ __forceinline__ void wait_acc(uint32_t bar, uint32_t parity, int debu
     }
     return;
   }
+#if NF_ACC_POLL == 1
+  mbar_wait(bar, parity);                                  // experiment: pure test_wait polling by all 16 warps
+#elif NF_ACC_POLL >= 2
+  for (int i = 0; i < NF_ACC_POLL; ++i) if (mbar_test_wait(bar, parity)) return;     // experiment: poll a few times, then suspend
   mbar_wait_suspend(bar, parity);
+#else
+  mbar_wait_suspend(bar, parity);
+#endif
 }
 
 // sin on the FMA pipe: the MUFU unit retires 16 sines per cycle per SM, so a 128 x 256 sin epilogue cannot finish in less than
@@ -133,22 +143,18 @@ __device__ __forceinline__ void wait_acc(uint32_t bar, uint32_t parity, int debu
 // minimax polynomial for sin(2 pi r): max error 6.3e-6, far inside the fp16 rounding of the result (2.4e-4).
 // MEASURED (profiles/r01_sin_poly_sweep.txt): 0 pairs 113.8 ms/frame, 2 pairs 115.0, 3 pairs 116.2, 4 pairs 119.7 -- the sin
 // epilogue is not MUFU-throughput-bound but issue/latency-bound, so the extra FMA-pipe instructions only cost.  Default 0.
-// boundary-warp mode: the boundary warps also write the View head's [p, elaz] x0 tail (else the density-out epilogue does)
+// boundary-warp mode (four more warps own the tile boundary); A/B switches of this round's measurements
 #ifndef NF_BW
 #define NF_BW 1
 #endif
-// one MMA-issuing thread per slot (else one thread issues both slots' Linears in turn)
 #ifndef NF_ISSUE_STRAIGHT
-#define NF_ISSUE_STRAIGHT 1
+#define NF_ISSUE_STRAIGHT 1   // straight-line issuer code for the 16-step Linears
 #endif
 #ifndef NF_REG_E
-#define NF_REG_E 88
+#define NF_REG_E 88           // setmaxnreg: epilogue warps; NF_REG_W4: the producer / issuer warp group
 #define NF_REG_W4 40
-#define NF_REG_W6 40
 #endif
-#ifndef NF_TWO_ISSUERS
-#define NF_TWO_ISSUERS 0
-#endif
+// the boundary warps also write the View head's [p, elaz] x0 tail (else the density-out epilogue does)
 #ifndef NF_BW_PRETAIL
 #define NF_BW_PRETAIL 1
 #endif
@@ -258,6 +264,9 @@ __device__ __forceinline__ void epi_hidden3_sin_pipelined(uint8_t* __restrict__ 
 // (a_ready[slot]: the next Linear's first eight hidden K-steps start), and then converts the two units of columns 128-255 while
 // those MMAs run (the caller arrives on a_ready[2 + slot] at the end of the phase).  With every load issued up front there is
 // no TMEM wait between units, so the sines of different units overlap without hand pipelining.
+#ifndef NF_SIN_POLY_SPLIT
+#define NF_SIN_POLY_SPLIT 0
+#endif
 #ifndef NF_SPLIT_HANDOFF
 #define NF_SPLIT_HANDOFF 1
 #endif
@@ -276,7 +285,12 @@ __device__ __forceinline__ void epi_hidden_split(uint8_t* __restrict__ H, uint32
     const int col = (cq + 4 * u) * 16;
     uint32_t o[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = act_pack_t<ACT>(__uint_as_float(v[u][2 * i]), __uint_as_float(v[u][2 * i + 1]));
+    for (int i = 0; i < 8; ++i) {
+      // NF_SIN_POLY_SPLIT of every 8 column pairs take the FMA-pipe polynomial instead of MUFU.SIN (the sin epilogue's floor is the
+      // MUFU rate: 16 per cycle per SM = 2048 cycles per 128 x 256 tile)
+      if (ACT == NF_ACT_SIN && i < NF_SIN_POLY_SPLIT) o[i] = pack_h2(sin_poly(__uint_as_float(v[u][2 * i])), sin_poly(__uint_as_float(v[u][2 * i + 1])));
+      else o[i] = act_pack_t<ACT>(__uint_as_float(v[u][2 * i]), __uint_as_float(v[u][2 * i + 1]));
+    }
     uint8_t* dst = H + (col >> 3) * KG_BYTES + row * 16;
     st_v4(dst, o[0], o[1], o[2], o[3]); st_v4(dst + KG_BYTES, o[4], o[5], o[6], o[7]);
     if (TRAIN && gA) {
@@ -475,7 +489,7 @@ __device__ __forceinline__ void composite_tile3(Tc3Smem& s, int slot, const NfPl
 // (bnd_full), hand the slot back to the issuer and only then composite -- so the 16 epilogue warps never leave the MLP phases
 // and the ~7 K-cycle boundary is off both the slot's critical path and the epilogue warps' time.  Needs T % 32 == 0, WIDE == 0.
 template <int NST, int SPCT, int NCQ, int WIDE, bool DYN, bool TRAIN = false, bool AUX = false, bool BW = false>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (4 * NCQ + NST + 1 + (BW ? 4 + 4 * NF_TWO_ISSUERS : 0)), 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (4 * NCQ + NST + 1 + (BW ? 4 : 0)), 1)
 k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Prog prog, const Tc3Args a, const __grid_constant__ Tc3Train tr) {
   static_assert(!BW || (WIDE == 0 && NST == 3 && NCQ == 4), "boundary warps: plain two-tile mode, warp groups {0-15, 16-19, 20-23}");
   constexpr int STAGE_BYTES = SPCT * 4096 + BIAS_PIECE;
@@ -495,8 +509,6 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
   const int passes = trips * map.tpr;
   const int n = prog.n_lin, lag = prog.lag;
   const int nsteps = passes * n;                   // MMA steps (Linears) per slot
-  constexpr bool TWO = BW && NF_TWO_ISSUERS;        // one MMA-issuing thread per slot (a seventh warp group, its first warp issues slot 1)
-  constexpr int W_ISSB = 4 * NCQ + NST + 1 + 4;
 
   // ---- one-time setup ----
   if (threadIdx.x == 0) {
@@ -527,15 +539,15 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
   tc_fence_after();
   if (s.tmem_base != 0) __trap();
 
-  // ---- the MMA issuer: one thread per slot (mask bit s = this thread issues slot s's Linears) ----
-  // A single thread cannot keep the tensor pipe fed: a tcgen05.mma costs the issuing thread >= 76 cycles and a commit + barrier
-  // probe ~190 (profiles/r01_mma_issue_microbench.csv), i.e. >= 500 cycles per 4-MMA ring stage against 512 cycles of execution
-  // before any bookkeeping; measured ~140 cycles per MMA.  With one issuing thread per slot the per-Linear work (program record,
-  // a_ready waits, the accumulator commit) of one slot overlaps the other slot's issue, and at the seams both threads issue.
-  // The weight ring is ONE stream in the global order (step by step: slot 0's Linear, then slot 1's); a thread lets the other
-  // slot's chunks pass by counting them.  The probe of the NEXT ring stage is issued before the current chunk's MMAs, so its
-  // ~150-cycle latency is hidden.
-  auto run_issuer = [&](const uint32_t mask) {
+  // ---- the MMA issuer (one thread of the leader CTA) ----
+  // A tcgen05.mma costs the issuing thread >= 76 cycles and a commit + barrier probe ~190 (profiles/r01_mma_issue_microbench.csv):
+  // >= 500 cycles per 4-MMA ring stage against 512 cycles of execution before any bookkeeping, and a lone warp retires about one
+  // instruction per 4-5 cycles -- the instruction count per chunk decides whether the tensor pipe is fed (round 2: ~90 -> ~45
+  // instructions per chunk took the frame from 103 to 96 ms).  Hence: chunks that read ONE activation buffer, straight-line code
+  // for the 16-step Linears, the probe of the NEXT ring stage issued before the current chunk's MMAs (its ~150-cycle latency is
+  // hidden).  (One issuing thread per slot, the two sharing the ring, was built and trapped on the hardware; removed.)
+  auto run_issuer = [&]() {
+    constexpr uint32_t mask = 3u;
     uint32_t stage = 0, phase = 0, a_par = 0;
     const uint32_t base4 = smem_u32(smem_raw) >> 4;
     const uint32_t w4 = base4 + (uint32_t)((offsetof(Tc3Smem, W) + RING_OFF) >> 4);
@@ -556,13 +568,6 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
         if (slot) li1 = ln; else li0 = ln;
         const uint4 r0 = *reinterpret_cast<const uint4*>(&prog.lin[li].k0_steps);
         const uint32_t k0s = r0.x, hs = r0.y, idesc = r0.z, bstep4 = r0.w;
-        if (!((mask >> slot) & 1u)) {
-          // the other issuer's Linear: its chunks pass through the ring
-          stage += (k0s + SPCT - 1) / SPCT + (hs + SPCT - 1) / SPCT;
-          while (stage >= (uint32_t)NST) { stage -= NST; phase ^= 1u; }
-          w_ok = false;
-          continue;
-        }
         const uint32_t bhi = prog.lin[li].bhi;
         ST_ADD(2);
         mbar_wait(bar_a + slot * 8u, (a_par >> slot) & 1u); a_par ^= 1u << slot;
@@ -651,7 +656,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
 
   if (warp >= EPIW && warp <= EPIW + NST) {
   // BW: 24 warps start at 80 registers (768 x 80 = the CTA's pool); the producer / issuer warp group gives 32 of them to the epilogue warp groups
-  if (BW) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(NF_REG_W4));          // register budget: see the epilogue branch (48 with one issuer)
+  if (BW) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(NF_REG_W4));          // register budget: see the epilogue branch
   if (warp < EPIW + NST) {
     // ================= weight producers (both CTAs): one ring stage each =================
     // The ring carries, step by step, slot 0's Linear then slot 1's (half a round behind); entry g goes to stage g % NST.
@@ -700,17 +705,12 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
       ST_FLUSH(8, blockIdx.x == 0 && p == 0);
     }
   } else {
-    // ================= MMA issuer of slot 0 (leader CTA only) =================
-    if (crank == 0 && elect_one()) run_issuer(TWO ? 1u : 3u);
+    // ================= MMA issuer (leader CTA only) =================
+    if (crank == 0 && elect_one()) run_issuer();
   }
-  } else if (TWO && warp >= W_ISSB) {
-    // ================= MMA issuer of slot 1 (leader CTA only) =================
-    if (NF_REG_W6) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(NF_REG_W6 ? NF_REG_W6 : 24));
-    if (warp == W_ISSB && crank == 0 && elect_one()) run_issuer(2u);
   } else if (!BW || warp < EPIW) {
     // ================= encode + epilogue: all 16 warps serve the two slots alternately =================
-    // The pool is what the CTA was launched with.  One issuer: 24 warps x 80 = 16 x 88 (epilogue) + 4 x 48 (producers, issuer) +
-    // 4 x 80 (boundary).  Two issuers: 28 warps x 72 = 16 x 88 + 4 x 40 + 4 x 72 + 4 x 40 (slot 1's issuer and three idle warps).
+    // The pool is what the CTA was launched with: 24 warps x 80 >= 16 x 88 (epilogue) + 4 x 40 (producers, issuer) + 4 x 80 (boundary).
     if (BW) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(NF_REG_E));
     // TMEM lane quarter q = warp % 4 (rows 32q..32q+31), column quarter cq = warp / 4 (64 accumulator columns).
     const int q = warp & 3, cq = warp >> 2;
@@ -1252,7 +1252,7 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
   }
   // boundary-warp mode (four more warps own the tile boundary): the plain two-tile instantiations, warp-aligned rays
   const bool bw = NF_BW && !wide && (T & 31) == 0 && ring == 3 && epiw == 16;
-  const int threads = 32 * (epiw + ring + 1 + (bw ? 4 + 4 * NF_TWO_ISSUERS : 0));
+  const int threads = 32 * (epiw + ring + 1 + (bw ? 4 : 0));
   const NfStreamMap map(T, ROWS);
   const long long units = map.units(n_rays);
   if (units == 0) return cudaSuccess;

@@ -7,8 +7,8 @@ LIB=nerf_atlas_b200/libnerf_b200.so
 dump() {  # $1 = mangled-name regex, $2 = output
   cuobjdump -sass $LIB | awk -v pat="$1" '/Function :/ { on = ($0 ~ pat) } on' | sed -E 's@/\* 0x[0-9a-f]+ \*/@@; s@^[[:space:]]+/\*[0-9a-f]{4,5}\*/@@; s/[[:space:]]+$//' | grep -v '^$' > $2
 }
-dump 'k_render_tc3ILi3ELi4ELi4ELb0ELb0ELb0ELb0E' profiles/${TAG}_k_render_tc3.sass
-dump 'k_render_tc3ILi3ELi4ELi4ELb0ELb0ELb1ELb0E' profiles/${TAG}_k_render_tc3_train.sass
+dump 'k_render_tc3ILi3ELi4ELi4ELi0ELb0ELb0ELb0ELb1E' profiles/${TAG}_k_render_tc3.sass
+dump 'k_render_tc3ILi3ELi4ELi4ELi0ELb0ELb1ELb0ELb1E' profiles/${TAG}_k_render_tc3_train.sass
 dump 'k_bwd_chain' profiles/${TAG}_k_bwd_chain.sass
 dump 'k_bwd_dw' profiles/${TAG}_k_bwd_dw.sass
 {
