@@ -637,6 +637,18 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
           tc_fence_after();
           chunk(h4 + 8u * kstep4, 4u, 1u, false);
           chunk(h4 + 12u * kstep4, 4u, 1u, true);
+        } else if (NF_ISSUE_STRAIGHT && SPCT == 3 && hs == 16u) {
+          // the shared-wide-x0 ring (3 x 14 KB): 3 + 3 + 3 + 3 + 3 + 1 K-steps
+          chunk(h4, 3u, k0s ? 1u : 0u, false);
+          chunk(h4 + 3u * kstep4, 3u, 1u, false);
+          ST_ADD(2);
+          mbar_wait(bar_a + (2u + slot) * 8u, (a_par >> (2u + slot)) & 1u); a_par ^= 1u << (2u + slot);
+          ST_ADD(0);
+          tc_fence_after();
+          chunk(h4 + 6u * kstep4, 3u, 1u, false);
+          chunk(h4 + 9u * kstep4, 3u, 1u, false);
+          chunk(h4 + 12u * kstep4, 3u, 1u, false);
+          chunk(h4 + 15u * kstep4, 1u, 1u, true);
         } else
 #pragma unroll 1
         for (uint32_t c0 = 0; c0 < hs || !hi_ok; c0 += SPCT) {
