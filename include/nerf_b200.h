@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NF_ABI_VERSION 5
+#define NF_ABI_VERSION 6
 
 /* error codes (negative; positive values are cudaError_t) */
 #define NF_E_BADARG    (-1)
@@ -332,6 +332,13 @@ int nf_hash_encode_backward(const nf_model_desc* desc, const float* pts, int64_t
  * arrives as `lr`).  step = 1 for the first update.  All pointers 16-byte aligned device pointers. */
 int nf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                  float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step, void* stream);
+
+/* The same step for n_tensors tensors that share the hyper-parameters and the step count (one parameter group of
+ * runner.load_optim's Adam, runner.py:448-458) in ONE launch: params / grads / exp_avg / exp_avg_sq are HOST arrays of device
+ * pointers (16-byte aligned), numel a host array of element counts (0 = skip). */
+int nf_adam_step_multi(int32_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                       float* const* exp_avg_sq, const int64_t* numel, float lr, float beta1, float beta2, float eps,
+                       float weight_decay, int32_t step, void* stream);
 
 #ifdef __cplusplus
 }

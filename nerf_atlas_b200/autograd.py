@@ -101,7 +101,7 @@ def hash_encode(engine: RenderEngine, pts: torch.Tensor, tables) -> torch.Tensor
 
 class FusedAdam(torch.optim.Optimizer):
   """torch.optim.Adam semantics (the reference's optimiser: runner.py:448-458 -- Adam, eps 1e-7, L2 weight_decay) with the
-  update of every tensor done by one hand-written kernel (`nf_adam_step`: 16 B read + 12 B written per element) instead of
+  update of ALL tensors of a parameter group done by one launch of a hand-written kernel (`nf_adam_step_multi`: 16 B read + 12 B written per element) instead of
   the ~10 element-wise launches of the eager implementation.  Learning-rate schedulers (runner.py:1289 CosineAnnealingLR) work
   unchanged: they write ``group["lr"]``."""
 
@@ -118,6 +118,8 @@ class FusedAdam(torch.optim.Optimizer):
     lib = _lib.lib()
     for group in self.param_groups:
       b1, b2 = group["betas"]
+      # tensors of one group that share the step count and the device go to the kernel together (nf_adam_step_multi: one launch)
+      buckets = {}
       for p in group["params"]:
         if p.grad is None: continue
         if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous(): raise RuntimeError("FusedAdam: contiguous fp32 CUDA parameters only")
@@ -125,14 +127,18 @@ class FusedAdam(torch.optim.Optimizer):
         if not st:
           st["step"] = 0; st["exp_avg"] = torch.zeros_like(p); st["exp_avg_sq"] = torch.zeros_like(p)
         st["step"] += 1
-        g = p.grad.contiguous()
-        with torch.cuda.device(p.device):
-          rc = lib.nf_adam_step(C.c_void_p(p.data_ptr()), C.c_void_p(g.data_ptr()), C.c_void_p(st["exp_avg"].data_ptr()),
-                                C.c_void_p(st["exp_avg_sq"].data_ptr()), p.numel(), float(group["lr"]), float(b1), float(b2),
-                                float(group["eps"]), float(group["weight_decay"]), int(st["step"]),
-                                C.c_void_p(torch.cuda.current_stream().cuda_stream))
-        _lib.check(rc, "nf_adam_step")
-        # the kernel wrote through the raw pointer: tell autograd (saved-tensor checks) and RenderEngine.pack (whose cache key
-        # is (data_ptr, _version)) that the parameter changed, exactly as an in-place torch op would
-        torch.autograd.graph.increment_version(p)
+        buckets.setdefault((p.device, int(st["step"])), []).append((p, p.grad.contiguous(), st))
+      for (dev, step), items in buckets.items():
+        n = len(items)
+        arr = lambda xs: (C.c_void_p * n)(*[x.data_ptr() for x in xs])
+        numel = (C.c_int64 * n)(*[p.numel() for p, _, _ in items])
+        with torch.cuda.device(dev):
+          rc = lib.nf_adam_step_multi(n, arr([p for p, _, _ in items]), arr([g for _, g, _ in items]), arr([s["exp_avg"] for _, _, s in items]),
+                                      arr([s["exp_avg_sq"] for _, _, s in items]), numel, float(group["lr"]), float(b1), float(b2),
+                                      float(group["eps"]), float(group["weight_decay"]), step,
+                                      C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(rc, "nf_adam_step_multi")
+        # the kernel wrote through raw pointers: tell autograd (saved-tensor checks) and RenderEngine.pack (whose cache key is
+        # (data_ptr, _version)) that the parameters changed, exactly as an in-place torch op would
+        for p, _, _ in items: torch.autograd.graph.increment_version(p)
     return loss

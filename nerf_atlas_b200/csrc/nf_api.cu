@@ -77,48 +77,28 @@ int nf_pack_weights(const nf_model_desc* desc, const float* const* params, int32
   cudaStream_t st = (cudaStream_t)stream;
   uint8_t* base = (uint8_t*)packed;
   int pi = 0;
-  for (int m = 0; m < p.n_mlps; ++m) {
-    for (int j = 0; j < p.mlp[m].n_lin; ++j) {
-      const NfLinPlan& L = p.mlp[m].lin[j];
-      const float* W = params[pi++]; const float* b = params[pi++];
-      if (!W || !b) return fail(NF_E_BADARG, "nf_pack_weights: null parameter");
-      // a narrower reference hidden size (PosLinearView.view: 128) is zero-padded to 256: exact, the extra units stay act(0) = 0
-      const int href = p.mlp[m].hidden_ref, kh_ref = L.k_hidden ? href : 0, n_ref = L.is_out ? L.n : href;
-      cudaError_t e = nf_launch_pack_fp32(W, b, (float*)(base + L.wt_off), (float*)(base + L.b_off), n_ref, kh_ref, L.k_hidden, L.k_x0, L.n_pad, st);
-      if (e != cudaSuccess) return cuda_fail(e, "pack fp32");
-      if (href != NF_HIDDEN) continue;                     // the tensor pipeline does not take such a model (nf_tensor_pipeline_support)
-      e = nf_launch_pack_fp16(p, m, j, W, b, packed, st);
-      if (e != cudaSuccess) return cuda_fail(e, "pack fp16");
-      e = nf_launch_pack_w16t(p, m, j, W, packed, st);
-      if (e != cudaSuccess) return cuda_fail(e, "pack fp16 (transposed)");
-    }
+  for (int m = 0; m < p.n_mlps; ++m)
+    for (int j = 0; j < p.mlp[m].n_lin; ++j) { if (!params[pi] || !params[pi + 1]) return fail(NF_E_BADARG, "nf_pack_weights: null parameter"); pi += 2; }
+  {
+    cudaError_t e = nf_launch_pack_all(p, params, packed, st);          // one memset + one launch for every Linear's images
+    if (e != cudaSuccess) return cuda_fail(e, "pack Linears");
   }
-  if (p.enc == NF_ENC_HASH) {
+  {
+    // the embedding tables (one parameter per level; up to three encoders): one launch
     const size_t per = (size_t)(p.hash_mask + 1) * 4 * sizeof(float);
-    for (int l = 0; l < p.hash_levels; ++l) {
-      const float* t = params[pi++];
-      if (!t) return fail(NF_E_BADARG, "nf_pack_weights: null hash table");
-      cudaError_t e = cudaMemcpyAsync(base + p.hash_off + l * per, t, per, cudaMemcpyDeviceToDevice, st);
-      if (e != cudaSuccess) return cuda_fail(e, "pack hash tables");
+    const float* src[48]; float* dst[48]; int nt = 0;
+    const int64_t offs[3] = {p.hash_off, p.hash2_off, p.hash3_off};
+    const bool on[3] = {p.enc == NF_ENC_HASH, p.kind == NF_KIND_DYN && p.deform_enc == NF_ENC_HASH, p.refl_kind != NF_REFL_VIEW};
+    for (int set = 0; set < 3; ++set) {
+      if (!on[set]) continue;
+      for (int l = 0; l < p.hash_levels; ++l) {
+        const float* t = params[pi++];
+        if (!t) return fail(NF_E_BADARG, "nf_pack_weights: null hash table");
+        src[nt] = t; dst[nt] = (float*)(base + offs[set] + l * per); ++nt;
+      }
     }
-  }
-  if (p.kind == NF_KIND_DYN && p.deform_enc == NF_ENC_HASH) {
-    const size_t per = (size_t)(p.hash_mask + 1) * 4 * sizeof(float);
-    for (int l = 0; l < p.hash_levels; ++l) {
-      const float* t = params[pi++];
-      if (!t) return fail(NF_E_BADARG, "nf_pack_weights: null deformation hash table");
-      cudaError_t e = cudaMemcpyAsync(base + p.hash2_off + l * per, t, per, cudaMemcpyDeviceToDevice, st);
-      if (e != cudaSuccess) return cuda_fail(e, "pack deformation hash tables");
-    }
-  }
-  if (p.refl_kind != NF_REFL_VIEW) {
-    const size_t per = (size_t)(p.hash_mask + 1) * 4 * sizeof(float);
-    for (int l = 0; l < p.hash_levels; ++l) {
-      const float* t = params[pi++];
-      if (!t) return fail(NF_E_BADARG, "nf_pack_weights: null refl hash table");
-      cudaError_t e = cudaMemcpyAsync(base + p.hash3_off + l * per, t, per, cudaMemcpyDeviceToDevice, st);
-      if (e != cudaSuccess) return cuda_fail(e, "pack refl hash tables");
-    }
+    cudaError_t e = nf_launch_copy_tables(src, dst, nt, per, st);
+    if (e != cudaSuccess) return cuda_fail(e, "pack hash tables");
   }
   if (p.enc == NF_ENC_FOURIER) {
     const float* b = params[pi++];
@@ -400,6 +380,22 @@ int nf_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
   if ((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) != 0) return fail(NF_E_BADARG, "nf_adam_step: pointers must be 16-byte aligned");
   cudaError_t e = nf_launch_adam_step(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(e, "nf_adam_step");
+}
+
+int nf_adam_step_multi(int32_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                       const int64_t* numel, float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step, void* stream) {
+  if (n_tensors < 0 || step < 1) return fail(NF_E_BADARG, "nf_adam_step_multi: n_tensors >= 0 and step >= 1");
+  if (n_tensors == 0) return 0;
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !numel) return fail(NF_E_BADARG, "nf_adam_step_multi: null pointer");
+  for (int t = 0; t < n_tensors; ++t) {
+    if (numel[t] < 0) return fail(NF_E_BADARG, "nf_adam_step_multi: numel < 0");
+    if (numel[t] == 0) continue;
+    if (!params[t] || !grads[t] || !exp_avg[t] || !exp_avg_sq[t]) return fail(NF_E_BADARG, "nf_adam_step_multi: null tensor pointer");
+    if ((((uintptr_t)params[t] | (uintptr_t)grads[t] | (uintptr_t)exp_avg[t] | (uintptr_t)exp_avg_sq[t]) & 15) != 0)
+      return fail(NF_E_BADARG, "nf_adam_step_multi: pointers must be 16-byte aligned");
+  }
+  cudaError_t e = nf_launch_adam_multi(n_tensors, params, grads, exp_avg, exp_avg_sq, numel, lr, beta1, beta2, eps, weight_decay, step, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nf_adam_step_multi");
 }
 
 }  // extern "C"

@@ -181,6 +181,37 @@ __global__ void k_adam_step(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// the same update for up to ADAM_MAX tensors in ONE launch (blockIdx.y = tensor; the reference model has 32 parameter tensors, from
+// an 8 MB embedding table to a 12-byte bias: 32 launches of ~4 us each were 0.12 ms of a 4.6 ms optimiser step)
+constexpr int ADAM_MAX = 64;
+struct AdamArgs { float* p[ADAM_MAX]; const float* g[ADAM_MAX]; float* m[ADAM_MAX]; float* v[ADAM_MAX]; long long n[ADAM_MAX]; };
+__global__ void k_adam_multi(const __grid_constant__ AdamArgs a, float step_size, float beta1, float beta2, float eps, float wd, float inv_bc2_sqrt) {
+  const int t = blockIdx.y;
+  float* __restrict__ p = a.p[t]; const float* __restrict__ g = a.g[t]; float* __restrict__ m = a.m[t]; float* __restrict__ v = a.v[t];
+  const long long n = a.n[t], n4 = n >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4 + (n & 3); i += (long long)gridDim.x * blockDim.x) {
+    if (i < n4) {
+      float4 P = reinterpret_cast<float4*>(p)[i], M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
+      const float4 G = __ldg(reinterpret_cast<const float4*>(g) + i);
+      float* pp = &P.x; float* mm = &M.x; float* vv = &V.x; const float* gg = &G.x;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float gr = gg[k] + wd * pp[k];
+        mm[k] = mm[k] + (1.f - beta1) * (gr - mm[k]);
+        vv[k] = beta2 * vv[k] + (1.f - beta2) * gr * gr;
+        pp[k] = pp[k] - step_size * (mm[k] / (sqrtf(vv[k]) * inv_bc2_sqrt + eps));
+      }
+      reinterpret_cast<float4*>(p)[i] = P; reinterpret_cast<float4*>(m)[i] = M; reinterpret_cast<float4*>(v)[i] = V;
+    } else {
+      const long long j = n4 * 4 + (i - n4);
+      const float gr = g[j] + wd * p[j];
+      m[j] = m[j] + (1.f - beta1) * (gr - m[j]);
+      v[j] = beta2 * v[j] + (1.f - beta2) * gr * gr;
+      p[j] = p[j] - step_size * (m[j] / (sqrtf(v[j]) * inv_bc2_sqrt + eps));
+    }
+  }
+}
+
 int bwd_num_sms() {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -217,5 +248,23 @@ cudaError_t nf_launch_adam_step(float* p, const float* g, float* m, float* v, in
   const long long want = ((n >> 2) + 3 + 255) / 256;
   const int grid = (int)(want < (long long)bwd_num_sms() * 16 ? want : (long long)bwd_num_sms() * 16);
   k_adam_step<<<grid, 256, 0, st>>>(p, g, m, v, n, (float)(lr / bc1), beta1, beta2, eps, wd, (float)(1.0 / sqrt(bc2)));
+  return cudaGetLastError();
+}
+
+cudaError_t nf_launch_adam_multi(int n_tensors, float* const* p, const float* const* g, float* const* m, float* const* v, const int64_t* numel,
+                                 float lr, float beta1, float beta2, float eps, float wd, int step, cudaStream_t st) {
+  const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+  for (int t0 = 0; t0 < n_tensors; t0 += ADAM_MAX) {
+    AdamArgs a{}; int cnt = 0; long long max_n = 0;
+    for (int t = t0; t < n_tensors && cnt < ADAM_MAX; ++t) {
+      if (numel[t] == 0) continue;
+      a.p[cnt] = p[t]; a.g[cnt] = g[t]; a.m[cnt] = m[t]; a.v[cnt] = v[t]; a.n[cnt] = numel[t];
+      max_n = numel[t] > max_n ? numel[t] : max_n; ++cnt;
+    }
+    if (cnt == 0) continue;
+    const long long want = ((max_n >> 2) + 3 + 255) / 256;
+    const int gx = (int)(want < (long long)bwd_num_sms() * 4 ? want : (long long)bwd_num_sms() * 4);
+    k_adam_multi<<<dim3(gx, cnt), 256, 0, st>>>(a, (float)(lr / bc1), beta1, beta2, eps, wd, (float)(1.0 / sqrt(bc2)));
+  }
   return cudaGetLastError();
 }

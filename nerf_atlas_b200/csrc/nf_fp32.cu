@@ -606,19 +606,6 @@ __global__ void k_ray_radii(const float* __restrict__ rays, long long B, int H, 
   }
 }
 
-// ---- packing -----------------------------------------------------------------------------------
-// W[n][k] (nn.Linear, row-major) -> Wt[k][n_pad] fp32, zero padded.
-__global__ void k_pack_fp32(const float* __restrict__ W, const float* __restrict__ b, float* __restrict__ Wt,
-                            float* __restrict__ bp, int n, int kh_ref, int kh_pad, int kx, int n_pad) {
-  const int total = (kh_pad + kx) * n_pad, k_ref = kh_ref + kx;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int kk = i / n_pad, nn = i - kk * n_pad;
-    const int kr = kk < kh_pad ? (kk < kh_ref ? kk : -1) : kh_ref + (kk - kh_pad);     // padded hidden rows have no source column
-    Wt[i] = (nn < n && kr >= 0) ? W[(size_t)nn * k_ref + kr] : 0.f;
-  }
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) bp[i] = i < n ? b[i] : 0.f;
-}
-
 int num_sms() {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -629,12 +616,6 @@ int num_sms() {
 }  // namespace
 
 // ---- launchers (called from nf_api.cu) -------------------------------------------------------
-cudaError_t nf_launch_pack_fp32(const float* W, const float* b, float* Wt, float* bp, int n_ref, int kh_ref, int kh_pad, int kx, int n_pad, cudaStream_t st) {
-  const int total = (kh_pad + kx) * n_pad;
-  k_pack_fp32<<<(total + 255) / 256, 256, 0, st>>>(W, b, Wt, bp, n_ref, kh_ref, kh_pad, kx, n_pad);
-  return cudaGetLastError();
-}
-
 cudaError_t nf_launch_generate_rays(const float* c2w, int64_t B, float focal, int size, int top, int left, int H, int W, int recip,
                                     float* out, cudaStream_t st) {
   const long long total = B * H * W;

@@ -3,8 +3,6 @@
 #include "nf_common.cuh"
 
 // W[n_ref][kh_ref + kx] (nn.Linear) -> Wt[kh_pad + kx][n_pad] (hidden rows kh_ref..kh_pad-1 and columns n_ref..n_pad-1 zero), bias[n_pad]
-cudaError_t nf_launch_pack_fp32(const float* W, const float* b, float* Wt, float* bp, int n_ref, int kh_ref, int kh_pad, int kx, int n_pad, cudaStream_t st);
-cudaError_t nf_launch_pack_fp16(const NfPlan& plan, int m, int j, const float* W, const float* b, void* packed, cudaStream_t st);
 cudaError_t nf_launch_render_fp32(const NfPlan& plan, const void* packed, const float* rays, int64_t n_rays, const float* ts,
                                   int T, int64_t ts_stride, const float* noise, const float* ray_time, const nf_mip_args* mip,
                                   float* rgb, float* alpha, float* weights, cudaStream_t st, const nf_render_aux* aux = nullptr);
@@ -46,7 +44,8 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
                                  const nf_render_aux* aux = nullptr);
 // training (nf_tc3.cu TRAIN instantiation + nf_train.cu): transposed weight images, the backward of the MLP chain on tcgen05
 const char* nf_train_unsupported(const NfPlan& plan);
-cudaError_t nf_launch_pack_w16t(const NfPlan& plan, int m, int j, const float* W, void* packed, cudaStream_t st);
+cudaError_t nf_launch_pack_all(const NfPlan& plan, const float* const* params, void* packed, cudaStream_t st);      // every Linear's images, one launch
+cudaError_t nf_launch_copy_tables(const float* const* src, float* const* dst, int n, size_t bytes, cudaStream_t st);
 cudaError_t nf_launch_render_backward(const NfPlan& plan, const NfTrainPlan& tp, const void* packed, void* ws, const float* rays,
                                       const float* ts, int64_t ts_stride, const float* d_rgb, float* const* grads, cudaStream_t st);
 // backward of the non-GEMM stages (nf_bwd.cu)
@@ -54,5 +53,7 @@ cudaError_t nf_launch_composite_bwd(const NfPlan& plan, const void* packed, cons
                                     int64_t n_rays, const float* ts, int T, int64_t ts_stride, const float* d_rgb, float* d_sigma,
                                     float* d_feats, cudaStream_t st, int feat_act = -1);
 cudaError_t nf_launch_hash_encode_bwd(const NfPlan& plan, const float* pts, int64_t n, const float* d_feats, float* d_tables, cudaStream_t st);
+cudaError_t nf_launch_adam_multi(int n_tensors, float* const* p, const float* const* g, float* const* m, float* const* v, const int64_t* numel,
+                                 float lr, float beta1, float beta2, float eps, float wd, int step, cudaStream_t st);
 cudaError_t nf_launch_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                                 float wd, int step, cudaStream_t st);

@@ -526,37 +526,6 @@ k_render_tc(const __grid_constant__ NfPlan plan, const __grid_constant__ TcProg 
   }
 }
 
-// ---- packing: nn.Linear W[n][k] -> fp16 UMMA-canonical image [K_tc/8][n_pad][8] + bias in tensor order ----
-__global__ void k_pack_fp16(const __grid_constant__ NfPlan plan, int m, int j, const float* __restrict__ W,
-                            const float* __restrict__ b, uint8_t* __restrict__ packed) {
-  const NfLinPlan& L = plan.mlp[m].lin[j];
-  const int k_ref_total = L.k_hidden + L.k_x0;
-  __half* img = reinterpret_cast<__half*>(packed + L.w16_off);
-  __half* imgh = reinterpret_cast<__half*>(packed + L.w16h_off);
-  const int k_total = L.k0_pad + L.k_hidden;
-  float* b16 = reinterpret_cast<float*>(packed + L.b16_off);
-  const int total = L.n * k_ref_total;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int n_ref = i / k_ref_total, k_ref = i - n_ref * k_ref_total;
-    const int k_tc = k_ref < L.k_hidden ? L.k0_pad + k_ref : nf_x0_perm(plan, m, k_ref - L.k_hidden);
-    const int n_tc = L.is_out ? nf_out_perm(plan, m, n_ref) : n_ref;
-    const __half h = __float2half_rn(W[i]);
-    img[(size_t)(k_tc >> 3) * (L.n_pad * 8) + n_tc * 8 + (k_tc & 7)] = h;
-    const int nh = L.n_pad >> 1, rank = n_tc / nh, nl = n_tc - rank * nh;        // CTA-pair split along N
-    imgh[(size_t)rank * ((k_total + 16) >> 3) * (nh * 8) + (size_t)(k_tc >> 3) * (nh * 8) + nl * 8 + (k_tc & 7)] = h;
-  }
-  for (int n_ref = blockIdx.x * blockDim.x + threadIdx.x; n_ref < L.n; n_ref += gridDim.x * blockDim.x) {
-    const int n_tc = L.is_out ? nf_out_perm(plan, m, n_ref) : n_ref;
-    b16[n_tc] = b[n_ref];
-    // the bias K-step of the pair images: rows k_total (fp16 hi) and k_total + 1 (fp16 lo) against a [1, 1, 0, ...] operand
-    const int nh = L.n_pad >> 1, rank = n_tc / nh, nl = n_tc - rank * nh;
-    const __half hi = __float2half_rn(b[n_ref]);
-    const __half lo = __float2half_rn(b[n_ref] - __half2float(hi));
-    __half* row = imgh + (size_t)rank * ((k_total + 16) >> 3) * (nh * 8) + (size_t)(k_total >> 3) * (nh * 8) + nl * 8;
-    row[0] = hi; row[1] = lo;
-  }
-}
-
 int tc_num_sms() {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -653,19 +622,6 @@ cudaError_t launch_tc(const NfPlan& plan, TcArgs a, long long units, cudaStream_
 }
 
 }  // namespace
-
-cudaError_t nf_launch_pack_fp16(const NfPlan& plan, int m, int j, const float* W, const float* b, void* packed, cudaStream_t st) {
-  const NfLinPlan& L = plan.mlp[m].lin[j];
-  cudaError_t e = cudaMemsetAsync((uint8_t*)packed + L.w16_off, 0, (size_t)(L.k0_pad + L.k_hidden) * L.n_pad * sizeof(__half), st);
-  if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync((uint8_t*)packed + L.w16h_off, 0, (size_t)(L.k0_pad + L.k_hidden + 16) * L.n_pad * sizeof(__half), st);
-  if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync((uint8_t*)packed + L.b16_off, 0, (size_t)L.n_pad * sizeof(float), st);
-  if (e != cudaSuccess) return e;
-  const int total = L.n * (L.k_hidden + L.k_x0);
-  k_pack_fp16<<<(total + 255) / 256, 256, 0, st>>>(plan, m, j, W, b, (uint8_t*)packed);
-  return cudaGetLastError();
-}
 
 cudaError_t nf_launch_render_tc(const NfPlan& plan, const void* packed, const float* rays, int64_t n_rays, const float* ts,
                                 int T, int64_t ts_stride, const float* noise, float* rgb, float* alpha, float* weights,

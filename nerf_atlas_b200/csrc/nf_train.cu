@@ -35,21 +35,67 @@ int tr_num_sms() {
 // =====================================================================================================================
 // transposed weight images
 // =====================================================================================================================
-// nn.Linear W[n][k] -> x0 part [n_pad/8][k0_pad][8] then hidden part [n_pad/8][256][8] (fp16; reduction dimension = the Linear's
-// OUTPUT feature in tensor order, rows = its INPUT feature in tensor order)
-__global__ void k_pack_w16t(const __grid_constant__ NfPlan plan, int m, int j, const float* __restrict__ W, uint8_t* __restrict__ packed) {
+// (layout: x0 part [n_pad/8][k0_pad][8] then hidden part [n_pad/8][256][8], fp16; reduction dimension = the Linear's OUTPUT feature in
+// tensor order, rows = its INPUT feature in tensor order -- written by k_pack_all)
+// Everything nf_pack_weights writes for the MLPs, ONE launch (blockIdx.y = Linear): the fp32 Wt[k][n_pad] + bias of the CUDA-core
+// pipeline, the fp16 UMMA-canonical images (whole and CTA-pair split, the latter with the bias K-step), the bias in tensor order
+// and the transposed images of the backward.  The caller has zeroed the region (one memset): padding rows / columns stay zero.
+// (Round 1-2 packed with 3 launches + 4 memsets per Linear: ~90 stream operations per optimiser step.)
+constexpr int PACK_MAX = 3 * NF_MAX_LIN;
+struct PackArgs { const float* W[PACK_MAX]; const float* b[PACK_MAX]; int32_t mj[PACK_MAX]; };
+__global__ void k_pack_all(const __grid_constant__ NfPlan plan, const __grid_constant__ PackArgs a, uint8_t* __restrict__ packed) {
+  const int li = blockIdx.y, m = a.mj[li] >> 4, j = a.mj[li] & 15;
   const NfLinPlan& L = plan.mlp[m].lin[j];
-  const int k_ref_total = L.k_hidden + L.k_x0;
-  __half* img_x = reinterpret_cast<__half*>(packed + L.w16t_off);
-  __half* img_h = img_x + (size_t)L.n_pad * L.k0_pad;
+  const float* __restrict__ W = a.W[li]; const float* __restrict__ b = a.b[li];
+  // a narrower reference hidden size (PosLinearView.view: 128) is zero-padded to 256: exact, the extra units stay act(0) = 0
+  const int href = plan.mlp[m].hidden_ref, kh_ref = L.k_hidden ? href : 0, n_src = L.is_out ? L.n : href;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  {
+    float* __restrict__ Wt = reinterpret_cast<float*>(packed + L.wt_off); float* __restrict__ bp = reinterpret_cast<float*>(packed + L.b_off);
+    const int kh_pad = L.k_hidden, kx = L.k_x0, n_pad = L.n_pad, total = (kh_pad + kx) * n_pad, k_src = kh_ref + kx;
+    for (int i = tid; i < total; i += nth) {
+      const int kk = i / n_pad, nn = i - kk * n_pad;
+      const int kr = kk < kh_pad ? (kk < kh_ref ? kk : -1) : kh_ref + (kk - kh_pad);     // padded hidden rows have no source column
+      Wt[i] = (nn < n_src && kr >= 0) ? W[(size_t)nn * k_src + kr] : 0.f;
+    }
+    for (int i = tid; i < n_pad; i += nth) bp[i] = i < n_src ? b[i] : 0.f;
+  }
+  if (href != NF_HIDDEN) return;                     // the tensor pipeline does not take such a model (nf_tensor_pipeline_support)
+  const int k_ref_total = L.k_hidden + L.k_x0, k_total = L.k0_pad + L.k_hidden, nh = L.n_pad >> 1;
+  __half* __restrict__ img = reinterpret_cast<__half*>(packed + L.w16_off);
+  __half* __restrict__ imgh = reinterpret_cast<__half*>(packed + L.w16h_off);
+  __half* __restrict__ img_x = reinterpret_cast<__half*>(packed + L.w16t_off);
+  __half* __restrict__ img_h = img_x + (size_t)L.n_pad * L.k0_pad;
+  float* __restrict__ b16 = reinterpret_cast<float*>(packed + L.b16_off);
   const int total = L.n * k_ref_total;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+  for (int i = tid; i < total; i += nth) {
     const int n_ref = i / k_ref_total, k_ref = i - n_ref * k_ref_total;
+    const int kx_tc = k_ref < L.k_hidden ? 0 : nf_x0_perm(plan, m, k_ref - L.k_hidden);
+    const int k_tc = k_ref < L.k_hidden ? L.k0_pad + k_ref : kx_tc;
     const int n_tc = L.is_out ? nf_out_perm(plan, m, n_ref) : n_ref;
     const __half h = __float2half_rn(W[i]);
+    img[(size_t)(k_tc >> 3) * (L.n_pad * 8) + n_tc * 8 + (k_tc & 7)] = h;
+    const int rank = n_tc / nh, nl = n_tc - rank * nh;                               // CTA-pair split along N
+    imgh[(size_t)rank * ((k_total + 16) >> 3) * (nh * 8) + (size_t)(k_tc >> 3) * (nh * 8) + nl * 8 + (k_tc & 7)] = h;
     if (k_ref < L.k_hidden) img_h[(size_t)(n_tc >> 3) * (NF_HIDDEN * 8) + k_ref * 8 + (n_tc & 7)] = h;
-    else img_x[(size_t)(n_tc >> 3) * (L.k0_pad * 8) + nf_x0_perm(plan, m, k_ref - L.k_hidden) * 8 + (n_tc & 7)] = h;
+    else img_x[(size_t)(n_tc >> 3) * (L.k0_pad * 8) + kx_tc * 8 + (n_tc & 7)] = h;
   }
+  for (int n_ref = tid; n_ref < L.n; n_ref += nth) {
+    const int n_tc = L.is_out ? nf_out_perm(plan, m, n_ref) : n_ref;
+    b16[n_tc] = b[n_ref];
+    // the bias K-step of the pair images: rows k_total (fp16 hi) and k_total + 1 (fp16 lo) against a [1, 1, 0, ...] operand
+    const int rank = n_tc / nh, nl = n_tc - rank * nh;
+    const __half hi = __float2half_rn(b[n_ref]);
+    const __half lo = __float2half_rn(b[n_ref] - __half2float(hi));
+    __half* row = imgh + (size_t)rank * ((k_total + 16) >> 3) * (nh * 8) + (size_t)(k_total >> 3) * (nh * 8) + nl * 8;
+    row[0] = hi; row[1] = lo;
+  }
+}
+// the embedding tables (one nn.Parameter per level) -> the blob, one launch (blockIdx.y = table)
+struct CopyArgs { const float4* src[48]; float4* dst[48]; };
+__global__ void k_copy_tables(const __grid_constant__ CopyArgs a, long long n4) {
+  const float4* __restrict__ s = a.src[blockIdx.y]; float4* __restrict__ d = a.dst[blockIdx.y];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) d[i] = __ldg(s + i);
 }
 
 // =====================================================================================================================
@@ -596,8 +642,11 @@ bool build_dw_prog(const NfTrainPlan& tp, int n_pairs, DwProg* P) {
 // =====================================================================================================================
 // gradients in the reference's parameter layout; hash-table scatter
 // =====================================================================================================================
-__global__ void k_unpack_grads(const __grid_constant__ NfPlan plan, int m, int j, const float* __restrict__ dwt, const float* __restrict__ db,
-                               const float* __restrict__ scale, float* __restrict__ gW, float* __restrict__ gb) {
+struct UnpackArgs { const float* dwt[PACK_MAX]; const float* db[PACK_MAX]; float* gW[PACK_MAX]; float* gb[PACK_MAX]; int32_t mj[PACK_MAX]; };
+__global__ void k_unpack_grads(const __grid_constant__ NfPlan plan, const __grid_constant__ UnpackArgs a, const float* __restrict__ scale) {
+  const int li = blockIdx.y, m = a.mj[li] >> 4, j = a.mj[li] & 15;
+  const float* __restrict__ dwt = a.dwt[li]; const float* __restrict__ db = a.db[li];
+  float* __restrict__ gW = a.gW[li]; float* __restrict__ gb = a.gb[li];
   const NfLinPlan& L = plan.mlp[m].lin[j];
   const int k_ref_total = L.k_hidden + L.k_x0, ld = L.k0_pad + L.k_hidden;
   const float invS = __ldg(scale + 1);
@@ -651,12 +700,33 @@ __global__ void k_hash_bwd_tiles(const __grid_constant__ NfPlan plan, const floa
 
 }  // namespace
 
-cudaError_t nf_launch_pack_w16t(const NfPlan& plan, int m, int j, const float* W, void* packed, cudaStream_t st) {
-  const NfLinPlan& L = plan.mlp[m].lin[j];
-  cudaError_t e = cudaMemsetAsync((uint8_t*)packed + L.w16t_off, 0, (size_t)(L.k0_pad + L.k_hidden) * L.n_pad * sizeof(__half), st);
+// params: W, b per Linear in the order of nf_pack_weights (MLP by MLP); one memset over the blob's MLP region + one launch
+cudaError_t nf_launch_pack_all(const NfPlan& plan, const float* const* params, void* packed, cudaStream_t st) {
+  PackArgs a{}; int n = 0, max_total = 0;
+  for (int m = 0; m < plan.n_mlps; ++m)
+    for (int j = 0; j < plan.mlp[m].n_lin; ++j, ++n) {
+      if (n >= PACK_MAX) return cudaErrorInvalidValue;
+      a.W[n] = params[2 * n]; a.b[n] = params[2 * n + 1]; a.mj[n] = m * 16 + j;
+      const NfLinPlan& L = plan.mlp[m].lin[j];
+      const int total = (L.k_hidden + L.k_x0) * L.n_pad;
+      max_total = total > max_total ? total : max_total;
+    }
+  const int64_t lo = plan.mlp[0].lin[0].wt_off;                 // the Linears' images are the tail of the blob (nf_build_plan)
+  cudaError_t e = cudaMemsetAsync((uint8_t*)packed + lo, 0, (size_t)(plan.total_bytes - lo), st);
   if (e != cudaSuccess) return e;
-  const int total = L.n * (L.k_hidden + L.k_x0);
-  k_pack_w16t<<<(total + 255) / 256, 256, 0, st>>>(plan, m, j, W, (uint8_t*)packed);
+  const int gx = (max_total + 255) / 256;
+  k_pack_all<<<dim3(gx < 96 ? gx : 96, n), 256, 0, st>>>(plan, a, (uint8_t*)packed);
+  return cudaGetLastError();
+}
+// n tables of `bytes` each (a multiple of 16): src[i] -> dst[i]
+cudaError_t nf_launch_copy_tables(const float* const* src, float* const* dst, int n, size_t bytes, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  if (n > 48 || (bytes & 15)) return cudaErrorInvalidValue;
+  CopyArgs a{};
+  for (int i = 0; i < n; ++i) { a.src[i] = (const float4*)src[i]; a.dst[i] = (float4*)dst[i]; }
+  const long long n4 = (long long)(bytes >> 4);
+  const long long want = (n4 + 255) / 256;
+  k_copy_tables<<<dim3((unsigned)(want < 64 ? want : 64), n), 256, 0, st>>>(a, n4);
   return cudaGetLastError();
 }
 
@@ -704,16 +774,22 @@ cudaError_t nf_launch_render_backward(const NfPlan& plan, const NfTrainPlan& tp,
   }
   // 5. reference layout
   int pi = 0;
-  for (int m = 0; m < plan.n_mlps; ++m)
-    for (int j = 0; j < plan.mlp[m].n_lin; ++j) {
-      float* gW = grads[pi++]; float* gb = grads[pi++];
-      if (!gW && !gb) continue;
-      int li = -1;
-      for (int k = 0; k < tp.n_lin; ++k) if (tp.lin[k].m == m && tp.lin[k].j == j) li = k;
-      const NfLinPlan& L = plan.mlp[m].lin[j];
-      const int total = L.n * (L.k_hidden + L.k_x0) + L.n;
-      k_unpack_grads<<<(total + 255) / 256, 256, 0, st>>>(plan, m, j, (const float*)(ws + tp.lin[li].dw_off), (const float*)(ws + tp.lin[li].db_off), scale, gW, gb);
-    }
+  {
+    UnpackArgs ua{}; int nu = 0, max_total = 0;
+    for (int m = 0; m < plan.n_mlps; ++m)
+      for (int j = 0; j < plan.mlp[m].n_lin; ++j) {
+        float* gW = grads[pi++]; float* gb = grads[pi++];
+        if (!gW && !gb) continue;
+        int li = -1;
+        for (int k = 0; k < tp.n_lin; ++k) if (tp.lin[k].m == m && tp.lin[k].j == j) li = k;
+        const NfLinPlan& L = plan.mlp[m].lin[j];
+        const int total = L.n * (L.k_hidden + L.k_x0) + L.n;
+        max_total = total > max_total ? total : max_total;
+        ua.dwt[nu] = (const float*)(ws + tp.lin[li].dw_off); ua.db[nu] = (const float*)(ws + tp.lin[li].db_off);
+        ua.gW[nu] = gW; ua.gb[nu] = gb; ua.mj[nu] = m * 16 + j; ++nu;
+      }
+    if (nu > 0) k_unpack_grads<<<dim3((max_total + 255) / 256 < 64 ? (max_total + 255) / 256 : 64, nu), 256, 0, st>>>(plan, ua, scale);
+  }
   if (plan.enc == NF_ENC_HASH) {
     HashGradPtrs hp{};
     bool any = false;

@@ -1,1 +1,2 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r02b_bench_2gpu.json 2> gpurun_out/r02b_bench_2gpu.err; tail -c 1500 gpurun_out/r02b_bench_2gpu.json; tail -3 gpurun_out/r02b_bench_2gpu.err
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-torch-eager-gpu 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['train'])"

@@ -692,6 +692,21 @@ def test_fused_adam_matches_torch_adam():
     oa.step(); ob.step(); sched_a.step(); sched_b.step()
   for x, y in zip(pa, pb):
     assert float((x.detach() - y.detach()).abs().max()) <= 1e-6 * max(float(y.detach().abs().max()), 1.0), x.shape
+  # the one-tensor entry (nf_adam_step) and the one-launch entry FusedAdam uses (nf_adam_step_multi) are the same update, bit for bit
+  import ctypes as C
+  from nerf_atlas_b200 import _lib
+  p1 = torch.randn(1003, generator=g).to(DEV); p2 = p1.clone()
+  gr = torch.randn(1003, generator=g).to(DEV)
+  m1, v1, m2, v2 = (torch.zeros_like(p1) for _ in range(4))
+  st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+  for step in (1, 2, 3):
+    _lib.check(_lib.lib().nf_adam_step(C.c_void_p(p1.data_ptr()), C.c_void_p(gr.data_ptr()), C.c_void_p(m1.data_ptr()), C.c_void_p(v1.data_ptr()),
+                                       1003, 5e-4, 0.9, 0.999, 1e-7, 1e-5, step, st), "nf_adam_step")
+    one = lambda t: (C.c_void_p * 1)(t.data_ptr())
+    _lib.check(_lib.lib().nf_adam_step_multi(1, one(p2), one(gr), one(m2), one(v2), (C.c_int64 * 1)(1003), 5e-4, 0.9, 0.999, 1e-7, 1e-5, step, st),
+               "nf_adam_step_multi")
+  torch.cuda.synchronize()
+  assert torch.equal(p1, p2) and torch.equal(m1, m2) and torch.equal(v1, v2)
 
 
 def test_fused_adam_step_is_seen_by_the_next_render(P):
