@@ -162,7 +162,7 @@ def train_leg(O, dev, world, rank, steps, warmup, barrier):
           "allreduce_ms_per_step": ar if world > 1 else 0.0, "allreduce_bytes": 4 * n_par if world > 1 else 0,
           "final_loss_per_ray": float(loss) / TRAIN_RAYS,
           "what": "native training step: k_render_tc3<TRAIN> + nf_render_backward (k_composite_bwd, k_bwd_chain, k_bwd_dw, k_unpack_grads, "
-                  "k_hash_bwd_tiles) + " + ("ncclAllReduce(flat fp32 gradient) + " if world > 1 else "") + "nf_adam_step"}
+                  "k_hash_bwd_tiles) + " + ("ncclAllReduce(flat fp32 gradient) + " if world > 1 else "") + "nf_adam_step_multi"}
 
 
 def strong_leg(eng, O, dev, world, rank, ts, steps, warmup, barrier):
