@@ -8,8 +8,8 @@ import os, subprocess, sys, hashlib
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-EXPERIMENTS = bool(os.environ.get("NF_EXPERIMENTS"))   # A/B-timing build: superseded pipelines + NF_TC_* environment switches (libnerf_b200_exp.so)
-SOURCES = ["nf_api.cu", "nf_fp32.cu", "nf_tc.cu", "nf_tc3.cu", "nf_bwd.cu", "nf_train.cu", "nf_march.cu"] + (["nf_tc2.cu"] if EXPERIMENTS else [])
+EXPERIMENTS = bool(os.environ.get("NF_EXPERIMENTS"))   # A/B-timing build: the NF_TC_* environment switches, incl. the single-CTA pipeline as the render path (libnerf_b200_exp.so)
+SOURCES = ["nf_api.cu", "nf_fp32.cu", "nf_tc.cu", "nf_tc3.cu", "nf_bwd.cu", "nf_train.cu", "nf_march.cu"]
 HEADERS = ["nf_common.cuh", "nf_kernels.h", "nf_tc_ptx.cuh", os.path.join("..", "..", "include", "nerf_b200.h")]
 TRACE = bool(os.environ.get("NF_TC_TRACE"))     # debug build: clock64 timeline of one tile (profiles/)
 STATS = bool(os.environ.get("NF_TC_STATS"))     # debug build: time-in-state counters of the staggered pipeline (nf_tc3.cu)
@@ -23,7 +23,7 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
 
 def _digest() -> str:
   h = hashlib.sha256()
-  for f in sorted(set(SOURCES + ["nf_tc2.cu"])) + HEADERS:
+  for f in sorted(SOURCES) + HEADERS:
     with open(os.path.join(CSRC, f), "rb") as fh: h.update(fh.read())
   h.update(" ".join(FLAGS).encode())
   return h.hexdigest()

@@ -187,7 +187,7 @@ int nf_render_forward_aux(const nf_model_desc* desc, const void* packed, const f
   else if (precision == NF_PREC_FP16_TC) {
     // The staggered paired pipeline (nf_tc3.cu) is the product path; the single-CTA pipeline (nf_tc.cu) takes the few
     // descriptors it cannot (odd hash levels, intermediate % 16 != 0).  Only NF_EXPERIMENTS builds (A/B timing,
-    // profiles/perf_variants.py) read NF_TC_PIPE: 3 = staggered, 2 = lockstep paired (nf_tc2.cu), 1 = single CTA.
+    // profiles/perf_variants.py) read NF_TC_PIPE: 3 = staggered, 1 = single CTA.
     int pipe = 3;
 #ifdef NF_EXPERIMENTS
     if (const char* env = getenv("NF_TC_PIPE")) pipe = atoi(env);
@@ -200,11 +200,7 @@ int nf_render_forward_aux(const nf_model_desc* desc, const void* packed, const f
     }
     if (pipe == 3 && nf_tc3_unsupported(p)) pipe = 1;
     cudaStream_t st = (cudaStream_t)stream;
-#ifdef NF_EXPERIMENTS
-    if (pipe == 2 && nf_tc2_unsupported(p)) pipe = 1;
-    if (pipe == 2) e = nf_launch_render_tc2(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, rgb_out, alpha_out, weights_out, st);
-    else
-#endif
+    if (pipe != 3) pipe = 1;
     if (train && pipe != 3) return fail(NF_E_UNSUPPORTED, "training forward: the staggered pipeline only");
     const bool want_aux = aux && (aux->pts || aux->bg_rand || side);
     if (want_aux && pipe != 3) return fail(NF_E_UNSUPPORTED, "explicit pts / random background / side channels: staggered tensor pipeline or NF_PREC_FP32 only");

@@ -31,11 +31,6 @@ cudaError_t nf_launch_hash_encode(const NfPlan& plan, const void* packed, const 
 cudaError_t nf_launch_composite(const NfPlan& plan, const void* packed, const float* sigma_raw, const float* feats, const float* rays, int64_t n_rays,
                                 const float* ts, int T, int64_t ts_stride, float* rgb, float* alpha, float* weights, cudaStream_t st);
 cudaError_t nf_launch_sample_pdf(const float* ts, int T, const float* weights, int64_t n_rays, const float* u, int nf, float* out, cudaStream_t st);
-// paired (cta_group::2, two tiles in flight) tensor pipeline, nf_tc2.cu
-const char* nf_tc2_unsupported(const NfPlan& plan);
-cudaError_t nf_launch_render_tc2(const NfPlan& plan, const void* packed, const float* rays, int64_t n_rays, const float* ts,
-                                 int T, int64_t ts_stride, const float* noise, float* rgb, float* alpha, float* weights,
-                                 cudaStream_t st);
 // staggered paired pipeline (slot 1 half a round behind slot 0, biases in shared memory), nf_tc3.cu
 const char* nf_tc3_unsupported(const NfPlan& plan);
 cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const float* rays, int64_t n_rays, const float* ts,

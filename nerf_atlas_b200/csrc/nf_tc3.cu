@@ -1,10 +1,10 @@
 // nf_tc3.cu -- the STAGGERED form of the paired (cta_group::2) tensor-core render pipeline.
 //
-// Same data path as nf_tc2.cu (CTA pair, two 128-sample tiles -- "slots" -- in flight per CTA, M = 256 MMAs issued by one
+// Data path (that of the lockstep paired kernel of round 1, nf_tc2.cu, since removed): CTA pair, two 128-sample tiles -- "slots" -- in flight per CTA, M = 256 MMAs issued by one
 // thread of the leader, fp16 operands in the UMMA canonical no-swizzle K-major layout, 3-stage bulk-copy weight ring, the
 // epilogue warps write the next layer's A operand in place).  What changes is the schedule (profiles/r01_trace_paired_*):
 //
-//  * In nf_tc2 both slots walk the Linears in lockstep, so at every tile boundary BOTH slots sit in "composite the old tile,
+//  * In the lockstep kernel both slots walk the Linears in lockstep, so at every tile boundary BOTH slots sit in "composite the old tile,
 //    hash-encode the new one" while the tensor pipe has nothing to do: 22 % of a round.  Here slot 1 runs half a round
 //    (n_lin / 2 Linears) behind slot 0: while one slot is at its tile boundary the other is in the middle of its MLPs and
 //    keeps the tensor pipe fed, and the LeakyReLU (density MLP) and sin (View head) epilogues alternate instead of bunching.
@@ -21,7 +21,7 @@
 // kernel runs ONE tile in flight per CTA ("single" mode) and keeps x0 in the idle slot's 64 KB activation buffer (the Fourier-
 // encoded SDF MLP's 272 columns spill over into the two unused 20 KB x0 buffers that follow it in shared memory).
 //
-// Warp roles as in nf_tc2.cu: 0-15 encode/epilogue (TMEM lane quarter q = warp % 4, column quarter cq = warp / 4), 16/18/19
+// Warp roles: 0-15 encode/epilogue (TMEM lane quarter q = warp % 4, column quarter cq = warp / 4), 16/18/19
 // weight producers (one ring stage each), 17 the MMA issuer (leader CTA only).
 #include <cstdio>
 #include <cstdlib>

@@ -12,12 +12,10 @@ import nerf_atlas_b200 as N
 from oracle import nerf_oracle as O   # synthetic inputs only
 
 VARIANTS = [
-  ("pipe2_lockstep", {"NF_TC_PIPE": "2"}),
   ("pipe3_ring3x16", {"NF_TC_PIPE": "3", "NF_TC_RING": "3"}),
   ("pipe3_ring3x16_24_epilogue_warps", {"NF_TC_PIPE": "3", "NF_TC_RING": "3", "NF_TC_EPIW": "24"}),
   ("pipe3_ring3x16_24_epilogue_warps_plain_sin", {"NF_TC_PIPE": "3", "NF_TC_RING": "3", "NF_TC_EPIW": "24", "NF_TC_DEBUG": "2048"}),
   ("pipe3_ring3x16_plain_sin_epilogue", {"NF_TC_PIPE": "3", "NF_TC_RING": "3", "NF_TC_DEBUG": "2048"}),
-  ("pipe3_ring6x8", {"NF_TC_PIPE": "3", "NF_TC_RING": "6"}),
   ("pipe1_single_cta", {"NF_TC_PIPE": "1"}),
 ]
 def main():

@@ -186,12 +186,11 @@ def test_tiny_nerf_vs_oracle():
     assert np.abs(rgb.cpu().numpy() - r["out"].numpy()).max() <= tol, precision
 
 # ---------------------------------------------------------------- every tensor pipeline / ring geometry
-@pytest.mark.parametrize("env", [{}, {"NF_TC_PIPE": "3", "NF_TC_RING": "6"}, {"NF_TC_PIPE": "3", "NF_TC_EPIW": "24"}, {"NF_TC_PIPE": "2"}, {"NF_TC_PIPE": "1"}],
-                         ids=["product", "pipe3_ring6", "pipe3_epiw24", "pipe2", "pipe1"])
+@pytest.mark.parametrize("env", [{}, {"NF_TC_PIPE": "3", "NF_TC_EPIW": "24"}, {"NF_TC_PIPE": "1"}], ids=["product", "pipe3_epiw24", "pipe1"])
 def test_tensor_pipeline_variants_vs_oracle(P, env, monkeypatch):
   """The product build runs the staggered paired pipeline and reads no environment variable.  An NF_EXPERIMENTS build
-  (NF_LIB=libnerf_b200_exp.so) also selects: ring 6x8 KB, 24 epilogue warps, 2 = lockstep paired pipeline, 1 = single-CTA
-  pipeline.  All must meet the same bars, incl. rays spanning two tiles (T = 256), ragged tiles (T = 100), several rays per
+  (NF_LIB=libnerf_b200_exp.so) also selects: 24 epilogue warps, 1 = single-CTA pipeline (the lockstep paired pipeline and the
+  6-stage ring of round 1 are gone).  All must meet the same bars, incl. rays spanning two tiles (T = 256), ragged tiles (T = 100), several rays per
   tile (T = 32), noise, per-ray ts and the white background."""
   import nerf_atlas_b200 as N
   if env and not N._lib.has_experiments(): pytest.skip("timing-experiment variants exist only in NF_EXPERIMENTS builds")
@@ -402,7 +401,7 @@ def test_dnerf_direct_matches_reference_golden():
   # the older tensor pipelines do not take the three-MLP chain: loud refusal, no fallback to them
   canon.precision = "fp16"
   import os
-  os.environ["NF_TC_PIPE"] = "2"
+  os.environ["NF_TC_PIPE"] = "1"
   try:
     with torch.no_grad(): o2 = m((rays.to(DEV), torch.from_numpy(fx["times"]).to(DEV)))     # DYN always runs on the staggered pipeline
   finally: os.environ.pop("NF_TC_PIPE")
