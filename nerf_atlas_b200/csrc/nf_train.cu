@@ -98,6 +98,9 @@ __global__ void k_copy_tables(const __grid_constant__ CopyArgs a, long long n4) 
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) d[i] = __ldg(s + i);
 }
 
+#ifndef NF_BWD_SIDE_STREAM
+#define NF_BWD_SIDE_STREAM 1
+#endif
 // =====================================================================================================================
 // loss scale
 // =====================================================================================================================
@@ -732,6 +735,22 @@ cudaError_t nf_launch_copy_tables(const float* const* src, float* const* dst, in
 
 // grads: one pointer per parameter in nf_pack_weights order (nullable entries are skipped): W, b per Linear (MLP order), then
 // the hash tables.  Every non-null gradient is OVERWRITTEN.
+// The hash-table scatter (atomic-bound, ~0.3 ms, little HBM traffic) and the dW pass (HBM-bound, ~1.1 ms) both depend only on the
+// chain kernel: the scatter runs on a side stream forked from / joined to the caller's stream (events; legal under graph capture),
+// next to the dW pass.  One side stream and two events per host thread and device, created on first use.
+struct BwSide { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+static BwSide* bw_side() {
+  thread_local BwSide side[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  BwSide& b = side[dev];
+  if (!b.s) {
+    if (cudaStreamCreateWithFlags(&b.s, cudaStreamNonBlocking) != cudaSuccess) { b.s = nullptr; return nullptr; }
+    if (cudaEventCreateWithFlags(&b.fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&b.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  }
+  return &b;
+}
+
 cudaError_t nf_launch_render_backward(const NfPlan& plan, const NfTrainPlan& tp, const void* packed, void* ws_, const float* rays,
                                       const float* ts, int64_t ts_stride, const float* d_rgb, float* const* grads, cudaStream_t st) {
   if (nf_train_unsupported(plan)) return cudaErrorNotSupported;
@@ -763,6 +782,33 @@ cudaError_t nf_launch_render_backward(const NfPlan& plan, const NfTrainPlan& tp,
     k_bwd_chain<<<grid, BW_THREADS, sizeof(BwSmem), st>>>(prog, a);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
+  // 3b. fork: the hash-table scatter next to the dW pass
+  BwSide* side = NF_BWD_SIDE_STREAM ? bw_side() : nullptr;
+  cudaStream_t hs = st;
+  if (side && plan.enc == NF_ENC_HASH) {
+    if ((e = cudaEventRecord(side->fork, st)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(side->s, side->fork, 0)) != cudaSuccess) return e;
+    hs = side->s;
+  }
+  if (plan.enc == NF_ENC_HASH) {
+    int pi_h = 0;
+    for (int m = 0; m < plan.n_mlps; ++m) pi_h += 2 * plan.mlp[m].n_lin;
+    HashGradPtrs hp{};
+    bool any = false;
+    const size_t per = (size_t)(plan.hash_mask + 1) * 4 * sizeof(float);
+    for (int l = 0; l < plan.hash_levels; ++l) {
+      hp.t[l] = grads[pi_h++];
+      if (hp.t[l]) { any = true; if ((e = cudaMemsetAsync(hp.t[l], 0, per, hs)) != cudaSuccess) return e; }
+    }
+    if (any) {
+      const long long total = tp.n_tiles * NF_TC_ROWS * plan.hash_levels;
+      const long long want = (total + 255) / 256;
+      const int grid = (int)(want < (long long)sms * 16 ? want : (long long)sms * 16);
+      k_hash_bwd_tiles<<<grid, 256, 0, hs>>>(plan, rays, tp.n_rays, ts, tp.T, ts_stride, tp.n_tiles, tp.tpr, dx0, hp);
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    if (hs != st && (e = cudaEventRecord(side->join, hs)) != cudaSuccess) return e;
+  }
   // 4. dW / db
   {
     DwProg prog;
@@ -790,20 +836,7 @@ cudaError_t nf_launch_render_backward(const NfPlan& plan, const NfTrainPlan& tp,
       }
     if (nu > 0) k_unpack_grads<<<dim3((max_total + 255) / 256 < 64 ? (max_total + 255) / 256 : 64, nu), 256, 0, st>>>(plan, ua, scale);
   }
-  if (plan.enc == NF_ENC_HASH) {
-    HashGradPtrs hp{};
-    bool any = false;
-    const size_t per = (size_t)(plan.hash_mask + 1) * 4 * sizeof(float);
-    for (int l = 0; l < plan.hash_levels; ++l) {
-      hp.t[l] = grads[pi++];
-      if (hp.t[l]) { any = true; if ((e = cudaMemsetAsync(hp.t[l], 0, per, st)) != cudaSuccess) return e; }
-    }
-    if (any) {
-      const long long total = tp.n_tiles * NF_TC_ROWS * plan.hash_levels;
-      const long long want = (total + 255) / 256;
-      const int grid = (int)(want < (long long)sms * 16 ? want : (long long)sms * 16);
-      k_hash_bwd_tiles<<<grid, 256, 0, st>>>(plan, rays, tp.n_rays, ts, tp.T, ts_stride, tp.n_tiles, tp.tpr, dx0, hp);
-    }
-  }
+  // join
+  if (hs != st && (e = cudaStreamWaitEvent(st, side->join, 0)) != cudaSuccess) return e;
   return cudaGetLastError();
 }
