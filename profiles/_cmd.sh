@@ -1,2 +1,5 @@
-timeout 900 python -m pytest tests/test_gpu_training.py -m gpu -x -q 2>&1 | tail -2
-for lib in libnerf_b200.so libnerf_b200_noside.so libnerf_b200.so libnerf_b200_noside.so; do NF_LIB=$lib python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-torch-eager-gpu 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$lib', d['train']['ms_per_step'])"; done
+mkdir -p gpurun_out
+for c in 2 3 4 5; do
+  ncu --metrics sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,gpu__time_duration.sum,sm__cycles_elapsed.avg,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:k_render_tc3 -s 3 -c 2 --csv python bench.py --config $c --steps 2 --warmup 3 2>/dev/null | grep -E '^"[0-9]' | awk -F'","' -v c=$c '{gsub(/"/,"",$NF); print "config" c "," $5 "," $(NF-2) "," $(NF-1) "," $NF}' 
+done > gpurun_out/r02b_configs_ncu.csv
+cat gpurun_out/r02b_configs_ncu.csv | cut -c1-220
