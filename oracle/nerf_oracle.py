@@ -504,10 +504,79 @@ def sphere_march(params: Params, r_o: Tensor, r_d: Tensor, *, sdf_kind: str = "s
   return r_o + r_d * curr_dist[:, None], hits, curr_dist
 
 
+def throughput_with_sign_change(params: Params, r_o: Tensor, r_d: Tensor, *, near: float, far: float, batch_size: int = 128, jitter: float = 0.0,
+                                sdf_kind: str = "siren", bound_rad: float = -1.0, prefix: str = "underlying", quant=None):
+  """march.throughput_with_sign_change (reference src/march.py:78-110) on flat rays [R,3]: the smallest SDF value of
+  batch_size + 1 equidistant samples and the sample indices around the first sign change, bug for bug: the first sample is taken at
+  `r_o + near` (the scalar added to every coordinate, march.py:90), and the indices become distances WITHOUT the near offset
+  (march.py:105-106; -1, "no crossing", becomes -step).  `jitter` = the reference's `random.random()` draw (march.py:86).
+  Returns (tput[R], best_pos[R,3], last_pos[R,1], first_neg[R,1], idxs[R], first_neg_idx[R])."""
+  f = lambda p: sdf_net(params, p, sdf_kind, prefix, bound_rad, quant)
+  max_t = far - near + jitter * (2 / batch_size)
+  step = max_t / batch_size
+  sd = f(r_o + near)[..., 0]
+  curr_min = sd
+  idxs = torch.zeros_like(sd, dtype=torch.long)
+  last_pos = torch.full_like(sd, -1, dtype=torch.long)
+  first_neg = torch.full_like(sd, -1, dtype=torch.long)
+  for i in range(batch_size):
+    t = near + step * (i + 1)
+    sd = f(r_o + t * r_d)[..., 0]
+    idxs = torch.where(sd < curr_min, i + 1, idxs)
+    curr_min = torch.minimum(curr_min, sd)
+    mask = (first_neg == -1) & (sd < 0)
+    last_pos = torch.where(mask, i, last_pos)
+    first_neg = torch.where(mask, i + 1, first_neg)
+  best_pos = r_o + (near + idxs.unsqueeze(-1) * step) * r_d
+  val = f(best_pos)
+  return val[..., 0], best_pos, last_pos.unsqueeze(-1) * step, first_neg.unsqueeze(-1) * step, idxs, first_neg
+
+
+def bisection(params: Params, r_o: Tensor, r_d: Tensor, near: Tensor, far: Tensor, *, iters: int = 32, eps: float = 1e-6,
+              sdf_kind: str = "siren", bound_rad: float = -1.0, prefix: str = "underlying", quant=None) -> Tensor:
+  """march.bisection (reference src/march.py:147-180): near / far [R,1] bracket the first sign change; rays without a bracket
+  (sdf(low) <= 0, sdf(high) >= 0 or an empty interval) keep the midpoint of what they were given."""
+  f = lambda p: sdf_net(params, p, sdf_kind, prefix, bound_rad, quant)
+  low, high = near.clone(), far.clone()
+  sdf_low = f(r_o + low * r_d)[..., 0, None]
+  sdf_high = f(r_o + high * r_d)[..., 0, None]
+  todo = ((high - low) > eps) & (sdf_low > 0) & (sdf_high < 0) & (high > low)
+  z_pred = (low + high) / 2
+  for _ in range(iters):
+    if not bool(todo.any()): break
+    sdf_mid = f(r_o + z_pred * r_d)[..., 0, None]
+    low_mask = (sdf_mid > 0) & todo
+    low[low_mask] = z_pred[low_mask]; sdf_low[low_mask] = sdf_mid[low_mask]
+    high_mask = (sdf_mid < 0) & todo
+    high[high_mask] = z_pred[high_mask]; sdf_high[high_mask] = sdf_mid[high_mask]
+    z_pred = (low + high) / 2
+    todo = todo & ((high - low) > eps) & (sdf_low > 0) & (sdf_high < 0) & (high > low)
+  return r_o + z_pred * r_d
+
+
+def bisect(params: Params, r_o: Tensor, r_d: Tensor, *, iters: int = 128, near: float = 0, far: float = 1, jitter: float = 0.0,
+           sdf_kind: str = "siren", bound_rad: float = -1.0, quant=None):
+  """march.bisect (reference src/march.py:63-75; `--sdf-isect-kind bisect`): (pts, hits, best_pos, tput)."""
+  tput, best_pos, last_pos, first_neg, _, _ = throughput_with_sign_change(params, r_o, r_d, near=near, far=far, batch_size=iters, jitter=jitter,
+                                                                          sdf_kind=sdf_kind, bound_rad=bound_rad, quant=quant)
+  pts = bisection(params, r_o, r_d, last_pos, first_neg, iters=min(32, iters), sdf_kind=sdf_kind, bound_rad=bound_rad, quant=quant)
+  return pts, tput < 0, best_pos, tput
+
+
 def sdf_forward(params: Params, rays: Tensor, *, sdf_kind: str = "siren", near: float = 0, far: float = 1, iters: int = 192,
-                sigmoid: str = "upshifted", bound_rad: float = -1.0, quant=None) -> Dict[str, Tensor]:
-  """SDF.forward in eval mode (reference src/sdf.py:137-156): rgb[hit] = act(View([pts, elaz(r_d), latent])), black elsewhere."""
+                sigmoid: str = "upshifted", bound_rad: float = -1.0, quant=None, isect: str = "sphere", jitter: float = 0.0) -> Dict[str, Tensor]:
+  """SDF.forward in eval mode (reference src/sdf.py:137-156): rgb[hit] = act(View([pts, elaz(r_d), latent])), black elsewhere.
+  isect = "sphere" (march.sphere_march) or "bisect" (march.bisect; `t` is then absent and `tput`, `best_pos` are returned)."""
   r_o, r_d = rays.reshape(-1, 6).split([3, 3], dim=-1)
+  if isect == "bisect":
+    pts, hit, best_pos, tput = bisect(params, r_o, r_d, iters=iters, near=near, far=far, jitter=jitter, sdf_kind=sdf_kind, bound_rad=bound_rad, quant=quant)
+    out = torch.zeros_like(r_d)
+    if bool(hit.any()):
+      latent = sdf_net(params, pts[hit], sdf_kind, "underlying", bound_rad, quant)[..., 1:]
+      x0 = torch.cat([pts[hit], dir_to_elev_azim(r_d[hit]), latent], dim=-1)
+      out[hit] = SIGMOIDS[sigmoid](skip_mlp(x0, params, "refl.mlp", "sin", quant=quant))
+    B = rays.shape[:-1]
+    return dict(out=out.reshape(B + (3,)), hit=hit.reshape(B), pts=pts.reshape(B + (3,)), tput=tput.reshape(B), best_pos=best_pos.reshape(B + (3,)))
   pts, hit, t = sphere_march(params, r_o, r_d, sdf_kind=sdf_kind, iters=iters, near=near, far=far, bound_rad=bound_rad, quant=quant)
   out = torch.zeros_like(r_d)
   if bool(hit.any()):

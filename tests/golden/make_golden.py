@@ -278,7 +278,7 @@ def case_trained(name, seed=1337, iters=400, T=64, crop=24, views=6, lr=2e-3):
   print(name, "final loss", float(loss), "max|h|", hmax[0], "psnr vs target", float(-10 * torch.log10(torch.nn.functional.mse_loss(out, analytic_scene(rays)))),
         "table rows stored", sum(len(fx[k]) for k in fx if k.startswith("rows.")))
 
-def case_sdf(name, seed=23, sdf_kind="siren", size=16, iters_fit=500, bound_rad=-1.0):
+def case_sdf(name, seed=23, sdf_kind="siren", size=16, iters_fit=500, bound_rad=-1.0, isect="sphere"):
   """The reference's surface renderer `sdf.SDF` (src/sdf.py:86-156) with the sphere-march intersection (src/march.py:27-47) and
   a View head, eval mode (192 iterations).  The SDF network is first fitted to a sphere of radius 1 with the reference's own
   modules (as `SDFModel.set_to_sphere` does, src/sdf.py:47-60), then ALL parameters are rounded to fp16 so that the fixture
@@ -300,16 +300,30 @@ def case_sdf(name, seed=23, sdf_kind="siren", size=16, iters_fit=500, bound_rad=
   orig_fwd = refl.View.forward
   refl.View.forward = lambda self, x, view, normal=None, light=None, latent=None, mask=None: orig_fwd(self, x, view, normal, light, latent)
   head = refl.View(latent_size=64, act="upshifted", out_features=3)
-  s = rsdf.SDF(wrapped, head, isect=march.sphere_march, t_near=2.0, t_far=6.0).eval()
+  s = rsdf.SDF(wrapped, head, isect=march.load_intersection_kind(isect), t_near=2.0, t_far=6.0).eval()
   with torch.no_grad():
     for p in s.parameters():
       if p.dtype.is_floating_point: p.copy_(p.to(torch.float16).to(torch.float32))
   rays = O.make_rays(2, size, size, size=size, seed=seed)
   rays = torch.cat([rays[..., :3], torch.nn.functional.normalize(rays[..., 3:], dim=-1)], dim=-1)
-  with torch.no_grad():
+  if isect == "bisect":
+    # march.bisect (src/march.py:63-75) = throughput_with_sign_change (78-110; it draws random.random() once, march.py:86: the draw is
+    # pinned with random.seed and stored) + bisection (147-180)
+    import random
+    random.seed(seed); jitter = random.random()
+    with torch.no_grad():
+      random.seed(seed); out = s(rays)
+      random.seed(seed); pts, hit, best_pos, tput = march.bisect(s.underlying, rays[..., :3], rays[..., 3:], iters=192, near=2.0, far=6.0)
+      random.seed(seed); _, _, last_pos, first_neg = march.throughput_with_sign_change(s.underlying, rays[..., :3], rays[..., 3:], near=2.0, far=6.0, batch_size=192)
+    fx = dict(kind="sdf", sdf_kind=sdf_kind, seed=seed, size=size, near=2.0, far=6.0, iters=192, sigmoid="upshifted", bound_rad=bound_rad, isect=isect,
+              jitter=jitter, rays=rays.numpy(), out=out.numpy(), hit=hit.numpy(), pts=pts.numpy(), best_pos=best_pos.numpy(), tput=tput.squeeze(-1).numpy(),
+              last_pos=last_pos.squeeze(-1).numpy(), first_neg=first_neg.squeeze(-1).numpy())
+    t = tput
+  else:
+   with torch.no_grad():
     out = s(rays)
     pts, hit, t, _ = march.sphere_march(s.underlying, rays[..., :3], rays[..., 3:], iters=192, near=2.0, far=6.0)
-  fx = dict(kind="sdf", sdf_kind=sdf_kind, seed=seed, size=size, near=2.0, far=6.0, iters=192, sigmoid="upshifted", bound_rad=bound_rad,
+   fx = dict(kind="sdf", sdf_kind=sdf_kind, seed=seed, size=size, near=2.0, far=6.0, iters=192, sigmoid="upshifted", bound_rad=bound_rad,
             rays=rays.numpy(), out=out.numpy(), hit=hit.numpy(), t=t.squeeze(-1).numpy(), pts=pts.numpy())
   for k, v in s.state_dict().items():
     if v.dtype.is_floating_point and v.numel(): fx["param16." + k.replace("underlying.inner.", "underlying.")] = v.to(torch.float16).numpy()
@@ -320,6 +334,9 @@ if __name__ == "__main__":
   check_rays()
   if "--sdf" in sys.argv:
     case_sdf("sdf_siren_march")
+    sys.exit(0)
+  if "--sdf-bisect" in sys.argv:
+    case_sdf("sdf_siren_bisect", size=12, isect="bisect")
     sys.exit(0)
   if "--trained" in sys.argv:
     torch.set_num_threads(int(os.environ.get("GOLDEN_THREADS", "8")))
@@ -357,4 +374,5 @@ if __name__ == "__main__":
   case_dtu_rays("dtu_rays")
   case_trained("plain_trained_t64")
   case_sdf("sdf_siren_march")
+  case_sdf("sdf_siren_bisect", size=12, isect="bisect")
   case_plain("plain_poslinview_t16", seed=83, B=1, H=4, W=5, T=16, sigma_gain=20.0, top=398, left=397, stages=False, refl_kind="pos-linear-view")

@@ -262,6 +262,27 @@ def test_sdf_surface_oracle_matches_reference(golden_dir):
   assert 0.2 < fx["hit"].mean() < 0.8 and np.abs(fx["out"][~fx["hit"]]).max() == 0
 
 
+def test_sdf_bisect_oracle_matches_reference(golden_dir):
+  """f-4: march.bisect = throughput_with_sign_change + bisection (reference src/march.py:63-110,147-180) behind sdf.SDF.forward,
+  restated bug for bug (first sample at r_o + near, index -> distance without the near offset); the reference's random.random()
+  draw is stored in the golden."""
+  from helpers import sdf_params
+  fx = load(golden_dir, "sdf_siren_bisect")
+  P = sdf_params(fx)
+  rays = torch.from_numpy(fx["rays"])
+  flat = rays.reshape(-1, 6)
+  with torch.no_grad():
+    res = O.sdf_forward(P, rays, sdf_kind=str(fx["sdf_kind"]), near=float(fx["near"]), far=float(fx["far"]), iters=int(fx["iters"]), sigmoid=str(fx["sigmoid"]),
+                        isect="bisect", jitter=float(fx["jitter"]))
+    tput, best, last_pos, first_neg, _, _ = O.throughput_with_sign_change(P, flat[:, :3], flat[:, 3:], near=float(fx["near"]), far=float(fx["far"]),
+                                                                          batch_size=int(fx["iters"]), jitter=float(fx["jitter"]))
+  assert np.array_equal(last_pos.reshape(fx["last_pos"].shape).numpy(), fx["last_pos"]) and np.array_equal(first_neg.reshape(fx["first_neg"].shape).numpy(), fx["first_neg"])
+  assert np.array_equal(res["hit"].numpy(), fx["hit"]) and np.array_equal(res["tput"].numpy(), fx["tput"])
+  assert np.array_equal(res["pts"].numpy(), fx["pts"]) and np.array_equal(res["best_pos"].numpy(), fx["best_pos"])
+  assert np.array_equal(res["out"].numpy(), fx["out"])
+  assert 0.2 < fx["hit"].mean() < 0.8 and np.abs(fx["out"][~fx["hit"]]).max() == 0
+
+
 def test_poslinview_head_oracle_matches_reference_bit_exact(golden_dir):
   """PlainNeRF with `--refl-kind pos-linear-view` (refl.PosLinearView, reference src/refl.py:248-290; makefile `dnerf`, `gibson`)."""
   fx = load(golden_dir, "plain_poslinview_t16")
