@@ -314,6 +314,15 @@ int nf_sphere_march(const nf_model_desc* desc, const void* packed, const float* 
 int nf_sdf_render(const nf_model_desc* desc, const void* packed, const float* rays, int64_t n_rays, float t_near, float t_far,
                   int32_t iters, float eps, float bound_rad, int32_t precision, float* rgb_out, uint8_t* hit_out, float* t_out,
                   float* pts_out, void* workspace, int64_t workspace_bytes, void* stream);
+/* march.bisect behind SDF.forward (reference src/march.py:63-75, `--sdf-isect-kind bisect`): throughput_with_sign_change over
+ * iters + 1 equidistant samples of EVERY ray (march.py:78-110, bug for bug: the first sample at r_o + t_near added to every coordinate,
+ * the bracket indices scaled by the step without the near offset; `jitter` in [0, 1) = its random.random() draw, march.py:86), then
+ * min(32, iters) bisection steps between the samples around the first sign change (march.py:147-180, eps 1e-6).
+ * Outputs (nullable): pts_out[R,3] (the bisection's point), hit_out[R] = tput < 0, tput_out[R] (the SDF at the sample where it is
+ * smallest), best_pos_out[R,3] (that sample); rgb_out[R,3] non-null: also SDF.forward's shading of the hits (sdf.py:143-153). */
+int nf_sdf_bisect(const nf_model_desc* desc, const void* packed, const float* rays, int64_t n_rays, float t_near, float t_far,
+                  int32_t iters, float jitter, float bound_rad, int32_t precision, float* pts_out, uint8_t* hit_out, float* tput_out,
+                  float* best_pos_out, float* rgb_out, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- backward of the non-GEMM stages (first blocks of the training half; the reference differentiates these ops through
  *      PyTorch autograd, runner.py:820) --------------------------------------------------------------------------- */

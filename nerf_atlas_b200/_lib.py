@@ -88,6 +88,8 @@ EXPORTS = {
   "nf_hash_encode_backward": (C.c_int, [C.POINTER(ModelDesc), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
   "nf_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                              C.c_int32, C.c_void_p]),
+  "nf_sdf_bisect": (C.c_int, [C.POINTER(ModelDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_int32, C.c_float, C.c_float,
+                              C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
   "nf_adam_step_multi": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float,
                                    C.c_float, C.c_int32, C.c_void_p]),
   "nf_mlp_forward": (C.c_int, [C.POINTER(ModelDesc), C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]),

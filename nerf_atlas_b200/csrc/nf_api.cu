@@ -342,6 +342,18 @@ int nf_sdf_render(const nf_model_desc* desc, const void* packed, const float* ra
   return e == cudaSuccess ? 0 : cuda_fail(e, "nf_sdf_render");
 }
 
+int nf_sdf_bisect(const nf_model_desc* desc, const void* packed, const float* rays, int64_t n_rays, float t_near, float t_far, int32_t iters,
+                  float jitter, float bound_rad, int32_t precision, float* pts_out, uint8_t* hit_out, float* tput_out, float* best_pos_out,
+                  float* rgb_out, void* workspace, int64_t workspace_bytes, void* stream) {
+  NfPlan p; if (int rc = sdf_check(desc, &p, packed, rays, n_rays, iters, precision, workspace, workspace_bytes)) return rc;
+  if (n_rays == 0) return 0;
+  if (iters < 1) return fail(NF_E_BADARG, "nf_sdf_bisect: iters >= 1");
+  if (!(jitter >= 0.f && jitter < 1.f)) return fail(NF_E_BADARG, "nf_sdf_bisect: jitter in [0, 1) (the reference's random.random() draw)");
+  cudaError_t e = nf_launch_sdf_bisect(p, packed, rays, n_rays, t_near, t_far, iters, jitter, bound_rad, precision, pts_out, hit_out, tput_out, best_pos_out,
+                                       rgb_out, workspace, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nf_sdf_bisect");
+}
+
 int nf_composite_backward(const nf_model_desc* desc, const void* packed, const float* sigma_raw, const float* feats,
                           const float* rays, int64_t n_rays, const float* ts, int32_t T, int64_t ts_ray_stride,
                           const float* d_rgb, float* d_sigma_raw_out, float* d_feats_out, void* stream) {

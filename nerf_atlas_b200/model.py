@@ -350,6 +350,23 @@ class RenderEngine:
     _lib.check(rc, "nf_sdf_render")
     return rgb, hit.bool(), t, pts
 
+  def sdf_bisect(self, rays: torch.Tensor, near: float, far: float, iters: int = 192, jitter: float = 0.0, bound_rad: float = -1.0,
+                 precision: Optional[str] = None, shade: bool = True):
+    """march.bisect (+ SDF.forward's shading when `shade`): rays[R,6] -> (rgb[R,3] | None, hit[R] bool, tput[R], pts[R,3], best_pos[R,3]).
+    `jitter` = the reference's random.random() draw (src/march.py:86)."""
+    self._need_packed(); _chk(rays, "rays")
+    R, dev = rays.shape[0], rays.device
+    rgb = torch.empty(R, 3, dtype=torch.float32, device=dev) if shade else None
+    pts = torch.empty(R, 3, dtype=torch.float32, device=dev); best = torch.empty(R, 3, dtype=torch.float32, device=dev)
+    tput = torch.empty(R, dtype=torch.float32, device=dev); hit = torch.empty(R, dtype=torch.uint8, device=dev)
+    ws = self._sdf_ws(R, dev)
+    with torch.cuda.device(dev):
+      rc = self.lib.nf_sdf_bisect(C.byref(self.desc), _ptr(self.packed), _ptr(rays), R, float(near), float(far), int(iters), float(jitter), float(bound_rad),
+                                  _lib.PRECISION[precision or self.precision], _ptr(pts), _ptr(hit), _ptr(tput), _ptr(best), _ptr(rgb) if shade else None,
+                                  _ptr(ws), ws.numel(), self._stream())
+    _lib.check(rc, "nf_sdf_bisect")
+    return rgb, hit.bool(), tput, pts, best
+
   # ---- stage entry points (parity tests, micro-benchmarks) ----
   def sample_points(self, rays: torch.Tensor, ts: torch.Tensor) -> torch.Tensor:
     _chk(rays, "rays"); _chk(ts, "ts")
@@ -814,14 +831,17 @@ class FusedVolSDF(FusedNeRF):
 
 
 class FusedSDF(nn.Module):
-  """Drop-in for the surface renderer `sdf.SDF` (reference src/sdf.py:86-156; `--model sdf --sdf-isect-kind sphere`) with a View
-  head, evaluation mode: sphere tracing of the SDF network (SIREN or Fourier-encoded MLP), then the View head on the hit points;
+  """Drop-in for the surface renderer `sdf.SDF` (reference src/sdf.py:86-156; `--model sdf --sdf-isect-kind sphere | bisect`) with a
+  View head, evaluation mode: sphere tracing (march.py:27-47) or bisection (march.py:63-110,147-180) of the SDF network (SIREN or
+  Fourier-encoded MLP), then the View head on the hit points;
   rays that miss render black.  Parameter names follow the reference (`underlying.{siren|mlp}.*`, `refl.mlp.*`).  Training of
   the surface model (throughput term, normals: sdf.py:120-125,150-153) is not built: forward under grad raises."""
 
   def __init__(self, sdf_kind: str = "siren", intermediate_size: int = 64, t_near: float = 0, t_far: float = 1, sigmoid_kind: str = "thin",
-               bound_sphere_rad: float = -1.0, precision: str = "fp32"):
+               bound_sphere_rad: float = -1.0, precision: str = "fp32", isect: str = "sphere"):
     super().__init__()
+    if isect not in ("sphere", "bisect"): raise NotImplementedError(f"intersection kind {isect} (built: sphere, bisect)")
+    self.isect_kind, self.jitter = isect, None      # jitter: march.py:86's random.random() draw; None = draw one per call like the reference
     self.underlying = _SdfNet(sdf_kind, intermediate_size)
     self.refl = ViewHead(latent_size=intermediate_size, out_features=3, act=sigmoid_kind)
     self.near, self.far, self.bound_sphere_rad, self.precision = t_near, t_far, bound_sphere_rad, precision
@@ -835,7 +855,9 @@ class FusedSDF(nn.Module):
     u, rad = ref.underlying, -1.0
     if type(u).__name__ == "UnitSphere": u, rad = u.inner, float(u.rad)
     if type(ref.refl).__name__ not in ("View", "ViewHead"): raise NotImplementedError(f"refl head {type(ref.refl).__name__}")
-    if getattr(ref.isect, "__name__", "sphere_march") != "sphere_march": raise NotImplementedError("only the sphere-march intersection is built")
+    kind = {"sphere_march": "sphere", "bisect": "bisect"}.get(getattr(ref.isect, "__name__", "sphere_march"))
+    if kind is None: raise NotImplementedError("intersection kinds built: sphere_march, bisect")
+    self.isect_kind, self.jitter = kind, None
     self.underlying, self.refl = u, ref.refl
     self.near, self.far, self.bound_sphere_rad, self.precision = ref.near, ref.far, rad, precision
     self._engine = None; self._engine_key = None
@@ -847,7 +869,7 @@ class FusedSDF(nn.Module):
   def intermediate_size(self): return self.underlying.intermediate_size
   def __getstate__(self):
     st = self.__dict__.copy(); st["_engine"] = None; st["_engine_key"] = None
-    for k in ("pts", "hit", "t"): st.pop(k, None)
+    for k in ("pts", "hit", "t", "tput", "best_pos"): st.pop(k, None)
     return st
 
   def _net(self):
@@ -881,7 +903,14 @@ class FusedSDF(nn.Module):
     B = rays.shape[:-1]
     flat = rays.reshape(-1, 6).to(torch.float32).contiguous()
     eng = self.engine(); eng.pack(self._param_list())
-    rgb, hit, t, pts = eng.sdf_render(flat, self.near, self.far, iters=128 if self.training else 192, bound_rad=self.bound_sphere_rad)
+    iters = 128 if self.training else 192
+    if getattr(self, "isect_kind", "sphere") == "bisect":
+      import random
+      u = random.random() if getattr(self, "jitter", None) is None else float(self.jitter)
+      rgb, hit, tput, pts, best = eng.sdf_bisect(flat, self.near, self.far, iters=iters, jitter=u, bound_rad=self.bound_sphere_rad)
+      self.pts, self.hit, self.tput, self.best_pos = pts.reshape(*B, 3), hit.reshape(B), tput.reshape(B), best.reshape(*B, 3)
+      return rgb.reshape(*B, 3)
+    rgb, hit, t, pts = eng.sdf_render(flat, self.near, self.far, iters=iters, bound_rad=self.bound_sphere_rad)
     self.pts, self.hit, self.t = pts.reshape(*B, 3), hit.reshape(B), t.reshape(B)
     return rgb.reshape(*B, 3)
 

@@ -81,4 +81,12 @@ for prec in ("fp16", "fp32"):
   ms = timed(fs, reps=2)
   rows.append({"config": f"f-4: SDF surface render (sphere march 192 it + View), 800x800, {prec}", "ms_per_frame": ms, "rays_per_s": 640000 / ms * 1e3,
                "hit_fraction": float(ms_.hit.float().mean())})
+# f-4: the bisect intersection (193 + 35 SDF evaluations of EVERY ray) + View
+mb = N.FusedSDF("siren", 64, t_near=2.0, t_far=6.0, sigmoid_kind="upshifted", precision="fp16", isect="bisect")
+mb.load_state_dict(sdf_params(fxs), strict=True); mb = mb.to(dev).eval(); mb.jitter = 0.5
+def fb():
+  with torch.no_grad(): return mb(ru.reshape(1, 800, 800, 6))
+ms = timed(fb, reps=2)
+rows.append({"config": "f-4: SDF surface render (bisect: 193 samples + 32 bisection steps + View), 800x800, fp16", "ms_per_frame": ms, "rays_per_s": 640000 / ms * 1e3,
+             "hit_fraction": float(mb.hit.float().mean())})
 for r in rows: print(json.dumps(r), flush=True)
