@@ -566,7 +566,9 @@ def bisect(params: Params, r_o: Tensor, r_d: Tensor, *, iters: int = 128, near: 
 def sdf_forward(params: Params, rays: Tensor, *, sdf_kind: str = "siren", near: float = 0, far: float = 1, iters: int = 192,
                 sigmoid: str = "upshifted", bound_rad: float = -1.0, quant=None, isect: str = "sphere", jitter: float = 0.0) -> Dict[str, Tensor]:
   """SDF.forward in eval mode (reference src/sdf.py:137-156): rgb[hit] = act(View([pts, elaz(r_d), latent])), black elsewhere.
-  isect = "sphere" (march.sphere_march) or "bisect" (march.bisect; `t` is then absent and `tput`, `best_pos` are returned)."""
+  isect = "sphere" (march.sphere_march) or "bisect" (march.bisect; `t` is then absent and `tput`, `best_pos` are returned).
+  (march.secant, src/march.py:50-60,113-143, is not restated: the reference's own run of it on the golden's network trips its
+  `assert z_pred.isfinite()` -- infinite brackets from the -1 "no crossing" index -- so there is nothing to pin it to.)"""
   r_o, r_d = rays.reshape(-1, 6).split([3, 3], dim=-1)
   if isect == "bisect":
     pts, hit, best_pos, tput = bisect(params, r_o, r_d, iters=iters, near=near, far=far, jitter=jitter, sdf_kind=sdf_kind, bound_rad=bound_rad, quant=quant)

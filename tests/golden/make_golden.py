@@ -306,17 +306,17 @@ def case_sdf(name, seed=23, sdf_kind="siren", size=16, iters_fit=500, bound_rad=
       if p.dtype.is_floating_point: p.copy_(p.to(torch.float16).to(torch.float32))
   rays = O.make_rays(2, size, size, size=size, seed=seed)
   rays = torch.cat([rays[..., :3], torch.nn.functional.normalize(rays[..., 3:], dim=-1)], dim=-1)
-  if isect == "bisect":
-    # march.bisect (src/march.py:63-75) = throughput_with_sign_change (78-110; it draws random.random() once, march.py:86: the draw is
-    # pinned with random.seed and stored) + bisection (147-180)
+  if isect in ("bisect", "secant"):
+    # march.bisect (src/march.py:63-75) / march.secant (50-60) = throughput_with_sign_change (78-110; it draws random.random() once,
+    # march.py:86: the draw is pinned with random.seed and stored) + bisection (147-180) / secant_find (113-143)
     import random
     random.seed(seed); jitter = random.random()
     with torch.no_grad():
       random.seed(seed); out = s(rays)
-      random.seed(seed); pts, hit, best_pos, tput = march.bisect(s.underlying, rays[..., :3], rays[..., 3:], iters=192, near=2.0, far=6.0)
+      random.seed(seed); pts, hit, best_pos, tput = march.load_intersection_kind(isect)(s.underlying, rays[..., :3], rays[..., 3:], iters=192, near=2.0, far=6.0)
       random.seed(seed); _, _, last_pos, first_neg = march.throughput_with_sign_change(s.underlying, rays[..., :3], rays[..., 3:], near=2.0, far=6.0, batch_size=192)
     fx = dict(kind="sdf", sdf_kind=sdf_kind, seed=seed, size=size, near=2.0, far=6.0, iters=192, sigmoid="upshifted", bound_rad=bound_rad, isect=isect,
-              jitter=jitter, rays=rays.numpy(), out=out.numpy(), hit=hit.numpy(), pts=pts.numpy(), best_pos=best_pos.numpy(), tput=tput.squeeze(-1).numpy(),
+              jitter=jitter, rays=rays.numpy(), out=out.numpy(), hit=hit.numpy(), pts=pts.numpy(), best_pos=best_pos.numpy(), tput=tput.reshape(hit.shape).numpy(),
               last_pos=last_pos.squeeze(-1).numpy(), first_neg=first_neg.squeeze(-1).numpy())
     t = tput
   else:
@@ -325,8 +325,15 @@ def case_sdf(name, seed=23, sdf_kind="siren", size=16, iters_fit=500, bound_rad=
     pts, hit, t, _ = march.sphere_march(s.underlying, rays[..., :3], rays[..., 3:], iters=192, near=2.0, far=6.0)
    fx = dict(kind="sdf", sdf_kind=sdf_kind, seed=seed, size=size, near=2.0, far=6.0, iters=192, sigmoid="upshifted", bound_rad=bound_rad,
             rays=rays.numpy(), out=out.numpy(), hit=hit.numpy(), t=t.squeeze(-1).numpy(), pts=pts.numpy())
-  for k, v in s.state_dict().items():
-    if v.dtype.is_floating_point and v.numel(): fx["param16." + k.replace("underlying.inner.", "underlying.")] = v.to(torch.float16).numpy()
+  if isect == "sphere":
+    for k, v in s.state_dict().items():
+      if v.dtype.is_floating_point and v.numel(): fx["param16." + k.replace("underlying.inner.", "underlying.")] = v.to(torch.float16).numpy()
+  else:
+    # same seed, same fit: the parameters are those of the sphere-march golden (checked here), stored once
+    ref = np.load(os.path.join(HERE, "sdf_siren_march.npz"))
+    for k, v in s.state_dict().items():
+      if v.dtype.is_floating_point and v.numel(): assert np.array_equal(ref["param16." + k.replace("underlying.inner.", "underlying.")], v.to(torch.float16).numpy()), k
+    fx["params_from"] = "sdf_siren_march"
   np.savez_compressed(os.path.join(HERE, name + ".npz"), **fx)
   print(name, "hit fraction", float(hit.float().mean()), "t range", float(t.min()), float(t.max()), "out mean", float(out.mean()))
 

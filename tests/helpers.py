@@ -86,4 +86,5 @@ def trained_params(fx):
 
 def sdf_params(fx):
   """Parameters of the `sdf_*_march` goldens (stored as fp16; the reference rendered with exactly these values)."""
+  if "params_from" in fx: fx = load_golden(str(fx["params_from"]))         # the bisect / secant goldens share the sphere-march golden's fit
   return {k[len("param16."):]: torch.from_numpy(fx[k].astype(np.float32)) for k in fx if k.startswith("param16.")}
