@@ -45,10 +45,14 @@ constexpr int RING_BYTES = 3 * (4 * 4096 + BIAS_PIECE);     // weight ring per C
 constexpr int MAX_LIN3 = 24;
 constexpr int MAX_STAGES3 = 6;
 
-struct Tc3Smem {
+// X0C = x0 columns per slot (80; 112 for the Positional head in boundary-warp mode, whose ring then has two stages), RINGB = ring bytes
+constexpr int X0K_POS = 112;
+constexpr int RING_BYTES_POS = 2 * (4 * 4096 + BIAS_PIECE);
+template <int X0C, int RINGB>
+struct Tc3SmemT {
   uint8_t H[2][ROWS * 256 * 2];
-  uint8_t X0[2][ROWS * X0K * 2];
-  uint8_t W[RING_BYTES];
+  uint8_t X0[2][ROWS * X0C * 2];
+  uint8_t W[RINGB];
   uint8_t ones[256];                                         // A operand of the bias K-step: core matrix [8 rows][1, 1, 0, ...] + a zero core matrix (read with SBO = 0)
   float sig[2][2][ROWS];                                     // raw density per row: [slot][tile parity (boundary-warp mode; else 0)]
   float warp_agg[2][4]; int warp_cont[2][4]; float warp_sum[2][4][4]; float carry[2][8];
@@ -59,7 +63,8 @@ struct Tc3Smem {
                                 // flags: 1 = `out` Linear, 2 = `init` Linear, bits 2-3 = what the epilogue of an `out` does:
                                 // 1 density-out -> View x0, 2 deformation-out -> deform + encode, 3 the path's last Linear
 };
-static_assert(sizeof(Tc3Smem) <= 227 * 1024, "staggered tensor pipeline smem");
+using Tc3Smem = Tc3SmemT<X0K, RING_BYTES>;
+static_assert(sizeof(Tc3Smem) <= 227 * 1024 && sizeof(Tc3SmemT<X0K_POS, RING_BYTES_POS>) <= 227 * 1024, "staggered tensor pipeline smem");
 static_assert(offsetof(Tc3Smem, X0) == offsetof(Tc3Smem, H) + sizeof(Tc3Smem::H), "single mode: wide x0 runs from H[1] on into X0[]");
 static_assert(offsetof(Tc3Smem, W) == offsetof(Tc3Smem, X0) + sizeof(Tc3Smem::X0), "shared wide x0 runs from X0[0] on into the first 12 KB of W");
 constexpr int SHARED_X0_COLS = (2 * ROWS * X0K * 2 + 12 * 1024) / (ROWS * 2);          // 208 columns
@@ -146,6 +151,9 @@ __device__ __forceinline__ void wait_acc(uint32_t bar, uint32_t parity, int debu
 // boundary-warp mode (four more warps own the tile boundary); A/B switches of this round's measurements
 #ifndef NF_BW
 #define NF_BW 1
+#endif
+#ifndef NF_POS_BW
+#define NF_POS_BW 1           // the Positional head on the boundary-warp kernel (else the shared-wide-x0 schedule)
 #endif
 #ifndef NF_ISSUE_STRAIGHT
 #define NF_ISSUE_STRAIGHT 1   // straight-line issuer code for the 16-step Linears
@@ -384,7 +392,8 @@ __device__ __forceinline__ void unit_of(int pass, int slot, int tpr, int nslot, 
 // A tile holds up to 128 / Tp + 2 ray segments; the first may continue a ray from the previous tile of the unit (carry in), the
 // last may be unfinished (carry out).  Products and sums are LEFT folds in sample order -- 32-sample chunk by chunk, across
 // tile boundaries -- so a ray's result does not depend on where in a unit it happens to sit.
-__device__ __forceinline__ void composite_tile3(Tc3Smem& s, int slot, const NfPlan& plan, const Tc3Args& a, const NfStreamMap& map,
+template <class Smem>
+__device__ __forceinline__ void composite_tile3(Smem& s, int slot, const NfPlan& plan, const Tc3Args& a, const NfStreamMap& map,
                                                 long long u, int sub, int row, int lane, int q, float cr, float cg, float cb,
                                                 const float* sig, float* sigma_out = nullptr, bool may_use_H = true) {
   long long ray; int t;
@@ -488,16 +497,23 @@ __device__ __forceinline__ void composite_tile3(Tc3Smem& s, int slot, const NfPl
 // soon as the chain's last x0 consumer is complete (x0_free), read the finished tile's colours when its last Linear is complete
 // (bnd_full), hand the slot back to the issuer and only then composite -- so the 16 epilogue warps never leave the MLP phases
 // and the ~7 K-cycle boundary is off both the slot's critical path and the epilogue warps' time.  Needs T % 32 == 0, WIDE == 0.
-template <int NST, int SPCT, int NCQ, int WIDE, bool DYN, bool TRAIN = false, bool AUX = false, bool BW = false>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (4 * NCQ + NST + 1 + (BW ? 4 : 0)), 1)
+// X0C = 112 (with BW, WIDE = 1, NST = 2): the Positional head (reference src/refl.py:230-245, the makefile's first target) with ITS OWN
+// x0 buffer per slot -- [inter(64) | hash'(32) | p, p | pad] -- instead of the shared-wide-x0 schedule: the boundary warps gather the
+// head's hash features into columns 64.. at encode time (the density MLP's x0 ends at column 48), so the epilogue warps see the
+// same phases as the View head's.  The 32 KB come out of the ring: two 18 KB stages.
+template <int NST, int SPCT, int NCQ, int WIDE, bool DYN, bool TRAIN = false, bool AUX = false, bool BW = false, int X0C = X0K>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (4 * NCQ + 3 + 1 + (BW ? 4 : 0)), 1)
 k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Prog prog, const Tc3Args a, const __grid_constant__ Tc3Train tr) {
-  static_assert(!BW || (WIDE == 0 && NST == 3 && NCQ == 4), "boundary warps: plain two-tile mode, warp groups {0-15, 16-19, 20-23}");
+  static_assert(!BW || ((WIDE == 0 || X0C == X0K_POS) && NST <= 3 && NCQ == 4), "boundary warps: two-tile mode with per-slot x0, warp groups {0-15, 16-19, 20-23}");
+  static_assert(X0C == X0K || (X0C == X0K_POS && BW && WIDE == 1 && NST == 2), "the 112-column instantiation is the Positional head's");
+  constexpr int RINGB = X0C == X0K ? RING_BYTES : RING_BYTES_POS;
+  using Smem = Tc3SmemT<X0C, RINGB>;
   constexpr int STAGE_BYTES = SPCT * 4096 + BIAS_PIECE;
-  static_assert(NST * STAGE_BYTES <= RING_BYTES && NST <= MAX_STAGES3, "ring geometry");
-  constexpr int RING_OFF = RING_BYTES - NST * STAGE_BYTES;     // a smaller ring sits at the END of the region (shared wide x0 in front)
+  static_assert(NST * STAGE_BYTES <= RINGB && NST <= 3, "ring geometry");
+  constexpr int RING_OFF = RINGB - NST * STAGE_BYTES;     // a smaller ring sits at the END of the region (shared wide x0 in front)
   constexpr int EPIW = 4 * NCQ, EPI_THREADS = 32 * EPIW;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  Tc3Smem& s = *reinterpret_cast<Tc3Smem*>(smem_raw);
+  Smem& s = *reinterpret_cast<Smem*>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();
   const NfStreamMap map(a.T, ROWS);
@@ -550,11 +566,11 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
     constexpr uint32_t mask = 3u;
     uint32_t stage = 0, phase = 0, a_par = 0;
     const uint32_t base4 = smem_u32(smem_raw) >> 4;
-    const uint32_t w4 = base4 + (uint32_t)((offsetof(Tc3Smem, W) + RING_OFF) >> 4);
+    const uint32_t w4 = base4 + (uint32_t)((offsetof(Smem, W) + RING_OFF) >> 4);
     const uint32_t bar_wready = smem_u32(&s.w_ready[0]), bar_wempty = smem_u32(&s.w_empty[0]);
     const uint32_t bar_a = smem_u32(&s.a_ready[0]), bar_acc = smem_u32(&s.acc_full[0]), bar_bnd = smem_u32(&s.bnd_full[0]);
     const uint32_t a_lbo = (uint32_t)(KG_BYTES >> 4) << 16, kstep4 = (uint32_t)(2 * KG_BYTES) >> 4;
-    const uint64_t ones_desc = ((uint64_t)0x4000u << 32) | (base4 + (uint32_t)(offsetof(Tc3Smem, ones) >> 4)) | (8u << 16);   // SBO = 0, LBO = 128 B
+    const uint64_t ones_desc = ((uint64_t)0x4000u << 32) | (base4 + (uint32_t)(offsetof(Smem, ones) >> 4)) | (8u << 16);   // SBO = 0, LBO = 128 B
     int li0 = 0, li1 = 0;
     bool w_ok = false;                               // ring stage `stage` is known to be full
     ST_DECL;
@@ -574,9 +590,9 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
         ST_ADD(0);
         tc_fence_after();
         const uint32_t d_tmem = slot * 256u;
-        const uint32_t x4 = (single ? base4 + (uint32_t)((offsetof(Tc3Smem, H) + sizeof(s.H[0])) >> 4)
-                                    : base4 + (uint32_t)(offsetof(Tc3Smem, X0) >> 4) + (shared_x0 ? 0u : slot * (uint32_t)(sizeof(s.X0[0]) >> 4))) | a_lbo;
-        const uint32_t h4 = (base4 + (uint32_t)(offsetof(Tc3Smem, H) >> 4) + slot * (uint32_t)(sizeof(s.H[0]) >> 4)) | a_lbo;
+        const uint32_t x4 = (single ? base4 + (uint32_t)((offsetof(Smem, H) + sizeof(s.H[0])) >> 4)
+                                    : base4 + (uint32_t)(offsetof(Smem, X0) >> 4) + (shared_x0 ? 0u : slot * (uint32_t)(sizeof(s.X0[0]) >> 4))) | a_lbo;
+        const uint32_t h4 = (base4 + (uint32_t)(offsetof(Smem, H) >> 4) + slot * (uint32_t)(sizeof(s.H[0]) >> 4)) | a_lbo;
         // one ring stage: nst K-steps read from ONE activation buffer; `last`: the Linear's last chunk, followed by the bias
         // K-step (its one non-zero K-group follows the chunk's data steps; LBO = 0 in the B descriptor)
         auto chunk = [&](const uint32_t a4, const uint32_t nst, const uint32_t acc0, const bool last) {
@@ -666,7 +682,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
     ST_FLUSH(0, blockIdx.x == 0 && (mask & 1u));
   };
 
-  if (warp >= EPIW && warp <= EPIW + NST) {
+  if (warp >= EPIW && warp <= EPIW + 3) {
   // BW: 24 warps start at 80 registers (768 x 80 = the CTA's pool); the producer / issuer warp group gives 32 of them to the epilogue warp groups
   if (BW) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(NF_REG_W4));          // register budget: see the epilogue branch
   if (warp < EPIW + NST) {
@@ -716,10 +732,10 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
       }
       ST_FLUSH(8, blockIdx.x == 0 && p == 0);
     }
-  } else {
+  } else if (warp == EPIW + NST) {
     // ================= MMA issuer (leader CTA only) =================
     if (crank == 0 && elect_one()) run_issuer();
-  }
+  }                                          // (with NST = 2 the group's fourth warp idles)
   } else if (!BW || warp < EPIW) {
     // ================= encode + epilogue: all 16 warps serve the two slots alternately =================
     // The pool is what the CTA was launched with: 24 warps x 80 >= 16 x 88 (epilogue) + 4 x 40 (producers, issuer) + 4 x 80 (boundary).
@@ -940,9 +956,10 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
             // density MLP out (tensor order [inter(I), sigma]) -> raw x0 of the RGB head + raw density
             const int iu = plan.intermediate >> 4;
             const bool pos_head = WIDE && plan.refl_kind == NF_REFL_POSITIONAL;
-            const bool pre_tail = BW && NF_BW_PRETAIL && !DYN && plan.kind == NF_KIND_PLAIN && plan.mlp[0].k0_pad <= plan.intermediate;   // the boundary warps wrote [p, elaz]
+            const bool pre_tail = BW && NF_BW_PRETAIL && !DYN && plan.kind == NF_KIND_PLAIN && plan.refl_kind == NF_REFL_VIEW && plan.mlp[0].k0_pad <= plan.intermediate;   // the boundary warps wrote [p, elaz]
+            const bool pos_pre = BW && X0C == X0K_POS && pos_head;       // ... or the Positional head's [hash'(p), p, p]
             const int mip1 = (WIDE == 2 && plan.mip != NF_MIP_NONE) ? nf_mip_col(plan, 1) : -1;
-            if (pos_head || mip1 >= 0) {
+            if ((pos_head && !pos_pre) || mip1 >= 0) {
               // wide RGB-head inputs (single mode): every thread takes a share of its row's Positional hash features and Mip latent
               long long u; int sub; unit_of(P, slot, map.tpr, nslot, u, sub);
               long long ray; int t;
@@ -1023,7 +1040,8 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
     const bool dyn = DYN && plan.kind == NF_KIND_DYN;
     const int first_m = dyn ? 2 : 0;
     const bool hashed = dyn ? plan.deform_enc == NF_ENC_HASH : plan.enc == NF_ENC_HASH;
-    const bool pre_tail = NF_BW_PRETAIL && !DYN && plan.kind == NF_KIND_PLAIN && plan.mlp[0].k0_pad <= plan.intermediate;
+    const bool pre_tail = NF_BW_PRETAIL && !DYN && plan.kind == NF_KIND_PLAIN && plan.refl_kind == NF_REFL_VIEW && plan.mlp[0].k0_pad <= plan.intermediate;
+    const bool pos_pre = X0C == X0K_POS && WIDE && plan.refl_kind == NF_REFL_POSITIONAL;
     ST_DECL;
     for (int P = 0; P <= passes; ++P) {
 #pragma unroll 1
@@ -1058,6 +1076,12 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
             const int g0 = plan.intermediate >> 3;
             st_v4(X0 + g0 * KG_BYTES + row * 16, pack_h2(px, py), pack_h2(pz, el), pack_h2(az, 0.f), 0);
             for (int g = g0 + 1; g < (plan.mlp[1].k0_pad >> 3); ++g) st_v4(X0 + g * KG_BYTES + row * 16, 0, 0, 0, 0);
+          }
+          if (WIDE && pos_pre) {
+            // the Positional head's own encoder (refl.py:233-237): columns [I, I + 4L) hash'(p), then [p, p] and the zero padding
+            uint8_t* Xh = X0 + (plan.intermediate >> 3) * KG_BYTES;
+            hash_x0(Xh, reinterpret_cast<const float4*>(a.packed + plan.hash3_off), plan, px, py, pz, row, 0, 1);
+            hash_x0_tail(Xh, plan, plan.mlp[1].k0_pad - plan.intermediate, px, py, pz, row, -1);
           }
           fence_proxy_async();
           ST_ADD(1);
@@ -1111,7 +1135,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
   }
 }
 
-bool build_prog3(const NfPlan& plan, Tc3Prog* P) {
+bool build_prog3(const NfPlan& plan, Tc3Prog* P, int x0_cap = X0K) {
   *P = Tc3Prog{};
   int nl = 0;
   for (int mi = 0; mi < plan.n_mlps; ++mi) {
@@ -1137,7 +1161,7 @@ bool build_prog3(const NfPlan& plan, Tc3Prog* P) {
   for (int i = 0; i < nl; ++i) if (P->lin[i].k0_steps) P->x0_last = i;
   int kmax = 0;
   for (int m = 0; m < plan.n_mlps; ++m) kmax = plan.mlp[m].k0_pad > kmax ? plan.mlp[m].k0_pad : kmax;
-  if (kmax > X0K) {
+  if (kmax > x0_cap) {
     P->single = 1;
     if (kmax <= SHARED_X0_COLS && plan.kind == NF_KIND_PLAIN) {
       // shared wide x0: writers = the phases that produce / activate an MLP's x0, consumers = the Linears that read it.  Slot 1
@@ -1229,8 +1253,11 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
   if (const char* r = getenv("NF_TC_EPIW")) epiw = atoi(r);
   if (epiw != 24) epiw = 16;
 #endif
+  // the Positional head with warp-aligned rays: per-slot 112-column x0, boundary warps (k_render_tc3<2, 4, 4, 1, ..., BW, 112>)
+  const bool pos_bw = NF_BW && NF_POS_BW && plan.refl_kind == NF_REFL_POSITIONAL && plan.mip == NF_MIP_NONE && plan.kind == NF_KIND_PLAIN && (T & 31) == 0 &&
+                      plan.mlp[0].k0_pad <= plan.intermediate && plan.mlp[1].k0_pad <= X0K_POS && !tp && !(aux && (aux->pts || plan.bg == NF_BG_RANDOM));
   Tc3Prog prog;
-  if (!build_prog3(plan, &prog)) return cudaErrorNotSupported;
+  if (!build_prog3(plan, &prog, pos_bw ? X0K_POS : X0K)) return cudaErrorNotSupported;
   const bool wide = prog.single != 0 || plan.mip != NF_MIP_NONE || plan.refl_kind != NF_REFL_VIEW;
   if (wide) { ring = 3; epiw = 16; }
   const bool wide_shared = wide && prog.single == 2;     // two tiles in flight over one wide x0 buffer, 3 x 12 KB ring
@@ -1263,7 +1290,7 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
     }
   }
   // boundary-warp mode (four more warps own the tile boundary): the plain two-tile instantiations, warp-aligned rays
-  const bool bw = NF_BW && !wide && (T & 31) == 0 && ring == 3 && epiw == 16;
+  const bool bw = NF_BW && (!wide || pos_bw) && (T & 31) == 0 && ring == 3 && epiw == 16;
   const int threads = 32 * (epiw + ring + 1 + (bw ? 4 : 0));
   const NfStreamMap map(T, ROWS);
   const long long units = map.units(n_rays);
@@ -1282,11 +1309,13 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
   a.stats = d_stats;
 #endif
   cudaError_t e = cudaSuccess;
+  const size_t smem_bytes = pos_bw ? sizeof(Tc3SmemT<X0K_POS, RING_BYTES_POS>) : sizeof(Tc3Smem);
   auto go = [&](auto kern) {
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tc3Smem));
-    if (e == cudaSuccess) kern<<<grid, threads, sizeof(Tc3Smem), st>>>(plan, prog, a, tr);
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e == cudaSuccess) kern<<<grid, threads, smem_bytes, st>>>(plan, prog, a, tr);
   };
-  if (bw) {
+  if (pos_bw) go(k_render_tc3<2, 4, 4, 1, false, false, false, true, X0K_POS>);
+  else if (bw) {
     if (train) go(k_render_tc3<3, 4, 4, 0, false, true, false, true>);
     else if (auxk) go(k_render_tc3<3, 4, 4, 0, false, false, true, true>);
     else if (dynk) go(k_render_tc3<3, 4, 4, 0, true, false, false, true>);
