@@ -579,6 +579,23 @@ def test_positional_head_matches_reference_golden():
   m.precision = "fp32"
   with torch.no_grad(): o2 = m(big.to(DEV))
   assert np.abs(o2.cpu().numpy() - ref["out"].numpy()).max() <= 3e-5
+  # warp-aligned rays run on the boundary-warp kernel with a 112-column x0 per slot (several rays per tile, rays packed across tiles,
+  # more tiles than one trip of the grid); other T take the shared-wide-x0 schedule: both against the fp16-operand emulation,
+  # and a sharded render equals the whole bit for bit
+  m.precision = "fp16"
+  for T, shape in ((32, (1, 40, 41)), (192, (1, 15, 21)), (100, (1, 7, 9))):
+    slab = O.make_rays(*shape, seed=83 + T, crop_top=250, crop_left=260)
+    tsT = torch.linspace(2, 6, T)
+    with torch.no_grad(): rq = O.plain_forward(P, slab, tsT, quant=torch.float16)["out"].numpy()
+    m.steps = T
+    with torch.no_grad(): oT = m(slab.to(DEV))
+    assert np.abs(oT.cpu().numpy() - rq).max() <= 3e-4, (T, np.abs(oT.cpu().numpy() - rq).max())
+    flat = slab.reshape(-1, 6).to(DEV)
+    eng = m.engine()
+    whole = eng.render(flat, tsT.to(DEV), want_weights=False)[0]
+    cut = (flat.shape[0] // 3) // 4 * 4
+    parts = torch.cat([eng.render(flat[:cut].contiguous(), tsT.to(DEV), want_weights=False)[0], eng.render(flat[cut:].contiguous(), tsT.to(DEV), want_weights=False)[0]])
+    if T % 32 == 0: assert torch.equal(parts, whole), T
 
 
 # ---------------------------------------------------------------- backward of the non-GEMM stages (SURVEY f-1, first blocks)
