@@ -1,2 +1,3 @@
-timeout 900 python -m pytest tests -m gpu -x -q -k "positional" 2>&1 | tail -8
-python profiles/configs_bench.py 2>/dev/null | tail -12 | cut -c1-230
+python profiles/sdf_run.py
+python profiles/sdf_run.py bisect
+python profiles/configs_bench.py 2>/dev/null | grep -E "f-4" | cut -c1-200
