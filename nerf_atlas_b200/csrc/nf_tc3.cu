@@ -58,6 +58,7 @@ struct Tc3SmemT {
   float warp_agg[2][4]; int warp_cont[2][4]; float warp_sum[2][4][4]; float carry[2][8];
   unsigned long long w_land[MAX_STAGES3], w_empty[MAX_STAGES3], w_ready[MAX_STAGES3], acc_full[2], a_ready[4];   // a_ready[slot]: x0 + hidden columns 0-127 of the next Linear's operand are written; a_ready[2 + slot]: columns 128-255 too
   unsigned long long bnd_full[2], x0_free[2];   // boundary-warp mode: the path's last Linear is complete / X0[slot] is no longer read
+  unsigned long long scr_ready[2], mip_land[2], col_read[2];   // WB: a tile's Mip block is in the scratch / has landed in x0 / the colours are out of TMEM
   uint32_t tmem_base; int pad_;
   int4 lin[MAX_LIN3][2];        // per Linear, for the epilogue warps: {n_pad, bias byte offset, act, flags}, {k0_pad, -, -, -}
                                 // flags: 1 = `out` Linear, 2 = `init` Linear, bits 2-3 = what the epilogue of an `out` does:
@@ -99,6 +100,7 @@ struct Tc3Args {
   const float* pts;   // AUX: explicit sample positions [R,T,3] (from_pts, reference nerf.py:340-361) instead of r_o + ts r_d
   const float* bg_rand;   // AUX / DYN: NF_BG_RANDOM draws [R]
   float* pts_out; float* dp_out; float* rigid_dp_out; float* rigidity_out;   // DYN side channels (runner.py:694-700,769,777-781)
+  uint8_t* scratch;   // WB (Mip, boundary warps): per CTA [slot][tile parity] 24 KB images of the 96 Mip features of a tile
   long long* stats;   // NF_TC_STATS builds: time-in-state counters of CTA 0 (issuer, producer 0, epilogue warps 0 and 15)
 };
 
@@ -151,6 +153,9 @@ __device__ __forceinline__ void wait_acc(uint32_t bar, uint32_t parity, int debu
 // boundary-warp mode (four more warps own the tile boundary); A/B switches of this round's measurements
 #ifndef NF_BW
 #define NF_BW 1
+#endif
+#ifndef NF_WB
+#define NF_WB 1               // the Mip encoder's shared-wide-x0 schedule with boundary warps (else all work on the 16 epilogue warps)
 #endif
 #ifndef NF_POS_BW
 #define NF_POS_BW 1           // the Positional head on the boundary-warp kernel (else the shared-wide-x0 schedule)
@@ -504,7 +509,13 @@ __device__ __forceinline__ void composite_tile3(Smem& s, int slot, const NfPlan&
 template <int NST, int SPCT, int NCQ, int WIDE, bool DYN, bool TRAIN = false, bool AUX = false, bool BW = false, int X0C = X0K>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (4 * NCQ + 3 + 1 + (BW ? 4 : 0)), 1)
 k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Prog prog, const Tc3Args a, const __grid_constant__ Tc3Train tr) {
-  static_assert(!BW || ((WIDE == 0 || X0C == X0K_POS) && NST <= 3 && NCQ == 4), "boundary warps: two-tile mode with per-slot x0, warp groups {0-15, 16-19, 20-23}");
+  static_assert(!BW || NCQ == 4, "boundary warps: warp groups {0-15, 16-19, 20-23}");
+  // WB: the Mip encoder's shared-wide-x0 schedule with boundary warps.  The x0 buffer is shared by the two slots, so the epilogue warps
+  // keep the boundary phase (hash gathers, p) -- but the boundary warps take the colour read + composite, and they compute every tile's
+  // 96 Mip features ONE TILE AHEAD into an L2-resident scratch image (the byte image of the 12 K-groups), from where one bulk copy
+  // brings them into the x0 buffer at the boundary phase (density x0) and again at the density-out phase (View x0).
+  constexpr bool WB = BW && WIDE == 2;
+  constexpr uint32_t MIP_BLOCK = NF_MIP_FEATS / 8 * KG_BYTES;      // 24 KB
   static_assert(X0C == X0K || (X0C == X0K_POS && BW && WIDE == 1 && NST == 2), "the 112-column instantiation is the Positional head's");
   constexpr int RINGB = X0C == X0K ? RING_BYTES : RING_BYTES_POS;
   using Smem = Tc3SmemT<X0C, RINGB>;
@@ -531,6 +542,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
     for (int i = 0; i < NST; ++i) { mbar_init(smem_u32(&s.w_land[i]), 1); mbar_init(smem_u32(&s.w_empty[i]), 1); mbar_init(smem_u32(&s.w_ready[i]), 2); }
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s.acc_full[i]), 1); mbar_init(smem_u32(&s.a_ready[i]), 2 * EPIW); mbar_init(smem_u32(&s.a_ready[2 + i]), 2 * EPIW); }
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s.bnd_full[i]), 1); mbar_init(smem_u32(&s.x0_free[i]), EPIW); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s.scr_ready[i]), 4); mbar_init(smem_u32(&s.mip_land[i]), 1); mbar_init(smem_u32(&s.col_read[i]), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == EPIW) {
@@ -754,7 +766,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
         const int kl = k - (slot ? lag : 0);
         if (kl < 0 || kl > nsteps || (slot && single)) continue;
         const int j = slot ? j1 : j0, P = slot ? P1 : P0;
-        if (BW && j == 0) { if (slot) j1 = 1; else j0 = 1; continue; }      // the tile boundary belongs to the boundary warps
+        if (BW && !WB && j == 0) { if (slot) j1 = 1; else j0 = 1; continue; }      // the tile boundary belongs to the boundary warps
         uint8_t* H = s.H[slot]; uint8_t* X0 = single ? s.H[1] : shared_x0 ? s.X0[0] : s.X0[slot];
         const uint32_t t_acc = t_lane + (uint32_t)slot * 256u;
         const uint32_t a_ready_leader = leader_addr(smem_u32(&s.a_ready[slot])), a_hi_leader = leader_addr(smem_u32(&s.a_ready[2 + slot]));
@@ -762,7 +774,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
         const int comp_cq = (NCQ / 2) * slot, tail_cq = comp_cq + 1;
         // bias of Linear j (consumed by this slot's NEXT phase): in flight across the acc_full wait
         const float* bias = nullptr; (void)bias;
-        if (kl > 0) {
+        if (kl > 0 && !(WB && j == 0)) {              // (WB: the last Linear reports to the boundary warps)
           ST_ADD(5);
           wait_acc(smem_u32(&s.acc_full[slot]), (acc_par >> slot) & 1u, a.debug);
           ST_ADD(0);
@@ -775,7 +787,14 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
           // Duties that only one warp per lane quarter can do rotate with the slot, so that no column quarter becomes the
           // critical path (measured: the composite is ~4.9 K cycles, the View-x0 unit ~1.5 K, the x0 tail ~1.4 K):
           //   composite: cq == 2 * slot;  x0 tail / View-x0 unit: cq == 2 * slot + 1
-          const bool comp = P >= 1;
+          const bool comp = P >= 1 && !WB;            // WB: the boundary warps composite
+          if (WB && has_next && e_tid == 0) {
+            // the tile's Mip block: scratch -> the density x0's columns [mip0, mip0 + 96) (12 contiguous K-groups)
+            mbar_wait(smem_u32(&s.scr_ready[slot]), (uint32_t)P & 1u);
+            mbar_expect_tx(smem_u32(&s.mip_land[slot]), MIP_BLOCK);
+            bulk_g2s(smem_u32(X0 + (nf_mip_col(plan, 0) >> 3) * KG_BYTES), a.scratch + ((size_t)(blockIdx.x * 2 + slot) * 2 + (P & 1)) * MIP_BLOCK, MIP_BLOCK,
+                     smem_u32(&s.mip_land[slot]));
+          }
           if (comp && cq == comp_cq) {
             long long u; int sub; unit_of(P - 1, slot, map.tpr, nslot, u, sub);
             uint32_t v[16];
@@ -817,7 +836,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
               hash_x0(X0, reinterpret_cast<const float4*>(a.packed + (dyn ? plan.hash2_off : plan.hash_off)), plan, px, py, pz, row,
                       comp ? (cq == comp_cq ? -1 : ((cq - comp_cq - 1 + NCQ) % NCQ)) : cq, comp ? NCQ - 1 : NCQ);
             const int mip0 = (WIDE == 2 && plan.mip != NF_MIP_NONE && !dyn) ? nf_mip_col(plan, 0) : -1;
-            if (mip0 >= 0) mip_x0(X0, a.mip, mip0, ok, ray, t, row, comp ? (cq == comp_cq ? NF_MIP_FEATS : ((cq - comp_cq - 1 + NCQ) % NCQ)) : cq, comp ? NCQ - 1 : NCQ);
+            if (mip0 >= 0 && !WB) mip_x0(X0, a.mip, mip0, ok, ray, t, row, comp ? (cq == comp_cq ? NF_MIP_FEATS : ((cq - comp_cq - 1 + NCQ) % NCQ)) : cq, comp ? NCQ - 1 : NCQ);
             const bool fourier = WIDE && !dyn && plan.enc == NF_ENC_FOURIER;
             if (fourier) {
               // x0 = [p, sin(p B), cos(p B)], B = basis[3][F] (reference src/neural_blocks.py:36-55, src/utils.py:14-17); reference
@@ -843,6 +862,10 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
                 st_v4(X0 + row * 16, pack_h2(px, py), pack_h2(pz, tt), 0, 0);
                 for (int g = 1; g < (plan.mlp[first_m].k0_pad >> 3); ++g) st_v4(X0 + g * KG_BYTES + row * 16, 0, 0, 0, 0);
               }
+            }
+            if (WB) {
+              mbar_wait_suspend(smem_u32(&s.mip_land[slot]), 0u);                                  // the Mip block has landed in x0 ...
+              if (P >= 1) mbar_wait_suspend(smem_u32(&s.col_read[slot]), (uint32_t)(P - 1) & 1u);  // ... and the previous tile's colours are out of TMEM
             }
             tc_fence_before();
             fence_proxy_async();
@@ -959,6 +982,12 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
             const bool pre_tail = BW && NF_BW_PRETAIL && !DYN && plan.kind == NF_KIND_PLAIN && plan.refl_kind == NF_REFL_VIEW && plan.mlp[0].k0_pad <= plan.intermediate;   // the boundary warps wrote [p, elaz]
             const bool pos_pre = BW && X0C == X0K_POS && pos_head;       // ... or the Positional head's [hash'(p), p, p]
             const int mip1 = (WIDE == 2 && plan.mip != NF_MIP_NONE) ? nf_mip_col(plan, 1) : -1;
+            if (WB && mip1 >= 0 && e_tid == 0) {
+              // the same Mip block again, now into the View x0's columns [mip1, mip1 + 96)
+              mbar_expect_tx(smem_u32(&s.mip_land[slot]), MIP_BLOCK);
+              bulk_g2s(smem_u32(X0 + (mip1 >> 3) * KG_BYTES), a.scratch + ((size_t)(blockIdx.x * 2 + slot) * 2 + (P & 1)) * MIP_BLOCK, MIP_BLOCK,
+                       smem_u32(&s.mip_land[slot]));
+            }
             if ((pos_head && !pos_pre) || mip1 >= 0) {
               // wide RGB-head inputs (single mode): every thread takes a share of its row's Positional hash features and Mip latent
               long long u; int sub; unit_of(P, slot, map.tpr, nslot, u, sub);
@@ -975,7 +1004,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
                 hash_x0(Xh, reinterpret_cast<const float4*>(a.packed + plan.hash3_off), plan, px, py, pz, row, cq, NCQ);
                 if (cq == tail_cq) hash_x0_tail(Xh, plan, plan.mlp[1].k0_pad - plan.intermediate, px, py, pz, row, mip1 >= 0 ? mip1 - plan.intermediate : -1);
               }
-              if (mip1 >= 0) mip_x0(X0, a.mip, mip1, ok, ray, t, row, cq, NCQ);
+              if (mip1 >= 0 && !WB) mip_x0(X0, a.mip, mip1, ok, ray, t, row, cq, NCQ);
             }
             for (int un0 = cq; un0 < iu + NCQ; un0 += NCQ) {
               // units 0..iu-1 (intermediate columns) are dealt round-robin; the last unit (sigma + View x0 tail) goes to tail_cq
@@ -1015,6 +1044,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
               }
             }
           }
+          if (WB && is_out && ((Lc.w >> 2) & 3) == 1 && plan.mip != NF_MIP_NONE) mbar_wait_suspend(smem_u32(&s.mip_land[slot]), 1u);   // density-out: the View x0's Mip block has landed
           tc_fence_before();
           fence_proxy_async();
           __syncwarp();
@@ -1043,6 +1073,53 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
     const bool pre_tail = NF_BW_PRETAIL && !DYN && plan.kind == NF_KIND_PLAIN && plan.refl_kind == NF_REFL_VIEW && plan.mlp[0].k0_pad <= plan.intermediate;
     const bool pos_pre = X0C == X0K_POS && WIDE && plan.refl_kind == NF_REFL_POSITIONAL;
     ST_DECL;
+    if (WB) {
+      // ---- Mip with a shared x0 buffer: colour read + composite, and the NEXT tile's Mip block into the scratch ----
+      auto mip_block = [&](int slot, int P) {
+        long long u; int sub; unit_of(P, slot, map.tpr, 2, u, sub);
+        long long ray; int t;
+        const bool ok = map.locate(u, sub, row, a.n_rays, ray, t);
+        uint8_t* scr = a.scratch + ((size_t)(blockIdx.x * 2 + slot) * 2 + (P & 1)) * MIP_BLOCK + row * 16;
+        NfMipRow R;
+        const bool per_row = a.mip.mode != NF_MIP_CYLINDER_REF;
+        if (ok && per_row) nf_mip_row(a.mip, ray, t, R);
+#pragma unroll 1
+        for (int g = 0; g < NF_MIP_FEATS / 16; ++g) {                       // pairs 8g .. 8g+7: sines -> K-group g, cosines -> K-group g + 6
+          float fs[8], fc[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            fs[k] = 0.f; fc[k] = 0.f;
+            if (ok) { if (per_row) nf_mip_pair_of_row<true>(R, 8 * g + k, fs[k], fc[k]); else nf_mip_feature_pair<true>(a.mip, ray, t, 8 * g + k, fs[k], fc[k]); }
+          }
+          *reinterpret_cast<uint4*>(scr + g * KG_BYTES) = make_uint4(pack_h2(fs[0], fs[1]), pack_h2(fs[2], fs[3]), pack_h2(fs[4], fs[5]), pack_h2(fs[6], fs[7]));
+          *reinterpret_cast<uint4*>(scr + (g + NF_MIP_FEATS / 16) * KG_BYTES) = make_uint4(pack_h2(fc[0], fc[1]), pack_h2(fc[2], fc[3]), pack_h2(fc[4], fc[5]), pack_h2(fc[6], fc[7]));
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");                  // generic-proxy global writes -> the bulk copy (async proxy) that reads them
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&s.scr_ready[slot]));
+      };
+      if (passes > 0) { mip_block(0, 0); mip_block(1, 0); }
+      for (int P = 0; P <= passes; ++P) {
+#pragma unroll 1
+        for (int slot = 0; slot < 2; ++slot) {
+          if (P >= 1) {
+            mbar_wait_suspend(smem_u32(&s.bnd_full[slot]), (uint32_t)(P - 1) & 1u);
+            tc_fence_after();
+            uint32_t v[16];
+            tmem_ld16(t_lane + (uint32_t)slot * 256u, v); tmem_ld_wait(); reg_fence16(v);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&s.col_read[slot]));
+            float cr = __uint_as_float(v[0]), cg = __uint_as_float(v[1]), cb = __uint_as_float(v[2]);
+            long long u; int sub; unit_of(P - 1, slot, map.tpr, 2, u, sub);
+            nf_feat_act3(cr, cg, cb, plan.feat_act);
+            composite_tile3(s, slot, plan, a, map, u, sub, row, lane, q, cr, cg, cb, s.sig[slot][(P - 1) & 1], nullptr, false);
+          }
+          if (P + 1 < passes) mip_block(slot, P + 1);
+        }
+      }
+    } else
     for (int P = 0; P <= passes; ++P) {
 #pragma unroll 1
       for (int slot = 0; slot < 2; ++slot) {
@@ -1290,7 +1367,9 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
     }
   }
   // boundary-warp mode (four more warps own the tile boundary): the plain two-tile instantiations, warp-aligned rays
-  const bool bw = NF_BW && (!wide || pos_bw) && (T & 31) == 0 && ring == 3 && epiw == 16;
+  // WB: the Mip encoder's shared-wide-x0 schedule with boundary warps (colour read + composite + the Mip features via an L2 scratch)
+  const bool wb = NF_BW && NF_WB && wide_shared && mipk && (T & 31) == 0 && !want_aux;
+  const bool bw = NF_BW && (!wide || pos_bw || wb) && (T & 31) == 0 && ring == 3 && epiw == 16;
   const int threads = 32 * (epiw + ring + 1 + (bw ? 4 : 0));
   const NfStreamMap map(T, ROWS);
   const long long units = map.units(n_rays);
@@ -1314,7 +1393,14 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e == cudaSuccess) kern<<<grid, threads, smem_bytes, st>>>(plan, prog, a, tr);
   };
-  if (pos_bw) go(k_render_tc3<2, 4, 4, 1, false, false, false, true, X0K_POS>);
+  uint8_t* scratch = nullptr;
+  if (wb) {
+    // 2 slots x 2 tile parities x 24 KB per CTA, stream-ordered allocation (no state kept between calls)
+    if ((e = cudaMallocAsync((void**)&scratch, (size_t)grid * 4 * (NF_MIP_FEATS / 8) * KG_BYTES, st)) != cudaSuccess) return e;
+    a.scratch = scratch;
+  }
+  if (wb) go(k_render_tc3<3, 3, 4, 2, false, false, false, true>);
+  else if (pos_bw) go(k_render_tc3<2, 4, 4, 1, false, false, false, true, X0K_POS>);
   else if (bw) {
     if (train) go(k_render_tc3<3, 4, 4, 0, false, true, false, true>);
     else if (auxk) go(k_render_tc3<3, 4, 4, 0, false, false, true, true>);
@@ -1331,6 +1417,7 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
   else if (epiw == 24) go(k_render_tc3<3, 4, 6, 0, false>);
 #endif
   else go(k_render_tc3<3, 4, 4, 0, false>);
+  if (scratch) { const cudaError_t ef = cudaFreeAsync(scratch, st); if (e == cudaSuccess) e = ef; }
   if (e != cudaSuccess) return e;
 #ifdef NF_TC_STATS
   if (getenv("NF_TC_STATS_PRINT")) {

@@ -1,3 +1,2 @@
-python profiles/sdf_run.py
-python profiles/sdf_run.py bisect
-python profiles/configs_bench.py 2>/dev/null | grep -E "f-4" | cut -c1-200
+timeout 600 python -m pytest tests -m gpu -x -q -k "mip" 2>&1 | tail -6
+for lib in libnerf_b200.so libnerf_b200_nowb.so libnerf_b200.so; do NF_LIB=$lib timeout 120 python profiles/mip_run.py 2>&1 | tail -1; done
