@@ -58,7 +58,7 @@ struct Tc3SmemT {
   float warp_agg[2][4]; int warp_cont[2][4]; float warp_sum[2][4][4]; float carry[2][8];
   unsigned long long w_land[MAX_STAGES3], w_empty[MAX_STAGES3], w_ready[MAX_STAGES3], acc_full[2], a_ready[4];   // a_ready[slot]: x0 + hidden columns 0-127 of the next Linear's operand are written; a_ready[2 + slot]: columns 128-255 too
   unsigned long long bnd_full[2], x0_free[2];   // boundary-warp mode: the path's last Linear is complete / X0[slot] is no longer read
-  unsigned long long scr_ready[2], mip_land[2], col_read[2];   // WB: a tile's Mip block is in the scratch / has landed in x0 / the colours are out of TMEM
+  unsigned long long scr_ready[2][2], mip_land[2], col_read[2];   // scr_ready[slot][tile parity]: the producer runs one tile ahead, two barriers keep its phases from aliasing   // WB: a tile's Mip block is in the scratch / has landed in x0 / the colours are out of TMEM
   uint32_t tmem_base; int pad_;
   int4 lin[MAX_LIN3][2];        // per Linear, for the epilogue warps: {n_pad, bias byte offset, act, flags}, {k0_pad, -, -, -}
                                 // flags: 1 = `out` Linear, 2 = `init` Linear, bits 2-3 = what the epilogue of an `out` does:
@@ -542,7 +542,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
     for (int i = 0; i < NST; ++i) { mbar_init(smem_u32(&s.w_land[i]), 1); mbar_init(smem_u32(&s.w_empty[i]), 1); mbar_init(smem_u32(&s.w_ready[i]), 2); }
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s.acc_full[i]), 1); mbar_init(smem_u32(&s.a_ready[i]), 2 * EPIW); mbar_init(smem_u32(&s.a_ready[2 + i]), 2 * EPIW); }
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s.bnd_full[i]), 1); mbar_init(smem_u32(&s.x0_free[i]), EPIW); }
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s.scr_ready[i]), 4); mbar_init(smem_u32(&s.mip_land[i]), 1); mbar_init(smem_u32(&s.col_read[i]), 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s.scr_ready[i][0]), 4); mbar_init(smem_u32(&s.scr_ready[i][1]), 4); mbar_init(smem_u32(&s.mip_land[i]), 1); mbar_init(smem_u32(&s.col_read[i]), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == EPIW) {
@@ -790,7 +790,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
           const bool comp = P >= 1 && !WB;            // WB: the boundary warps composite
           if (WB && has_next && e_tid == 0) {
             // the tile's Mip block: scratch -> the density x0's columns [mip0, mip0 + 96) (12 contiguous K-groups)
-            mbar_wait(smem_u32(&s.scr_ready[slot]), (uint32_t)P & 1u);
+            mbar_wait(smem_u32(&s.scr_ready[slot][P & 1]), (uint32_t)(P >> 1) & 1u);
             mbar_expect_tx(smem_u32(&s.mip_land[slot]), MIP_BLOCK);
             bulk_g2s(smem_u32(X0 + (nf_mip_col(plan, 0) >> 3) * KG_BYTES), a.scratch + ((size_t)(blockIdx.x * 2 + slot) * 2 + (P & 1)) * MIP_BLOCK, MIP_BLOCK,
                      smem_u32(&s.mip_land[slot]));
@@ -1097,7 +1097,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
         asm volatile("fence.proxy.async;" ::: "memory");                  // generic-proxy global writes -> the bulk copy (async proxy) that reads them
         __threadfence();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&s.scr_ready[slot]));
+        if (lane == 0) mbar_arrive(smem_u32(&s.scr_ready[slot][P & 1]));
       };
       if (passes > 0) { mip_block(0, 0); mip_block(1, 0); }
       for (int P = 0; P <= passes; ++P) {

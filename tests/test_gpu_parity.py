@@ -487,6 +487,20 @@ def test_mip_intended_encoder_vs_oracle(kind):
     r16, _, _ = e.render(rays.reshape(-1, 6).to(DEV), ts.to(DEV), radius=rad.reshape(-1), precision="fp16", want_weights=False)
     o16 = r16.cpu().numpy().reshape(ref["out"].shape)
     assert np.isfinite(o16).all() and np.abs(o16 - ref["out"].numpy()).max() <= 1e-3, (kind, T, "fp16", np.abs(o16 - ref["out"].numpy()).max())
+  # warp-aligned rays take the boundary-warp form of the shared-wide-x0 schedule (Mip features through the L2 scratch): several
+  # rays per tile, rays packed across tiles, more tiles than one trip of the grid; vs the fp16-operand emulation, shard == whole
+  e = _mip_engine(P, kind, DEV)
+  for T, shape in ((32, (1, 36, 37)), (192, (1, 14, 19))):
+    slab = O.make_rays(*shape, seed=90 + T, crop_top=280, crop_left=300)
+    ts = torch.linspace(2, 6, T)
+    with torch.no_grad(): rq = O.plain_forward(P, slab, ts, mip=kind, mip_layout="intended", quant=torch.float16)["out"].numpy()
+    flat = slab.reshape(-1, 6).to(DEV); rad = e.ray_radii(slab.to(DEV)).reshape(-1)
+    whole = e.render(flat, ts.to(DEV), radius=rad, precision="fp16", want_weights=False)[0]
+    assert np.abs(whole.cpu().numpy().reshape(rq.shape) - rq).max() <= 3e-4, (kind, T, np.abs(whole.cpu().numpy().reshape(rq.shape) - rq).max())
+    cut = (flat.shape[0] // 3) // 4 * 4
+    parts = torch.cat([e.render(flat[:cut].contiguous(), ts.to(DEV), radius=rad[:cut].contiguous(), precision="fp16", want_weights=False)[0],
+                       e.render(flat[cut:].contiguous(), ts.to(DEV), radius=rad[cut:].contiguous(), precision="fp16", want_weights=False)[0]])
+    assert torch.equal(parts, whole), (kind, T)
 
 
 @pytest.mark.parametrize("name,spline", [("dnerf_direct_t64", 0), ("dnerf_spline5_t32", 5), ("dnerf_spline4_t32", 4)])
