@@ -154,6 +154,9 @@ __device__ __forceinline__ void wait_acc(uint32_t bar, uint32_t parity, int debu
 #ifndef NF_BW
 #define NF_BW 1
 #endif
+#ifndef NF_WB_NST2
+#define NF_WB_NST2 0
+#endif
 #ifndef NF_WB
 #define NF_WB 1               // the Mip encoder's shared-wide-x0 schedule with boundary warps (else all work on the 16 epilogue warps)
 #endif
@@ -1399,7 +1402,11 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
     if ((e = cudaMallocAsync((void**)&scratch, (size_t)grid * 4 * (NF_MIP_FEATS / 8) * KG_BYTES, st)) != cudaSuccess) return e;
     a.scratch = scratch;
   }
-  if (wb) go(k_render_tc3<3, 3, 4, 2, false, false, false, true>);
+#if NF_WB_NST2
+  if (wb) go(k_render_tc3<2, 4, 4, 2, false, false, false, true>);       // two 18 KB stages (4 K-steps): 4 chunks per Linear, straight-line issuer
+#else
+  if (wb) go(k_render_tc3<3, 3, 4, 2, false, false, false, true>);       // three 14 KB stages (3 K-steps)
+#endif
   else if (pos_bw) go(k_render_tc3<2, 4, 4, 1, false, false, false, true, X0K_POS>);
   else if (bw) {
     if (train) go(k_render_tc3<3, 4, 4, 0, false, true, false, true>);

@@ -1,3 +1,2 @@
-for args in "cylinder 256 9 9" "cylinder 256 3 2" "cylinder 192 14 19" "cone 160 9 9"; do timeout 60 python profiles/_dbg.py $args 2>&1 | grep -v "^$" | tail -1 | cut -c1-120; done
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python profiles/mip_run.py | tail -1
+for lib in libnerf_b200.so libnerf_b200_nst2.so libnerf_b200.so libnerf_b200_nst2.so; do NF_LIB=$lib timeout 120 python profiles/mip_run.py 2>&1 | tail -1; done
+NF_LIB=libnerf_b200_nst2.so timeout 600 python -m pytest tests -m gpu -x -q -k "mip" 2>&1 | tail -2

@@ -1,4 +1,5 @@
-"""One Mip render on the tensor pipeline for a given (mip kind, T, H, W): the case runner used to find the scratch-ready barrier aliasing\n(python profiles/mip_case.py cylinder 192 14 19; under compute-sanitizer for a trapped launch)."""
+"""One Mip render on the tensor pipeline for a given (mip kind, T, H, W): the case runner used to find the scratch-ready barrier aliasing
+(python profiles/mip_case.py cylinder 192 14 19; under compute-sanitizer for a trapped launch)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
