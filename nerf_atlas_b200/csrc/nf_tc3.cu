@@ -1371,7 +1371,8 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
   }
   // boundary-warp mode (four more warps own the tile boundary): the plain two-tile instantiations, warp-aligned rays
   // WB: the Mip encoder's shared-wide-x0 schedule with boundary warps (colour read + composite + the Mip features via an L2 scratch)
-  const bool wb = NF_BW && NF_WB && wide_shared && mipk && (T & 31) == 0 && !want_aux;
+  // (not for the reference's bug-compatible layout: its per-feature crop-wide gathers want all 16 epilogue warps, 540 vs 625 ms)
+  const bool wb = NF_BW && NF_WB && wide_shared && mipk && plan.mip != NF_MIP_CYLINDER_REF && (T & 31) == 0 && !want_aux;
   const bool bw = NF_BW && (!wide || pos_bw || wb) && (T & 31) == 0 && ring == 3 && epiw == 16;
   const int threads = 32 * (epiw + ring + 1 + (bw ? 4 : 0));
   const NfStreamMap map(T, ROWS);
