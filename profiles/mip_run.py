@@ -24,5 +24,7 @@ else:
 for _ in range(3): f()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record(); f(); e1.record(); torch.cuda.synchronize()
-print("ms", e0.elapsed_time(e1))
+e0.record()
+for _ in range(4): f()
+e1.record(); torch.cuda.synchronize()
+print("ms", e0.elapsed_time(e1) / 4)
