@@ -1,2 +1,1 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r02c_bench_2gpu.json 2> gpurun_out/r02c_bench_2gpu.err; python -c "
-import json; d=json.load(open('gpurun_out/r02c_bench_2gpu.json')); print(d['value'], d['ms_per_step'], d['train'], d['strong_scaling'])"; tail -2 gpurun_out/r02c_bench_2gpu.err
+timeout 900 python -m pytest tests -m gpu -x -q -k "ragged_grids" 2>&1 | tail -12

@@ -171,6 +171,44 @@ def test_render_per_ray_ts_noise_white_bg(P):
     rgb, _, w = e.render(rays.to(DEV), tsr.to(DEV), noise.to(DEV))
     assert np.abs(rgb.cpu().numpy() - ref["out"].numpy()).max() <= tol, precision
 
+@pytest.mark.parametrize("T,nr", [(32, 1), (32, 5), (256, 5), (64, 37), (256, 81), (192, 266)])
+def test_boundary_warp_kernels_ragged_grids(P, T, nr):
+  """The boundary-warp kernels (plain, white background + per-ray ts + noise; Positional head; Mip) on grids with idle slots and
+  all-idle CTAs, one to several sub-tiles per ray, fewer tiles than slots: vs the fp16-operand emulation.  (A producer / consumer
+  barrier pair whose producer runs ahead shows up exactly here: idle CTAs produce their blocks much faster than busy ones.)"""
+  import nerf_atlas_b200 as N
+  g = torch.Generator().manual_seed(T * 1000 + nr)
+  rays = O.make_rays(1, 20, 20, seed=T + nr, crop_top=310, crop_left=420).reshape(-1, 6)[:nr].contiguous()
+  ts = torch.linspace(2, 6, T)
+  # plain + View: per-ray ts, density noise, white background
+  tsr = torch.sort(torch.rand(nr, T, generator=g) * 4 + 2, dim=1).values
+  noise = torch.randn(nr, T, generator=g) * 0.2
+  pts = (rays[:, None, :3] + tsr[:, :, None] * rays[:, None, 3:]).permute(1, 0, 2).contiguous()
+  with torch.no_grad():
+    refq = O.plain_from_pts(P, pts, tsr.t().contiguous(), rays[:, :3], rays[:, 3:], bg="white", density_noise=noise.t().contiguous(), per_ray_ts=True,
+                            quant=torch.float16)["out"].numpy()
+  e = plain_engine(P, DEV, bg="white", precision="fp16")
+  rgb, _, _ = e.render(rays.to(DEV), tsr.to(DEV), noise.to(DEV))
+  assert np.abs(rgb.cpu().numpy() - refq).max() <= 3e-4, ("plain", np.abs(rgb.cpu().numpy() - refq).max())
+  # Positional head
+  Pp = O.make_plain_params(81, 64, 20.0, refl_kind="pos")
+  with torch.no_grad(): rq = O.plain_forward(Pp, rays.reshape(1, 1, nr, 6), ts, quant=torch.float16)["out"].numpy().reshape(nr, 3)
+  mp = N.FusedPlainNeRF(steps=T, t_near=2, t_far=6, intermediate_size=64, sigmoid_kind="upshifted", precision="fp16", refl_kind="pos")
+  mp.load_state_dict(Pp, strict=True); mp = mp.to(DEV).eval()
+  with torch.no_grad(): op = mp(rays.reshape(1, 1, nr, 6).to(DEV)).cpu().numpy().reshape(nr, 3)
+  assert np.abs(op - rq).max() <= 3e-4, ("positional", np.abs(op - rq).max())
+  # Mip (the radii need an image: H >= 3)
+  if nr >= 9:
+    h = 3; w = nr // 3
+    slab = O.make_rays(1, h, w, seed=T + nr + 1, crop_top=310, crop_left=420)
+    Pm = O.make_plain_params(62, 64, 20.0, mip=True)
+    with torch.no_grad(): rm = O.plain_forward(Pm, slab, ts, mip="cone", mip_layout="intended", quant=torch.float16)["out"].numpy()
+    em = _mip_engine(Pm, "cone", DEV)
+    rad = em.ray_radii(slab.to(DEV)).reshape(-1)
+    om = em.render(slab.reshape(-1, 6).to(DEV), ts.to(DEV), radius=rad, precision="fp16", want_weights=False)[0].cpu().numpy().reshape(rm.shape)
+    assert np.abs(om - rm).max() <= 3e-4, ("mip", np.abs(om - rm).max())
+
+
 def test_tiny_nerf_vs_oracle():
   import nerf_atlas_b200 as N
   Pt = make_tiny_params()
