@@ -323,6 +323,13 @@ int nf_sdf_render(const nf_model_desc* desc, const void* packed, const float* ra
 int nf_sdf_bisect(const nf_model_desc* desc, const void* packed, const float* rays, int64_t n_rays, float t_near, float t_far,
                   int32_t iters, float jitter, float bound_rad, int32_t precision, float* pts_out, uint8_t* hit_out, float* tput_out,
                   float* best_pos_out, float* rgb_out, void* workspace, int64_t workspace_bytes, void* stream);
+/* SDFModel.normals (reference src/sdf.py:43-49; SDF.normals / intersect_w_n, sdf.py:112,114-125): the gradient with respect to the
+ * point of the SUM OF ALL outputs of the SDF network -- utils.autograd (utils.py:266-277) back-propagates ones over every channel,
+ * the latent included -- by forward-mode differentiation on the fp32 CUDA-core pipeline (value + three tangents per point through
+ * the same Linears; act' at the value's pre-activation).  pts[N,3] -> normals_out[N,3]; values_out[N, 1 + I] (nullable) = the
+ * network's outputs at the points.  bound_rad > 0: UnitSphere (sdf.py:66-83), output 0 = max(inner, |p| - rad). */
+int nf_sdf_normals(const nf_model_desc* desc, const void* packed, const float* pts, int64_t n, float bound_rad,
+                   float* normals_out, float* values_out, void* stream);
 
 /* ---- backward of the non-GEMM stages (first blocks of the training half; the reference differentiates these ops through
  *      PyTorch autograd, runner.py:820) --------------------------------------------------------------------------- */

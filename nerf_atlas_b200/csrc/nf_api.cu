@@ -354,6 +354,19 @@ int nf_sdf_bisect(const nf_model_desc* desc, const void* packed, const float* ra
   return e == cudaSuccess ? 0 : cuda_fail(e, "nf_sdf_bisect");
 }
 
+int nf_sdf_normals(const nf_model_desc* desc, const void* packed, const float* pts, int64_t n, float bound_rad, float* normals_out,
+                   float* values_out, void* stream) {
+  NfPlan p; if (int rc = plan_of(desc, &p)) return rc;
+  if (p.kind != NF_KIND_PLAIN || p.mip != NF_MIP_NONE || (p.enc != NF_ENC_NONE && p.enc != NF_ENC_FOURIER))
+    return fail(NF_E_UNSUPPORTED, "nf_sdf_normals: a VolSDF-style descriptor (SIREN or Fourier-encoded SDF network)");
+  if (p.mlp[0].hidden_ref != NF_HIDDEN) return fail(NF_E_UNSUPPORTED, "nf_sdf_normals: hidden_size 256");
+  if (n < 0) return fail(NF_E_BADARG, "nf_sdf_normals: n >= 0");
+  if (n == 0) return 0;
+  if (!packed || !pts || !normals_out) return fail(NF_E_BADARG, "nf_sdf_normals: null pointer");
+  cudaError_t e = nf_launch_sdf_normals(p, packed, pts, n, bound_rad, normals_out, values_out, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nf_sdf_normals");
+}
+
 int nf_composite_backward(const nf_model_desc* desc, const void* packed, const float* sigma_raw, const float* feats,
                           const float* rays, int64_t n_rays, const float* ts, int32_t T, int64_t ts_ray_stride,
                           const float* d_rgb, float* d_sigma_raw_out, float* d_feats_out, void* stream) {

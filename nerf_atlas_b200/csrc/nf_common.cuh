@@ -217,6 +217,15 @@ __device__ __forceinline__ float nf_apply_act(float x, int act) {
     default:           return x;
   }
 }
+// d act / d x at the pre-activation x (torch's conventions at the kinks: LeakyReLU' = ReLU' = the negative-side slope at x <= 0)
+__device__ __forceinline__ float nf_act_grad(float x, int act) {
+  switch (act) {
+    case NF_ACT_LEAKY: return x > 0.f ? 1.f : 0.01f;
+    case NF_ACT_SIN:   return cosf(x);
+    case NF_ACT_RELU:  return x > 0.f ? 1.f : 0.f;
+    default:           return 1.f;
+  }
+}
 __device__ __forceinline__ float nf_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
 __device__ __forceinline__ float nf_softplus(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 // sigmoid family, reference src/utils.py:484-518

@@ -24,6 +24,10 @@ struct Fp32Smem {
 };
 
 // One Linear of SkipConnMLP (reference src/neural_blocks.py:289-296): Hout = [act?](W [act(Hin), act?(X0)] + b)
+// JAC (forward-mode derivative, nf_sdf_normals): a thread's four rows are ONE point -- row 0 its value, rows 1-3 the tangents
+// d/dp_x, d/dp_y, d/dp_z.  The same FMAs propagate all four (W is linear); the bias goes to the value row only and the activation
+// becomes act(z) for the value, act'(z) * tangent for the other three.
+template <bool JAC = false>
 __device__ __forceinline__ void linear_fp32(const NfLinPlan& L, int act, const uint8_t* __restrict__ packed,
                                             const float* __restrict__ Hin, const float* __restrict__ X0,
                                             float* __restrict__ Hout) {
@@ -56,7 +60,10 @@ __device__ __forceinline__ void linear_fp32(const NfLinPlan& L, int act, const u
     const float* __restrict__ Wx = Wt + (size_t)L.k_hidden * np;
     for (int k = 0; k < L.k_x0; ++k) {
       float4 a = *reinterpret_cast<const float4*>(X0 + k * ROWS + r0);
-      if (!L.x0_raw) { a.x = nf_apply_act(a.x, act); a.y = nf_apply_act(a.y, act); a.z = nf_apply_act(a.z, act); a.w = nf_apply_act(a.w, act); }
+      if (!L.x0_raw) {
+        if (JAC) { const float d = nf_act_grad(a.x, act); a.x = nf_apply_act(a.x, act); a.y *= d; a.z *= d; a.w *= d; }
+        else { a.x = nf_apply_act(a.x, act); a.y = nf_apply_act(a.y, act); a.z = nf_apply_act(a.z, act); a.w = nf_apply_act(a.w, act); }
+      }
       fma_row(a, Wx + (size_t)k * np);
     }
     const float* __restrict__ b = reinterpret_cast<const float*>(packed + L.b_off) + n0;
@@ -64,8 +71,13 @@ __device__ __forceinline__ void linear_fp32(const NfLinPlan& L, int act, const u
     for (int j = 0; j < 16; ++j) {
       const float bj = __ldg(b + j);
       float4 o;
+      if (JAC) {
+        const float z = acc[0][j] + bj, d = L.is_out ? 1.f : nf_act_grad(z, act);
+        o.x = L.is_out ? z : nf_apply_act(z, act); o.y = acc[1][j] * d; o.z = acc[2][j] * d; o.w = acc[3][j] * d;
+      } else {
       o.x = acc[0][j] + bj; o.y = acc[1][j] + bj; o.z = acc[2][j] + bj; o.w = acc[3][j] + bj;
       if (!L.is_out) { o.x = nf_apply_act(o.x, act); o.y = nf_apply_act(o.y, act); o.z = nf_apply_act(o.z, act); o.w = nf_apply_act(o.w, act); }
+      }
       *reinterpret_cast<float4*>(Hout + (n0 + j) * ROWS + r0) = o;
     }
   }
@@ -73,10 +85,11 @@ __device__ __forceinline__ void linear_fp32(const NfLinPlan& L, int act, const u
 }
 
 // Runs every Linear of one MLP; returns the H buffer index holding out[n][row].
+template <bool JAC = false>
 __device__ __forceinline__ int mlp_fp32(const NfMlpPlan& M, const uint8_t* __restrict__ packed, Fp32Smem& s) {
   int cur = 0;
   for (int j = 0; j < M.n_lin; ++j) {
-    linear_fp32(M.lin[j], M.act, packed, s.H[cur], s.X0, s.H[cur ^ 1]);
+    linear_fp32<JAC>(M.lin[j], M.act, packed, s.H[cur], s.X0, s.H[cur ^ 1]);
     cur ^= 1;
   }
   return cur;
@@ -362,6 +375,79 @@ k_mlp_fp32(const __grid_constant__ NfPlan plan, int which, const uint8_t* __rest
       const int row = i / M.out_dims, c = i - row * M.out_dims;
       const long long g = tile * ROWS + row;
       if (g < n) out[g * M.out_dims + c] = s.H[ob][c * ROWS + row];
+    }
+    __syncthreads();
+  }
+}
+
+// SDFModel.normals (reference src/sdf.py:43-49): d (sum of ALL outputs of the SDF network) / d p -- utils.autograd (utils.py:266-277)
+// back-propagates ones over every output channel, the latent included -- by forward-mode differentiation: 16 points per tile, four
+// rows each (value + three tangents).  bound_rad > 0: UnitSphere (sdf.py:66-83), output 0 = max(inner, |p| - rad).
+__global__ void __launch_bounds__(THREADS, 1)
+k_sdf_normals_fp32(const __grid_constant__ NfPlan plan, const uint8_t* __restrict__ packed, const float* __restrict__ pts, long long n, float bound_rad,
+                   float* __restrict__ normals, float* __restrict__ values) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  Fp32Smem& s = *reinterpret_cast<Fp32Smem*>(smem_raw);
+  const NfMlpPlan& M = plan.mlp[0];
+  constexpr int PPT = ROWS / 4;                          // points per tile
+  const long long tiles = (n + PPT - 1) / PPT;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    // x0 rows: [p] (SIREN) or [p, sin(p B), cos(p B)] (Fourier MLP) and their derivatives with respect to p
+    for (int i = threadIdx.x; i < M.in_dims * PPT; i += THREADS) {
+      const int pt = i / M.in_dims, k = i - pt * M.in_dims;
+      const long long g = tile * PPT + pt;
+      float v = 0.f, t3[3] = {0.f, 0.f, 0.f};
+      if (g < n) {
+        const float px = __ldg(pts + g * 3), py = __ldg(pts + g * 3 + 1), pz = __ldg(pts + g * 3 + 2);
+        if (k < 3) { v = k == 0 ? px : k == 1 ? py : pz; t3[k] = 1.f; }
+        else {
+          const float* B = reinterpret_cast<const float*>(packed + plan.fourier_off);
+          const int F = plan.fourier_freqs, f = (k - 3) % F;
+          const bool is_cos = k - 3 >= F;
+          const float bx = __ldg(B + f), by = __ldg(B + F + f), bz = __ldg(B + 2 * F + f);
+          const float m = fmaf(pz, bz, fmaf(py, by, __fmul_rn(px, bx)));
+          const float sn = sinf(m), cs = cosf(m);
+          v = is_cos ? cs : sn;
+          const float d = is_cos ? -sn : cs;
+          t3[0] = d * bx; t3[1] = d * by; t3[2] = d * bz;
+        }
+      }
+      float* col = s.X0 + k * ROWS + pt * 4;
+      col[0] = v; col[1] = t3[0]; col[2] = t3[1]; col[3] = t3[2];
+    }
+    __syncthreads();
+    const int ob = mlp_fp32<true>(M, packed, s);
+    for (int i = threadIdx.x; i < PPT * 3; i += THREADS) {
+      const int pt = i / 3, c = i - pt * 3;
+      const long long g = tile * PPT + pt;
+      if (g >= n) continue;
+      float acc = 0.f;
+      for (int k = 0; k < M.out_dims; ++k) {
+        float t = s.H[ob][k * ROWS + pt * 4 + 1 + c];
+        if (k == 0 && bound_rad > 0.f) {
+          const float px = __ldg(pts + g * 3), py = __ldg(pts + g * 3 + 1), pz = __ldg(pts + g * 3 + 2);
+          const float r = sqrtf(px * px + py * py + pz * pz);
+          // torch.maximum's gradient: the larger operand takes it (ties: split evenly)
+          const float inner = s.H[ob][pt * 4], sph = r - bound_rad;
+          const float ds = (c == 0 ? px : c == 1 ? py : pz) / r;
+          t = inner > sph ? t : inner < sph ? ds : 0.5f * (t + ds);
+        }
+        acc += t;
+      }
+      normals[g * 3 + c] = acc;
+    }
+    if (values) {
+      for (int i = threadIdx.x; i < PPT * M.out_dims; i += THREADS) {
+        const int pt = i / M.out_dims, c = i - pt * M.out_dims;
+        const long long g = tile * PPT + pt;
+        if (g >= n) continue;
+        float v = s.H[ob][c * ROWS + pt * 4];
+        if (c == 0 && bound_rad > 0.f) {
+          const float px = __ldg(pts + g * 3), py = __ldg(pts + g * 3 + 1), pz = __ldg(pts + g * 3 + 2);
+          v = fmaxf(v, sqrtf(px * px + py * py + pz * pz) - bound_rad);
+        }
+        values[g * M.out_dims + c] = v;
+      }
     }
     __syncthreads();
   }
@@ -679,6 +765,17 @@ cudaError_t nf_launch_mlp_fp32(const NfPlan& plan, int which, const void* packed
   if (tiles == 0) return cudaSuccess;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   k_mlp_fp32<<<grid, THREADS, sizeof(Fp32Smem), st>>>(plan, which, (const uint8_t*)packed, x0, n, out, n_dev);
+  return cudaGetLastError();
+}
+
+cudaError_t nf_launch_sdf_normals(const NfPlan& plan, const void* packed, const float* pts, int64_t n, float bound_rad, float* normals, float* values,
+                                  cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(k_sdf_normals_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Fp32Smem));
+  if (e != cudaSuccess) return e;
+  const long long tiles = (n + ROWS / 4 - 1) / (ROWS / 4);
+  if (tiles == 0) return cudaSuccess;
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  k_sdf_normals_fp32<<<grid, THREADS, sizeof(Fp32Smem), st>>>(plan, (const uint8_t*)packed, pts, n, bound_rad, normals, values);
   return cudaGetLastError();
 }
 

@@ -22,6 +22,8 @@ cudaError_t nf_launch_mlp_tc(const NfPlan& plan, int which, const void* packed, 
 // SDF surface side (nf_march.cu): sphere tracing + shading of the hit points
 cudaError_t nf_launch_sphere_march(const NfPlan& plan, const void* packed, const float* rays, int64_t n_rays, float near, float far, int iters,
                                    float eps, float bound_rad, int precision, float* pts_out, uint8_t* hit_out, float* t_out, void* ws, cudaStream_t st);
+cudaError_t nf_launch_sdf_normals(const NfPlan& plan, const void* packed, const float* pts, int64_t n, float bound_rad, float* normals, float* values,
+                                  cudaStream_t st);
 cudaError_t nf_launch_sdf_bisect(const NfPlan& plan, const void* packed, const float* rays, int64_t n_rays, float near, float far, int iters, float jitter,
                                  float bound_rad, int precision, float* pts_out, uint8_t* hit_out, float* tput_out, float* best_out, float* rgb_out,
                                  void* ws, cudaStream_t st);

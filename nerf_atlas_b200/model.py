@@ -350,6 +350,17 @@ class RenderEngine:
     _lib.check(rc, "nf_sdf_render")
     return rgb, hit.bool(), t, pts
 
+  def sdf_normals(self, pts: torch.Tensor, bound_rad: float = -1.0, want_values: bool = False):
+    """SDFModel.normals (reference src/sdf.py:43-49): pts[N,3] -> normals[N,3] (+ the network's outputs [N, 1 + I])."""
+    self._need_packed(); _chk(pts, "pts")
+    n, dev = pts.shape[0], pts.device
+    nrm = torch.empty(n, 3, dtype=torch.float32, device=dev)
+    vals = torch.empty(n, 1 + self.desc.intermediate, dtype=torch.float32, device=dev) if want_values else None
+    with torch.cuda.device(dev):
+      rc = self.lib.nf_sdf_normals(C.byref(self.desc), _ptr(self.packed), _ptr(pts), n, float(bound_rad), _ptr(nrm), _ptr(vals) if want_values else None, self._stream())
+    _lib.check(rc, "nf_sdf_normals")
+    return (nrm, vals) if want_values else nrm
+
   def sdf_bisect(self, rays: torch.Tensor, near: float, far: float, iters: int = 192, jitter: float = 0.0, bound_rad: float = -1.0,
                  precision: Optional[str] = None, shade: bool = True):
     """march.bisect (+ SDF.forward's shading when `shade`): rays[R,6] -> (rgb[R,3] | None, hit[R] bool, tput[R], pts[R,3], best_pos[R,3]).
@@ -895,6 +906,27 @@ class FusedSDF(nn.Module):
     if not hasattr(self, "_beta") or self._beta.device != ps[0].device: self._beta = torch.ones(1, device=ps[0].device)    # the descriptor's Laplace beta: unused by the surface side
     ps.append(self._beta)
     return ps
+
+  def normals(self, pts: torch.Tensor, values=None) -> torch.Tensor:
+    """SDF.normals (reference src/sdf.py:112 -> SDFModel.normals, 43-49), no graph: the fused path does not train the surface model."""
+    if not pts.is_cuda: raise RuntimeError("FusedSDF.normals needs CUDA points: the fused path has no CPU fallback")
+    eng = self.engine(); eng.pack(self._param_list())
+    shape = pts.shape
+    return eng.sdf_normals(pts.reshape(-1, 3).to(torch.float32).contiguous(), bound_rad=self.bound_sphere_rad).reshape(shape)
+
+  def intersect_w_n(self, r_o: torch.Tensor, r_d: torch.Tensor):
+    """SDF.intersect_w_n in eval mode (reference src/sdf.py:114-125: iters 256, eps 5e-5): (pts, hit, tput | None, normals)."""
+    B = r_o.shape[:-1]
+    flat = torch.cat([r_o, r_d], dim=-1).reshape(-1, 6).to(torch.float32).contiguous()
+    eng = self.engine(); eng.pack(self._param_list())
+    if getattr(self, "isect_kind", "sphere") == "bisect":
+      import random
+      u = random.random() if getattr(self, "jitter", None) is None else float(self.jitter)
+      _, hit, tput, pts, _ = eng.sdf_bisect(flat, self.near, self.far, iters=256, jitter=u, bound_rad=self.bound_sphere_rad, shade=False)
+      tput = tput.reshape(*B, 1)
+    else:
+      pts, hit, _ = eng.sphere_march(flat, self.near, self.far, iters=256, eps=5e-5, bound_rad=self.bound_sphere_rad); tput = None
+    return pts.reshape(*B, 3), hit.reshape(B), tput, eng.sdf_normals(pts, bound_rad=self.bound_sphere_rad).reshape(*B, 3)
 
   def forward(self, rays: torch.Tensor, with_throughput: bool = True) -> torch.Tensor:
     if not rays.is_cuda: raise RuntimeError("FusedSDF.forward needs CUDA rays: the fused path has no CPU fallback")

@@ -480,12 +480,22 @@ def volsdf_forward(params: Params, rays: Tensor, ts: Tensor, *, sdf_kind: str = 
 def sdf_net(params: Params, pts: Tensor, sdf_kind: str = "siren", prefix: str = "underlying", bound_rad: float = -1.0,
             quant: Optional[torch.dtype] = None) -> Tensor:
   """[sdf, latent(I)] of the SDF network at pts[N,3] (sdf.py:250-287), optionally intersected with a sphere (UnitSphere, 66-83)."""
+  sph = torch.linalg.norm(pts, dim=-1, ord=2) - bound_rad if bound_rad > 0 else None        # (computed first, as sdf.py:78 does: autograd's sums follow)
   if sdf_kind == "siren": raw = skip_mlp(pts, params, f"{prefix}.siren", "sin", quant=quant)
-  else: raw = skip_mlp(fourier_encode(pts, params[f"{prefix}.mlp.enc.basis"]), params, f"{prefix}.mlp", "leaky_relu", quant=quant)
+  else: raw = skip_mlp(torch.cat([pts, fourier_encode(pts, params[f"{prefix}.mlp.enc.basis"])], dim=-1), params, f"{prefix}.mlp", "leaky_relu", quant=quant)
   if bound_rad > 0:
-    sph = torch.linalg.norm(pts, dim=-1, ord=2) - bound_rad
     raw = torch.cat([torch.maximum(raw[..., 0], sph).unsqueeze(-1), raw[..., 1:]], dim=-1)
   return raw
+
+
+def sdf_normals(params: Params, pts: Tensor, *, sdf_kind: str = "siren", bound_rad: float = -1.0, prefix: str = "underlying") -> Tensor:
+  """SDFModel.normals (reference src/sdf.py:43-49) through utils.autograd (utils.py:266-277): grad_outputs = ones over EVERY output
+  channel of the SDF network, i.e. the gradient of sdf + sum(latent) with respect to the point."""
+  with torch.enable_grad():
+    p = pts.detach().clone().requires_grad_(True)
+    values = sdf_net(params, p, sdf_kind, prefix, bound_rad)
+    grad, = torch.autograd.grad(inputs=p, outputs=values, grad_outputs=torch.ones_like(values))
+  return grad
 
 
 def sphere_march(params: Params, r_o: Tensor, r_d: Tensor, *, sdf_kind: str = "siren", iters: int = 32, eps: float = 1e-3,

@@ -337,8 +337,29 @@ def case_sdf(name, seed=23, sdf_kind="siren", size=16, iters_fit=500, bound_rad=
   np.savez_compressed(os.path.join(HERE, name + ".npz"), **fx)
   print(name, "hit fraction", float(hit.float().mean()), "t range", float(t.min()), float(t.max()), "out mean", float(out.mean()))
 
+def case_sdf_normals(name="sdf_siren_normals"):
+  """SDFModel.normals (src/sdf.py:43-49, utils.autograd 266-277) of the reference's own SIREN SDF module holding the sphere-march
+  golden's parameters: at that golden's march points and at random points, bare and inside a UnitSphere (sdf.py:66-83; rad 1.0 = the fitted radius, so both branches of the max occur)."""
+  runner, nerf, refl, utils, cameras = ref_shim.load()
+  import src.sdf as rsdf
+  ref = np.load(os.path.join(HERE, "sdf_siren_march.npz"))
+  model = rsdf.sdf_kinds["siren"](intermediate_size=64)
+  sd = {k[len("param16.underlying."):]: torch.from_numpy(ref[k].astype(np.float32)) for k in ref.files if k.startswith("param16.underlying.")}
+  model.load_state_dict(sd, strict=True)
+  g = torch.Generator().manual_seed(77)
+  pts = torch.cat([torch.from_numpy(ref["pts"]).reshape(-1, 3)[:300], torch.randn(213, 3, generator=g) * 1.2])
+  n_bare = model.normals(pts.clone()).detach()
+  n_unit = rsdf.UnitSphere(inner=model, rad=1.0).normals(pts.clone()).detach()
+  with torch.no_grad(): vals = model(pts)
+  np.savez_compressed(os.path.join(HERE, name + ".npz"), kind="sdf_normals", sdf_kind="siren", params_from="sdf_siren_march", bound_rad=1.0,
+                      pts=pts.numpy(), normals=n_bare.numpy(), normals_unit=n_unit.numpy(), values=vals.numpy())
+  print(name, "points", pts.shape[0], "|n| mean", float(n_bare.norm(dim=-1).mean()), "unit-sphere branch taken", float((pts.norm(dim=-1) - 1.0 > vals[:, 0]).float().mean()))
+
 if __name__ == "__main__":
   check_rays()
+  if "--sdf-normals" in sys.argv:
+    case_sdf_normals()
+    sys.exit(0)
   if "--sdf" in sys.argv:
     case_sdf("sdf_siren_march")
     sys.exit(0)
@@ -382,4 +403,5 @@ if __name__ == "__main__":
   case_trained("plain_trained_t64")
   case_sdf("sdf_siren_march")
   case_sdf("sdf_siren_bisect", size=12, isect="bisect")
+  case_sdf_normals()
   case_plain("plain_poslinview_t16", seed=83, B=1, H=4, W=5, T=16, sigma_gain=20.0, top=398, left=397, stages=False, refl_kind="pos-linear-view")

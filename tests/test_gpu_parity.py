@@ -985,6 +985,42 @@ def test_sdf_bisect_vs_reference_golden(precision, hit_tol, p_tol, rgb_tol):
   with pytest.raises(NotImplementedError): N.FusedSDF("siren", 64, isect="secant")
 
 
+def test_sdf_normals_vs_reference_golden():
+  """nf_sdf_normals (forward-mode derivative of the SDF network on the fp32 pipeline) against the reference's SDFModel.normals
+  (autograd; golden), bare and inside a UnitSphere, and FusedSDF.normals / intersect_w_n; a Fourier-encoded SDF network vs the oracle."""
+  import nerf_atlas_b200 as N
+  from helpers import sdf_params
+  fx = load_golden("sdf_siren_normals")
+  P = sdf_params(fx)
+  m = N.FusedSDF("siren", 64, t_near=2.0, t_far=6.0, sigmoid_kind="upshifted", precision="fp32")
+  m.load_state_dict(P, strict=True); m = m.to(DEV).eval()
+  pts = torch.from_numpy(fx["pts"]).to(DEV)
+  scale = float(np.abs(fx["normals"]).max())
+  n = m.normals(pts).cpu().numpy()
+  assert np.abs(n - fx["normals"]).max() <= 2e-5 * scale, np.abs(n - fx["normals"]).max() / scale
+  nrm, vals = m.engine().sdf_normals(pts, want_values=True)
+  assert np.abs(vals.cpu().numpy() - fx["values"]).max() <= 2e-5 * max(1.0, float(np.abs(fx["values"]).max()))
+  m.bound_sphere_rad = float(fx["bound_rad"])
+  nu = m.normals(pts).cpu().numpy()
+  # (a point whose two SDF candidates agree to rounding may take the other branch of the max)
+  close = np.abs(np.linalg.norm(fx["pts"], axis=-1) - float(fx["bound_rad"]) - fx["values"][:, 0]) < 1e-5
+  assert np.abs(nu - fx["normals_unit"])[~close].max() <= 2e-5 * scale
+  m.bound_sphere_rad = -1.0
+  rays = torch.from_numpy(load_golden("sdf_siren_march")["rays"]).to(DEV)
+  p2, hit, tput, n2 = m.intersect_w_n(rays[..., :3], rays[..., 3:])
+  assert tput is None and n2.shape == p2.shape and bool(hit.any())
+  with torch.no_grad(): ref2 = O.sdf_normals(P, p2.reshape(-1, 3).cpu())
+  assert float((n2.reshape(-1, 3).cpu() - ref2).abs().max()) <= 2e-5 * scale
+  # Fourier-encoded SDF network (sdf.py:250-258): x0 = [p, sin(p B), cos(p B)] and its Jacobian
+  from helpers import volsdf_engine
+  Pv = O.make_volsdf_params(32, "mlp", 64, 0.1)
+  ef = volsdf_engine(Pv, "mlp", DEV, "upshifted", "fp32")
+  q = torch.randn(333, 3, generator=torch.Generator().manual_seed(4)) * 0.8
+  with torch.no_grad(): rf = O.sdf_normals(Pv, q, sdf_kind="mlp", prefix="sdf.underlying")
+  nf_ = ef.sdf_normals(q.to(DEV)).cpu()
+  assert float((nf_ - rf).abs().max()) <= 1e-4 * max(1.0, float(rf.abs().max())), float((nf_ - rf).abs().max())
+
+
 def test_poslinview_head_matches_reference_golden():
   """PlainNeRF + refl.PosLinearView (`--refl-kind pos-linear-view`; reference src/refl.py:248-290): the fp32 pipeline (the view
   sub-MLP's hidden 128 evaluated as 256 with zero-padded weights) vs a golden from the reference run and, on a larger ragged

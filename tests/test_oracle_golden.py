@@ -283,6 +283,18 @@ def test_sdf_bisect_oracle_matches_reference(golden_dir):
   assert 0.2 < fx["hit"].mean() < 0.8 and np.abs(fx["out"][~fx["hit"]]).max() == 0
 
 
+def test_sdf_normals_oracle_matches_reference(golden_dir):
+  """SDFModel.normals (reference src/sdf.py:43-49): the gradient of the SUM of all outputs (utils.autograd back-propagates ones over
+  every channel), bare and inside a UnitSphere; golden = the reference's own module holding the sphere-march golden's parameters."""
+  from helpers import sdf_params
+  fx = load(golden_dir, "sdf_siren_normals")
+  P = sdf_params(fx)
+  pts = torch.from_numpy(fx["pts"])
+  assert np.array_equal(O.sdf_normals(P, pts).numpy(), fx["normals"])
+  assert np.array_equal(O.sdf_normals(P, pts, bound_rad=float(fx["bound_rad"])).numpy(), fx["normals_unit"])
+  assert np.abs(fx["normals"] - fx["normals_unit"]).max() > 1e-2            # both branches of the max occur
+
+
 def test_poslinview_head_oracle_matches_reference_bit_exact(golden_dir):
   """PlainNeRF with `--refl-kind pos-linear-view` (refl.PosLinearView, reference src/refl.py:248-290; makefile `dnerf`, `gibson`)."""
   fx = load(golden_dir, "plain_poslinview_t16")
