@@ -151,6 +151,9 @@ __device__ __forceinline__ void wait_acc(uint32_t bar, uint32_t parity, int debu
 // MEASURED (profiles/r01_sin_poly_sweep.txt): 0 pairs 113.8 ms/frame, 2 pairs 115.0, 3 pairs 116.2, 4 pairs 119.7 -- the sin
 // epilogue is not MUFU-throughput-bound but issue/latency-bound, so the extra FMA-pipe instructions only cost.  Default 0.
 // boundary-warp mode (four more warps own the tile boundary); A/B switches of this round's measurements
+#ifndef NF_WIDE_CHUNKS
+#define NF_WIDE_CHUNKS 1      // narrow Linears: 8 / 16 K-steps per ring stage
+#endif
 #ifndef NF_BW
 #define NF_BW 1
 #endif
@@ -627,9 +630,11 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
           umma2_commit_mc(bar_wempty + stage * 8u);
           stage = nstage; phase = nphase;
         };
+        const uint32_t sbytes = bstep4 << 4;                                   // bytes of one K-step of this CTA's half image
+        const uint32_t spc = NF_WIDE_CHUNKS && sbytes * 16u <= (uint32_t)SPCT * 4096u ? 16u : NF_WIDE_CHUNKS && sbytes * 8u <= (uint32_t)SPCT * 4096u ? 8u : (uint32_t)SPCT;   // as the producers
 #pragma unroll 1
-        for (uint32_t c0 = 0; c0 < k0s; c0 += SPCT)
-          chunk(x4 + c0 * kstep4, k0s - c0 < (uint32_t)SPCT ? k0s - c0 : (uint32_t)SPCT, c0 ? 1u : 0u, hs == 0 && c0 + SPCT >= k0s);
+        for (uint32_t c0 = 0; c0 < k0s; c0 += spc)
+          chunk(x4 + c0 * kstep4, k0s - c0 < spc ? k0s - c0 : spc, c0 ? 1u : 0u, hs == 0 && c0 + spc >= k0s);
         // the second half of the hidden operand (columns 128-255) is handed over separately: the first eight hidden K-steps run
         // while the epilogue warps still convert the second half (they read the whole accumulator into registers first)
         bool hi_ok = false;
@@ -658,7 +663,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
           tc_fence_after();
           chunk4(h4 + 8u * kstep4, 1u, false);
           chunk4(h4 + 12u * kstep4, 1u, true);
-        } else if (NF_ISSUE_STRAIGHT && SPCT == 4 && hs == 16u) {
+        } else if (NF_ISSUE_STRAIGHT && SPCT == 4 && hs == 16u && spc == 4u) {
           // the same for the narrower Linears (density-out, the head's last Linear): their MMAs are issue-bound anyway
           chunk(h4, 4u, k0s ? 1u : 0u, false);
           chunk(h4 + 4u * kstep4, 4u, 1u, false);
@@ -668,7 +673,7 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
           tc_fence_after();
           chunk(h4 + 8u * kstep4, 4u, 1u, false);
           chunk(h4 + 12u * kstep4, 4u, 1u, true);
-        } else if (NF_ISSUE_STRAIGHT && SPCT == 3 && hs == 16u) {
+        } else if (NF_ISSUE_STRAIGHT && SPCT == 3 && hs == 16u && spc == 3u) {
           // the shared-wide-x0 ring (3 x 14 KB): 3 + 3 + 3 + 3 + 3 + 1 K-steps
           chunk(h4, 3u, k0s ? 1u : 0u, false);
           chunk(h4 + 3u * kstep4, 3u, 1u, false);
@@ -682,14 +687,14 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
           chunk(h4 + 15u * kstep4, 1u, 1u, true);
         } else
 #pragma unroll 1
-        for (uint32_t c0 = 0; c0 < hs || !hi_ok; c0 += SPCT) {
-          if (!hi_ok && (c0 + SPCT > 8u || c0 >= hs)) {
+        for (uint32_t c0 = 0; c0 < hs || !hi_ok; c0 += spc) {
+          if (!hi_ok && (c0 + spc > 8u || c0 >= hs)) {
             ST_ADD(2);
             mbar_wait(bar_a + (2u + slot) * 8u, (a_par >> (2u + slot)) & 1u); a_par ^= 1u << (2u + slot); hi_ok = true;
             ST_ADD(0);
             tc_fence_after();
           }
-          if (c0 < hs) chunk(h4 + c0 * kstep4, hs - c0 < (uint32_t)SPCT ? hs - c0 : (uint32_t)SPCT, (k0s || c0) ? 1u : 0u, c0 + SPCT >= hs);
+          if (c0 < hs) chunk(h4 + c0 * kstep4, hs - c0 < spc ? hs - c0 : spc, (k0s || c0) ? 1u : 0u, c0 + spc >= hs);
         }
         umma2_commit_mc((BW && li + 1 == n ? bar_bnd : bar_acc) + slot * 8u);      // BW: the path's last Linear reports to the boundary warps
       }
@@ -722,12 +727,15 @@ k_render_tc3(const __grid_constant__ NfPlan plan, const __grid_constant__ Tc3Pro
           // "stage empty" and the next copy's issue whenever the issuer is ahead)
           const uint32_t k0s = prog.lin[li].k0_steps, hs = prog.lin[li].h_steps, sb = prog.lin[li].step_bytes;
           const uint8_t* src = a.packed + prog.lin[li].w_off + (size_t)crank * prog.lin[li].half_bytes;
-          const uint32_t n0 = (k0s + SPCT - 1) / SPCT, nch = n0 + (hs + SPCT - 1) / SPCT;
+          // K-steps per chunk: SPCT at 4 KB per step (N = 256); a narrow Linear (density-out: 1.25 KB per step, the head's last Linear:
+          // 256 B) packs 8 or 16 steps into a stage -- fewer commits and probes for the issuer, whose MMAs are issue-bound there anyway
+          const uint32_t spc = NF_WIDE_CHUNKS && sb * 16u <= (uint32_t)SPCT * 4096u ? 16u : NF_WIDE_CHUNKS && sb * 8u <= (uint32_t)SPCT * 4096u ? 8u : (uint32_t)SPCT;
+          const uint32_t n0 = (k0s + spc - 1) / spc, nch = n0 + (hs + spc - 1) / spc;
 #pragma unroll 1
           for (uint32_t c = (uint32_t)p >= rs ? (uint32_t)p - rs : (uint32_t)p + NST - rs; c < nch; c += NST) {
             const bool hid = c >= n0;
-            const uint32_t st0 = (hid ? c - n0 : c) * SPCT, steps = hid ? hs : k0s, base = hid ? k0s : 0u;
-            const uint32_t nst = steps - st0 < (uint32_t)SPCT ? steps - st0 : (uint32_t)SPCT;
+            const uint32_t st0 = (hid ? c - n0 : c) * spc, steps = hid ? hs : k0s, base = hid ? k0s : 0u;
+            const uint32_t nst = steps - st0 < spc ? steps - st0 : spc;
             const uint32_t bytes = nst * sb + (c + 1 == nch ? sb >> 1 : 0u);
             const uint32_t par = use & 1u; ++use;
             ST_ADD(2);
