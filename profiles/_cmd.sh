@@ -1,2 +1,1 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/r02c_bench_8gpu.json 2> gpurun_out/r02c_bench_8gpu.err; grep "^{" gpurun_out/r02c_bench_8gpu.json | python -c "
-import sys,json; d=json.loads(sys.stdin.read()); print(d['n_gpus'], d['value'], d['ms_per_step']); print(d['train']); print(d['strong_scaling'])"; tail -2 gpurun_out/r02c_bench_8gpu.err | cut -c1-200
+timeout 900 python -m pytest tests -m gpu -x -q -k "ragged_grids" 2>&1 | tail -8

@@ -197,6 +197,8 @@ def test_boundary_warp_kernels_ragged_grids(P, T, nr):
   mp.load_state_dict(Pp, strict=True); mp = mp.to(DEV).eval()
   with torch.no_grad(): op = mp(rays.reshape(1, 1, nr, 6).to(DEV)).cpu().numpy().reshape(nr, 3)
   assert np.abs(op - rq).max() <= 3e-4, ("positional", np.abs(op - rq).max())
+  with torch.no_grad(): wq = O.plain_forward(Pp, rays.reshape(1, 1, nr, 6), ts, quant=torch.float16)["weights"].numpy().reshape(T, nr)
+  assert np.abs(mp.weights.cpu().numpy().reshape(T, nr) - wq).max() <= 1e-3, ("positional weights", np.abs(mp.weights.cpu().numpy().reshape(T, nr) - wq).max())
   # Mip (the radii need an image: H >= 3)
   if nr >= 9:
     h = 3; w = nr // 3
@@ -205,8 +207,10 @@ def test_boundary_warp_kernels_ragged_grids(P, T, nr):
     with torch.no_grad(): rm = O.plain_forward(Pm, slab, ts, mip="cone", mip_layout="intended", quant=torch.float16)["out"].numpy()
     em = _mip_engine(Pm, "cone", DEV)
     rad = em.ray_radii(slab.to(DEV)).reshape(-1)
-    om = em.render(slab.reshape(-1, 6).to(DEV), ts.to(DEV), radius=rad, precision="fp16", want_weights=False)[0].cpu().numpy().reshape(rm.shape)
-    assert np.abs(om - rm).max() <= 3e-4, ("mip", np.abs(om - rm).max())
+    om, _, wm = em.render(slab.reshape(-1, 6).to(DEV), ts.to(DEV), radius=rad, precision="fp16", want_weights=True)
+    assert np.abs(om.cpu().numpy().reshape(rm.shape) - rm).max() <= 3e-4, ("mip", np.abs(om.cpu().numpy().reshape(rm.shape) - rm).max())
+    with torch.no_grad(): wr = O.plain_forward(Pm, slab, ts, mip="cone", mip_layout="intended", quant=torch.float16)["weights"].numpy().reshape(T, -1)
+    assert np.abs(wm.cpu().numpy().T - wr).max() <= 1e-3, ("mip weights", np.abs(wm.cpu().numpy().T - wr).max())
 
 
 def test_tiny_nerf_vs_oracle():
