@@ -1,1 +1,2 @@
-timeout 900 python -m pytest tests -m gpu -x -q -k "ragged_grids" 2>&1 | tail -8
+NF_LIB=libnerf_b200_stats.so timeout 300 python profiles/stats_run.py 3 2>&1 | tail -14
+timeout 200 python profiles/ab_time.py libnerf_b200.so 2>&1 | tail -2
