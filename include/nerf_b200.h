@@ -241,7 +241,8 @@ int nf_mlp_forward(const nf_model_desc* desc, const void* packed, int32_t which,
 
 /* ---- training: forward with an activation stash, backward of the whole path ------------------------------------------
  * What the reference gets from PyTorch autograd (loss.backward(), runner.py:820) for model(rays): gradients of every
- * parameter of the path given d loss / d rgb.  NF_PREC_FP16_TC only (tcgen05 forward AND backward), PlainNeRF + View.
+ * parameter of the path given d loss / d rgb.  NF_PREC_FP16_TC only (tcgen05 forward AND backward): PlainNeRF + View (hash-encoded
+ * density MLP), and VolSDF's volume branch with the SIREN SDF + View (src/nerf.py:981-1013) including the learned beta (`scale`).
  *   1. nf_train_layout_of()    -> workspace size (total_bytes) and where everything lives in it
  *   2. nf_render_forward_aux() with aux.train_ws: the normal forward, plus the stash (per 128-sample tile and Linear: the
  *      input operand as the MMA consumed it, fp16; cos of the pre-activations for sin MLPs; raw density / colours per sample)
@@ -293,7 +294,8 @@ int nf_render_forward_aux(const nf_model_desc* desc, const void* packed,
                           const nf_render_aux* aux, int32_t precision, void* stream);
 /* Backward of the render that filled `train_ws` (same desc, packed, rays, ts): d_rgb[R,3] -> one gradient per parameter, in
  * the order of nf_pack_weights (grads_host[i] == NULL skips parameter i; every other gradient buffer is OVERWRITTEN, shapes as
- * the parameters).  Replaces loss.backward() through PlainNeRF.forward (reference runner.py:820, src/nerf.py:326-361). */
+ * the parameters; VolSDF: the last one is the scalar d loss / d beta).  Replaces loss.backward() through PlainNeRF.forward /
+ * VolSDF.forward (reference runner.py:820, src/nerf.py:326-361, 981-1013). */
 int nf_render_backward(const nf_model_desc* desc, const void* packed, void* train_ws, int64_t train_ws_bytes,
                        const float* rays, int64_t n_rays, const float* ts, int32_t T, int64_t ts_ray_stride,
                        const float* d_rgb, float* const* grads_host, int32_t n_grads, void* stream);
@@ -334,7 +336,7 @@ int nf_sdf_normals(const nf_model_desc* desc, const void* packed, const float* p
 /* ---- backward of the non-GEMM stages (first blocks of the training half; the reference differentiates these ops through
  *      PyTorch autograd, runner.py:820) --------------------------------------------------------------------------- */
 /* Backward of nf_composite: d_rgb[R,3] -> d_sigma_raw_out[R,T], d_feats_out[R,T,3] (same inputs as the forward; T <= 2048).
- * The gradient with respect to VolSDF's beta is not produced. */
+ * The gradient with respect to VolSDF's beta is not produced by this stand-alone stage (nf_render_backward produces it). */
 int nf_composite_backward(const nf_model_desc* desc, const void* packed, const float* sigma_raw, const float* feats,
                           const float* rays, int64_t n_rays, const float* ts, int32_t T, int64_t ts_ray_stride,
                           const float* d_rgb, float* d_sigma_raw_out, float* d_feats_out, void* stream);

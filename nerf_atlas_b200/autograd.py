@@ -16,8 +16,8 @@ from .model import RenderEngine
 class _Composite(torch.autograd.Function):
   @staticmethod
   def forward(ctx, engine: RenderEngine, sigma_raw, feats, rays, ts):
-    if engine.desc.density_act == 2:   # NF_DENS_LAPLACE: the gradient with respect to VolSDF's learned beta is not produced
-      raise NotImplementedError("autograd.composite: the Laplace density (VolSDF) has no backward for beta; use softplus / relu")
+    if engine.desc.density_act == 2:   # NF_DENS_LAPLACE: this stand-alone stage does not return d loss / d beta (fused_render does)
+      raise NotImplementedError("autograd.composite: the Laplace density (VolSDF) has no backward for beta here; use fused_render (FusedVolSDF.forward)")
     rgb, _, _ = engine.composite(sigma_raw, feats, rays, ts, want_weights=False)
     ctx.engine = engine
     ctx.save_for_backward(sigma_raw, feats, rays, ts)

@@ -25,6 +25,15 @@ __device__ __forceinline__ float dens_act_grad(float d, int kind, float beta) {
   return x > 20.f ? 1.f : 1.f / (1.f + expf(-x));
 }
 
+// d sigma / d beta of VolSDF's density (reference src/nerf.py:1000-1003: density = 1 / beta * laplace_cdf(-sdf, beta), then relu):
+//   sc = -sdf / beta;  d sigma / d beta = -cdf(sc) / beta^2 - pdf(sc) sc / beta^2,  pdf(sc) = exp(-|sc|) / 2
+__device__ __forceinline__ float dens_beta_grad(float d, float beta) {
+  const float sc = (-d) / beta;
+  const float cdf = sc <= 0.f ? expf(fminf(sc, 0.f)) / 2.f : 1.f - expf(-fmaxf(sc, 0.f)) / 2.f;
+  if (!(1.f / beta * cdf > 0.f)) return 0.f;                         // relu
+  return -(cdf + (expf(-fabsf(sc)) / 2.f) * sc) / (beta * beta);
+}
+
 // d act(v) / d v for the sigmoid family (reference src/utils.py:484-518); `d` = gradient with respect to the activated colours
 __device__ __forceinline__ void feat_act3_bwd(float r, float g, float b, int kind, float& dr, float& dg, float& db) {
   if (kind == NF_FEAT_SOFTMAX) {
@@ -57,7 +66,7 @@ __device__ __forceinline__ void feat_act3_bwd(float r, float g, float b, int kin
 __global__ void k_composite_bwd(int density_act, const float* __restrict__ beta_ptr, int bg, const float* __restrict__ sigma_raw,
                                 const float* __restrict__ feats, const float* __restrict__ rays, long long n_rays,
                                 const float* __restrict__ ts, int T, long long ts_stride, const float* __restrict__ d_rgb,
-                                float* __restrict__ d_sigma, float* __restrict__ d_feats, int feat_act) {
+                                float* __restrict__ d_sigma, float* __restrict__ d_feats, int feat_act, float* __restrict__ d_beta) {
   // feat_act >= 0: `feats` are the RAW colours (the training stash); the activation is applied here and d_feats is the
   // gradient with respect to the raw values.  feat_act < 0: `feats` are already activated (the stand-alone stage).
   __shared__ float s_carry[8][BWD_MAX_CHUNKS];
@@ -67,6 +76,7 @@ __global__ void k_composite_bwd(int density_act, const float* __restrict__ beta_
   const float beta = beta_ptr ? __ldg(beta_ptr) : 1.f;
   float* carry_in = s_carry[wib];
   const int nchunk = (T + 31) >> 5;
+  float acc_beta = 0.f;                                 // d_beta (nullable): sum over this thread's samples of dL/dsigma * d sigma / d beta
   for (long long ray = warp; ray < n_rays; ray += nwarps) {
     const float* r = rays + ray * 6;
     const float dx = __ldg(r + 3), dy = __ldg(r + 4), dz = __ldg(r + 5);
@@ -115,7 +125,9 @@ __global__ void k_composite_bwd(int density_act, const float* __restrict__ beta_
       const float later = (sfx - wa) + suffix;
       if (t < T) {
         const float dalpha = trans * A - later / om;
-        d_sigma[ray * T + t] = dalpha * delta * (1.f - al) * dens_act_grad(sr, density_act, beta);
+        const float dsig = dalpha * delta * (1.f - al);              // dL / d sigma
+        d_sigma[ray * T + t] = dsig * dens_act_grad(sr, density_act, beta);
+        if (d_beta) acc_beta = fmaf(dsig, dens_beta_grad(sr, beta), acc_beta);
         float* df = d_feats + (ray * T + t) * 3;
         float d0 = w * gr, d1 = w * gg, d2 = w * gb;
         if (feat_act >= 0) feat_act3_bwd(rr, rg, rb, feat_act, d0, d1, d2);
@@ -124,6 +136,11 @@ __global__ void k_composite_bwd(int density_act, const float* __restrict__ beta_
       suffix += __shfl_sync(0xffffffffu, sfx, 0);
     }
     __syncwarp();
+  }
+  if (d_beta) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc_beta += __shfl_xor_sync(0xffffffffu, acc_beta, d);
+    if (lane == 0 && acc_beta != 0.f) atomicAdd(d_beta, acc_beta);
   }
 }
 
@@ -222,13 +239,14 @@ int bwd_num_sms() {
 
 cudaError_t nf_launch_composite_bwd(const NfPlan& plan, const void* packed, const float* sigma_raw, const float* feats, const float* rays,
                                     int64_t n_rays, const float* ts, int T, int64_t ts_stride, const float* d_rgb, float* d_sigma,
-                                    float* d_feats, cudaStream_t st, int feat_act) {
+                                    float* d_feats, cudaStream_t st, int feat_act, float* d_beta) {
   if (n_rays == 0) return cudaSuccess;
+  if (plan.density_act != NF_DENS_LAPLACE) d_beta = nullptr;
   if (T > 32 * BWD_MAX_CHUNKS) return cudaErrorInvalidValue;
   const long long want = (n_rays * 32 + 255) / 256;
   const int grid = (int)(want < (long long)bwd_num_sms() * 8 ? want : (long long)bwd_num_sms() * 8);
   const float* beta = (plan.density_act == NF_DENS_LAPLACE && packed) ? reinterpret_cast<const float*>((const uint8_t*)packed + plan.scale_off) : nullptr;
-  k_composite_bwd<<<grid, 256, 0, st>>>(plan.density_act, beta, plan.bg, sigma_raw, feats, rays, n_rays, ts, T, ts_stride, d_rgb, d_sigma, d_feats, feat_act);
+  k_composite_bwd<<<grid, 256, 0, st>>>(plan.density_act, beta, plan.bg, sigma_raw, feats, rays, n_rays, ts, T, ts_stride, d_rgb, d_sigma, d_feats, feat_act, d_beta);
   return cudaGetLastError();
 }
 

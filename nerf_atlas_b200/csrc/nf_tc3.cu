@@ -1304,8 +1304,7 @@ const char* nf_train_unsupported(const NfPlan& p) {
   if (const char* why = nf_tc3_unsupported(p)) return why;
   if (p.kind != NF_KIND_PLAIN) return "training: PlainNeRF + View only (DynamicNeRF needs the gradient with respect to the sample position)";
   if (p.mip != NF_MIP_NONE || p.refl_kind != NF_REFL_VIEW || p.enc == NF_ENC_FOURIER) return "training: wide-x0 models (Mip, Positional, Fourier SDF) are not built";
-  if (p.kind == NF_KIND_PLAIN && p.enc != NF_ENC_HASH) return "training: PlainNeRF needs the hash-encoded density MLP (the SIREN SDF needs d/dp)";
-  if (p.density_act == NF_DENS_LAPLACE) return "training: the gradient of VolSDF's beta is not built";
+  // (VolSDF's SIREN SDF, x0 = [p], trains here: weights and beta; its eikonal regulariser (runner.py:736) needs d sdf / d p: nf_sdf_normals)
   if (p.bg == NF_BG_RANDOM) return "training: the random background is not built";
   for (int m = 0; m < p.n_mlps; ++m) if (p.mlp[m].act != NF_ACT_LEAKY && p.mlp[m].act != NF_ACT_SIN) return "training: LeakyReLU / sin MLPs only";
   return nullptr;

@@ -763,8 +763,18 @@ cudaError_t nf_launch_render_backward(const NfPlan& plan, const NfTrainPlan& tp,
   cudaError_t e;
   if ((e = cudaMemsetAsync(ws + tp.dw_begin, 0, (size_t)(tp.dw_end - tp.dw_begin), st)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(scale, 0, 16, st)) != cudaSuccess) return e;
-  // 1. composite backward with the feature activation's derivative folded in
-  if ((e = nf_launch_composite_bwd(plan, packed, sigma, rgbraw, rays, tp.n_rays, ts, tp.T, ts_stride, d_rgb, dsigma, drgbraw, st, plan.feat_act)) != cudaSuccess) return e;
+  // 1. composite backward with the feature activation's derivative folded in (VolSDF: + the gradient of the learned beta, the last
+  //    parameter of nf_pack_weights' order)
+  float* d_beta = nullptr;
+  if (plan.density_act == NF_DENS_LAPLACE) {
+    int pi_b = 0;
+    for (int m = 0; m < plan.n_mlps; ++m) pi_b += 2 * plan.mlp[m].n_lin;
+    if (plan.enc == NF_ENC_HASH) pi_b += plan.hash_levels;
+    if (plan.enc == NF_ENC_FOURIER) pi_b += 1;
+    d_beta = grads[pi_b];
+    if (d_beta && (e = cudaMemsetAsync(d_beta, 0, sizeof(float), st)) != cudaSuccess) return e;
+  }
+  if ((e = nf_launch_composite_bwd(plan, packed, sigma, rgbraw, rays, tp.n_rays, ts, tp.T, ts_stride, d_rgb, dsigma, drgbraw, st, plan.feat_act, d_beta)) != cudaSuccess) return e;
   // 2. loss scale
   const long long ns = tp.n_rays * tp.T;
   const int sms = tr_num_sms();

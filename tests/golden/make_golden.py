@@ -83,6 +83,29 @@ def case_volsdf(name, seed, sdf_kind, B, H, W, T, top=0, left=0):
   np.savez_compressed(os.path.join(HERE, name + ".npz"), **fx)
   print(name, "out", out.shape, "mean", float(out.mean()), "acc-before-last", float(model.weights[:-1].sum(0).mean()))
 
+def case_volsdf_grads(name, seed, B, H, W, T, top=0, left=0, beta=0.25):
+  """Gradients of the reference's VolSDF (SIREN SDF + View, volume branch) through its own loss.backward(): every Linear of both
+  MLPs (every 16th row of the 256-row matrices) and the learned `scale` (beta)."""
+  params = O.make_volsdf_params(seed, "siren", 64, beta)
+  rays = O.make_rays(B, H, W, size=800, seed=seed, crop_top=top, crop_left=left)
+  model, args = ref_shim.build_model("volsdf", T, extra=("--sdf-kind", "siren"))
+  model.load_state_dict({k: v.clone() for k, v in params.items()}, strict=True)
+  model.eval()
+  for p in model.parameters(): p.requires_grad_(p.dtype.is_floating_point and p.numel() > 0)
+  g = np.random.default_rng(seed)
+  target = torch.from_numpy(g.uniform(0, 1, size=(B, H, W, 3)).astype(np.float32))
+  out = model(rays)
+  loss = torch.nn.functional.mse_loss(out, target)
+  loss.backward()
+  fx = dict(kind="volsdf_grads", sdf_kind="siren", seed=seed, beta=beta, B=B, H=H, W=W, T=T, top=top, left=left, near=float(args.near), far=float(args.far),
+            sigmoid=args.sigmoid_kind, target=target.numpy(), out=out.detach().numpy(), loss=float(loss), ts=model.ts.numpy())
+  for n, p in model.named_parameters():
+    if p.grad is None: continue
+    gr = p.grad.numpy()
+    fx["grad." + n] = gr[::16] if gr.ndim == 2 and gr.shape[0] == 256 else gr
+  np.savez_compressed(os.path.join(HERE, name + ".npz"), **fx)
+  print(name, "loss", float(loss), "d scale", float(model.scale.grad), "grads", sum(1 for k in fx if k.startswith("grad.")))
+
 def case_dnerf(name, seed, B, H, W, T, top=0, left=0):
   runner, nerf, refl, utils, cameras = ref_shim.load()
   params = O.make_dnerf_params(seed, 64)
@@ -372,6 +395,9 @@ if __name__ == "__main__":
     sys.exit(0)
   if "--dtu" in sys.argv:
     case_dtu_rays("dtu_rays")
+    sys.exit(0)
+  if "--volsdf-grads" in sys.argv:
+    case_volsdf_grads("volsdf_siren_t32_grads", seed=33, B=1, H=3, W=4, T=32, top=398, left=397)
     sys.exit(0)
   if "--grads" in sys.argv:
     case_plain_grads("plain_t16_grads", seed=91, B=1, H=3, W=4, T=16, top=398, left=397)

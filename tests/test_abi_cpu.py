@@ -364,7 +364,10 @@ def test_train_layout_host_logic():
     for (o0, n0), (o1, _) in zip(regions, regions[1:]): assert o0 % 1024 == 0 and o0 + n0 <= o1, (R, T, o0, n0, o1)
     assert regions[-1][0] + regions[-1][1] <= lay.total_bytes
   assert [(lay.lin[i].m, lay.lin[i].j) for i in range(12)] == [(0, j) for j in range(6)] + [(1, j) for j in range(6)]
-  for bad in (N.describe_volsdf("siren"), N.describe_dyn(), N.describe_plain(64, "upshifted", "black", mip="cylinder"), N.describe_tiny(),
+  lay = _lib.TrainLayout()                                                      # VolSDF, SIREN SDF + View: 7 + 6 Linears, cos stash for both MLPs
+  assert lib.nf_train_layout_of(C.byref(N.describe_volsdf("siren")), 16, 16, C.byref(lay)) == 0 and lay.n_lin == 13
+  assert all((lay.lin[i].c_off >= 0) == (lay.lin[i].k_hidden > 0) for i in range(13))
+  for bad in (N.describe_volsdf("mlp"), N.describe_dyn(), N.describe_plain(64, "upshifted", "black", mip="cylinder"), N.describe_tiny(),
               N.describe_plain(64, "upshifted", "black", refl_kind="pos"), N.describe_plain(64, "upshifted", "random")):
     lay = _lib.TrainLayout()
     assert lib.nf_train_layout_of(C.byref(bad), 16, 16, C.byref(lay)) == -2        # NF_E_UNSUPPORTED

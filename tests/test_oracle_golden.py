@@ -217,6 +217,28 @@ def test_oracle_autograd_matches_the_reference_backward(golden_dir):
     assert np.abs(g[rows].numpy() - fx[f"grad.emb{lvl}.vals"]).max() <= 1e-6 * max(np.abs(fx[f"grad.emb{lvl}.vals"]).max(), 1e-3)
 
 
+def test_oracle_volsdf_autograd_matches_the_reference_backward(golden_dir):
+  """VolSDF (SIREN SDF + View, volume branch; nerf.py:981-1013): autograd through the oracle == the reference's own loss.backward(),
+  every Linear of both MLPs and the learned `scale` (beta) -- the parity target of the fused VolSDF training step."""
+  fx = load(golden_dir, "volsdf_siren_t32_grads")
+  P = O.make_volsdf_params(int(fx["seed"]), "siren", 64, float(fx["beta"]))
+  names = [k[len("grad."):] for k in fx if k.startswith("grad.")]
+  assert "scale" in names and len(names) == 27
+  for n in names: P[n] = P[n].clone().requires_grad_(True)
+  rays = O.make_rays(int(fx["B"]), int(fx["H"]), int(fx["W"]), 800, int(fx["seed"]), int(fx["top"]), int(fx["left"]))
+  ts = O.compute_ts(float(fx["near"]), float(fx["far"]), int(fx["T"]))
+  assert np.array_equal(ts.numpy(), fx["ts"])
+  out = O.volsdf_forward(P, rays, ts, sdf_kind="siren", sigmoid=str(fx["sigmoid"]))["out"]
+  assert np.array_equal(out.detach().numpy(), fx["out"])
+  loss = torch.nn.functional.mse_loss(out, torch.from_numpy(fx["target"]))
+  assert abs(float(loss) - float(fx["loss"])) <= 1e-7
+  loss.backward()
+  for n in names:
+    g = P[n].grad.numpy(); ref = fx["grad." + n]
+    if g.ndim == 2 and g.shape[0] == 256: g = g[::16]
+    assert np.abs(g - ref).max() <= 1e-6 * max(np.abs(ref).max(), 1e-3), n
+
+
 def test_dtu_rays_oracle_matches_reference_camera(golden_dir):
   """DTUCamera.sample_positions (reference src/cameras.py:189-223) restated; golden = the reference camera's own output."""
   fx = load(golden_dir, "dtu_rays")
