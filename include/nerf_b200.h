@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NF_ABI_VERSION 6
+#define NF_ABI_VERSION 7
 
 /* error codes (negative; positive values are cudaError_t) */
 #define NF_E_BADARG    (-1)
@@ -226,6 +226,13 @@ int nf_hash_encode(const nf_model_desc* desc, const void* packed, const float* p
 int nf_composite(const nf_model_desc* desc, const void* packed, const float* sigma_raw, const float* feats,
                  const float* rays, int64_t n_rays, const float* ts, int32_t T, int64_t ts_ray_stride,
                  float* rgb_out, float* alpha_out, float* weights_out, void* stream);
+/* volumetric_integrate (reference src/nerf.py:79-80) of per-sample values other than the colours, over the weights a render kept:
+ *   out[r, c] = sum_t weights[r, t] * vals[r * vals_ray_stride + t * channels + c]
+ * depth (runner.py:511-514,894-897): vals = ts, channels 1, vals_ray_stride 0 (shared ts[T]) or T' (per-ray ts); flow / rigidity
+ * maps (runner.py:521-531,909-914): vals = the rigid_dp / rigidity side channels of nf_render_aux ([R,T,3] / [R,T,1] ray-major),
+ * vals_ray_stride = T * channels.  channels is 1 or 3.  HBM-bound: 4 T (1 + channels) bytes read per ray. */
+int nf_integrate(const float* weights, const float* vals, int64_t n_rays, int32_t T, int32_t channels, int64_t vals_ray_stride,
+                 float* out, void* stream);
 /* Hierarchical resampling for the coarse+fine configuration: restatement of the reference's dead
  * sample_pdf (reference src/nerf.py:1745-1779, called from CoarseFineNeRF.from_pts nerf.py:573-577):
  * bins = mid-points of ts_coarse[T]; pdf from weights[r, 1:T-1] + 1e-5; inverse-CDF at u[R,Nf] in [0,1)

@@ -7,7 +7,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, os.environ.get("NF_LIB", "libnerf_b200.so"))
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 # enums of include/nerf_b200.h
 ACT = {"none": 0, "leaky_relu": 1, "sin": 2, "relu": 3}
 ENC = {"none": 0, "hash": 1, "fourier": 2}
@@ -90,6 +90,7 @@ EXPORTS = {
                              C.c_int32, C.c_void_p]),
   "nf_sdf_bisect": (C.c_int, [C.POINTER(ModelDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_int32, C.c_float, C.c_float,
                               C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+  "nf_integrate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
   "nf_sdf_normals": (C.c_int, [C.POINTER(ModelDesc), C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
   "nf_adam_step_multi": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float,
                                    C.c_float, C.c_int32, C.c_void_p]),

@@ -274,6 +274,18 @@ int nf_composite(const nf_model_desc* desc, const void* packed, const float* sig
   return e == cudaSuccess ? 0 : cuda_fail(e, "nf_composite");
 }
 
+int nf_integrate(const float* weights, const float* vals, int64_t n_rays, int32_t T, int32_t channels, int64_t vals_ray_stride,
+                 float* out, void* stream) {
+  if (n_rays < 0) return fail(NF_E_BADARG, "n_rays < 0");
+  if (n_rays == 0) return 0;
+  if (!weights || !vals || !out) return fail(NF_E_BADARG, "nf_integrate: null pointer");
+  if (T < 1) return fail(NF_E_BADARG, "nf_integrate: T >= 1");
+  if (channels != 1 && channels != 3) return fail(NF_E_UNSUPPORTED, "nf_integrate: 1 or 3 channels (depth / rigidity, flow)");
+  if (vals_ray_stride != 0 && vals_ray_stride < (int64_t)T * channels) return fail(NF_E_BADARG, "nf_integrate: vals_ray_stride is 0 (values shared by all rays) or >= T * channels");
+  cudaError_t e = nf_launch_integrate(weights, vals, n_rays, T, channels, vals_ray_stride, out, (cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "nf_integrate");
+}
+
 int nf_sample_pdf(const float* ts_coarse, int32_t T, const float* weights, int64_t n_rays, const float* u, int32_t n_fine,
                   float* ts_out, void* stream) {
   if (n_rays < 0) return fail(NF_E_BADARG, "n_rays < 0");

@@ -812,6 +812,42 @@ cudaError_t nf_launch_sample_pdf(const float* ts, int T, const float* weights, i
   return cudaGetLastError();
 }
 
+// volumetric_integrate (reference src/nerf.py:79-80) of per-sample values other than the colours: out[r, c] = sum_t w[r, t] v[r, t, c]
+// (depth: v = ts; flow / rigidity maps: v = rigid_dp / rigidity, runner.py:511-531,894-916).  A warp per ray, lanes over (t, c) pairs
+// in memory order (coalesced), one shuffle reduction per channel.  HBM-bound: 4 T (1 + C) bytes read per ray.
+template <int C>
+__global__ void k_integrate(const float* __restrict__ w, const float* __restrict__ v, long long n_rays, int T, long long v_stride,
+                            float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long ray = warp; ray < n_rays; ray += nwarps) {
+    const float* wr = w + ray * T; const float* vr = v + ray * v_stride;
+    float acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0.f;
+    for (int t = lane; t < T; t += 32) {
+      const float wt = __ldg(wr + t);
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[c] = fmaf(wt, __ldg(vr + (long long)t * C + c), acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], d);
+      if (lane == 0) out[ray * C + c] = acc[c];
+    }
+  }
+}
+cudaError_t nf_launch_integrate(const float* weights, const float* vals, int64_t n_rays, int T, int C, int64_t vals_ray_stride, float* out, cudaStream_t st) {
+  if (n_rays == 0) return cudaSuccess;
+  const long long want = (n_rays * 32 + 255) / 256;
+  const int grid = (int)(want < (long long)num_sms() * 8 ? want : (long long)num_sms() * 8);
+  if (C == 1) k_integrate<1><<<grid, 256, 0, st>>>(weights, vals, n_rays, T, vals_ray_stride, out);
+  else if (C == 3) k_integrate<3><<<grid, 256, 0, st>>>(weights, vals, n_rays, T, vals_ray_stride, out);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
 cudaError_t nf_launch_composite(const NfPlan& plan, const void* packed, const float* sigma_raw, const float* feats, const float* rays, int64_t n_rays,
                                 const float* ts, int T, int64_t ts_stride, float* rgb, float* alpha, float* weights, cudaStream_t st) {
   if (n_rays == 0) return cudaSuccess;

@@ -48,6 +48,7 @@ cudaError_t nf_launch_pack_all(const NfPlan& plan, const float* const* params, v
 cudaError_t nf_launch_copy_tables(const float* const* src, float* const* dst, int n, size_t bytes, cudaStream_t st);
 cudaError_t nf_launch_render_backward(const NfPlan& plan, const NfTrainPlan& tp, const void* packed, void* ws, const float* rays,
                                       const float* ts, int64_t ts_stride, const float* d_rgb, float* const* grads, cudaStream_t st);
+cudaError_t nf_launch_integrate(const float* weights, const float* vals, int64_t n_rays, int T, int C, int64_t vals_ray_stride, float* out, cudaStream_t st);
 // backward of the non-GEMM stages (nf_bwd.cu)
 cudaError_t nf_launch_composite_bwd(const NfPlan& plan, const void* packed, const float* sigma_raw, const float* feats, const float* rays,
                                     int64_t n_rays, const float* ts, int T, int64_t ts_stride, const float* d_rgb, float* d_sigma,

@@ -1036,6 +1036,31 @@ class FusedDynamicNeRF(nn.Module):
     return rgb.reshape(*B, 3)
 
 
+def volumetric_integrate(weights: torch.Tensor, other: torch.Tensor) -> torch.Tensor:
+  """The reference's free function (src/nerf.py:79-80: ``sum(weights[..., None] * other, dim=0)``) for the quantities the runner
+  integrates over the weights a render kept -- depth (``other = model.nerf.ts[:, None, None, None, None]``, runner.py:511-514,
+  894-897), flow and rigidity maps (``other = model.rigid_dp / model.rigidity``, runner.py:521-531,909-914) -- on `nf_integrate`.
+  ``weights[T, *B]``, ``other[T, *B, C]`` or ``[T, 1, ..., 1]`` (shared by all rays), C in (1, 3) -> ``[*B, C]``.  The modules keep
+  ``weights`` and the side channels as transposed views of ray-major buffers, so nothing is copied for them."""
+  if not weights.is_cuda: raise RuntimeError("volumetric_integrate needs CUDA tensors: the fused path has no CPU fallback")
+  T = weights.shape[0]; B = weights.shape[1:]
+  w = weights.to(torch.float32).movedim(0, -1).reshape(-1, T).contiguous()
+  R = w.shape[0]
+  if other.shape[0] != T: raise ValueError(f"volumetric_integrate: other has {other.shape[0]} samples, weights {T}")
+  if other.numel() == T:
+    v = other.to(torch.float32).reshape(T).contiguous(); Cn, stride = 1, 0
+  else:
+    if tuple(other.shape[1:-1]) != tuple(B): raise ValueError(f"volumetric_integrate: other {tuple(other.shape)} does not match weights {tuple(weights.shape)}")
+    Cn = other.shape[-1]
+    v = other.to(torch.float32).movedim(0, -2).reshape(R, T * Cn).contiguous(); stride = T * Cn
+  if Cn not in (1, 3): raise NotImplementedError("volumetric_integrate: 1 or 3 channels")
+  out = torch.empty(R, Cn, dtype=torch.float32, device=weights.device)
+  with torch.cuda.device(weights.device):
+    rc = _lib.lib().nf_integrate(_ptr(w), _ptr(v), R, T, Cn, stride, _ptr(out), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+  _lib.check(rc, "nf_integrate")
+  return out.reshape(*B, Cn)
+
+
 class FusedTinyNeRF(FusedNeRF):
   """Drop-in for TinyNeRF with the intended density semantics (reference src/nerf.py:278-305)."""
   kind = "tiny"

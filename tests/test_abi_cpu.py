@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
   assert len(names) >= 10
   for n in names: assert hasattr(l, n), f"{n} declared in include/nerf_b200.h but not exported"
   assert sorted(_lib.EXPORTS) == names, "ctypes binding table and header disagree"
-  assert _lib.lib().nf_version() == _lib.ABI_VERSION == 6
+  assert _lib.lib().nf_version() == _lib.ABI_VERSION == 7
   assert _lib.lib().nf_build_flags() == 0 or os.environ.get('NF_LIB'), 'the default library must be the product build (no experiment hooks)'
 
 def test_descriptor_host_logic():

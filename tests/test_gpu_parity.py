@@ -1052,3 +1052,43 @@ def test_poslinview_head_matches_reference_golden():
   m.precision = "fp16"
   with pytest.raises(RuntimeError):
     with torch.no_grad(): m(rays)
+
+
+# ---------------------------------------------------------------- depth / flow / rigidity maps (runner.py:511-531,894-916)
+def test_volumetric_integrate_depth_flow_rigidity_maps():
+  """`nerf.volumetric_integrate(model.nerf.weights, other)` for the quantities the runner integrates after a render: depth
+  (other = ts[:, None, None, None, None]) on a PlainNeRF, flow (rigid_dp, 3 channels) and rigidity maps on a DynamicNeRF's retained
+  side channels -- against the oracle's volumetric_integrate (== the reference's one-line function) on the SAME weights, to 1e-6
+  relative (the summation order over T differs), and against the oracle's own weights within the render's tolerance."""
+  import nerf_atlas_b200 as N
+  P = O.make_plain_params(1337, 64, 20.0)
+  m = N.FusedPlainNeRF(steps=96, t_near=2, t_far=6, intermediate_size=64, sigmoid_kind="upshifted", precision="fp32")
+  m.load_state_dict(P, strict=True); m = m.to(DEV).eval()
+  rays = O.make_rays(2, 7, 9, seed=5, crop_top=390, crop_left=392)
+  with torch.no_grad(): m(rays.to(DEV))
+  depth = N.volumetric_integrate(m.nerf.weights, m.nerf.ts[:, None, None, None, None])
+  assert depth.shape == (2, 7, 9, 1)
+  want = O.volumetric_integrate(m.weights.cpu(), m.ts.cpu()[:, None, None, None, None])
+  assert float((depth.cpu() - want).abs().max()) <= 1e-6 * float(want.abs().max())
+  ref = O.plain_forward(P, rays, m.ts.cpu())
+  want_ref = O.volumetric_integrate(ref["weights"], m.ts.cpu()[:, None, None, None, None])
+  assert float((depth.cpu() - want_ref).abs().max()) <= 1e-4
+  # a copy in another memory layout gives the same map (the helper makes its own ray-major copy)
+  d2 = N.volumetric_integrate(m.weights.contiguous(), m.ts[:, None, None, None, None].contiguous())
+  assert torch.equal(d2, depth)
+  # DynamicNeRF: flow and rigidity maps from the retained side channels
+  fx = load_golden("dnerf_direct_t64")
+  Pd = O.make_dnerf_params(int(fx["seed"]), 64)
+  raysd = O.make_rays(int(fx["B"]), int(fx["H"]), int(fx["W"]), 800, int(fx["seed"]), int(fx["top"]), int(fx["left"]))
+  canon = N.FusedPlainNeRF(steps=int(fx["T"]), t_near=float(fx["near"]), t_far=float(fx["far"]), intermediate_size=64,
+                           sigmoid_kind=str(fx["sigmoid"]), bg=str(fx["bg"]), precision="fp32")
+  d = N.FusedDynamicNeRF(canon); d.load_state_dict(Pd, strict=True); d = d.to(DEV).eval()
+  with torch.no_grad(): d((raysd.to(DEV), torch.from_numpy(fx["times"]).to(DEV)))
+  w = d.canonical.weights
+  for name in ("rigid_dp", "rigidity"):
+    other = getattr(d, name)
+    got = N.volumetric_integrate(w, other)
+    want = O.volumetric_integrate(w.cpu(), other.cpu())
+    assert got.shape == want.shape == tuple(w.shape[1:]) + (3,)
+    assert float((got.cpu() - want).abs().max()) <= 1e-6 * max(float(want.abs().max()), 1e-3), name
+  with pytest.raises(RuntimeError): N.volumetric_integrate(w.cpu(), d.rigid_dp.cpu())
