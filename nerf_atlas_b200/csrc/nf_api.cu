@@ -126,6 +126,7 @@ int nf_train_layout_of(const nf_model_desc* desc, int64_t n_rays, int32_t T, nf_
   NfPlan p; if (int rc = plan_of(desc, &p)) return rc;
   if (!out || n_rays < 0 || T < 1) return fail(NF_E_BADARG, "nf_train_layout_of: bad argument");
   if (const char* why = nf_train_unsupported(p)) return fail(NF_E_UNSUPPORTED, why);
+  if (p.refl_kind == NF_REFL_POSITIONAL && (T & 31)) return fail(NF_E_UNSUPPORTED, "training the Positional head: T must be a multiple of 32 (warp-aligned rays)");
   if (int rc = nf_build_train_plan(p, n_rays, T, out)) return fail(rc, "nf_train_layout_of: too many Linear layers");
   return 0;
 }

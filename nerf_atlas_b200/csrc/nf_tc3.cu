@@ -1303,7 +1303,11 @@ const char* nf_tc3_unsupported(const NfPlan& p) {
 const char* nf_train_unsupported(const NfPlan& p) {
   if (const char* why = nf_tc3_unsupported(p)) return why;
   if (p.kind != NF_KIND_PLAIN) return "training: PlainNeRF + View only (DynamicNeRF needs the gradient with respect to the sample position)";
-  if (p.mip != NF_MIP_NONE || p.refl_kind != NF_REFL_VIEW || p.enc == NF_ENC_FOURIER) return "training: wide-x0 models (Mip, Positional, Fourier SDF) are not built";
+  if (p.mip != NF_MIP_NONE || p.enc == NF_ENC_FOURIER) return "training: wide-x0 models (Mip, Fourier SDF) are not built";
+  if (p.refl_kind != NF_REFL_VIEW && p.refl_kind != NF_REFL_POSITIONAL) return "training: View and Positional heads only";
+  // the Positional head (refl.py:230-245): on its boundary-warp instantiation (112-column x0 per slot; T % 32 == 0, checked at launch)
+  if (p.refl_kind == NF_REFL_POSITIONAL && (p.enc != NF_ENC_HASH || p.hash_levels * 4 != 32 || p.mlp[0].k0_pad > p.intermediate || p.mlp[1].k0_pad > X0K_POS))
+    return "training: Positional head needs the hash-encoded density MLP (8 levels x 4) and an x0 of at most 112 columns";
   // (VolSDF's SIREN SDF, x0 = [p], trains here: weights and beta; its eikonal regulariser (runner.py:736) needs d sdf / d p: nf_sdf_normals)
   if (p.bg == NF_BG_RANDOM) return "training: the random background is not built";
   for (int m = 0; m < p.n_mlps; ++m) if (p.mlp[m].act != NF_ACT_LEAKY && p.mlp[m].act != NF_ACT_SIN) return "training: LeakyReLU / sin MLPs only";
@@ -1342,7 +1346,7 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
 #endif
   // the Positional head with warp-aligned rays: per-slot 112-column x0, boundary warps (k_render_tc3<2, 4, 4, 1, ..., BW, 112>)
   const bool pos_bw = NF_BW && NF_POS_BW && plan.refl_kind == NF_REFL_POSITIONAL && plan.mip == NF_MIP_NONE && plan.kind == NF_KIND_PLAIN && (T & 31) == 0 &&
-                      plan.mlp[0].k0_pad <= plan.intermediate && plan.mlp[1].k0_pad <= X0K_POS && !tp && !(aux && (aux->pts || plan.bg == NF_BG_RANDOM));
+                      plan.mlp[0].k0_pad <= plan.intermediate && plan.mlp[1].k0_pad <= X0K_POS && !(aux && (aux->pts || plan.bg == NF_BG_RANDOM));
   Tc3Prog prog;
   if (!build_prog3(plan, &prog, pos_bw ? X0K_POS : X0K)) return cudaErrorNotSupported;
   const bool wide = prog.single != 0 || plan.mip != NF_MIP_NONE || plan.refl_kind != NF_REFL_VIEW;
@@ -1353,6 +1357,7 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
   if (dynk) { ring = 3; epiw = 16; }
   const bool train = tp != nullptr;
   if (train) { ring = 3; epiw = 16; }
+  if (train && wide && !pos_bw) return cudaErrorNotSupported;      // the Positional head trains on its boundary-warp instantiation (T % 32 == 0)
   if (want_aux) {
     // from_pts / random background: the AUX instantiation of the plain two-tile kernel, or the DynamicNeRF one (background only)
     if (wide || train || (dynk && a.pts)) return cudaErrorNotSupported;
@@ -1415,6 +1420,7 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
 #else
   if (wb) go(k_render_tc3<3, 3, 4, 2, false, false, false, true>);       // three 14 KB stages (3 K-steps)
 #endif
+  else if (pos_bw && train) go(k_render_tc3<2, 4, 4, 1, false, true, false, true, X0K_POS>);
   else if (pos_bw) go(k_render_tc3<2, 4, 4, 1, false, false, false, true, X0K_POS>);
   else if (bw) {
     if (train) go(k_render_tc3<3, 4, 4, 0, false, true, false, true>);

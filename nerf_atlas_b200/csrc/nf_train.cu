@@ -152,7 +152,7 @@ struct __align__(16) BwPhase {
   int32_t kind, act, job0, n_jobs;                 // the jobs run AFTER this phase's epilogue
   uint32_t s_off256, s_tile256, s_bytes, has_xa;   // stash tile this phase's act' needs
   uint32_t g_off256, g_tile256, g_cols, k0_pad;    // where the G this phase produces goes (g_cols = its width)
-  int32_t inter, pad0_, pad1_, pad2_;
+  int32_t inter, hcols2, pad1_, pad2_;             // hcols2 (PH_MID): x0 columns [inter, inter + hcols2) are the head's own hash features
 };
 struct __align__(16) BwProg { int32_t n_phases, n_jobs, pad0_, pad1_; BwPhase ph[NF_TRAIN_MAX_LIN + 1]; BwJob job[BW_MAX_JOBS]; };
 
@@ -160,6 +160,7 @@ struct BwArgs {
   const uint8_t* packed; uint8_t* ws;
   long long n_rays, n_tiles; int T, rpu, tpr;
   const float* d_sigma; const float* d_rgbraw; float* dx0_out; const float* scale;
+  float* dx0b_out;      // Positional head: gradient of its own encoder's features [n_tiles * 128][32]
 };
 
 __device__ __forceinline__ void stg_v4(uint8_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -331,6 +332,11 @@ k_bwd_chain(const __grid_constant__ BwProg prog, const BwArgs a) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) o[k] = make_float4(d[4 * k] * invS, d[4 * k + 1] * invS, d[4 * k + 2] * invS, d[4 * k + 3] * invS);
               }
+            } else if (P.hcols2 && un * 16 >= P.inter && un * 16 < P.inter + P.hcols2) {
+              // the Positional head's x0 (tensor order [inter(I), hash'(4L), p, p, pad]): its own encoder's feature columns leave as fp32, unscaled
+              float4* o = reinterpret_cast<float4*>(a.dx0b_out + ((size_t)g * ROWS + row) * 32 + (un * 16 - P.inter));
+#pragma unroll
+              for (int k = 0; k < 4; ++k) o[k] = make_float4(d[4 * k] * invS, d[4 * k + 1] * invS, d[4 * k + 2] * invS, d[4 * k + 3] * invS);
             } else if (un * 16 < P.inter) {
               // columns [0, I) of the RGB head's x0 are the density MLP's `intermediate` outputs (tensor order [inter(I), sigma])
               uint32_t o[8];
@@ -421,6 +427,7 @@ bool build_bw_prog(const NfPlan& plan, const NfTrainPlan& tp, BwProg* P) {
         Ph.kind = li == 0 ? PH_END : PH_MID;
         Ph.s_off256 = (uint32_t)(L.a_off >> 8); Ph.s_tile256 = (uint32_t)(L.a_tile >> 8); Ph.s_bytes = (uint32_t)L.k0_pad * 256u;
         Ph.k0_pad = (uint32_t)L.k0_pad; Ph.inter = plan.intermediate;
+        if (Ph.kind == PH_MID && plan.refl_kind == NF_REFL_POSITIONAL) Ph.hcols2 = plan.hash_levels * 4;
         for (int k = li + 1; k < n && tp.lin[k].m == L.m; ++k) if (tp.lin[k].k0_pad) Ph.has_xa = 1;
       }
       if (li > 0) {
@@ -787,6 +794,7 @@ cudaError_t nf_launch_render_backward(const NfPlan& plan, const NfTrainPlan& tp,
     BwArgs a{};
     a.packed = (const uint8_t*)packed; a.ws = ws; a.n_rays = tp.n_rays; a.n_tiles = tp.n_tiles; a.T = tp.T; a.rpu = tp.rpu; a.tpr = tp.tpr;
     a.d_sigma = dsigma; a.d_rgbraw = drgbraw; a.dx0_out = dx0; a.scale = scale;
+    a.dx0b_out = dx0 + (size_t)tp.n_tiles * NF_TC_ROWS * 32;
     if ((e = cudaFuncSetAttribute(k_bwd_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwSmem))) != cudaSuccess) return e;
     const int grid = (int)(tp.n_tiles < sms ? tp.n_tiles : sms);
     k_bwd_chain<<<grid, BW_THREADS, sizeof(BwSmem), st>>>(prog, a);
@@ -816,6 +824,22 @@ cudaError_t nf_launch_render_backward(const NfPlan& plan, const NfTrainPlan& tp,
       const int grid = (int)(want < (long long)sms * 16 ? want : (long long)sms * 16);
       k_hash_bwd_tiles<<<grid, 256, 0, hs>>>(plan, rays, tp.n_rays, ts, tp.T, ts_stride, tp.n_tiles, tp.tpr, dx0, hp);
       if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    if (plan.refl_kind == NF_REFL_POSITIONAL) {
+      // the head's own encoder (refl.py:233-237): same sample positions and level resolutions, its own tables (the next `levels` parameters)
+      HashGradPtrs hp2{};
+      bool any2 = false;
+      for (int l = 0; l < plan.hash_levels; ++l) {
+        hp2.t[l] = grads[pi_h++];
+        if (hp2.t[l]) { any2 = true; if ((e = cudaMemsetAsync(hp2.t[l], 0, per, hs)) != cudaSuccess) return e; }
+      }
+      if (any2) {
+        const long long total = tp.n_tiles * NF_TC_ROWS * plan.hash_levels;
+        const long long want = (total + 255) / 256;
+        const int grid = (int)(want < (long long)sms * 16 ? want : (long long)sms * 16);
+        k_hash_bwd_tiles<<<grid, 256, 0, hs>>>(plan, rays, tp.n_rays, ts, tp.T, ts_stride, tp.n_tiles, tp.tpr, dx0 + (size_t)tp.n_tiles * NF_TC_ROWS * 32, hp2);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+      }
     }
     if (hs != st && (e = cudaEventRecord(side->join, hs)) != cudaSuccess) return e;
   }

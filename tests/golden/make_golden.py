@@ -167,29 +167,34 @@ def case_dnerf_spline(name, seed, n, B, H, W, T, top=0, left=0):
   np.savez_compressed(os.path.join(HERE, name + ".npz"), **fx)
   print(name, "out", out.shape, "mean", float(out.mean()), "max|rigid_dp|", float(model.rigid_dp.abs().max()))
 
-def case_plain_grads(name, seed, B, H, W, T, top=0, left=0):
+def case_plain_grads(name, seed, B, H, W, T, top=0, left=0, refl_kind="view"):
   """Gradients of the reference itself: loss = mse(model(rays), target), loss.backward() through the reference's own modules
-  (runner.py:600-602,820).  The parity target of the future fused backward (SURVEY f-1)."""
-  params = O.make_plain_params(seed, 64, 20.0)
+  (runner.py:600-602,820).  The parity target of the fused backward (SURVEY f-1).  refl_kind "pos": the makefile's main training
+  configuration (makefile:12), whose head has its own hash encoder (refl.py:233-237)."""
+  params = O.make_plain_params(seed, 64, 20.0, refl_kind=refl_kind)
   rays = O.make_rays(B, H, W, size=800, seed=seed, crop_top=top, crop_left=left)
-  model, args = ref_plain(params, T, train=False)
+  model, args = ref_plain(params, T, train=False, refl_kind=refl_kind)
   for p in model.parameters(): p.requires_grad_(p.dtype.is_floating_point and p.numel() > 0)
   g = np.random.default_rng(seed)
   target = torch.from_numpy(g.uniform(0, 1, size=(B, H, W, 3)).astype(np.float32))
   out = model(rays)
   loss = torch.nn.functional.mse_loss(out, target)
   loss.backward()
-  fx = dict(kind="plain_grads", seed=seed, B=B, H=H, W=W, T=T, top=top, left=left, near=float(args.near), far=float(args.far),
+  fx = dict(kind="plain_grads", refl_kind=refl_kind, seed=seed, B=B, H=H, W=W, T=T, top=top, left=left, near=float(args.near), far=float(args.far),
             sigmoid=args.sigmoid_kind, bg=args.bg, target=target.numpy(), out=out.detach().numpy(), loss=float(loss))
   sd = dict(model.named_parameters())
-  for n in ("first.init.weight", "first.layers.0.weight", "first.layers.2.bias", "first.out.weight", "first.out.bias",
-            "refl.mlp.init.weight", "refl.mlp.layers.0.weight", "refl.mlp.layers.3.weight", "refl.mlp.out.weight", "refl.mlp.out.bias"):
+  names = ("first.init.weight", "first.layers.0.weight", "first.layers.2.bias", "first.out.weight", "first.out.bias",
+           "refl.mlp.init.weight", "refl.mlp.layers.0.weight", "refl.mlp.layers.3.weight", "refl.mlp.out.weight", "refl.mlp.out.bias")
+  if refl_kind == "pos": names += ("refl.mlp.layers.4.weight", "refl.mlp.init.bias")
+  for n in names:
     gr = sd[n].grad.numpy()
     fx["grad." + n] = gr[::16] if gr.ndim == 2 and gr.shape[0] == 256 else gr       # every 16th row of the 256-row matrices keeps the fixture small
-  for lvl in (0, 7):                                   # hash tables: sparse rows
-    gt = sd[f"first.enc.embs.{lvl}.weight"].grad
-    rows = torch.nonzero(gt.abs().sum(1)).squeeze(1)
-    fx[f"grad.emb{lvl}.rows"] = rows.numpy().astype(np.int32); fx[f"grad.emb{lvl}.vals"] = gt[rows].numpy()
+  tables = [("emb", "first.enc.embs")] + ([("remb", "refl.mlp.enc.embs")] if refl_kind == "pos" else [])
+  for tag, pre in tables:
+    for lvl in (0, 7):                                   # hash tables: sparse rows
+      gt = sd[f"{pre}.{lvl}.weight"].grad
+      rows = torch.nonzero(gt.abs().sum(1)).squeeze(1)
+      fx[f"grad.{tag}{lvl}.rows"] = rows.numpy().astype(np.int32); fx[f"grad.{tag}{lvl}.vals"] = gt[rows].numpy()
   np.savez_compressed(os.path.join(HERE, name + ".npz"), **fx)
   print(name, "loss", float(loss), "rows", len(fx["grad.emb0.rows"]), len(fx["grad.emb7.rows"]))
 
@@ -398,6 +403,9 @@ if __name__ == "__main__":
     sys.exit(0)
   if "--volsdf-grads" in sys.argv:
     case_volsdf_grads("volsdf_siren_t32_grads", seed=33, B=1, H=3, W=4, T=32, top=398, left=397)
+    sys.exit(0)
+  if "--pos-grads" in sys.argv:
+    case_plain_grads("plain_pos_t32_grads", seed=93, B=1, H=3, W=4, T=32, top=398, left=397, refl_kind="pos")
     sys.exit(0)
   if "--grads" in sys.argv:
     case_plain_grads("plain_t16_grads", seed=91, B=1, H=3, W=4, T=16, top=398, left=397)

@@ -217,6 +217,32 @@ def test_oracle_autograd_matches_the_reference_backward(golden_dir):
     assert np.abs(g[rows].numpy() - fx[f"grad.emb{lvl}.vals"]).max() <= 1e-6 * max(np.abs(fx[f"grad.emb{lvl}.vals"]).max(), 1e-3)
 
 
+def test_oracle_positional_autograd_matches_the_reference_backward(golden_dir):
+  """PlainNeRF + the Positional head (refl.py:230-245; the makefile's main training configuration, makefile:12): autograd through the
+  oracle == the reference's own loss.backward(), including the head's second set of hash tables."""
+  fx = load(golden_dir, "plain_pos_t32_grads")
+  P = O.make_plain_params(int(fx["seed"]), 64, 20.0, refl_kind="pos")
+  names = [k[len("grad."):] for k in fx if k.startswith("grad.") and "emb" not in k]
+  tabs = {"emb": "first.enc.embs", "remb": "refl.mlp.enc.embs"}
+  for n in names + [f"{pre}.{l}.weight" for pre in tabs.values() for l in (0, 7)]: P[n] = P[n].clone().requires_grad_(True)
+  rays = O.make_rays(int(fx["B"]), int(fx["H"]), int(fx["W"]), 800, int(fx["seed"]), int(fx["top"]), int(fx["left"]))
+  ts = O.compute_ts(float(fx["near"]), float(fx["far"]), int(fx["T"]))
+  out = O.plain_forward(P, rays, ts, sigmoid=str(fx["sigmoid"]), bg=str(fx["bg"]))["out"]
+  assert np.array_equal(out.detach().numpy(), fx["out"])
+  loss = torch.nn.functional.mse_loss(out, torch.from_numpy(fx["target"]))
+  loss.backward()
+  for n in names:
+    g = P[n].grad.numpy(); ref = fx["grad." + n]
+    if g.ndim == 2 and g.shape[0] == 256: g = g[::16]
+    assert np.abs(g - ref).max() <= 1e-6 * max(np.abs(ref).max(), 1e-3), n
+  for tag, pre in tabs.items():
+    for lvl in (0, 7):
+      g = P[f"{pre}.{lvl}.weight"].grad
+      rows = torch.nonzero(g.abs().sum(1)).squeeze(1).numpy()
+      assert np.array_equal(rows, fx[f"grad.{tag}{lvl}.rows"]), (tag, lvl)
+      assert np.abs(g[rows].numpy() - fx[f"grad.{tag}{lvl}.vals"]).max() <= 1e-6 * max(np.abs(fx[f"grad.{tag}{lvl}.vals"]).max(), 1e-3)
+
+
 def test_oracle_volsdf_autograd_matches_the_reference_backward(golden_dir):
   """VolSDF (SIREN SDF + View, volume branch; nerf.py:981-1013): autograd through the oracle == the reference's own loss.backward(),
   every Linear of both MLPs and the learned `scale` (beta) -- the parity target of the fused VolSDF training step."""
