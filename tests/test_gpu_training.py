@@ -242,7 +242,7 @@ def test_volsdf_training_step_vs_reference_golden():
   assert out.requires_grad
   assert float((out.detach().cpu() - torch.from_numpy(fx["out"])).abs().max()) <= 1e-3
   loss = torch.nn.functional.mse_loss(out, torch.from_numpy(fx["target"]).to(DEV))
-  assert abs(float(loss) - float(fx["loss"])) <= 1e-4
+  assert abs(float(loss.detach()) - float(fx["loss"])) <= 1e-4
   loss.backward()
   named = dict(m.named_parameters())
   for key in [k for k in fx if k.startswith("grad.")]:
@@ -280,12 +280,12 @@ def test_volsdf_training_step_vs_oracle_autograd(T, n_side, beta):
     assert torch.isfinite(gr).all(), name
     err = float((gr - r).abs().max()); ref = float(r.abs().max())
     assert err <= (3 if name == "scale" else 1) * GRAD_TOL * ref + 1e-12, (name, err, ref)
-  lr = 0.05 * float(loss) / sum(float((p.grad ** 2).sum()) for p in m.parameters() if p.grad is not None)
+  lr = 0.05 * float(loss.detach()) / sum(float((p.grad ** 2).sum()) for p in m.parameters() if p.grad is not None)
   with torch.no_grad():
     for p in m.parameters():
       if p.grad is not None: p -= lr * p.grad
     loss2 = torch.nn.functional.mse_loss(m(rays.to(DEV)), target.to(DEV))
-  assert float(loss2) < float(loss)
+  assert float(loss2) < float(loss.detach())
 
 
 # ---------------------------------------------------------------- PlainNeRF + Positional head (makefile:12, the reference's main training target)
@@ -355,11 +355,11 @@ def test_positional_training_step_vs_oracle_autograd():
     assert torch.isfinite(gr).all(), name
     err = float((gr - r).abs().max()); mx = float(r.abs().max())
     assert err <= (2 if ".embs." in name else 1) * GRAD_TOL * mx + 1e-12, (name, err, mx)
-  lr = 0.05 * float(loss) / sum(float((p.grad ** 2).sum()) for p in m.parameters() if p.grad is not None)
+  lr = 0.05 * float(loss.detach()) / sum(float((p.grad ** 2).sum()) for p in m.parameters() if p.grad is not None)
   with torch.no_grad():
     for p in m.parameters():
       if p.grad is not None: p -= lr * p.grad
     loss2 = torch.nn.functional.mse_loss(m(rays.to(DEV)), target.to(DEV))
-  assert float(loss2) < float(loss)
+  assert float(loss2) < float(loss.detach())
   m.steps = 48                                                                  # T % 32 != 0: refused, not a fallback
   with pytest.raises(RuntimeError): m(rays.to(DEV))
