@@ -249,7 +249,7 @@ int nf_mlp_forward(const nf_model_desc* desc, const void* packed, int32_t which,
 /* ---- training: forward with an activation stash, backward of the whole path ------------------------------------------
  * What the reference gets from PyTorch autograd (loss.backward(), runner.py:820) for model(rays): gradients of every
  * parameter of the path given d loss / d rgb.  NF_PREC_FP16_TC only (tcgen05 forward AND backward): PlainNeRF (hash-encoded density
- * MLP) with the View or the Positional head (refl.py:230-245; T % 32 == 0), and VolSDF's volume branch with the SIREN SDF + View (src/nerf.py:981-1013) including the learned beta (`scale`).
+ * MLP) with the View or the Positional head (refl.py:230-245; T % 32 == 0), TinyNeRF (one MLP), and VolSDF's volume branch with the SIREN SDF + View (src/nerf.py:981-1013) including the learned beta (`scale`).
  *   1. nf_train_layout_of()    -> workspace size (total_bytes) and where everything lives in it
  *   2. nf_render_forward_aux() with aux.train_ws: the normal forward, plus the stash (per 128-sample tile and Linear: the
  *      input operand as the MMA consumed it, fp16; cos of the pre-activations for sin MLPs; raw density / colours per sample)

@@ -1302,7 +1302,7 @@ const char* nf_tc3_unsupported(const NfPlan& p) {
 // nullptr if the training forward/backward (activation stash + nf_train.cu) can run this model, else the reason.
 const char* nf_train_unsupported(const NfPlan& p) {
   if (const char* why = nf_tc3_unsupported(p)) return why;
-  if (p.kind != NF_KIND_PLAIN) return "training: PlainNeRF + View only (DynamicNeRF needs the gradient with respect to the sample position)";
+  if (p.kind == NF_KIND_DYN) return "training: DynamicNeRF needs the gradient with respect to the sample position (not built)";
   if (p.mip != NF_MIP_NONE || p.enc == NF_ENC_FOURIER) return "training: wide-x0 models (Mip, Fourier SDF) are not built";
   if (p.refl_kind != NF_REFL_VIEW && p.refl_kind != NF_REFL_POSITIONAL) return "training: View and Positional heads only";
   // the Positional head (refl.py:230-245): on its boundary-warp instantiation (112-column x0 per slot; T % 32 == 0, checked at launch)

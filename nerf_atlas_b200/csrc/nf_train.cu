@@ -152,7 +152,7 @@ struct __align__(16) BwPhase {
   int32_t kind, act, job0, n_jobs;                 // the jobs run AFTER this phase's epilogue
   uint32_t s_off256, s_tile256, s_bytes, has_xa;   // stash tile this phase's act' needs
   uint32_t g_off256, g_tile256, g_cols, k0_pad;    // where the G this phase produces goes (g_cols = its width)
-  int32_t inter, hcols2, pad1_, pad2_;             // hcols2 (PH_MID): x0 columns [inter, inter + hcols2) are the head's own hash features
+  int32_t inter, hcols2, tiny, pad2_;              // hcols2 (PH_MID): x0 columns [inter, inter + hcols2) are the head's own hash features; tiny (PH_DY): one MLP, outputs [sigma, rgb]
 };
 struct __align__(16) BwProg { int32_t n_phases, n_jobs, pad0_, pad1_; BwPhase ph[NF_TRAIN_MAX_LIN + 1]; BwJob job[BW_MAX_JOBS]; };
 
@@ -277,11 +277,12 @@ k_bwd_chain(const __grid_constant__ BwProg prog, const BwArgs a) {
         }
         uint8_t* gG = a.ws + ((size_t)P.g_off256 + (size_t)g * P.g_tile256) * 256;     // the G this phase produces (if any)
         if (P.kind == PH_DY) {
-          // G of the path's last Linear: [d rgb_raw (3) * S, 0 ...], 16 columns
+          // G of the path's last Linear: [d rgb_raw (3) * S, 0 ...], 16 columns (TinyNeRF's single MLP: [d sigma_raw, d rgb_raw] * S)
           if (cq == 0) {
-            float r = 0.f, gg = 0.f, b = 0.f;
+            float r = 0.f, gg = 0.f, b = 0.f, ds = 0.f;
             if (valid) { const float* d = a.d_rgbraw + (ray * a.T + t) * 3; r = __ldg(d) * S; gg = __ldg(d + 1) * S; b = __ldg(d + 2) * S; }
-            const uint32_t o0 = pack_h2(r, gg), o1 = pack_h2(b, 0.f);
+            if (valid && P.tiny) ds = __ldg(a.d_sigma + ray * a.T + t) * S;
+            const uint32_t o0 = P.tiny ? pack_h2(ds, r) : pack_h2(r, gg), o1 = P.tiny ? pack_h2(gg, b) : pack_h2(b, 0.f);
             st_v4(s.H + row * 16, o0, o1, 0, 0); st_v4(s.H + KG_BYTES + row * 16, 0, 0, 0, 0);
             stg_v4(gG + row * 16, o0, o1, 0, 0); stg_v4(gG + KG_BYTES + row * 16, 0, 0, 0, 0);
           }
@@ -411,7 +412,7 @@ bool build_bw_prog(const NfPlan& plan, const NfTrainPlan& tp, BwProg* P) {
     }
     Ph.n_jobs = nj - Ph.job0;
     if (p == 0) {
-      Ph.kind = PH_DY;
+      Ph.kind = PH_DY; Ph.tiny = plan.kind == NF_KIND_TINY ? 1 : 0;
       const NfTrainLin& L = tp.lin[n - 1];
       Ph.g_off256 = (uint32_t)(L.g_off >> 8); Ph.g_tile256 = (uint32_t)(L.g_tile >> 8); Ph.g_cols = (uint32_t)L.n_pad;
       if (L.n_pad != 16) return false;

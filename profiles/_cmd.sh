@@ -1,1 +1,1 @@
-timeout 400 python profiles/train_kinds.py 2>/dev/null | tee gpurun_out/r02d_train_kinds.jsonl
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5

@@ -369,7 +369,8 @@ def test_train_layout_host_logic():
   assert all((lay.lin[i].c_off >= 0) == (lay.lin[i].k_hidden > 0) for i in range(13))
   pos = N.describe_plain(64, "upshifted", "black", refl_kind="pos")              # Positional head: 6 + 7 Linears, warp-aligned rays only
   assert lib.nf_train_layout_of(C.byref(pos), 16, 32, C.byref(lay)) == 0 and lay.n_lin == 13 and lay.lin[6].k0_pad == 112
-  for bad in (N.describe_volsdf("mlp"), N.describe_dyn(), N.describe_plain(64, "upshifted", "black", mip="cylinder"), N.describe_tiny(),
+  assert lib.nf_train_layout_of(C.byref(N.describe_tiny()), 16, 16, C.byref(lay)) == 0 and lay.n_lin == 8      # TinyNeRF: one MLP
+  for bad in (N.describe_volsdf("mlp"), N.describe_dyn(), N.describe_plain(64, "upshifted", "black", mip="cylinder"),
               N.describe_plain(64, "upshifted", "black", refl_kind="pos"), N.describe_plain(64, "upshifted", "random")):
     lay = _lib.TrainLayout()
     assert lib.nf_train_layout_of(C.byref(bad), 16, 16, C.byref(lay)) == -2        # NF_E_UNSUPPORTED
