@@ -273,6 +273,7 @@ typedef struct nf_train_layout {
   int64_t scale_off;                   /* float[4]: loss scale S, 1/S, max|g| (bits), - */
   int64_t dw_begin, dw_end;
   int64_t total_bytes;                 /* = the workspace size */
+  int64_t bgrand_off;                  /* NF_BG_RANDOM: fp32 [R], the forward's background draws (nf_render_aux.bg_rand) kept for the backward; else -1 */
   nf_train_lin lin[NF_TRAIN_LIN_MAX];
 } nf_train_layout;
 int nf_train_layout_of(const nf_model_desc* desc, int64_t n_rays, int32_t T, nf_train_layout* out);

@@ -45,7 +45,7 @@ class TrainLin(C.Structure):
 class TrainLayout(C.Structure):
   _fields_ = [(n, C.c_int32) for n in ("n_lin", "T", "rpu", "tpr")] + \
              [(n, C.c_int64) for n in ("n_rays", "n_tiles", "sigma_off", "rgbraw_off", "dsigma_off", "drgbraw_off", "dx0_off",
-                                       "scale_off", "dw_begin", "dw_end", "total_bytes")] + [("lin", TrainLin * TRAIN_LIN_MAX)]
+                                       "scale_off", "dw_begin", "dw_end", "total_bytes", "bgrand_off")] + [("lin", TrainLin * TRAIN_LIN_MAX)]
 
 class RenderAux(C.Structure):
   _fields_ = [("struct_bytes", C.c_int32), ("reserved", C.c_int32), ("train_ws", C.c_void_p), ("train_ws_bytes", C.c_int64),

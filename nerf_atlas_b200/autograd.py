@@ -55,12 +55,12 @@ class _HashEncode(torch.autograd.Function):
 class _FusedRender(torch.autograd.Function):
   """rays[R,6], ts -> rgb[R,3] (+ alpha, weights [R,T], not differentiable) with gradients to the packed parameters."""
   @staticmethod
-  def forward(ctx, engine: RenderEngine, rays, ts, noise, want_weights, *params):
+  def forward(ctx, engine: RenderEngine, rays, ts, noise, want_weights, bg_rand, *params):
     engine.pack(params)
     R = rays.shape[0]; T = ts.shape[-1]
     lay = engine.train_layout(R, T)
     ws = RenderEngine.train_workspace(lay, rays.device)
-    rgb, alpha, weights = engine.render(rays, ts, noise, want_weights=want_weights, train_ws=ws)
+    rgb, alpha, weights = engine.render(rays, ts, noise, want_weights=want_weights, train_ws=ws, bg_rand=bg_rand)
     ctx.engine, ctx.ws, ctx.params = engine, ws, params
     ctx.pack_key = engine._key
     ctx.save_for_backward(rays, ts)
@@ -74,17 +74,19 @@ class _FusedRender(torch.autograd.Function):
     if ctx.ws is None: raise RuntimeError("fused_render: backward called twice (the activation stash is freed after the first)")
     if ctx.engine._key != ctx.pack_key:
       raise RuntimeError("fused_render: the parameters were modified or re-packed between forward and backward")
-    grads = [torch.empty_like(p) if need else None for p, need in zip(ctx.params, ctx.needs_input_grad[5:])]
+    grads = [torch.empty_like(p) if need else None for p, need in zip(ctx.params, ctx.needs_input_grad[6:])]
     ctx.engine.render_backward(ctx.ws, rays, ts, d_rgb.contiguous().to(torch.float32), grads)
     ctx.ws = None                                           # several GB: free it as soon as it has been consumed
-    return (None, None, None, None, None) + tuple(grads)
+    return (None, None, None, None, None, None) + tuple(grads)
 
 
-def fused_render(engine: RenderEngine, rays: torch.Tensor, ts: torch.Tensor, params, density_noise=None, want_weights: bool = True):
+def fused_render(engine: RenderEngine, rays: torch.Tensor, ts: torch.Tensor, params, density_noise=None, want_weights: bool = True,
+                 bg_rand: torch.Tensor = None):
   """The whole render path as one differentiable op: gradients flow to ``params`` (the live parameter tensors in
-  `nf_pack_weights` order).  Not differentiable with respect to rays / ts / noise (camera training is out of scope)."""
+  `nf_pack_weights` order).  Not differentiable with respect to rays / ts / noise (camera training is out of scope).
+  ``bg_rand[R]``: the draws of the "random" background (nerf.py:100-103), kept in the workspace for the backward's sky term."""
   if rays.requires_grad or ts.requires_grad: raise NotImplementedError("fused_render: gradients with respect to rays / ts are not built")
-  rgb, alpha, weights = _FusedRender.apply(engine, rays, ts, density_noise, want_weights, *params)
+  rgb, alpha, weights = _FusedRender.apply(engine, rays, ts, density_noise, want_weights, bg_rand, *params)
   return (rgb, alpha, weights) if want_weights else (rgb, None, None)
 
 

@@ -173,7 +173,7 @@ int nf_render_forward_aux(const nf_model_desc* desc, const void* packed, const f
   const bool side = aux && (aux->pts_out || aux->dp_out || aux->rigid_dp_out || aux->rigidity_out);
   if (side && p.kind != NF_KIND_DYN && (aux->dp_out || aux->rigid_dp_out || aux->rigidity_out)) return fail(NF_E_BADARG, "dp / rigid_dp / rigidity outputs exist for NF_KIND_DYN only");
   if (aux && aux->pts && p.kind == NF_KIND_DYN) return fail(NF_E_UNSUPPORTED, "from_pts (explicit sample positions) is not built for NF_KIND_DYN");
-  if (train && (aux->pts || p.bg == NF_BG_RANDOM)) return fail(NF_E_UNSUPPORTED, "training forward: explicit pts / random background are not built");
+  if (train && aux->pts) return fail(NF_E_UNSUPPORTED, "training forward: explicit pts are not built");
   if (int rc = check_ts(T, ts_ray_stride)) return rc;
   if (p.kind == NF_KIND_DYN && !ray_time) return fail(NF_E_BADARG, "nf_render_forward: ray_time is required for NF_KIND_DYN");
   if (p.mip != NF_MIP_NONE) {
@@ -205,7 +205,9 @@ int nf_render_forward_aux(const nf_model_desc* desc, const void* packed, const f
     if (train && pipe != 3) return fail(NF_E_UNSUPPORTED, "training forward: the staggered pipeline only");
     const bool want_aux = aux && (aux->pts || aux->bg_rand || side);
     if (want_aux && pipe != 3) return fail(NF_E_UNSUPPORTED, "explicit pts / random background / side channels: staggered tensor pipeline or NF_PREC_FP32 only");
-    if (want_aux && (p.mip != NF_MIP_NONE || p.refl_kind != NF_REFL_VIEW || p.enc == NF_ENC_FOURIER) && (aux->pts || p.bg == NF_BG_RANDOM))
+    // (the training instantiation of the Positional head's kernel reads the background draws itself)
+    const bool pos_train = train && p.refl_kind == NF_REFL_POSITIONAL && p.mip == NF_MIP_NONE && !aux->pts;
+    if (want_aux && !pos_train && (p.mip != NF_MIP_NONE || p.refl_kind != NF_REFL_VIEW || p.enc == NF_ENC_FOURIER) && (aux->pts || p.bg == NF_BG_RANDOM))
       return fail(NF_E_UNSUPPORTED, "explicit pts / random background with a wide-x0 model (Mip, Positional, Fourier SDF): NF_PREC_FP32 only");
     if (aux && aux->pts_out && p.kind != NF_KIND_DYN) return fail(NF_E_UNSUPPORTED, "pts_out on the tensor pipeline: NF_KIND_DYN only (use nf_sample_points)");
     e = pipe == 3 ? nf_launch_render_tc3(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, ray_time, mip, rgb_out, alpha_out, weights_out, st, train, train ? aux->train_ws : nullptr, aux)

@@ -66,7 +66,8 @@ __device__ __forceinline__ void feat_act3_bwd(float r, float g, float b, int kin
 __global__ void k_composite_bwd(int density_act, const float* __restrict__ beta_ptr, int bg, const float* __restrict__ sigma_raw,
                                 const float* __restrict__ feats, const float* __restrict__ rays, long long n_rays,
                                 const float* __restrict__ ts, int T, long long ts_stride, const float* __restrict__ d_rgb,
-                                float* __restrict__ d_sigma, float* __restrict__ d_feats, int feat_act, float* __restrict__ d_beta) {
+                                float* __restrict__ d_sigma, float* __restrict__ d_feats, int feat_act, float* __restrict__ d_beta,
+                                const float* __restrict__ bg_rand) {
   // feat_act >= 0: `feats` are the RAW colours (the training stash); the activation is applied here and d_feats is the
   // gradient with respect to the raw values.  feat_act < 0: `feats` are already activated (the stand-alone stage).
   __shared__ float s_carry[8][BWD_MAX_CHUNKS];
@@ -83,7 +84,8 @@ __global__ void k_composite_bwd(int density_act, const float* __restrict__ beta_
     const float nrm = sqrtf(dx * dx + dy * dy + dz * dz);
     const float* tsr = ts + ray * ts_stride;
     const float gr = __ldg(d_rgb + ray * 3), gg = __ldg(d_rgb + ray * 3 + 1), gb = __ldg(d_rgb + ray * 3 + 2);
-    const float gsky = bg == NF_BG_WHITE ? gr + gg + gb : 0.f;
+    // sky = c (1 - sum_{t<T-1} w_t) added to every channel: c = 1 (white) or the ray's draw (random_color, nerf.py:100-103)
+    const float gsky = bg == NF_BG_WHITE ? gr + gg + gb : (bg == NF_BG_RANDOM && bg_rand) ? __ldg(bg_rand + ray) * (gr + gg + gb) : 0.f;
     // pass 1
     float carry = 1.f;
     for (int c = 0; c < nchunk; ++c) {
@@ -239,14 +241,14 @@ int bwd_num_sms() {
 
 cudaError_t nf_launch_composite_bwd(const NfPlan& plan, const void* packed, const float* sigma_raw, const float* feats, const float* rays,
                                     int64_t n_rays, const float* ts, int T, int64_t ts_stride, const float* d_rgb, float* d_sigma,
-                                    float* d_feats, cudaStream_t st, int feat_act, float* d_beta) {
+                                    float* d_feats, cudaStream_t st, int feat_act, float* d_beta, const float* bg_rand) {
   if (n_rays == 0) return cudaSuccess;
   if (plan.density_act != NF_DENS_LAPLACE) d_beta = nullptr;
   if (T > 32 * BWD_MAX_CHUNKS) return cudaErrorInvalidValue;
   const long long want = (n_rays * 32 + 255) / 256;
   const int grid = (int)(want < (long long)bwd_num_sms() * 8 ? want : (long long)bwd_num_sms() * 8);
   const float* beta = (plan.density_act == NF_DENS_LAPLACE && packed) ? reinterpret_cast<const float*>((const uint8_t*)packed + plan.scale_off) : nullptr;
-  k_composite_bwd<<<grid, 256, 0, st>>>(plan.density_act, beta, plan.bg, sigma_raw, feats, rays, n_rays, ts, T, ts_stride, d_rgb, d_sigma, d_feats, feat_act, d_beta);
+  k_composite_bwd<<<grid, 256, 0, st>>>(plan.density_act, beta, plan.bg, sigma_raw, feats, rays, n_rays, ts, T, ts_stride, d_rgb, d_sigma, d_feats, feat_act, d_beta, bg_rand);
   return cudaGetLastError();
 }
 

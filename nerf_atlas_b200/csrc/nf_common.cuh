@@ -529,6 +529,7 @@ static inline int nf_build_train_plan(const NfPlan& p, int64_t n_rays, int T, Nf
   tp->dsigma_off = take(n_rays * T * 4); tp->drgbraw_off = take(n_rays * T * 12);
   // fp32 gradient of the density MLP's hash features [n_tiles * 128][32]; Positional head: followed by the head's own encoder's
   tp->dx0_off = take(tp->n_tiles * NF_TC_ROWS * 32 * 4 * (p.refl_kind == NF_REFL_POSITIONAL ? 2 : 1));
+  tp->bgrand_off = p.bg == NF_BG_RANDOM ? take(n_rays * 4) : -1;
   int nl = 0;
   for (int mi = 0; mi < p.n_mlps; ++mi) {
     const int m = p.kind == NF_KIND_DYN ? (mi + 2) % 3 : mi;          // execution order (as build_prog3)

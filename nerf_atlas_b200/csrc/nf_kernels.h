@@ -52,7 +52,8 @@ cudaError_t nf_launch_integrate(const float* weights, const float* vals, int64_t
 // backward of the non-GEMM stages (nf_bwd.cu)
 cudaError_t nf_launch_composite_bwd(const NfPlan& plan, const void* packed, const float* sigma_raw, const float* feats, const float* rays,
                                     int64_t n_rays, const float* ts, int T, int64_t ts_stride, const float* d_rgb, float* d_sigma,
-                                    float* d_feats, cudaStream_t st, int feat_act = -1, float* d_beta = nullptr);   // d_beta (NF_DENS_LAPLACE, nullable): ACCUMULATED into
+                                    float* d_feats, cudaStream_t st, int feat_act = -1, float* d_beta = nullptr,    // d_beta (NF_DENS_LAPLACE, nullable): ACCUMULATED into
+                                    const float* bg_rand = nullptr);                                          // NF_BG_RANDOM: the forward's draws [R]
 cudaError_t nf_launch_hash_encode_bwd(const NfPlan& plan, const float* pts, int64_t n, const float* d_feats, float* d_tables, cudaStream_t st);
 cudaError_t nf_launch_adam_multi(int n_tensors, float* const* p, const float* const* g, float* const* m, float* const* v, const int64_t* numel,
                                  float lr, float beta1, float beta2, float eps, float wd, int step, cudaStream_t st);

@@ -1309,7 +1309,6 @@ const char* nf_train_unsupported(const NfPlan& p) {
   if (p.refl_kind == NF_REFL_POSITIONAL && (p.enc != NF_ENC_HASH || p.hash_levels * 4 != 32 || p.mlp[0].k0_pad > p.intermediate || p.mlp[1].k0_pad > X0K_POS))
     return "training: Positional head needs the hash-encoded density MLP (8 levels x 4) and an x0 of at most 112 columns";
   // (VolSDF's SIREN SDF, x0 = [p], trains here: weights and beta; its eikonal regulariser (runner.py:736) needs d sdf / d p: nf_sdf_normals)
-  if (p.bg == NF_BG_RANDOM) return "training: the random background is not built";
   for (int m = 0; m < p.n_mlps; ++m) if (p.mlp[m].act != NF_ACT_LEAKY && p.mlp[m].act != NF_ACT_SIN) return "training: LeakyReLU / sin MLPs only";
   return nullptr;
 }
@@ -1326,7 +1325,7 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
     a.pts = aux->pts; a.bg_rand = aux->bg_rand;
     a.pts_out = aux->pts_out; a.dp_out = aux->dp_out; a.rigid_dp_out = aux->rigid_dp_out; a.rigidity_out = aux->rigidity_out;
   }
-  const bool want_aux = a.pts != nullptr || plan.bg == NF_BG_RANDOM;
+  const bool want_aux = a.pts != nullptr || (plan.bg == NF_BG_RANDOM && !tp);      // (the training kernels read bg_rand themselves)
   if (plan.bg == NF_BG_RANDOM && !a.bg_rand) return cudaErrorInvalidValue;
   a.packed = (const uint8_t*)packed; a.rays = rays; a.n_rays = n_rays; a.ts = ts; a.T = T; a.ts_stride = ts_stride;
   a.noise = noise; a.ray_time = ray_time; a.rgb_out = rgb; a.alpha_out = alpha; a.weights_out = weights;
@@ -1346,7 +1345,7 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
 #endif
   // the Positional head with warp-aligned rays: per-slot 112-column x0, boundary warps (k_render_tc3<2, 4, 4, 1, ..., BW, 112>)
   const bool pos_bw = NF_BW && NF_POS_BW && plan.refl_kind == NF_REFL_POSITIONAL && plan.mip == NF_MIP_NONE && plan.kind == NF_KIND_PLAIN && (T & 31) == 0 &&
-                      plan.mlp[0].k0_pad <= plan.intermediate && plan.mlp[1].k0_pad <= X0K_POS && !(aux && (aux->pts || plan.bg == NF_BG_RANDOM));
+                      plan.mlp[0].k0_pad <= plan.intermediate && plan.mlp[1].k0_pad <= X0K_POS && !(aux && (aux->pts || (plan.bg == NF_BG_RANDOM && !tp)));
   Tc3Prog prog;
   if (!build_prog3(plan, &prog, pos_bw ? X0K_POS : X0K)) return cudaErrorNotSupported;
   const bool wide = prog.single != 0 || plan.mip != NF_MIP_NONE || plan.refl_kind != NF_REFL_VIEW;
@@ -1439,6 +1438,8 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
 #endif
   else go(k_render_tc3<3, 4, 4, 0, false>);
   if (scratch) { const cudaError_t ef = cudaFreeAsync(scratch, st); if (e == cudaSuccess) e = ef; }
+  if (e == cudaSuccess && train && plan.bg == NF_BG_RANDOM)       // the backward's sky term needs the same draws
+    e = cudaMemcpyAsync((uint8_t*)ws + tp->bgrand_off, a.bg_rand, (size_t)n_rays * sizeof(float), cudaMemcpyDeviceToDevice, st);
   if (e != cudaSuccess) return e;
 #ifdef NF_TC_STATS
   if (getenv("NF_TC_STATS_PRINT")) {

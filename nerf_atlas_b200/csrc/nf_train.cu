@@ -782,7 +782,8 @@ cudaError_t nf_launch_render_backward(const NfPlan& plan, const NfTrainPlan& tp,
     d_beta = grads[pi_b];
     if (d_beta && (e = cudaMemsetAsync(d_beta, 0, sizeof(float), st)) != cudaSuccess) return e;
   }
-  if ((e = nf_launch_composite_bwd(plan, packed, sigma, rgbraw, rays, tp.n_rays, ts, tp.T, ts_stride, d_rgb, dsigma, drgbraw, st, plan.feat_act, d_beta)) != cudaSuccess) return e;
+  if ((e = nf_launch_composite_bwd(plan, packed, sigma, rgbraw, rays, tp.n_rays, ts, tp.T, ts_stride, d_rgb, dsigma, drgbraw, st, plan.feat_act, d_beta,
+                                   plan.bg == NF_BG_RANDOM ? (const float*)(ws + tp.bgrand_off) : nullptr)) != cudaSuccess) return e;
   // 2. loss scale
   const long long ns = tp.n_rays * tp.T;
   const int sms = tr_num_sms();

@@ -684,9 +684,8 @@ class FusedNeRF(nn.Module):
     if self._wants_grad(params):
       if rays.requires_grad: raise NotImplementedError("gradients with respect to the rays (--train-parts camera) are not built")
       if radius is not None: raise NotImplementedError("training a Mip model through the fused path is not built")
-      if bg_rand is not None: raise NotImplementedError("training with the random background through the fused path is not built")
       from .autograd import fused_render
-      rgb, alpha, weights = fused_render(eng, flat.detach(), ts, params, noise, want_weights=self.keep_weights)
+      rgb, alpha, weights = fused_render(eng, flat.detach(), ts, params, noise, want_weights=self.keep_weights, bg_rand=bg_rand)
     else:
       eng.pack(params)
       rgb, alpha, weights = eng.render(flat, ts, noise, want_weights=self.keep_weights, radius=radius, bg_rand=bg_rand)

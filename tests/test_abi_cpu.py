@@ -370,8 +370,10 @@ def test_train_layout_host_logic():
   pos = N.describe_plain(64, "upshifted", "black", refl_kind="pos")              # Positional head: 6 + 7 Linears, warp-aligned rays only
   assert lib.nf_train_layout_of(C.byref(pos), 16, 32, C.byref(lay)) == 0 and lay.n_lin == 13 and lay.lin[6].k0_pad == 112
   assert lib.nf_train_layout_of(C.byref(N.describe_tiny()), 16, 16, C.byref(lay)) == 0 and lay.n_lin == 8      # TinyNeRF: one MLP
+  assert lib.nf_train_layout_of(C.byref(N.describe_plain(64, "upshifted", "random")), 16, 16, C.byref(lay)) == 0 and lay.bgrand_off > 0      # draws kept for the backward
+  assert lib.nf_train_layout_of(C.byref(N.describe_plain(64, "upshifted", "black")), 16, 16, C.byref(lay)) == 0 and lay.bgrand_off == -1
   for bad in (N.describe_volsdf("mlp"), N.describe_dyn(), N.describe_plain(64, "upshifted", "black", mip="cylinder"),
-              N.describe_plain(64, "upshifted", "black", refl_kind="pos"), N.describe_plain(64, "upshifted", "random")):
+              N.describe_plain(64, "upshifted", "black", refl_kind="pos")):
     lay = _lib.TrainLayout()
     assert lib.nf_train_layout_of(C.byref(bad), 16, 16, C.byref(lay)) == -2        # NF_E_UNSUPPORTED
     assert b"training" in lib.nf_last_error()

@@ -398,3 +398,36 @@ def test_tiny_training_step_vs_oracle_autograd():
       if p.grad is not None: p -= lr * p.grad
     loss2 = torch.nn.functional.mse_loss(m(rays.to(DEV)), target.to(DEV))
   assert float(loss2) < float(loss.detach())
+
+
+# ---------------------------------------------------------------- random background (nerf.py:100-103) in training
+@pytest.mark.parametrize("refl_kind", ["view", "pos"])
+def test_random_background_training_step_vs_oracle_autograd(refl_kind):
+  """`--bg random`: out = sum_t w_t f_t + u (1 - sum_{t<T-1} w_t) with one uniform draw u per ray (random_color).  The module
+  draws u itself; the draws are fixed here by seeding torch's CUDA generator and re-drawing the same stream for the oracle.  The
+  backward's sky term reads the draws the forward left in the training workspace (nf_train_layout.bgrand_off)."""
+  import nerf_atlas_b200 as N
+  T, n = 64, 16
+  P = O.make_plain_params(55, 64, 20.0, refl_kind=refl_kind)
+  m = N.FusedPlainNeRF(steps=T, t_near=2, t_far=6, intermediate_size=64, sigmoid_kind="upshifted", bg="random", precision="fp16", refl_kind=refl_kind)
+  m.load_state_dict(P, strict=True); m = m.to(DEV).eval(); m.differentiable = True
+  rays = O.make_rays(1, n, n, seed=8, crop_top=394, crop_left=394)
+  g = torch.Generator().manual_seed(12)
+  target = torch.rand(1, n, n, 3, generator=g)
+  torch.manual_seed(1234)
+  out = m(rays.to(DEV))
+  torch.manual_seed(1234)
+  u = torch.rand(n * n, device=DEV).cpu().reshape(1, n, n)                    # the same draw as FusedNeRF.forward's
+  names = [k for k, v in P.items() if v.dtype.is_floating_point and v.numel() > 0]
+  Pg = {k: (v.clone().requires_grad_(True) if k in names else v) for k, v in P.items()}
+  res = O.plain_forward(Pg, rays, m.ts.cpu(), sigmoid="upshifted", bg="black")
+  ref = res["out"] + (u * (1 - res["weights"][:-1].sum(0)))[..., None]
+  torch.nn.functional.mse_loss(ref, target).backward()
+  assert float((out.detach().cpu() - ref.detach()).abs().max()) <= 1e-3
+  torch.nn.functional.mse_loss(out, target.to(DEV)).backward()
+  named = dict(m.named_parameters())
+  for name in names:
+    r = Pg[name].grad; gr = named[name].grad.cpu()
+    assert torch.isfinite(gr).all(), name
+    err = float((gr - r).abs().max()); mx = float(r.abs().max())
+    assert err <= (2 if ".embs." in name else 1) * GRAD_TOL * mx + 1e-12, (name, err, mx)
