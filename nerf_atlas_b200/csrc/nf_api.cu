@@ -205,10 +205,8 @@ int nf_render_forward_aux(const nf_model_desc* desc, const void* packed, const f
     if (train && pipe != 3) return fail(NF_E_UNSUPPORTED, "training forward: the staggered pipeline only");
     const bool want_aux = aux && (aux->pts || aux->bg_rand || side);
     if (want_aux && pipe != 3) return fail(NF_E_UNSUPPORTED, "explicit pts / random background / side channels: staggered tensor pipeline or NF_PREC_FP32 only");
-    // (the training instantiation of the Positional head's kernel reads the background draws itself)
-    const bool pos_train = train && p.refl_kind == NF_REFL_POSITIONAL && p.mip == NF_MIP_NONE && !aux->pts;
-    if (want_aux && !pos_train && (p.mip != NF_MIP_NONE || p.refl_kind != NF_REFL_VIEW || p.enc == NF_ENC_FOURIER) && (aux->pts || p.bg == NF_BG_RANDOM))
-      return fail(NF_E_UNSUPPORTED, "explicit pts / random background with a wide-x0 model (Mip, Positional, Fourier SDF): NF_PREC_FP32 only");
+    if (want_aux && (p.mip != NF_MIP_NONE || p.refl_kind != NF_REFL_VIEW || p.enc == NF_ENC_FOURIER) && aux->pts)
+      return fail(NF_E_UNSUPPORTED, "explicit pts with a wide-x0 model (Mip, Positional, Fourier SDF): NF_PREC_FP32 only");
     if (aux && aux->pts_out && p.kind != NF_KIND_DYN) return fail(NF_E_UNSUPPORTED, "pts_out on the tensor pipeline: NF_KIND_DYN only (use nf_sample_points)");
     e = pipe == 3 ? nf_launch_render_tc3(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, ray_time, mip, rgb_out, alpha_out, weights_out, st, train, train ? aux->train_ws : nullptr, aux)
                   : nf_launch_render_tc(p, packed, rays, n_rays, ts, T, ts_ray_stride, density_noise, rgb_out, alpha_out, weights_out, st);

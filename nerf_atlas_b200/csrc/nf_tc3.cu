@@ -1325,7 +1325,7 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
     a.pts = aux->pts; a.bg_rand = aux->bg_rand;
     a.pts_out = aux->pts_out; a.dp_out = aux->dp_out; a.rigid_dp_out = aux->rigid_dp_out; a.rigidity_out = aux->rigidity_out;
   }
-  const bool want_aux = a.pts != nullptr || (plan.bg == NF_BG_RANDOM && !tp);      // (the training kernels read bg_rand themselves)
+  const bool want_aux = a.pts != nullptr;      // explicit positions need the AUX instantiation; every instantiation reads bg_rand (composite_tile3)
   if (plan.bg == NF_BG_RANDOM && !a.bg_rand) return cudaErrorInvalidValue;
   a.packed = (const uint8_t*)packed; a.rays = rays; a.n_rays = n_rays; a.ts = ts; a.T = T; a.ts_stride = ts_stride;
   a.noise = noise; a.ray_time = ray_time; a.rgb_out = rgb; a.alpha_out = alpha; a.weights_out = weights;
@@ -1345,7 +1345,7 @@ cudaError_t nf_launch_render_tc3(const NfPlan& plan, const void* packed, const f
 #endif
   // the Positional head with warp-aligned rays: per-slot 112-column x0, boundary warps (k_render_tc3<2, 4, 4, 1, ..., BW, 112>)
   const bool pos_bw = NF_BW && NF_POS_BW && plan.refl_kind == NF_REFL_POSITIONAL && plan.mip == NF_MIP_NONE && plan.kind == NF_KIND_PLAIN && (T & 31) == 0 &&
-                      plan.mlp[0].k0_pad <= plan.intermediate && plan.mlp[1].k0_pad <= X0K_POS && !(aux && (aux->pts || (plan.bg == NF_BG_RANDOM && !tp)));
+                      plan.mlp[0].k0_pad <= plan.intermediate && plan.mlp[1].k0_pad <= X0K_POS && !(aux && aux->pts);
   Tc3Prog prog;
   if (!build_prog3(plan, &prog, pos_bw ? X0K_POS : X0K)) return cudaErrorNotSupported;
   const bool wide = prog.single != 0 || plan.mip != NF_MIP_NONE || plan.refl_kind != NF_REFL_VIEW;

@@ -1092,3 +1092,23 @@ def test_volumetric_integrate_depth_flow_rigidity_maps():
     assert got.shape == want.shape == tuple(w.shape[1:]) + (3,)
     assert float((got.cpu() - want).abs().max()) <= 1e-6 * max(float(want.abs().max()), 1e-3), name
   with pytest.raises(RuntimeError): N.volumetric_integrate(w.cpu(), d.rigid_dp.cpu())
+
+
+@pytest.mark.parametrize("T", [64, 48])
+def test_random_background_positional_head_tensor_pipeline(T):
+  """The random background on the wide-x0 kernels of the tensor pipeline (every instantiation's composite reads the draws): the
+  Positional head through the module, T = 64 (its boundary-warp kernel) and T = 48 (rays not warp-aligned: the shared-x0 kernel),
+  against the oracle's black-background render + u (1 - sum_{t<T-1} w_t) with the module's own draws re-drawn from the same seed."""
+  import nerf_atlas_b200 as N
+  Pp = O.make_plain_params(81, 64, 20.0, refl_kind="pos")
+  m = N.FusedPlainNeRF(steps=T, t_near=2, t_far=6, intermediate_size=64, sigmoid_kind="upshifted", bg="random", precision="fp16", refl_kind="pos")
+  m.load_state_dict(Pp, strict=True); m = m.to(DEV).eval()
+  rays = O.make_rays(1, 9, 11, seed=14, crop_top=394, crop_left=390)
+  torch.manual_seed(77)
+  with torch.no_grad(): out = m(rays.to(DEV))
+  torch.manual_seed(77)
+  u = torch.rand(99, device=DEV).cpu().reshape(1, 9, 11)
+  with torch.no_grad(): ref = O.plain_forward(Pp, rays, m.ts.cpu(), bg="black")
+  want = ref["out"] + (u * (1 - ref["weights"][:-1].sum(0)))[..., None]
+  assert float((out.cpu() - want).abs().max()) <= 1e-3
+  assert float((u * (1 - ref["weights"][:-1].sum(0))).abs().max()) > 1e-2          # the sky term is visible in this case
