@@ -1,1 +1,2 @@
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r02d_bench_2gpu.json 2> gpurun_out/r02d_bench_2gpu.err; tail -c 400 gpurun_out/r02d_bench_2gpu.err; head -c 1500 gpurun_out/r02d_bench_2gpu.json
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02d_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-torch-eager-gpu > gpurun_out/r02d_launches_bench.log 2>&1
+tail -c 300 gpurun_out/r02d_launches_bench.log; wc -l gpurun_out/r02d_launches.csv
