@@ -115,15 +115,15 @@ def torch_eager_gpu_rays_per_s(dev, tile=200, reps=3):
   return tile * tile / (ms * 1e-3), how
 
 
-def train_leg(O, dev, world, rank, steps, warmup, barrier):
+def train_leg(O, dev, world, rank, steps, warmup, barrier, refl_kind="view"):
   """One optimiser step of the reference's training loop (runner.py:600-602,820-824) per step, natively: training forward
   (jittered ts, density noise, activation stash) -> MSE -> fused backward (tcgen05 dX + dW) -> ONE NCCL all-reduce of the flat
   gradient (N > 1) -> FusedAdam.  TRAIN_RAYS rays x T samples per GPU per step (weak scaling: the global batch grows with N)."""
   import torch
   import torch.distributed as dist
   import nerf_atlas_b200 as N
-  model = N.FusedPlainNeRF(steps=T, t_near=2, t_far=6, intermediate_size=64, sigmoid_kind="upshifted", precision="fp16")
-  model.load_state_dict(O.make_plain_params(1337, 64, 1.0), strict=True)          # its own copy: the render legs keep the seeded weights
+  model = N.FusedPlainNeRF(steps=T, t_near=2, t_far=6, intermediate_size=64, sigmoid_kind="upshifted", precision="fp16", refl_kind=refl_kind)
+  model.load_state_dict(O.make_plain_params(1337, 64, 1.0, refl_kind=refl_kind), strict=True)          # its own copy: the render legs keep the seeded weights
   model = model.to(dev).train()
   opt = N.autograd.FusedAdam(model.parameters(), lr=5e-4, eps=1e-7)
   red = N.GradientAllReducer(model.parameters())
@@ -155,12 +155,14 @@ def train_leg(O, dev, world, rank, steps, warmup, barrier):
     t = torch.tensor([ms, ar], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms, ar = float(t[0]), float(t[1])
   barrier()
   per = ms / steps
+  if refl_kind != "view":     # the short form: the Positional head of the reference's main training target (makefile:12, --refl-kind pos)
+    return {"it_per_sec": 1e3 / per, "ms_per_step": per, "rays_per_step_per_gpu": TRAIN_RAYS, "samples_per_ray": T, "final_loss_per_ray": float(loss.detach()) / TRAIN_RAYS}
   flops = 3 * FLOP_PER_SAMPLE * TRAIN_RAYS * T                          # forward + dX + dW GEMMs
   n_par = sum(p.numel() for p in model.parameters() if p.requires_grad)
   return {"it_per_sec": 1e3 / per, "ms_per_step": per, "rays_per_sec": world * TRAIN_RAYS * 1e3 / per, "rays_per_step_per_gpu": TRAIN_RAYS,
           "samples_per_ray": T, "steps": steps, "achieved_tflops_per_gpu": flops / (per * 1e-3) / 1e12,
           "allreduce_ms_per_step": ar if world > 1 else 0.0, "allreduce_bytes": 4 * n_par if world > 1 else 0,
-          "final_loss_per_ray": float(loss) / TRAIN_RAYS,
+          "final_loss_per_ray": float(loss.detach()) / TRAIN_RAYS,
           "what": "native training step: k_render_tc3<TRAIN> + nf_render_backward (k_composite_bwd, k_bwd_chain, k_bwd_dw, k_unpack_grads, "
                   "k_hash_bwd_tiles) + " + ("ncclAllReduce(flat fp32 gradient) + " if world > 1 else "") + "nf_adam_step_multi"}
 
@@ -337,6 +339,9 @@ def run_ours(args):
   if not args.no_train:
     try: train = train_leg(O, dev, world, rank, steps=max(5, args.steps), warmup=3, barrier=barrier)
     except Exception as ex: train = {"error": str(ex)[:300]}
+    if world == 1 and "error" not in train:
+      try: train["positional_head"] = train_leg(O, dev, world, rank, steps=max(5, args.steps), warmup=3, barrier=barrier, refl_kind="pos")
+      except Exception as ex: train["positional_head"] = {"error": str(ex)[:300]}
   if world > 1:
     try: strong = strong_leg(eng, O, dev, world, rank, ts, steps=max(5, args.steps), warmup=3, barrier=barrier)
     except Exception as ex: strong = {"error": str(ex)[:300]}
