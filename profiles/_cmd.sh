@@ -1,5 +1,2 @@
-timeout 900 python bench.py --no-cpu-baseline --no-torch-eager-gpu --steps 5 > gpurun_out/r02d_bench_quick.json 2> gpurun_out/err.txt; tail -c 300 gpurun_out/err.txt
-python -c "
-import json
-d=[json.loads(l) for l in open('gpurun_out/r02d_bench_quick.json') if l.startswith('{')][-1]
-print(d['value'], d['ms_per_step'], d['train'])"
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+timeout 900 python bench.py > gpurun_out/r02d_bench.json 2> gpurun_out/r02d_bench.err; tail -c 200 gpurun_out/r02d_bench.err
